@@ -1,0 +1,235 @@
+/* slam_b200.h -- C ABI of the B200-native GraphSLAM back end.
+ *
+ * Drop-in boundary for the hot path of cfsd/opendlv-logic-cfsd18-sensation-slam: the private
+ * back-half methods of class Slam (src/slam.hpp:66-91) and its `g2o::SparseOptimizer m_optimizer`
+ * member (src/slam.hpp:98).  Every entry point below names the reference interface it replaces.
+ * Plain C types only; the handle is opaque; callers own every pointer they pass; nothing is
+ * allocated across the ABI; nothing throws.  All floating point is fp64, all indices int32.
+ *
+ * Return value: >= 0 success (meaning per function), < 0 one of the SLAM_B200_E_* codes;
+ * slam_b200_last_error() gives a human-readable reason.  There is no CPU fallback: without a
+ * CUDA device every compute entry point returns SLAM_B200_E_CUDA.
+ *
+ * Threading: a context may be used from any host thread, one call at a time (the reference
+ * serialises the same calls with m_mapMutex / m_optimizerMutex, slam.hpp:105-106).  All device
+ * work of a context is issued on one CUDA stream (given at creation or owned).
+ *
+ * "host" pointers are ordinary host memory (pinned memory makes the copies asynchronous);
+ * "_dev" entry points take device pointers valid on the context's device.
+ */
+#ifndef SLAM_B200_H
+#define SLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct slam_b200_ctx slam_b200_ctx;
+
+#define SLAM_B200_OK 0
+#define SLAM_B200_E_CUDA (-100)     /* CUDA runtime error or no device */
+#define SLAM_B200_E_ARG (-101)      /* bad argument (null pointer, unknown id, duplicate id ...) */
+#define SLAM_B200_E_STATE (-102)    /* call not valid in the current state */
+#define SLAM_B200_E_NOMEM (-103)
+
+/* association result codes written to status[] */
+#define SLAM_B200_ASSOC_MATCHED 0   /* matched map cone idx[i]            (slam.cpp:584-592) */
+#define SLAM_B200_ASSOC_NEW 1       /* created map cone idx[i]            (slam.cpp:608-619) */
+#define SLAM_B200_ASSOC_NONE 2      /* unmatched, not added               (slam.cpp:608)     */
+#define SLAM_B200_ASSOC_SKIPPED 3   /* loop closing already set           (slam.cpp:575,608) */
+
+/* gate of the match-only / localiser association */
+#define SLAM_B200_GATE_MAPPING 0    /* fabs(mapType-obsType)<1e-4 && dist<thr   (slam.cpp:576,584) */
+#define SLAM_B200_GATE_LOCALIZER 1  /* dist<thr && (mapType-(int)obsType)<1e-4  (slam.cpp:360)     */
+
+#define SLAM_B200_ALGO_BRUTE 0      /* every observation against every map cone, map tiles in smem */
+#define SLAM_B200_ALGO_GRID 1       /* uniform-grid buckets (cell >= thr), identical results        */
+
+/* ------------------------------------------------------------------------------------------------
+ * context
+ * ---------------------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`.  `stream` is a cudaStream_t to issue all work on, or
+ * NULL to let the context create and own one.  Replaces Slam::setupOptimizer (slam.cpp:53-65). */
+int slam_b200_create(int device, void* stream, slam_b200_ctx** out);
+int slam_b200_destroy(slam_b200_ctx* ctx);
+const char* slam_b200_last_error(const slam_b200_ctx* ctx);
+int slam_b200_version(void);
+/* blocks until all work issued on the context's stream has finished */
+int slam_b200_sync(slam_b200_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * polar -> Cartesian conversion on the device
+ * Replaces Slam::coneToGlobal (slam.cpp:499-510), Slam::Spherical2Cartesian (637-654) and
+ * Slam::transformConeToCoG (513-523) for a whole frame.
+ *   cones4xN : host, column-major 4 x n (azimuth deg, zenith deg, range, type) = the frame matrix
+ *              performSLAM receives (slam.cpp:298).
+ *   global3  : host out, n x 3 (x, y, type) or NULL.   local3 : host out, n x 3 (x, y, z) or NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int slam_b200_cones_to_global(slam_b200_ctx* ctx, const double* cones4xN, int n,
+                              const double pose[3], double* global3, double* local3);
+
+/* ------------------------------------------------------------------------------------------------
+ * cone map (replaces std::vector<Cone> m_map, slam.hpp:110; element = Cone{x,y,type}, cone.hpp:51-55;
+ * the cone id is its index, slam.cpp:556,610)
+ * ---------------------------------------------------------------------------------------------- */
+int slam_b200_map_clear(slam_b200_ctx* ctx);
+int slam_b200_map_append(slam_b200_ctx* ctx, const double* x, const double* y, const int32_t* type, int n);
+int slam_b200_map_size(slam_b200_ctx* ctx);
+int slam_b200_map_read(slam_b200_ctx* ctx, int first, int n, double* x, double* y, int32_t* type);
+/* Slam::updateMap (slam.cpp:713-732) with caller-provided coordinates */
+int slam_b200_map_write_xy(slam_b200_ctx* ctx, int first, int n, const double* x, const double* y);
+
+/* ------------------------------------------------------------------------------------------------
+ * association
+ * ---------------------------------------------------------------------------------------------- */
+/* Mapping-phase association of one frame.  Replaces the matching / map-growth / loop-closure
+ * detection / current-cone tracking of Slam::addConesToMap (slam.cpp:552-623) incl.
+ * Slam::loopClosing (697-706) and Slam::distanceBetweenCones (708-711).  The device map grows by
+ * the cones created.  The graph side effects are returned as records:
+ *   idx[i], status[i] : see SLAM_B200_ASSOC_*;   z2 : n x 2 vehicle-frame xy each edge carries
+ *   (addConeMeasurement, 539-545);   g3 : n x 3 coneToGlobal of every column (572).
+ *   *current_cone_index, *loop_closing : in/out = m_currentConeIndex, m_loopClosing.
+ *   *first_cone_created : 1 if the map was empty and cone 0 was made from column 0 (554-567; its
+ *   edge precedes the per-observation edges).  *loop_closing_obs : column that set m_loopClosing
+ *   in this frame, else -1 (the caller then runs optimise once per column >= it, 625-633).
+ * Returns the new map size. */
+int slam_b200_assoc_map_frame(slam_b200_ctx* ctx, const double* cones4xN, int n, const double pose[3],
+                              double same_cone_threshold, double cone_mapping_threshold,
+                              uint32_t* current_cone_index, int32_t* loop_closing,
+                              int32_t* idx, int32_t* status, double* z2, double* g3,
+                              int32_t* first_cone_created, int32_t* loop_closing_obs);
+
+/* Localisation-phase association of one frame.  Replaces the matching loop of Slam::localizer
+ * (slam.cpp:350-387).  idx[i] = first map index passing the localiser gate or -1.
+ * *current_cone_index in/out (387); *n_reobserved (366); *send_cone_data (385, only meaningful
+ * when *n_reobserved > 0).  Returns *n_reobserved. */
+int slam_b200_assoc_localize_frame(slam_b200_ctx* ctx, const double* cones4xN, int n, const double pose[3],
+                                   double threshold, uint32_t* current_cone_index, int32_t* idx,
+                                   double* g3, int32_t* n_reobserved, int32_t* send_cone_data);
+
+/* Match-only association of a large observation batch against the frozen device map (phase 1 of
+ * addConesToMap / the localizer loop; BASELINE config "large cone field").  gate, algo: see above.
+ * Host variant copies cones in and idx out; _dev variant works on device pointers (cones4xN_dev:
+ * 4 x n column-major doubles, idx_dev: n int32) and only enqueues work on the context's stream. */
+int slam_b200_assoc_bulk(slam_b200_ctx* ctx, const double* cones4xN, int n, const double pose[3],
+                         double threshold, int gate, int algo, int32_t* idx);
+int slam_b200_assoc_bulk_dev(slam_b200_ctx* ctx, const double* cones4xN_dev, int n, const double pose[3],
+                             double threshold, int gate, int algo, int32_t* idx_dev);
+/* (Re)builds the uniform-grid index of the device map for SLAM_B200_ALGO_GRID with cells of
+ * `cell` metres (>= the threshold used later).  Called implicitly when missing or stale. */
+int slam_b200_map_build_grid(slam_b200_ctx* ctx, double cell);
+
+/* ------------------------------------------------------------------------------------------------
+ * pose-landmark graph (replaces g2o::SparseOptimizer m_optimizer and the g2o types the reference
+ * instantiates: VertexSE2, VertexPointXY, EdgeSE2, EdgeSE2PointXY; slam.hpp:26-35,98)
+ * ---------------------------------------------------------------------------------------------- */
+int slam_b200_graph_clear(slam_b200_ctx* ctx);
+/* Slam::addPoseToGraph vertex part (slam.cpp:434-438) */
+int slam_b200_graph_add_pose(slam_b200_ctx* ctx, int id, double x, double y, double theta);
+/* Slam::addConeToGraph vertex part (slam.cpp:526-531) */
+int slam_b200_graph_add_landmark(slam_b200_ctx* ctx, int id, double x, double y);
+/* EdgeSE2 with explicit measurement and row-major 3x3 information (slam.cpp:447-457) */
+int slam_b200_graph_add_edge_se2(slam_b200_ctx* ctx, int id_from, int id_to, const double z[3], const double info[9]);
+/* Slam::addOdometryMeasurement (slam.cpp:445-459): measurement = estimate(id_prev)^-1 * SE2(pose) */
+int slam_b200_graph_add_odometry(slam_b200_ctx* ctx, int id_prev, int id_cur, const double pose[3], const double info[9]);
+/* EdgeSE2PointXY, row-major 2x2 information (Slam::addConeMeasurement, slam.cpp:537-547) */
+int slam_b200_graph_add_edge_se2_xy(slam_b200_ctx* ctx, int pose_id, int landmark_id, const double z[2], const double info[4]);
+/* Vertex::setFixed (slam.cpp:464-474) */
+int slam_b200_graph_set_fixed(slam_b200_ctx* ctx, int id, int fixed);
+/* Bulk loader (same semantics as the calls above, SoA host arrays).  Vertex ids must be unique. */
+int slam_b200_graph_load(slam_b200_ctx* ctx,
+                         int n_poses, const int32_t* pose_ids, const double* pose_est3,
+                         int n_landmarks, const int32_t* lm_ids, const double* lm_est2,
+                         int n_eo, const int32_t* eo_from, const int32_t* eo_to, const double* eo_z3, const double* eo_info9,
+                         int n_el, const int32_t* el_pose, const int32_t* el_lm, const double* el_z2, const double* el_info4,
+                         int n_fixed, const int32_t* fixed_ids);
+/* Overwrites all estimates / measurements (same counts and order as loaded); NULL keeps a field. */
+int slam_b200_graph_set_values(slam_b200_ctx* ctx, const double* pose_est3, const double* lm_est2,
+                               const double* eo_z3, const double* el_z2);
+
+/* m_optimizer.initializeOptimization(); m_optimizer.optimize(iters) (slam.cpp:480-481).
+ * chi2[k] (may be NULL) = active chi2 after iteration k (what g2o prints in verbose mode,
+ * slam.cpp:63).  Returns g2o's convention: -1 nothing to optimise, 0 factorisation failed
+ * (zero pivot), else the number of iterations done.  Host estimates are refreshed on return. */
+int slam_b200_graph_optimize(slam_b200_ctx* ctx, int iters, double* chi2);
+
+/* VertexSE2/VertexPointXY::estimate() (slam.cpp:418-420, 719-720).  Returns the dimension. */
+int slam_b200_graph_get_vertex(slam_b200_ctx* ctx, int id, double out[3]);
+/* all estimates in insertion order: poses n x 3, landmarks n x 2 (either may be NULL) */
+int slam_b200_graph_get_estimates(slam_b200_ctx* ctx, double* pose_est3, double* lm_est2);
+int slam_b200_graph_num_poses(slam_b200_ctx* ctx);
+int slam_b200_graph_num_landmarks(slam_b200_ctx* ctx);
+int slam_b200_graph_num_edges(slam_b200_ctx* ctx);
+/* active chi2 at the current estimate (SparseOptimizer::computeActiveErrors + activeRobustChi2) */
+int slam_b200_graph_chi2(slam_b200_ctx* ctx, double* chi2);
+
+/* ---- finer-grained, device-resident control (bench / profiling / multi-GPU) ------------------ */
+/* Uploads the graph and runs the host symbolic phase (index mapping, block structure, ordering,
+ * assembly tree) if the structure changed.  Returns the scalar dimension of the system. */
+int slam_b200_graph_prepare(slam_b200_ctx* ctx);
+/* Enqueues `iters` Gauss-Newton iterations on the stream without any host synchronisation or
+ * copy.  Status / chi2 stay on the device until slam_b200_graph_finish. */
+int slam_b200_graph_iterate_async(slam_b200_ctx* ctx, int iters);
+/* Synchronises, returns like slam_b200_graph_optimize for the iterations enqueued since prepare /
+ * the last finish, copies chi2 and refreshes host estimates. */
+int slam_b200_graph_finish(slam_b200_ctx* ctx, double* chi2, int chi2_cap);
+/* Re-uploads the host-side estimates and measurements (device state <- host state). */
+int slam_b200_graph_reset_device(slam_b200_ctx* ctx);
+/* Enqueues one linearise + assemble pass (no solve).  Pose range [p0,p1) selects the edge shard
+ * (edges are partitioned by their pose; landmark blocks receive partial sums) -- whole graph:
+ * 0, n_poses. */
+int slam_b200_graph_assemble_async(slam_b200_ctx* ctx, int p0, int p1);
+/* Device pointers into the assembled system for collectives over peer memory / NCCL:
+ * which: 0 = landmark diagonal blocks + landmark rhs (contiguous, the part that needs a
+ * reduction across pose shards), 1 = full H value array, 2 = rhs b.  Returns element count. */
+long slam_b200_graph_system_dev(slam_b200_ctx* ctx, int which, double** ptr);
+/* Enqueues factorise + solve + update for the system currently assembled. */
+int slam_b200_graph_solve_async(slam_b200_ctx* ctx);
+
+/* Debug / test export of the assembled system in g2o's Hessian order (ascending vertex id among
+ * non-fixed active vertices): upper-triangular scalar CSC.  Call with Ai == NULL to query
+ * (returns nnz, *n = dimension).  Assembles at the current device estimate. */
+long slam_b200_graph_export_system(slam_b200_ctx* ctx, int* n, int32_t* Ap, int32_t* Ai, double* Ax, double* b);
+/* Statistics of the symbolic phase and last run, see DESIGN.md:
+ * out[0..15] = n_scalar, n_blocks, n_fronts, n_levels, nnz_H_upper, nnz_L, factor_flops,
+ * max_front, front_storage_doubles, symbolic_seconds, upload_seconds, 5 reserved. */
+int slam_b200_graph_stats(slam_b200_ctx* ctx, double out[16]);
+/* Export of the symbolic analysis for tests (query the length with out == NULL): what = 0 sizes
+ * [nb, n, nf, nlevels, n_upd_rows, n_asm, max_front], 1 pos, 2 boff, 3 level_ptr, 4 piv0, 5 npiv,
+ * 6 nupd, 7 parent, 8 rows_ptr, 9 upd_rows, 10 rel, 11 asm_ptr, 12 asm entries (hoff, r, c, meta),
+ * 13 g2o scalar offset per block, 14 dims, 15 child_ptr, 16 children.  See csrc/symbolic.h. */
+long slam_b200_graph_export_symbolic(slam_b200_ctx* ctx, int what, int32_t* out, long cap);
+/* The same symbolic analysis on a bare block pattern, no device needed (host logic under test):
+ * nb blocks of dimension dim[], n_pairs distinct off-diagonal pairs a[k] < b[k].  H blocks are
+ * assumed stored diag blocks first (d*d each, block order) then the pairs (dim[a] x dim[b]). */
+void* slam_b200_symbolic_create(int nb, const int32_t* dim, int n_pairs, const int32_t* a, const int32_t* b, int leaf_size);
+long slam_b200_symbolic_export(void* handle, int what, int32_t* out, long cap);
+/* what: 0 nnz(L), 1 factor flops, 2 max front, 3 seconds, 4 front storage (doubles) */
+double slam_b200_symbolic_stat(void* handle, int what);
+void slam_b200_symbolic_destroy(void* handle);
+
+/* ---- batched Monte-Carlo replicas of the loaded topology (BASELINE config 3) ----------------- */
+/* Each replica r has its own estimates and measurements (host arrays, replica-major:
+ * pose_est3 [R][P][3], lm_est2 [R][L][2], eo_z3 [R][Eo][3], el_z2 [R][El][2]); information
+ * matrices, topology and gauge are those of the loaded graph.  Runs `iters` GN iterations on all
+ * replicas; writes optimised estimates back into pose_est3 / lm_est2, chi2 [R][iters] (may be
+ * NULL) and iterations_done [R] (g2o convention).  Returns 0. */
+int slam_b200_graph_optimize_batch(slam_b200_ctx* ctx, int n_replicas, double* pose_est3, double* lm_est2,
+                                   const double* eo_z3, const double* el_z2, int iters,
+                                   double* chi2, int32_t* iterations_done);
+/* Device-resident variant: allocate/upload once, iterate without copies. */
+int slam_b200_batch_upload(slam_b200_ctx* ctx, int n_replicas, const double* pose_est3, const double* lm_est2,
+                           const double* eo_z3, const double* el_z2);
+int slam_b200_batch_iterate_async(slam_b200_ctx* ctx, int iters);
+int slam_b200_batch_download(slam_b200_ctx* ctx, double* pose_est3, double* lm_est2, double* chi2,
+                             int chi2_cap_per_replica, int32_t* iterations_done);
+
+/* number of kernel launches issued by this context since creation (bench bookkeeping) */
+long slam_b200_launch_count(slam_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAM_B200_H */

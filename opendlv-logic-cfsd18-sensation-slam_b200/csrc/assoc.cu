@@ -1,0 +1,798 @@
+// assoc.cu -- cone data association on the device (sm_100a).
+//
+// Replaces, for whole frames at a time, Slam::coneToGlobal (slam.cpp:499-510),
+// Slam::Spherical2Cartesian (637-654), Slam::transformConeToCoG (513-523),
+// Slam::distanceBetweenCones (708-711), the matching/map-growth/loop-closure part of
+// Slam::addConesToMap (552-623), Slam::loopClosing (697-706) and the matching loop of
+// Slam::localizer (350-387).
+//
+// The reference association is FIRST-FIT in map-index order (575-607): the result for one
+// observation is the MINIMUM map index among the gated candidates, which is what every kernel here
+// computes (ascending scans that stop at the first hit, or an explicit min over bucket candidates).
+//
+// Compiled with -fmad=false: the reference build (x86-64 -O2, CMakeLists.txt:35-38) has no fused
+// multiply-add, and the gate decisions must be bit-exact, so products and sums are rounded
+// separately exactly like the CPU does.  sqrt is IEEE correctly rounded on both sides.
+#include <cub/device/device_scan.cuh>
+#include <cmath>
+#include <cfloat>
+
+#include "ctx.h"
+
+namespace {
+
+__device__ __forceinline__ double ref_deg2rad() { return 0.017453292522222; }   // slam.hpp:134
+__device__ __forceinline__ double ref_rad2deg() { return 57.295779513082325; }  // slam.hpp:135
+__device__ __forceinline__ double ref_pi() { return (double)3.14159265f; }      // slam.hpp:136
+
+// slam.cpp:513-523
+__device__ __forceinline__ void transform_cone_to_cog(double angle, double distance, double& angOut,
+                                                      double& distOut) {
+  const double lidarDistToCoG = 1.5;
+  double sign = angle / fabs(angle);
+  angle = ref_pi() - fabs(angle * ref_deg2rad());
+  double distanceNew = sqrt(lidarDistToCoG * lidarDistToCoG + distance * distance -
+                            2 * lidarDistToCoG * distance * cos(angle));
+  double angleNew = asin((sin(angle) * distance) / distanceNew) * ref_rad2deg();
+  angOut = angleNew * sign;
+  distOut = distanceNew;
+}
+
+// slam.cpp:637-654
+__device__ __forceinline__ void spherical2cartesian(double az, double zen, double dist, double& x,
+                                                    double& y, double& z) {
+  double a, d;
+  transform_cone_to_cog(az, dist, a, d);
+  x = d * cos(zen * ref_deg2rad()) * cos(a * ref_deg2rad());
+  y = d * cos(zen * ref_deg2rad()) * sin(a * ref_deg2rad());
+  z = d * sin(zen * ref_deg2rad());
+}
+
+// slam.cpp:499-510 (pose trig hoisted by the callers: cp = cos(pose.theta), sp = sin(pose.theta))
+__device__ __forceinline__ void local_to_global(double lx, double ly, double px, double py, double cp,
+                                                double sp, double& gx, double& gy) {
+  double newX = lx * cp - ly * sp;
+  double newY = lx * sp + ly * cp;
+  gx = newX + px;
+  gy = newY + py;
+}
+
+// slam.cpp:708-711
+__device__ __forceinline__ double cone_distance(double x1, double y1, double x2, double y2) {
+  return sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+}
+__device__ __forceinline__ double cone_distance2(double x1, double y1, double x2, double y2) {
+  return (x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2);
+}
+
+// type gates.  mapping: fabs(mapType - obsType) < 0.0001 (slam.cpp:576), obsType the raw double.
+// localizer: (mapType - (int)obsType) < 0.0001 (slam.cpp:358,360) == mapType <= (int)obsType.
+template <int GATE>
+__device__ __forceinline__ bool type_gate(int mapType, double obsType, int obsTypeInt) {
+  if (GATE == SLAM_B200_GATE_MAPPING) return fabs((double)mapType - obsType) < 0.0001;
+  return (mapType - obsTypeInt) < 0.0001;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame kernels (one CTA; a frame is <= a few thousand observations, slam.cpp:46,244)
+// ------------------------------------------------------------------------------------------------
+constexpr int FRAME_THREADS = 512;
+constexpr int FRAME_TILE = 2048;  // map cones staged in shared memory per pass (40 KB)
+
+struct FrameScalars {  // ints at the head of the int output buffer
+  int first_cone_created, loop_closing_obs, map_n, current_cone_index, loop_closing, n_reobserved,
+      send_cone_data, pad;
+};
+
+// Phase 1 of both frame kernels: first-fit of every observation against map[0, M) (frozen),
+// one warp per observation, map tiles staged in shared memory, ascending 32-wide chunks with a
+// ballot so the first chunk containing a hit yields the minimum index.
+template <int GATE>
+__device__ void frame_first_fit(const double* __restrict__ gx, const double* __restrict__ gy,
+                                const double* __restrict__ gt, int n, const double* map_x,
+                                const double* map_y, const int* map_type, int M, double thr,
+                                int* idx, double* sx, double* sy, int* st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) idx[i] = -1;
+  for (int t0 = 0; t0 < M; t0 += FRAME_TILE) {
+    int tn = min(FRAME_TILE, M - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) {
+      sx[k] = map_x[t0 + k];
+      sy[k] = map_y[t0 + k];
+      st[k] = map_type[t0 + k];
+    }
+    __syncthreads();
+    for (int i = warp; i < n; i += nwarps) {
+      if (idx[i] >= 0) continue;  // warp-uniform
+      double ox = gx[i], oy = gy[i], ot = gt[i];
+      int oti = (int)ot;
+      int found = -1;
+      for (int c = 0; c < tn && found < 0; c += 32) {
+        int k = c + lane;
+        bool hit = false;
+        if (k < tn) hit = type_gate<GATE>(st[k], ot, oti) && cone_distance(sx[k], sy[k], ox, oy) < thr;
+        unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (b) found = t0 + c + __ffs(b) - 1;
+      }
+      if (found >= 0 && lane == 0) idx[i] = found;
+    }
+  }
+  __syncthreads();
+}
+
+// Mapping-phase frame (slam.cpp:552-623).  in: 4n frame doubles then pose(3).
+__global__ void __launch_bounds__(FRAME_THREADS, 1)
+assoc_map_frame_kernel(const double* __restrict__ in, int n, double thr, double mapThr, double* map_x,
+                       double* map_y, int* map_type, int M0, unsigned cci_in, int lc_in,
+                       double* __restrict__ outd, int* __restrict__ outi) {
+  __shared__ double sx[FRAME_TILE], sy[FRAME_TILE];
+  __shared__ int st[FRAME_TILE];
+  FrameScalars* sc = reinterpret_cast<FrameScalars*>(outi);
+  int* idx = outi + 8;
+  int* status = outi + 8 + n;
+  double* z2 = outd;           // 2n
+  double* g3 = outd + 2 * (size_t)n;  // 3n
+  const double px = in[4 * (size_t)n], py = in[4 * (size_t)n + 1];
+  const double cp = in[4 * (size_t)n + 3], sp = in[4 * (size_t)n + 4];
+  // conversion of all columns (slam.cpp:572, 539)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double* col = in + 4 * (size_t)i;
+    double lx, ly, lz, gx, gy;
+    spherical2cartesian(col[0], col[1], col[2], lx, ly, lz);
+    local_to_global(lx, ly, px, py, cp, sp, gx, gy);
+    z2[2 * i] = lx;
+    z2[2 * i + 1] = ly;
+    g3[3 * i] = gx;
+    g3[3 * i + 1] = gy;
+    g3[3 * i + 2] = col[3];
+  }
+  __syncthreads();
+  int M = M0;
+  int first = 0;
+  if (M == 0 && n > 0) {  // slam.cpp:554-567
+    if (threadIdx.x == 0) {
+      map_x[0] = g3[0];
+      map_y[0] = g3[1];
+      map_type[0] = (int)g3[2];
+    }
+    M = 1;
+    first = 1;
+    __syncthreads();
+  }
+  // SoA views of g for the shared routine: read straight from g3 with stride 3 via small lambdas
+  // is awkward, so stage gx/gy/type contiguously behind g3 (outd has 8n doubles).
+  double* gxs = outd + 5 * (size_t)n;
+  double* gys = gxs + n;
+  double* gts = gys + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    gxs[i] = g3[3 * i];
+    gys[i] = g3[3 * i + 1];
+    gts[i] = g3[3 * i + 2];
+  }
+  __syncthreads();
+  if (!lc_in)
+    frame_first_fit<SLAM_B200_GATE_MAPPING>(gxs, gys, gts, n, map_x, map_y, map_type, M, thr, idx, sx, sy, st);
+  else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) idx[i] = -1;
+    __syncthreads();
+  }
+  // Phase 2: the order-dependent part, one warp, observations in order: cones created earlier in
+  // this frame are visible to later observations (611 inside the loop), m_currentConeIndex feeds
+  // the loop-closure test (702), m_loopClosing short-circuits everything after it (575, 608).
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int Mpre = M;  // pre-frame map (incl. the first cone)
+    unsigned cci = cci_in;
+    int lc = lc_in, lcObs = -1;
+    double minDistance = 100;  // 569
+    double m0x = 0, m0y = 0;
+    if (M > 0) { m0x = map_x[0]; m0y = map_y[0]; }
+    for (int i = 0; i < n; i++) {
+      double d2c = in[4 * (size_t)i + 2];
+      double ox = gxs[i], oy = gys[i], ot = gts[i];
+      int j = lc ? -1 : idx[i];
+      if (!lc && j < 0) {
+        for (int c = Mpre; c < M && j < 0; c += 32) {  // cones created earlier in this frame
+          int k = c + lane;
+          bool hit = false;
+          if (k < M) {
+            double kx = ((volatile double*)map_x)[k], ky = ((volatile double*)map_y)[k];
+            int kt = ((volatile int*)map_type)[k];
+            hit = type_gate<SLAM_B200_GATE_MAPPING>(kt, ot, 0) && cone_distance(kx, ky, ox, oy) < thr;
+          }
+          unsigned b = __ballot_sync(0xffffffffu, hit);
+          if (b) j = c + __ffs(b) - 1;
+        }
+      }
+      int stt;
+      if (lc) {
+        stt = SLAM_B200_ASSOC_SKIPPED;
+        j = -1;
+      } else if (j >= 0) {
+        stt = SLAM_B200_ASSOC_MATCHED;
+        double jx = ((volatile double*)map_x)[j], jy = ((volatile double*)map_y)[j];
+        if (cone_distance(m0x, m0y, jx, jy) < 1 && cci > 20 && d2c < mapThr) {  // 697-706, 593-596
+          lc = 1;
+          lcObs = i;
+        }
+        if (d2c < minDistance) {  // 598-601
+          cci = (unsigned)j;
+          minDistance = d2c;
+        }
+      } else if (d2c < mapThr) {  // 608-611
+        stt = SLAM_B200_ASSOC_NEW;
+        j = M;
+        if (lane == 0) {
+          map_x[M] = ox;
+          map_y[M] = oy;
+          map_type[M] = (int)ot;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (M == 0) { m0x = ox; m0y = oy; }
+        M++;
+      } else {
+        stt = SLAM_B200_ASSOC_NONE;
+      }
+      if (lane == 0) {
+        idx[i] = j;
+        status[i] = stt;
+      }
+    }
+    if (lane == 0) {
+      sc->first_cone_created = first;
+      sc->loop_closing_obs = lcObs;
+      sc->map_n = M;
+      sc->current_cone_index = (int)cci;
+      sc->loop_closing = lc;
+      sc->n_reobserved = 0;
+      sc->send_cone_data = 0;
+      sc->pad = 0;
+    }
+  }
+}
+
+// Localisation-phase frame (slam.cpp:350-387)
+__global__ void __launch_bounds__(FRAME_THREADS, 1)
+assoc_localize_frame_kernel(const double* __restrict__ in, int n, double thr, const double* map_x,
+                            const double* map_y, const int* map_type, int M, unsigned cci_in,
+                            double* __restrict__ outd, int* __restrict__ outi) {
+  __shared__ double sx[FRAME_TILE], sy[FRAME_TILE];
+  __shared__ int st[FRAME_TILE];
+  FrameScalars* sc = reinterpret_cast<FrameScalars*>(outi);
+  int* idx = outi + 8;
+  double* g3 = outd + 2 * (size_t)n;
+  double* gxs = outd + 5 * (size_t)n;
+  double* gys = gxs + n;
+  double* gts = gys + n;
+  const double px = in[4 * (size_t)n], py = in[4 * (size_t)n + 1];
+  const double cp = in[4 * (size_t)n + 3], sp = in[4 * (size_t)n + 4];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double* col = in + 4 * (size_t)i;
+    double lx, ly, lz, gx, gy;
+    spherical2cartesian(col[0], col[1], col[2], lx, ly, lz);
+    local_to_global(lx, ly, px, py, cp, sp, gx, gy);
+    g3[3 * i] = gx; g3[3 * i + 1] = gy; g3[3 * i + 2] = col[3];
+    gxs[i] = gx; gys[i] = gy; gts[i] = col[3];
+  }
+  __syncthreads();
+  frame_first_fit<SLAM_B200_GATE_LOCALIZER>(gxs, gys, gts, n, map_x, map_y, map_type, M, thr, idx, sx, sy, st);
+  if (threadIdx.x == 0) {  // 375-378, 385-387: nearest matched observation, strict <, first wins
+    double minDistance = 100;
+    unsigned cci = 0;
+    int reobs = 0;
+    for (int i = 0; i < n; i++) {
+      if (idx[i] >= 0) {
+        reobs++;
+        double d2c = in[4 * (size_t)i + 2];
+        if (d2c < minDistance) { cci = (unsigned)idx[i]; minDistance = d2c; }
+      }
+    }
+    sc->first_cone_created = 0;
+    sc->loop_closing_obs = -1;
+    sc->map_n = M;
+    sc->n_reobserved = reobs;
+    sc->send_cone_data = reobs > 0 ? (cci != cci_in) : 0;
+    sc->current_cone_index = reobs > 0 ? (int)cci : (int)cci_in;
+    sc->loop_closing = 0;
+    sc->pad = 0;
+  }
+}
+
+// conversion only (slam_b200_cones_to_global)
+__global__ void convert_kernel(const double* __restrict__ in, int n, double* __restrict__ g3,
+                               double* __restrict__ l3) {
+  const double px = in[4 * (size_t)n], py = in[4 * (size_t)n + 1];
+  const double cp = in[4 * (size_t)n + 3], sp = in[4 * (size_t)n + 4];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* col = in + 4 * (size_t)i;
+  double lx, ly, lz, gx, gy;
+  spherical2cartesian(col[0], col[1], col[2], lx, ly, lz);
+  local_to_global(lx, ly, px, py, cp, sp, gx, gy);
+  g3[3 * i] = gx; g3[3 * i + 1] = gy; g3[3 * i + 2] = col[3];
+  l3[3 * i] = lx; l3[3 * i + 1] = ly; l3[3 * i + 2] = lz;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bulk match-only kernels (large cone field).  thr2x = smallest double s with sqrt(s) >= thr, so
+// `d2 < thr2x` decides exactly like `sqrt(d2) < thr` (sqrt is monotone and correctly rounded)
+// without a square root in the inner loop.
+// ------------------------------------------------------------------------------------------------
+constexpr int BULK_THREADS = 128;
+constexpr int BULK_TILE = 1024;
+
+struct PoseTrig { double px, py, cp, sp; };
+
+__device__ __forceinline__ void load_obs(const double* __restrict__ cones, int i, const PoseTrig& pt,
+                                         double& gx, double& gy, double& ot) {
+  // one observation = one 32-byte column: two 16-byte loads
+  const double2* c2 = reinterpret_cast<const double2*>(cones + 4 * (size_t)i);
+  double2 a = __ldg(c2), b = __ldg(c2 + 1);
+  double lx, ly, lz;
+  spherical2cartesian(a.x, a.y, b.x, lx, ly, lz);
+  local_to_global(lx, ly, pt.px, pt.py, pt.cp, pt.sp, gx, gy);
+  ot = b.y;
+}
+
+// brute force: one thread per observation, the whole map streamed through shared memory in tiles,
+// ascending index, stop at the first hit.
+template <int GATE>
+__global__ void __launch_bounds__(BULK_THREADS)
+assoc_bulk_brute_kernel(const double* __restrict__ cones, int n, PoseTrig pt, double thr2x,
+                        const double* __restrict__ map_x, const double* __restrict__ map_y,
+                        const int* __restrict__ map_type, int M, int* __restrict__ idx) {
+  __shared__ double sx[BULK_TILE], sy[BULK_TILE];
+  __shared__ int st[BULK_TILE];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double gx = 0, gy = 0, ot = 0;
+  int found = -1;
+  bool active = i < n;
+  if (active) load_obs(cones, i, pt, gx, gy, ot);
+  int oti = (int)ot;
+  for (int t0 = 0; t0 < M; t0 += BULK_TILE) {
+    int tn = min(BULK_TILE, M - t0);
+    if (__syncthreads_and(!active || found >= 0)) break;
+    for (int k = threadIdx.x; k < tn; k += blockDim.x) {
+      sx[k] = __ldg(map_x + t0 + k);
+      sy[k] = __ldg(map_y + t0 + k);
+      st[k] = __ldg(map_type + t0 + k);
+    }
+    __syncthreads();
+    if (active && found < 0) {
+      for (int k = 0; k < tn; k++) {
+        if (type_gate<GATE>(st[k], ot, oti) && cone_distance2(sx[k], sy[k], gx, gy) < thr2x) {
+          found = t0 + k;
+          break;
+        }
+      }
+    }
+  }
+  if (active) idx[i] = found;
+}
+
+// ---- uniform grid index --------------------------------------------------------------------------
+__global__ void bbox_kernel(const double* __restrict__ x, const double* __restrict__ y, int M,
+                            double* __restrict__ bbox) {  // bbox pre-set to +inf,+inf,-inf,-inf
+  double mnx = DBL_MAX, mny = DBL_MAX, mxx = -DBL_MAX, mxy = -DBL_MAX;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    double a = x[i], b = y[i];
+    if (isfinite(a) && isfinite(b)) {
+      mnx = fmin(mnx, a); mxx = fmax(mxx, a);
+      mny = fmin(mny, b); mxy = fmax(mxy, b);
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // doubles are ordered like their sign-magnitude bit patterns; use CAS loops on the 4 slots
+    auto amin = [](double* addr, double v) {
+      unsigned long long* a = (unsigned long long*)addr;
+      unsigned long long old = *a, assumed;
+      do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) <= v) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+      } while (assumed != old);
+    };
+    auto amax = [](double* addr, double v) {
+      unsigned long long* a = (unsigned long long*)addr;
+      unsigned long long old = *a, assumed;
+      do {
+        assumed = old;
+        if (__longlong_as_double((long long)assumed) >= v) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+      } while (assumed != old);
+    };
+    amin(bbox + 0, mnx); amin(bbox + 1, mny); amax(bbox + 2, mxx); amax(bbox + 3, mxy);
+  }
+}
+
+struct GridParams { double x0, y0, inv; int nx, ny; };
+
+__device__ __forceinline__ int cell_coord(double v, double v0, double inv) {
+  // floor((v - v0) * inv): monotone in v, so |a-b| < cell  =>  cells differ by at most 1
+  return (int)floor((v - v0) * inv);
+}
+
+__global__ void grid_count_kernel(const double* __restrict__ x, const double* __restrict__ y, int M,
+                                  GridParams gp, int* __restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double a = x[i], b = y[i];
+  if (!(isfinite(a) && isfinite(b))) return;  // a NaN cone can never pass the distance gate
+  int cx = min(max(cell_coord(a, gp.x0, gp.inv), 0), gp.nx - 1);
+  int cy = min(max(cell_coord(b, gp.y0, gp.inv), 0), gp.ny - 1);
+  atomicAdd(count + (size_t)cy * gp.nx + cx, 1);
+}
+
+__global__ void grid_fill_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                 const int* __restrict__ type, int M, GridParams gp,
+                                 int* __restrict__ cursor, double* __restrict__ sx,
+                                 double* __restrict__ sy, int2* __restrict__ sti) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  double a = x[i], b = y[i];
+  if (!(isfinite(a) && isfinite(b))) return;
+  int cx = min(max(cell_coord(a, gp.x0, gp.inv), 0), gp.nx - 1);
+  int cy = min(max(cell_coord(b, gp.y0, gp.inv), 0), gp.ny - 1);
+  int slot = atomicAdd(cursor + (size_t)cy * gp.nx + cx, 1);
+  sx[slot] = a;
+  sy[slot] = b;
+  sti[slot] = make_int2(type[i], i);
+}
+
+// bucketed: one thread per observation; the 3x3 cell neighbourhood is three contiguous runs of the
+// cell-sorted map; the answer is the minimum ORIGINAL index over gated candidates.
+template <int GATE>
+__global__ void __launch_bounds__(BULK_THREADS)
+assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, double thr2x, GridParams gp,
+                       const int* __restrict__ cell_start, const double* __restrict__ sx,
+                       const double* __restrict__ sy, const int2* __restrict__ sti,
+                       int* __restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double gx, gy, ot;
+  load_obs(cones, i, pt, gx, gy, ot);
+  int oti = (int)ot;
+  int best = 0x7fffffff;
+  if (isfinite(gx) && isfinite(gy)) {
+    double fx = floor((gx - gp.x0) * gp.inv), fy = floor((gy - gp.y0) * gp.inv);
+    // observations far outside the map's bounding box have no candidates
+    if (fx >= -1.0 && fx <= (double)gp.nx && fy >= -1.0 && fy <= (double)gp.ny) {
+      int cx = (int)fx, cy = (int)fy;
+      int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, gp.nx - 1);
+      // clamped border cells also hold cones whose raw cell fell outside; they are within
+      // [x_lo, x_hi] whenever they can be within one cell of the observation
+      if (x_lo <= x_hi) {
+        int rs[3], re[3];
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+          int row = cy + dy;
+          bool ok = row >= 0 && row < gp.ny;
+          size_t base = (size_t)(ok ? row : 0) * gp.nx;
+          rs[dy + 1] = ok ? __ldg(cell_start + base + x_lo) : 0;
+          re[dy + 1] = ok ? __ldg(cell_start + base + x_hi + 1) : 0;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          for (int k = rs[r]; k < re[r]; k++) {
+            int2 ti = __ldg(sti + k);
+            if (type_gate<GATE>(ti.x, ot, oti) && ti.y < best &&
+                cone_distance2(__ldg(sx + k), __ldg(sy + k), gx, gy) < thr2x)
+              best = ti.y;
+          }
+        }
+      }
+    }
+  }
+  idx[i] = best == 0x7fffffff ? -1 : best;
+}
+
+// smallest double s with sqrt(s) >= thr  (host; IEEE sqrt on both sides)
+double sqrt_gate_threshold(double thr) {
+  if (!(thr > 0)) return 0.0;  // dist < thr never true for thr <= 0 (dist >= 0)
+  double s = thr * thr;
+  while (std::sqrt(s) >= thr) s = std::nextafter(s, -INFINITY);
+  while (std::sqrt(s) < thr) s = std::nextafter(s, INFINITY);
+  return s;
+}
+
+int ensure_frame_buffers(slam_b200_ctx* c, int n) {
+  SLAM_CUDA_TRY(c, c->frame_in.exact(4 * (size_t)n + 8));
+  SLAM_CUDA_TRY(c, c->frame_outd.exact(8 * (size_t)n + 8));
+  SLAM_CUDA_TRY(c, c->frame_outi.exact(2 * (size_t)n + 8));
+  SLAM_CUDA_TRY(c, c->pin_d.reserve(8 * (size_t)n + 8));
+  SLAM_CUDA_TRY(c, c->pin_i.reserve(2 * (size_t)n + 8));
+  return 0;
+}
+
+int upload_frame(slam_b200_ctx* c, const double* cones, int n, const double pose[3]) {
+  std::memcpy(c->pin_d.p, cones, sizeof(double) * 4 * (size_t)n);
+  std::memcpy(c->pin_d.p + 4 * (size_t)n, pose, sizeof(double) * 3);
+  // cos/sin of the heading are two scalars per frame: taken from the host libm the reference
+  // itself uses (slam.cpp:504-505) so every column is rotated by bit-identical factors
+  c->pin_d.p[4 * (size_t)n + 3] = std::cos(pose[2]);
+  c->pin_d.p[4 * (size_t)n + 4] = std::sin(pose[2]);
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->frame_in.p, c->pin_d.p, sizeof(double) * (4 * (size_t)n + 5),
+                                   cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int slam_b200_cones_to_global(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
+                              double* global3, double* local3) {
+  if (!c || !cones || !pose || n < 0) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n == 0) return 0;
+  if (int rc = ensure_frame_buffers(c, n)) return rc;
+  if (int rc = upload_frame(c, cones, n, pose)) return rc;
+  double* g3 = c->frame_outd.p;
+  double* l3 = c->frame_outd.p + 3 * (size_t)n;
+  convert_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->frame_in.p, n, g3, l3);
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, c->frame_outd.p, sizeof(double) * 6 * (size_t)n,
+                                   cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (global3) std::memcpy(global3, c->pin_d.p, sizeof(double) * 3 * (size_t)n);
+  if (local3) std::memcpy(local3, c->pin_d.p + 3 * (size_t)n, sizeof(double) * 3 * (size_t)n);
+  return 0;
+}
+
+int slam_b200_map_clear(slam_b200_ctx* c) {
+  if (!c) return SLAM_B200_E_ARG;
+  c->map_n = 0;
+  c->map_version++;
+  return 0;
+}
+
+int slam_b200_map_append(slam_b200_ctx* c, const double* x, const double* y, const int32_t* type, int n) {
+  if (!c || n < 0 || (n > 0 && (!x || !y || !type))) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n == 0) return c->map_n;
+  size_t need = (size_t)c->map_n + n;
+  SLAM_CUDA_TRY(c, c->map_x.reserve(need, c->map_n, c->stream));
+  SLAM_CUDA_TRY(c, c->map_y.reserve(need, c->map_n, c->stream));
+  SLAM_CUDA_TRY(c, c->map_type.reserve(need, c->map_n, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->map_x.p + c->map_n, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->map_y.p + c->map_n, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->map_type.p + c->map_n, type, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->map_n += n;
+  c->map_version++;
+  return c->map_n;
+}
+
+int slam_b200_map_size(slam_b200_ctx* c) { return c ? c->map_n : SLAM_B200_E_ARG; }
+
+int slam_b200_map_read(slam_b200_ctx* c, int first, int n, double* x, double* y, int32_t* type) {
+  if (!c || first < 0 || n < 0 || first + n > c->map_n) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n == 0) return 0;
+  if (x) SLAM_CUDA_TRY(c, cudaMemcpyAsync(x, c->map_x.p + first, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (y) SLAM_CUDA_TRY(c, cudaMemcpyAsync(y, c->map_y.p + first, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (type) SLAM_CUDA_TRY(c, cudaMemcpyAsync(type, c->map_type.p + first, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return n;
+}
+
+int slam_b200_map_write_xy(slam_b200_ctx* c, int first, int n, const double* x, const double* y) {
+  if (!c || first < 0 || n < 0 || first + n > c->map_n || (n > 0 && (!x || !y))) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n == 0) return 0;
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->map_x.p + first, x, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->map_y.p + first, y, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->map_version++;
+  return n;
+}
+
+int slam_b200_assoc_map_frame(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
+                              double thr, double mapThr, uint32_t* cci, int32_t* loop_closing,
+                              int32_t* idx, int32_t* status, double* z2, double* g3,
+                              int32_t* first_cone_created, int32_t* loop_closing_obs) {
+  if (!c || !pose || !cci || !loop_closing || n < 0 || (n > 0 && (!cones || !idx || !status)))
+    return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (first_cone_created) *first_cone_created = 0;
+  if (loop_closing_obs) *loop_closing_obs = -1;
+  if (n == 0) return c->map_n;
+  if (int rc = ensure_frame_buffers(c, n)) return rc;
+  size_t need = (size_t)c->map_n + n + 1;  // every column may create a cone
+  SLAM_CUDA_TRY(c, c->map_x.reserve(need, c->map_n, c->stream));
+  SLAM_CUDA_TRY(c, c->map_y.reserve(need, c->map_n, c->stream));
+  SLAM_CUDA_TRY(c, c->map_type.reserve(need, c->map_n, c->stream));
+  if (int rc = upload_frame(c, cones, n, pose)) return rc;
+  assoc_map_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, mapThr, c->map_x.p,
+                                                            c->map_y.p, c->map_type.p, c->map_n, *cci,
+                                                            *loop_closing, c->frame_outd.p, c->frame_outi.p);
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_i.p, c->frame_outi.p, sizeof(int) * (2 * (size_t)n + 8),
+                                   cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, c->frame_outd.p, sizeof(double) * 5 * (size_t)n,
+                                   cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const FrameScalars* sc = reinterpret_cast<const FrameScalars*>(c->pin_i.p);
+  std::memcpy(idx, c->pin_i.p + 8, sizeof(int) * n);
+  std::memcpy(status, c->pin_i.p + 8 + n, sizeof(int) * n);
+  if (z2) std::memcpy(z2, c->pin_d.p, sizeof(double) * 2 * (size_t)n);
+  if (g3) std::memcpy(g3, c->pin_d.p + 2 * (size_t)n, sizeof(double) * 3 * (size_t)n);
+  if (first_cone_created) *first_cone_created = sc->first_cone_created;
+  if (loop_closing_obs) *loop_closing_obs = sc->loop_closing_obs;
+  *cci = (uint32_t)sc->current_cone_index;
+  *loop_closing = sc->loop_closing;
+  if (sc->map_n != c->map_n) c->map_version++;
+  c->map_n = sc->map_n;
+  return c->map_n;
+}
+
+int slam_b200_assoc_localize_frame(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
+                                   double thr, uint32_t* cci, int32_t* idx, double* g3,
+                                   int32_t* n_reobserved, int32_t* send_cone_data) {
+  if (!c || !pose || !cci || n < 0 || (n > 0 && (!cones || !idx))) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n_reobserved) *n_reobserved = 0;
+  if (send_cone_data) *send_cone_data = 0;
+  if (n == 0) return 0;
+  if (int rc = ensure_frame_buffers(c, n)) return rc;
+  if (int rc = upload_frame(c, cones, n, pose)) return rc;
+  assoc_localize_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, c->map_x.p, c->map_y.p,
+                                                                 c->map_type.p, c->map_n, *cci,
+                                                                 c->frame_outd.p, c->frame_outi.p);
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_i.p, c->frame_outi.p, sizeof(int) * ((size_t)n + 8),
+                                   cudaMemcpyDeviceToHost, c->stream));
+  if (g3)
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, c->frame_outd.p + 2 * (size_t)n, sizeof(double) * 3 * (size_t)n,
+                                     cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const FrameScalars* sc = reinterpret_cast<const FrameScalars*>(c->pin_i.p);
+  std::memcpy(idx, c->pin_i.p + 8, sizeof(int) * n);
+  if (g3) std::memcpy(g3, c->pin_d.p, sizeof(double) * 3 * (size_t)n);
+  *cci = (uint32_t)sc->current_cone_index;
+  if (n_reobserved) *n_reobserved = sc->n_reobserved;
+  if (send_cone_data) *send_cone_data = sc->send_cone_data;
+  return sc->n_reobserved;
+}
+
+int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) {
+  if (!c || !(cell > 0)) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  int M = c->map_n;
+  c->grid_map_version = 0;
+  if (M == 0) {
+    c->grid_nx = c->grid_ny = 0;
+    c->grid_cell = cell;
+    c->grid_map_version = c->map_version;
+    return 0;
+  }
+  SLAM_CUDA_TRY(c, c->grid_bbox.exact(4));
+  double init[4] = {DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX}, bb[4];
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->grid_bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  bbox_kernel<<<std::min((M + 255) / 256, 4 * c->num_sms), 256, 0, c->stream>>>(c->map_x.p, c->map_y.p, M, c->grid_bbox.p);
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(bb, c->grid_bbox.p, sizeof(bb), cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (!(bb[0] <= bb[2])) { bb[0] = bb[1] = 0; bb[2] = bb[3] = 0; }  // no finite cone
+  // cells are (1 + 1e-9) * cell wide: a pair closer than `cell` then provably lands in adjacent
+  // cells even after the rounding of (v - x0) * inv (relative 2^-52 on coordinates <= 1e6 cells)
+  double width = cell * (1.0 + 1e-9);
+  GridParams gp;
+  gp.x0 = bb[0];
+  gp.y0 = bb[1];
+  gp.inv = 1.0 / width;
+  double nxd = std::floor((bb[2] - bb[0]) * gp.inv) + 1, nyd = std::floor((bb[3] - bb[1]) * gp.inv) + 1;
+  if (nxd * nyd > 2.0e8) {  // keep the cell table bounded (800 MB of int); coarser cells stay exact
+    double f = std::sqrt(nxd * nyd / 2.0e8);
+    width *= f;
+    gp.inv = 1.0 / width;
+    nxd = std::floor((bb[2] - bb[0]) * gp.inv) + 1;
+    nyd = std::floor((bb[3] - bb[1]) * gp.inv) + 1;
+  }
+  gp.nx = (int)nxd;
+  gp.ny = (int)nyd;
+  size_t ncell = (size_t)gp.nx * gp.ny;
+  SLAM_CUDA_TRY(c, c->grid_cell_start.exact(ncell + 1));
+  SLAM_CUDA_TRY(c, c->grid_cursor.exact(ncell + 1));
+  SLAM_CUDA_TRY(c, c->grid_x.exact(M));
+  SLAM_CUDA_TRY(c, c->grid_y.exact(M));
+  SLAM_CUDA_TRY(c, c->grid_ti.exact(M));
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(c->grid_cursor.p, 0, sizeof(int) * (ncell + 1), c->stream));
+  grid_count_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(c->map_x.p, c->map_y.p, M, gp, c->grid_cursor.p);
+  c->launches++;
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->grid_cursor.p, c->grid_cell_start.p, (int)(ncell + 1), c->stream);
+  SLAM_CUDA_TRY(c, c->grid_tmp.exact(tmp_bytes));
+  SLAM_CUDA_TRY(c, cub::DeviceScan::ExclusiveSum(c->grid_tmp.p, tmp_bytes, c->grid_cursor.p, c->grid_cell_start.p,
+                                                  (int)(ncell + 1), c->stream));
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->grid_cursor.p, c->grid_cell_start.p, sizeof(int) * ncell, cudaMemcpyDeviceToDevice, c->stream));
+  grid_fill_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(c->map_x.p, c->map_y.p, c->map_type.p, M, gp,
+                                                          c->grid_cursor.p, c->grid_x.p, c->grid_y.p, c->grid_ti.p);
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->grid_cell = cell;
+  c->grid_x0 = gp.x0;
+  c->grid_y0 = gp.y0;
+  c->grid_nx = gp.nx;
+  c->grid_ny = gp.ny;
+  c->grid_inv = gp.inv;
+  c->grid_map_version = c->map_version;
+  return (int)std::min<size_t>(ncell, 0x7fffffff);
+}
+
+int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, const double pose[3],
+                             double thr, int gate, int algo, int32_t* idx_dev) {
+  if (!c || !pose || n < 0 || (n > 0 && (!cones_dev || !idx_dev))) return SLAM_B200_E_ARG;
+  if (gate != SLAM_B200_GATE_MAPPING && gate != SLAM_B200_GATE_LOCALIZER) return SLAM_B200_E_ARG;
+  if (algo != SLAM_B200_ALGO_BRUTE && algo != SLAM_B200_ALGO_GRID) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n == 0) return 0;
+  PoseTrig pt{pose[0], pose[1], std::cos(pose[2]), std::sin(pose[2])};
+  double thr2x = sqrt_gate_threshold(thr);
+  int blocks = (n + BULK_THREADS - 1) / BULK_THREADS;
+  if (c->map_n == 0 || !(thr > 0)) {
+    SLAM_CUDA_TRY(c, cudaMemsetAsync(idx_dev, 0xff, sizeof(int) * (size_t)n, c->stream));
+    return 0;
+  }
+  if (algo == SLAM_B200_ALGO_BRUTE) {
+    if (gate == SLAM_B200_GATE_MAPPING)
+      assoc_bulk_brute_kernel<SLAM_B200_GATE_MAPPING><<<blocks, BULK_THREADS, 0, c->stream>>>(
+          cones_dev, n, pt, thr2x, c->map_x.p, c->map_y.p, c->map_type.p, c->map_n, idx_dev);
+    else
+      assoc_bulk_brute_kernel<SLAM_B200_GATE_LOCALIZER><<<blocks, BULK_THREADS, 0, c->stream>>>(
+          cones_dev, n, pt, thr2x, c->map_x.p, c->map_y.p, c->map_type.p, c->map_n, idx_dev);
+  } else {
+    if (c->grid_map_version != c->map_version || !(c->grid_cell >= thr)) {
+      int rc = slam_b200_map_build_grid(c, thr);
+      if (rc < 0) return rc;
+    }
+    GridParams gp;
+    gp.x0 = c->grid_x0;
+    gp.y0 = c->grid_y0;
+    gp.nx = c->grid_nx;
+    gp.ny = c->grid_ny;
+    gp.inv = c->grid_inv;  // the exact value the index was built with
+    if (gate == SLAM_B200_GATE_MAPPING)
+      assoc_bulk_grid_kernel<SLAM_B200_GATE_MAPPING><<<blocks, BULK_THREADS, 0, c->stream>>>(
+          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_x.p, c->grid_y.p, c->grid_ti.p, idx_dev);
+    else
+      assoc_bulk_grid_kernel<SLAM_B200_GATE_LOCALIZER><<<blocks, BULK_THREADS, 0, c->stream>>>(
+          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_x.p, c->grid_y.p, c->grid_ti.p, idx_dev);
+  }
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  return 0;
+}
+
+int slam_b200_assoc_bulk(slam_b200_ctx* c, const double* cones, int n, const double pose[3], double thr,
+                         int gate, int algo, int32_t* idx) {
+  if (!c || !pose || n < 0 || (n > 0 && (!cones || !idx))) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n == 0) return 0;
+  SLAM_CUDA_TRY(c, c->frame_in.exact(4 * (size_t)n + 4));
+  SLAM_CUDA_TRY(c, c->frame_outi.exact(2 * (size_t)n + 8));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->frame_in.p, cones, sizeof(double) * 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  int rc = slam_b200_assoc_bulk_dev(c, c->frame_in.p, n, pose, thr, gate, algo, c->frame_outi.p);
+  if (rc < 0) return rc;
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(idx, c->frame_outi.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // extern "C"

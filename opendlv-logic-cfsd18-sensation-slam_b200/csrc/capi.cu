@@ -1,0 +1,680 @@
+// capi.cu -- context management and the graph half of the C ABI (include/slam_b200.h).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <map>
+
+#include "graph_dev.h"
+
+int ctx_set_device(slam_b200_ctx* c) {
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) {
+    c->fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return SLAM_B200_E_CUDA;
+  }
+  return 0;
+}
+
+namespace {
+
+// g2o stuff/misc.h normalize_theta and types/slam2d/se2.h inverse()/operator* on the host: only
+// used to form the odometry measurement when a pose is added (Slam::addOdometryMeasurement,
+// slam.cpp:452-455) -- graph construction, not the hot path.
+double normalize_theta_host(double theta) {
+  if (theta >= -M_PI && theta < M_PI) return theta;
+  double multiplier = std::floor(theta / (2 * M_PI));
+  theta = theta - multiplier * 2 * M_PI;
+  if (theta >= M_PI) theta -= 2 * M_PI;
+  if (theta < -M_PI) theta += 2 * M_PI;
+  return theta;
+}
+void se2_between(const double* prev, const double* cur, double* z) {
+  double ith = normalize_theta_host(-prev[2]);
+  double s = std::sin(ith), c = std::cos(ith);
+  double itx = c * (-1 * prev[0]) - s * (-1 * prev[1]);
+  double ity = s * (-1 * prev[0]) + c * (-1 * prev[1]);
+  z[0] = itx + (c * cur[0] - s * cur[1]);
+  z[1] = ity + (s * cur[0] + c * cur[1]);
+  z[2] = normalize_theta_host(ith + cur[2]);
+}
+
+int lookup(slam_b200_ctx* c, int id, bool want_lm, int* local) {
+  auto it = c->g.id2v.find(id);
+  if (it == c->g.id2v.end()) return SLAM_B200_E_ARG;
+  if (((it->second & 1) != 0) != want_lm) return SLAM_B200_E_ARG;
+  *local = it->second >> 1;
+  return 0;
+}
+
+int refresh_host_estimates(slam_b200_ctx* c) {  // device replica 0 -> host graph
+  DeviceSystem& D = *c->sys;
+  HostGraph& g = c->g;
+  size_t ne = (size_t)D.estStride;
+  if (!ne) return 0;
+  SLAM_CUDA_TRY(c, c->pin_d.reserve(ne));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, D.est.p, sizeof(double) * ne, cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  const double* e = c->pin_d.p;
+  const int P = D.P, L = D.L;
+  for (int p = 0; p < P; p++) {
+    g.pose_est[3 * (size_t)p] = e[p];
+    g.pose_est[3 * (size_t)p + 1] = e[P + p];
+    g.pose_est[3 * (size_t)p + 2] = e[2 * (size_t)P + p];
+  }
+  for (int l = 0; l < L; l++) {
+    g.lm_est[2 * (size_t)l] = e[3 * (size_t)P + l];
+    g.lm_est[2 * (size_t)l + 1] = e[3 * (size_t)P + L + l];
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int slam_b200_version(void) { return 100; }
+
+int slam_b200_create(int device, void* stream, slam_b200_ctx** out) {
+  if (!out) return SLAM_B200_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SLAM_B200_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SLAM_B200_E_CUDA;
+  slam_b200_ctx* c = new slam_b200_ctx();
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return SLAM_B200_E_CUDA;
+    }
+    c->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  *out = c;
+  return 0;
+}
+
+int slam_b200_destroy(slam_b200_ctx* c) {
+  if (!c) return SLAM_B200_E_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  graph_release(c);
+  c->map_x.release(); c->map_y.release(); c->map_type.release();
+  c->grid_cell_start.release(); c->grid_cursor.release(); c->grid_x.release(); c->grid_y.release();
+  c->grid_ti.release(); c->grid_bbox.release(); c->grid_tmp.release();
+  c->frame_in.release(); c->frame_outd.release(); c->frame_outi.release();
+  c->pin_d.release(); c->pin_i.release();
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+const char* slam_b200_last_error(const slam_b200_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int slam_b200_sync(slam_b200_ctx* c) {
+  if (!c) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+long slam_b200_launch_count(slam_b200_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// graph construction (host mirror; uploaded by prepare)
+// ------------------------------------------------------------------------------------------------
+int slam_b200_graph_clear(slam_b200_ctx* c) {
+  if (!c) return SLAM_B200_E_ARG;
+  uint64_t sv = c->g.structure_version + 1, vv = c->g.values_version + 1;
+  c->g = HostGraph();
+  c->g.structure_version = sv;
+  c->g.values_version = vv;
+  return 0;
+}
+
+int slam_b200_graph_add_pose(slam_b200_ctx* c, int id, double x, double y, double theta) {
+  if (!c) return SLAM_B200_E_ARG;
+  HostGraph& g = c->g;
+  if (g.id2v.count(id)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+  g.id2v[id] = g.P() << 1;
+  g.pose_id.push_back(id);
+  g.pose_est.push_back(x); g.pose_est.push_back(y); g.pose_est.push_back(theta);
+  g.pose_fixed.push_back(0);
+  g.structure_version++;
+  g.values_version++;
+  return 0;
+}
+
+int slam_b200_graph_add_landmark(slam_b200_ctx* c, int id, double x, double y) {
+  if (!c) return SLAM_B200_E_ARG;
+  HostGraph& g = c->g;
+  if (g.id2v.count(id)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+  g.id2v[id] = (g.L() << 1) | 1;
+  g.lm_id.push_back(id);
+  g.lm_est.push_back(x); g.lm_est.push_back(y);
+  g.lm_fixed.push_back(0);
+  g.structure_version++;
+  g.values_version++;
+  return 0;
+}
+
+int slam_b200_graph_add_edge_se2(slam_b200_ctx* c, int id_from, int id_to, const double z[3], const double info[9]) {
+  if (!c || !z || !info) return SLAM_B200_E_ARG;
+  int i, j;
+  if (lookup(c, id_from, false, &i) || lookup(c, id_to, false, &j) || i == j) {
+    c->fail("EdgeSE2: unknown or identical pose ids");
+    return SLAM_B200_E_ARG;
+  }
+  HostGraph& g = c->g;
+  g.eo_i.push_back(i);
+  g.eo_j.push_back(j);
+  for (int k = 0; k < 3; k++) g.eo_z.push_back(z[k]);
+  // information matrices are symmetric; the upper triangle is kept
+  g.eo_info.push_back(info[0]); g.eo_info.push_back(info[1]); g.eo_info.push_back(info[2]);
+  g.eo_info.push_back(info[4]); g.eo_info.push_back(info[5]); g.eo_info.push_back(info[8]);
+  g.structure_version++;
+  g.values_version++;
+  return 0;
+}
+
+int slam_b200_graph_add_odometry(slam_b200_ctx* c, int id_prev, int id_cur, const double pose[3], const double info[9]) {
+  if (!c || !pose || !info) return SLAM_B200_E_ARG;
+  int i;
+  if (lookup(c, id_prev, false, &i)) { c->fail("odometry: unknown previous pose"); return SLAM_B200_E_ARG; }
+  double z[3];
+  se2_between(&c->g.pose_est[3 * (size_t)i], pose, z);
+  return slam_b200_graph_add_edge_se2(c, id_prev, id_cur, z, info);
+}
+
+int slam_b200_graph_add_edge_se2_xy(slam_b200_ctx* c, int pose_id, int landmark_id, const double z[2], const double info[4]) {
+  if (!c || !z || !info) return SLAM_B200_E_ARG;
+  int p, l;
+  if (lookup(c, pose_id, false, &p) || lookup(c, landmark_id, true, &l)) {
+    c->fail("EdgeSE2PointXY: unknown pose or landmark id");
+    return SLAM_B200_E_ARG;
+  }
+  HostGraph& g = c->g;
+  g.el_p.push_back(p);
+  g.el_l.push_back(l);
+  g.el_z.push_back(z[0]); g.el_z.push_back(z[1]);
+  g.el_info.push_back(info[0]); g.el_info.push_back(info[1]); g.el_info.push_back(info[3]);
+  g.structure_version++;
+  g.values_version++;
+  return 0;
+}
+
+int slam_b200_graph_set_fixed(slam_b200_ctx* c, int id, int fixed) {
+  if (!c) return SLAM_B200_E_ARG;
+  auto it = c->g.id2v.find(id);
+  if (it == c->g.id2v.end()) { c->fail("setFixed: unknown id"); return SLAM_B200_E_ARG; }
+  char f = fixed ? 1 : 0;
+  char& cur = (it->second & 1) ? c->g.lm_fixed[it->second >> 1] : c->g.pose_fixed[it->second >> 1];
+  if (cur != f) {
+    cur = f;
+    c->g.structure_version++;
+  }
+  return 0;
+}
+
+int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids, const double* pose_est3,
+                         int n_landmarks, const int32_t* lm_ids, const double* lm_est2, int n_eo,
+                         const int32_t* eo_from, const int32_t* eo_to, const double* eo_z3, const double* eo_info9,
+                         int n_el, const int32_t* el_pose, const int32_t* el_lm, const double* el_z2,
+                         const double* el_info4, int n_fixed, const int32_t* fixed_ids) {
+  if (!c || n_poses < 0 || n_landmarks < 0 || n_eo < 0 || n_el < 0 || n_fixed < 0) return SLAM_B200_E_ARG;
+  slam_b200_graph_clear(c);
+  HostGraph& g = c->g;
+  g.id2v.reserve((size_t)n_poses + n_landmarks);
+  g.pose_id.assign(pose_ids, pose_ids + n_poses);
+  g.pose_est.assign(pose_est3, pose_est3 + 3 * (size_t)n_poses);
+  g.pose_fixed.assign(n_poses, 0);
+  g.lm_id.assign(lm_ids, lm_ids + n_landmarks);
+  g.lm_est.assign(lm_est2, lm_est2 + 2 * (size_t)n_landmarks);
+  g.lm_fixed.assign(n_landmarks, 0);
+  for (int p = 0; p < n_poses; p++)
+    if (!g.id2v.emplace(pose_ids[p], p << 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+  for (int l = 0; l < n_landmarks; l++)
+    if (!g.id2v.emplace(lm_ids[l], (l << 1) | 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+  g.eo_i.resize(n_eo); g.eo_j.resize(n_eo);
+  g.eo_z.assign(eo_z3, eo_z3 + 3 * (size_t)n_eo);
+  g.eo_info.resize(6 * (size_t)n_eo);
+  for (int e = 0; e < n_eo; e++) {
+    int i, j;
+    if (lookup(c, eo_from[e], false, &i) || lookup(c, eo_to[e], false, &j) || i == j) {
+      c->fail("EdgeSE2: unknown or identical pose ids");
+      return SLAM_B200_E_ARG;
+    }
+    g.eo_i[e] = i; g.eo_j[e] = j;
+    const double* in = eo_info9 + 9 * (size_t)e;
+    double* o = &g.eo_info[6 * (size_t)e];
+    o[0] = in[0]; o[1] = in[1]; o[2] = in[2]; o[3] = in[4]; o[4] = in[5]; o[5] = in[8];
+  }
+  g.el_p.resize(n_el); g.el_l.resize(n_el);
+  g.el_z.assign(el_z2, el_z2 + 2 * (size_t)n_el);
+  g.el_info.resize(3 * (size_t)n_el);
+  for (int e = 0; e < n_el; e++) {
+    int p, l;
+    if (lookup(c, el_pose[e], false, &p) || lookup(c, el_lm[e], true, &l)) {
+      c->fail("EdgeSE2PointXY: unknown pose or landmark id");
+      return SLAM_B200_E_ARG;
+    }
+    g.el_p[e] = p; g.el_l[e] = l;
+    const double* in = el_info4 + 4 * (size_t)e;
+    double* o = &g.el_info[3 * (size_t)e];
+    o[0] = in[0]; o[1] = in[1]; o[2] = in[3];
+  }
+  for (int k = 0; k < n_fixed; k++) {
+    int rc = slam_b200_graph_set_fixed(c, fixed_ids[k], 1);
+    if (rc) return rc;
+  }
+  g.structure_version++;
+  g.values_version++;
+  return 0;
+}
+
+int slam_b200_graph_set_values(slam_b200_ctx* c, const double* pose_est3, const double* lm_est2,
+                               const double* eo_z3, const double* el_z2) {
+  if (!c) return SLAM_B200_E_ARG;
+  HostGraph& g = c->g;
+  if (pose_est3) std::copy(pose_est3, pose_est3 + 3 * (size_t)g.P(), g.pose_est.begin());
+  if (lm_est2) std::copy(lm_est2, lm_est2 + 2 * (size_t)g.L(), g.lm_est.begin());
+  if (eo_z3) std::copy(eo_z3, eo_z3 + 3 * (size_t)g.Eo(), g.eo_z.begin());
+  if (el_z2) std::copy(el_z2, el_z2 + 2 * (size_t)g.El(), g.el_z.begin());
+  g.values_version++;
+  return 0;
+}
+
+int slam_b200_graph_num_poses(slam_b200_ctx* c) { return c ? c->g.P() : SLAM_B200_E_ARG; }
+int slam_b200_graph_num_landmarks(slam_b200_ctx* c) { return c ? c->g.L() : SLAM_B200_E_ARG; }
+int slam_b200_graph_num_edges(slam_b200_ctx* c) { return c ? c->g.Eo() + c->g.El() : SLAM_B200_E_ARG; }
+
+int slam_b200_graph_get_vertex(slam_b200_ctx* c, int id, double out[3]) {
+  if (!c || !out) return SLAM_B200_E_ARG;
+  auto it = c->g.id2v.find(id);
+  if (it == c->g.id2v.end()) return SLAM_B200_E_ARG;
+  int k = it->second >> 1;
+  if (it->second & 1) {
+    out[0] = c->g.lm_est[2 * (size_t)k]; out[1] = c->g.lm_est[2 * (size_t)k + 1]; out[2] = 0;
+    return 2;
+  }
+  out[0] = c->g.pose_est[3 * (size_t)k]; out[1] = c->g.pose_est[3 * (size_t)k + 1]; out[2] = c->g.pose_est[3 * (size_t)k + 2];
+  return 3;
+}
+
+int slam_b200_graph_get_estimates(slam_b200_ctx* c, double* pose_est3, double* lm_est2) {
+  if (!c) return SLAM_B200_E_ARG;
+  if (pose_est3) std::copy(c->g.pose_est.begin(), c->g.pose_est.end(), pose_est3);
+  if (lm_est2) std::copy(c->g.lm_est.begin(), c->g.lm_est.end(), lm_est2);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimisation
+// ------------------------------------------------------------------------------------------------
+int slam_b200_graph_prepare(slam_b200_ctx* c) {
+  if (!c) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  int n = graph_build_structure(c);
+  if (n < 0) return n;
+  DeviceSystem& D = *c->sys;
+  if (D.R != 1 || D.values_version != c->g.values_version) {
+    int rc = graph_alloc_values(c, 1);
+    if (rc) return rc;
+    rc = graph_upload_host_values(c);
+    if (rc) return rc;
+  }
+  return n;
+}
+
+int slam_b200_graph_reset_device(slam_b200_ctx* c) {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  int rc = graph_alloc_values(c, 1);
+  if (rc) return rc;
+  return graph_upload_host_values(c);
+}
+
+int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) {
+  if (!c || !c->sys || iters < 0) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  if (D.n == 0) return 0;
+  for (int it = 0; it < iters; it++) {
+    int rc = graph_enqueue_assemble(c, 0, D.P, false);
+    if (rc) return rc;
+    rc = graph_enqueue_solve(c);
+    if (rc) return rc;
+  }
+  D.iters_enqueued += iters;
+  return 0;
+}
+
+int slam_b200_graph_finish(slam_b200_ctx* c, double* chi2, int chi2_cap) {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  if (D.n == 0) return -1;
+  // chi2 after the last update (g2o verbose: computeActiveErrors after every iteration)
+  int rc = graph_enqueue_assemble(c, 0, D.P, true);
+  if (rc) return rc;
+  int st[2];
+  double ch[64];
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(st, D.status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(ch, D.chi2.p, sizeof(double) * D.chi2_cap, cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  rc = refresh_host_estimates(c);
+  if (rc) return rc;
+  c->g.values_version++;
+  D.values_version = c->g.values_version;  // device and host agree again
+  int done = st[1];
+  if (chi2)
+    for (int k = 0; k < done && k < chi2_cap && k + 1 < D.chi2_cap; k++) chi2[k] = ch[k + 1];
+  int failed = st[0];
+  // next round of iterations starts a fresh chi2 log / status
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)D.R, c->stream));
+  D.chi2_slots = 0;
+  D.iters_enqueued = 0;
+  if (failed) return 0;
+  return done;
+}
+
+int slam_b200_graph_optimize(slam_b200_ctx* c, int iters, double* chi2) {
+  if (!c || iters < 0) return SLAM_B200_E_ARG;
+  int n = slam_b200_graph_prepare(c);
+  if (n < 0) return n;
+  if (n == 0) return -1;  // g2o: nothing to optimise
+  int rc = slam_b200_graph_iterate_async(c, iters);
+  if (rc) return rc;
+  return slam_b200_graph_finish(c, chi2, iters);
+}
+
+int slam_b200_graph_chi2(slam_b200_ctx* c, double* chi2) {
+  if (!c || !chi2) return SLAM_B200_E_ARG;
+  int n = slam_b200_graph_prepare(c);
+  if (n < 0) return n;
+  DeviceSystem& D = *c->sys;
+  int slot = D.chi2_slots;
+  int rc = graph_enqueue_assemble(c, 0, D.P, true);
+  if (rc) return rc;
+  D.chi2_slots = slot;  // do not disturb the iteration log
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(chi2, D.chi2.p + slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int slam_b200_graph_assemble_async(slam_b200_ctx* c, int p0, int p1) {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
+  int slot = D.chi2_slots;
+  int rc = graph_enqueue_assemble(c, p0, p1, false);
+  D.chi2_slots = slot;
+  return rc;
+}
+
+long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) {
+  if (!c || !c->sys || !ptr) return SLAM_B200_E_STATE;
+  DeviceSystem& D = *c->sys;
+  *ptr = D.V.p;
+  if (which == 0) return 6L * D.L;
+  if (which == 1) return D.nV;
+  if (which == 2) { *ptr = D.x.p; return D.n; }
+  return SLAM_B200_E_ARG;
+}
+
+int slam_b200_graph_solve_async(slam_b200_ctx* c) {
+  if (!c || !c->sys || !c->sys->assembled) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  return graph_enqueue_solve(c);
+}
+
+long slam_b200_graph_export_system(slam_b200_ctx* c, int* n_out, int32_t* Ap, int32_t* Ai, double* Ax, double* b) {
+  if (!c || !n_out) return SLAM_B200_E_ARG;
+  int n = slam_b200_graph_prepare(c);
+  if (n < 0) return n;
+  DeviceSystem& D = *c->sys;
+  *n_out = D.n;
+  // scalar upper-triangular CSC in g2o order, built from the block list
+  std::vector<std::map<int, std::pair<long, int>>> cols(D.n);  // col -> row -> (V offset, unused)
+  auto dimOf = [&](int b) { return (D.blk_kind_local[b] & 1) ? 2 : 3; };
+  for (int bb = 0; bb < D.nb; bb++) {
+    int d = dimOf(bb), h = D.blk_hidx[bb];
+    for (int i = 0; i < d; i++)
+      for (int j = i; j < d; j++) cols[h + j][h + i] = {D.hoff_diag[bb] + i * d + j, 0};
+  }
+  for (size_t k = 0; k < D.off_a.size(); k++) {
+    int a = D.off_a[k], bb = D.off_b[k];
+    int da = dimOf(a), db = dimOf(bb), ha = D.blk_hidx[a], hb = D.blk_hidx[bb];
+    for (int i = 0; i < da; i++)
+      for (int j = 0; j < db; j++) cols[hb + j][ha + i] = {D.hoff_off[k] + i * db + j, 0};
+  }
+  long nnz = 0;
+  for (auto& cm : cols) nnz += (long)cm.size();
+  if (!Ai) return nnz;
+  int slot = D.chi2_slots;
+  int rc = graph_enqueue_assemble(c, 0, D.P, false);
+  D.chi2_slots = slot;
+  if (rc) return rc;
+  std::vector<double> V(D.nV);
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(V.data(), D.V.p, sizeof(double) * D.nV, cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  long q = 0;
+  for (int j = 0; j < D.n; j++) {
+    Ap[j] = (int)q;
+    for (auto& kv : cols[j]) {
+      Ai[q] = kv.first;
+      Ax[q] = V[kv.second.first];
+      q++;
+    }
+  }
+  Ap[D.n] = (int)q;
+  if (b)
+    for (int bb = 0; bb < D.nb; bb++) {
+      int kl = D.blk_kind_local[bb], h = D.blk_hidx[bb];
+      if (kl & 1) {
+        b[h] = V[2 * (size_t)(kl >> 1)];
+        b[h + 1] = V[2 * (size_t)(kl >> 1) + 1];
+      } else {
+        for (int k = 0; k < 3; k++) b[h + k] = V[6 * (size_t)D.L + 3 * (size_t)(kl >> 1) + k];
+      }
+    }
+  return nnz;
+}
+
+int slam_b200_graph_stats(slam_b200_ctx* c, double out[16]) {
+  if (!c || !c->sys || !out) return SLAM_B200_E_STATE;
+  DeviceSystem& D = *c->sys;
+  for (int k = 0; k < 16; k++) out[k] = 0;
+  out[0] = D.n; out[1] = D.nb; out[2] = D.sym.nf; out[3] = D.sym.nlevels;
+  long nnzH = 0;
+  for (int b = 0; b < D.nb; b++) { int d = (D.blk_kind_local[b] & 1) ? 2 : 3; nnzH += d * (d + 1) / 2; }
+  for (size_t k = 0; k < D.off_a.size(); k++)
+    nnzH += ((D.blk_kind_local[D.off_a[k]] & 1) ? 2 : 3) * ((D.blk_kind_local[D.off_b[k]] & 1) ? 2 : 3);
+  out[4] = (double)nnzH; out[5] = (double)D.sym.nnzL; out[6] = D.sym.flops; out[7] = D.sym.max_front;
+  out[8] = (double)(D.nL + D.nU); out[9] = D.sym.seconds; out[10] = D.upload_seconds;
+  out[11] = (double)D.nV; out[12] = (double)D.nFbig; out[13] = (double)D.off_a.size();
+  return 0;
+}
+
+long slam_b200_graph_export_symbolic(slam_b200_ctx* c, int what, int32_t* out, long cap);
+
+// ---- symbolic analysis without a device (host logic; testable on a CPU-only box) ----------------
+struct SymHandle {
+  Symbolic S;
+  std::vector<int> hoff_diag, hoff_off;
+};
+
+void* slam_b200_symbolic_create(int nb, const int32_t* dim, int n_pairs, const int32_t* a, const int32_t* b,
+                                int leaf_size) {
+  if (nb < 0 || n_pairs < 0 || (nb > 0 && !dim) || (n_pairs > 0 && (!a || !b))) return nullptr;
+  SymHandle* h = new SymHandle();
+  int cur = 0;
+  h->hoff_diag.resize(nb);
+  for (int k = 0; k < nb; k++) { h->hoff_diag[k] = cur; cur += dim[k] * dim[k]; }
+  h->hoff_off.resize(n_pairs);
+  for (int k = 0; k < n_pairs; k++) { h->hoff_off[k] = cur; cur += dim[a[k]] * dim[b[k]]; }
+  symbolic_analyze(nb, dim, n_pairs, a, b, h->hoff_diag.data(), h->hoff_off.data(), leaf_size, h->S);
+  return h;
+}
+void slam_b200_symbolic_destroy(void* h) { delete static_cast<SymHandle*>(h); }
+
+static long export_symbolic(const Symbolic& S, const std::vector<int>* blk_hidx, int what, int32_t* out, long cap) {
+  std::vector<int> tmp;
+  const std::vector<int>* v = nullptr;
+  switch (what) {
+    case 0: tmp = {S.nb, S.n, S.nf, S.nlevels, (int)S.upd_rows.size(), (int)S.asm_entries.size(), S.max_front}; v = &tmp; break;
+    case 1: v = &S.pos; break;
+    case 2: v = &S.boff; break;
+    case 3: v = &S.level_ptr; break;
+    case 4: v = &S.piv0; break;
+    case 5: v = &S.npiv; break;
+    case 6: v = &S.nupd; break;
+    case 7: v = &S.parent; break;
+    case 8: v = &S.rows_ptr; break;
+    case 9: v = &S.upd_rows; break;
+    case 10: v = &S.rel; break;
+    case 11: v = &S.asm_ptr; break;
+    case 12:
+      for (auto& e : S.asm_entries) { tmp.push_back(e.hoff); tmp.push_back(e.r); tmp.push_back(e.c); tmp.push_back(e.meta); }
+      v = &tmp;
+      break;
+    case 13: if (!blk_hidx) return SLAM_B200_E_ARG; v = blk_hidx; break;
+    case 14: v = &S.dim; break;
+    case 15: v = &S.child_ptr; break;
+    case 16: v = &S.children; break;
+    default: return SLAM_B200_E_ARG;
+  }
+  if (out) std::copy(v->begin(), v->begin() + std::min<long>((long)v->size(), cap), out);
+  return (long)v->size();
+}
+long slam_b200_symbolic_export(void* h, int what, int32_t* out, long cap) {
+  if (!h) return SLAM_B200_E_ARG;
+  return export_symbolic(static_cast<SymHandle*>(h)->S, nullptr, what, out, cap);
+}
+double slam_b200_symbolic_stat(void* h, int what) {
+  if (!h) return -1;
+  const Symbolic& S = static_cast<SymHandle*>(h)->S;
+  switch (what) {
+    case 0: return (double)S.nnzL;
+    case 1: return S.flops;
+    case 2: return S.max_front;
+    case 3: return S.seconds;
+    case 4: return (double)(S.lptr[S.nf] + S.uptr[S.nf]);
+    default: return -1;
+  }
+}
+
+long slam_b200_graph_export_symbolic(slam_b200_ctx* c, int what, int32_t* out, long cap) {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  return export_symbolic(c->sys->sym, &c->sys->blk_hidx, what, out, cap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched replicas
+// ------------------------------------------------------------------------------------------------
+int slam_b200_batch_upload(slam_b200_ctx* c, int R, const double* pose_est3, const double* lm_est2,
+                           const double* eo_z3, const double* el_z2) {
+  if (!c || R < 1 || !pose_est3 || !lm_est2 || !eo_z3 || !el_z2) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  int n = graph_build_structure(c);
+  if (n < 0) return n;
+  DeviceSystem& D = *c->sys;
+  int rc = graph_alloc_values(c, R);
+  if (rc) return rc;
+  const int P = D.P, L = D.L, Eo = D.Eo, El = D.El;
+  const size_t ne = (size_t)D.estStride, nm = (size_t)D.measStride;
+  // AoS (caller) -> SoA (device layout) through a pinned staging buffer, a few replicas at a time
+  const int chunk = std::max(1, (int)std::min<size_t>((size_t)R, (64u << 20) / (8 * (ne + nm + 1))));
+  SLAM_CUDA_TRY(c, c->pin_d.reserve((size_t)chunk * (ne + nm)));
+  for (int r0 = 0; r0 < R; r0 += chunk) {
+    int rn = std::min(chunk, R - r0);
+    double* e = c->pin_d.p;
+    double* m = e + (size_t)rn * ne;
+    for (int rr = 0; rr < rn; rr++) {
+      const int r = r0 + rr;
+      double* er = e + (size_t)rr * ne;
+      const double* pe = pose_est3 + (size_t)r * 3 * P;
+      for (int p = 0; p < P; p++) { er[p] = pe[3 * p]; er[P + p] = pe[3 * p + 1]; er[2 * (size_t)P + p] = pe[3 * p + 2]; }
+      const double* le = lm_est2 + (size_t)r * 2 * L;
+      for (int l = 0; l < L; l++) { er[3 * (size_t)P + l] = le[2 * l]; er[3 * (size_t)P + L + l] = le[2 * l + 1]; }
+      double* mr = m + (size_t)rr * nm;
+      const double* lz = el_z2 + (size_t)r * 2 * El;
+      for (int q = 0; q < El; q++) { int o = D.el_perm[q]; mr[q] = lz[2 * (size_t)o]; mr[El + (size_t)q] = lz[2 * (size_t)o + 1]; }
+      const double* oz = eo_z3 + (size_t)r * 3 * Eo;
+      for (int k = 0; k < Eo; k++) {
+        mr[2 * (size_t)El + k] = oz[3 * (size_t)k];
+        mr[2 * (size_t)El + Eo + k] = oz[3 * (size_t)k + 1];
+        mr[2 * (size_t)El + 2 * (size_t)Eo + k] = oz[3 * (size_t)k + 2];
+      }
+    }
+    if (ne) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.est.p + (size_t)r0 * ne, e, sizeof(double) * rn * ne, cudaMemcpyHostToDevice, c->stream));
+    if (nm) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.meas.p + (size_t)r0 * nm, m, sizeof(double) * rn * nm, cudaMemcpyHostToDevice, c->stream));
+    SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
+  D.values_version = 0;  // replica 0 no longer mirrors the host graph
+  return 0;
+}
+
+int slam_b200_batch_iterate_async(slam_b200_ctx* c, int iters) { return slam_b200_graph_iterate_async(c, iters); }
+
+int slam_b200_batch_download(slam_b200_ctx* c, double* pose_est3, double* lm_est2, double* chi2,
+                             int chi2_cap_per_replica, int32_t* iterations_done) {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  const int R = D.R, P = D.P, L = D.L;
+  int rc = graph_enqueue_assemble(c, 0, D.P, true);
+  if (rc) return rc;
+  const size_t ne = (size_t)D.estStride;
+  std::vector<int> st(2 * (size_t)R);
+  std::vector<double> ch((size_t)R * D.chi2_cap);
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(st.data(), D.status.p, sizeof(int) * st.size(), cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(ch.data(), D.chi2.p, sizeof(double) * ch.size(), cudaMemcpyDeviceToHost, c->stream));
+  const int chunk = std::max(1, (int)std::min<size_t>((size_t)R, (64u << 20) / (8 * (ne + 1))));
+  SLAM_CUDA_TRY(c, c->pin_d.reserve((size_t)chunk * ne));
+  for (int r0 = 0; r0 < R; r0 += chunk) {
+    int rn = std::min(chunk, R - r0);
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, D.est.p + (size_t)r0 * ne, sizeof(double) * rn * ne, cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int rr = 0; rr < rn; rr++) {
+      const int r = r0 + rr;
+      const double* er = c->pin_d.p + (size_t)rr * ne;
+      if (pose_est3) {
+        double* pe = pose_est3 + (size_t)r * 3 * P;
+        for (int p = 0; p < P; p++) { pe[3 * p] = er[p]; pe[3 * p + 1] = er[P + p]; pe[3 * p + 2] = er[2 * (size_t)P + p]; }
+      }
+      if (lm_est2) {
+        double* le = lm_est2 + (size_t)r * 2 * L;
+        for (int l = 0; l < L; l++) { le[2 * l] = er[3 * (size_t)P + l]; le[2 * l + 1] = er[3 * (size_t)P + L + l]; }
+      }
+    }
+  }
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < R; r++) {
+    int done = st[2 * r + 1], failed = st[2 * r];
+    if (iterations_done) iterations_done[r] = failed ? 0 : done;
+    if (chi2)
+      for (int k = 0; k < done && k < chi2_cap_per_replica && k + 1 < D.chi2_cap; k++)
+        chi2[(size_t)r * chi2_cap_per_replica + k] = ch[(size_t)r * D.chi2_cap + k + 1];
+  }
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)R, c->stream));
+  D.chi2_slots = 0;
+  D.iters_enqueued = 0;
+  return 0;
+}
+
+int slam_b200_graph_optimize_batch(slam_b200_ctx* c, int R, double* pose_est3, double* lm_est2,
+                                   const double* eo_z3, const double* el_z2, int iters, double* chi2,
+                                   int32_t* iterations_done) {
+  int rc = slam_b200_batch_upload(c, R, pose_est3, lm_est2, eo_z3, el_z2);
+  if (rc) return rc;
+  rc = slam_b200_batch_iterate_async(c, iters);
+  if (rc) return rc;
+  return slam_b200_batch_download(c, pose_est3, lm_est2, chi2, iters, iterations_done);
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// ctx.h -- context object behind the opaque slam_b200_ctx handle (include/slam_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/slam_b200.h"
+#include "symbolic.h"
+
+#define SLAM_CUDA_TRY(ctx, expr)                                                      \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      (ctx)->fail(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+      return SLAM_B200_E_CUDA;                                                        \
+    }                                                                                 \
+  } while (0)
+
+// growable device array; grow() keeps the first `keep` elements
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = cap ? cap : 256;
+    while (ncap < n) ncap *= 2;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p) {
+      e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+      e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) return e;
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = ncap;
+    return cudaSuccess;
+  }
+  cudaError_t exact(size_t n) {  // (re)allocate exactly, contents dropped
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n ? n : 1;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <class T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    size_t ncap = cap ? cap : 1024;
+    while (ncap < n) ncap *= 2;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, ncap * sizeof(T));
+    if (e == cudaSuccess) cap = ncap;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// ---- host-side graph (insertion order preserved; the reference's g2o graph owns the same data) --
+struct HostGraph {
+  // vertices
+  std::vector<int> pose_id, lm_id;
+  std::vector<double> pose_est;  // 3 per pose
+  std::vector<double> lm_est;    // 2 per landmark
+  std::vector<char> pose_fixed, lm_fixed;
+  std::unordered_map<int, int> id2v;  // id -> (local index << 1) | is_landmark
+  // pose-pose edges (EdgeSE2)
+  std::vector<int> eo_i, eo_j;     // local pose indices
+  std::vector<double> eo_z;        // 3 per edge
+  std::vector<double> eo_info;     // 6 per edge: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+  // pose-landmark edges (EdgeSE2PointXY)
+  std::vector<int> el_p, el_l;     // local pose / landmark indices
+  std::vector<double> el_z;        // 2 per edge
+  std::vector<double> el_info;     // 3 per edge: (0,0) (0,1) (1,1)
+  uint64_t structure_version = 1;  // bumped by anything that changes topology / gauge
+  uint64_t values_version = 1;     // bumped by anything that changes numbers on the host
+  int P() const { return (int)pose_id.size(); }
+  int L() const { return (int)lm_id.size(); }
+  int Eo() const { return (int)eo_i.size(); }
+  int El() const { return (int)el_p.size(); }
+};
+
+// ---- device-side system of one topology (see graph.cu / solver.cu) ------------------------------
+struct DeviceSystem;  // defined in graph_dev.h
+
+struct slam_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  long launches = 0;
+  int num_sms = 148;
+  int max_smem_optin = 0;
+
+  // ---- cone map ----
+  DevBuf<double> map_x, map_y;
+  DevBuf<int> map_type;
+  int map_n = 0;
+  uint64_t map_version = 1;
+  // uniform grid index over the map (assoc.cu)
+  DevBuf<int> grid_cell_start;   // ncell + 1
+  DevBuf<int> grid_cursor;       // ncell
+  DevBuf<double> grid_x, grid_y; // cones sorted by cell
+  DevBuf<int2> grid_ti;          // (type, original index) sorted by cell
+  DevBuf<double> grid_bbox;      // 4 doubles: minx, miny, maxx, maxy
+  DevBuf<char> grid_tmp;         // scan workspace
+  double grid_cell = 0, grid_x0 = 0, grid_y0 = 0, grid_inv = 0;
+  int grid_nx = 0, grid_ny = 0;
+  uint64_t grid_map_version = 0;
+
+  // ---- frame staging ----
+  DevBuf<double> frame_in;       // 4n + 3
+  DevBuf<double> frame_outd;     // 5n doubles: z2, g3
+  DevBuf<int> frame_outi;        // 2n + 8 ints
+  PinBuf<double> pin_d;
+  PinBuf<int> pin_i;
+
+  // ---- graph ----
+  HostGraph g;
+  DeviceSystem* sys = nullptr;
+
+  void fail(const std::string& m) { err = m; }
+};
+
+int ctx_set_device(slam_b200_ctx* c);
+void graph_release(slam_b200_ctx* c);  // graph.cu

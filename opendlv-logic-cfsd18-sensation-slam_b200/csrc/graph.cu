@@ -1,0 +1,693 @@
+// graph.cu -- Gauss-Newton linearisation + normal-equation assembly + state update (sm_100a),
+// and the host-side structure pass that prepares them.
+//
+// Replaces g2o's SparseOptimizer::initializeOptimization / buildIndexMapping (active set and
+// Hessian index mapping), BlockSolver::buildStructure (block pattern), BlockSolver::buildSystem
+// (EdgeSE2 / EdgeSE2PointXY computeError + linearizeOplus + BaseBinaryEdge::constructQuadraticForm)
+// , SparseOptimizer::update (VertexSE2 / VertexPointXY oplusImpl) and computeActiveErrors /
+// activeRobustChi2, which the reference reaches from Slam::optimizeGraph (slam.cpp:461-484).
+//
+// Assembly is "owner computes": one thread per pose walks that pose's edges (landmark edges of a
+// pose are contiguous -- performSLAM inserts them per frame), accumulates the pose's diagonal block
+// and rhs in registers and writes every off-diagonal block exactly once; one thread per landmark
+// gathers its diagonal block and rhs over the edges that see it (recomputing the 2x2 part of the
+// linearisation instead of exchanging it through memory).  No atomics, fixed summation order,
+// bit-reproducible run to run.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <unordered_map>
+
+#include "graph_dev.h"
+
+namespace {
+
+__device__ __forceinline__ double normalize_theta_dev(double theta) {  // g2o stuff/misc.h
+  const double pi = 3.14159265358979323846;
+  if (theta >= -pi && theta < pi) return theta;
+  double multiplier = floor(theta / (2 * pi));
+  theta = theta - multiplier * 2 * pi;
+  if (theta >= pi) theta -= 2 * pi;
+  if (theta < -pi) theta += 2 * pi;
+  return theta;
+}
+
+struct AsmArgs {
+  int P, L, Eo, El;
+  long estStride, measStride, nV;
+  const double* est;
+  const double* meas;
+  double* V;
+  const unsigned char* pose_free;
+  const unsigned char* lm_free;
+  const int *el_start, *el_pose, *el_lm, *el_slot, *el_flags;
+  const double* el_info;
+  const int *lm_start, *lm_edges;
+  const int *eo_i, *eo_j, *eo_slot, *eo_flags, *po_start, *po_list;
+  const double* eo_info;
+  double* chi2_part;
+  int chi2_blocks;
+  double* chi2;
+  int chi2_cap, chi2_slot;
+};
+
+constexpr int ASM_THREADS = 128;
+
+template <bool CHI2_ONLY>
+__global__ void __launch_bounds__(ASM_THREADS)
+assemble_pose_kernel(AsmArgs a, int p0, int p1) {
+  const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  const double* est = a.est + (size_t)r * a.estStride;
+  const double* meas = a.meas + (size_t)r * a.measStride;
+  double* V = a.V + (size_t)r * a.nV;
+  const int P = a.P, L = a.L, El = a.El, Eo = a.Eo;
+  double chi = 0;
+  if (p < p1) {
+    const double px = est[p], py = est[P + p], pt = est[2 * P + p];
+    double s, c;
+    sincos(pt, &s, &c);
+    const bool free = a.pose_free[p] != 0;
+    double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
+    // ---- landmark edges of this pose (EdgeSE2PointXY) ----
+    const int e0 = a.el_start[p], e1 = a.el_start[p + 1];
+    for (int e = e0; e < e1; e++) {
+      const int fl = a.el_flags[e];
+      if (!(fl & EF_ACTIVE)) continue;
+      const int l = a.el_lm[e];
+      const double dx = est[3 * P + l] - px, dy = est[3 * P + L + l] - py;
+      const double i00 = a.el_info[e], i01 = a.el_info[El + e], i11 = a.el_info[2 * El + e];
+      const double j02 = -s * dx + c * dy;  // d e_x / d theta
+      const double j12 = -c * dx - s * dy;  // d e_y / d theta
+      const double ex = c * dx + s * dy - meas[e];
+      const double ey = j02 - meas[El + e];
+      chi += ex * (i00 * ex + i01 * ey) + ey * (i01 * ex + i11 * ey);
+      if (CHI2_ONLY || !free) continue;
+      // A = Ji^T Omega, Ji = [[-c, -s, j02], [s, -c, j12]]
+      const double a00 = -c * i00 + s * i01, a01 = -c * i01 + s * i11;
+      const double a10 = -s * i00 - c * i01, a11 = -s * i01 - c * i11;
+      const double a20 = j02 * i00 + j12 * i01, a21 = j02 * i01 + j12 * i11;
+      b0 -= a00 * ex + a01 * ey;
+      b1 -= a10 * ex + a11 * ey;
+      b2 -= a20 * ex + a21 * ey;
+      h00 += a00 * (-c) + a01 * s;
+      h01 += a00 * (-s) + a01 * (-c);
+      h02 += a00 * j02 + a01 * j12;
+      h11 += a10 * (-s) + a11 * (-c);
+      h12 += a10 * j02 + a11 * j12;
+      h22 += a20 * j02 + a21 * j12;
+      if (fl & EF_OFFDIAG) {  // Ji^T Omega Jl, Jl = [[c, s], [-s, c]]
+        double B[6] = {a00 * c - a01 * s, a00 * s + a01 * c, a10 * c - a11 * s,
+                       a10 * s + a11 * c, a20 * c - a21 * s, a20 * s + a21 * c};
+        double* hv = V + a.el_slot[e];
+        double o[6];
+        if (fl & EF_TRANS) {  // stored landmark rows x pose columns (2x3)
+          o[0] = B[0]; o[1] = B[2]; o[2] = B[4]; o[3] = B[1]; o[4] = B[3]; o[5] = B[5];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) o[k] = B[k];
+        }
+        if (fl & EF_FIRST) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) hv[k] = o[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) hv[k] += o[k];
+        }
+      }
+    }
+    // ---- pose-pose edges incident to this pose (EdgeSE2) ----
+    const int q0 = a.po_start[p], q1 = a.po_start[p + 1];
+    for (int q = q0; q < q1; q++) {
+      const int ent = a.po_list[q];
+      const int e = ent >> 1, side = ent & 1;
+      const int fl = a.eo_flags[e];
+      if (!(fl & EF_ACTIVE)) continue;
+      const int i = a.eo_i[e], j = a.eo_j[e];
+      double xi, yi, ti, xj, yj, tj, si, ci;
+      if (side == 0) {
+        xi = px; yi = py; ti = pt; si = s; ci = c;
+        xj = est[j]; yj = est[P + j]; tj = est[2 * P + j];
+      } else {
+        xj = px; yj = py; tj = pt;
+        xi = est[i]; yi = est[P + i]; ti = est[2 * P + i];
+        sincos(ti, &si, &ci);
+      }
+      const double* mo = meas + 2 * (size_t)El;
+      const double zx = mo[e], zy = mo[Eo + e], zt = mo[2 * Eo + e];
+      const double o00 = a.eo_info[e], o01 = a.eo_info[Eo + e], o02 = a.eo_info[2 * Eo + e],
+                   o11 = a.eo_info[3 * Eo + e], o12 = a.eo_info[4 * Eo + e], o22 = a.eo_info[5 * Eo + e];
+      const double dtx = xj - xi, dty = yj - yi;
+      const double tx = ci * dtx + si * dty, ty = -si * dtx + ci * dty;  // R_i^T (t_j - t_i)
+      double sz, cz;
+      sincos(zt, &sz, &cz);
+      double err[3];
+      err[0] = cz * (tx - zx) + sz * (ty - zy);
+      err[1] = -sz * (tx - zx) + cz * (ty - zy);
+      err[2] = normalize_theta_dev(tj - ti - zt);
+      const double Om[3][3] = {{o00, o01, o02}, {o01, o11, o12}, {o02, o12, o22}};
+      double Oe[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) Oe[k] = Om[k][0] * err[0] + Om[k][1] * err[1] + Om[k][2] * err[2];
+      if (side == 0) chi += err[0] * Oe[0] + err[1] * Oe[1] + err[2] * Oe[2];
+      if (CHI2_ONLY) continue;
+      // Ji = Z A, Jj = Z B with Z = diag(R(-zt), 1)
+      const double A0[3] = {-ci, -si, ty}, A1[3] = {si, -ci, -tx};
+      const double B0[3] = {ci, si, 0}, B1[3] = {-si, ci, 0};
+      double Ji[3][3], Jj[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        Ji[0][k] = cz * A0[k] + sz * A1[k];
+        Ji[1][k] = -sz * A0[k] + cz * A1[k];
+        Jj[0][k] = cz * B0[k] + sz * B1[k];
+        Jj[1][k] = -sz * B0[k] + cz * B1[k];
+      }
+      Ji[2][0] = 0; Ji[2][1] = 0; Ji[2][2] = -1;
+      Jj[2][0] = 0; Jj[2][1] = 0; Jj[2][2] = 1;
+      if (free) {
+        double AtO[3][3];  // Jm^T Omega
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+            double jm0 = side == 0 ? Ji[0][k] : Jj[0][k];
+            double jm1 = side == 0 ? Ji[1][k] : Jj[1][k];
+            double jm2 = side == 0 ? Ji[2][k] : Jj[2][k];
+            AtO[k][m] = jm0 * Om[0][m] + jm1 * Om[1][m] + jm2 * Om[2][m];
+          }
+        b0 -= AtO[0][0] * err[0] + AtO[0][1] * err[1] + AtO[0][2] * err[2];
+        b1 -= AtO[1][0] * err[0] + AtO[1][1] * err[1] + AtO[1][2] * err[2];
+        b2 -= AtO[2][0] * err[0] + AtO[2][1] * err[1] + AtO[2][2] * err[2];
+        double Hm[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = k; m < 3; m++) {
+            double v = 0;
+#pragma unroll
+            for (int t = 0; t < 3; t++) v += AtO[k][t] * (side == 0 ? Ji[t][m] : Jj[t][m]);
+            Hm[k][m] = v;
+          }
+        h00 += Hm[0][0]; h01 += Hm[0][1]; h02 += Hm[0][2];
+        h11 += Hm[1][1]; h12 += Hm[1][2]; h22 += Hm[2][2];
+      }
+      if ((fl & EF_OFFDIAG) && p == min(i, j)) {  // Ji^T Omega Jj, written by one owner thread
+        double AtO[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = 0; m < 3; m++)
+            AtO[k][m] = Ji[0][k] * Om[0][m] + Ji[1][k] * Om[1][m] + Ji[2][k] * Om[2][m];
+        double* hv = V + a.eo_slot[e];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+            double v = AtO[k][0] * Jj[0][m] + AtO[k][1] * Jj[1][m] + AtO[k][2] * Jj[2][m];
+            int o = (fl & EF_TRANS) ? (m * 3 + k) : (k * 3 + m);
+            if (fl & EF_FIRST) hv[o] = v;
+            else hv[o] += v;
+          }
+      }
+    }
+    if (!CHI2_ONLY && free) {
+      double* bp = V + 6 * (size_t)L + 3 * (size_t)p;
+      bp[0] = b0; bp[1] = b1; bp[2] = b2;
+      double* hp = V + 6 * (size_t)L + 3 * (size_t)P + 9 * (size_t)p;
+      hp[0] = h00; hp[1] = h01; hp[2] = h02;
+      hp[3] = h01; hp[4] = h11; hp[5] = h12;
+      hp[6] = h02; hp[7] = h12; hp[8] = h22;
+    }
+  }
+  // chi2: fixed-order block reduction -> one partial per block
+  __shared__ double red[ASM_THREADS / 32];
+  for (int o = 16; o; o >>= 1) chi += __shfl_down_sync(0xffffffffu, chi, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = chi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < ASM_THREADS / 32; w++) t += red[w];
+    a.chi2_part[(size_t)r * a.chi2_blocks + blockIdx.x] = t;
+  }
+}
+
+// one thread per landmark: diagonal block + rhs over the edges (with pose in [p0,p1)) that see it
+template <bool CHI2_ONLY>
+__global__ void __launch_bounds__(ASM_THREADS)
+assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  const double* est = a.est + (size_t)r * a.estStride;
+  const double* meas = a.meas + (size_t)r * a.measStride;
+  double* V = a.V + (size_t)r * a.nV;
+  const int P = a.P, L = a.L, El = a.El;
+  if (!CHI2_ONLY && l < L && a.lm_free[l]) {
+    const double lx = est[3 * P + l], ly = est[3 * P + L + l];
+    double h00 = 0, h01 = 0, h11 = 0, b0 = 0, b1 = 0;
+    const int q0 = a.lm_start[l], q1 = a.lm_start[l + 1];
+    for (int q = q0; q < q1; q++) {
+      const int e = a.lm_edges[q];
+      if (!(a.el_flags[e] & EF_ACTIVE)) continue;
+      const int p = a.el_pose[e];
+      if (p < p0 || p >= p1) continue;
+      double s, c;
+      sincos(est[2 * P + p], &s, &c);
+      const double dx = lx - est[p], dy = ly - est[P + p];
+      const double ex = c * dx + s * dy - meas[e];
+      const double ey = -s * dx + c * dy - meas[El + e];
+      const double i00 = a.el_info[e], i01 = a.el_info[El + e], i11 = a.el_info[2 * El + e];
+      // A = Jl^T Omega, Jl = [[c, s], [-s, c]]
+      const double a00 = c * i00 - s * i01, a01 = c * i01 - s * i11;
+      const double a10 = s * i00 + c * i01, a11 = s * i01 + c * i11;
+      b0 -= a00 * ex + a01 * ey;
+      b1 -= a10 * ex + a11 * ey;
+      h00 += a00 * c - a01 * s;
+      h01 += a00 * s + a01 * c;
+      h11 += a10 * s + a11 * c;
+    }
+    double* bl = V + 2 * (size_t)l;
+    bl[0] = b0; bl[1] = b1;
+    double* hl = V + 2 * (size_t)L + 4 * (size_t)l;
+    hl[0] = h00; hl[1] = h01; hl[2] = h01; hl[3] = h11;
+  }
+  // final chi2 of this replica: fixed-order sum of the pose kernel's block partials
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    double t = 0;
+    for (int k = threadIdx.x; k < chi2_nblocks; k += 32) t += a.chi2_part[(size_t)r * a.chi2_blocks + k];
+    for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0 && a.chi2_slot < a.chi2_cap) a.chi2[(size_t)r * a.chi2_cap + a.chi2_slot] = t;
+  }
+}
+
+// SparseOptimizer::update: VertexSE2::oplusImpl (additive, normalised angle) / VertexPointXY
+__global__ void update_kernel(int P, int L, long estStride, double* est_all, const double* x_all, int n,
+                              const int* __restrict__ pose_boff, const int* __restrict__ lm_boff,
+                              int* status) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (status[2 * r] != 0) return;  // factorisation failed: leave the state alone
+  double* est = est_all + (size_t)r * estStride;
+  const double* x = x_all + (size_t)r * n;
+  if (v < P) {
+    int o = pose_boff[v];
+    if (o >= 0) {
+      est[v] += x[o];
+      est[P + v] += x[o + 1];
+      est[2 * P + v] = normalize_theta_dev(est[2 * P + v] + x[o + 2]);
+    }
+  } else if (v < P + L) {
+    int l = v - P;
+    int o = lm_boff[l];
+    if (o >= 0) {
+      est[3 * P + l] += x[o];
+      est[3 * P + L + l] += x[o + 1];
+    }
+  }
+  if (v == 0) status[2 * r + 1] += 1;
+}
+
+template <class T>
+int upload_vec(slam_b200_ctx* c, DevBuf<T>& d, const std::vector<T>& h) {
+  SLAM_CUDA_TRY(c, d.exact(h.size()));
+  if (!h.empty())
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(d.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+}  // namespace
+
+int graph_enqueue_update(slam_b200_ctx* c) {
+  DeviceSystem& D = *c->sys;
+  int nv = D.P + D.L;
+  dim3 grid((nv + 255) / 256, D.R);
+  update_kernel<<<grid, 256, 0, c->stream>>>(D.P, D.L, D.estStride, D.est.p, D.x.p, D.n, D.pose_boff.p,
+                                            D.lm_boff.p, D.status.p);
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  return 0;
+}
+
+int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
+  DeviceSystem& D = *c->sys;
+  AsmArgs a;
+  a.P = D.P; a.L = D.L; a.Eo = D.Eo; a.El = D.El;
+  a.estStride = D.estStride; a.measStride = D.measStride; a.nV = D.nV;
+  a.est = D.est.p; a.meas = D.meas.p; a.V = D.V.p;
+  a.pose_free = D.pose_free.p; a.lm_free = D.lm_free.p;
+  a.el_start = D.el_start.p; a.el_pose = D.el_pose.p; a.el_lm = D.el_lm.p; a.el_slot = D.el_slot.p;
+  a.el_flags = D.el_flags.p; a.el_info = D.el_info.p;
+  a.lm_start = D.lm_start.p; a.lm_edges = D.lm_edges.p;
+  a.eo_i = D.eo_i.p; a.eo_j = D.eo_j.p; a.eo_slot = D.eo_slot.p; a.eo_flags = D.eo_flags.p;
+  a.po_start = D.po_start.p; a.po_list = D.po_list.p; a.eo_info = D.eo_info.p;
+  a.chi2_part = D.chi2_part.p; a.chi2_blocks = D.chi2_blocks;
+  a.chi2 = D.chi2.p; a.chi2_cap = D.chi2_cap; a.chi2_slot = D.chi2_slots;
+  int np = std::max(0, p1 - p0);
+  int nblk = (np + ASM_THREADS - 1) / ASM_THREADS;
+  if (nblk > 0) {
+    dim3 grid(nblk, D.R);
+    if (chi2_only) assemble_pose_kernel<true><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
+    else assemble_pose_kernel<false><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
+    c->launches++;
+  }
+  dim3 gl(std::max(1, (D.L + ASM_THREADS - 1) / ASM_THREADS), D.R);
+  if (chi2_only) assemble_landmark_kernel<true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk);
+  else assemble_landmark_kernel<false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk);
+  c->launches++;
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  D.chi2_slots++;
+  if (!chi2_only) D.assembled = true;
+  return 0;
+}
+
+// ================================================================================================
+// host structure pass
+// ================================================================================================
+int graph_build_structure(slam_b200_ctx* c) {
+  HostGraph& g = c->g;
+  if (!c->sys) c->sys = new DeviceSystem();
+  DeviceSystem& D = *c->sys;
+  if (D.structure_version == g.structure_version) return D.n;
+  auto t0 = std::chrono::steady_clock::now();
+  const int P = g.P(), L = g.L(), Eo = g.Eo(), El = g.El();
+  D.P = P; D.L = L; D.Eo = Eo; D.El = El;
+  // ---- active set (initializeOptimization): edges whose vertices are not all fixed ----
+  std::vector<char> pose_act(P, 0), lm_act(L, 0);
+  std::vector<int> el_flags(El, 0), eo_flags(Eo, 0);
+  for (int e = 0; e < El; e++)
+    if (!(g.pose_fixed[g.el_p[e]] && g.lm_fixed[g.el_l[e]])) {
+      el_flags[e] = EF_ACTIVE;
+      pose_act[g.el_p[e]] = 1;
+      lm_act[g.el_l[e]] = 1;
+    }
+  for (int e = 0; e < Eo; e++)
+    if (!(g.pose_fixed[g.eo_i[e]] && g.pose_fixed[g.eo_j[e]])) {
+      eo_flags[e] = EF_ACTIVE;
+      pose_act[g.eo_i[e]] = pose_act[g.eo_j[e]] = 1;
+    }
+  // ---- Hessian index mapping (buildIndexMapping): non-fixed active vertices by ascending id ----
+  std::vector<std::pair<int, int>> byId;  // (id, (local<<1)|is_lm)
+  for (int p = 0; p < P; p++)
+    if (pose_act[p] && !g.pose_fixed[p]) byId.push_back({g.pose_id[p], p << 1});
+  for (int l = 0; l < L; l++)
+    if (lm_act[l] && !g.lm_fixed[l]) byId.push_back({g.lm_id[l], (l << 1) | 1});
+  std::sort(byId.begin(), byId.end());
+  const int nb = (int)byId.size();
+  D.nb = nb;
+  D.pose_b.assign(P, -1);
+  D.lm_b.assign(L, -1);
+  D.blk_hidx.assign(nb, 0);
+  D.blk_kind_local.assign(nb, 0);
+  std::vector<int> dim(nb);
+  {
+    int off = 0;
+    for (int b = 0; b < nb; b++) {
+      int kl = byId[b].second;
+      D.blk_kind_local[b] = kl;
+      if (kl & 1) { D.lm_b[kl >> 1] = b; dim[b] = 2; }
+      else { D.pose_b[kl >> 1] = b; dim[b] = 3; }
+      D.blk_hidx[b] = off;
+      off += dim[b];
+    }
+    D.n = off;
+  }
+  // ---- V layout ----
+  const long base_off = 6L * L + 12L * P;
+  D.hoff_diag.assign(nb, 0);
+  for (int b = 0; b < nb; b++) {
+    int kl = D.blk_kind_local[b];
+    D.hoff_diag[b] = (kl & 1) ? (int)(2L * L + 4L * (kl >> 1)) : (int)(6L * L + 3L * P + 9L * (kl >> 1));
+  }
+  // ---- block structure (buildStructure): one slot per distinct free vertex pair ----
+  std::unordered_map<uint64_t, int> slotOf;
+  slotOf.reserve((size_t)(El + Eo) * 2);
+  D.off_a.clear(); D.off_b.clear(); D.hoff_off.clear();
+  long cursor = base_off;
+  auto slot = [&](int ba, int bb) -> int {
+    int lo = std::min(ba, bb), hi = std::max(ba, bb);
+    uint64_t key = ((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi;
+    auto it = slotOf.find(key);
+    if (it != slotOf.end()) return it->second;
+    int k = (int)D.off_a.size();
+    slotOf.emplace(key, k);
+    D.off_a.push_back(lo);
+    D.off_b.push_back(hi);
+    D.hoff_off.push_back((int)cursor);
+    cursor += dim[lo] * dim[hi];
+    return k;
+  };
+  // landmark edges sorted by pose (stable): the order performSLAM creates them in
+  D.el_perm.resize(El);
+  std::vector<int> el_start(P + 1, 0);
+  for (int e = 0; e < El; e++) el_start[g.el_p[e] + 1]++;
+  for (int p = 0; p < P; p++) el_start[p + 1] += el_start[p];
+  {
+    std::vector<int> cur(el_start.begin(), el_start.end() - 1);
+    for (int e = 0; e < El; e++) D.el_perm[cur[g.el_p[e]]++] = e;
+  }
+  std::vector<int> s_pose(El), s_lm(El), s_slot(El, -1), s_flags(El, 0);
+  std::vector<double> s_info(3 * (size_t)El);
+  {
+    std::unordered_map<int, int> seen;  // slot -> 1 within the current pose run
+    int curPose = -1;
+    for (int q = 0; q < El; q++) {
+      int e = D.el_perm[q];
+      int p = g.el_p[e], l = g.el_l[e];
+      if (p != curPose) { seen.clear(); curPose = p; }
+      s_pose[q] = p;
+      s_lm[q] = l;
+      int fl = el_flags[e];
+      if ((fl & EF_ACTIVE) && D.pose_b[p] >= 0 && D.lm_b[l] >= 0) {
+        int k = slot(D.pose_b[p], D.lm_b[l]);
+        s_slot[q] = D.hoff_off[k];
+        fl |= EF_OFFDIAG;
+        if (D.lm_b[l] < D.pose_b[p]) fl |= EF_TRANS;
+        if (seen.emplace(k, 1).second) fl |= EF_FIRST;
+      }
+      s_flags[q] = fl;
+      s_info[q] = g.el_info[3 * (size_t)e];
+      s_info[El + (size_t)q] = g.el_info[3 * (size_t)e + 1];
+      s_info[2 * (size_t)El + q] = g.el_info[3 * (size_t)e + 2];
+    }
+  }
+  // CSR landmark -> sorted edge positions
+  std::vector<int> lm_start(L + 1, 0), lm_edges(El);
+  for (int q = 0; q < El; q++) lm_start[s_lm[q] + 1]++;
+  for (int l = 0; l < L; l++) lm_start[l + 1] += lm_start[l];
+  {
+    std::vector<int> cur(lm_start.begin(), lm_start.end() - 1);
+    for (int q = 0; q < El; q++) lm_edges[cur[s_lm[q]]++] = q;
+  }
+  // pose-pose edges: incidence lists, slots, owner = min(i, j)
+  std::vector<int> po_start(P + 1, 0), po_list(2 * (size_t)Eo), eo_slot(Eo, -1);
+  for (int e = 0; e < Eo; e++) { po_start[g.eo_i[e] + 1]++; po_start[g.eo_j[e] + 1]++; }
+  for (int p = 0; p < P; p++) po_start[p + 1] += po_start[p];
+  {
+    std::vector<int> cur(po_start.begin(), po_start.end() - 1);
+    for (int e = 0; e < Eo; e++) {
+      po_list[cur[g.eo_i[e]]++] = (e << 1);
+      po_list[cur[g.eo_j[e]]++] = (e << 1) | 1;
+    }
+    std::unordered_map<uint64_t, int> seen;  // (owner, slot) first-writer detection
+    for (int e = 0; e < Eo; e++) {
+      int i = g.eo_i[e], j = g.eo_j[e];
+      if ((eo_flags[e] & EF_ACTIVE) && D.pose_b[i] >= 0 && D.pose_b[j] >= 0) {
+        int k = slot(D.pose_b[i], D.pose_b[j]);
+        eo_slot[e] = D.hoff_off[k];
+        eo_flags[e] |= EF_OFFDIAG;
+        if (D.pose_b[j] < D.pose_b[i]) eo_flags[e] |= EF_TRANS;
+        // edges of one pair are all processed by thread min(i,j) in incidence (= edge) order
+        uint64_t key = ((uint64_t)(uint32_t)std::min(i, j) << 32) | (uint32_t)k;
+        if (seen.emplace(key, 1).second) eo_flags[e] |= EF_FIRST;
+      }
+    }
+  }
+  std::vector<double> eo_info(6 * (size_t)Eo);
+  for (int e = 0; e < Eo; e++)
+    for (int k = 0; k < 6; k++) eo_info[(size_t)k * Eo + e] = g.eo_info[6 * (size_t)e + k];
+  D.nV = cursor;
+  // ---- symbolic analysis ----
+  int leaf = 1024;
+  if (const char* s = getenv("SLAM_B200_ND_LEAF")) leaf = std::max(1, atoi(s));
+  symbolic_analyze(nb, dim.data(), (int)D.off_a.size(), D.off_a.data(), D.off_b.data(), D.hoff_diag.data(),
+                   D.hoff_off.data(), leaf, D.sym);
+  Symbolic& S = D.sym;
+  D.nL = S.lptr[S.nf];
+  D.nU = S.uptr[S.nf];
+  D.nUvec = S.rows_ptr[S.nf];
+  // per-level launch lists: fronts whose dense frontal matrix fits in shared memory vs the rest
+  const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
+  std::vector<int> launch_list;
+  std::vector<long> fbig(S.nf, -1);
+  D.levels.assign(S.nlevels, LevelLaunch());
+  D.nFbig = 0;
+  for (int lv = 0; lv < S.nlevels; lv++) {
+    LevelLaunch& LL = D.levels[lv];
+    LL.list_off = (int)launch_list.size();
+    std::vector<int> big;
+    for (int f = S.level_ptr[lv]; f < S.level_ptr[lv + 1]; f++) {
+      size_t fs = (size_t)S.npiv[f] + S.nupd[f];
+      size_t need = fs * fs * sizeof(double);
+      if (need <= smem_limit) {
+        launch_list.push_back(f);
+        LL.n_small++;
+        LL.smem_factor = std::max(LL.smem_factor, need);
+      } else {
+        big.push_back(f);
+        fbig[f] = D.nFbig;
+        D.nFbig += (long)(fs * fs);
+      }
+      size_t sneed = (fs * S.npiv[f] + fs) * sizeof(double);
+      LL.smem_solve = std::max(LL.smem_solve, std::min(sneed, smem_limit));
+    }
+    for (int f : big) launch_list.push_back(f);
+    LL.n_big = (int)big.size();
+  }
+  // solver scalar -> V offset of the rhs entry; vertex -> solver offset
+  std::vector<int> solver2v(D.n), pose_boff(P, -1), lm_boff(L, -1);
+  std::vector<unsigned char> pose_free(P, 0), lm_free(L, 0);
+  for (int b = 0; b < nb; b++) {
+    int kl = D.blk_kind_local[b];
+    int so = S.boff[b];
+    if (kl & 1) {
+      int l = kl >> 1;
+      lm_boff[l] = so;
+      lm_free[l] = 1;
+      solver2v[so] = 2 * l;
+      solver2v[so + 1] = 2 * l + 1;
+    } else {
+      int p = kl >> 1;
+      pose_boff[p] = so;
+      pose_free[p] = 1;
+      for (int k = 0; k < 3; k++) solver2v[so + k] = 6 * L + 3 * p + k;
+    }
+  }
+  // ---- upload structure ----
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  int rc = 0;
+  rc |= upload_vec(c, D.pose_free, pose_free);
+  rc |= upload_vec(c, D.lm_free, lm_free);
+  rc |= upload_vec(c, D.pose_boff, pose_boff);
+  rc |= upload_vec(c, D.lm_boff, lm_boff);
+  rc |= upload_vec(c, D.el_start, el_start);
+  rc |= upload_vec(c, D.el_pose, s_pose);
+  rc |= upload_vec(c, D.el_lm, s_lm);
+  rc |= upload_vec(c, D.el_slot, s_slot);
+  rc |= upload_vec(c, D.el_flags, s_flags);
+  rc |= upload_vec(c, D.el_info, s_info);
+  rc |= upload_vec(c, D.lm_start, lm_start);
+  rc |= upload_vec(c, D.lm_edges, lm_edges);
+  rc |= upload_vec(c, D.eo_i, g.eo_i);
+  rc |= upload_vec(c, D.eo_j, g.eo_j);
+  rc |= upload_vec(c, D.eo_slot, eo_slot);
+  rc |= upload_vec(c, D.eo_flags, eo_flags);
+  rc |= upload_vec(c, D.po_start, po_start);
+  rc |= upload_vec(c, D.po_list, po_list);
+  rc |= upload_vec(c, D.eo_info, eo_info);
+  rc |= upload_vec(c, D.ds.piv0, S.piv0);
+  rc |= upload_vec(c, D.ds.npiv, S.npiv);
+  rc |= upload_vec(c, D.ds.nupd, S.nupd);
+  rc |= upload_vec(c, D.ds.rows_ptr, S.rows_ptr);
+  rc |= upload_vec(c, D.ds.upd_rows, S.upd_rows);
+  rc |= upload_vec(c, D.ds.rel, S.rel);
+  rc |= upload_vec(c, D.ds.child_ptr, S.child_ptr);
+  rc |= upload_vec(c, D.ds.children, S.children);
+  rc |= upload_vec(c, D.ds.asm_ptr, S.asm_ptr);
+  rc |= upload_vec(c, D.ds.asm_entries, S.asm_entries);
+  rc |= upload_vec(c, D.ds.solver2v, solver2v);
+  rc |= upload_vec(c, D.ds.lptr, S.lptr);
+  rc |= upload_vec(c, D.ds.uptr, S.uptr);
+  rc |= upload_vec(c, D.ds.fbig, fbig);
+  rc |= upload_vec(c, D.ds.launch_list, launch_list);
+  if (rc) return SLAM_B200_E_CUDA;
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  D.structure_version = g.structure_version;
+  D.values_version = 0;
+  D.R = 0;  // value arrays must be (re)allocated for the new sizes
+  D.assembled = false;
+  D.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - S.seconds;
+  return D.n;
+}
+
+int graph_alloc_values(slam_b200_ctx* c, int R) {
+  DeviceSystem& D = *c->sys;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  D.estStride = 3L * D.P + 2L * D.L;
+  D.measStride = 2L * D.El + 3L * D.Eo;
+  D.chi2_cap = 64;
+  D.chi2_blocks = std::max(1, (D.P + ASM_THREADS - 1) / ASM_THREADS);
+  if (R != D.R) {
+    size_t r = (size_t)R;
+    SLAM_CUDA_TRY(c, D.est.exact(r * D.estStride));
+    SLAM_CUDA_TRY(c, D.meas.exact(r * D.measStride));
+    SLAM_CUDA_TRY(c, D.V.exact(r * D.nV));
+    SLAM_CUDA_TRY(c, D.Lv.exact(r * D.nL));
+    SLAM_CUDA_TRY(c, D.Uv.exact(r * D.nU));
+    SLAM_CUDA_TRY(c, D.uvec.exact(r * D.nUvec));
+    SLAM_CUDA_TRY(c, D.x.exact(r * D.n));
+    SLAM_CUDA_TRY(c, D.Fbig.exact(r * D.nFbig));
+    SLAM_CUDA_TRY(c, D.chi2.exact(r * D.chi2_cap));
+    SLAM_CUDA_TRY(c, D.chi2_part.exact(r * D.chi2_blocks));
+    SLAM_CUDA_TRY(c, D.status.exact(2 * r));
+    D.R = R;
+    D.values_version = 0;
+  }
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)R, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(D.chi2.p, 0, sizeof(double) * (size_t)R * D.chi2_cap, c->stream));
+  D.chi2_slots = 0;
+  D.iters_enqueued = 0;
+  D.assembled = false;
+  return 0;
+}
+
+// replica 0 <- host graph numbers (estimates + measurements)
+int graph_upload_host_values(slam_b200_ctx* c) {
+  HostGraph& g = c->g;
+  DeviceSystem& D = *c->sys;
+  const int P = D.P, L = D.L, Eo = D.Eo, El = D.El;
+  size_t ne = (size_t)D.estStride, nm = (size_t)D.measStride;
+  SLAM_CUDA_TRY(c, c->pin_d.reserve(ne + nm + 8));
+  double* e = c->pin_d.p;
+  for (int p = 0; p < P; p++) {
+    e[p] = g.pose_est[3 * (size_t)p];
+    e[P + p] = g.pose_est[3 * (size_t)p + 1];
+    e[2 * (size_t)P + p] = g.pose_est[3 * (size_t)p + 2];
+  }
+  for (int l = 0; l < L; l++) {
+    e[3 * (size_t)P + l] = g.lm_est[2 * (size_t)l];
+    e[3 * (size_t)P + L + l] = g.lm_est[2 * (size_t)l + 1];
+  }
+  double* m = e + ne;
+  for (int q = 0; q < El; q++) {
+    int o = D.el_perm[q];
+    m[q] = g.el_z[2 * (size_t)o];
+    m[El + (size_t)q] = g.el_z[2 * (size_t)o + 1];
+  }
+  for (int k = 0; k < Eo; k++) {
+    m[2 * (size_t)El + k] = g.eo_z[3 * (size_t)k];
+    m[2 * (size_t)El + Eo + k] = g.eo_z[3 * (size_t)k + 1];
+    m[2 * (size_t)El + 2 * (size_t)Eo + k] = g.eo_z[3 * (size_t)k + 2];
+  }
+  if (ne) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.est.p, e, sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
+  if (nm) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.meas.p, m, sizeof(double) * nm, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pinned staging buffer is reused
+  D.values_version = g.values_version;
+  return 0;
+}
+
+void graph_release(slam_b200_ctx* c) {
+  if (!c->sys) return;
+  DeviceSystem& D = *c->sys;
+  D.pose_free.release(); D.lm_free.release(); D.pose_boff.release(); D.lm_boff.release();
+  D.el_start.release(); D.el_pose.release(); D.el_lm.release(); D.el_slot.release(); D.el_flags.release();
+  D.el_info.release(); D.lm_start.release(); D.lm_edges.release();
+  D.eo_i.release(); D.eo_j.release(); D.eo_slot.release(); D.eo_flags.release(); D.po_start.release();
+  D.po_list.release(); D.eo_info.release();
+  D.ds.piv0.release(); D.ds.npiv.release(); D.ds.nupd.release(); D.ds.rows_ptr.release();
+  D.ds.upd_rows.release(); D.ds.rel.release(); D.ds.child_ptr.release(); D.ds.children.release();
+  D.ds.asm_ptr.release(); D.ds.solver2v.release(); D.ds.lptr.release(); D.ds.uptr.release();
+  D.ds.fbig.release(); D.ds.asm_entries.release(); D.ds.launch_list.release();
+  D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
+  D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
+  delete c->sys;
+  c->sys = nullptr;
+}

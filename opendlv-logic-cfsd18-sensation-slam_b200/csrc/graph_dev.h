@@ -1,0 +1,70 @@
+// graph_dev.h -- device-resident Gauss-Newton system of one graph topology.
+//
+// Memory layout (all fp64, replica-major: replica r lives at base + r * stride):
+//   est   : [x[P] | y[P] | theta[P] | lx[L] | ly[L]]                      SoA estimates
+//   meas  : [el_zx[El] | el_zy[El] | eo_zx[Eo] | eo_zy[Eo] | eo_zt[Eo]]   SoA measurements
+//           (landmark edges sorted by pose, the order performSLAM inserts them in)
+//   V     : [b_lm 2L | H_lm 4L | b_pose 3P | H_pose 9P | H_offdiag ...]   the normal equations
+//           H blocks are dense row-major; an off-diagonal block is stored once, oriented like
+//           g2o's upper-triangular block matrix (rows = vertex with the lower Hessian index).
+//           The first 6L doubles are the landmark part that pose-range shards must reduce.
+//   Lv    : concatenated L panels of all fronts (fsize x npiv, column-major, D on the diagonal)
+//   Uv    : concatenated update (Schur complement) matrices of all fronts (nupd x nupd)
+//   uvec  : update vectors of the forward solve (one per front);   x : solution, solver order
+// Information matrices, topology, gauge and the symbolic analysis are shared by all replicas.
+#pragma once
+#include "ctx.h"
+
+enum : int { EF_ACTIVE = 1, EF_OFFDIAG = 2, EF_FIRST = 4, EF_TRANS = 8 };
+
+struct DevSym {  // symbolic analysis on the device (see symbolic.h)
+  DevBuf<int> piv0, npiv, nupd, rows_ptr, upd_rows, rel, child_ptr, children, asm_ptr, solver2v;
+  DevBuf<long> lptr, uptr, fbig;
+  DevBuf<AsmEntry> asm_entries;
+  DevBuf<int> launch_list;  // front ids grouped per (level, small|big)
+};
+
+struct LevelLaunch {
+  int list_off = 0, n_small = 0, n_big = 0;   // launch_list[list_off .. +n_small) then big
+  size_t smem_factor = 0, smem_solve = 0;     // dynamic shared memory of the small launches
+};
+
+struct DeviceSystem {
+  uint64_t structure_version = 0;  // HostGraph version this was built from
+  uint64_t values_version = 0;     // HostGraph values currently on the device (replica 0)
+  int P = 0, L = 0, Eo = 0, El = 0;
+  int nb = 0, n = 0;               // free blocks / scalar dimension
+  long nV = 0, nL = 0, nU = 0, nUvec = 0, nFbig = 0;
+  int R = 0;                       // replicas currently allocated
+  long estStride = 0, measStride = 0;
+  // host structure
+  std::vector<int> pose_b, lm_b;   // g2o block index or -1
+  std::vector<int> blk_hidx;       // g2o scalar offset of every block
+  std::vector<int> blk_kind_local; // (local << 1) | is_landmark
+  std::vector<int> off_a, off_b, hoff_diag, hoff_off;
+  std::vector<int> el_perm;        // sorted landmark-edge position -> insertion index
+  Symbolic sym;
+  std::vector<LevelLaunch> levels;
+  double upload_seconds = 0;
+  // device structure
+  DevBuf<unsigned char> pose_free, lm_free;
+  DevBuf<int> pose_boff, lm_boff;  // solver scalar offset or -1
+  DevBuf<int> el_start, el_pose, el_lm, el_slot, el_flags;   // landmark edges sorted by pose
+  DevBuf<double> el_info;          // [3][El] SoA
+  DevBuf<int> lm_start, lm_edges;  // CSR landmark -> sorted edge positions
+  DevBuf<int> eo_i, eo_j, eo_slot, eo_flags, po_start, po_list;
+  DevBuf<double> eo_info;          // [6][Eo] SoA
+  DevSym ds;
+  // device values
+  DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part;
+  DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done
+  int chi2_slots = 0, chi2_cap = 0, chi2_blocks = 0;
+  int iters_enqueued = 0;
+  bool assembled = false;
+};
+
+int graph_build_structure(slam_b200_ctx* c);            // host: index mapping, blocks, symbolic
+int graph_alloc_values(slam_b200_ctx* c, int R);        // device value arrays for R replicas
+int graph_upload_host_values(slam_b200_ctx* c);         // replica 0 <- HostGraph numbers
+int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only);
+int graph_enqueue_solve(slam_b200_ctx* c);              // factor + forward + backward + update

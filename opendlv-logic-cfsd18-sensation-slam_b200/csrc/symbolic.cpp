@@ -1,0 +1,578 @@
+// symbolic.cpp -- nested-dissection ordering + assembly tree + front structures (host).
+// See symbolic.h.  Pure index work; runs once per graph structure.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <functional>
+#include <numeric>
+#include <set>
+
+namespace {
+
+struct NdNode {
+  std::vector<int> verts;  // pivots of this front (block indices)
+  std::vector<int> kids;   // nested-dissection children (node ids)
+};
+
+struct Nd {
+  int nb;
+  const int* dim;
+  std::vector<int> xadj, adj;
+  std::vector<int> region;  // current region label of every vertex
+  std::vector<int> lvl;     // BFS level scratch
+  std::vector<NdNode> nodes;
+  int leaf_size;
+  int next_label = 1;
+
+  // BFS inside region `lab` from r; fills order (visit order) and lvl[]; returns number of levels
+  int bfs(int r, int lab, std::vector<int>& order, std::vector<int>& level_start) {
+    order.clear();
+    level_start.clear();
+    order.push_back(r);
+    lvl[r] = 0;
+    level_start.push_back(0);
+    size_t head = 0;
+    int cur = 0;
+    while (head < order.size()) {
+      int v = order[head];
+      if (lvl[v] != cur) {
+        cur = lvl[v];
+        level_start.push_back((int)head);
+      }
+      head++;
+      for (int p = xadj[v]; p < xadj[v + 1]; p++) {
+        int u = adj[p];
+        if (region[u] == lab && lvl[u] < 0) {
+          lvl[u] = lvl[v] + 1;
+          order.push_back(u);
+        }
+      }
+    }
+    level_start.push_back((int)order.size());
+    return (int)level_start.size() - 1;
+  }
+
+  // orders the vertex set `verts` (all carrying region label `lab`); appends the resulting
+  // subtree roots to `roots`
+  void order_region(std::vector<int>& verts, int lab, std::vector<int>& roots) {
+    // split into connected components
+    for (int v : verts) lvl[v] = -1;
+    std::vector<int> order, level_start;
+    std::vector<std::vector<int>> comps;
+    for (int v : verts) {
+      if (lvl[v] >= 0) continue;
+      bfs(v, lab, order, level_start);
+      comps.push_back(order);
+    }
+    for (auto& comp : comps) {
+      if ((int)comp.size() <= leaf_size) {
+        NdNode nd;
+        nd.verts = comp;
+        nodes.push_back(nd);
+        roots.push_back((int)nodes.size() - 1);
+        continue;
+      }
+      // pseudo-peripheral start: two sweeps
+      int r = comp[0];
+      for (int sweep = 0; sweep < 2; sweep++) {
+        for (int v : comp) lvl[v] = -1;
+        bfs(r, lab, order, level_start);
+        r = order.back();
+      }
+      for (int v : comp) lvl[v] = -1;
+      int nl = bfs(r, lab, order, level_start);
+      // per-level weights and boundary weights
+      std::vector<double> w(nl, 0), wnext(nl, 0), wprev(nl, 0);
+      for (int l = 0; l < nl; l++)
+        for (int q = level_start[l]; q < level_start[l + 1]; q++) {
+          int v = order[q];
+          w[l] += dim[v];
+          bool hn = false, hp = false;
+          for (int p = xadj[v]; p < xadj[v + 1]; p++) {
+            int u = adj[p];
+            if (region[u] != lab) continue;
+            if (lvl[u] == l + 1) hn = true;
+            else if (lvl[u] == l - 1) hp = true;
+          }
+          if (hn) wnext[l] += dim[v];
+          if (hp) wprev[l] += dim[v];
+        }
+      double W = 0;
+      for (double x : w) W += x;
+      // candidates: cut between level l and l+1; option 1 separator = boundary of level l
+      // (towards l+1), option 2 = boundary of level l+1 (towards l)
+      int bestL = -1, bestOpt = 0;
+      double bestCost = 1e300;
+      double below = 0;
+      for (int l = 0; l + 1 < nl; l++) {
+        below += w[l];
+        for (int opt = 1; opt <= 2; opt++) {
+          double sep = opt == 1 ? wnext[l] : wprev[l + 1];
+          double a = opt == 1 ? below - sep : below;
+          double b = opt == 1 ? W - below : W - below - sep;
+          if (a <= 0 || b <= 0) continue;
+          double bal = std::min(a, b) / (a + b);
+          if (bal < 0.2) continue;
+          double cost = sep * (1.0 + 0.5 * (0.5 - bal));
+          if (cost < bestCost) {
+            bestCost = cost;
+            bestL = l;
+            bestOpt = opt;
+          }
+        }
+      }
+      if (bestL < 0) {
+        // no balanced level cut (e.g. a near-clique): relax balance, else dense leaf
+        below = 0;
+        for (int l = 0; l + 1 < nl; l++) {
+          below += w[l];
+          for (int opt = 1; opt <= 2; opt++) {
+            double sep = opt == 1 ? wnext[l] : wprev[l + 1];
+            double a = opt == 1 ? below - sep : below;
+            double b = opt == 1 ? W - below : W - below - sep;
+            if (a <= 0 || b <= 0) continue;
+            double cost = sep / std::min(a, b);
+            if (sep < 0.5 * W && cost < bestCost) {
+              bestCost = cost;
+              bestL = l;
+              bestOpt = opt;
+            }
+          }
+        }
+      }
+      if (bestL < 0) {
+        NdNode nd;
+        nd.verts = comp;
+        nodes.push_back(nd);
+        roots.push_back((int)nodes.size() - 1);
+        continue;
+      }
+      int sepLevel = bestOpt == 1 ? bestL : bestL + 1;
+      int other = bestOpt == 1 ? bestL + 1 : bestL;
+      std::vector<int> S, A, B;
+      for (int q = 0; q < (int)order.size(); q++) {
+        int v = order[q];
+        int l = lvl[v];
+        bool inSep = false;
+        if (l == sepLevel) {
+          for (int p = xadj[v]; p < xadj[v + 1]; p++) {
+            int u = adj[p];
+            if (region[u] == lab && lvl[u] == other) { inSep = true; break; }
+          }
+        }
+        if (inSep) S.push_back(v);
+        else if (l <= bestL) A.push_back(v);
+        else B.push_back(v);
+      }
+      int la = next_label++, lb = next_label++;
+      for (int v : A) region[v] = la;
+      for (int v : B) region[v] = lb;
+      for (int v : S) region[v] = 0;  // separators leave every region
+      NdNode nd;
+      nd.verts = S;
+      nodes.push_back(nd);
+      int me = (int)nodes.size() - 1;
+      std::vector<int> kids;
+      order_region(A, la, kids);
+      order_region(B, lb, kids);
+      nodes[me].kids = kids;
+      roots.push_back(me);
+    }
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Constrained minimum degree on the block graph.  rank[v] orders groups (all vertices of a lower
+// rank are eliminated before any vertex of a higher rank: nested-dissection leaves first, then the
+// separators bottom-up); inside a group the vertex of minimum weighted external degree goes next.
+// Hub vertices (a landmark seen from hundreds of poses) therefore stay until their spokes are gone,
+// which is what keeps fill low on pose-landmark graphs.  Exact elimination graph, sorted adjacency.
+// ------------------------------------------------------------------------------------------------
+static std::vector<int> constrained_min_degree(int nb, const int* dim, const std::vector<int>& xadj,
+                                               const std::vector<int>& adjv, const std::vector<int>& rank) {
+  std::vector<std::vector<int>> adj(nb);
+  for (int v = 0; v < nb; v++) {
+    adj[v].assign(adjv.begin() + xadj[v], adjv.begin() + xadj[v + 1]);
+    std::sort(adj[v].begin(), adj[v].end());
+    adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end());
+  }
+  std::vector<long> wdeg(nb, 0);
+  typedef std::pair<std::pair<int, long>, int> Key;
+  std::set<Key> pq;
+  for (int v = 0; v < nb; v++) {
+    for (int u : adj[v]) wdeg[v] += dim[u];
+    pq.insert({{rank[v], wdeg[v]}, v});
+  }
+  std::vector<int> order;
+  order.reserve(nb);
+  std::vector<int> merged;
+  while (!pq.empty()) {
+    int v = pq.begin()->second;
+    pq.erase(pq.begin());
+    order.push_back(v);
+    std::vector<int> N;
+    N.swap(adj[v]);
+    for (int u : N) {
+      pq.erase({{rank[u], wdeg[u]}, u});
+      merged.clear();
+      merged.reserve(adj[u].size() + N.size());
+      // (adj[u] U N) \ {u, v}
+      size_t a = 0, b = 0;
+      const std::vector<int>& A = adj[u];
+      while (a < A.size() || b < N.size()) {
+        int x;
+        if (b >= N.size() || (a < A.size() && A[a] < N[b])) x = A[a++];
+        else if (a >= A.size() || N[b] < A[a]) x = N[b++];
+        else { x = A[a]; a++; b++; }
+        if (x != u && x != v) merged.push_back(x);
+      }
+      adj[u].swap(merged);
+      long w = 0;
+      for (int x : adj[u]) w += dim[x];
+      wdeg[u] = w;
+      pq.insert({{rank[u], wdeg[u]}, u});
+    }
+  }
+  return order;
+}
+
+void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const int* off_b,
+                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S) {
+  auto t0 = std::chrono::steady_clock::now();
+  S = Symbolic();
+  S.nb = nb;
+  S.dim.assign(dim, dim + nb);
+  // ---- adjacency ----
+  Nd nd;
+  nd.nb = nb;
+  nd.dim = dim;
+  nd.leaf_size = std::max(1, leaf_size);
+  nd.xadj.assign(nb + 1, 0);
+  for (int k = 0; k < nnb; k++) {
+    nd.xadj[off_a[k] + 1]++;
+    nd.xadj[off_b[k] + 1]++;
+  }
+  for (int v = 0; v < nb; v++) nd.xadj[v + 1] += nd.xadj[v];
+  nd.adj.assign(nd.xadj[nb], 0);
+  {
+    std::vector<int> cur(nd.xadj.begin(), nd.xadj.end() - 1);
+    for (int k = 0; k < nnb; k++) {
+      nd.adj[cur[off_a[k]]++] = off_b[k];
+      nd.adj[cur[off_b[k]]++] = off_a[k];
+    }
+  }
+  // ---- stage 1: coarse nested dissection (regions of <= leaf_size vertices) gives the group
+  // ranks: all region interiors first, then separators from the deepest level up to the root
+  nd.region.assign(nb, 1);
+  nd.lvl.assign(nb, -1);
+  nd.next_label = 2;
+  std::vector<int> all(nb), roots;
+  std::iota(all.begin(), all.end(), 0);
+  nd.order_region(all, 1, roots);
+  std::vector<int> rank(nb, 0);
+  {
+    // depth of every nested-dissection node; leaves (no kids) get rank 0, a separator at depth d
+    // gets rank maxdepth - d + 1
+    std::vector<int> depth(nd.nodes.size(), 0);
+    int maxdepth = 0;
+    std::vector<int> stack(roots.begin(), roots.end());
+    while (!stack.empty()) {
+      int f = stack.back();
+      stack.pop_back();
+      maxdepth = std::max(maxdepth, depth[f]);
+      for (int k : nd.nodes[f].kids) { depth[k] = depth[f] + 1; stack.push_back(k); }
+    }
+    for (size_t f = 0; f < nd.nodes.size(); f++) {
+      int r = nd.nodes[f].kids.empty() ? 0 : (maxdepth - depth[f] + 1);
+      for (int v : nd.nodes[f].verts) rank[v] = r;
+    }
+  }
+  // ---- stage 2: constrained minimum degree -> elimination order ----
+  std::vector<int> order = constrained_min_degree(nb, dim, nd.xadj, nd.adj, rank);
+  std::vector<int> epos(nb);
+  for (int k = 0; k < nb; k++) epos[order[k]] = k;
+  // ---- stage 3: block elimination tree + column structures, postorder, supernodes ----
+  std::vector<std::vector<int>> cstruct(nb);  // struct of column k: positions > k, sorted
+  std::vector<int> eparent(nb, -1);
+  {
+    std::vector<std::vector<int>> ekids(nb);
+    std::vector<int> mark(nb, -1);
+    for (int k = 0; k < nb; k++) {
+      int v = order[k];
+      std::vector<int>& st = cstruct[k];
+      for (int p = nd.xadj[v]; p < nd.xadj[v + 1]; p++) {
+        int q = epos[nd.adj[p]];
+        if (q > k && mark[q] != k) { mark[q] = k; st.push_back(q); }
+      }
+      for (int c : ekids[k])
+        for (int q : cstruct[c])
+          if (q != k && mark[q] != k) { mark[q] = k; st.push_back(q); }
+      std::sort(st.begin(), st.end());
+      if (!st.empty()) {
+        eparent[k] = st[0];
+        ekids[st[0]].push_back(k);
+      }
+    }
+    // postorder of the elimination tree (children in ascending order); relabel positions
+    std::vector<int> postpos(nb, -1), seq;
+    seq.reserve(nb);
+    std::vector<std::pair<int, int>> st;
+    for (int r = 0; r < nb; r++) {
+      if (eparent[r] >= 0) continue;
+      st.push_back({r, 0});
+      while (!st.empty()) {
+        auto& top = st.back();
+        if (top.second < (int)ekids[top.first].size()) {
+          int k = ekids[top.first][top.second++];
+          st.push_back({k, 0});
+        } else {
+          postpos[top.first] = (int)seq.size();
+          seq.push_back(top.first);
+          st.pop_back();
+        }
+      }
+    }
+    // apply: new order, new parents, new structures
+    std::vector<int> order2(nb), eparent2(nb, -1);
+    std::vector<std::vector<int>> cstruct2(nb);
+    for (int k = 0; k < nb; k++) {
+      int nk = postpos[k];
+      order2[nk] = order[k];
+      eparent2[nk] = eparent[k] >= 0 ? postpos[eparent[k]] : -1;
+      std::vector<int>& d = cstruct2[nk];
+      d.reserve(cstruct[k].size());
+      for (int q : cstruct[k]) d.push_back(postpos[q]);
+      std::sort(d.begin(), d.end());
+    }
+    order.swap(order2);
+    eparent.swap(eparent2);
+    cstruct.swap(cstruct2);
+    for (int k = 0; k < nb; k++) epos[order[k]] = k;
+  }
+  // supernodes: fundamental (parent[k] == k+1 and struct(k) == {k+1} U struct(k+1)), then relaxed
+  // amalgamation of a last child into its parent when the padding it introduces is small
+  std::vector<int> snode_first;  // first column of every supernode
+  {
+    std::vector<int> nkids(nb, 0);
+    for (int k = 0; k < nb; k++)
+      if (eparent[k] >= 0) nkids[eparent[k]]++;
+    snode_first.push_back(0);
+    for (int k = 0; k + 1 < nb; k++) {
+      bool merge = eparent[k] == k + 1 && cstruct[k].size() == cstruct[k + 1].size() + 1;
+      if (!merge && eparent[k] == k + 1) {
+        // relaxed: column k+1 starts a supernode whose first column has struct(k+1); padding if k
+        // joins = rows of (k+1's front) not in struct(k)
+        long sk = 0, sk1 = 0;
+        for (int q : cstruct[k]) sk += dim[order[q]];
+        for (int q : cstruct[k + 1]) sk1 += dim[order[q]];
+        long pad = (sk1 + dim[order[k + 1]]) - sk;  // extra rows carried by the columns merged so far
+        long cols = 0;
+        for (int c = snode_first.back(); c <= k; c++) cols += dim[order[c]];
+        if (pad * cols <= 64 || (pad <= 6 && cols <= 48)) merge = true;
+      }
+      if (!merge) snode_first.push_back(k + 1);
+    }
+    if (nb == 0) snode_first.clear();
+  }
+  // hand the supernode partition to the generic front builder below, in elimination order
+  nd.nodes.clear();
+  for (size_t sidx = 0; sidx < snode_first.size(); sidx++) {
+    int c0 = snode_first[sidx], c1 = sidx + 1 < snode_first.size() ? snode_first[sidx + 1] : nb;
+    NdNode node;
+    for (int c = c0; c < c1; c++) node.verts.push_back(order[c]);
+    nd.nodes.push_back(node);
+  }
+  const int nf = (int)nd.nodes.size();
+  S.nf = nf;
+  std::vector<int> post(nf);
+  std::iota(post.begin(), post.end(), 0);
+  std::vector<int> ppos(nb, -1), front_of(nb, -1);  // provisional position, owning node
+  {
+    int p = 0;
+    for (int f : post) {
+      for (int v : nd.nodes[f].verts) {
+        ppos[v] = p++;
+        front_of[v] = f;
+      }
+    }
+  }
+  // ---- pass 1: update sets of every front and the assembly tree ----
+  std::vector<std::vector<int>> U(nf);       // update blocks of every node (sorted by ppos)
+  std::vector<std::vector<int>> akids(nf);   // assembly-tree children
+  std::vector<int> aparent(nf, -1);
+  {
+    std::vector<int> mark(nb, -1);
+    for (int f : post) {
+      std::vector<int>& u = U[f];
+      int last = -1;
+      for (int v : nd.nodes[f].verts) last = std::max(last, ppos[v]);
+      for (int v : nd.nodes[f].verts)
+        for (int p = nd.xadj[v]; p < nd.xadj[v + 1]; p++) {
+          int w = nd.adj[p];
+          if (ppos[w] > last && mark[w] != f) { mark[w] = f; u.push_back(w); }
+        }
+      for (int c : akids[f])
+        for (int w : U[c])
+          if (front_of[w] != f && mark[w] != f) { mark[w] = f; u.push_back(w); }
+      std::sort(u.begin(), u.end(), [&](int a, int b) { return ppos[a] < ppos[b]; });
+      if (!u.empty()) {
+        int p = front_of[u[0]];
+        aparent[f] = p;
+        akids[p].push_back(f);
+      }
+    }
+  }
+  // ---- pass 2: levels of the assembly tree, level-major renumbering ----
+  std::vector<int> level(nf, 0);
+  for (int f : post)
+    for (int c : akids[f]) level[f] = std::max(level[f], level[c] + 1);
+  int nlevels = 0;
+  for (int f = 0; f < nf; f++) nlevels = std::max(nlevels, level[f] + 1);
+  S.nlevels = nlevels;
+  std::vector<int> newid(nf, -1), oldid(nf, -1);
+  S.level_ptr.assign(nlevels + 1, 0);
+  for (int f = 0; f < nf; f++) S.level_ptr[level[f] + 1]++;
+  for (int l = 0; l < nlevels; l++) S.level_ptr[l + 1] += S.level_ptr[l];
+  {
+    std::vector<int> cur(S.level_ptr.begin(), S.level_ptr.end() - 1);
+    for (int f : post) {  // keeps the postorder inside a level (locality)
+      newid[f] = cur[level[f]]++;
+      oldid[newid[f]] = f;
+    }
+  }
+  // final positions
+  S.pos.assign(nb, -1);
+  S.boff.assign(nb, -1);
+  S.piv0.assign(nf, 0);
+  S.npiv.assign(nf, 0);
+  S.nupd.assign(nf, 0);
+  S.parent.assign(nf, -1);
+  std::vector<int> fof(nb, -1);  // new front id of every block
+  {
+    int p = 0, off = 0;
+    for (int g = 0; g < nf; g++) {
+      int f = oldid[g];
+      S.piv0[g] = off;
+      for (int v : nd.nodes[f].verts) {
+        S.pos[v] = p++;
+        S.boff[v] = off;
+        off += dim[v];
+        fof[v] = g;
+      }
+      S.npiv[g] = off - S.piv0[g];
+      S.parent[g] = aparent[f] >= 0 ? newid[aparent[f]] : -1;
+    }
+    S.n = off;
+  }
+  // children lists (new ids)
+  S.child_ptr.assign(nf + 1, 0);
+  for (int g = 0; g < nf; g++)
+    if (S.parent[g] >= 0) S.child_ptr[S.parent[g] + 1]++;
+  for (int g = 0; g < nf; g++) S.child_ptr[g + 1] += S.child_ptr[g];
+  S.children.assign(S.child_ptr[nf], 0);
+  {
+    std::vector<int> cur(S.child_ptr.begin(), S.child_ptr.end() - 1);
+    for (int g = 0; g < nf; g++)
+      if (S.parent[g] >= 0) S.children[cur[S.parent[g]]++] = g;
+  }
+  // update rows (scalar), sorted by final position
+  S.rows_ptr.assign(nf + 1, 0);
+  for (int g = 0; g < nf; g++) {
+    std::vector<int>& u = U[oldid[g]];
+    std::sort(u.begin(), u.end(), [&](int a, int b) { return S.pos[a] < S.pos[b]; });
+    int cnt = 0;
+    for (int w : u) cnt += dim[w];
+    S.nupd[g] = cnt;
+    S.rows_ptr[g + 1] = S.rows_ptr[g] + cnt;
+  }
+  S.upd_rows.assign(S.rows_ptr[nf], 0);
+  S.rel.assign(S.rows_ptr[nf], -1);
+  // position of a block's first scalar inside front g (pivot or update row), -1 if absent
+  std::vector<int> rowpos(nb, -1);  // scratch, valid for one front at a time
+  auto fill_rowpos = [&](int g, bool set) {
+    int f = oldid[g];
+    int r = 0;
+    for (int v : nd.nodes[f].verts) { rowpos[v] = set ? r : -1; r += dim[v]; }
+    for (int w : U[f]) { rowpos[w] = set ? r : -1; r += dim[w]; }
+  };
+  for (int g = 0; g < nf; g++) {
+    int q = S.rows_ptr[g];
+    for (int w : U[oldid[g]])
+      for (int k = 0; k < dim[w]; k++) S.upd_rows[q++] = S.boff[w] + k;
+  }
+  for (int p = 0; p < nf; p++) {  // rel of every child of p
+    if (S.child_ptr[p] == S.child_ptr[p + 1]) continue;
+    fill_rowpos(p, true);
+    for (int ci = S.child_ptr[p]; ci < S.child_ptr[p + 1]; ci++) {
+      int g = S.children[ci];
+      int q = S.rows_ptr[g];
+      for (int w : U[oldid[g]])
+        for (int k = 0; k < dim[w]; k++) S.rel[q++] = rowpos[w] + k;
+    }
+    fill_rowpos(p, false);
+  }
+  // storage offsets, statistics
+  S.lptr.assign(nf + 1, 0);
+  S.uptr.assign(nf + 1, 0);
+  S.nnzL = 0;
+  S.flops = 0;
+  S.max_front = 0;
+  for (int g = 0; g < nf; g++) {
+    long s = S.npiv[g], u = S.nupd[g], fs = s + u;
+    S.lptr[g + 1] = S.lptr[g] + fs * s;
+    S.uptr[g + 1] = S.uptr[g] + u * u;
+    S.nnzL += s * (s - 1) / 2 + s * u;
+    for (long k = 0; k < s; k++) {
+      double m = (double)(fs - k - 1);
+      S.flops += m * (m + 1) + m;  // rank-1 update of the trailing lower triangle + scaling
+    }
+    S.max_front = std::max<int>(S.max_front, (int)fs);
+  }
+  // ---- assembly entries: every H block lands in the front of its earlier-eliminated vertex ----
+  std::vector<std::vector<AsmEntry>> per(nf);
+  for (int b = 0; b < nb; b++) {
+    int g = fof[b];
+    AsmEntry e;
+    e.hoff = hoff_diag[b];
+    e.r = e.c = S.boff[b] - S.piv0[g];
+    e.meta = dim[b] | (dim[b] << 8) | (1 << 17);
+    per[g].push_back(e);
+  }
+  {
+    // group off-diagonal blocks by the front of the earlier vertex, resolve row positions per front
+    std::vector<std::vector<int>> byFront(nf);
+    for (int k = 0; k < nnb; k++) {
+      int a = off_a[k], b = off_b[k];
+      int e = S.pos[a] < S.pos[b] ? a : b;
+      byFront[fof[e]].push_back(k);
+    }
+    for (int g = 0; g < nf; g++) {
+      if (byFront[g].empty()) continue;
+      fill_rowpos(g, true);
+      for (int k : byFront[g]) {
+        int a = off_a[k], b = off_b[k];
+        bool aEarlier = S.pos[a] < S.pos[b];
+        int e = aEarlier ? a : b, l = aEarlier ? b : a;
+        AsmEntry en;
+        en.hoff = hoff_off[k];
+        en.c = S.boff[e] - S.piv0[g];
+        en.r = rowpos[l];
+        // stored block is dim[a] x dim[b] (rows a).  We need rows l, columns e.
+        int trans = (l == a) ? 0 : 1;
+        en.meta = dim[a] | (dim[b] << 8) | (trans << 16);
+        per[g].push_back(en);
+      }
+      fill_rowpos(g, false);
+    }
+  }
+  S.asm_ptr.assign(nf + 1, 0);
+  for (int g = 0; g < nf; g++) S.asm_ptr[g + 1] = S.asm_ptr[g] + (int)per[g].size();
+  S.asm_entries.reserve(S.asm_ptr[nf]);
+  for (int g = 0; g < nf; g++)
+    for (auto& e : per[g]) S.asm_entries.push_back(e);
+  S.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}

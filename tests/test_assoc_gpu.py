@@ -1,0 +1,198 @@
+"""Association on the B200 through the C ABI vs the CPU oracle: indices and status codes bit-exact
+(north_star), coordinates to a few ulp (device sin/cos/asin vs glibc)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+THR, MAPTHR = 1.2, 50.0
+
+
+def _ulp_close(a, b, ulps=16):
+    a = np.asarray(a); b = np.asarray(b)
+    both_nan = np.isnan(a) & np.isnan(b)
+    tol = ulps * np.spacing(np.maximum(np.abs(a), np.abs(b)))
+    return np.all(both_nan | (np.abs(a - b) <= tol + 1e-300))
+
+
+def test_conversion_matches_oracle(ctx, orc, c1_drive):
+    fr = np.concatenate(c1_drive.frames[:40], axis=1)
+    fr = np.asfortranarray(fr)
+    fr[1, ::3] = 1.5  # non-zero zenith on some columns
+    pose = np.array([3.0, -2.0, 0.7])
+    g, l = ctx.cones_to_global(fr, pose)
+    for i in range(fr.shape[1]):
+        go = orc.cone_to_global(pose, fr[:, i])
+        lo = orc.spherical2cartesian(fr[0, i], fr[1, i], fr[2, i])
+        assert _ulp_close(g[i, :2], go[:2]) and g[i, 2] == go[2]
+        assert _ulp_close(l[i], lo)
+
+
+def test_conversion_nan_at_zero_azimuth(ctx):
+    fr = np.asfortranarray(np.array([[0.0], [0.0], [5.0], [1.0]]))
+    g, l = ctx.cones_to_global(fr, np.zeros(3))
+    assert np.isnan(g[0, 0]) and np.isnan(g[0, 1]) and l[0, 2] == 0.0  # slam.cpp:515
+
+
+def _lockstep_mapping(ctx, orc, frames, poses, thr=THR, map_thr=MAPTHR, stop_at_closure=True):
+    """Drives the device map and an oracle map through the same frames; asserts bit-exact records."""
+    ctx.map_clear()
+    cap = sum(f.shape[1] for f in frames) + 8
+    mx = np.zeros(cap); my = np.zeros(cap); mt = np.zeros(cap, dtype=np.int32)
+    M = 0; cci = 0; lc = 0
+    dcci = 0; dlc = 0
+    for k, (fr, p) in enumerate(zip(frames, poses)):
+        o = orc.assoc_map_frame(fr, p, thr, map_thr, mx, my, mt, M, cci, lc)
+        d = ctx.assoc_map_frame(fr, p, thr, map_thr, dcci, dlc)
+        assert np.array_equal(d["idx"], o["idx"]), f"frame {k}"
+        assert np.array_equal(d["status"], o["status"]), f"frame {k}"
+        assert (d["first"], d["lc_obs"], d["M"], d["cci"], d["loop_closing"]) == \
+               (o["first"], o["lc_obs"], o["M"], o["cci"], o["loop_closing"]), f"frame {k}"
+        assert _ulp_close(d["z"], o["z"]) and _ulp_close(d["g"], o["g"])
+        M, cci, lc = o["M"], o["cci"], o["loop_closing"]
+        dcci, dlc = d["cci"], d["loop_closing"]
+        if lc and stop_at_closure:
+            break
+    dx, dy, dt = ctx.map_read()
+    assert len(dx) == M and np.array_equal(dt, mt[:M])
+    assert _ulp_close(dx, mx[:M]) and _ulp_close(dy, my[:M])
+    return M, k
+
+
+def test_mapping_phase_c1_replay_bit_exact(ctx, orc, c1_drive):
+    M, k = _lockstep_mapping(ctx, orc, c1_drive.frames, c1_drive.poses_noisy)
+    assert M == 300 and k > 900   # the whole lap, loop closure near the end
+
+
+def test_mapping_phase_edge_cases(ctx, orc, synth):
+    pose = np.array([0.0, 0.0, 0.1])
+    frames = [
+        np.zeros((4, 0), order="F"),                                              # empty frame
+        np.asfortranarray(np.array([[10.0, 10.0, -20.0, 0.0, 30.0],               # two columns = the same new cone
+                                    [0, 0, 0, 0, 0],                               # (second must match the first, created
+                                    [5.0, 5.2, 7.0, 4.0, 60.0],                    #  in this very frame); az == 0 -> NaN cone;
+                                    [1.0, 1.0, 2.0, 1.0, 2.0]])),                  # range 60 >= 50 -> not added
+        np.asfortranarray(np.array([[10.0, -20.0, 12.0], [0, 0, 0], [5.0, 7.0, 5.1], [1.5, 2.0, 2.0]])),  # non-integer type
+    ]
+    poses = [pose, pose, pose + np.array([0.2, 0.0, 0.0])]
+    _lockstep_mapping(ctx, orc, frames, poses, stop_at_closure=False)
+
+
+def test_mapping_phase_mid_frame_loop_closure(ctx, orc, c1_drive):
+    """An unsorted frame whose FIRST column closes the loop: every later column is skipped and
+    the caller owes one optimise per remaining column (slam.cpp:625-633)."""
+    frames = [f.copy(order="F") for f in c1_drive.frames]
+    # find the closing frame with the oracle, then reverse its columns
+    cap = 4000
+    mx = np.zeros(cap); my = np.zeros(cap); mt = np.zeros(cap, dtype=np.int32)
+    M = cci = lc = 0
+    for k, (fr, p) in enumerate(zip(frames, c1_drive.poses_noisy)):
+        o = orc.assoc_map_frame(fr, p, THR, MAPTHR, mx, my, mt, M, cci, lc)
+        M, cci, lc = o["M"], o["cci"], o["loop_closing"]
+        if lc:
+            break
+    frames[k] = np.asfortranarray(frames[k][:, ::-1])
+    ctx.map_clear()
+    mx[:] = 0; my[:] = 0; mt[:] = 0
+    M = cci = lc = 0; dcci = dlc = 0
+    for q in range(k + 1):
+        o = orc.assoc_map_frame(frames[q], c1_drive.poses_noisy[q], THR, MAPTHR, mx, my, mt, M, cci, lc)
+        d = ctx.assoc_map_frame(frames[q], c1_drive.poses_noisy[q], THR, MAPTHR, dcci, dlc)
+        assert np.array_equal(d["idx"], o["idx"]) and np.array_equal(d["status"], o["status"])
+        assert d["lc_obs"] == o["lc_obs"]
+        M, cci, lc = o["M"], o["cci"], o["loop_closing"]; dcci, dlc = d["cci"], d["loop_closing"]
+    assert o["lc_obs"] == 0 and np.all(o["status"][1:] == 3)
+
+
+def test_mapping_phase_large_frame_many_tiles(ctx, orc, synth):
+    """A frame and a map larger than one shared-memory tile (2048 cones) and than the warp count."""
+    f = synth.cone_field(n_map=6000, n_obs=1500, seed=11, density=0.02)
+    ctx.map_clear()
+    ctx.map_append(f.map_x, f.map_y, f.map_type)
+    cap = 6000 + 1500 + 1
+    mx = np.zeros(cap); my = np.zeros(cap); mt = np.zeros(cap, dtype=np.int32)
+    mx[:6000], my[:6000], mt[:6000] = f.map_x, f.map_y, f.map_type
+    o = orc.assoc_map_frame(f.frame, f.pose, THR, 1e9, mx, my, mt, 6000, 0, 0)
+    d = ctx.assoc_map_frame(f.frame, f.pose, THR, 1e9, 0, 0)
+    assert np.array_equal(d["idx"], o["idx"]) and np.array_equal(d["status"], o["status"])
+    assert d["M"] == o["M"] and d["cci"] == o["cci"] and d["lc_obs"] == o["lc_obs"]
+    assert (o["status"] == 1).sum() > 50 and (o["status"] == 0).sum() > 1000
+
+
+def test_localize_phase_matches_oracle(ctx, orc, synth, c1_drive):
+    trk = c1_drive.track
+    ctx.map_clear()
+    ctx.map_append(trk.cones_xy[:, 0], trk.cones_xy[:, 1], trk.cones_type)
+    mx, my, mt = trk.cones_xy[:, 0].copy(), trk.cones_xy[:, 1].copy(), trk.cones_type.copy()
+    cci = dcci = 7
+    for k in range(0, 1000, 37):
+        fr = c1_drive.frames[k].copy(order="F")
+        if k % 2:
+            fr[3] = 3.0 - fr[3]          # swap types: exercises the asymmetric gate (slam.cpp:360)
+        o = orc.assoc_localize_frame(fr, c1_drive.poses_noisy[k], THR, mx, my, mt, cci)
+        d = ctx.assoc_localize_frame(fr, c1_drive.poses_noisy[k], THR, dcci)
+        assert np.array_equal(d["idx"], o["idx"])
+        assert (d["cci"], d["n_reobserved"]) == (o["cci"], o["n_reobserved"])
+        if o["n_reobserved"] > 0:
+            assert d["send_cone_data"] == o["send_cone_data"]
+        cci, dcci = o["cci"], d["cci"]
+    # nothing matched: current cone index is left alone (slam.cpp:387)
+    far = np.asfortranarray(np.array([[5.0], [0.0], [3.0], [1.0]]))
+    d = ctx.assoc_localize_frame(far, np.array([150.0, 150.0, 0.0]), THR, 11)
+    assert d["n_reobserved"] == 0 and d["cci"] == 11 and d["idx"][0] == -1
+
+
+@pytest.mark.parametrize("gate", [0, 1])
+def test_bulk_match_only_vs_oracle(ctx, orc, synth, pkg, gate):
+    f = synth.cone_field(n_map=200_000, n_obs=3000, seed=4)
+    ctx.map_clear()
+    ctx.map_append(f.map_x, f.map_y, f.map_type)
+    o = orc.assoc_match_only(f.frame, f.pose, THR, gate, f.map_x, f.map_y, f.map_type)
+    brute = ctx.assoc_bulk(f.frame, f.pose, THR, gate, pkg.capi.ALGO_BRUTE).copy()
+    grid = ctx.assoc_bulk(f.frame, f.pose, THR, gate, pkg.capi.ALGO_GRID).copy()
+    assert np.array_equal(brute, o["idx"])
+    assert np.array_equal(grid, o["idx"])
+    assert (o["idx"] >= 0).sum() > 2000
+    # no decision sits within rounding distance of the threshold, so the few-ulp difference of the
+    # device trig cannot flip one
+    assert o["min_margin"] > 1e-9
+
+
+def test_bulk_edge_cases(ctx, synth, pkg):
+    f = synth.cone_field(n_map=5000, n_obs=400, seed=5)
+    ctx.map_clear()
+    assert np.all(ctx.assoc_bulk(f.frame, f.pose, THR, 0, pkg.capi.ALGO_GRID) == -1)   # empty map
+    ctx.map_append(f.map_x, f.map_y, f.map_type)
+    assert len(ctx.assoc_bulk(f.frame[:, :0], f.pose, THR, 0, pkg.capi.ALGO_GRID)) == 0  # empty batch
+    fr = f.frame.copy(order="F")
+    fr[0, 5] = 0.0                                    # NaN observation never matches
+    fr[2, 6] = 1e7                                    # far outside the map's bounding box
+    a = ctx.assoc_bulk(fr, f.pose, THR, 0, pkg.capi.ALGO_GRID).copy()
+    b = ctx.assoc_bulk(fr, f.pose, THR, 0, pkg.capi.ALGO_BRUTE).copy()
+    assert np.array_equal(a, b) and a[5] == -1 and a[6] == -1
+    # a NaN cone in the map (what the reference stores after an az == 0 column) matches nothing
+    ctx.map_append(np.array([np.nan]), np.array([np.nan]), np.array([1], dtype=np.int32))
+    a2 = ctx.assoc_bulk(fr, f.pose, THR, 0, pkg.capi.ALGO_GRID).copy()
+    assert np.array_equal(a2, a)
+    # duplicate cones: the LOWEST index wins (first-fit, slam.cpp:575-607)
+    ctx.map_clear()
+    x = np.concatenate([f.map_x, f.map_x]); y = np.concatenate([f.map_y, f.map_y]); t = np.concatenate([f.map_type, f.map_type])
+    ctx.map_append(x, y, t)
+    a3 = ctx.assoc_bulk(f.frame, f.pose, THR, 0, pkg.capi.ALGO_GRID).copy()
+    assert np.all(a3 < 5000) and (a3 >= 0).sum() > 300
+
+
+def test_bulk_full_size_c4_grid_equals_brute(ctx, orc, synth, pkg):
+    """BASELINE config 4 at full size (1M cones, 100k observations): both device algorithms agree on
+    every observation, and a 1,500-observation sample agrees with the oracle."""
+    f = synth.cone_field()
+    ctx.map_clear()
+    ctx.map_append(f.map_x, f.map_y, f.map_type)
+    for gate in (0, 1):
+        grid = ctx.assoc_bulk(f.frame, f.pose, THR, gate, pkg.capi.ALGO_GRID).copy()
+        brute = ctx.assoc_bulk(f.frame, f.pose, THR, gate, pkg.capi.ALGO_BRUTE).copy()
+        assert np.array_equal(grid, brute)
+        sample = np.asfortranarray(f.frame[:, :1500])
+        o = orc.assoc_match_only(sample, f.pose, THR, gate, f.map_x, f.map_y, f.map_type)
+        assert np.array_equal(grid[:1500], o["idx"])
+    assert (grid >= 0).mean() > 0.85

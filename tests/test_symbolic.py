@@ -1,0 +1,98 @@
+"""Host symbolic phase (nested dissection + assembly tree): structural invariants and, through a
+numpy emulation of the front schedule, that it really factorises and solves H x = b."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import small_graph
+import mf_emul
+
+
+def _check_structure(sym, dims):
+    n = int(np.sum(dims))
+    assert sym.n == n and sym.nb == len(dims)
+    assert sorted(sym.pos.tolist()) == list(range(len(dims)))
+    # pivots tile the solver index space; children precede parents; levels are contiguous
+    order = np.argsort(sym.piv0, kind="stable")
+    assert np.array_equal(order, np.arange(sym.nf))
+    assert sym.piv0[0] == 0 and np.all(sym.piv0[1:] == np.cumsum(sym.npiv)[:-1]) and np.sum(sym.npiv) == n
+    for f in range(sym.nf):
+        if sym.parent[f] >= 0:
+            assert sym.parent[f] > f
+        rows = sym.upd_rows[sym.rows_ptr[f]:sym.rows_ptr[f + 1]]
+        assert np.all(np.diff(rows) > 0)
+        if len(rows):
+            assert rows[0] >= sym.piv0[f] + sym.npiv[f]
+            assert sym.parent[f] >= 0
+    lvl = np.zeros(sym.nf, dtype=int)
+    for l in range(sym.nlevels):
+        lvl[sym.level_ptr[l]:sym.level_ptr[l + 1]] = l
+    for f in range(sym.nf):
+        if sym.parent[f] >= 0:
+            assert lvl[sym.parent[f]] > lvl[f]
+
+
+@pytest.mark.parametrize("leaf", [1, 8, 64, 100000])
+def test_symbolic_solves_small_graph(pkg, synth, orc, leaf):
+    g = small_graph(synth, 150)
+    ids, dims, pa, pb = mf_emul.block_pattern(g)
+    sym = pkg.SymbolicAnalysis(dims, pa, pb, leaf_size=leaf)
+    _check_structure(sym, dims)
+    G = orc.graph_from_soa(g)
+    sysm = G.build_system()
+    n = sysm["n"]
+    assert n == sym.n
+    U = sp.csc_matrix((sysm["Ax"], sysm["Ai"], sysm["Ap"]), shape=(n, n))
+    H = (U + sp.triu(U, 1).T).toarray()
+    hv = mf_emul.hvals_from_dense(H, dims, pa, pb, sym)
+    perm = mf_emul.solver_perm(sym, dims)
+    x_solver = mf_emul.factor_solve(sym, hv, sysm["b"][perm])
+    x = np.zeros(n)
+    x[perm] = x_solver
+    x_ref = spla.spsolve(sp.csc_matrix(H), sysm["b"])
+    assert np.allclose(x, x_ref, rtol=1e-9, atol=1e-12)
+
+
+def test_symbolic_c1_quality(pkg, synth, c1_graph):
+    """The ordering must stay sparse on the trackdrive topology (never a dense Schur)."""
+    ids, dims, pa, pb = mf_emul.block_pattern(c1_graph)
+    sym = pkg.SymbolicAnalysis(dims, pa, pb, leaf_size=1024)
+    _check_structure(sym, dims)
+    n = sym.n
+    assert sym.nnzL < 40 * n          # AMD on the reference solver gives ~20 n on this pattern
+    assert sym.nlevels < 40           # short assembly tree = few dependent kernel levels
+    assert sym.max_front < 400
+
+
+def test_symbolic_random_sparse(pkg):
+    """Generic patterns (disconnected pieces, cliques, isolated vertices) are handled."""
+    rng = np.random.default_rng(3)
+    nb = 200
+    dims = rng.integers(2, 4, nb).astype(np.int32)
+    pairs = set()
+    for _ in range(500):
+        a, b = rng.integers(0, nb - 20, 2)   # leaves the last 20 vertices isolated
+        if a != b:
+            pairs.add((min(a, b), max(a, b)))
+    for a in range(60, 70):                  # a clique
+        for b in range(a + 1, 70):
+            pairs.add((a, b))
+    pairs = sorted(pairs)
+    pa = np.array([p[0] for p in pairs], dtype=np.int32); pb = np.array([p[1] for p in pairs], dtype=np.int32)
+    sym = pkg.SymbolicAnalysis(dims, pa, pb, leaf_size=4)
+    _check_structure(sym, dims)
+    n = int(dims.sum())
+    off = np.concatenate([[0], np.cumsum(dims)])
+    H = np.zeros((n, n))
+    for a, b in pairs:
+        blk = rng.normal(size=(dims[a], dims[b])) * 0.1
+        H[off[a]:off[a + 1], off[b]:off[b + 1]] = blk
+        H[off[b]:off[b + 1], off[a]:off[a + 1]] = blk.T
+    H += np.eye(n) * (np.abs(H).sum(axis=1).max() + 1.0)
+    b = rng.normal(size=n)
+    hv = mf_emul.hvals_from_dense(H, dims, pa, pb, sym)
+    perm = mf_emul.solver_perm(sym, dims)
+    x = np.zeros(n)
+    x[perm] = mf_emul.factor_solve(sym, hv, b[perm])
+    assert np.allclose(H @ x, b, rtol=1e-9, atol=1e-10)
