@@ -187,6 +187,17 @@ int slam_b200_graph_assemble_async(slam_b200_ctx* ctx, int p0, int p1);
 long slam_b200_graph_system_dev(slam_b200_ctx* ctx, int which, double** ptr);
 /* Enqueues factorise + solve + update for the system currently assembled. */
 int slam_b200_graph_solve_async(slam_b200_ctx* ctx);
+/* Device-side copy of all estimates (every replica) and its restoration, so repeated runs start
+ * from the same state without touching the host.  restore also clears status / iteration count. */
+int slam_b200_graph_snapshot(slam_b200_ctx* ctx);
+int slam_b200_graph_restore_async(slam_b200_ctx* ctx);
+/* Per-phase device timing with CUDA events on the context's stream.  While enabled, iterations are
+ * launched kernel by kernel (no CUDA-graph replay).  read: out[0..4] = ms summed over the profiled
+ * iterations for assemble, factorise, forward solve, backward solve, update; out[5] = iterations. */
+int slam_b200_profile_enable(slam_b200_ctx* ctx, int on);
+int slam_b200_profile_read(slam_b200_ctx* ctx, double out[8]);
+/* Measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator for the solve). */
+int slam_b200_fp64_peak(slam_b200_ctx* ctx, double* tflops);
 
 /* Debug / test export of the assembled system in g2o's Hessian order (ascending vertex id among
  * non-fixed active vertices): upper-triangular scalar CSC.  Call with Ai == NULL to query

@@ -49,7 +49,8 @@ def lib():
         for name in ("slam_b200_destroy", "slam_b200_sync", "slam_b200_map_clear", "slam_b200_map_size",
                      "slam_b200_graph_clear", "slam_b200_graph_prepare", "slam_b200_graph_num_poses",
                      "slam_b200_graph_num_landmarks", "slam_b200_graph_num_edges", "slam_b200_launch_count",
-                     "slam_b200_graph_reset_device", "slam_b200_graph_solve_async"):
+                     "slam_b200_graph_reset_device", "slam_b200_graph_solve_async", "slam_b200_graph_snapshot",
+                     "slam_b200_graph_restore_async"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.slam_b200_graph_add_pose.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         L.slam_b200_graph_add_landmark.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
@@ -63,6 +64,9 @@ def lib():
         L.slam_b200_graph_finish.argtypes = [C.c_void_p, c_dp, C.c_int]
         L.slam_b200_graph_assemble_async.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.slam_b200_map_build_grid.argtypes = [C.c_void_p, C.c_double]
+        L.slam_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.slam_b200_profile_read.argtypes = [C.c_void_p, c_dp]
+        L.slam_b200_fp64_peak.argtypes = [C.c_void_p, c_dp]
         _lib = L
     return _lib
 
@@ -269,6 +273,26 @@ class Context:
 
     def graph_reset_device(self):
         self._ck(self.L.slam_b200_graph_reset_device(self.h), "graph_reset_device")
+
+    def graph_snapshot(self):
+        self._ck(self.L.slam_b200_graph_snapshot(self.h), "graph_snapshot")
+
+    def graph_restore_async(self):
+        self._ck(self.L.slam_b200_graph_restore_async(self.h), "graph_restore_async")
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.slam_b200_profile_enable(self.h, int(bool(on))), "profile_enable")
+
+    def profile_read(self):
+        out = np.zeros(8)
+        self._ck(self.L.slam_b200_profile_read(self.h, _dp(out)), "profile_read")
+        return dict(assemble_ms=out[0], factor_ms=out[1], forward_ms=out[2], backward_ms=out[3], update_ms=out[4],
+                    iterations=int(out[5]))
+
+    def fp64_peak_tflops(self):
+        v = C.c_double(0)
+        self._ck(self.L.slam_b200_fp64_peak(self.h, C.byref(v)), "fp64_peak")
+        return v.value
 
     def graph_assemble_async(self, p0, p1):
         self._ck(self.L.slam_b200_graph_assemble_async(self.h, int(p0), int(p1)), "graph_assemble_async")

@@ -343,9 +343,7 @@ int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) {
   DeviceSystem& D = *c->sys;
   if (D.n == 0) return 0;
   for (int it = 0; it < iters; it++) {
-    int rc = graph_enqueue_assemble(c, 0, D.P, false);
-    if (rc) return rc;
-    rc = graph_enqueue_solve(c);
+    int rc = graph_enqueue_iteration(c);
     if (rc) return rc;
   }
   D.iters_enqueued += iters;
@@ -375,7 +373,6 @@ int slam_b200_graph_finish(slam_b200_ctx* c, double* chi2, int chi2_cap) {
   int failed = st[0];
   // next round of iterations starts a fresh chi2 log / status
   SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)D.R, c->stream));
-  D.chi2_slots = 0;
   D.iters_enqueued = 0;
   if (failed) return 0;
   return done;
@@ -396,10 +393,13 @@ int slam_b200_graph_chi2(slam_b200_ctx* c, double* chi2) {
   int n = slam_b200_graph_prepare(c);
   if (n < 0) return n;
   DeviceSystem& D = *c->sys;
-  int slot = D.chi2_slots;
+  if (D.n == 0) { *chi2 = 0; return 0; }
   int rc = graph_enqueue_assemble(c, 0, D.P, true);
   if (rc) return rc;
-  D.chi2_slots = slot;  // do not disturb the iteration log
+  int st[2];
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(st, D.status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  int slot = std::min(st[1], D.chi2_cap - 1);  // the slot the kernel wrote (= iterations done so far)
   SLAM_CUDA_TRY(c, cudaMemcpyAsync(chi2, D.chi2.p + slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -410,10 +410,7 @@ int slam_b200_graph_assemble_async(slam_b200_ctx* c, int p0, int p1) {
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
   if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
-  int slot = D.chi2_slots;
-  int rc = graph_enqueue_assemble(c, p0, p1, false);
-  D.chi2_slots = slot;
-  return rc;
+  return graph_enqueue_assemble(c, p0, p1, false);
 }
 
 long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) {
@@ -455,9 +452,7 @@ long slam_b200_graph_export_system(slam_b200_ctx* c, int* n_out, int32_t* Ap, in
   long nnz = 0;
   for (auto& cm : cols) nnz += (long)cm.size();
   if (!Ai) return nnz;
-  int slot = D.chi2_slots;
   int rc = graph_enqueue_assemble(c, 0, D.P, false);
-  D.chi2_slots = slot;
   if (rc) return rc;
   std::vector<double> V(D.nV);
   SLAM_CUDA_TRY(c, cudaMemcpyAsync(V.data(), D.V.p, sizeof(double) * D.nV, cudaMemcpyDeviceToHost, c->stream));
@@ -501,6 +496,54 @@ int slam_b200_graph_stats(slam_b200_ctx* c, double out[16]) {
 }
 
 long slam_b200_graph_export_symbolic(slam_b200_ctx* c, int what, int32_t* out, long cap);
+
+// ---- device-side snapshot of the estimates (bench: every timed step starts from the same state) --
+int slam_b200_graph_snapshot(slam_b200_ctx* c) {
+  if (!c || !c->sys || c->sys->R < 1) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  size_t n = (size_t)D.R * D.estStride;
+  if (n) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.est0.p, D.est.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+  D.have_snapshot = true;
+  return 0;
+}
+int slam_b200_graph_restore_async(slam_b200_ctx* c) {
+  if (!c || !c->sys || !c->sys->have_snapshot) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  size_t n = (size_t)D.R * D.estStride;
+  if (n) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.est.p, D.est0.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)D.R, c->stream));
+  D.iters_enqueued = 0;
+  return 0;
+}
+
+// ---- per-phase timing with CUDA events (bench) ----------------------------------------------------
+int slam_b200_profile_enable(slam_b200_ctx* c, int on) {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  c->sys->profile = on != 0;
+  return 0;
+}
+// out[0..4] = milliseconds summed over the profiled iterations: assemble, factor, forward, backward,
+// update; out[5] = iterations profiled.  Synchronises the stream and clears the record.
+int slam_b200_profile_read(slam_b200_ctx* c, double out[8]) {
+  if (!c || !c->sys || !out) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 8; k++) out[k] = 0;
+  size_t nit = D.prof_events.size() / 6;
+  for (size_t it = 0; it < nit; it++)
+    for (int ph = 0; ph < 5; ph++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, D.prof_events[6 * it + ph], D.prof_events[6 * it + ph + 1]);
+      out[ph] += ms;
+    }
+  out[5] = (double)nit;
+  for (cudaEvent_t e : D.prof_events) cudaEventDestroy(e);
+  D.prof_events.clear();
+  return 0;
+}
 
 // ---- symbolic analysis without a device (host logic; testable on a CPU-only box) ----------------
 struct SymHandle {
@@ -662,7 +705,6 @@ int slam_b200_batch_download(slam_b200_ctx* c, double* pose_est3, double* lm_est
         chi2[(size_t)r * chi2_cap_per_replica + k] = ch[(size_t)r * D.chi2_cap + k + 1];
   }
   SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)R, c->stream));
-  D.chi2_slots = 0;
   D.iters_enqueued = 0;
   return 0;
 }
@@ -678,3 +720,47 @@ int slam_b200_graph_optimize_batch(slam_b200_ctx* c, int R, double* pose_est3, d
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// fp64 FMA peak of the device (the denominator for the solve's fp64 roofline; MEASURED_PEAKS.json
+// only carries HBM bandwidth and bf16 tensor throughput)
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+extern "C" int slam_b200_fp64_peak(slam_b200_ctx* c, double* tflops) {
+  if (!c || !tflops) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  const int blocks = c->num_sms * 8, threads = 256, iters = 1 << 15;
+  double* buf = nullptr;
+  SLAM_CUDA_TRY(c, cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, c->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>(buf, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double fl = 2.0 * 8 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  c->launches += 4;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  SLAM_CUDA_TRY(c, cudaGetLastError());
+  *tflops = best;
+  return 0;
+}

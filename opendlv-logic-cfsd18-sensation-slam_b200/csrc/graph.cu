@@ -48,7 +48,8 @@ struct AsmArgs {
   double* chi2_part;
   int chi2_blocks;
   double* chi2;
-  int chi2_cap, chi2_slot;
+  int chi2_cap;
+  const int* status;  // per replica [fail flag, iterations done]; the latter is the chi2 slot
 };
 
 constexpr int ASM_THREADS = 128;
@@ -275,7 +276,9 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks) {
     double t = 0;
     for (int k = threadIdx.x; k < chi2_nblocks; k += 32) t += a.chi2_part[(size_t)r * a.chi2_blocks + k];
     for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-    if (threadIdx.x == 0 && a.chi2_slot < a.chi2_cap) a.chi2[(size_t)r * a.chi2_cap + a.chi2_slot] = t;
+    // slot k holds chi2 at the state reached after k iterations (slot 0 = initial estimate)
+    const int slot = a.status[2 * r + 1];
+    if (threadIdx.x == 0 && slot < a.chi2_cap) a.chi2[(size_t)r * a.chi2_cap + slot] = t;
   }
 }
 
@@ -340,7 +343,7 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
   a.eo_i = D.eo_i.p; a.eo_j = D.eo_j.p; a.eo_slot = D.eo_slot.p; a.eo_flags = D.eo_flags.p;
   a.po_start = D.po_start.p; a.po_list = D.po_list.p; a.eo_info = D.eo_info.p;
   a.chi2_part = D.chi2_part.p; a.chi2_blocks = D.chi2_blocks;
-  a.chi2 = D.chi2.p; a.chi2_cap = D.chi2_cap; a.chi2_slot = D.chi2_slots;
+  a.chi2 = D.chi2.p; a.chi2_cap = D.chi2_cap; a.status = D.status.p;
   int np = std::max(0, p1 - p0);
   int nblk = (np + ASM_THREADS - 1) / ASM_THREADS;
   if (nblk > 0) {
@@ -354,7 +357,6 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
   else assemble_landmark_kernel<false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk);
   c->launches++;
   SLAM_CUDA_TRY(c, cudaGetLastError());
-  D.chi2_slots++;
   if (!chi2_only) D.assembled = true;
   return 0;
 }
@@ -603,6 +605,7 @@ int graph_build_structure(slam_b200_ctx* c) {
   D.structure_version = g.structure_version;
   D.values_version = 0;
   D.R = 0;  // value arrays must be (re)allocated for the new sizes
+  D.drop_graph();
   D.assembled = false;
   D.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - S.seconds;
   return D.n;
@@ -628,12 +631,13 @@ int graph_alloc_values(slam_b200_ctx* c, int R) {
     SLAM_CUDA_TRY(c, D.chi2.exact(r * D.chi2_cap));
     SLAM_CUDA_TRY(c, D.chi2_part.exact(r * D.chi2_blocks));
     SLAM_CUDA_TRY(c, D.status.exact(2 * r));
+    SLAM_CUDA_TRY(c, D.est0.exact(r * D.estStride));
     D.R = R;
+    D.drop_graph();
     D.values_version = 0;
   }
   SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)R, c->stream));
   SLAM_CUDA_TRY(c, cudaMemsetAsync(D.chi2.p, 0, sizeof(double) * (size_t)R * D.chi2_cap, c->stream));
-  D.chi2_slots = 0;
   D.iters_enqueued = 0;
   D.assembled = false;
   return 0;
@@ -688,6 +692,8 @@ void graph_release(slam_b200_ctx* c) {
   D.ds.fbig.release(); D.ds.asm_entries.release(); D.ds.launch_list.release();
   D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
   D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
+  D.est0.release();
+  D.drop_graph();
   delete c->sys;
   c->sys = nullptr;
 }

@@ -56,11 +56,23 @@ struct DeviceSystem {
   DevBuf<double> eo_info;          // [6][Eo] SoA
   DevSym ds;
   // device values
-  DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part;
-  DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done
-  int chi2_slots = 0, chi2_cap = 0, chi2_blocks = 0;
+  DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part, est0;
+  DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done (= chi2 slot)
+  int chi2_cap = 0, chi2_blocks = 0;
   int iters_enqueued = 0;
   bool assembled = false;
+  bool have_snapshot = false;
+  // one Gauss-Newton iteration (assemble + factor + solves + update) captured as a CUDA graph:
+  // ~40 dependent small launches replayed with one host call per iteration
+  cudaGraphExec_t iter_graph = nullptr;
+  int launches_per_iter = 0;
+  void drop_graph() {
+    if (iter_graph) cudaGraphExecDestroy(iter_graph);
+    iter_graph = nullptr;
+  }
+  // profiling (bench): CUDA events between the phases of every iteration
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;  // 6 per iteration: start, assembled, factored, forward, backward, updated
 };
 
 int graph_build_structure(slam_b200_ctx* c);            // host: index mapping, blocks, symbolic
@@ -68,3 +80,4 @@ int graph_alloc_values(slam_b200_ctx* c, int R);        // device value arrays f
 int graph_upload_host_values(slam_b200_ctx* c);         // replica 0 <- HostGraph numbers
 int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only);
 int graph_enqueue_solve(slam_b200_ctx* c);              // factor + forward + backward + update
+int graph_enqueue_iteration(slam_b200_ctx* c);          // one GN iteration (CUDA graph replay when possible)

@@ -1,0 +1,114 @@
+// slam.hpp -- host-side mirror of the reference's class Slam (src/slam.hpp:43-137) with the g2o
+// optimiser member and the private back-half methods re-implemented over the C ABI of
+// include/slam_b200.h (CUDA on the B200).  Public draw* accessors, private method names, member
+// names, defaults and mutex discipline follow the reference so that INTEGRATION.md's patch is a
+// body swap, not a redesign.
+//
+// What is NOT here: the front half (nextCone / nextPose / nextSplitPose / nextYawRate,
+// initializeCollection, isKeyframe; src/slam.cpp:67-295) and the OD4 senders (sendCones / sendPose,
+// 656-695).  north_star keeps message handling unchanged; inside the reference tree those bodies
+// stay as they are and call performSLAM() below.  Stand-alone, setOdometry()/setYawRate() stand in
+// for what nextPose()/nextYawRate() store, and the senders are optional callbacks.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/slam_b200.h"
+#include "cone.hpp"
+#include "slam_types.hpp"
+
+class Slam {
+ private:
+  Slam(const Slam&) = delete;
+  Slam(Slam&&) = delete;
+  Slam& operator=(const Slam&) = delete;
+  Slam& operator=(Slam&&) = delete;
+
+ public:
+  // Same configuration map as the reference constructor (src/slam.cpp:25-51, setUp 736-756):
+  // keys gatheringTimeMs, sameConeThreshold, refLatitude, refLongitude, timeBetweenKeyframes,
+  // coneMappingThreshold, conesPerPacket, id.  Throws like std::stoi/std::stod on a missing key.
+  // Extra optional key "cudaDevice" (default 0).
+  explicit Slam(std::map<std::string, std::string> commandlineArguments);
+  ~Slam();
+
+  std::vector<Cone> drawCones();
+  std::vector<slamtypes::Vector3d> drawPoses();
+  slamtypes::Vector3d drawCurrentPose();
+  std::vector<std::vector<int>> drawGraph();
+
+  // ---- seam to the (unchanged) front half ----
+  void setOdometry(double x, double y, double heading);       // what nextPose stores (slam.cpp:207-209)
+  void setYawRate(float yawRate, double secondsSinceYaw);     // nextYawRate + the delta of slam.cpp:309
+  void performSLAM(slamtypes::MatrixXd Cones);                // slam.cpp:298-338 (private there)
+  std::function<void(const slamtypes::Vector3d&)> onSendPose;                         // sendPose 681-695
+  std::function<void(const std::vector<Cone>&, uint32_t, const slamtypes::Vector3d&)> onSendCones;  // 656-679
+
+  // ---- introspection for tests ----
+  bool loopClosing() const { return m_loopClosing; }
+  bool loopClosingComplete() const { return m_loopClosingComplete; }
+  uint32_t currentConeIndex() const { return m_currentConeIndex; }
+  int poseId() const { return m_poseId; }
+  int optimizeCalls() const { return m_optimizeCalls; }
+  int lastIterations() const { return m_lastIterations; }
+  const std::vector<double>& chi2Log() const { return m_chi2Log; }
+  const std::vector<int32_t>& lastIdx() const { return m_lastIdx; }
+  const std::vector<int32_t>& lastStatus() const { return m_lastStatus; }
+  int lastFrameKind() const { return m_lastFrameKind; }
+  slam_b200_ctx* backend() { return m_ctx; }
+  int getPoseEstimate(int id, double out[3]);
+
+ private:
+  void setUp(std::map<std::string, std::string> commandlineArguments);
+  void setupOptimizer();
+  void tearDown();
+  void addOdometryMeasurement(slamtypes::Vector3d pose);
+  void optimizeGraph();
+  void localizer(slamtypes::Vector3d pose, slamtypes::MatrixXd cones);
+  slamtypes::Vector3d updatePoseFromGraph();
+  void addPoseToGraph(slamtypes::Vector3d pose);
+  void addConesToMap(slamtypes::MatrixXd cones, slamtypes::Vector3d pose);
+  void addConeMeasurement(Cone cone, const double xyMeasurement[2]);
+  void addConeToGraph(Cone cone, const double xyMeasurement[2]);
+  void updateMap();
+  void sendCones();
+  void sendPose();
+
+  /* Member variables (names as in src/slam.hpp:96-136) */
+  slam_b200_ctx* m_ctx = nullptr;  // replaces g2o::SparseOptimizer m_optimizer (slam.hpp:98)
+  int32_t m_timeDiffMilliseconds = 110;
+  std::mutex m_sensorMutex;
+  std::mutex m_mapMutex;
+  std::mutex m_optimizerMutex;
+  std::mutex m_yawMutex;
+  slamtypes::Vector3d m_odometryData;
+  std::array<double, 2> m_gpsReference;
+  std::vector<Cone> m_map;
+  std::vector<slamtypes::Vector3d> m_poses = {};
+  std::vector<std::vector<int>> m_connectivityGraph = {};
+  double m_newConeThreshold = 1;
+  double m_timeBetweenKeyframes = 0.5;
+  double m_coneMappingThreshold = 67;
+  uint32_t m_currentConeIndex = 0;
+  int m_poseId = 1000;
+  uint32_t m_conesPerPacket = 20;
+  bool m_sendConeData = false;
+  bool m_sendPoseData = false;
+  bool m_loopClosing = false;
+  bool m_loopClosingComplete = false;
+  slamtypes::Vector3d m_sendPose;
+  std::mutex m_sendMutex;
+  uint32_t m_senderStamp = 0;
+  float m_yawRate = 0.0f;
+  double m_yawElapsed = 0.0;
+
+  // bookkeeping the tests read
+  int m_optimizeCalls = 0, m_lastIterations = 0, m_lastFrameKind = 0;
+  std::vector<double> m_chi2Log;
+  std::vector<int32_t> m_lastIdx, m_lastStatus;
+};

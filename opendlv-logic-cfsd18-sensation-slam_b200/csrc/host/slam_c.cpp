@@ -1,0 +1,115 @@
+// slam_c.cpp -- flat C wrappers around the C++ Slam mirror so the Python tests can drive it the way
+// the reference's frame-gathering thread drives Slam::performSLAM.
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "slam.hpp"
+
+namespace {
+thread_local std::string g_err;
+}
+
+extern "C" {
+
+const char* slamhost_last_error() { return g_err.c_str(); }
+
+void* slamhost_create(double sameConeThreshold, double coneMappingThreshold, int conesPerPacket, int cudaDevice) {
+  try {
+    std::map<std::string, std::string> args;
+    args["gatheringTimeMs"] = "110";
+    args["sameConeThreshold"] = std::to_string(sameConeThreshold);
+    args["refLatitude"] = "57.70924648";
+    args["refLongitude"] = "11.9462";
+    args["timeBetweenKeyframes"] = "0.5";
+    args["coneMappingThreshold"] = std::to_string(coneMappingThreshold);
+    args["conesPerPacket"] = std::to_string(conesPerPacket);
+    args["id"] = "120";
+    args["cudaDevice"] = std::to_string(cudaDevice);
+    return new Slam(args);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+// missing-key behaviour of the reference constructor (std::stoi throws, slam.cpp:739-747)
+int slamhost_create_missing_key_throws() {
+  try {
+    std::map<std::string, std::string> args;
+    args["sameConeThreshold"] = "1.2";
+    Slam s(args);
+    return 0;
+  } catch (const std::exception&) {
+    return 1;
+  }
+}
+
+void slamhost_destroy(void* h) { delete static_cast<Slam*>(h); }
+
+// one frame: what initializeCollection hands to performSLAM (slam.cpp:254) after nextPose stored
+// the odometry.  Returns the frame kind (-1 rejected, 0 mapping, 1 loop closed, 2 localiser) or -100.
+int slamhost_perform(void* h, const double* cones4xN, int n, const double* pose3, float yawRate, double yawElapsed,
+                     int32_t* idx, int32_t* status) {
+  try {
+    Slam& s = *static_cast<Slam*>(h);
+    s.setOdometry(pose3[0], pose3[1], pose3[2]);
+    s.setYawRate(yawRate, yawElapsed);
+    slamtypes::MatrixXd m(4, n);
+    if (n) std::memcpy(m.data(), cones4xN, sizeof(double) * 4 * (size_t)n);
+    s.performSLAM(m);
+    for (int i = 0; i < n; i++) {
+      idx[i] = s.lastIdx()[i];
+      status[i] = s.lastStatus()[i];
+    }
+    return s.lastFrameKind();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -100;
+  }
+}
+
+// [currentConeIndex, poseId, loopClosing, loopClosingComplete, optimizeCalls, lastIterations, nChi2, mapSize]
+void slamhost_state(void* h, int* out8) {
+  Slam& s = *static_cast<Slam*>(h);
+  out8[0] = (int)s.currentConeIndex(); out8[1] = s.poseId(); out8[2] = s.loopClosing();
+  out8[3] = s.loopClosingComplete(); out8[4] = s.optimizeCalls(); out8[5] = s.lastIterations();
+  out8[6] = (int)s.chi2Log().size(); out8[7] = (int)s.drawCones().size();
+}
+void slamhost_chi2_log(void* h, double* out) {
+  Slam& s = *static_cast<Slam*>(h);
+  for (size_t k = 0; k < s.chi2Log().size(); k++) out[k] = s.chi2Log()[k];
+}
+void slamhost_draw_cones(void* h, double* x, double* y, int* type, int* id) {
+  std::vector<Cone> m = static_cast<Slam*>(h)->drawCones();
+  for (size_t j = 0; j < m.size(); j++) { x[j] = m[j].getX(); y[j] = m[j].getY(); type[j] = m[j].getType(); id[j] = m[j].getId(); }
+}
+int slamhost_draw_poses(void* h, double* out3, int cap) {
+  std::vector<slamtypes::Vector3d> p = static_cast<Slam*>(h)->drawPoses();
+  for (size_t k = 0; k < p.size() && (int)k < cap; k++) { out3[3 * k] = p[k](0); out3[3 * k + 1] = p[k](1); out3[3 * k + 2] = p[k](2); }
+  return (int)p.size();
+}
+void slamhost_draw_current_pose(void* h, double* out3) {
+  slamtypes::Vector3d p = static_cast<Slam*>(h)->drawCurrentPose();
+  out3[0] = p(0); out3[1] = p(1); out3[2] = p(2);
+}
+// flattened drawGraph(): counts[k] = edges of pose k; flat = concatenated cone ids; returns number of poses
+int slamhost_draw_graph(void* h, int* counts, int cap_counts, int* flat, int cap_flat) {
+  std::vector<std::vector<int>> g = static_cast<Slam*>(h)->drawGraph();
+  int q = 0;
+  for (size_t k = 0; k < g.size(); k++) {
+    if ((int)k < cap_counts) counts[k] = (int)g[k].size();
+    for (int c : g[k]) { if (q < cap_flat) flat[q] = c; q++; }
+  }
+  return (int)g.size();
+}
+int slamhost_pose_estimate(void* h, int id, double* out3) { return static_cast<Slam*>(h)->getPoseEstimate(id, out3); }
+// Cone::getDirection / getDistance (src/cone.cpp:34-53)
+void slamhost_cone_bearing(double cx, double cy, const double* pose3, float* az, float* dist) {
+  Cone c(cx, cy, 1, 0);
+  slamtypes::Vector3d p(pose3[0], pose3[1], pose3[2]);
+  *az = c.getDirection(p).azimuthAngle;
+  *dist = c.getDistance(p).distance;
+}
+
+}  // extern "C"

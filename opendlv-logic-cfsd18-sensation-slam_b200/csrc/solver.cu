@@ -200,8 +200,7 @@ bool g_attr_set = false;
 
 int graph_enqueue_update(slam_b200_ctx* c);  // graph.cu
 
-int graph_enqueue_solve(slam_b200_ctx* c) {
-  DeviceSystem& D = *c->sys;
+static int solver_init_attrs(slam_b200_ctx* c) {
   if (!g_attr_set) {
     int lim = c->max_smem_optin;
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -209,9 +208,22 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     g_attr_set = true;
   }
+  return 0;
+}
+
+int graph_enqueue_solve(slam_b200_ctx* c) {
+  DeviceSystem& D = *c->sys;
+  if (int rc = solver_init_attrs(c)) return rc;
   SymArgs S = sym_args(D);
   const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
   const int nlv = (int)D.levels.size();
+  auto mark = [&]() {
+    if (!D.profile) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    D.prof_events.push_back(e);
+  };
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
     if (LL.n_small) {
@@ -227,6 +239,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       c->launches++;
     }
   }
+  mark();  // factored
   // solves: a level's fronts either all stage their L panel in shared memory or none does
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
@@ -257,6 +270,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     }
     c->launches++;
   }
+  mark();  // forward done
   for (int lv = nlv - 1; lv >= 0; lv--) {
     const LevelLaunch& LL = D.levels[lv];
     int nfr = LL.n_small + LL.n_big;
@@ -279,5 +293,64 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     c->launches++;
   }
   SLAM_CUDA_TRY(c, cudaGetLastError());
-  return graph_enqueue_update(c);
+  mark();  // backward done
+  int rc = graph_enqueue_update(c);
+  mark();  // updated
+  return rc;
+}
+
+// One Gauss-Newton iteration.  Kernel arguments do not change between iterations (the chi2 slot
+// is a device-side counter), so the ~40 launches are captured once into a CUDA graph and replayed.
+int graph_enqueue_iteration(slam_b200_ctx* c) {
+  DeviceSystem& D = *c->sys;
+  static const bool env_no_graph = getenv("SLAM_B200_NO_CUDA_GRAPH") != nullptr;
+  // the legacy / per-thread default streams cannot be captured
+  const bool no_graph = env_no_graph || c->stream == nullptr || c->stream == cudaStreamLegacy ||
+                        c->stream == cudaStreamPerThread;
+  if (int rc = solver_init_attrs(c)) return rc;
+  if (D.profile || no_graph) {
+    if (D.profile) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, c->stream);
+      D.prof_events.push_back(e);
+    }
+    int rc = graph_enqueue_assemble(c, 0, D.P, false);
+    if (rc) return rc;
+    if (D.profile) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, c->stream);
+      D.prof_events.push_back(e);
+    }
+    return graph_enqueue_solve(c);
+  }
+  if (!D.iter_graph) {
+    long before = c->launches;
+    cudaGraph_t graph = nullptr;
+    SLAM_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = graph_enqueue_assemble(c, 0, D.P, false);
+    if (!rc) rc = graph_enqueue_solve(c);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    c->launches = before;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    SLAM_CUDA_TRY(c, e);
+    SLAM_CUDA_TRY(c, cudaGraphInstantiate(&D.iter_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    D.launches_per_iter = 0;
+    {
+      // count the kernel nodes once: bookkeeping for slam_b200_launch_count
+      // (assemble 2 + per level factor/forward/backward + update)
+      int n = 2 + 1;
+      for (const LevelLaunch& LL : D.levels) {
+        n += (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);
+        n += (LL.n_small + LL.n_big) ? 2 : 0;
+      }
+      D.launches_per_iter = n;
+    }
+  }
+  SLAM_CUDA_TRY(c, cudaGraphLaunch(D.iter_graph, c->stream));
+  c->launches += D.launches_per_iter;
+  D.assembled = true;
+  return 0;
 }

@@ -362,9 +362,16 @@ def cone_field(n_map=1_000_000, n_obs=100_000, seed=4, density=0.1, sigma=0.2, f
     mt = rng.integers(n_map, 1, 5).astype(np.int32)
     pose = np.array([0.0, 0.0, 0.3])
     n_m = int(round(n_obs * frac_matched))
-    pick = rng.integers(n_m, 0, n_map)
-    gx = np.concatenate([mx[pick] + sigma * rng.normal(n_m), (rng.uniform(n_obs - n_m) - 0.5) * side])
-    gy = np.concatenate([my[pick] + sigma * rng.normal(n_m), (rng.uniform(n_obs - n_m) - 0.5) * side])
+    # The reference conversion folds anything behind the vehicle to the front (asin in
+    # transformConeToCoG, slam.cpp:518), like a forward-looking lidar: observe only cones ahead.
+    c, s = np.cos(pose[2]), np.sin(pose[2])
+    ahead = np.nonzero(c * (mx - pose[0]) + s * (my - pose[1]) > LIDAR_TO_COG + 2.0)[0]
+    pick = ahead[rng.integers(n_m, 0, len(ahead))]
+    n_u = n_obs - n_m
+    ux = 2.0 + LIDAR_TO_COG + rng.uniform(n_u) * (0.5 * side - 4.0)      # vehicle frame, ahead
+    uy = (rng.uniform(n_u) - 0.5) * side
+    gx = np.concatenate([mx[pick] + sigma * rng.normal(n_m), pose[0] + c * ux - s * uy])
+    gy = np.concatenate([my[pick] + sigma * rng.normal(n_m), pose[1] + s * ux + c * uy])
     ty = np.concatenate([mt[pick], rng.integers(n_obs - n_m, 1, 5).astype(np.int32)]).astype(np.float64)
     sh = rng.integers(n_obs, 0, 1 << 62)
     perm = np.argsort(sh, kind="stable")

@@ -172,28 +172,16 @@ class OracleGraph:
         return self.L.orc_graph_set_fixed(self.h, int(vid), int(bool(flag)))
 
     def load_soa(self, g):
-        """Vertices in id order of creation (landmarks then poses is NOT required: the Hessian
-        order is by id, slam.hpp:118); edges: odometry and landmark edges interleaved the way
-        performSLAM inserts them (pose k's odometry edge, then pose k's cone edges)."""
-        for i, vid in enumerate(g.lm_ids):
-            self.add_landmark(vid, g.lm_est[i, 0], g.lm_est[i, 1])
-        for i, vid in enumerate(g.pose_ids):
-            self.add_pose(vid, *g.pose_est[i])
-        # interleave by pose of origin (stable): odometry edge into pose k first
-        pos = {int(v): k for k, v in enumerate(g.pose_ids)}
-        el_by_pose = {}
-        for e in range(len(g.el_pose)):
-            el_by_pose.setdefault(int(g.el_pose[e]), []).append(e)
-        eo_by_to = {}
-        for e in range(len(g.eo_to)):
-            eo_by_to.setdefault(int(g.eo_to[e]), []).append(e)
-        for vid in g.pose_ids:
-            for e in eo_by_to.get(int(vid), []):
-                self.add_edge_se2(g.eo_from[e], g.eo_to[e], g.eo_z[e], g.eo_info[e])
-            for e in el_by_pose.get(int(vid), []):
-                self.add_edge_se2_xy(g.el_pose[e], g.el_lm[e], g.el_z[e], g.el_info[e])
-        for vid in g.fixed_ids:
-            self.set_fixed(vid, True)
+        """Vertices: landmarks then poses (the Hessian order is by id anyway, slam.hpp:118); edges
+        interleaved the way performSLAM inserts them (pose k's odometry edge, then its cone edges)."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        a = [i32(g.pose_ids), f64(g.pose_est), i32(g.lm_ids), f64(g.lm_est), i32(g.eo_from), i32(g.eo_to), f64(g.eo_z),
+             f64(g.eo_info), i32(g.el_pose), i32(g.el_lm), f64(g.el_z), f64(g.el_info), i32(g.fixed_ids)]
+        rc = self.L.orc_graph_load(self.h, len(a[0]), _ip(a[0]), _dp(a[1]), len(a[2]), _ip(a[2]), _dp(a[3]),
+                                   len(a[4]), _ip(a[4]), _ip(a[5]), _dp(a[6]), _dp(a[7]),
+                                   len(a[8]), _ip(a[8]), _ip(a[9]), _dp(a[10]), _dp(a[11]), len(a[12]), _ip(a[12]))
+        assert rc == 0
 
     def optimize(self, iters=10):
         chi2 = np.zeros(max(iters, 1))

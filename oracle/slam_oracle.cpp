@@ -1260,3 +1260,38 @@ void orc_slam_send_pose(void* p, double* out3) {
 void* orc_slam_graph(void* p) { return static_cast<OracleSlam*>(p)->graph; }
 
 }  // extern "C"
+
+// Bulk loader (same insertion order as performSLAM produces: all landmark and pose vertices, then
+// per pose its incoming odometry edge(s) followed by its cone edges), so large graphs load fast.
+extern "C" int orc_graph_load(void* g, int P, const int* pose_ids, const double* pose_est3, int L,
+                              const int* lm_ids, const double* lm_est2, int Eo, const int* eo_from,
+                              const int* eo_to, const double* eo_z3, const double* eo_info9, int El,
+                              const int* el_pose, const int* el_lm, const double* el_z2,
+                              const double* el_info4, int nfixed, const int* fixed_ids) {
+  for (int l = 0; l < L; l++)
+    if (orc_graph_add_landmark(g, lm_ids[l], lm_est2[2 * l], lm_est2[2 * l + 1])) return -1;
+  for (int p = 0; p < P; p++)
+    if (orc_graph_add_pose(g, pose_ids[p], pose_est3[3 * p], pose_est3[3 * p + 1], pose_est3[3 * p + 2])) return -1;
+  std::map<int, int> pos;
+  for (int p = 0; p < P; p++) pos[pose_ids[p]] = p;
+  std::vector<std::vector<int>> eoBy(P), elBy(P);
+  for (int e = 0; e < Eo; e++) {
+    auto it = pos.find(eo_to[e]);
+    if (it == pos.end()) return -1;
+    eoBy[it->second].push_back(e);
+  }
+  for (int e = 0; e < El; e++) {
+    auto it = pos.find(el_pose[e]);
+    if (it == pos.end()) return -1;
+    elBy[it->second].push_back(e);
+  }
+  for (int p = 0; p < P; p++) {
+    for (int e : eoBy[p])
+      if (orc_graph_add_edge_se2(g, eo_from[e], eo_to[e], eo_z3 + 3 * (size_t)e, eo_info9 + 9 * (size_t)e)) return -1;
+    for (int e : elBy[p])
+      if (orc_graph_add_edge_se2_xy(g, el_pose[e], el_lm[e], el_z2 + 2 * (size_t)e, el_info4 + 4 * (size_t)e)) return -1;
+  }
+  for (int k = 0; k < nfixed; k++)
+    if (orc_graph_set_fixed(g, fixed_ids[k], 1)) return -1;
+  return 0;
+}

@@ -1,0 +1,154 @@
+"""The C++ Slam mirror (csrc/host/slam.cpp, the reference's class interface over the C ABI) replayed
+frame by frame against the restated reference back half in the oracle: configuration C1."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+
+
+@pytest.fixture(scope="module")
+def host(pkg):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    pkg.build()
+    from importlib import import_module
+    b = import_module(pkg.__name__ + "._build")
+    L = C.CDLL(b.HOSTLIB)
+    L.slamhost_create.restype = C.c_void_p
+    L.slamhost_create.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+    L.slamhost_destroy.argtypes = [C.c_void_p]
+    L.slamhost_perform.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.c_float, C.c_double, c_ip, c_ip]
+    L.slamhost_last_error.restype = C.c_char_p
+    for n in ("slamhost_state", "slamhost_chi2_log", "slamhost_draw_cones", "slamhost_draw_poses",
+              "slamhost_draw_current_pose", "slamhost_draw_graph", "slamhost_pose_estimate"):
+        getattr(L, n).argtypes = None
+    return L
+
+
+class HostSlam:
+    def __init__(self, L, thr, map_thr):
+        self.L = L
+        self.h = C.c_void_p(L.slamhost_create(thr, map_thr, 20, 0))
+        assert self.h, L.slamhost_last_error()
+
+    def close(self):
+        self.L.slamhost_destroy(self.h)
+
+    def perform(self, frame, pose, yaw=0.0, dt=0.0):
+        frame = np.asfortranarray(frame, dtype=np.float64); pose = np.ascontiguousarray(pose, dtype=np.float64)
+        n = frame.shape[1]
+        idx = np.zeros(max(n, 1), dtype=np.int32); st = np.zeros(max(n, 1), dtype=np.int32)
+        rc = self.L.slamhost_perform(self.h, frame.ctypes.data_as(c_dp), n, pose.ctypes.data_as(c_dp), yaw, dt,
+                                     idx.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip))
+        assert rc != -100, self.L.slamhost_last_error()
+        return rc, idx[:n], st[:n]
+
+    def state(self):
+        out = np.zeros(8, dtype=np.int32)
+        self.L.slamhost_state(self.h, out.ctypes.data_as(c_ip))
+        return out
+
+    def chi2(self):
+        n = self.state()[6]
+        out = np.zeros(max(n, 1))
+        self.L.slamhost_chi2_log(self.h, out.ctypes.data_as(c_dp))
+        return out[:n]
+
+    def cones(self):
+        M = self.state()[7]
+        x = np.zeros(max(M, 1)); y = np.zeros(max(M, 1)); t = np.zeros(max(M, 1), dtype=np.int32); i = np.zeros(max(M, 1), dtype=np.int32)
+        self.L.slamhost_draw_cones(self.h, x.ctypes.data_as(c_dp), y.ctypes.data_as(c_dp), t.ctypes.data_as(c_ip), i.ctypes.data_as(c_ip))
+        return x[:M], y[:M], t[:M], i[:M]
+
+    def poses(self, cap=4096):
+        out = np.zeros((cap, 3))
+        n = self.L.slamhost_draw_poses(self.h, out.ctypes.data_as(c_dp), cap)
+        return out[:n]
+
+    def graph(self, cap=4096, capf=65536):
+        cnt = np.zeros(cap, dtype=np.int32); flat = np.zeros(capf, dtype=np.int32)
+        n = self.L.slamhost_draw_graph(self.h, cnt.ctypes.data_as(c_ip), cap, flat.ctypes.data_as(c_ip), capf)
+        return cnt[:n], flat[:cnt[:n].sum()]
+
+    def pose_estimate(self, vid):
+        out = np.zeros(3)
+        d = self.L.slamhost_pose_estimate(self.h, int(vid), out.ctypes.data_as(c_dp))
+        return d, out
+
+    def current_pose(self):
+        out = np.zeros(3)
+        self.L.slamhost_draw_current_pose(self.h, out.ctypes.data_as(c_dp))
+        return out
+
+
+def test_c1_replay_through_slam_class(host, orc, synth, c1_drive):
+    s = HostSlam(host, synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    o = orc.slam(synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    kinds = []
+    for k, (fr, p) in enumerate(zip(c1_drive.frames, c1_drive.poses_noisy)):
+        rc, idx, st = s.perform(fr, p)
+        rco, idxo, sto = o.perform(fr, p)
+        assert rc == rco, k
+        assert np.array_equal(idx, idxo) and np.array_equal(st, sto), k     # association bit-exact
+        kinds.append(rc)
+    assert 1 in kinds and 2 in kinds                                         # closed the loop, then localised
+    so = o.state(); sd = s.state()
+    assert sd[0] == so["current_cone_index"] and sd[1] == so["pose_id"]
+    assert sd[3] == 1 and sd[4] == so["optimize_calls"] and sd[5] == so["last_iterations"] == 10
+    assert np.allclose(s.chi2(), o.chi2_log(), rtol=1e-8)
+    x, y, t, ids = s.cones(); ox, oy, ot = o.map()
+    assert np.array_equal(t, ot) and np.array_equal(ids, np.arange(len(ids)))
+    scale = max(1.0, np.abs(ox).max(), np.abs(oy).max())
+    assert np.max(np.abs(x - ox)) <= 1e-6 * scale and np.max(np.abs(y - oy)) <= 1e-6 * scale
+    # optimised poses (graph vertices), first/last and a few in between
+    for vid in [1000, 1001, 1002, 1500, 1973, 1974, 1999]:
+        d, e = s.pose_estimate(vid)
+        assert d == 3 and np.max(np.abs(e - o.pose(vid))) <= 1e-6 * scale, vid
+    assert np.allclose(s.current_pose(), o.send_pose(), rtol=0, atol=1e-6 * scale)
+    assert len(s.poses()) == 1000
+    cnt, flat = s.graph()
+    assert len(cnt) == 1000 and cnt.sum() == so["n_edges"] - 999            # cone edges; odometry edges excluded
+    s.close()
+
+
+def test_burst_of_optimise_calls_and_gates(host, orc, synth, c1_drive):
+    """Closing column first in its frame -> one optimise per remaining column (slam.cpp:625-633);
+    a pose outside +-200 m is rejected (300-303); the yaw-rate heading correction (315-317)."""
+    frames = [f.copy(order="F") for f in c1_drive.frames]
+    probe = orc.slam(synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    for k, (fr, p) in enumerate(zip(frames, c1_drive.poses_noisy)):
+        if probe.perform(fr, p)[0] == 1:
+            break
+    frames[k] = np.asfortranarray(frames[k][:, ::-1])
+    s = HostSlam(host, synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    o = orc.slam(synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    assert s.perform(frames[0], np.array([250.0, 0.0, 0.0]))[0] == -1
+    assert o.perform(frames[0], np.array([250.0, 0.0, 0.0]))[0] == -1
+    for q in range(k + 1):
+        yaw, dt = (0.05, 0.2) if q % 5 == 0 else (0.0, 0.0)
+        rc, idx, st = s.perform(frames[q], c1_drive.poses_noisy[q], yaw, dt)
+        rco, idxo, sto = o.perform(frames[q], c1_drive.poses_noisy[q], np.float32(yaw), dt)
+        assert rc == rco and np.array_equal(idx, idxo) and np.array_equal(st, sto), q
+    n_cols = frames[k].shape[1]
+    assert s.state()[4] == o.state()["optimize_calls"] == n_cols            # closing column was column 0
+    assert np.allclose(s.chi2(), o.chi2_log(), rtol=1e-7)
+    x, y, _, _ = s.cones(); ox, oy, _ = o.map()
+    assert np.allclose(x, ox, rtol=0, atol=1e-4) and np.allclose(y, oy, rtol=0, atol=1e-4)
+    s.close()
+
+
+def test_constructor_and_cone_accessors(host):
+    assert host.slamhost_create_missing_key_throws() == 1                  # std::stoi throws (slam.cpp:739)
+    az = C.c_float(); dist = C.c_float()
+    pose = np.array([1.0, 2.0, 30.0])
+    host.slamhost_cone_bearing(C.c_double(4.0), C.c_double(6.0), pose.ctypes.data_as(c_dp), C.byref(az), C.byref(dist))
+    assert dist.value == pytest.approx(5.0)
+    want = np.degrees(np.arctan2(4.0, 3.0)) - 30.0 / 57.295779513082325      # src/cone.cpp:37-39
+    assert az.value == pytest.approx(np.float32(want), rel=1e-6)
