@@ -169,6 +169,9 @@ int slam_b200_graph_chi2(slam_b200_ctx* ctx, double* chi2);
 /* Uploads the graph and runs the host symbolic phase (index mapping, block structure, ordering,
  * assembly tree) if the structure changed.  Returns the scalar dimension of the system. */
 int slam_b200_graph_prepare(slam_b200_ctx* ctx);
+/* Like prepare but without the symbolic phase: only slam_b200_graph_assemble_async / export /
+ * chi2 are valid afterwards (used to measure the edge-partitioned assembly of very large graphs). */
+int slam_b200_graph_prepare_assembly_only(slam_b200_ctx* ctx);
 /* Enqueues `iters` Gauss-Newton iterations on the stream without any host synchronisation or
  * copy.  Status / chi2 stay on the device until slam_b200_graph_finish. */
 int slam_b200_graph_iterate_async(slam_b200_ctx* ctx, int iters);

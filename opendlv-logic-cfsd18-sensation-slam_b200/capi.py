@@ -47,7 +47,7 @@ def lib():
         L.slam_b200_symbolic_stat.argtypes = [C.c_void_p, C.c_int]
         L.slam_b200_symbolic_destroy.argtypes = [C.c_void_p]
         for name in ("slam_b200_destroy", "slam_b200_sync", "slam_b200_map_clear", "slam_b200_map_size",
-                     "slam_b200_graph_clear", "slam_b200_graph_prepare", "slam_b200_graph_num_poses",
+                     "slam_b200_graph_clear", "slam_b200_graph_prepare", "slam_b200_graph_prepare_assembly_only", "slam_b200_graph_num_poses",
                      "slam_b200_graph_num_landmarks", "slam_b200_graph_num_edges", "slam_b200_launch_count",
                      "slam_b200_graph_reset_device", "slam_b200_graph_solve_async", "slam_b200_graph_snapshot",
                      "slam_b200_graph_restore_async"):
@@ -260,6 +260,9 @@ class Context:
 
     def graph_prepare(self):
         return self._ck(self.L.slam_b200_graph_prepare(self.h), "graph_prepare")
+
+    def graph_prepare_assembly_only(self):
+        return self._ck(self.L.slam_b200_graph_prepare_assembly_only(self.h), "graph_prepare_assembly_only")
 
     def graph_iterate_async(self, iters):
         self._ck(self.L.slam_b200_graph_iterate_async(self.h, int(iters)), "graph_iterate_async")

@@ -413,10 +413,11 @@ __global__ void bbox_kernel(const double* __restrict__ x, const double* __restri
   }
 }
 
-struct GridParams { double x0, y0, inv; int nx, ny; };
+struct GridParams { double x0, y0, inv, h; int nx, ny; };
 
 __device__ __forceinline__ int cell_coord(double v, double v0, double inv) {
-  // floor((v - v0) * inv): monotone in v, so |a-b| < cell  =>  cells differ by at most 1
+  // floor((v - v0) * inv): monotone non-decreasing in v (fp subtract and multiply by a positive
+  // constant are monotone), which is all the bucket argument needs
   return (int)floor((v - v0) * inv);
 }
 
@@ -433,8 +434,7 @@ __global__ void grid_count_kernel(const double* __restrict__ x, const double* __
 
 __global__ void grid_fill_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                  const int* __restrict__ type, int M, GridParams gp,
-                                 int* __restrict__ cursor, double* __restrict__ sx,
-                                 double* __restrict__ sy, int2* __restrict__ sti) {
+                                 int* __restrict__ cursor, GridRec* __restrict__ rec) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   double a = x[i], b = y[i];
@@ -442,18 +442,46 @@ __global__ void grid_fill_kernel(const double* __restrict__ x, const double* __r
   int cx = min(max(cell_coord(a, gp.x0, gp.inv), 0), gp.nx - 1);
   int cy = min(max(cell_coord(b, gp.y0, gp.inv), 0), gp.ny - 1);
   int slot = atomicAdd(cursor + (size_t)cy * gp.nx + cx, 1);
-  sx[slot] = a;
-  sy[slot] = b;
-  sti[slot] = make_int2(type[i], i);
+  GridRec r;
+  r.x = a; r.y = b; r.type = type[i]; r.idx = i; r.pad0 = 0; r.pad1 = 0;
+  rec[slot] = r;
 }
 
-// bucketed: one thread per observation; the 3x3 cell neighbourhood is three contiguous runs of the
-// cell-sorted map; the answer is the minimum ORIGINAL index over gated candidates.
+// bucketed: one thread per observation.  Cells are 2*h wide (h = threshold plus a 1e-9 relative
+// margin), so the disc of radius thr around the observation overlaps at most 2 x 2 cells = two
+// contiguous runs of the cell-sorted map.  Every cone is one aligned 32-byte record (one DRAM
+// sector); the records of a run are fetched four at a time before any is tested, so the dependent
+// chain per observation is: observation -> cell table -> records.  The answer is the minimum
+// ORIGINAL index over the gated candidates (= the reference's first fit, slam.cpp:575-607).
+template <int GATE>
+__device__ __forceinline__ void scan_run(const GridRec* __restrict__ rec, int s, int e, double gx, double gy,
+                                         double ot, int oti, double thr2x, int& best) {
+  for (int k = s; k < e; k += 4) {
+    double2 xy[4];
+    int4 ti[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (k + q < e) {
+        const double2* p = reinterpret_cast<const double2*>(rec + k + q);
+        xy[q] = __ldg(p);
+        ti[q] = __ldg(reinterpret_cast<const int4*>(p + 1));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (k + q < e) {
+        if (type_gate<GATE>(ti[q].x, ot, oti) && ti[q].y < best &&
+            cone_distance2(xy[q].x, xy[q].y, gx, gy) < thr2x)
+          best = ti[q].y;
+      }
+    }
+  }
+}
+
 template <int GATE>
 __global__ void __launch_bounds__(BULK_THREADS)
 assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, double thr2x, GridParams gp,
-                       const int* __restrict__ cell_start, const double* __restrict__ sx,
-                       const double* __restrict__ sy, const int2* __restrict__ sti,
+                       const int* __restrict__ cell_start, const GridRec* __restrict__ rec,
                        int* __restrict__ idx) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -462,33 +490,22 @@ assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, dou
   int oti = (int)ot;
   int best = 0x7fffffff;
   if (isfinite(gx) && isfinite(gy)) {
-    double fx = floor((gx - gp.x0) * gp.inv), fy = floor((gy - gp.y0) * gp.inv);
-    // observations far outside the map's bounding box have no candidates
-    if (fx >= -1.0 && fx <= (double)gp.nx && fy >= -1.0 && fy <= (double)gp.ny) {
-      int cx = (int)fx, cy = (int)fy;
-      int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, gp.nx - 1);
-      // clamped border cells also hold cones whose raw cell fell outside; they are within
-      // [x_lo, x_hi] whenever they can be within one cell of the observation
-      if (x_lo <= x_hi) {
-        int rs[3], re[3];
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++) {
-          int row = cy + dy;
-          bool ok = row >= 0 && row < gp.ny;
-          size_t base = (size_t)(ok ? row : 0) * gp.nx;
-          rs[dy + 1] = ok ? __ldg(cell_start + base + x_lo) : 0;
-          re[dy + 1] = ok ? __ldg(cell_start + base + x_hi + 1) : 0;
-        }
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-          for (int k = rs[r]; k < re[r]; k++) {
-            int2 ti = __ldg(sti + k);
-            if (type_gate<GATE>(ti.x, ot, oti) && ti.y < best &&
-                cone_distance2(__ldg(sx + k), __ldg(sy + k), gx, gy) < thr2x)
-              best = ti.y;
-          }
-        }
+    const double fx0 = floor((gx - gp.h - gp.x0) * gp.inv), fx1 = floor((gx + gp.h - gp.x0) * gp.inv);
+    const double fy0 = floor((gy - gp.h - gp.y0) * gp.inv), fy1 = floor((gy + gp.h - gp.y0) * gp.inv);
+    // observations whose disc misses the map's bounding box have no candidates
+    if (fx1 >= 0.0 && fx0 <= (double)(gp.nx - 1) && fy1 >= 0.0 && fy0 <= (double)(gp.ny - 1)) {
+      const int cx0 = (int)fmax(fx0, 0.0), cx1 = (int)fmin(fx1, (double)(gp.nx - 1));
+      const int cy0 = (int)fmax(fy0, 0.0), cy1 = (int)fmin(fy1, (double)(gp.ny - 1));
+      const size_t b0 = (size_t)cy0 * gp.nx;
+      const int s0 = __ldg(cell_start + b0 + cx0), e0 = __ldg(cell_start + b0 + cx1 + 1);
+      int s1 = 0, e1 = 0;
+      if (cy1 > cy0) {
+        const size_t b1 = (size_t)cy1 * gp.nx;
+        s1 = __ldg(cell_start + b1 + cx0);
+        e1 = __ldg(cell_start + b1 + cx1 + 1);
       }
+      scan_run<GATE>(rec, s0, e0, gx, gy, ot, oti, thr2x, best);
+      scan_run<GATE>(rec, s1, e1, gx, gy, ot, oti, thr2x, best);
     }
   }
   idx[i] = best == 0x7fffffff ? -1 : best;
@@ -688,10 +705,12 @@ int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) {
   SLAM_CUDA_TRY(c, cudaMemcpyAsync(bb, c->grid_bbox.p, sizeof(bb), cudaMemcpyDeviceToHost, c->stream));
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   if (!(bb[0] <= bb[2])) { bb[0] = bb[1] = 0; bb[2] = bb[3] = 0; }  // no finite cone
-  // cells are (1 + 1e-9) * cell wide: a pair closer than `cell` then provably lands in adjacent
-  // cells even after the rounding of (v - x0) * inv (relative 2^-52 on coordinates <= 1e6 cells)
-  double width = cell * (1.0 + 1e-9);
+  // query half-width h = cell * (1 + 1e-9) (covers the rounding of the exact gate, which admits
+  // |dx| up to thr * (1 + a few ulp)); cell width = 2 h (1 + 1e-9) so [g-h, g+h] spans <= 2 cells
+  // even after the rounding of (v - x0) * inv (relative 2^-52 on <= 1e6 cells)
   GridParams gp;
+  gp.h = cell * (1.0 + 1e-9);
+  double width = 2.0 * gp.h * (1.0 + 1e-9);
   gp.x0 = bb[0];
   gp.y0 = bb[1];
   gp.inv = 1.0 / width;
@@ -708,9 +727,7 @@ int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) {
   size_t ncell = (size_t)gp.nx * gp.ny;
   SLAM_CUDA_TRY(c, c->grid_cell_start.exact(ncell + 1));
   SLAM_CUDA_TRY(c, c->grid_cursor.exact(ncell + 1));
-  SLAM_CUDA_TRY(c, c->grid_x.exact(M));
-  SLAM_CUDA_TRY(c, c->grid_y.exact(M));
-  SLAM_CUDA_TRY(c, c->grid_ti.exact(M));
+  SLAM_CUDA_TRY(c, c->grid_rec.exact(M));
   SLAM_CUDA_TRY(c, cudaMemsetAsync(c->grid_cursor.p, 0, sizeof(int) * (ncell + 1), c->stream));
   grid_count_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(c->map_x.p, c->map_y.p, M, gp, c->grid_cursor.p);
   c->launches++;
@@ -722,7 +739,7 @@ int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) {
   c->launches++;
   SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->grid_cursor.p, c->grid_cell_start.p, sizeof(int) * ncell, cudaMemcpyDeviceToDevice, c->stream));
   grid_fill_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(c->map_x.p, c->map_y.p, c->map_type.p, M, gp,
-                                                          c->grid_cursor.p, c->grid_x.p, c->grid_y.p, c->grid_ti.p);
+                                                          c->grid_cursor.p, c->grid_rec.p);
   c->launches++;
   SLAM_CUDA_TRY(c, cudaGetLastError());
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -732,6 +749,7 @@ int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) {
   c->grid_nx = gp.nx;
   c->grid_ny = gp.ny;
   c->grid_inv = gp.inv;
+  c->grid_h = gp.h;
   c->grid_map_version = c->map_version;
   return (int)std::min<size_t>(ncell, 0x7fffffff);
 }
@@ -767,13 +785,14 @@ int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, c
     gp.y0 = c->grid_y0;
     gp.nx = c->grid_nx;
     gp.ny = c->grid_ny;
-    gp.inv = c->grid_inv;  // the exact value the index was built with
+    gp.inv = c->grid_inv;  // the exact values the index was built with
+    gp.h = c->grid_h;
     if (gate == SLAM_B200_GATE_MAPPING)
       assoc_bulk_grid_kernel<SLAM_B200_GATE_MAPPING><<<blocks, BULK_THREADS, 0, c->stream>>>(
-          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_x.p, c->grid_y.p, c->grid_ti.p, idx_dev);
+          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_rec.p, idx_dev);
     else
       assoc_bulk_grid_kernel<SLAM_B200_GATE_LOCALIZER><<<blocks, BULK_THREADS, 0, c->stream>>>(
-          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_x.p, c->grid_y.p, c->grid_ti.p, idx_dev);
+          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_rec.p, idx_dev);
   }
   c->launches++;
   SLAM_CUDA_TRY(c, cudaGetLastError());

@@ -103,8 +103,8 @@ int slam_b200_destroy(slam_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   graph_release(c);
   c->map_x.release(); c->map_y.release(); c->map_type.release();
-  c->grid_cell_start.release(); c->grid_cursor.release(); c->grid_x.release(); c->grid_y.release();
-  c->grid_ti.release(); c->grid_bbox.release(); c->grid_tmp.release();
+  c->grid_cell_start.release(); c->grid_cursor.release(); c->grid_rec.release();
+  c->grid_bbox.release(); c->grid_tmp.release();
   c->frame_in.release(); c->frame_outd.release(); c->frame_outi.release();
   c->pin_d.release(); c->pin_i.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -329,6 +329,14 @@ int slam_b200_graph_prepare(slam_b200_ctx* c) {
   return n;
 }
 
+int slam_b200_graph_prepare_assembly_only(slam_b200_ctx* c) {
+  if (!c) return SLAM_B200_E_ARG;
+  c->assembly_only = true;
+  int n = slam_b200_graph_prepare(c);
+  c->assembly_only = false;
+  return n;
+}
+
 int slam_b200_graph_reset_device(slam_b200_ctx* c) {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
@@ -338,7 +346,7 @@ int slam_b200_graph_reset_device(slam_b200_ctx* c) {
 }
 
 int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) {
-  if (!c || !c->sys || iters < 0) return SLAM_B200_E_STATE;
+  if (!c || !c->sys || iters < 0 || c->sys->assembly_only) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
   if (D.n == 0) return 0;
@@ -424,7 +432,7 @@ long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) {
 }
 
 int slam_b200_graph_solve_async(slam_b200_ctx* c) {
-  if (!c || !c->sys || !c->sys->assembled) return SLAM_B200_E_STATE;
+  if (!c || !c->sys || !c->sys->assembled || c->sys->assembly_only) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   return graph_enqueue_solve(c);
 }
@@ -607,6 +615,8 @@ double slam_b200_symbolic_stat(void* h, int what) {
     case 2: return S.max_front;
     case 3: return S.seconds;
     case 4: return (double)(S.lptr[S.nf] + S.uptr[S.nf]);
+    case 5: return S.t_nd;
+    case 6: return S.t_md;
     default: return -1;
   }
 }

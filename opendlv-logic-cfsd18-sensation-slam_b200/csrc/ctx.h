@@ -81,6 +81,12 @@ struct PinBuf {
   }
 };
 
+// one map cone in the cell-sorted index: exactly one aligned 32-byte DRAM sector
+struct alignas(32) GridRec {
+  double x, y;
+  int type, idx, pad0, pad1;
+};
+
 // ---- host-side graph (insertion order preserved; the reference's g2o graph owns the same data) --
 struct HostGraph {
   // vertices
@@ -125,11 +131,10 @@ struct slam_b200_ctx {
   // uniform grid index over the map (assoc.cu)
   DevBuf<int> grid_cell_start;   // ncell + 1
   DevBuf<int> grid_cursor;       // ncell
-  DevBuf<double> grid_x, grid_y; // cones sorted by cell
-  DevBuf<int2> grid_ti;          // (type, original index) sorted by cell
+  DevBuf<GridRec> grid_rec;      // cones sorted by cell, one 32-byte record each
   DevBuf<double> grid_bbox;      // 4 doubles: minx, miny, maxx, maxy
   DevBuf<char> grid_tmp;         // scan workspace
-  double grid_cell = 0, grid_x0 = 0, grid_y0 = 0, grid_inv = 0;
+  double grid_cell = 0, grid_x0 = 0, grid_y0 = 0, grid_inv = 0, grid_h = 0;
   int grid_nx = 0, grid_ny = 0;
   uint64_t grid_map_version = 0;
 
@@ -143,6 +148,7 @@ struct slam_b200_ctx {
   // ---- graph ----
   HostGraph g;
   DeviceSystem* sys = nullptr;
+  bool assembly_only = false;  // prepare without the symbolic phase (assembly measurements)
 
   void fail(const std::string& m) { err = m; }
 };

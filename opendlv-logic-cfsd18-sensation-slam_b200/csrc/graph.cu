@@ -232,21 +232,28 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
   }
 }
 
-// one thread per landmark: diagonal block + rhs over the edges (with pose in [p0,p1)) that see it
+// one WARP per landmark: diagonal block + rhs over the edges (with pose in [p0,p1)) that see it.
+// A landmark is seen from tens to hundreds of poses (24 per lap on the trackdrive), so the edge list
+// is strided over the lanes and the five partial sums are combined with a fixed xor-shuffle tree
+// (deterministic).  The 2x2 part of the linearisation is recomputed from the pose instead of being
+// exchanged through memory.
+constexpr int LM_PER_BLOCK = ASM_THREADS / 32;
+
 template <bool CHI2_ONLY>
 __global__ void __launch_bounds__(ASM_THREADS)
 assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int l = blockIdx.x * LM_PER_BLOCK + (threadIdx.x >> 5);
   const int r = blockIdx.y;
   const double* est = a.est + (size_t)r * a.estStride;
   const double* meas = a.meas + (size_t)r * a.measStride;
   double* V = a.V + (size_t)r * a.nV;
   const int P = a.P, L = a.L, El = a.El;
-  if (!CHI2_ONLY && l < L && a.lm_free[l]) {
+  if (!CHI2_ONLY && l < L && a.lm_free[l]) {  // warp-uniform
     const double lx = est[3 * P + l], ly = est[3 * P + L + l];
     double h00 = 0, h01 = 0, h11 = 0, b0 = 0, b1 = 0;
     const int q0 = a.lm_start[l], q1 = a.lm_start[l + 1];
-    for (int q = q0; q < q1; q++) {
+    for (int q = q0 + lane; q < q1; q += 32) {
       const int e = a.lm_edges[q];
       if (!(a.el_flags[e] & EF_ACTIVE)) continue;
       const int p = a.el_pose[e];
@@ -266,10 +273,20 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks) {
       h01 += a00 * s + a01 * c;
       h11 += a10 * s + a11 * c;
     }
-    double* bl = V + 2 * (size_t)l;
-    bl[0] = b0; bl[1] = b1;
-    double* hl = V + 2 * (size_t)L + 4 * (size_t)l;
-    hl[0] = h00; hl[1] = h01; hl[2] = h01; hl[3] = h11;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      h00 += __shfl_xor_sync(0xffffffffu, h00, o);
+      h01 += __shfl_xor_sync(0xffffffffu, h01, o);
+      h11 += __shfl_xor_sync(0xffffffffu, h11, o);
+      b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+    }
+    if (lane == 0) {
+      double* bl = V + 2 * (size_t)l;
+      bl[0] = b0; bl[1] = b1;
+      double* hl = V + 2 * (size_t)L + 4 * (size_t)l;
+      hl[0] = h00; hl[1] = h01; hl[2] = h01; hl[3] = h11;
+    }
   }
   // final chi2 of this replica: fixed-order sum of the pose kernel's block partials
   if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -352,7 +369,7 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
     else assemble_pose_kernel<false><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
     c->launches++;
   }
-  dim3 gl(std::max(1, (D.L + ASM_THREADS - 1) / ASM_THREADS), D.R);
+  dim3 gl(std::max(1, (D.L + LM_PER_BLOCK - 1) / LM_PER_BLOCK), D.R);
   if (chi2_only) assemble_landmark_kernel<true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk);
   else assemble_landmark_kernel<false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk);
   c->launches++;
@@ -368,7 +385,8 @@ int graph_build_structure(slam_b200_ctx* c) {
   HostGraph& g = c->g;
   if (!c->sys) c->sys = new DeviceSystem();
   DeviceSystem& D = *c->sys;
-  if (D.structure_version == g.structure_version) return D.n;
+  if (D.structure_version == g.structure_version && D.assembly_only == c->assembly_only) return D.n;
+  D.assembly_only = c->assembly_only;
   auto t0 = std::chrono::steady_clock::now();
   const int P = g.P(), L = g.L(), Eo = g.Eo(), El = g.El();
   D.P = P; D.L = L; D.Eo = Eo; D.El = El;
@@ -510,14 +528,25 @@ int graph_build_structure(slam_b200_ctx* c) {
   // ---- symbolic analysis ----
   int leaf = 1024;
   if (const char* s = getenv("SLAM_B200_ND_LEAF")) leaf = std::max(1, atoi(s));
-  symbolic_analyze(nb, dim.data(), (int)D.off_a.size(), D.off_a.data(), D.off_b.data(), D.hoff_diag.data(),
-                   D.hoff_off.data(), leaf, D.sym);
+  if (c->assembly_only) {
+    // linearise + assemble only (config 5 measures the edge-partitioned assembly; the solve is
+    // reported separately): no ordering, no fronts
+    D.sym = Symbolic();
+    D.sym.nb = nb;
+    D.sym.n = D.n;
+    D.sym.boff = D.blk_hidx;  // solver order = g2o order
+  } else {
+    symbolic_analyze(nb, dim.data(), (int)D.off_a.size(), D.off_a.data(), D.off_b.data(), D.hoff_diag.data(),
+                     D.hoff_off.data(), leaf, D.sym);
+  }
   Symbolic& S = D.sym;
+  if (S.lptr.empty()) { S.lptr.assign(1, 0); S.uptr.assign(1, 0); S.rows_ptr.assign(1, 0); S.child_ptr.assign(1, 0); S.asm_ptr.assign(1, 0); }
   D.nL = S.lptr[S.nf];
   D.nU = S.uptr[S.nf];
   D.nUvec = S.rows_ptr[S.nf];
   // per-level launch lists: fronts whose dense frontal matrix fits in shared memory vs the rest
-  const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 1024);
+  // room behind the front for the row map and the scaled panel (solver.cu: factor_extra_smem)
+  const size_t smem_limit = (size_t)std::max(0, c->max_smem_optin - 16384);
   std::vector<int> launch_list;
   std::vector<long> fbig(S.nf, -1);
   D.levels.assign(S.nlevels, LevelLaunch());
@@ -525,13 +554,17 @@ int graph_build_structure(slam_b200_ctx* c) {
   for (int lv = 0; lv < S.nlevels; lv++) {
     LevelLaunch& LL = D.levels[lv];
     LL.list_off = (int)launch_list.size();
-    std::vector<int> big;
+    std::vector<int> small, big;
     for (int f = S.level_ptr[lv]; f < S.level_ptr[lv + 1]; f++) {
       size_t fs = (size_t)S.npiv[f] + S.nupd[f];
       size_t need = fs * fs * sizeof(double);
-      if (need <= smem_limit) {
+      LL.max_fs = std::max(LL.max_fs, (int)fs);
+      if (fs <= 64 && need <= smem_limit) {
         launch_list.push_back(f);
-        LL.n_small++;
+        LL.n_tiny++;
+        LL.smem_tiny = std::max(LL.smem_tiny, need);
+      } else if (need <= smem_limit) {
+        small.push_back(f);
         LL.smem_factor = std::max(LL.smem_factor, need);
       } else {
         big.push_back(f);
@@ -541,8 +574,31 @@ int graph_build_structure(slam_b200_ctx* c) {
       size_t sneed = (fs * S.npiv[f] + fs) * sizeof(double);
       LL.smem_solve = std::max(LL.smem_solve, std::min(sneed, smem_limit));
     }
+    for (int f : small) launch_list.push_back(f);
     for (int f : big) launch_list.push_back(f);
+    LL.n_small = (int)small.size();
     LL.n_big = (int)big.size();
+  }
+  // forward-solve gather lists (by destination row of the parent front, children in order)
+  std::vector<int> frow_ptr(S.nf + 1, 0), gather_ptr, gather_src;
+  for (int f = 0; f < S.nf; f++) frow_ptr[f + 1] = frow_ptr[f] + S.npiv[f] + S.nupd[f] + 1;
+  gather_ptr.assign(frow_ptr[S.nf], 0);
+  {
+    std::vector<std::vector<int>> per_row;
+    for (int f = 0; f < S.nf; f++) {
+      const int fs = S.npiv[f] + S.nupd[f];
+      per_row.assign(fs, std::vector<int>());
+      for (int ci = S.child_ptr[f]; ci < S.child_ptr[f + 1]; ci++) {
+        const int ch = S.children[ci];
+        for (int q = S.rows_ptr[ch]; q < S.rows_ptr[ch + 1]; q++) per_row[S.rel[q]].push_back(q);
+      }
+      int* gp = gather_ptr.data() + frow_ptr[f];
+      for (int i = 0; i < fs; i++) {
+        gp[i] = (int)gather_src.size();
+        gather_src.insert(gather_src.end(), per_row[i].begin(), per_row[i].end());
+      }
+      gp[fs] = (int)gather_src.size();
+    }
   }
   // solver scalar -> V offset of the rhs entry; vertex -> solver offset
   std::vector<int> solver2v(D.n), pose_boff(P, -1), lm_boff(L, -1);
@@ -600,6 +656,9 @@ int graph_build_structure(slam_b200_ctx* c) {
   rc |= upload_vec(c, D.ds.uptr, S.uptr);
   rc |= upload_vec(c, D.ds.fbig, fbig);
   rc |= upload_vec(c, D.ds.launch_list, launch_list);
+  rc |= upload_vec(c, D.ds.frow_ptr, frow_ptr);
+  rc |= upload_vec(c, D.ds.gather_ptr, gather_ptr);
+  rc |= upload_vec(c, D.ds.gather_src, gather_src);
   if (rc) return SLAM_B200_E_CUDA;
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   D.structure_version = g.structure_version;
@@ -690,6 +749,7 @@ void graph_release(slam_b200_ctx* c) {
   D.ds.upd_rows.release(); D.ds.rel.release(); D.ds.child_ptr.release(); D.ds.children.release();
   D.ds.asm_ptr.release(); D.ds.solver2v.release(); D.ds.lptr.release(); D.ds.uptr.release();
   D.ds.fbig.release(); D.ds.asm_entries.release(); D.ds.launch_list.release();
+  D.ds.frow_ptr.release(); D.ds.gather_ptr.release(); D.ds.gather_src.release();
   D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
   D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
   D.est0.release();

@@ -22,11 +22,17 @@ struct DevSym {  // symbolic analysis on the device (see symbolic.h)
   DevBuf<long> lptr, uptr, fbig;
   DevBuf<AsmEntry> asm_entries;
   DevBuf<int> launch_list;  // front ids grouped per (level, small|big)
+  // forward-solve gather: for front g and row i, gather_src[gather_ptr[frow_ptr[g]+i] ..) are the
+  // positions in the update-vector array that the children contribute to that row (child order)
+  DevBuf<int> frow_ptr, gather_ptr, gather_src;
 };
 
 struct LevelLaunch {
-  int list_off = 0, n_small = 0, n_big = 0;   // launch_list[list_off .. +n_small) then big
-  size_t smem_factor = 0, smem_solve = 0;     // dynamic shared memory of the small launches
+  // launch_list[list_off ..): n_tiny fronts (fs <= 64, 128-thread CTAs), then n_small (front fits in
+  // shared memory, 256-thread CTAs), then n_big (front in a global scratch slab)
+  int list_off = 0, n_tiny = 0, n_small = 0, n_big = 0;
+  size_t smem_tiny = 0, smem_factor = 0, smem_solve = 0;
+  int max_fs = 0;
 };
 
 struct DeviceSystem {
@@ -62,6 +68,7 @@ struct DeviceSystem {
   int iters_enqueued = 0;
   bool assembled = false;
   bool have_snapshot = false;
+  bool assembly_only = false;
   // one Gauss-Newton iteration (assemble + factor + solves + update) captured as a CUDA graph:
   // ~40 dependent small launches replayed with one host call per iteration
   cudaGraphExec_t iter_graph = nullptr;

@@ -14,11 +14,14 @@
 
 namespace {
 
-constexpr int FACTOR_THREADS = 256;
-constexpr int SOLVE_THREADS = 128;
+constexpr int FACTOR_THREADS = 512;
+constexpr int FACTOR_THREADS_TINY = 128;  // fronts of <= 64 rows
+constexpr int SOLVE_THREADS = 1024;      // levels with fronts of > 64 rows: few CTAs, stage L fast
+constexpr int SOLVE_THREADS_TINY = 128;
 
 struct SymArgs {
   const int *piv0, *npiv, *nupd, *rows_ptr, *upd_rows, *rel, *child_ptr, *children, *asm_ptr, *solver2v;
+  const int *frow_ptr, *gather_ptr, *gather_src;
   const long *lptr, *uptr, *fbig;
   const AsmEntry* asm_entries;
   const int* launch_list;
@@ -27,6 +30,17 @@ struct SymArgs {
 // ---- factorisation -----------------------------------------------------------------------------
 // F is the dense frontal matrix, column-major with leading dimension fs; only the lower triangle
 // is meaningful.  SMEM: F in dynamic shared memory; otherwise in a per-front global scratch slab.
+//
+// Blocked right-looking LDL^T, panels of NB pivot columns:
+//  (1) panel: every thread factorises the NB x NB diagonal triangle redundantly in registers (it is
+//      tiny and this avoids a barrier + broadcast), then one thread per row below it eliminates
+//      that row's NB panel entries in registers;
+//  (2) trailing update F[i,j] -= sum_p F[i,p] F[j,p] / d_p: one warp per group of 4 columns, lanes
+//      over rows, the 4 x NB scaled panel entries of the columns held in registers -> 32 FMAs per 8
+//      shared-memory loads, conflict-free (lanes read consecutive rows).
+// Two barriers per NB pivots.  Columns stay unscaled (F[i,k] = l_ik d_k) until the write-out.
+constexpr int NB = 8;
+
 template <bool SMEM>
 __global__ void __launch_bounds__(FACTOR_THREADS)
 factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV, double* Lv_all, long nL,
@@ -39,6 +53,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   double* Uv = Uv_all + (size_t)r * nU;
   double* F = SMEM ? smem : (Fbig_all + (size_t)r * nFbig + S.fbig[g]);
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   for (int t = tid; t < fs * fs; t += nt) F[t] = 0.0;
   __syncthreads();
   // original entries: every H block whose earlier-eliminated vertex is a pivot of this front
@@ -60,52 +75,164 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   }
   __syncthreads();
   // extend-add the children's Schur complements (one child at a time: positions of different
-  // children overlap, positions inside one child do not)
+  // children overlap, positions inside one child do not); warp per column, lanes over rows
+  int* srel = reinterpret_cast<int*>(smem + (SMEM ? (size_t)fs * fs : 0));  // fs ints behind the front
   for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
     const int ch = S.children[ci];
     const int uc = S.nupd[ch];
     const double* Uc = Uv + S.uptr[ch];
     const int* rel = S.rel + S.rows_ptr[ch];
-    for (int t = tid; t < uc * uc; t += nt) {
-      const int i = t % uc, j = t / uc;
-      if (i >= j) F[(size_t)rel[j] * fs + rel[i]] += Uc[t];
+    for (int i = tid; i < uc; i += nt) srel[i] = rel[i];
+    __syncthreads();
+    for (int j = warp; j < uc; j += nw) {
+      const double* col = Uc + (size_t)j * uc;
+      double* dst = F + (size_t)srel[j] * fs;
+      for (int i = j + lane; i < uc; i += 128) {  // four independent loads in flight per lane
+        const int i1 = i + 32, i2 = i + 64, i3 = i + 96;
+        const double v0 = col[i];
+        const double v1 = i1 < uc ? col[i1] : 0.0;
+        const double v2 = i2 < uc ? col[i2] : 0.0;
+        const double v3 = i3 < uc ? col[i3] : 0.0;
+        dst[srel[i]] += v0;
+        if (i1 < uc) dst[srel[i1]] += v1;
+        if (i2 < uc) dst[srel[i2]] += v2;
+        if (i3 < uc) dst[srel[i3]] += v3;
+      }
     }
     __syncthreads();
   }
-  // right-looking LDL^T on the pivot columns; columns stay unscaled (F[i,k] = l_ik d_k) until the
-  // write-out so one barrier per pivot suffices
-  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  for (int k = 0; k < s; k++) {
-    const double d = F[(size_t)k * fs + k];
-    if (d == 0.0 || !isfinite(d)) {  // SimplicialCholesky_impl.h:175-179: zero pivot = failure
-      if (tid == 0) status[2 * r] = 1;
+  // Sp: the current panel scaled by 1/d (Sp[p*fs + j] = F[j, k0+p] / d_p), written by the row threads
+  // of step (1) and broadcast-read as the column factors of step (2)
+  double* Sp = reinterpret_cast<double*>(srel + ((fs + 1) & ~1));
+  for (int k0 = 0; k0 < s; k0 += NB) {
+    const int nb = min(NB, s - k0);
+    double* Pk = F + (size_t)k0 * fs;  // panel columns: Pk[p * fs + row]
+    // ---- (1) panel ----
+    double T[NB][NB], invd[NB];
+#pragma unroll
+    for (int p = 0; p < NB; p++)
+#pragma unroll
+      for (int q = p; q < NB; q++) T[q][p] = (q < nb) ? Pk[p * fs + k0 + q] : (q == p ? 1.0 : 0.0);
+    bool bad = false;
+#pragma unroll
+    for (int p = 0; p < NB; p++) {
+      const double d = T[p][p];
+      if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;  // SimplicialCholesky_impl.h:175-179
+      invd[p] = __drcp_rn(d);
+#pragma unroll
+      for (int q = p + 1; q < NB; q++) {
+        const double lqp = T[q][p] * invd[p];
+#pragma unroll
+        for (int q2 = q; q2 < NB; q2++) T[q2][q] -= T[q2][p] * lqp;
+      }
     }
-    const double inv = 1.0 / d;
-    const double* colk = F + (size_t)k * fs;
-    for (int j = k + 1 + warp; j < fs; j += nw) {
-      const double cj = colk[j] * inv;
-      double* colj = F + (size_t)j * fs;
-      for (int i = j + lane; i < fs; i += 32) colj[i] -= colk[i] * cj;
+    if (bad && tid == 0) status[2 * r] = 1;
+    for (int i = k0 + nb + tid; i < fs; i += nt) {
+      double rr[NB];
+#pragma unroll
+      for (int p = 0; p < NB; p++) rr[p] = (p < nb) ? Pk[p * fs + i] : 0.0;
+#pragma unroll
+      for (int p = 0; p < NB; p++) {
+        const double rp = rr[p] * invd[p];
+        Sp[p * fs + i] = rp;
+#pragma unroll
+        for (int q = p + 1; q < NB; q++) rr[q] -= rp * T[q][p];
+      }
+#pragma unroll
+      for (int p = 1; p < NB; p++)
+        if (p < nb) Pk[p * fs + i] = rr[p];
+    }
+    if (tid < nb) {  // the triangle's own rows
+#pragma unroll
+      for (int q = 0; q < NB; q++)
+        if (q == tid) {
+#pragma unroll
+          for (int p = 0; p <= q; p++) Pk[p * fs + k0 + q] = T[q][p];
+        }
+    }
+    __syncthreads();
+    // ---- (2) trailing update ----
+    const int c0 = k0 + nb;
+    for (int jg = c0 + 4 * warp; jg < fs; jg += 4 * nw) {
+      double B[4][NB];
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int p = 0; p < NB; p++) B[b][p] = (jg + b < fs) ? Sp[p * fs + jg + b] : 0.0;
+      double* Cj = F + (size_t)jg * fs;
+      for (int i = jg + lane; i < fs; i += 64) {  // two independent row chunks in flight
+        const int i2 = i + 32;
+        const bool v2 = i2 < fs;
+        double A[NB], A2[NB];
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          A[p] = (p < nb) ? Pk[p * fs + i] : 0.0;
+          A2[p] = (p < nb && v2) ? Pk[p * fs + i2] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          if (jg + b < fs) {
+            const bool w1 = i >= jg + b, w2 = v2;  // i2 > i >= jg, so i2 >= jg + b always holds for b < 32
+            double acc = w1 ? Cj[b * fs + i] : 0.0;
+            double acc2 = w2 ? Cj[b * fs + i2] : 0.0;
+#pragma unroll
+            for (int p = 0; p < NB; p++) {
+              acc -= A[p] * B[b][p];
+              acc2 -= A2[p] * B[b][p];
+            }
+            if (w1) Cj[b * fs + i] = acc;
+            if (w2) Cj[b * fs + i2] = acc2;
+          }
+        }
+      }
     }
     __syncthreads();
   }
   // L panel (fs x s, unit lower with D on the diagonal) and the Schur complement for the parent
   double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
-  for (int t = tid; t < fs * s; t += nt) {
-    const int i = t % fs, j = t / fs;
-    double v = 0.0;
-    if (i == j) v = F[t];
-    else if (i > j) v = F[t] / F[(size_t)j * fs + j];
-    Lg[t] = v;
+  for (int j = warp; j < s; j += nw) {
+    const double* col = F + (size_t)j * fs;
+    const double d = col[j];
+    const double inv = 1.0 / d;
+    double* out = Lg + (size_t)j * fs;
+    for (int i = lane; i < fs; i += 32) out[i] = i < j ? 0.0 : (i == j ? d : col[i] * inv);
   }
   double* Ug = Uv + S.uptr[g];
-  for (int t = tid; t < u * u; t += nt) {
-    const int i = t % u, j = t / u;
-    if (i >= j) Ug[t] = F[(size_t)(s + j) * fs + s + i];
+  for (int j = warp; j < u; j += nw) {
+    const double* col = F + (size_t)(s + j) * fs + s;
+    double* out = Ug + (size_t)j * u;
+    for (int i = j + lane; i < u; i += 32) out[i] = col[i];
+  }
+}
+
+// L panel (fs x s, leading dimension fs) from global into shared memory with leading dimension ld:
+// one warp per column, lanes over rows, up to five independent loads in flight per lane
+__device__ __forceinline__ void stage_panel(double* Ls, const double* __restrict__ Lg, int fs, int s, int ld,
+                                            int warp, int nw, int lane) {
+  for (int j = warp; j < s; j += nw) {
+    const double* src = Lg + (size_t)j * fs;
+    double* dst = Ls + (size_t)j * ld;
+    for (int i = j + lane; i < fs; i += 160) {  // rows above the diagonal are never read
+      const int i1 = i + 32, i2 = i + 64, i3 = i + 96, i4 = i + 128;
+      const double v0 = src[i];
+      const double v1 = i1 < fs ? src[i1] : 0.0;
+      const double v2 = i2 < fs ? src[i2] : 0.0;
+      const double v3 = i3 < fs ? src[i3] : 0.0;
+      const double v4 = i4 < fs ? src[i4] : 0.0;
+      dst[i] = v0;
+      if (i1 < fs) dst[i1] = v1;
+      if (i2 < fs) dst[i2] = v2;
+      if (i3 < fs) dst[i3] = v3;
+      if (i4 < fs) dst[i4] = v4;
+    }
   }
 }
 
 // ---- forward solve: L y = b, then z = D^-1 y, one front per CTA, leaves -> root ------------------
+// Blocked like the factorisation: per panel of NB pivots every thread solves the NB x NB unit
+// triangle redundantly in registers, then one thread per remaining row subtracts the panel's
+// contribution.  One barrier per NB pivots.  The L panel is staged in shared memory with an odd
+// leading dimension (conflict-free row and column access).
 template <bool SMEM>
 __global__ void __launch_bounds__(SOLVE_THREADS)
 forward_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV,
@@ -119,29 +246,48 @@ forward_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   double* uvec = uvec_all + (size_t)r * nUvec;
   double* x = x_all + (size_t)r * n;
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int ld = SMEM ? (fs | 1) : fs;
   double* w = smem;             // fs
-  double* Ls = smem + fs;       // fs * s when SMEM
-  for (int i = tid; i < fs; i += nt) w[i] = i < s ? V[S.solver2v[p0 + i]] : 0.0;
-  if (SMEM)
-    for (int t = tid; t < fs * s; t += nt) Ls[t] = Lg[t];
-  __syncthreads();
-  for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
-    const int ch = S.children[ci];
-    const int uc = S.nupd[ch];
-    const double* uv = uvec + S.rows_ptr[ch];
-    const int* rel = S.rel + S.rows_ptr[ch];
-    for (int i = tid; i < uc; i += nt) w[rel[i]] += uv[i];
-    __syncthreads();
+  double* ys = smem + fs;       // s (solution of the unit-triangular part)
+  double* Ls = smem + fs + s;   // ld * s when SMEM
+  // w = rhs of the pivots + the children's update vectors, gathered per destination row in child
+  // order (fixed summation order, no atomics, no per-child barrier)
+  const int* gp = S.gather_ptr + S.frow_ptr[g];
+  for (int i = tid; i < fs; i += nt) {
+    double acc = i < s ? V[S.solver2v[p0 + i]] : 0.0;
+    for (int q = gp[i]; q < gp[i + 1]; q++) acc += uvec[S.gather_src[q]];
+    w[i] = acc;
   }
+  if (SMEM) stage_panel(Ls, Lg, fs, s, ld, warp, nw, lane);
+  __syncthreads();
   const double* Lp = SMEM ? Ls : Lg;
-  for (int k = 0; k < s; k++) {
-    const double wk = w[k];
-    const double* col = Lp + (size_t)k * fs;
-    for (int i = k + 1 + tid; i < fs; i += nt) w[i] -= col[i] * wk;
+  for (int k0 = 0; k0 < s; k0 += NB) {
+    const int nb = min(NB, s - k0);
+    double y[NB];
+#pragma unroll
+    for (int p = 0; p < NB; p++) y[p] = (p < nb) ? w[k0 + p] : 0.0;
+#pragma unroll
+    for (int p = 0; p < NB; p++)
+#pragma unroll
+      for (int q = p + 1; q < NB; q++)
+        if (q < nb) y[q] -= Lp[(size_t)(k0 + p) * ld + k0 + q] * y[p];
+    for (int i = k0 + nb + tid; i < fs; i += nt) {
+      double acc = w[i];
+#pragma unroll
+      for (int p = 0; p < NB; p++)
+        if (p < nb) acc -= Lp[(size_t)(k0 + p) * ld + i] * y[p];
+      w[i] = acc;
+    }
+    if (tid < nb) {
+#pragma unroll
+      for (int p = 0; p < NB; p++)
+        if (p == tid) ys[k0 + p] = y[p];
+    }
     __syncthreads();
   }
   for (int i = tid; i < fs; i += nt) {
-    if (i < s) x[p0 + i] = w[i] / Lp[(size_t)i * fs + i];
+    if (i < s) x[p0 + i] = ys[i] / Lp[(size_t)i * ld + i];
     else uvec[S.rows_ptr[g] + i - s] = w[i];
   }
 }
@@ -158,30 +304,57 @@ backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long
   double* x = x_all + (size_t)r * n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  double* xs = smem;
-  double* Ls = smem + fs;
+  const int ld = SMEM ? (fs | 1) : fs;
+  double* xs = smem;            // fs
+  double* xo = smem + fs;       // s
+  double* Ls = smem + fs + s;
   const int* rows = S.upd_rows + S.rows_ptr[g];
   for (int i = tid; i < fs; i += nt) xs[i] = i < s ? x[p0 + i] : x[rows[i - s]];
-  if (SMEM)
-    for (int t = tid; t < fs * s; t += nt) Ls[t] = Lg[t];
+  if (SMEM) stage_panel(Ls, Lg, fs, s, ld, warp, nw, lane);
   __syncthreads();
   const double* Lp = SMEM ? Ls : Lg;
   // contribution of the already-solved ancestor rows: xs[k] -= sum_{i>=s} L[i,k] xs[i]
   for (int k = warp; k < s; k += nw) {
-    const double* col = Lp + (size_t)k * fs;
+    const double* col = Lp + (size_t)k * ld;
     double t = 0.0;
     for (int i = s + lane; i < fs; i += 32) t += col[i] * xs[i];
     for (int o = 16; o; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
     if (lane == 0) xs[k] -= t;
   }
   __syncthreads();
-  // unit upper-triangular solve with L11^T, column sweep from the last pivot
-  for (int i = s - 1; i > 0; i--) {
-    const double xi = xs[i];
-    for (int k = tid; k < i; k += nt) xs[k] -= Lp[(size_t)k * fs + i] * xi;
+  // unit upper-triangular solve with L11^T, panels from the last pivot down
+  const int npan = (s + NB - 1) / NB;
+  for (int pan = npan - 1; pan >= 0; pan--) {
+    const int k0 = pan * NB;
+    const int nb = min(NB, s - k0);
+    double xp[NB];
+#pragma unroll
+    for (int p = 0; p < NB; p++) xp[p] = (p < nb) ? xs[k0 + p] : 0.0;
+#pragma unroll
+    for (int p = NB - 1; p >= 0; p--)
+#pragma unroll
+      for (int q = 0; q < p; q++)
+        if (p < nb) xp[q] -= Lp[(size_t)(k0 + q) * ld + k0 + p] * xp[p];
+    for (int k = tid; k < k0; k += nt) {
+      const double* col = Lp + (size_t)k * ld + k0;
+      double acc = xs[k];
+#pragma unroll
+      for (int p = 0; p < NB; p++)
+        if (p < nb) acc -= col[p] * xp[p];
+      xs[k] = acc;
+    }
+    if (tid < nb) {
+#pragma unroll
+      for (int p = 0; p < NB; p++)
+        if (p == tid) xo[k0 + p] = xp[p];
+    }
     __syncthreads();
   }
-  for (int i = tid; i < s; i += nt) x[p0 + i] = xs[i];
+  for (int i = tid; i < s; i += nt) x[p0 + i] = xo[i];
+}
+
+size_t factor_extra_smem(int max_fs) {  // srel (ints, even count) + scaled panel
+  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + (size_t)NB * max_fs * sizeof(double);
 }
 
 SymArgs sym_args(const DeviceSystem& D) {
@@ -191,6 +364,7 @@ SymArgs sym_args(const DeviceSystem& D) {
   a.children = D.ds.children.p; a.asm_ptr = D.ds.asm_ptr.p; a.solver2v = D.ds.solver2v.p;
   a.lptr = D.ds.lptr.p; a.uptr = D.ds.uptr.p; a.fbig = D.ds.fbig.p;
   a.asm_entries = D.ds.asm_entries.p; a.launch_list = D.ds.launch_list.p;
+  a.frow_ptr = D.ds.frow_ptr.p; a.gather_ptr = D.ds.gather_ptr.p; a.gather_src = D.ds.gather_src.p;
   return a;
 }
 
@@ -226,16 +400,23 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   };
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
+    if (LL.n_tiny) {
+      dim3 grid(LL.n_tiny, D.R);
+      factor_kernel<true><<<grid, FACTOR_THREADS_TINY, LL.smem_tiny + 64 * sizeof(int) + NB * 64 * sizeof(double), c->stream>>>(
+          S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p);
+      c->launches++;
+    }
     if (LL.n_small) {
       dim3 grid(LL.n_small, D.R);
-      factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor, c->stream>>>(
-          S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p);
+      factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
+          S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p);
       c->launches++;
     }
     if (LL.n_big) {
       dim3 grid(LL.n_big, D.R);
-      factor_kernel<false><<<grid, FACTOR_THREADS, 0, c->stream>>>(
-          S, LL.list_off + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p);
+      factor_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
+          S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
+          D.status.p);
       c->launches++;
     }
   }
@@ -243,7 +424,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   // solves: a level's fronts either all stage their L panel in shared memory or none does
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
-    int nfr = LL.n_small + LL.n_big;
+    int nfr = LL.n_tiny + LL.n_small + LL.n_big;
     if (!nfr) continue;
     dim3 grid(nfr, D.R);
     // smem_solve was clamped to the limit; recompute whether every front of the level fits
@@ -252,28 +433,29 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     for (int q = 0; q < nfr; q++) {
       int f = D.sym.level_ptr[lv] + q;  // same set as the launch list of this level
       size_t fs = (size_t)D.sym.npiv[f] + D.sym.nupd[f];
-      size_t nd = (fs * D.sym.npiv[f] + fs) * sizeof(double);
+      size_t nd = ((fs | 1) * D.sym.npiv[f] + fs + D.sym.npiv[f]) * sizeof(double);
       need = std::max(need, nd);
       if (nd > smem_limit) fits = false;
     }
+    const int sthreads = LL.max_fs > 64 ? SOLVE_THREADS : SOLVE_THREADS_TINY;
     if (fits)
-      forward_kernel<true><<<grid, SOLVE_THREADS, need, c->stream>>>(S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL,
-                                                                   D.uvec.p, D.nUvec, D.x.p, D.n);
+      forward_kernel<true><<<grid, sthreads, need, c->stream>>>(S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL,
+                                                              D.uvec.p, D.nUvec, D.x.p, D.n);
     else {
       size_t wneed = 0;
       for (int q = 0; q < nfr; q++) {
         int f = D.sym.level_ptr[lv] + q;
-        wneed = std::max(wneed, ((size_t)D.sym.npiv[f] + D.sym.nupd[f]) * sizeof(double));
+        wneed = std::max(wneed, ((size_t)2 * D.sym.npiv[f] + D.sym.nupd[f]) * sizeof(double));
       }
-      forward_kernel<false><<<grid, SOLVE_THREADS, wneed, c->stream>>>(S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL,
-                                                                     D.uvec.p, D.nUvec, D.x.p, D.n);
+      forward_kernel<false><<<grid, sthreads, wneed, c->stream>>>(S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL,
+                                                                D.uvec.p, D.nUvec, D.x.p, D.n);
     }
     c->launches++;
   }
   mark();  // forward done
   for (int lv = nlv - 1; lv >= 0; lv--) {
     const LevelLaunch& LL = D.levels[lv];
-    int nfr = LL.n_small + LL.n_big;
+    int nfr = LL.n_tiny + LL.n_small + LL.n_big;
     if (!nfr) continue;
     dim3 grid(nfr, D.R);
     bool fits = true;
@@ -281,15 +463,16 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     for (int q = 0; q < nfr; q++) {
       int f = D.sym.level_ptr[lv] + q;
       size_t fs = (size_t)D.sym.npiv[f] + D.sym.nupd[f];
-      size_t nd = (fs * D.sym.npiv[f] + fs) * sizeof(double);
+      size_t nd = ((fs | 1) * D.sym.npiv[f] + fs + D.sym.npiv[f]) * sizeof(double);
       need = std::max(need, nd);
-      wneed = std::max(wneed, fs * sizeof(double));
+      wneed = std::max(wneed, (fs + D.sym.npiv[f]) * sizeof(double));
       if (nd > smem_limit) fits = false;
     }
+    const int sthreads = LL.max_fs > 64 ? SOLVE_THREADS : SOLVE_THREADS_TINY;
     if (fits)
-      backward_kernel<true><<<grid, SOLVE_THREADS, need, c->stream>>>(S, LL.list_off, D.Lv.p, D.nL, D.x.p, D.n);
+      backward_kernel<true><<<grid, sthreads, need, c->stream>>>(S, LL.list_off, D.Lv.p, D.nL, D.x.p, D.n);
     else
-      backward_kernel<false><<<grid, SOLVE_THREADS, wneed, c->stream>>>(S, LL.list_off, D.Lv.p, D.nL, D.x.p, D.n);
+      backward_kernel<false><<<grid, sthreads, wneed, c->stream>>>(S, LL.list_off, D.Lv.p, D.nL, D.x.p, D.n);
     c->launches++;
   }
   SLAM_CUDA_TRY(c, cudaGetLastError());
@@ -343,8 +526,8 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
       // (assemble 2 + per level factor/forward/backward + update)
       int n = 2 + 1;
       for (const LevelLaunch& LL : D.levels) {
-        n += (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);
-        n += (LL.n_small + LL.n_big) ? 2 : 0;
+        n += (LL.n_tiny ? 1 : 0) + (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);
+        n += (LL.n_tiny + LL.n_small + LL.n_big) ? 2 : 0;
       }
       D.launches_per_iter = n;
     }

@@ -200,41 +200,66 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
     std::sort(adj[v].begin(), adj[v].end());
     adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end());
   }
+  // degree buckets per rank: doubly linked lists, O(1) insert / remove
+  int nrank = 1;
+  for (int v = 0; v < nb; v++) nrank = std::max(nrank, rank[v] + 1);
   std::vector<long> wdeg(nb, 0);
-  typedef std::pair<std::pair<int, long>, int> Key;
-  std::set<Key> pq;
+  std::vector<std::vector<int>> head(nrank);
+  std::vector<int> nxt(nb, -1), prv(nb, -1), remaining(nrank, 0), mindeg(nrank, 0);
+  auto bucket_insert = [&](int v) {
+    std::vector<int>& h = head[rank[v]];
+    long d = wdeg[v];
+    if ((long)h.size() <= d) h.resize(d + 1 + (d >> 2), -1);
+    nxt[v] = h[d];
+    prv[v] = -1;
+    if (h[d] >= 0) prv[h[d]] = v;
+    h[d] = v;
+    if (d < mindeg[rank[v]]) mindeg[rank[v]] = (int)d;
+  };
+  auto bucket_remove = [&](int v) {
+    std::vector<int>& h = head[rank[v]];
+    if (prv[v] >= 0) nxt[prv[v]] = nxt[v];
+    else h[wdeg[v]] = nxt[v];
+    if (nxt[v] >= 0) prv[nxt[v]] = prv[v];
+  };
   for (int v = 0; v < nb; v++) {
     for (int u : adj[v]) wdeg[v] += dim[u];
-    pq.insert({{rank[v], wdeg[v]}, v});
+    remaining[rank[v]]++;
   }
+  for (int v = nb - 1; v >= 0; v--) bucket_insert(v);  // ties resolved towards the lower index
   std::vector<int> order;
   order.reserve(nb);
-  std::vector<int> merged;
-  while (!pq.empty()) {
-    int v = pq.begin()->second;
-    pq.erase(pq.begin());
-    order.push_back(v);
-    std::vector<int> N;
-    N.swap(adj[v]);
-    for (int u : N) {
-      pq.erase({{rank[u], wdeg[u]}, u});
-      merged.clear();
-      merged.reserve(adj[u].size() + N.size());
-      // (adj[u] U N) \ {u, v}
-      size_t a = 0, b = 0;
-      const std::vector<int>& A = adj[u];
-      while (a < A.size() || b < N.size()) {
-        int x;
-        if (b >= N.size() || (a < A.size() && A[a] < N[b])) x = A[a++];
-        else if (a >= A.size() || N[b] < A[a]) x = N[b++];
-        else { x = A[a]; a++; b++; }
-        if (x != u && x != v) merged.push_back(x);
+  std::vector<int> N;
+  for (int rk = 0; rk < nrank; rk++) {
+    while (remaining[rk] > 0) {
+      std::vector<int>& h = head[rk];
+      int d = mindeg[rk];
+      while (d < (int)h.size() && h[d] < 0) d++;
+      mindeg[rk] = d;
+      const int v = h[d];
+      bucket_remove(v);
+      remaining[rk]--;
+      order.push_back(v);
+      N.swap(adj[v]);
+      adj[v].clear();
+      adj[v].shrink_to_fit();
+      for (int u : N) {
+        bucket_remove(u);
+        std::vector<int>& A = adj[u];
+        long w = wdeg[u];
+        // remove v
+        auto it = std::lower_bound(A.begin(), A.end(), v);
+        if (it != A.end() && *it == v) { A.erase(it); w -= dim[v]; }
+        // insert the members of N that are missing (usually none: neighbours of a low-degree vertex
+        // mostly know each other already)
+        for (int x : N) {
+          if (x == u) continue;
+          auto jt = std::lower_bound(A.begin(), A.end(), x);
+          if (jt == A.end() || *jt != x) { A.insert(jt, x); w += dim[x]; }
+        }
+        wdeg[u] = w;
+        bucket_insert(u);
       }
-      adj[u].swap(merged);
-      long w = 0;
-      for (int x : adj[u]) w += dim[x];
-      wdeg[u] = w;
-      pq.insert({{rank[u], wdeg[u]}, u});
     }
   }
   return order;
@@ -291,8 +316,10 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
       for (int v : nd.nodes[f].verts) rank[v] = r;
     }
   }
+  S.t_nd = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // ---- stage 2: constrained minimum degree -> elimination order ----
   std::vector<int> order = constrained_min_degree(nb, dim, nd.xadj, nd.adj, rank);
+  S.t_md = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - S.t_nd;
   std::vector<int> epos(nb);
   for (int k = 0; k < nb; k++) epos[order[k]] = k;
   // ---- stage 3: block elimination tree + column structures, postorder, supernodes ----

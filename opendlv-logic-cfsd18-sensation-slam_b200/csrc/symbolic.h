@@ -42,7 +42,7 @@ struct Symbolic {
   long nnzL = 0;                    // scalar entries of L below the diagonal (incl. explicit zeros)
   double flops = 0;                 // factor flops, sum over fronts
   int max_front = 0;
-  double seconds = 0;
+  double seconds = 0, t_nd = 0, t_md = 0;
 };
 
 // offdiag: nnb pairs (a, b), a < b, distinct, block indices in g2o order; hoff_diag[b] / hoff_off[k]

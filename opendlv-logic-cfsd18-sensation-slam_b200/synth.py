@@ -173,8 +173,36 @@ class Drive:
     track: Track
     poses_true: np.ndarray        # (P,3)
     poses_noisy: np.ndarray       # (P,3)  what the UKF would have delivered
-    frames: list                  # P arrays, each (4,N) float64 F-order: az deg, zen deg, range, type
-    frame_cone_ids: list          # P arrays of ground-truth cone ids per column
+    # all observations, flat, ordered by pose then by measured range (the column order of a frame)
+    obs_pose: np.ndarray          # (E,) pose index
+    obs_cone: np.ndarray          # (E,) ground-truth cone id
+    obs_az: np.ndarray            # (E,) degrees, float32-rounded
+    obs_range: np.ndarray         # (E,) float32-rounded
+    obs_type: np.ndarray          # (E,)
+    _frames: list = None
+    _ids: list = None
+
+    def _split(self):
+        P = len(self.poses_true)
+        counts = np.bincount(self.obs_pose, minlength=P)
+        cuts = np.cumsum(counts)[:-1]
+        fr = np.zeros((4, len(self.obs_pose)), order="F")
+        fr[0] = self.obs_az; fr[2] = self.obs_range; fr[3] = self.obs_type
+        self._frames = [np.asfortranarray(a) for a in np.split(fr, cuts, axis=1)]
+        self._ids = np.split(self.obs_cone.astype(np.int64), cuts)
+
+    @property
+    def frames(self):
+        """P arrays, each (4,N) float64 F-order (az deg, zen deg, range, type): what performSLAM gets."""
+        if self._frames is None:
+            self._split()
+        return self._frames
+
+    @property
+    def frame_cone_ids(self):
+        if self._ids is None:
+            self._split()
+        return self._ids
 
 
 def simulate_drive(track: Track, n_poses: int, s_start=0.0, s_step=None, seed=18, r_min=0.5,
@@ -196,10 +224,10 @@ def simulate_drive(track: Track, n_poses: int, s_start=0.0, s_step=None, seed=18
     # candidate cones per pose: pairs whose arclength is within r_max+4 m of the lidar
     half = int(np.ceil((r_max + 4.0) / spacing)) + 1
     offs = np.arange(-half, half + 1)
-    frames, ids = [], []
     lid_x = cx + LIDAR_TO_COG * np.cos(h)
     lid_y = cy + LIDAR_TO_COG * np.sin(h)
     pair0 = np.floor((s % track.length if closed else s) / spacing).astype(np.int64)
+    out = {k: [] for k in ("pose", "cone", "az", "rng")}
     for c0 in range(0, n_poses, chunk):
         c1 = min(n_poses, c0 + chunk)
         pr = pair0[c0:c1, None] + offs[None, :]
@@ -224,17 +252,17 @@ def simulate_drive(track: Track, n_poses: int, s_start=0.0, s_step=None, seed=18
         az_obs = f32(az_true + sigma_az * nz[1])
         tiny = np.abs(az_obs) < 1e-3
         az_obs = np.where(tiny, f32(np.where(az_obs < 0, -1e-3, 1e-3)), az_obs)
-        for k in range(c1 - c0):
-            sel = np.nonzero(vis[k])[0]
-            order = np.argsort(r_obs[k, sel], kind="stable")
-            sel = sel[order]
-            fr = np.zeros((4, sel.size), dtype=np.float64, order="F")
-            fr[0] = az_obs[k, sel]
-            fr[2] = r_obs[k, sel]
-            fr[3] = track.cones_type[cid[k, sel]]
-            frames.append(fr)
-            ids.append(cid[k, sel].astype(np.int64))
-    return Drive(track, poses_true, poses_noisy, frames, ids)
+        rows, cols = np.nonzero(vis)                       # row-major: by pose, then candidate column
+        order = np.lexsort((r_obs[rows, cols], rows))      # by pose, then measured range (stable)
+        rows, cols = rows[order], cols[order]
+        out["pose"].append(rows + c0)
+        out["cone"].append(cid[rows, cols])
+        out["az"].append(az_obs[rows, cols])
+        out["rng"].append(r_obs[rows, cols])
+    obs_pose = np.concatenate(out["pose"]).astype(np.int64)
+    obs_cone = np.concatenate(out["cone"]).astype(np.int64)
+    return Drive(track, poses_true, poses_noisy, obs_pose, obs_cone, np.concatenate(out["az"]),
+                 np.concatenate(out["rng"]), track.cones_type[obs_cone].astype(np.float64))
 
 
 def trackdrive(n_laps=1, poses_per_lap=1000, seed=18) -> Drive:
@@ -275,13 +303,11 @@ def graph_from_drive(drive: Drive, pose_id_base=None) -> GraphSoA:
     observation mapped through the noisy pose (coneToGlobal, slam.cpp:499-510); odometry
     measurement = prev^-1 * cur of the noisy poses (slam.cpp:452-455); gauge = first two poses
     and first two cones fixed (slam.cpp:464-474)."""
-    P = len(drive.frames)
-    counts = np.array([f.shape[1] for f in drive.frames], dtype=np.int64)
-    El = int(counts.sum())
-    cols = np.concatenate([f.T for f in drive.frames], axis=0) if El else np.zeros((0, 4))
-    cone = np.concatenate(drive.frame_cone_ids) if El else np.zeros(0, dtype=np.int64)
-    pose_of = np.repeat(np.arange(P), counts)
-    zx, zy, _ = spherical_to_cartesian(cols[:, 0], cols[:, 1], cols[:, 2])
+    P = len(drive.poses_noisy)
+    El = len(drive.obs_pose)
+    cone = drive.obs_cone
+    pose_of = drive.obs_pose
+    zx, zy, _ = spherical_to_cartesian(drive.obs_az, np.zeros(El), drive.obs_range)
     # landmark numbering by first appearance
     uniq, first = np.unique(cone, return_index=True)
     order = np.argsort(first, kind="stable")

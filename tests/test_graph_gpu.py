@@ -214,3 +214,32 @@ def test_optimize_c2_full_size(ctx, orc, synth):
     assert _rel_close(pe, po) and _rel_close(le, lo)
     # size-independent property: a converged GN step leaves chi2 stationary
     assert abs(chi2[-1] - chi2[-2]) <= 1e-9 * chi2[-1]
+
+
+def test_sharded_assembly_partials_sum_to_full(ctx, pkg, synth):
+    """Edge-partitioned assembly (config 5): assembling pose ranges separately gives pose blocks and
+    off-diagonal blocks owned by exactly one shard and landmark partial sums that add up to the full
+    assembly (the part ranks all-reduce)."""
+    import importlib
+    import torch
+    par = importlib.import_module(pkg.__name__ + ".parallel")
+    g = small_graph(synth, 200)
+    ctx.graph_load(g)
+    ctx.graph_prepare_assembly_only()
+    P, L = len(g.pose_ids), len(g.lm_ids)
+    ptr, nV = ctx.graph_system_dev(1)
+    V = torch.as_tensor(par.DeviceArray(ptr, nV), device="cuda")
+    V.zero_(); torch.cuda.synchronize()          # slots of fixed vertices are never written
+    ctx.graph_assemble_async(0, P); ctx.sync()
+    full = V.clone()
+    parts = []
+    for r in range(3):
+        lo, hi = par.shard_range(P, r, 3)
+        V.zero_(); torch.cuda.synchronize()
+        ctx.graph_assemble_async(lo, hi); ctx.sync()
+        parts.append(V.clone())
+    tot = parts[0] + parts[1] + parts[2]
+    assert torch.allclose(tot[:6 * L], full[:6 * L], rtol=1e-12, atol=1e-14)        # landmark part: sums
+    assert torch.equal(tot[6 * L:], full[6 * L:])                                    # everything else: one owner
+    lm, n = ctx.graph_system_dev(0)
+    assert n == 6 * L and lm == ptr
