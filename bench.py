@@ -110,7 +110,20 @@ def dist_setup(n):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout at the first collective; the driver expects ONE
+        # JSON line there, so stdout is pointed at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return world, rank, local
 
 
@@ -465,7 +478,8 @@ def run_ours(args):
             "solve_fp64": {"factor_flops": st["factor_flops"], "gflops": st["factor_flops"] / fac_s / 1e9,
                            "fp64_peak_tflops_measured": fp64_peak,
                            "frac_of_fp64_peak": st["factor_flops"] / fac_s / 1e12 / max(fp64_peak, 1e-9)},
-            "symbolic": {"seconds": st["symbolic_seconds"], "fronts": int(st["n_fronts"]), "levels": int(st["n_levels"]),
+            "symbolic": {"seconds": st["symbolic_seconds"], "host_structure_seconds": st["structure_seconds"],
+                         "launch_lists_seconds": st["launch_lists_seconds"], "upload_seconds": st["upload_seconds"], "fronts": int(st["n_fronts"]), "levels": int(st["n_levels"]),
                          "nnz_L": int(st["nnz_L"]), "max_front": int(st["max_front"]),
                          "ordering": "nested dissection (regions <= 1024 vertices) + constrained minimum degree"},
             "parity_in_run": {"iterations_done_ok": r["done_ok"], "chi2_final": r["chi2_last"]},

@@ -337,7 +337,8 @@ class Context:
         out = np.zeros(16)
         self._ck(self.L.slam_b200_graph_stats(self.h, _dp(out)), "graph_stats")
         keys = ["n", "n_blocks", "n_fronts", "n_levels", "nnz_H_upper", "nnz_L", "factor_flops", "max_front",
-                "front_storage", "symbolic_seconds", "upload_seconds", "nV", "nFbig", "n_offdiag_blocks"]
+                "front_storage", "symbolic_seconds", "upload_seconds", "nV", "nFbig", "n_offdiag_blocks",
+                "structure_seconds", "launch_lists_seconds"]
         return dict(zip(keys, out.tolist()))
 
     # ---- batched replicas ------------------------------------------------------------------------

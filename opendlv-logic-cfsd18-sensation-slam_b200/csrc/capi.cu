@@ -106,7 +106,7 @@ int slam_b200_destroy(slam_b200_ctx* c) {
   c->grid_cell_start.release(); c->grid_cursor.release(); c->grid_rec.release();
   c->grid_bbox.release(); c->grid_tmp.release();
   c->frame_in.release(); c->frame_outd.release(); c->frame_outi.release();
-  c->pin_d.release(); c->pin_i.release();
+  c->pin_d.release(); c->pin_i.release(); c->pin_stage.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -500,6 +500,7 @@ int slam_b200_graph_stats(slam_b200_ctx* c, double out[16]) {
   out[4] = (double)nnzH; out[5] = (double)D.sym.nnzL; out[6] = D.sym.flops; out[7] = D.sym.max_front;
   out[8] = (double)(D.nL + D.nU); out[9] = D.sym.seconds; out[10] = D.upload_seconds;
   out[11] = (double)D.nV; out[12] = (double)D.nFbig; out[13] = (double)D.off_a.size();
+  out[14] = D.t_structure; out[15] = D.t_lists;
   return 0;
 }
 
@@ -663,6 +664,8 @@ int slam_b200_batch_upload(slam_b200_ctx* c, int R, const double* pose_est3, con
         mr[2 * (size_t)El + Eo + k] = oz[3 * (size_t)k + 1];
         mr[2 * (size_t)El + 2 * (size_t)Eo + k] = oz[3 * (size_t)k + 2];
       }
+      double* ml = mr + 2 * (size_t)El + 3 * (size_t)Eo;  // landmark order
+      for (int q = 0; q < El; q++) { int e = D.lm_order[q]; ml[q] = mr[e]; ml[El + (size_t)q] = mr[El + (size_t)e]; }
     }
     if (ne) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.est.p + (size_t)r0 * ne, e, sizeof(double) * rn * ne, cudaMemcpyHostToDevice, c->stream));
     if (nm) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.meas.p + (size_t)r0 * nm, m, sizeof(double) * rn * nm, cudaMemcpyHostToDevice, c->stream));

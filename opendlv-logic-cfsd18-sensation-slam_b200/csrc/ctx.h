@@ -144,6 +144,7 @@ struct slam_b200_ctx {
   DevBuf<int> frame_outi;        // 2n + 8 ints
   PinBuf<double> pin_d;
   PinBuf<int> pin_i;
+  PinBuf<char> pin_stage;        // structure uploads
 
   // ---- graph ----
   HostGraph g;

@@ -42,7 +42,9 @@ struct AsmArgs {
   const unsigned char* lm_free;
   const int *el_start, *el_pose, *el_lm, *el_slot, *el_flags;
   const double* el_info;
-  const int *lm_start, *lm_edges;
+  const int *lm_start, *lm_edges, *lmo_pose;
+  const double* lmo_info;
+  double* trig;  // [2][P] per replica: sin, cos of every pose heading, written by the pose kernel
   const int *eo_i, *eo_j, *eo_slot, *eo_flags, *po_start, *po_list;
   const double* eo_info;
   double* chi2_part;
@@ -54,69 +56,150 @@ struct AsmArgs {
 
 constexpr int ASM_THREADS = 128;
 
+// Pose-centred assembly, one WARP per 32 consecutive poses ("warp-aggregated block scatter"):
+//  * the landmark edges of those poses are one contiguous range of the pose-sorted edge arrays, so
+//    the lanes walk it 32 edges at a time with fully coalesced loads (each byte fetched once);
+//  * every lane linearises one edge (pose trig comes from a per-warp shared-memory cache: sincos is
+//    evaluated once per pose, not once per edge) and writes its off-diagonal block directly;
+//  * the nine numbers an edge adds to its pose's diagonal block and rhs are combined by a segmented
+//    shuffle scan over the lanes of the same pose; the tail lane of each segment adds the segment
+//    sum to that pose's accumulator in shared memory (one writer per pose per step -> no atomics,
+//    fixed order);
+//  * finally lane l finishes pose l: its (at most a few) pose-pose edges, then one write of the
+//    diagonal block and rhs.
+constexpr int ASM_WARPS = ASM_THREADS / 32;
+
+// minBlocksPerSM = 6 caps the kernel at 80 registers: the register-hungry part (3x3 algebra of the
+// pose-pose edges) runs once per pose and may spill; the per-edge loop needs the occupancy to hide
+// the latency of the landmark gather
 template <bool CHI2_ONLY>
-__global__ void __launch_bounds__(ASM_THREADS)
+__global__ void __launch_bounds__(ASM_THREADS, 6)
 assemble_pose_kernel(AsmArgs a, int p0, int p1) {
-  const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_pose[ASM_WARPS][4][32];   // x, y, sin, cos of the warp's poses
+  __shared__ double s_acc[ASM_WARPS][9][32];    // h00 h01 h02 h11 h12 h22 b0 b1 b2 per pose
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r = blockIdx.y;
   const double* est = a.est + (size_t)r * a.estStride;
   const double* meas = a.meas + (size_t)r * a.measStride;
   double* V = a.V + (size_t)r * a.nV;
   const int P = a.P, L = a.L, El = a.El, Eo = a.Eo;
+  const int pw0 = p0 + (blockIdx.x * ASM_WARPS + wid) * 32;  // first pose of this warp
+  const int p = pw0 + lane;
   double chi = 0;
+  double px = 0, py = 0, pt = 0, s = 0, c = 1;
+  bool free = false;
   if (p < p1) {
-    const double px = est[p], py = est[P + p], pt = est[2 * P + p];
-    double s, c;
+    px = est[p]; py = est[P + p]; pt = est[2 * P + p];
     sincos(pt, &s, &c);
-    const bool free = a.pose_free[p] != 0;
-    double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
-    // ---- landmark edges of this pose (EdgeSE2PointXY) ----
-    const int e0 = a.el_start[p], e1 = a.el_start[p + 1];
-    for (int e = e0; e < e1; e++) {
-      const int fl = a.el_flags[e];
-      if (!(fl & EF_ACTIVE)) continue;
-      const int l = a.el_lm[e];
-      const double dx = est[3 * P + l] - px, dy = est[3 * P + L + l] - py;
-      const double i00 = a.el_info[e], i01 = a.el_info[El + e], i11 = a.el_info[2 * El + e];
-      const double j02 = -s * dx + c * dy;  // d e_x / d theta
-      const double j12 = -c * dx - s * dy;  // d e_y / d theta
-      const double ex = c * dx + s * dy - meas[e];
-      const double ey = j02 - meas[El + e];
-      chi += ex * (i00 * ex + i01 * ey) + ey * (i01 * ex + i11 * ey);
-      if (CHI2_ONLY || !free) continue;
-      // A = Ji^T Omega, Ji = [[-c, -s, j02], [s, -c, j12]]
-      const double a00 = -c * i00 + s * i01, a01 = -c * i01 + s * i11;
-      const double a10 = -s * i00 - c * i01, a11 = -s * i01 - c * i11;
-      const double a20 = j02 * i00 + j12 * i01, a21 = j02 * i01 + j12 * i11;
-      b0 -= a00 * ex + a01 * ey;
-      b1 -= a10 * ex + a11 * ey;
-      b2 -= a20 * ex + a21 * ey;
-      h00 += a00 * (-c) + a01 * s;
-      h01 += a00 * (-s) + a01 * (-c);
-      h02 += a00 * j02 + a01 * j12;
-      h11 += a10 * (-s) + a11 * (-c);
-      h12 += a10 * j02 + a11 * j12;
-      h22 += a20 * j02 + a21 * j12;
-      if (fl & EF_OFFDIAG) {  // Ji^T Omega Jl, Jl = [[c, s], [-s, c]]
-        double B[6] = {a00 * c - a01 * s, a00 * s + a01 * c, a10 * c - a11 * s,
-                       a10 * s + a11 * c, a20 * c - a21 * s, a20 * s + a21 * c};
-        double* hv = V + a.el_slot[e];
-        double o[6];
-        if (fl & EF_TRANS) {  // stored landmark rows x pose columns (2x3)
-          o[0] = B[0]; o[1] = B[2]; o[2] = B[4]; o[3] = B[1]; o[4] = B[3]; o[5] = B[5];
-        } else {
+    free = a.pose_free[p] != 0;
+    if (!CHI2_ONLY) {  // the landmark kernel reuses the trig instead of recomputing it per edge
+      double* trig = a.trig + (size_t)r * 2 * P;
+      trig[p] = s;
+      trig[P + p] = c;
+    }
+  }
+  s_pose[wid][0][lane] = px; s_pose[wid][1][lane] = py; s_pose[wid][2][lane] = s; s_pose[wid][3][lane] = c;
 #pragma unroll
-          for (int k = 0; k < 6; k++) o[k] = B[k];
-        }
-        if (fl & EF_FIRST) {
+  for (int k = 0; k < 9; k++) s_acc[wid][k][lane] = 0.0;
+  __syncwarp();
+  if (pw0 < p1) {  // warp-uniform
+    const int pw1 = min(pw0 + 32, p1);
+    const int e_begin = a.el_start[pw0], e_end = a.el_start[pw1];
+    for (int base = e_begin; base < e_end; base += 32) {
+      const int e = base + lane;
+      const bool valid = e < e_end;
+      int pl = -1 - lane;  // unique key for idle lanes
+      double v[9];
 #pragma unroll
-          for (int k = 0; k < 6; k++) hv[k] = o[k];
-        } else {
+      for (int k = 0; k < 9; k++) v[k] = 0.0;
+      int fl = 0;
+      double o[6];
+      int slot = 0;
+      if (valid) {
+        fl = a.el_flags[e];
+        pl = a.el_pose[e] - pw0;
+      }
+      if (valid && (fl & EF_ACTIVE)) {
+        const int l = a.el_lm[e];
+        const double qx = s_pose[wid][0][pl], qy = s_pose[wid][1][pl], qs = s_pose[wid][2][pl], qc = s_pose[wid][3][pl];
+        const double dx = est[3 * P + l] - qx, dy = est[3 * P + L + l] - qy;
+        const double i00 = a.el_info[e], i01 = a.el_info[El + e], i11 = a.el_info[2 * El + e];
+        const double j02 = -qs * dx + qc * dy;  // d e_x / d theta
+        const double j12 = -qc * dx - qs * dy;  // d e_y / d theta
+        const double ex = qc * dx + qs * dy - meas[e];
+        const double ey = j02 - meas[El + e];
+        chi += ex * (i00 * ex + i01 * ey) + ey * (i01 * ex + i11 * ey);
+        if (!CHI2_ONLY && a.pose_free[pw0 + pl]) {
+          // A = Ji^T Omega, Ji = [[-c, -s, j02], [s, -c, j12]]
+          const double a00 = -qc * i00 + qs * i01, a01 = -qc * i01 + qs * i11;
+          const double a10 = -qs * i00 - qc * i01, a11 = -qs * i01 - qc * i11;
+          const double a20 = j02 * i00 + j12 * i01, a21 = j02 * i01 + j12 * i11;
+          v[6] = -(a00 * ex + a01 * ey);
+          v[7] = -(a10 * ex + a11 * ey);
+          v[8] = -(a20 * ex + a21 * ey);
+          v[0] = a00 * (-qc) + a01 * qs;
+          v[1] = a00 * (-qs) + a01 * (-qc);
+          v[2] = a00 * j02 + a01 * j12;
+          v[3] = a10 * (-qs) + a11 * (-qc);
+          v[4] = a10 * j02 + a11 * j12;
+          v[5] = a20 * j02 + a21 * j12;
+          if (fl & EF_OFFDIAG) {  // Ji^T Omega Jl, Jl = [[c, s], [-s, c]]
+            const double B[6] = {a00 * qc - a01 * qs, a00 * qs + a01 * qc, a10 * qc - a11 * qs,
+                                 a10 * qs + a11 * qc, a20 * qc - a21 * qs, a20 * qs + a21 * qc};
+            slot = a.el_slot[e];
+            if (fl & EF_TRANS) {  // stored landmark rows x pose columns (2x3)
+              o[0] = B[0]; o[1] = B[2]; o[2] = B[4]; o[3] = B[1]; o[4] = B[3]; o[5] = B[5];
+            } else {
 #pragma unroll
-          for (int k = 0; k < 6; k++) hv[k] += o[k];
+              for (int k = 0; k < 6; k++) o[k] = B[k];
+            }
+            if (fl & EF_FIRST) {
+              double* hv = V + slot;
+#pragma unroll
+              for (int k = 0; k < 6; k++) hv[k] = o[k];
+            }
+          }
         }
       }
+      if (!CHI2_ONLY) {
+        // duplicate edges of one (pose, landmark) pair (the doubled first-cone edge, repeated
+        // matches) add to the block their first edge stored: rare, so serialised in edge order
+        unsigned dup = __ballot_sync(0xffffffffu, valid && (fl & EF_ACTIVE) && (fl & EF_OFFDIAG) && !(fl & EF_FIRST) &&
+                                                      a.pose_free[pw0 + max(pl, 0)]);
+        while (dup) {
+          __syncwarp();
+          const int src = __ffs(dup) - 1;
+          if (lane == src) {
+            double* hv = V + slot;
+#pragma unroll
+            for (int k = 0; k < 6; k++) hv[k] += o[k];
+          }
+          dup &= dup - 1;
+        }
+        // segmented inclusive scan over lanes of the same pose (edges are sorted by pose)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int plo = __shfl_up_sync(0xffffffffu, pl, d);
+          const bool take = lane >= d && plo == pl;
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            const double t = __shfl_up_sync(0xffffffffu, v[k], d);
+            if (take) v[k] += t;
+          }
+        }
+        const int pln = __shfl_down_sync(0xffffffffu, pl, 1);
+        if (valid && (lane == 31 || pln != pl)) {  // tail of a segment: the only writer of this pose now
+#pragma unroll
+          for (int k = 0; k < 9; k++) s_acc[wid][k][pl] += v[k];
+        }
+        __syncwarp();
+      }
     }
+  }
+  if (p < p1) {
+    double h00 = s_acc[wid][0][lane], h01 = s_acc[wid][1][lane], h02 = s_acc[wid][2][lane];
+    double h11 = s_acc[wid][3][lane], h12 = s_acc[wid][4][lane], h22 = s_acc[wid][5][lane];
+    double b0 = s_acc[wid][6][lane], b1 = s_acc[wid][7][lane], b2 = s_acc[wid][8][lane];
     // ---- pose-pose edges incident to this pose (EdgeSE2) ----
     const int q0 = a.po_start[p], q1 = a.po_start[p + 1];
     for (int q = q0; q < q1; q++) {
@@ -252,18 +335,30 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks) {
   if (!CHI2_ONLY && l < L && a.lm_free[l]) {  // warp-uniform
     const double lx = est[3 * P + l], ly = est[3 * P + L + l];
     double h00 = 0, h01 = 0, h11 = 0, b0 = 0, b1 = 0;
-    const int q0 = a.lm_start[l], q1 = a.lm_start[l + 1];
+    int q0 = a.lm_start[l], q1 = a.lm_start[l + 1];
+    if (p0 > 0 || p1 < P) {
+      // pose-range shard: landmark edges are sorted by pose, so the shard's edges are the sorted
+      // positions [el_start[p0], el_start[p1]); the landmark's list is ascending -> two bisections
+      const int elo = a.el_start[p0], ehi = a.el_start[p1];
+      int lo = q0, hi = q1;
+      while (lo < hi) { int m = (lo + hi) >> 1; if (a.lm_edges[m] < elo) lo = m + 1; else hi = m; }
+      const int b0 = lo;
+      hi = q1;
+      while (lo < hi) { int m = (lo + hi) >> 1; if (a.lm_edges[m] < ehi) lo = m + 1; else hi = m; }
+      q0 = b0;
+      q1 = lo;
+    }
+    const double* trig = a.trig + (size_t)r * 2 * P;
+    const double* mlm = meas + 2 * (size_t)El + 3 * (size_t)a.Eo;  // measurements in landmark order
     for (int q = q0 + lane; q < q1; q += 32) {
-      const int e = a.lm_edges[q];
-      if (!(a.el_flags[e] & EF_ACTIVE)) continue;
-      const int p = a.el_pose[e];
-      if (p < p0 || p >= p1) continue;
-      double s, c;
-      sincos(est[2 * P + p], &s, &c);
+      // everything indexed by q is laid out in landmark order: coalesced across the lanes
+      const int p = a.lmo_pose[q];
+      if (p < 0) continue;  // inactive edge
+      const double s = trig[p], c = trig[P + p];
       const double dx = lx - est[p], dy = ly - est[P + p];
-      const double ex = c * dx + s * dy - meas[e];
-      const double ey = -s * dx + c * dy - meas[El + e];
-      const double i00 = a.el_info[e], i01 = a.el_info[El + e], i11 = a.el_info[2 * El + e];
+      const double ex = c * dx + s * dy - mlm[q];
+      const double ey = -s * dx + c * dy - mlm[El + q];
+      const double i00 = a.lmo_info[q], i01 = a.lmo_info[El + q], i11 = a.lmo_info[2 * (size_t)El + q];
       // A = Jl^T Omega, Jl = [[c, s], [-s, c]]
       const double a00 = c * i00 - s * i01, a01 = c * i01 - s * i11;
       const double a10 = s * i00 + c * i01, a11 = s * i01 + c * i11;
@@ -326,11 +421,30 @@ __global__ void update_kernel(int P, int L, long estStride, double* est_all, con
   if (v == 0) status[2 * r + 1] += 1;
 }
 
+// Structure arrays go up through ONE pinned staging buffer: ~40 small copies from pageable vectors
+// would each be staged synchronously by the driver (measured 16 ms for the 10-lap graph).
+struct PendingUpload { void* dst; const void* src; size_t bytes; };
+std::vector<PendingUpload> g_uploads;
+
 template <class T>
 int upload_vec(slam_b200_ctx* c, DevBuf<T>& d, const std::vector<T>& h) {
   SLAM_CUDA_TRY(c, d.exact(h.size()));
-  if (!h.empty())
-    SLAM_CUDA_TRY(c, cudaMemcpyAsync(d.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, c->stream));
+  if (!h.empty()) g_uploads.push_back({d.p, h.data(), sizeof(T) * h.size()});
+  return 0;
+}
+
+int flush_uploads(slam_b200_ctx* c) {
+  size_t total = 0;
+  for (auto& u : g_uploads) total += (u.bytes + 255) & ~(size_t)255;
+  SLAM_CUDA_TRY(c, c->pin_stage.reserve(total + 256));
+  size_t off = 0;
+  for (auto& u : g_uploads) {
+    std::memcpy(c->pin_stage.p + off, u.src, u.bytes);
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(u.dst, c->pin_stage.p + off, u.bytes, cudaMemcpyHostToDevice, c->stream));
+    off += (u.bytes + 255) & ~(size_t)255;
+  }
+  g_uploads.clear();
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -356,7 +470,8 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
   a.pose_free = D.pose_free.p; a.lm_free = D.lm_free.p;
   a.el_start = D.el_start.p; a.el_pose = D.el_pose.p; a.el_lm = D.el_lm.p; a.el_slot = D.el_slot.p;
   a.el_flags = D.el_flags.p; a.el_info = D.el_info.p;
-  a.lm_start = D.lm_start.p; a.lm_edges = D.lm_edges.p;
+  a.lm_start = D.lm_start.p; a.lm_edges = D.lm_edges.p; a.lmo_pose = D.lmo_pose.p; a.lmo_info = D.lmo_info.p;
+  a.trig = D.trig.p;
   a.eo_i = D.eo_i.p; a.eo_j = D.eo_j.p; a.eo_slot = D.eo_slot.p; a.eo_flags = D.eo_flags.p;
   a.po_start = D.po_start.p; a.po_list = D.po_list.p; a.eo_info = D.eo_info.p;
   a.chi2_part = D.chi2_part.p; a.chi2_blocks = D.chi2_blocks;
@@ -497,6 +612,18 @@ int graph_build_structure(slam_b200_ctx* c) {
     std::vector<int> cur(lm_start.begin(), lm_start.end() - 1);
     for (int q = 0; q < El; q++) lm_edges[cur[s_lm[q]]++] = q;
   }
+  // landmark-ordered payload of the landmark kernel: pose of every edge (-1 = inactive) and its
+  // information matrix, in the order of lm_edges, so the lanes of a warp read consecutive memory
+  std::vector<int> lmo_pose(El);
+  std::vector<double> lmo_info(3 * (size_t)El);
+  for (int q = 0; q < El; q++) {
+    const int e = lm_edges[q];  // pose-sorted position
+    lmo_pose[q] = (s_flags[e] & EF_ACTIVE) ? s_pose[e] : -1;
+    lmo_info[q] = s_info[e];
+    lmo_info[El + (size_t)q] = s_info[El + (size_t)e];
+    lmo_info[2 * (size_t)El + q] = s_info[2 * (size_t)El + e];
+  }
+  D.lm_order = lm_edges;
   // pose-pose edges: incidence lists, slots, owner = min(i, j)
   std::vector<int> po_start(P + 1, 0), po_list(2 * (size_t)Eo), eo_slot(Eo, -1);
   for (int e = 0; e < Eo; e++) { po_start[g.eo_i[e] + 1]++; po_start[g.eo_j[e] + 1]++; }
@@ -525,6 +652,7 @@ int graph_build_structure(slam_b200_ctx* c) {
   for (int e = 0; e < Eo; e++)
     for (int k = 0; k < 6; k++) eo_info[(size_t)k * Eo + e] = g.eo_info[6 * (size_t)e + k];
   D.nV = cursor;
+  D.t_structure = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // ---- symbolic analysis ----
   int leaf = 1024;
   if (const char* s = getenv("SLAM_B200_ND_LEAF")) leaf = std::max(1, atoi(s));
@@ -563,6 +691,7 @@ int graph_build_structure(slam_b200_ctx* c) {
         launch_list.push_back(f);
         LL.n_tiny++;
         LL.smem_tiny = std::max(LL.smem_tiny, need);
+        LL.max_fs_tiny = std::max(LL.max_fs_tiny, (int)fs);
       } else if (need <= smem_limit) {
         small.push_back(f);
         LL.smem_factor = std::max(LL.smem_factor, need);
@@ -579,6 +708,7 @@ int graph_build_structure(slam_b200_ctx* c) {
     LL.n_small = (int)small.size();
     LL.n_big = (int)big.size();
   }
+  D.launch_list_host = launch_list;
   // forward-solve gather lists (by destination row of the parent front, children in order)
   std::vector<int> frow_ptr(S.nf + 1, 0), gather_ptr, gather_src;
   for (int f = 0; f < S.nf; f++) frow_ptr[f + 1] = frow_ptr[f] + S.npiv[f] + S.nupd[f] + 1;
@@ -619,8 +749,11 @@ int graph_build_structure(slam_b200_ctx* c) {
       for (int k = 0; k < 3; k++) solver2v[so + k] = 6 * L + 3 * p + k;
     }
   }
+  D.t_lists = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - D.t_structure - S.seconds;
   // ---- upload structure ----
+  auto tu0 = std::chrono::steady_clock::now();
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  g_uploads.clear();
   int rc = 0;
   rc |= upload_vec(c, D.pose_free, pose_free);
   rc |= upload_vec(c, D.lm_free, lm_free);
@@ -634,6 +767,8 @@ int graph_build_structure(slam_b200_ctx* c) {
   rc |= upload_vec(c, D.el_info, s_info);
   rc |= upload_vec(c, D.lm_start, lm_start);
   rc |= upload_vec(c, D.lm_edges, lm_edges);
+  rc |= upload_vec(c, D.lmo_pose, lmo_pose);
+  rc |= upload_vec(c, D.lmo_info, lmo_info);
   rc |= upload_vec(c, D.eo_i, g.eo_i);
   rc |= upload_vec(c, D.eo_j, g.eo_j);
   rc |= upload_vec(c, D.eo_slot, eo_slot);
@@ -659,14 +794,14 @@ int graph_build_structure(slam_b200_ctx* c) {
   rc |= upload_vec(c, D.ds.frow_ptr, frow_ptr);
   rc |= upload_vec(c, D.ds.gather_ptr, gather_ptr);
   rc |= upload_vec(c, D.ds.gather_src, gather_src);
-  if (rc) return SLAM_B200_E_CUDA;
-  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (rc) { g_uploads.clear(); return SLAM_B200_E_CUDA; }
+  if (int frc = flush_uploads(c)) return frc;
   D.structure_version = g.structure_version;
   D.values_version = 0;
   D.R = 0;  // value arrays must be (re)allocated for the new sizes
   D.drop_graph();
   D.assembled = false;
-  D.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - S.seconds;
+  D.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tu0).count();
   return D.n;
 }
 
@@ -674,7 +809,7 @@ int graph_alloc_values(slam_b200_ctx* c, int R) {
   DeviceSystem& D = *c->sys;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   D.estStride = 3L * D.P + 2L * D.L;
-  D.measStride = 2L * D.El + 3L * D.Eo;
+  D.measStride = 4L * D.El + 3L * D.Eo;  // + the landmark-ordered copy of the cone measurements
   D.chi2_cap = 64;
   D.chi2_blocks = std::max(1, (D.P + ASM_THREADS - 1) / ASM_THREADS);
   if (R != D.R) {
@@ -691,6 +826,7 @@ int graph_alloc_values(slam_b200_ctx* c, int R) {
     SLAM_CUDA_TRY(c, D.chi2_part.exact(r * D.chi2_blocks));
     SLAM_CUDA_TRY(c, D.status.exact(2 * r));
     SLAM_CUDA_TRY(c, D.est0.exact(r * D.estStride));
+    SLAM_CUDA_TRY(c, D.trig.exact(r * 2 * (size_t)D.P));
     D.R = R;
     D.drop_graph();
     D.values_version = 0;
@@ -730,6 +866,12 @@ int graph_upload_host_values(slam_b200_ctx* c) {
     m[2 * (size_t)El + Eo + k] = g.eo_z[3 * (size_t)k + 1];
     m[2 * (size_t)El + 2 * (size_t)Eo + k] = g.eo_z[3 * (size_t)k + 2];
   }
+  double* ml = m + 2 * (size_t)El + 3 * (size_t)Eo;  // landmark order
+  for (int q = 0; q < El; q++) {
+    int e = D.lm_order[q];
+    ml[q] = m[e];
+    ml[El + (size_t)q] = m[El + (size_t)e];
+  }
   if (ne) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.est.p, e, sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
   if (nm) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.meas.p, m, sizeof(double) * nm, cudaMemcpyHostToDevice, c->stream));
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // pinned staging buffer is reused
@@ -752,7 +894,7 @@ void graph_release(slam_b200_ctx* c) {
   D.ds.frow_ptr.release(); D.ds.gather_ptr.release(); D.ds.gather_src.release();
   D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
   D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
-  D.est0.release();
+  D.est0.release(); D.trig.release(); D.lmo_pose.release(); D.lmo_info.release();
   D.drop_graph();
   delete c->sys;
   c->sys = nullptr;

@@ -2,8 +2,9 @@
 //
 // Memory layout (all fp64, replica-major: replica r lives at base + r * stride):
 //   est   : [x[P] | y[P] | theta[P] | lx[L] | ly[L]]                      SoA estimates
-//   meas  : [el_zx[El] | el_zy[El] | eo_zx[Eo] | eo_zy[Eo] | eo_zt[Eo]]   SoA measurements
-//           (landmark edges sorted by pose, the order performSLAM inserts them in)
+//   meas  : [el_zx[El] | el_zy[El] | eo_zx[Eo] | eo_zy[Eo] | eo_zt[Eo] | lm_zx[El] | lm_zy[El]]
+//           SoA measurements; landmark edges sorted by pose (the order performSLAM inserts them in)
+//           plus a second copy in landmark order so both assembly kernels read coalesced
 //   V     : [b_lm 2L | H_lm 4L | b_pose 3P | H_pose 9P | H_offdiag ...]   the normal equations
 //           H blocks are dense row-major; an off-diagonal block is stored once, oriented like
 //           g2o's upper-triangular block matrix (rows = vertex with the lower Hessian index).
@@ -32,7 +33,7 @@ struct LevelLaunch {
   // shared memory, 256-thread CTAs), then n_big (front in a global scratch slab)
   int list_off = 0, n_tiny = 0, n_small = 0, n_big = 0;
   size_t smem_tiny = 0, smem_factor = 0, smem_solve = 0;
-  int max_fs = 0;
+  int max_fs = 0, max_fs_tiny = 0;
 };
 
 struct DeviceSystem {
@@ -51,18 +52,22 @@ struct DeviceSystem {
   std::vector<int> el_perm;        // sorted landmark-edge position -> insertion index
   Symbolic sym;
   std::vector<LevelLaunch> levels;
-  double upload_seconds = 0;
+  std::vector<int> launch_list_host;
+  double upload_seconds = 0, t_structure = 0, t_lists = 0;
   // device structure
   DevBuf<unsigned char> pose_free, lm_free;
   DevBuf<int> pose_boff, lm_boff;  // solver scalar offset or -1
   DevBuf<int> el_start, el_pose, el_lm, el_slot, el_flags;   // landmark edges sorted by pose
   DevBuf<double> el_info;          // [3][El] SoA
   DevBuf<int> lm_start, lm_edges;  // CSR landmark -> sorted edge positions
+  DevBuf<int> lmo_pose;            // landmark order: pose of the edge, -1 if inactive
+  DevBuf<double> lmo_info;         // landmark order: [3][El] information
+  std::vector<int> lm_order;       // host copy of lm_edges (to lay measurements out in landmark order)
   DevBuf<int> eo_i, eo_j, eo_slot, eo_flags, po_start, po_list;
   DevBuf<double> eo_info;          // [6][Eo] SoA
   DevSym ds;
   // device values
-  DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part, est0;
+  DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part, est0, trig;
   DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done (= chi2 slot)
   int chi2_cap = 0, chi2_blocks = 0;
   int iters_enqueued = 0;

@@ -15,9 +15,9 @@
 namespace {
 
 constexpr int FACTOR_THREADS = 512;
-constexpr int FACTOR_THREADS_TINY = 128;  // fronts of <= 64 rows
+
 constexpr int SOLVE_THREADS = 1024;      // levels with fronts of > 64 rows: few CTAs, stage L fast
-constexpr int SOLVE_THREADS_TINY = 128;
+
 
 struct SymArgs {
   const int *piv0, *npiv, *nupd, *rows_ptr, *upd_rows, *rel, *child_ptr, *children, *asm_ptr, *solver2v;
@@ -205,6 +205,260 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   }
 }
 
+// ================================================================================================
+// Warp-per-front kernels for small fronts (fs <= 64 rows): no block barriers, no redundant work.
+// Lane l owns front rows l and l + 32.  Most fronts of a trackdrive graph are this small (the
+// leaves of the assembly tree) and all fronts of the batched Monte-Carlo configuration are, so
+// these kernels carry the throughput; the CTA-per-front kernels above carry the few large fronts
+// near the root.
+// ================================================================================================
+constexpr int TINY_WARPS = 4;   // fronts per CTA
+constexpr int TNB = 4;          // pivots per panel
+
+// The front is stored PACKED (lower triangle only, column j holds rows j..fs-1 at offset
+// j*fs - j(j-1)/2): half the shared memory of a square front = twice the fronts resident per SM,
+// which is what bounds this latency-dominated kernel.
+__device__ __forceinline__ int tri_off(int j, int fs) { return j * fs - ((j * (j - 1)) >> 1) - j; }  // + row
+
+__global__ void __launch_bounds__(TINY_WARPS * 32)
+factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* __restrict__ V_all, long nV,
+                   double* Lv_all, long nL, double* Uv_all, long nU, int* status) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fi = blockIdx.x * TINY_WARPS + wid;
+  if (fi >= count) return;  // no block-wide barrier below
+  const int g = S.launch_list[list_off + fi];
+  const int r = blockIdx.y;
+  const int s = S.npiv[g], u = S.nupd[g], fs = s + u;
+  const double* V = V_all + (size_t)r * nV;
+  double* Uv = Uv_all + (size_t)r * nU;
+  double* F = smem + (size_t)wid * slab;  // packed lower triangle: F[tri_off(j, fs) + i], i >= j
+  const int ntri = (fs * (fs + 1)) >> 1;
+  for (int t = lane; t < ntri; t += 32) F[t] = 0.0;
+  __syncwarp();
+  for (int q = S.asm_ptr[g] + lane; q < S.asm_ptr[g + 1]; q += 32) {
+    const AsmEntry en = S.asm_entries[q];
+    const double* hv = V + en.hoff;
+    const int dr = en.meta & 0xff, dc = (en.meta >> 8) & 0xff;
+    const bool trans = (en.meta >> 16) & 1, diag = (en.meta >> 17) & 1;
+    if (diag) {
+      for (int i = 0; i < dr; i++)
+        for (int j = 0; j <= i; j++) F[tri_off(en.c + j, fs) + en.r + i] = hv[i * dc + j];
+    } else if (!trans) {
+      for (int i = 0; i < dr; i++)
+        for (int j = 0; j < dc; j++) F[tri_off(en.c + j, fs) + en.r + i] = hv[i * dc + j];
+    } else {
+      for (int i = 0; i < dc; i++)
+        for (int j = 0; j < dr; j++) F[tri_off(en.c + j, fs) + en.r + i] = hv[j * dc + i];
+    }
+  }
+  __syncwarp();
+  // extend-add the children's Schur complements (children of a small front are small: uc <= 64)
+  for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
+    const int ch = S.children[ci];
+    const int uc = S.nupd[ch];
+    const double* Uc = Uv + S.uptr[ch];
+    const int* rel = S.rel + S.rows_ptr[ch];
+    const int i0 = lane, i1 = lane + 32;
+    const int rl0 = i0 < uc ? rel[i0] : 0, rl1 = i1 < uc ? rel[i1] : 0;
+    for (int j = 0; j < uc; j++) {
+      const int ra = __shfl_sync(0xffffffffu, rl0, j & 31), rb = __shfl_sync(0xffffffffu, rl1, j & 31);
+      const int relj = j < 32 ? ra : rb;
+      const double* col = Uc + j * uc;
+      double* dst = F + tri_off(relj, fs);
+      if (i0 >= j && i0 < uc) dst[rl0] += col[i0];
+      if (i1 >= j && i1 < uc) dst[rl1] += col[i1];
+    }
+    __syncwarp();
+  }
+  // right-looking LDL^T, panels of TNB pivots held in registers; the panel's triangle and the
+  // column factors travel between lanes by shuffle
+  bool bad = false;
+  for (int k0 = 0; k0 < s; k0 += TNB) {
+    const int nb = min(TNB, s - k0);
+    const int r0 = k0 + lane, r1 = r0 + 32;
+    double a0[TNB], a1[TNB], inv[TNB];
+#pragma unroll
+    for (int p = 0; p < TNB; p++) {
+      // lanes above the diagonal of the panel (r0 < k0 + p) hold 0: the packed layout has no such entry
+      a0[p] = (p < nb) ? ((r0 < fs && r0 >= k0 + p) ? F[tri_off(k0 + p, fs) + r0] : 0.0) : (lane == p ? 1.0 : 0.0);
+      a1[p] = (p < nb && r1 < fs) ? F[tri_off(k0 + p, fs) + r1] : 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < TNB; p++) {
+      const double d = __shfl_sync(0xffffffffu, a0[p], p);
+      if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;  // SimplicialCholesky_impl.h:175-179
+      inv[p] = __drcp_rn(d);
+#pragma unroll
+      for (int q = p + 1; q < TNB; q++) {
+        const double f = __shfl_sync(0xffffffffu, a0[p], q) * inv[p];
+        a0[q] -= a0[p] * f;
+        a1[q] -= a1[p] * f;
+      }
+    }
+#pragma unroll
+    for (int p = 1; p < TNB; p++) {
+      if (p < nb) {
+        if (r0 < fs && r0 >= k0 + p) F[tri_off(k0 + p, fs) + r0] = a0[p];
+        if (r1 < fs) F[tri_off(k0 + p, fs) + r1] = a1[p];
+      }
+    }
+    double c0[TNB], c1[TNB];
+#pragma unroll
+    for (int p = 0; p < TNB; p++) {
+      c0[p] = (p < nb) ? a0[p] * inv[p] : 0.0;
+      c1[p] = (p < nb) ? a1[p] * inv[p] : 0.0;
+    }
+    const int jend0 = min(fs, k0 + 32);
+    int j = k0 + nb;
+    for (; j + 1 < jend0; j += 2) {  // two independent columns per step; row factors in slot 0 of lanes j-k0, j+1-k0
+      const int src = j - k0;
+      double* cA = F + tri_off(j, fs);
+      double* cB = F + tri_off(j + 1, fs);
+      const bool wA0 = r0 >= j && r0 < fs, wB0 = r0 >= j + 1 && r0 < fs, w1 = r1 < fs;
+      double aA0 = wA0 ? cA[r0] : 0.0, aA1 = w1 ? cA[r1] : 0.0;
+      double aB0 = wB0 ? cB[r0] : 0.0, aB1 = w1 ? cB[r1] : 0.0;
+#pragma unroll
+      for (int p = 0; p < TNB; p++) {
+        const double cjA = __shfl_sync(0xffffffffu, c0[p], src);
+        const double cjB = __shfl_sync(0xffffffffu, c0[p], src + 1);
+        aA0 -= a0[p] * cjA; aA1 -= a1[p] * cjA;
+        aB0 -= a0[p] * cjB; aB1 -= a1[p] * cjB;
+      }
+      if (wA0) cA[r0] = aA0;
+      if (w1) cA[r1] = aA1;
+      if (wB0) cB[r0] = aB0;
+      if (w1) cB[r1] = aB1;
+    }
+    for (; j < jend0; j++) {
+      const int src = j - k0;
+      double* cA = F + tri_off(j, fs);
+      const bool wA0 = r0 >= j && r0 < fs, w1 = r1 < fs;
+      double acc0 = wA0 ? cA[r0] : 0.0, acc1 = w1 ? cA[r1] : 0.0;
+#pragma unroll
+      for (int p = 0; p < TNB; p++) {
+        const double cj = __shfl_sync(0xffffffffu, c0[p], src);
+        acc0 -= a0[p] * cj;
+        acc1 -= a1[p] * cj;
+      }
+      if (wA0) cA[r0] = acc0;
+      if (w1) cA[r1] = acc1;
+    }
+    for (j = max(k0 + nb, k0 + 32); j < fs; j++) {  // row factor in slot 1 of lane j - k0 - 32
+      const int src = j - k0 - 32;
+      const bool w1 = r1 >= j && r1 < fs;
+      double* cA = F + tri_off(j, fs);
+      double acc1 = w1 ? cA[r1] : 0.0;
+#pragma unroll
+      for (int p = 0; p < TNB; p++) acc1 -= a1[p] * __shfl_sync(0xffffffffu, c1[p], src);
+      if (w1) cA[r1] = acc1;
+    }
+    __syncwarp();
+  }
+  if (bad && lane == 0) status[2 * r] = 1;
+  double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
+  for (int j = 0; j < s; j++) {
+    const double* col = F + tri_off(j, fs);
+    const double d = col[j];
+    const double iv = __drcp_rn(d);
+    double* out = Lg + (size_t)j * fs;
+    for (int i = lane; i < fs; i += 32) out[i] = i < j ? 0.0 : (i == j ? d : col[i] * iv);
+  }
+  double* Ug = Uv + S.uptr[g];
+  for (int j = 0; j < u; j++) {
+    const double* col = F + tri_off(s + j, fs) + s;
+    double* out = Ug + (size_t)j * u;
+    for (int i = j + lane; i < u; i += 32) out[i] = col[i];
+  }
+}
+
+__global__ void __launch_bounds__(TINY_WARPS * 32)
+forward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restrict__ V_all, long nV,
+                    const double* __restrict__ Lv_all, long nL, double* uvec_all, long nUvec, double* x_all, int n) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fi = blockIdx.x * TINY_WARPS + wid;
+  if (fi >= count) return;
+  const int g = S.launch_list[list_off + fi];
+  const int r = blockIdx.y;
+  const int s = S.npiv[g], u = S.nupd[g], fs = s + u, p0 = S.piv0[g];
+  const double* V = V_all + (size_t)r * nV;
+  const double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
+  double* uvec = uvec_all + (size_t)r * nUvec;
+  double* x = x_all + (size_t)r * n;
+  const int* gp = S.gather_ptr + S.frow_ptr[g];
+  const int i0 = lane, i1 = lane + 32;
+  double w0 = 0.0, w1 = 0.0;
+  if (i0 < fs) {
+    w0 = i0 < s ? V[S.solver2v[p0 + i0]] : 0.0;
+    for (int q = gp[i0]; q < gp[i0 + 1]; q++) w0 += uvec[S.gather_src[q]];
+  }
+  if (i1 < fs) {
+    w1 = i1 < s ? V[S.solver2v[p0 + i1]] : 0.0;
+    for (int q = gp[i1]; q < gp[i1 + 1]; q++) w1 += uvec[S.gather_src[q]];
+  }
+  for (int k0 = 0; k0 < s; k0 += 4) {  // four columns of L in flight, then the dependent updates
+    double l0[4], l1[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const int k = k0 + p;
+      l0[p] = (k < s && i0 > k && i0 < fs) ? Lg[(size_t)k * fs + i0] : 0.0;
+      l1[p] = (k < s && i1 > k && i1 < fs) ? Lg[(size_t)k * fs + i1] : 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const int k = k0 + p;
+      const double wa = __shfl_sync(0xffffffffu, w0, k & 31), wb = __shfl_sync(0xffffffffu, w1, k & 31);
+      const double wk = k < 32 ? wa : wb;
+      w0 -= l0[p] * wk;
+      w1 -= l1[p] * wk;
+    }
+  }
+  if (i0 < s) x[p0 + i0] = w0 / Lg[(size_t)i0 * fs + i0];
+  else if (i0 < fs) uvec[S.rows_ptr[g] + i0 - s] = w0;
+  if (i1 < s) x[p0 + i1] = w1 / Lg[(size_t)i1 * fs + i1];
+  else if (i1 < fs) uvec[S.rows_ptr[g] + i1 - s] = w1;
+}
+
+__global__ void __launch_bounds__(TINY_WARPS * 32)
+backward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restrict__ Lv_all, long nL,
+                     double* x_all, int n) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int fi = blockIdx.x * TINY_WARPS + wid;
+  if (fi >= count) return;
+  const int g = S.launch_list[list_off + fi];
+  const int r = blockIdx.y;
+  const int s = S.npiv[g], u = S.nupd[g], fs = s + u, p0 = S.piv0[g];
+  const double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
+  double* x = x_all + (size_t)r * n;
+  const int* rows = S.upd_rows + S.rows_ptr[g];
+  const int i0 = lane, i1 = lane + 32;
+  double x0 = 0.0, x1 = 0.0;
+  if (i0 < fs) x0 = i0 < s ? x[p0 + i0] : x[rows[i0 - s]];
+  if (i1 < fs) x1 = i1 < s ? x[p0 + i1] : x[rows[i1 - s]];
+  for (int kb = ((s - 1) / 4) * 4; kb >= 0; kb -= 4) {
+    double l0[4], l1[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const int k = kb + p;
+      l0[p] = (k < s && i0 > k && i0 < fs) ? Lg[(size_t)k * fs + i0] : 0.0;
+      l1[p] = (k < s && i1 > k && i1 < fs) ? Lg[(size_t)k * fs + i1] : 0.0;
+    }
+#pragma unroll
+    for (int p = 3; p >= 0; p--) {
+      const int k = kb + p;
+      if (k < s) {  // warp-uniform
+        double t = l0[p] * x0 + l1[p] * x1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (k < 32) { if (lane == k) x0 -= t; }
+        else if (lane == k - 32) x1 -= t;
+      }
+    }
+  }
+  if (i0 < s) x[p0 + i0] = x0;
+  if (i1 < s) x[p0 + i1] = x1;
+}
+
 // L panel (fs x s, leading dimension fs) from global into shared memory with leading dimension ld:
 // one warp per column, lanes over rows, up to five independent loads in flight per lane
 __device__ __forceinline__ void stage_panel(double* Ls, const double* __restrict__ Lg, int fs, int s, int ld,
@@ -353,6 +607,13 @@ backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long
   for (int i = tid; i < s; i += nt) x[p0 + i] = xo[i];
 }
 
+// Small fronts (<= 64 rows): one warp per front when there are enough of them to fill the machine
+// (batched replicas, very large graphs), otherwise one 128-thread CTA per front (a single mid-size
+// graph has only ~1,000 leaves: more threads per front shorten the level's latency).
+bool warp_kernels(const slam_b200_ctx* c, const DeviceSystem& D, const LevelLaunch& LL) {
+  return (long)LL.n_tiny * D.R >= 16L * c->num_sms;
+}
+
 size_t factor_extra_smem(int max_fs) {  // srel (ints, even count) + scaled panel
   return (size_t)((max_fs + 1) & ~1) * sizeof(int) + (size_t)NB * max_fs * sizeof(double);
 }
@@ -380,6 +641,7 @@ static int solver_init_attrs(slam_b200_ctx* c) {
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     g_attr_set = true;
   }
   return 0;
@@ -400,9 +662,15 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   };
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
-    if (LL.n_tiny) {
+    if (LL.n_tiny && warp_kernels(c, D, LL)) {
+      dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
+      const int slab = (LL.max_fs_tiny * (LL.max_fs_tiny + 1)) / 2;
+      factor_tiny_kernel<<<grid, TINY_WARPS * 32, (size_t)TINY_WARPS * slab * sizeof(double), c->stream>>>(
+          S, LL.list_off, LL.n_tiny, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.status.p);
+      c->launches++;
+    } else if (LL.n_tiny) {
       dim3 grid(LL.n_tiny, D.R);
-      factor_kernel<true><<<grid, FACTOR_THREADS_TINY, LL.smem_tiny + 64 * sizeof(int) + NB * 64 * sizeof(double), c->stream>>>(
+      factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
           S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p);
       c->launches++;
     }
@@ -421,59 +689,63 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     }
   }
   mark();  // factored
-  // solves: a level's fronts either all stage their L panel in shared memory or none does
-  for (int lv = 0; lv < nlv; lv++) {
+  // solves: small fronts by the warp kernels; per level the remaining fronts either all stage their
+  // L panel in shared memory or none does
+  auto rest_smem = [&](int lv, size_t& need, size_t& wneed, bool& fits) {
     const LevelLaunch& LL = D.levels[lv];
-    int nfr = LL.n_tiny + LL.n_small + LL.n_big;
-    if (!nfr) continue;
-    dim3 grid(nfr, D.R);
-    // smem_solve was clamped to the limit; recompute whether every front of the level fits
-    bool fits = true;
-    size_t need = 0;
-    for (int q = 0; q < nfr; q++) {
-      int f = D.sym.level_ptr[lv] + q;  // same set as the launch list of this level
-      size_t fs = (size_t)D.sym.npiv[f] + D.sym.nupd[f];
-      size_t nd = ((fs | 1) * D.sym.npiv[f] + fs + D.sym.npiv[f]) * sizeof(double);
-      need = std::max(need, nd);
-      if (nd > smem_limit) fits = false;
-    }
-    const int sthreads = LL.max_fs > 64 ? SOLVE_THREADS : SOLVE_THREADS_TINY;
-    if (fits)
-      forward_kernel<true><<<grid, sthreads, need, c->stream>>>(S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL,
-                                                              D.uvec.p, D.nUvec, D.x.p, D.n);
-    else {
-      size_t wneed = 0;
-      for (int q = 0; q < nfr; q++) {
-        int f = D.sym.level_ptr[lv] + q;
-        wneed = std::max(wneed, ((size_t)2 * D.sym.npiv[f] + D.sym.nupd[f]) * sizeof(double));
-      }
-      forward_kernel<false><<<grid, sthreads, wneed, c->stream>>>(S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL,
-                                                                D.uvec.p, D.nUvec, D.x.p, D.n);
-    }
-    c->launches++;
-  }
-  mark();  // forward done
-  for (int lv = nlv - 1; lv >= 0; lv--) {
-    const LevelLaunch& LL = D.levels[lv];
-    int nfr = LL.n_tiny + LL.n_small + LL.n_big;
-    if (!nfr) continue;
-    dim3 grid(nfr, D.R);
-    bool fits = true;
-    size_t need = 0, wneed = 0;
-    for (int q = 0; q < nfr; q++) {
-      int f = D.sym.level_ptr[lv] + q;
+    need = wneed = 0;
+    fits = true;
+    for (int q = LL.n_tiny; q < LL.n_tiny + LL.n_small + LL.n_big; q++) {
+      int f = D.launch_list_host[LL.list_off + q];
       size_t fs = (size_t)D.sym.npiv[f] + D.sym.nupd[f];
       size_t nd = ((fs | 1) * D.sym.npiv[f] + fs + D.sym.npiv[f]) * sizeof(double);
       need = std::max(need, nd);
       wneed = std::max(wneed, (fs + D.sym.npiv[f]) * sizeof(double));
       if (nd > smem_limit) fits = false;
     }
-    const int sthreads = LL.max_fs > 64 ? SOLVE_THREADS : SOLVE_THREADS_TINY;
+  };
+  for (int lv = 0; lv < nlv; lv++) {
+    const LevelLaunch& LL = D.levels[lv];
+    if (LL.n_tiny) {  // warp kernel: registers + shuffles, L read straight from global, no staging
+      dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
+      forward_tiny_kernel<<<grid, TINY_WARPS * 32, 0, c->stream>>>(S, LL.list_off, LL.n_tiny, D.V.p, D.nV, D.Lv.p,
+                                                                  D.nL, D.uvec.p, D.nUvec, D.x.p, D.n);
+      c->launches++;
+    }
+    const int nrest = LL.n_small + LL.n_big;
+    if (!nrest) continue;
+    dim3 grid(nrest, D.R);
+    size_t need, wneed;
+    bool fits;
+    rest_smem(lv, need, wneed, fits);
     if (fits)
-      backward_kernel<true><<<grid, sthreads, need, c->stream>>>(S, LL.list_off, D.Lv.p, D.nL, D.x.p, D.n);
+      forward_kernel<true><<<grid, SOLVE_THREADS, need, c->stream>>>(S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p,
+                                                                   D.nL, D.uvec.p, D.nUvec, D.x.p, D.n);
     else
-      backward_kernel<false><<<grid, sthreads, wneed, c->stream>>>(S, LL.list_off, D.Lv.p, D.nL, D.x.p, D.n);
+      forward_kernel<false><<<grid, SOLVE_THREADS, wneed, c->stream>>>(S, LL.list_off + LL.n_tiny, D.V.p, D.nV,
+                                                                     D.Lv.p, D.nL, D.uvec.p, D.nUvec, D.x.p, D.n);
     c->launches++;
+  }
+  mark();  // forward done
+  for (int lv = nlv - 1; lv >= 0; lv--) {
+    const LevelLaunch& LL = D.levels[lv];
+    const int nrest = LL.n_small + LL.n_big;
+    if (nrest) {
+      dim3 grid(nrest, D.R);
+      size_t need, wneed;
+      bool fits;
+      rest_smem(lv, need, wneed, fits);
+      if (fits)
+        backward_kernel<true><<<grid, SOLVE_THREADS, need, c->stream>>>(S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n);
+      else
+        backward_kernel<false><<<grid, SOLVE_THREADS, wneed, c->stream>>>(S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n);
+      c->launches++;
+    }
+    if (LL.n_tiny) {
+      dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
+      backward_tiny_kernel<<<grid, TINY_WARPS * 32, 0, c->stream>>>(S, LL.list_off, LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n);
+      c->launches++;
+    }
   }
   SLAM_CUDA_TRY(c, cudaGetLastError());
   mark();  // backward done
@@ -526,8 +798,8 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
       // (assemble 2 + per level factor/forward/backward + update)
       int n = 2 + 1;
       for (const LevelLaunch& LL : D.levels) {
-        n += (LL.n_tiny ? 1 : 0) + (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);
-        n += (LL.n_tiny + LL.n_small + LL.n_big) ? 2 : 0;
+        n += (LL.n_tiny ? 1 : 0) + (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);   // factor
+        n += 2 * ((LL.n_tiny ? 1 : 0) + ((LL.n_small + LL.n_big) ? 1 : 0));      // forward + backward
       }
       D.launches_per_iter = n;
     }

@@ -240,6 +240,10 @@ def test_sharded_assembly_partials_sum_to_full(ctx, pkg, synth):
         parts.append(V.clone())
     tot = parts[0] + parts[1] + parts[2]
     assert torch.allclose(tot[:6 * L], full[:6 * L], rtol=1e-12, atol=1e-14)        # landmark part: sums
-    assert torch.equal(tot[6 * L:], full[6 * L:])                                    # everything else: one owner
+    # everything else has exactly one owner shard (other shards leave zeros); the warp-level
+    # summation tree depends on where a shard starts, so last-bit differences are allowed
+    assert torch.allclose(tot[6 * L:], full[6 * L:], rtol=1e-13, atol=1e-15)
+    owners = sum((p[6 * L:] != 0).to(torch.int32) for p in parts)
+    assert int(owners.max()) <= 1
     lm, n = ctx.graph_system_dev(0)
     assert n == 6 * L and lm == ptr
