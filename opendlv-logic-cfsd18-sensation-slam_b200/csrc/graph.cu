@@ -324,15 +324,15 @@ constexpr int LM_PER_BLOCK = ASM_THREADS / 32;
 
 template <bool CHI2_ONLY>
 __global__ void __launch_bounds__(ASM_THREADS)
-assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks) {
+assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_first, int l_end) {
   const int lane = threadIdx.x & 31;
-  const int l = blockIdx.x * LM_PER_BLOCK + (threadIdx.x >> 5);
+  const int l = l_first + blockIdx.x * LM_PER_BLOCK + (threadIdx.x >> 5);
   const int r = blockIdx.y;
   const double* est = a.est + (size_t)r * a.estStride;
   const double* meas = a.meas + (size_t)r * a.measStride;
   double* V = a.V + (size_t)r * a.nV;
   const int P = a.P, L = a.L, El = a.El;
-  if (!CHI2_ONLY && l < L && a.lm_free[l]) {  // warp-uniform
+  if (!CHI2_ONLY && l < l_end && a.lm_free[l]) {  // warp-uniform
     const double lx = est[3 * P + l], ly = est[3 * P + L + l];
     double h00 = 0, h01 = 0, h11 = 0, b0 = 0, b1 = 0;
     int q0 = a.lm_start[l], q1 = a.lm_start[l + 1];
@@ -484,9 +484,25 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
     else assemble_pose_kernel<false><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
     c->launches++;
   }
-  dim3 gl(std::max(1, (D.L + LM_PER_BLOCK - 1) / LM_PER_BLOCK), D.R);
-  if (chi2_only) assemble_landmark_kernel<true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk);
-  else assemble_landmark_kernel<false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk);
+  // landmarks touched by this pose range (a shard of a large graph sees a small, contiguous-ish part
+  // of the landmarks); the untouched part of the landmark blocks must read as zero for the reduction
+  int l_first = 0, l_end = D.L;
+  if (!chi2_only && (p0 > 0 || p1 < D.P) && D.R == 1) {
+    if (D.shard_p0 != p0 || D.shard_p1 != p1) {
+      int lo = D.L, hi = -1;
+      const int e0 = D.el_start_host[p0], e1 = D.el_start_host[p1];
+      for (int e = e0; e < e1; e++) { lo = std::min(lo, D.s_lm_host[e]); hi = std::max(hi, D.s_lm_host[e]); }
+      D.shard_p0 = p0; D.shard_p1 = p1;
+      D.shard_l0 = hi < 0 ? 0 : lo;
+      D.shard_l1 = hi < 0 ? 0 : hi + 1;
+    }
+    l_first = D.shard_l0;
+    l_end = D.shard_l1;
+    SLAM_CUDA_TRY(c, cudaMemsetAsync(D.V.p, 0, sizeof(double) * 6 * (size_t)D.L, c->stream));
+  }
+  dim3 gl(std::max(1, (l_end - l_first + LM_PER_BLOCK - 1) / LM_PER_BLOCK), D.R);
+  if (chi2_only) assemble_landmark_kernel<true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
+  else assemble_landmark_kernel<false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
   c->launches++;
   SLAM_CUDA_TRY(c, cudaGetLastError());
   if (!chi2_only) D.assembled = true;
@@ -554,7 +570,7 @@ int graph_build_structure(slam_b200_ctx* c) {
   }
   // ---- block structure (buildStructure): one slot per distinct free vertex pair ----
   std::unordered_map<uint64_t, int> slotOf;
-  slotOf.reserve((size_t)(El + Eo) * 2);
+  slotOf.reserve((size_t)Eo * 2);
   D.off_a.clear(); D.off_b.clear(); D.hoff_off.clear();
   long cursor = base_off;
   auto slot = [&](int ba, int bb) -> int {
@@ -582,21 +598,42 @@ int graph_build_structure(slam_b200_ctx* c) {
   std::vector<int> s_pose(El), s_lm(El), s_slot(El, -1), s_flags(El, 0);
   std::vector<double> s_info(3 * (size_t)El);
   {
-    std::unordered_map<int, int> seen;  // slot -> 1 within the current pose run
-    int curPose = -1;
+    // A (pose, landmark) pair can only repeat inside one pose's run of edges, so duplicates are found
+    // by a linear look-back over that run (a handful of edges) -- no global hash for the 10^5..10^7
+    // pose-landmark blocks; only pose-pose pairs go through the hash map below.
+    auto new_slot = [&](int ba, int bb) -> int {
+      int lo = std::min(ba, bb), hi = std::max(ba, bb);
+      int k = (int)D.off_a.size();
+      D.off_a.push_back(lo);
+      D.off_b.push_back(hi);
+      D.hoff_off.push_back((int)cursor);
+      cursor += dim[lo] * dim[hi];
+      return k;
+    };
+    D.off_a.reserve((size_t)El + Eo);
+    D.off_b.reserve((size_t)El + Eo);
+    D.hoff_off.reserve((size_t)El + Eo);
+    std::vector<int> run_slot(El, -1);  // slot index of every sorted edge (or -1)
+    int runStart = 0;
     for (int q = 0; q < El; q++) {
       int e = D.el_perm[q];
       int p = g.el_p[e], l = g.el_l[e];
-      if (p != curPose) { seen.clear(); curPose = p; }
+      if (q > 0 && p != s_pose[q - 1]) runStart = q;
       s_pose[q] = p;
       s_lm[q] = l;
       int fl = el_flags[e];
       if ((fl & EF_ACTIVE) && D.pose_b[p] >= 0 && D.lm_b[l] >= 0) {
-        int k = slot(D.pose_b[p], D.lm_b[l]);
+        int k = -1;
+        for (int t = runStart; t < q; t++)
+          if (s_lm[t] == l && run_slot[t] >= 0) { k = run_slot[t]; break; }
+        if (k < 0) {
+          k = new_slot(D.pose_b[p], D.lm_b[l]);
+          fl |= EF_FIRST;
+        }
+        run_slot[q] = k;
         s_slot[q] = D.hoff_off[k];
         fl |= EF_OFFDIAG;
         if (D.lm_b[l] < D.pose_b[p]) fl |= EF_TRANS;
-        if (seen.emplace(k, 1).second) fl |= EF_FIRST;
       }
       s_flags[q] = fl;
       s_info[q] = g.el_info[3 * (size_t)e];
@@ -624,6 +661,9 @@ int graph_build_structure(slam_b200_ctx* c) {
     lmo_info[2 * (size_t)El + q] = s_info[2 * (size_t)El + e];
   }
   D.lm_order = lm_edges;
+  D.s_lm_host = s_lm;
+  D.el_start_host = el_start;
+  D.shard_p0 = D.shard_p1 = -1;
   // pose-pose edges: incidence lists, slots, owner = min(i, j)
   std::vector<int> po_start(P + 1, 0), po_list(2 * (size_t)Eo), eo_slot(Eo, -1);
   for (int e = 0; e < Eo; e++) { po_start[g.eo_i[e] + 1]++; po_start[g.eo_j[e] + 1]++; }

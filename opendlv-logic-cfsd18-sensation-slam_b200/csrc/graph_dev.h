@@ -63,6 +63,8 @@ struct DeviceSystem {
   DevBuf<int> lmo_pose;            // landmark order: pose of the edge, -1 if inactive
   DevBuf<double> lmo_info;         // landmark order: [3][El] information
   std::vector<int> lm_order;       // host copy of lm_edges (to lay measurements out in landmark order)
+  std::vector<int> s_lm_host, el_start_host;  // landmark of every pose-sorted edge; edge range per pose
+  int shard_p0 = -1, shard_p1 = -1, shard_l0 = 0, shard_l1 = 0;  // cached landmark range of the last pose shard
   DevBuf<int> eo_i, eo_j, eo_slot, eo_flags, po_start, po_list;
   DevBuf<double> eo_info;          // [6][Eo] SoA
   DevSym ds;

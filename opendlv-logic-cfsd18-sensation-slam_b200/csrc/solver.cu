@@ -44,7 +44,8 @@ constexpr int NB = 8;
 template <bool SMEM>
 __global__ void __launch_bounds__(FACTOR_THREADS)
 factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV, double* Lv_all, long nL,
-              double* Uv_all, long nU, double* Fbig_all, long nFbig, int* status) {
+              double* Uv_all, long nU, double* Fbig_all, long nFbig, int* status, double* uvec_all, long nUvec,
+              double* x_all, int n) {
   extern __shared__ double smem[];
   const int g = S.launch_list[list_off + blockIdx.x];
   const int r = blockIdx.y;
@@ -104,6 +105,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   // Sp: the current panel scaled by 1/d (Sp[p*fs + j] = F[j, k0+p] / d_p), written by the row threads
   // of step (1) and broadcast-read as the column factors of step (2)
   double* Sp = reinterpret_cast<double*>(srel + ((fs + 1) & ~1));
+  double* dinv = Sp + (size_t)NB * fs;  // 1/d of every pivot (s doubles), then w (fs) for the fused forward solve
   for (int k0 = 0; k0 < s; k0 += NB) {
     const int nb = min(NB, s - k0);
     double* Pk = F + (size_t)k0 * fs;  // panel columns: Pk[p * fs + row]
@@ -127,6 +129,11 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
       }
     }
     if (bad && tid == 0) status[2 * r] = 1;
+    if (tid < nb) {
+#pragma unroll
+      for (int p = 0; p < NB; p++)
+        if (p == tid) dinv[k0 + p] = invd[p];
+    }
     for (int i = k0 + nb + tid; i < fs; i += nt) {
       double rr[NB];
 #pragma unroll
@@ -188,6 +195,53 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
     }
     __syncthreads();
   }
+  // ---- fused forward solve of this front (L y = b, z = D^-1 y): the factor is still in shared
+  // memory, so the leaves-to-root sweep rides along with the factorisation instead of re-reading
+  // every L panel in a second pass of kernels.  Columns are unscaled: l_ik = F[i,k] * dinv[k].
+  {
+    double* w = dinv + s;  // fs
+    const int p0 = S.piv0[g];
+    const double* uvecr = uvec_all + (size_t)r * nUvec;
+    const int* gp = S.gather_ptr + S.frow_ptr[g];
+    for (int i = tid; i < fs; i += nt) {
+      double acc = i < s ? V[S.solver2v[p0 + i]] : 0.0;
+      for (int q = gp[i]; q < gp[i + 1]; q++) acc += uvecr[S.gather_src[q]];
+      w[i] = acc;
+    }
+    __syncthreads();
+    double* xr = x_all + (size_t)r * n;
+    for (int k0 = 0; k0 < s; k0 += NB) {
+      const int nb = min(NB, s - k0);
+      const double* Pk = F + (size_t)k0 * fs;
+      double yd[NB];  // y[p] * dinv[p]
+#pragma unroll
+      for (int p = 0; p < NB; p++) yd[p] = (p < nb) ? w[k0 + p] : 0.0;
+#pragma unroll
+      for (int p = 0; p < NB; p++) {
+        if (p < nb) {
+          yd[p] *= dinv[k0 + p];
+#pragma unroll
+          for (int q = p + 1; q < NB; q++)
+            if (q < nb) yd[q] -= Pk[p * fs + k0 + q] * yd[p];
+        }
+      }
+      for (int i = k0 + nb + tid; i < fs; i += nt) {
+        double acc = w[i];
+#pragma unroll
+        for (int p = 0; p < NB; p++)
+          if (p < nb) acc -= Pk[p * fs + i] * yd[p];
+        w[i] = acc;
+      }
+      if (tid < nb) {
+#pragma unroll
+        for (int p = 0; p < NB; p++)
+          if (p == tid) xr[p0 + k0 + p] = yd[p];  // z = D^-1 y
+      }
+      __syncthreads();
+    }
+    double* uo = uvec_all + (size_t)r * nUvec + S.rows_ptr[g];
+    for (int i = s + tid; i < fs; i += nt) uo[i - s] = w[i];
+  }
   // L panel (fs x s, unit lower with D on the diagonal) and the Schur complement for the parent
   double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
   for (int j = warp; j < s; j += nw) {
@@ -222,7 +276,8 @@ __device__ __forceinline__ int tri_off(int j, int fs) { return j * fs - ((j * (j
 
 __global__ void __launch_bounds__(TINY_WARPS * 32)
 factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* __restrict__ V_all, long nV,
-                   double* Lv_all, long nL, double* Uv_all, long nU, int* status) {
+                   double* Lv_all, long nL, double* Uv_all, long nU, int* status, double* uvec_all, long nUvec,
+                   double* x_all, int n) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int fi = blockIdx.x * TINY_WARPS + wid;
@@ -356,6 +411,35 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
     __syncwarp();
   }
   if (bad && lane == 0) status[2 * r] = 1;
+  // ---- fused forward solve (see factor_kernel): lane l owns rows l and l + 32 of w ----
+  {
+    const int p0 = S.piv0[g];
+    const double* uvecr = uvec_all + (size_t)r * nUvec;
+    const int* gp = S.gather_ptr + S.frow_ptr[g];
+    const int i0 = lane, i1 = lane + 32;
+    double w0 = 0.0, w1 = 0.0;
+    if (i0 < fs) {
+      w0 = i0 < s ? V[S.solver2v[p0 + i0]] : 0.0;
+      for (int q = gp[i0]; q < gp[i0 + 1]; q++) w0 += uvecr[S.gather_src[q]];
+    }
+    if (i1 < fs) {
+      w1 = i1 < s ? V[S.solver2v[p0 + i1]] : 0.0;
+      for (int q = gp[i1]; q < gp[i1 + 1]; q++) w1 += uvecr[S.gather_src[q]];
+    }
+    for (int k = 0; k < s; k++) {
+      const double* col = F + tri_off(k, fs);
+      const double dk = col[k];
+      const double wa = __shfl_sync(0xffffffffu, w0, k & 31), wb = __shfl_sync(0xffffffffu, w1, k & 31);
+      const double zk = (k < 32 ? wa : wb) * __drcp_rn(dk);  // y_k / d_k; l_ik = col[i] / d_k
+      if (i0 > k && i0 < fs) w0 -= col[i0] * zk;
+      if (i1 > k && i1 < fs) w1 -= col[i1] * zk;
+      if (lane == (k & 31)) { if (k < 32) w0 = zk; else w1 = zk; }  // keep z in the pivot's slot
+    }
+    double* xr = x_all + (size_t)r * n;
+    double* uo = uvec_all + (size_t)r * nUvec + S.rows_ptr[g];
+    if (i0 < s) xr[p0 + i0] = w0; else if (i0 < fs) uo[i0 - s] = w0;
+    if (i1 < s) xr[p0 + i1] = w1; else if (i1 < fs) uo[i1 - s] = w1;
+  }
   double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
   for (int j = 0; j < s; j++) {
     const double* col = F + tri_off(j, fs);
@@ -615,7 +699,7 @@ bool warp_kernels(const slam_b200_ctx* c, const DeviceSystem& D, const LevelLaun
 }
 
 size_t factor_extra_smem(int max_fs) {  // srel (ints, even count) + scaled panel
-  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + (size_t)NB * max_fs * sizeof(double);
+  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + (size_t)(NB + 2) * max_fs * sizeof(double);
 }
 
 SymArgs sym_args(const DeviceSystem& D) {
@@ -666,25 +750,28 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
       const int slab = (LL.max_fs_tiny * (LL.max_fs_tiny + 1)) / 2;
       factor_tiny_kernel<<<grid, TINY_WARPS * 32, (size_t)TINY_WARPS * slab * sizeof(double), c->stream>>>(
-          S, LL.list_off, LL.n_tiny, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.status.p);
+          S, LL.list_off, LL.n_tiny, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.status.p, D.uvec.p, D.nUvec,
+          D.x.p, D.n);
       c->launches++;
     } else if (LL.n_tiny) {
       dim3 grid(LL.n_tiny, D.R);
       factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
-          S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p);
+          S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
+          D.x.p, D.n);
       c->launches++;
     }
     if (LL.n_small) {
       dim3 grid(LL.n_small, D.R);
       factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
-          S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p);
+          S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
+          D.nUvec, D.x.p, D.n);
       c->launches++;
     }
     if (LL.n_big) {
       dim3 grid(LL.n_big, D.R);
       factor_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
           S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
-          D.status.p);
+          D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n);
       c->launches++;
     }
   }
@@ -704,7 +791,10 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       if (nd > smem_limit) fits = false;
     }
   };
-  for (int lv = 0; lv < nlv; lv++) {
+  // The forward sweep is fused into the factor kernels above.  SLAM_B200_SEPARATE_FORWARD=1 runs the
+  // stand-alone forward kernels as well (same results; kept for A/B measurements).
+  static const bool separate_forward = getenv("SLAM_B200_SEPARATE_FORWARD") != nullptr;
+  for (int lv = 0; separate_forward && lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
     if (LL.n_tiny) {  // warp kernel: registers + shuffles, L read straight from global, no staging
       dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
@@ -799,7 +889,7 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
       int n = 2 + 1;
       for (const LevelLaunch& LL : D.levels) {
         n += (LL.n_tiny ? 1 : 0) + (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);   // factor
-        n += 2 * ((LL.n_tiny ? 1 : 0) + ((LL.n_small + LL.n_big) ? 1 : 0));      // forward + backward
+        n += (LL.n_tiny ? 1 : 0) + ((LL.n_small + LL.n_big) ? 1 : 0);            // backward (forward is fused)
       }
       D.launches_per_iter = n;
     }

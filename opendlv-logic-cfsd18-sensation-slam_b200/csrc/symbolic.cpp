@@ -5,9 +5,14 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <numeric>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <set>
+#include <thread>
 
 namespace {
 
@@ -192,20 +197,98 @@ struct Nd {
 // Hub vertices (a landmark seen from hundreds of poses) therefore stay until their spokes are gone,
 // which is what keeps fill low on pose-landmark graphs.  Exact elimination graph, sorted adjacency.
 // ------------------------------------------------------------------------------------------------
-static std::vector<int> constrained_min_degree(int nb, const int* dim, const std::vector<int>& xadj,
-                                               const std::vector<int>& adjv, const std::vector<int>& rank) {
-  std::vector<std::vector<int>> adj(nb);
-  for (int v = 0; v < nb; v++) {
-    adj[v].assign(adjv.begin() + xadj[v], adjv.begin() + xadj[v + 1]);
-    std::sort(adj[v].begin(), adj[v].end());
-    adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end());
+
+// A small persistent pool of host threads (created once per process: thread creation costs
+// milliseconds inside container sandboxes, which would eat the whole gain of a per-call pool).
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool p;
+    return p;
   }
-  // degree buckets per rank: doubly linked lists, O(1) insert / remove
+  int size() const { return (int)workers_.size() + 1; }
+  // runs fn(0..njobs-1), the caller participates; returns when every job is done
+  void run(int njobs, const std::function<void(int)>& fn) {
+    if (njobs <= 0) return;
+    if (workers_.empty() || njobs == 1) {
+      for (int j = 0; j < njobs; j++) fn(j);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn;
+      njobs_ = njobs;
+      next_.store(0);
+      pending_ = njobs;
+      generation_++;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = (int)std::min<unsigned>(std::max(1u, hw), 16u);
+    if (const char* e = getenv("SLAM_B200_SYM_THREADS")) n = std::max(1, atoi(e));
+    for (int t = 1; t < n; t++) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      generation_++;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void work() {
+    for (;;) {
+      int j = next_.fetch_add(1);
+      if (j >= njobs_) break;
+      (*fn_)(j);
+      std::lock_guard<std::mutex> lk(m_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        if (stop_) return;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int njobs_ = 0, pending_ = 0;
+  std::atomic<int> next_{0};
+  unsigned long generation_ = 0;
+  bool stop_ = false;
+};
+
+// Generic kernel: eliminates every vertex with rank <= max_rank in (rank, weighted degree) order on
+// the elimination graph `adj` (sorted adjacency lists, updated in place: what is left afterwards is
+// the elimination graph of the remaining vertices).  Appends to `order`.
+static void min_degree_eliminate(std::vector<std::vector<int>>& adj, const int* dim, const std::vector<int>& rank,
+                                 int max_rank, std::vector<int>& order) {
+  const int nb = (int)adj.size();
   int nrank = 1;
-  for (int v = 0; v < nb; v++) nrank = std::max(nrank, rank[v] + 1);
+  for (int v = 0; v < nb; v++)
+    if (rank[v] <= max_rank) nrank = std::max(nrank, rank[v] + 1);
   std::vector<long> wdeg(nb, 0);
   std::vector<std::vector<int>> head(nrank);
   std::vector<int> nxt(nb, -1), prv(nb, -1), remaining(nrank, 0), mindeg(nrank, 0);
+  auto in_play = [&](int v) { return rank[v] <= max_rank; };
   auto bucket_insert = [&](int v) {
     std::vector<int>& h = head[rank[v]];
     long d = wdeg[v];
@@ -224,11 +307,10 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
   };
   for (int v = 0; v < nb; v++) {
     for (int u : adj[v]) wdeg[v] += dim[u];
-    remaining[rank[v]]++;
+    if (in_play(v)) remaining[rank[v]]++;
   }
-  for (int v = nb - 1; v >= 0; v--) bucket_insert(v);  // ties resolved towards the lower index
-  std::vector<int> order;
-  order.reserve(nb);
+  for (int v = nb - 1; v >= 0; v--)
+    if (in_play(v)) bucket_insert(v);  // ties resolved towards the lower index
   std::vector<int> N;
   for (int rk = 0; rk < nrank; rk++) {
     while (remaining[rk] > 0) {
@@ -244,24 +326,134 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
       adj[v].clear();
       adj[v].shrink_to_fit();
       for (int u : N) {
-        bucket_remove(u);
+        const bool play = in_play(u);
+        if (play) bucket_remove(u);
         std::vector<int>& A = adj[u];
         long w = wdeg[u];
-        // remove v
         auto it = std::lower_bound(A.begin(), A.end(), v);
         if (it != A.end() && *it == v) { A.erase(it); w -= dim[v]; }
-        // insert the members of N that are missing (usually none: neighbours of a low-degree vertex
-        // mostly know each other already)
+        // insert the members of N that are missing (usually none: the neighbours of a low-degree
+        // vertex mostly know each other already)
         for (int x : N) {
           if (x == u) continue;
           auto jt = std::lower_bound(A.begin(), A.end(), x);
           if (jt == A.end() || *jt != x) { A.insert(jt, x); w += dim[x]; }
         }
         wdeg[u] = w;
-        bucket_insert(u);
+        if (play) bucket_insert(u);
       }
     }
   }
+}
+
+// Constrained minimum degree.  The interiors of the nested-dissection regions (rank 0) do not touch
+// each other -- only the separators around them -- so every region is ordered independently on its
+// own copy of (interior + halo) by a pool of host threads; the fill each region leaves among its
+// halo vertices is merged into the separator graph, which is then ordered rank by rank.
+static std::vector<int> constrained_min_degree(int nb, const int* dim, const std::vector<int>& xadj,
+                                               const std::vector<int>& adjv, const std::vector<int>& rank,
+                                               const std::vector<std::vector<int>>& regions) {
+  auto tdbg0 = std::chrono::steady_clock::now();
+  std::vector<int> order;
+  order.reserve(nb);
+  const int nreg = (int)regions.size();
+  std::vector<std::vector<int>> reg_order(nreg);
+  std::vector<std::vector<std::pair<int, int>>> reg_fill(nreg);  // halo-halo fill edges (global ids)
+  auto do_region = [&](int ri) {
+    auto tr0 = std::chrono::steady_clock::now();
+    const std::vector<int>& R = regions[ri];
+    // local numbering: interior first, then halo
+    std::vector<int> loc2g(R);
+    std::vector<std::pair<int, int>> g2l;  // sorted (global, local)
+    g2l.reserve(R.size() * 2);
+    for (size_t k = 0; k < R.size(); k++) g2l.push_back({R[k], (int)k});
+    std::sort(g2l.begin(), g2l.end());
+    auto find_local = [&](int gv) -> int {
+      auto it = std::lower_bound(g2l.begin(), g2l.end(), std::make_pair(gv, -1));
+      return (it != g2l.end() && it->first == gv) ? it->second : -1;
+    };
+    const int nint = (int)R.size();
+    // discover the halo
+    std::vector<int> halo;
+    for (int v : R)
+      for (int p = xadj[v]; p < xadj[v + 1]; p++) {
+        int u = adjv[p];
+        if (find_local(u) < 0) halo.push_back(u);
+      }
+    std::sort(halo.begin(), halo.end());
+    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+    for (int hv : halo) { g2l.push_back({hv, (int)loc2g.size()}); loc2g.push_back(hv); }
+    std::sort(g2l.begin(), g2l.end());
+    const int nloc = (int)loc2g.size();
+    std::vector<std::vector<int>> ladj(nloc);
+    std::vector<int> ldim(nloc), lrank(nloc);
+    for (int k = 0; k < nloc; k++) { ldim[k] = dim[loc2g[k]]; lrank[k] = k < nint ? 0 : 1; }
+    for (int k = 0; k < nint; k++) {
+      int v = loc2g[k];
+      for (int p = xadj[v]; p < xadj[v + 1]; p++) {
+        int lu = find_local(adjv[p]);
+        ladj[k].push_back(lu);
+        if (lu >= nint) ladj[lu].push_back(k);  // halo side of an interior-halo edge
+      }
+    }
+    for (auto& a : ladj) {
+      std::sort(a.begin(), a.end());
+      a.erase(std::unique(a.begin(), a.end()), a.end());
+    }
+    std::vector<int> lord;
+    lord.reserve(nint);
+    min_degree_eliminate(ladj, ldim.data(), lrank, 0, lord);
+    reg_order[ri].reserve(nint);
+    for (int k : lord) reg_order[ri].push_back(loc2g[k]);
+    for (int k = nint; k < nloc; k++)
+      for (int u : ladj[k])
+        if (u > k) reg_fill[ri].push_back({loc2g[k], loc2g[u]});
+    if (getenv("SLAM_B200_SYM_DEBUG"))
+      fprintf(stderr, "[symbolic] region %d: %d interior, %d halo, start %.4f dur %.4f s\n", ri, nint, nloc - nint, std::chrono::duration<double>(tr0 - tdbg0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count());
+  };
+  {
+    // largest regions first: better balance when a few regions dominate
+    std::vector<int> by_size(nreg);
+    std::iota(by_size.begin(), by_size.end(), 0);
+    std::sort(by_size.begin(), by_size.end(), [&](int a, int b) { return regions[a].size() > regions[b].size(); });
+    HostPool::get().run(nreg, [&](int j) { do_region(by_size[j]); });
+  }
+  if (getenv("SLAM_B200_SYM_DEBUG"))
+    fprintf(stderr, "[symbolic] regions joined %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tdbg0).count());
+  if (getenv("SLAM_B200_SYM_DEBUG")) {
+    size_t mx = 0, tot = 0, fill = 0;
+    for (int ri = 0; ri < nreg; ri++) { mx = std::max(mx, regions[ri].size()); tot += regions[ri].size(); fill += reg_fill[ri].size(); }
+    fprintf(stderr, "[symbolic] %d regions, max %zu, total %zu of %d, halo fill edges %zu\n", nreg, mx, tot, nb, fill);
+  }
+  for (int ri = 0; ri < nreg; ri++) order.insert(order.end(), reg_order[ri].begin(), reg_order[ri].end());
+  // separator graph: original edges among the remaining vertices + the regions' fill
+  std::vector<char> gone(nb, 0);
+  for (int v : order) gone[v] = 1;
+  std::vector<std::vector<int>> adj(nb);
+  for (int v = 0; v < nb; v++) {
+    if (gone[v]) continue;
+    for (int p = xadj[v]; p < xadj[v + 1]; p++)
+      if (!gone[adjv[p]]) adj[v].push_back(adjv[p]);
+  }
+  for (int ri = 0; ri < nreg; ri++)
+    for (auto& e : reg_fill[ri]) { adj[e.first].push_back(e.second); adj[e.second].push_back(e.first); }
+  for (int v = 0; v < nb; v++) {
+    std::sort(adj[v].begin(), adj[v].end());
+    adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end());
+  }
+  // remaining vertices by rank; already-eliminated ones get a rank beyond the limit
+  std::vector<int> rank2(rank);
+  int maxr = 0;
+  for (int v = 0; v < nb; v++) maxr = std::max(maxr, rank[v]);
+  for (int v = 0; v < nb; v++)
+    if (gone[v]) rank2[v] = maxr + 1;
+  if (getenv("SLAM_B200_SYM_DEBUG"))
+    fprintf(stderr, "[symbolic] regions+merge %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tdbg0).count());
+  std::vector<int> rest;
+  min_degree_eliminate(adj, dim, rank2, maxr, rest);
+  if (getenv("SLAM_B200_SYM_DEBUG"))
+    fprintf(stderr, "[symbolic] +separators %.4f s (%zu vertices)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tdbg0).count(), rest.size());
+  order.insert(order.end(), rest.begin(), rest.end());
   return order;
 }
 
@@ -318,7 +510,10 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   }
   S.t_nd = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // ---- stage 2: constrained minimum degree -> elimination order ----
-  std::vector<int> order = constrained_min_degree(nb, dim, nd.xadj, nd.adj, rank);
+  std::vector<std::vector<int>> regions;  // interiors of the nested-dissection leaves (rank 0)
+  for (auto& node : nd.nodes)
+    if (node.kids.empty() && !node.verts.empty()) regions.push_back(node.verts);
+  std::vector<int> order = constrained_min_degree(nb, dim, nd.xadj, nd.adj, rank, regions);
   S.t_md = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - S.t_nd;
   std::vector<int> epos(nb);
   for (int k = 0; k < nb; k++) epos[order[k]] = k;
