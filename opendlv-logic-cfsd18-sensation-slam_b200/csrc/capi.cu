@@ -554,6 +554,17 @@ int slam_b200_profile_read(slam_b200_ctx* c, double out[8]) {
   return 0;
 }
 
+// Debug: phase clocks (SM cycles) of block 0 of the most recent CTA-per-front factor launch; needs
+// SLAM_B200_PHASE_CLOCKS=1 in the environment when the graph is prepared.  out[0..6] = clock64 at:
+// start, zeroed, H scattered, children added, factorised, forward done, written; out[7..9] = s, fs, children.
+int slam_b200_debug_phase_clocks(slam_b200_ctx* c, long long out[10]) {
+  if (!c || !c->sys || !out || !c->sys->dbg_clocks.p) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpy(out, c->sys->dbg_clocks.p, sizeof(long long) * 10, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 // ---- symbolic analysis without a device (host logic; testable on a CPU-only box) ----------------
 struct SymHandle {
   Symbolic S;

@@ -865,6 +865,7 @@ int graph_alloc_values(slam_b200_ctx* c, int R) {
     SLAM_CUDA_TRY(c, D.chi2.exact(r * D.chi2_cap));
     SLAM_CUDA_TRY(c, D.chi2_part.exact(r * D.chi2_blocks));
     SLAM_CUDA_TRY(c, D.status.exact(2 * r));
+    if (getenv("SLAM_B200_PHASE_CLOCKS")) SLAM_CUDA_TRY(c, D.dbg_clocks.exact(16));
     SLAM_CUDA_TRY(c, D.est0.exact(r * D.estStride));
     SLAM_CUDA_TRY(c, D.trig.exact(r * 2 * (size_t)D.P));
     D.R = R;
@@ -934,7 +935,7 @@ void graph_release(slam_b200_ctx* c) {
   D.ds.frow_ptr.release(); D.ds.gather_ptr.release(); D.ds.gather_src.release();
   D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
   D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
-  D.est0.release(); D.trig.release(); D.lmo_pose.release(); D.lmo_info.release();
+  D.est0.release(); D.trig.release(); D.dbg_clocks.release(); D.lmo_pose.release(); D.lmo_info.release();
   D.drop_graph();
   delete c->sys;
   c->sys = nullptr;

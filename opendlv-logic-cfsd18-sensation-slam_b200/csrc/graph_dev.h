@@ -71,6 +71,7 @@ struct DeviceSystem {
   // device values
   DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part, est0, trig;
   DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done (= chi2 slot)
+  DevBuf<long long> dbg_clocks;    // optional (SLAM_B200_PHASE_CLOCKS): phase clocks of one factor CTA
   int chi2_cap = 0, chi2_blocks = 0;
   int iters_enqueued = 0;
   bool assembled = false;

@@ -22,6 +22,7 @@ constexpr int SOLVE_THREADS = 1024;      // levels with fronts of > 64 rows: few
 struct SymArgs {
   const int *piv0, *npiv, *nupd, *rows_ptr, *upd_rows, *rel, *child_ptr, *children, *asm_ptr, *solver2v;
   const int *frow_ptr, *gather_ptr, *gather_src;
+  long long* dbg;  // optional phase clocks of the last-launched CTA-per-front kernel (SLAM_B200_PHASE_CLOCKS)
   const long *lptr, *uptr, *fbig;
   const AsmEntry* asm_entries;
   const int* launch_list;
@@ -55,8 +56,10 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   double* F = SMEM ? smem : (Fbig_all + (size_t)r * nFbig + S.fbig[g]);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[0] = clock64();
   for (int t = tid; t < fs * fs; t += nt) F[t] = 0.0;
   __syncthreads();
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[1] = clock64();
   // original entries: every H block whose earlier-eliminated vertex is a pivot of this front
   for (int q = S.asm_ptr[g] + tid; q < S.asm_ptr[g + 1]; q += nt) {
     const AsmEntry en = S.asm_entries[q];
@@ -77,6 +80,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   __syncthreads();
   // extend-add the children's Schur complements (one child at a time: positions of different
   // children overlap, positions inside one child do not); warp per column, lanes over rows
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[2] = clock64();
   int* srel = reinterpret_cast<int*>(smem + (SMEM ? (size_t)fs * fs : 0));  // fs ints behind the front
   for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
     const int ch = S.children[ci];
@@ -104,58 +108,75 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   }
   // Sp: the current panel scaled by 1/d (Sp[p*fs + j] = F[j, k0+p] / d_p), written by the row threads
   // of step (1) and broadcast-read as the column factors of step (2)
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[3] = clock64();
   double* Sp = reinterpret_cast<double*>(srel + ((fs + 1) & ~1));
   double* dinv = Sp + (size_t)NB * fs;  // 1/d of every pivot (s doubles), then w (fs) for the fused forward solve
+  double* Tsm = dinv + 2 * (size_t)fs;   // current panel: NB x NB triangle + NB reciprocals, then NB forward values
   for (int k0 = 0; k0 < s; k0 += NB) {
     const int nb = min(NB, s - k0);
     double* Pk = F + (size_t)k0 * fs;  // panel columns: Pk[p * fs + row]
-    // ---- (1) panel ----
-    double T[NB][NB], invd[NB];
-#pragma unroll
-    for (int p = 0; p < NB; p++)
-#pragma unroll
-      for (int q = p; q < NB; q++) T[q][p] = (q < nb) ? Pk[p * fs + k0 + q] : (q == p ? 1.0 : 0.0);
-    bool bad = false;
-#pragma unroll
-    for (int p = 0; p < NB; p++) {
-      const double d = T[p][p];
-      if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;  // SimplicialCholesky_impl.h:175-179
-      invd[p] = __drcp_rn(d);
-#pragma unroll
-      for (int q = p + 1; q < NB; q++) {
-        const double lqp = T[q][p] * invd[p];
-#pragma unroll
-        for (int q2 = q; q2 < NB; q2++) T[q2][q] -= T[q2][p] * lqp;
-      }
-    }
-    if (bad && tid == 0) status[2 * r] = 1;
-    if (tid < nb) {
+    // ---- (1a) warp 0 factorises the NB x NB diagonal triangle in registers (a dependent chain of
+    // 8 reciprocals: one warp, not sixteen, pays its instruction stream) and publishes the final
+    // triangle + reciprocals of the pivots in shared memory
+    if (warp == 0) {
+      double T[NB][NB], iv[NB];
 #pragma unroll
       for (int p = 0; p < NB; p++)
-        if (p == tid) dinv[k0 + p] = invd[p];
-    }
-    for (int i = k0 + nb + tid; i < fs; i += nt) {
-      double rr[NB];
 #pragma unroll
-      for (int p = 0; p < NB; p++) rr[p] = (p < nb) ? Pk[p * fs + i] : 0.0;
+        for (int q = p; q < NB; q++) T[q][p] = (q < nb) ? Pk[p * fs + k0 + q] : (q == p ? 1.0 : 0.0);
+      bool bad = false;
 #pragma unroll
       for (int p = 0; p < NB; p++) {
-        const double rp = rr[p] * invd[p];
-        Sp[p * fs + i] = rp;
+        const double d = T[p][p];
+        if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;  // SimplicialCholesky_impl.h:175-179
+        iv[p] = __drcp_rn(d);
 #pragma unroll
-        for (int q = p + 1; q < NB; q++) rr[q] -= rp * T[q][p];
-      }
+        for (int q = p + 1; q < NB; q++) {
+          const double lqp = T[q][p] * iv[p];
 #pragma unroll
-      for (int p = 1; p < NB; p++)
-        if (p < nb) Pk[p * fs + i] = rr[p];
-    }
-    if (tid < nb) {  // the triangle's own rows
-#pragma unroll
-      for (int q = 0; q < NB; q++)
-        if (q == tid) {
-#pragma unroll
-          for (int p = 0; p <= q; p++) Pk[p * fs + k0 + q] = T[q][p];
+          for (int q2 = q; q2 < NB; q2++) T[q2][q] -= T[q2][p] * lqp;
         }
+      }
+      if (lane == 0) {
+        if (bad) status[2 * r] = 1;
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          Tsm[NB * NB + p] = iv[p];
+          if (p < nb) dinv[k0 + p] = iv[p];
+#pragma unroll
+          for (int q = p; q < NB; q++) {
+            Tsm[q * NB + p] = T[q][p];
+            if (q < nb && p < nb) Pk[p * fs + k0 + q] = T[q][p];  // the triangle's own rows
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (1b) one thread per row below the triangle eliminates that row's panel entries ----
+    double invd[NB];
+#pragma unroll
+    for (int p = 0; p < NB; p++) invd[p] = Tsm[NB * NB + p];
+    if (k0 + nb + tid < fs) {
+      double T[NB][NB];
+#pragma unroll
+      for (int p = 0; p < NB; p++)
+#pragma unroll
+        for (int q = p + 1; q < NB; q++) T[q][p] = Tsm[q * NB + p];
+      for (int i = k0 + nb + tid; i < fs; i += nt) {
+        double rr[NB];
+#pragma unroll
+        for (int p = 0; p < NB; p++) rr[p] = (p < nb) ? Pk[p * fs + i] : 0.0;
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          const double rp = rr[p] * invd[p];
+          Sp[p * fs + i] = rp;
+#pragma unroll
+          for (int q = p + 1; q < NB; q++) rr[q] -= rp * T[q][p];
+        }
+#pragma unroll
+        for (int p = 1; p < NB; p++)
+          if (p < nb) Pk[p * fs + i] = rr[p];
+      }
     }
     __syncthreads();
     // ---- (2) trailing update ----
@@ -195,6 +216,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
     }
     __syncthreads();
   }
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[4] = clock64();
   // ---- fused forward solve of this front (L y = b, z = D^-1 y): the factor is still in shared
   // memory, so the leaves-to-root sweep rides along with the factorisation instead of re-reading
   // every L panel in a second pass of kernels.  Columns are unscaled: l_ik = F[i,k] * dinv[k].
@@ -213,35 +235,42 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
     for (int k0 = 0; k0 < s; k0 += NB) {
       const int nb = min(NB, s - k0);
       const double* Pk = F + (size_t)k0 * fs;
-      double yd[NB];  // y[p] * dinv[p]
+      double* ysm = Tsm + NB * NB + NB;  // NB forward values of this panel (z = y / d)
+      if (warp == 0) {
+        double yd[NB];
 #pragma unroll
-      for (int p = 0; p < NB; p++) yd[p] = (p < nb) ? w[k0 + p] : 0.0;
+        for (int p = 0; p < NB; p++) yd[p] = (p < nb) ? w[k0 + p] : 0.0;
 #pragma unroll
-      for (int p = 0; p < NB; p++) {
-        if (p < nb) {
-          yd[p] *= dinv[k0 + p];
+        for (int p = 0; p < NB; p++) {
+          if (p < nb) {
+            yd[p] *= dinv[k0 + p];
 #pragma unroll
-          for (int q = p + 1; q < NB; q++)
-            if (q < nb) yd[q] -= Pk[p * fs + k0 + q] * yd[p];
+            for (int q = p + 1; q < NB; q++)
+              if (q < nb) yd[q] -= Pk[p * fs + k0 + q] * yd[p];
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int p = 0; p < NB; p++) {
+            ysm[p] = yd[p];
+            if (p < nb) xr[p0 + k0 + p] = yd[p];  // z = D^-1 y
+          }
         }
       }
+      __syncthreads();
       for (int i = k0 + nb + tid; i < fs; i += nt) {
         double acc = w[i];
 #pragma unroll
         for (int p = 0; p < NB; p++)
-          if (p < nb) acc -= Pk[p * fs + i] * yd[p];
+          if (p < nb) acc -= Pk[p * fs + i] * ysm[p];
         w[i] = acc;
-      }
-      if (tid < nb) {
-#pragma unroll
-        for (int p = 0; p < NB; p++)
-          if (p == tid) xr[p0 + k0 + p] = yd[p];  // z = D^-1 y
       }
       __syncthreads();
     }
     double* uo = uvec_all + (size_t)r * nUvec + S.rows_ptr[g];
     for (int i = s + tid; i < fs; i += nt) uo[i - s] = w[i];
   }
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[5] = clock64();
   // L panel (fs x s, unit lower with D on the diagonal) and the Schur complement for the parent
   double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
   for (int j = warp; j < s; j += nw) {
@@ -257,6 +286,9 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
     double* out = Ug + (size_t)j * u;
     for (int i = j + lane; i < u; i += 32) out[i] = col[i];
   }
+  __syncthreads();
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[6] = clock64();
+  if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { S.dbg[7] = s; S.dbg[8] = fs; S.dbg[9] = S.child_ptr[g + 1] - S.child_ptr[g]; }
 }
 
 // ================================================================================================
@@ -660,31 +692,35 @@ backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long
     if (lane == 0) xs[k] -= t;
   }
   __syncthreads();
-  // unit upper-triangular solve with L11^T, panels from the last pivot down
+  // unit upper-triangular solve with L11^T, panels from the last pivot down: warp 0 solves the
+  // NB x NB triangle (a dependent chain), everybody then subtracts the panel from the earlier rows
   const int npan = (s + NB - 1) / NB;
   for (int pan = npan - 1; pan >= 0; pan--) {
     const int k0 = pan * NB;
     const int nb = min(NB, s - k0);
-    double xp[NB];
+    if (warp == 0) {
+      double xp[NB];
 #pragma unroll
-    for (int p = 0; p < NB; p++) xp[p] = (p < nb) ? xs[k0 + p] : 0.0;
+      for (int p = 0; p < NB; p++) xp[p] = (p < nb) ? xs[k0 + p] : 0.0;
 #pragma unroll
-    for (int p = NB - 1; p >= 0; p--)
+      for (int p = NB - 1; p >= 0; p--)
 #pragma unroll
-      for (int q = 0; q < p; q++)
-        if (p < nb) xp[q] -= Lp[(size_t)(k0 + q) * ld + k0 + p] * xp[p];
+        for (int q = 0; q < p; q++)
+          if (p < nb) xp[q] -= Lp[(size_t)(k0 + q) * ld + k0 + p] * xp[p];
+      if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < NB; p++)
+          if (p < nb) xo[k0 + p] = xp[p];
+      }
+    }
+    __syncthreads();
     for (int k = tid; k < k0; k += nt) {
       const double* col = Lp + (size_t)k * ld + k0;
       double acc = xs[k];
 #pragma unroll
       for (int p = 0; p < NB; p++)
-        if (p < nb) acc -= col[p] * xp[p];
+        if (p < nb) acc -= col[p] * xo[k0 + p];
       xs[k] = acc;
-    }
-    if (tid < nb) {
-#pragma unroll
-      for (int p = 0; p < NB; p++)
-        if (p == tid) xo[k0 + p] = xp[p];
     }
     __syncthreads();
   }
@@ -699,7 +735,7 @@ bool warp_kernels(const slam_b200_ctx* c, const DeviceSystem& D, const LevelLaun
 }
 
 size_t factor_extra_smem(int max_fs) {  // srel (ints, even count) + scaled panel
-  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + (size_t)(NB + 2) * max_fs * sizeof(double);
+  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + ((size_t)(NB + 2) * max_fs + NB * NB + 2 * NB) * sizeof(double);
 }
 
 SymArgs sym_args(const DeviceSystem& D) {
@@ -710,6 +746,7 @@ SymArgs sym_args(const DeviceSystem& D) {
   a.lptr = D.ds.lptr.p; a.uptr = D.ds.uptr.p; a.fbig = D.ds.fbig.p;
   a.asm_entries = D.ds.asm_entries.p; a.launch_list = D.ds.launch_list.p;
   a.frow_ptr = D.ds.frow_ptr.p; a.gather_ptr = D.ds.gather_ptr.p; a.gather_src = D.ds.gather_src.p;
+  a.dbg = D.dbg_clocks.p;
   return a;
 }
 

@@ -36,7 +36,7 @@ def main():
         a[0] += 1; a[1] += us; a[2] = max(a[2], us)
     tot = sum(a[1] for a in agg.values())
     print(f"# ncu launch list: {title}\n")
-    print(f"{len(seq)} launches, {tot:.1f} us summed device time (cold-cache, serialised under ncu).\n")
+    print(f"{len(seq)} launches, {tot:.1f} us summed device time (serialised under ncu; see the file name for the cache control used).\n")
     print("| kernel | launches | total us | avg us | max us | share |\n|---|---:|---:|---:|---:|---:|")
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"| `{name}` | {a[0]} | {a[1]:.1f} | {a[1] / a[0]:.2f} | {a[2]:.2f} | {100 * a[1] / tot:.1f}% |")
