@@ -263,6 +263,34 @@ void Slam::sendCones() {
   onSendCones(m_map, m_currentConeIndex, pose);
 }
 
+// slam.cpp:656-679 without the OD4 sends: which cones go out, in which order, with which payload.
+// The reference computes index = (cci + i < size) ? cci + i : cci + i - size with no further check;
+// an index that is still out of range (map smaller than the packet) is skipped here instead of read.
+std::vector<ConePacketEntry> Slam::buildConePacket() {
+  Vector3d pose;
+  {
+    std::lock_guard<std::mutex> lockSend(m_sendMutex);
+    pose = m_sendPose;
+  }
+  std::lock_guard<std::mutex> lockMap(m_mapMutex);
+  std::vector<ConePacketEntry> out;
+  const size_t size = m_map.size();
+  for (uint32_t i = 0; i < m_conesPerPacket; i++) {
+    size_t index = (m_currentConeIndex + i < size) ? (m_currentConeIndex + i) : (m_currentConeIndex + i - size);
+    if (index >= size) continue;
+    ConePacketEntry e;
+    e.objectId = i;
+    e.mapIndex = (int)index;
+    ConeDirection d = m_map[index].getDirection(pose);
+    e.azimuthAngle = d.azimuthAngle;
+    e.zenithAngle = d.zenithAngle;
+    e.distance = m_map[index].getDistance(pose).distance;
+    e.type = m_map[index].getType();
+    out.push_back(e);
+  }
+  return out;
+}
+
 std::vector<Vector3d> Slam::drawPoses() {
   std::lock_guard<std::mutex> lockSensor(m_sensorMutex);
   return m_poses;

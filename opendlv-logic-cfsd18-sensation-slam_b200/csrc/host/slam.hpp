@@ -22,6 +22,14 @@
 #include "cone.hpp"
 #include "slam_types.hpp"
 
+// one entry of the cone packet the path planner receives (Slam::sendCones, slam.cpp:656-679)
+struct ConePacketEntry {
+  uint32_t objectId;   // position in the packet
+  int mapIndex;        // which map cone
+  float azimuthAngle, zenithAngle, distance;
+  int type;
+};
+
 class Slam {
  private:
   Slam(const Slam&) = delete;
@@ -48,6 +56,9 @@ class Slam {
   void performSLAM(slamtypes::MatrixXd Cones);                // slam.cpp:298-338 (private there)
   std::function<void(const slamtypes::Vector3d&)> onSendPose;                         // sendPose 681-695
   std::function<void(const std::vector<Cone>&, uint32_t, const slamtypes::Vector3d&)> onSendCones;  // 656-679
+  // The packet sendCones() emits: the next conesPerPacket map cones from m_currentConeIndex on, with
+  // wrap-around (slam.cpp:666-677), bearing/range relative to the last sent pose.
+  std::vector<ConePacketEntry> buildConePacket();
 
   // ---- introspection for tests ----
   bool loopClosing() const { return m_loopClosing; }

@@ -4,6 +4,7 @@
 #include <exception>
 #include <string>
 
+#include "frame_assembler.hpp"
 #include "slam.hpp"
 
 namespace {
@@ -110,6 +111,46 @@ void slamhost_cone_bearing(double cx, double cy, const double* pose3, float* az,
   slamtypes::Vector3d p(pose3[0], pose3[1], pose3[2]);
   *az = c.getDirection(p).azimuthAngle;
   *dist = c.getDistance(p).distance;
+}
+
+// Slam::sendCones payload; returns the number of entries
+int slamhost_cone_packet(void* h, int cap, int* mapIndex, float* az, float* dist, int* type) {
+  std::vector<ConePacketEntry> p = static_cast<Slam*>(h)->buildConePacket();
+  for (size_t k = 0; k < p.size() && (int)k < cap; k++) {
+    mapIndex[k] = p[k].mapIndex; az[k] = p[k].azimuthAngle; dist[k] = p[k].distance; type[k] = p[k].type;
+  }
+  return (int)p.size();
+}
+
+// ---- frame assembler: host logic only, usable without a GPU ----------------
+void* frameasm_create(int gatheringTimeMs, double timeBetweenKeyframes) {
+  return new FrameAssembler(gatheringTimeMs, timeBetweenKeyframes);
+}
+void frameasm_destroy(void* h) { delete static_cast<FrameAssembler*>(h); }
+void frameasm_add_direction(void* h, unsigned id, float az, float zen, long long now_us) {
+  static_cast<FrameAssembler*>(h)->addDirection(id, az, zen, now_us);
+}
+void frameasm_add_distance(void* h, unsigned id, float d, long long now_us) {
+  static_cast<FrameAssembler*>(h)->addDistance(id, d, now_us);
+}
+void frameasm_add_type(void* h, unsigned id, unsigned type, long long now_us) {
+  static_cast<FrameAssembler*>(h)->addType(id, type, now_us);
+}
+// returns the number of columns of the emitted frame (written column-major into out4xN, capacity
+// cap columns) or -1 when no keyframe was emitted
+int frameasm_poll(void* h, long long now_us, double* out4xN, int cap) {
+  slamtypes::MatrixXd f;
+  if (!static_cast<FrameAssembler*>(h)->poll(now_us, f)) return -1;
+  int n = (int)f.cols();
+  for (int j = 0; j < n && j < cap; j++)
+    for (int r = 0; r < 4; r++) out4xN[4 * (size_t)j + r] = f(r, j);
+  return n;
+}
+// [frameOpen, framesGathered, framesDropped, messagesOutOfRange, capacity]
+void frameasm_state(void* h, int* out5) {
+  FrameAssembler& a = *static_cast<FrameAssembler*>(h);
+  out5[0] = a.frameOpen(); out5[1] = a.framesGathered(); out5[2] = a.framesDroppedByKeyframeGate();
+  out5[3] = a.messagesOutOfRange(); out5[4] = a.capacity();
 }
 
 }  // extern "C"

@@ -26,6 +26,7 @@ def host(pkg):
     L.slamhost_destroy.argtypes = [C.c_void_p]
     L.slamhost_perform.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.c_float, C.c_double, c_ip, c_ip]
     L.slamhost_last_error.restype = C.c_char_p
+    L.slamhost_cone_packet.argtypes = [C.c_void_p, C.c_int, c_ip, C.POINTER(C.c_float), C.POINTER(C.c_float), c_ip]
     for n in ("slamhost_state", "slamhost_chi2_log", "slamhost_draw_cones", "slamhost_draw_poses",
               "slamhost_draw_current_pose", "slamhost_draw_graph", "slamhost_pose_estimate"):
         getattr(L, n).argtypes = None
@@ -115,6 +116,19 @@ def test_c1_replay_through_slam_class(host, orc, synth, c1_drive):
     assert len(s.poses()) == 1000
     cnt, flat = s.graph()
     assert len(cnt) == 1000 and cnt.sum() == so["n_edges"] - 999            # cone edges; odometry edges excluded
+    # the packet sendCones() emits (slam.cpp:656-679): 20 cones from m_currentConeIndex on, wrapping
+    mi = np.zeros(32, dtype=np.int32); az = np.zeros(32, dtype=np.float32); di = np.zeros(32, dtype=np.float32)
+    ty = np.zeros(32, dtype=np.int32)
+    n = host.slamhost_cone_packet(s.h, 32, mi.ctypes.data_as(c_ip), az.ctypes.data_as(C.POINTER(C.c_float)),
+                                  di.ctypes.data_as(C.POINTER(C.c_float)), ty.ctypes.data_as(c_ip))
+    assert n == 20
+    M = len(x); cci = int(sd[0]); sp = s.current_pose()
+    assert np.array_equal(mi[:n], (cci + np.arange(20)) % M)
+    assert np.array_equal(ty[:n], t[mi[:n]])
+    want_d = np.hypot(x[mi[:n]] - sp[0], y[mi[:n]] - sp[1]).astype(np.float32)
+    assert np.allclose(di[:n], want_d, rtol=1e-6)
+    want_az = (np.degrees(np.arctan2(y[mi[:n]] - sp[1], x[mi[:n]] - sp[0])) - sp[2] / 57.295779513082325).astype(np.float32)
+    assert np.allclose(az[:n], want_az, rtol=1e-5, atol=1e-4)
     s.close()
 
 
