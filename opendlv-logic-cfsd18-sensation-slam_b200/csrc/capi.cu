@@ -645,7 +645,9 @@ int slam_b200_batch_upload(slam_b200_ctx* c, int R, const double* pose_est3, con
                            const double* eo_z3, const double* el_z2) {
   if (!c || R < 1 || !pose_est3 || !lm_est2 || !eo_z3 || !el_z2) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  c->batch_ordering = true;
   int n = graph_build_structure(c);
+  c->batch_ordering = false;
   if (n < 0) return n;
   DeviceSystem& D = *c->sys;
   int rc = graph_alloc_values(c, R);

@@ -150,6 +150,7 @@ struct slam_b200_ctx {
   HostGraph g;
   DeviceSystem* sys = nullptr;
   bool assembly_only = false;  // prepare without the symbolic phase (assembly measurements)
+  bool batch_ordering = false; // structure is being built for a replica batch (fill-minimising ordering)
 
   void fail(const std::string& m) { err = m; }
 };

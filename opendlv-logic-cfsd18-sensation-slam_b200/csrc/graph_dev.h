@@ -77,6 +77,7 @@ struct DeviceSystem {
   bool assembled = false;
   bool have_snapshot = false;
   bool assembly_only = false;
+  bool batch_ordering = false;
   // one Gauss-Newton iteration (assemble + factor + solves + update) captured as a CUDA graph:
   // ~40 dependent small launches replayed with one host call per iteration
   cudaGraphExec_t iter_graph = nullptr;
