@@ -248,13 +248,22 @@ def bench_gn_e2e(pkg, torch, ctx, graph, steps, cold=True):
                 chi2=chi2, pe=pe, le=le)
 
 
+ASSOC_COPIES = 8          # replicas of map index + frame the timed trains rotate through (8 x 42.5 MB > 126 MB L2)
+
+
 def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
-    """Config 4: match-only association, observation batch split across ranks, map replicated."""
+    """Config 4: match-only association, observation batch split across ranks, map replicated.
+    A step = one frame (this rank's n observations against the 1M-cone map).  Three timings:
+      latency   one launch between two events, L2 flushed before (includes the ~5 us event/launch floor);
+      train     K frames back to back on one stream, one event pair around the train;
+      pipelined the same train with SLAM_B200_ALGO_GRID_PIPELINED (frames overlap on the device) = `value`.
+    The trains rotate through ASSOC_COPIES replicas of the map index and the frame (total > L2), so
+    every frame finds its inputs in HBM, not in L2."""
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)
-    ctx = pkg.Context(local, stream=stream.cuda_stream)
+    ctxs = [pkg.Context(local, stream=stream.cuda_stream) for _ in range(ASSOC_COPIES)]
+    ctx = ctxs[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ctx.map_append(field.map_x, field.map_y, field.map_type)
     lo = (n_total * rank) // world
     hi = (n_total * (rank + 1)) // world
     frame = np.asfortranarray(field.frame[:, lo:hi])
@@ -263,13 +272,17 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
     host_in = torch.from_numpy(np.ascontiguousarray(frame.T)).pin_memory()     # n x 4 == column-major 4 x n
     host_out = torch.empty(n, dtype=torch.int32).pin_memory()
     with torch.cuda.stream(stream):
-        d_in = host_in.to(dev, non_blocking=True)
-        d_out = torch.empty(n, dtype=torch.int32, device=dev)
+        d_ins = [host_in.to(dev, non_blocking=True) for _ in range(ASSOC_COPIES)]
+        d_outs = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(ASSOC_COPIES)]
     stream.synchronize()
-    t0 = time.perf_counter()
-    ctx.map_build_grid(THR)
-    ctx.sync()
-    grid_build_s = time.perf_counter() - t0
+    d_in, d_out = d_ins[0], d_outs[0]
+    grid_build_s = None
+    for c in ctxs:
+        c.map_append(field.map_x, field.map_y, field.map_type)
+        t0 = time.perf_counter()
+        c.map_build_grid(THR)
+        c.sync()
+        grid_build_s = time.perf_counter() - t0
     out = {}
     for algo_name, algo, steps in (("grid", pkg.capi.ALGO_GRID, args.steps), ("brute", pkg.capi.ALGO_BRUTE, min(args.steps, 3))):
         def body():
@@ -284,6 +297,25 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
         total = max_over_ranks(float(np.sum(ms)), world, dev)
         out[algo_name] = dict(ms_per_frame=total / steps, assoc_per_s=n_total * steps / (total * 1e-3),
                               matched=int((d_out >= 0).sum().item()))
+    ref_idx = d_out.clone()
+    # trains of K frames over the replicas
+    K = args.steps
+    order = [k % ASSOC_COPIES for k in range(K)]
+    trains = {}
+    for name, algo in (("train", pkg.capi.ALGO_GRID), ("pipelined", pkg.capi.ALGO_GRID_PIPELINED)):
+        launch = pkg.capi.Context.assoc_bulk_frames_dev([ctxs[q] for q in order], [d_ins[q].data_ptr() for q in order],
+                                                        [n] * K, np.tile(field.pose, (K, 1)), THR, pkg.capi.GATE_MAPPING, algo,
+                                                        [d_outs[q].data_ptr() for q in order])
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                launch()
+        stream.synchronize()
+        barrier(world)
+        ms = timed_steps(torch, stream, flush, 7, launch)     # 7 trains of K frames, L2 flushed before each
+        barrier(world)
+        med = max_over_ranks(float(np.median(ms)), world, dev)
+        same = all(bool(torch.equal(d_outs[q], ref_idx)) for q in range(min(ASSOC_COPIES, K)))
+        trains[name] = dict(ms_per_frame=med / K, assoc_per_s=n_total * K / (med * 1e-3), identical_to_single_launch=same)
     # end to end: pinned host frame in, host indices out, copies inside the timed region
     hin = host_in.numpy().T   # 4 x n view, column-major
     hout = host_out.numpy()
@@ -298,19 +330,32 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
     e2e_s = max_over_ranks(e2e_s * 1e3, world, dev) * 1e-3
     hbm, how = peaks()
     bytes_alg = 36.0 * n + 20.0 * M   # per frame, per rank (map replicated)
-    g = out["grid"]
+    g, tp = out["grid"], trains["pipelined"]
+
+    def roof(ms_per_frame):
+        return bytes_alg / (ms_per_frame * 1e-3) / 1e9
     res = dict(
-        workload=f"c4: {M} map cones, {n_total} observations/frame, match-only, mapping gate", value=g["assoc_per_s"],
-        unit="assoc/s", ms_per_frame=g["ms_per_frame"], matched_fraction=g["matched"] / max(n, 1),
+        workload=f"c4: {M} map cones, {n_total} observations/frame, match-only, mapping gate", value=tp["assoc_per_s"],
+        unit="assoc/s", ms_per_frame=tp["ms_per_frame"], matched_fraction=g["matched"] / max(n, 1),
+        timing=f"median of 7 trains of {K} frames launched back to back with SLAM_B200_ALGO_GRID_PIPELINED, one event pair "
+               f"per train, L2 flushed before each train; the train rotates through {ASSOC_COPIES} replicas of map index "
+               f"+ frame ({ASSOC_COPIES} x {(32.0 * M + 4.0 * M * 1.75 + 36.0 * n) / 1e6:.0f} MB > L2)",
+        single_launch={"ms_per_frame": g["ms_per_frame"], "assoc_per_s": g["assoc_per_s"],
+                       "note": "one launch between two events after an L2 flush (includes the event/launch floor, "
+                               "~5 us for an empty kernel)"},
+        train_unpipelined={"ms_per_frame": trains["train"]["ms_per_frame"], "assoc_per_s": trains["train"]["assoc_per_s"]},
+        identical_to_single_launch=bool(tp["identical_to_single_launch"] and trains["train"]["identical_to_single_launch"]),
         e2e={"value": n_total / e2e_s, "unit": "assoc/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 4 * n},
-        roofline={"bound": "hbm", "kernel": "assoc_bulk_grid_kernel", "achieved": bytes_alg / (g["ms_per_frame"] * 1e-3) / 1e9,
-                  "peak": hbm, "unit": "GB/s", "frac": bytes_alg / (g["ms_per_frame"] * 1e-3) / 1e9 / hbm,
+        roofline={"bound": "hbm", "kernel": "assoc_bulk_grid_kernel", "achieved": roof(tp["ms_per_frame"]),
+                  "peak": hbm, "unit": "GB/s", "frac": roof(tp["ms_per_frame"]) / hbm,
+                  "frac_single_launch": roof(g["ms_per_frame"]) / hbm, "frac_train_unpipelined": roof(trains["train"]["ms_per_frame"]) / hbm,
                   "traffic": None, "algorithmic_bytes_per_launch": bytes_alg, "peak_source": how},
         brute_force={"assoc_per_s": out["brute"]["assoc_per_s"], "ms_per_frame": out["brute"]["ms_per_frame"],
                      "pair_tests_per_s": float(n) * M / (out["brute"]["ms_per_frame"] * 1e-3) * world,
                      "note": "fp64-issue-bound variant (N*M pair tests), identical indices"},
         grid_build_ms=grid_build_s * 1e3)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     return res
 
 
@@ -537,7 +582,9 @@ def run_ours(args):
         line = {"metric": "cone assoc/s", "value": a["value"], "unit": "assoc/s", "n_gpus": world, "steps": args.steps,
                 "warmup": 3, "ms_per_step": a["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": a["workload"]},
-                "e2e": a["e2e"], "roofline": a["roofline"], "brute_force": a["brute_force"], "gpu_launches": args.steps}
+                "e2e": a["e2e"], "roofline": a["roofline"], "brute_force": a["brute_force"], "gpu_launches": args.steps,
+                "timing": a["timing"], "single_launch": a["single_launch"], "train_unpipelined": a["train_unpipelined"],
+                "identical_to_single_launch": a["identical_to_single_launch"]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -46,6 +46,11 @@ typedef struct slam_b200_ctx slam_b200_ctx;
 
 #define SLAM_B200_ALGO_BRUTE 0      /* every observation against every map cone, map tiles in smem */
 #define SLAM_B200_ALGO_GRID 1       /* uniform-grid buckets (cell >= thr), identical results        */
+#define SLAM_B200_ALGO_GRID_PIPELINED 2 /* ALGO_GRID, launched so that successive frames on the
+                                      * context's stream overlap (programmatic dependent launch,
+                                      * _dev entry points only): the caller gives every frame in
+                                      * flight its own idx buffer and reads results after a stream
+                                      * synchronisation, an event, or any ordinary launch/copy     */
 
 /* ------------------------------------------------------------------------------------------------
  * context
@@ -117,6 +122,13 @@ int slam_b200_assoc_bulk(slam_b200_ctx* ctx, const double* cones4xN, int n, cons
                          double threshold, int gate, int algo, int32_t* idx);
 int slam_b200_assoc_bulk_dev(slam_b200_ctx* ctx, const double* cones4xN_dev, int n, const double pose[3],
                              double threshold, int gate, int algo, int32_t* idx_dev);
+/* A train of independent frames (frame f: context ctxs[f] -- the same handle or replicas sharing
+ * one stream --, cones_dev[f] = 4 x n[f] doubles, poses[3f..3f+2], idx_dev[f]); one launch each,
+ * back to back.  With SLAM_B200_ALGO_GRID_PIPELINED the frames overlap on the device.  Returns
+ * n_frames. */
+int slam_b200_assoc_bulk_frames_dev(int n_frames, slam_b200_ctx* const* ctxs, const double* const* cones4xN_dev,
+                                    const int* n, const double* poses3, double threshold, int gate, int algo,
+                                    int32_t* const* idx_dev);
 /* (Re)builds the uniform-grid index of the device map for SLAM_B200_ALGO_GRID with cells of
  * `cell` metres (>= the threshold used later).  Called implicitly when missing or stale. */
 int slam_b200_map_build_grid(slam_b200_ctx* ctx, double cell);

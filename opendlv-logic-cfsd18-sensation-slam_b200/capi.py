@@ -18,7 +18,7 @@ c_ip = C.POINTER(C.c_int32)
 E_CUDA, E_ARG, E_STATE = -100, -101, -102
 ASSOC_MATCHED, ASSOC_NEW, ASSOC_NONE, ASSOC_SKIPPED = 0, 1, 2, 3
 GATE_MAPPING, GATE_LOCALIZER = 0, 1
-ALGO_BRUTE, ALGO_GRID = 0, 1
+ALGO_BRUTE, ALGO_GRID, ALGO_GRID_PIPELINED = 0, 1, 2
 
 _lib = None
 
@@ -202,6 +202,27 @@ class Context:
         pose = _f64(pose)
         self._ck(self.L.slam_b200_assoc_bulk_dev(self.h, C.c_void_p(cones_dev_ptr), int(n), _dp(pose), C.c_double(thr),
                                                  gate, algo, C.c_void_p(idx_dev_ptr)), "assoc_bulk_dev")
+
+    @staticmethod
+    def assoc_bulk_frames_dev(ctxs, cones_dev_ptrs, ns, poses, thr, gate, algo, idx_dev_ptrs):
+        """A train of independent frames, one launch each (see include/slam_b200.h); returns a callable
+        that relaunches the same train without rebuilding the argument arrays."""
+        F = len(ctxs)
+        L = ctxs[0].L
+        hs = (C.c_void_p * F)(*[c.h for c in ctxs])
+        cp = (C.c_void_p * F)(*[int(p) for p in cones_dev_ptrs])
+        ip = (C.c_void_p * F)(*[int(p) for p in idx_dev_ptrs])
+        na = (C.c_int * F)(*[int(v) for v in ns])
+        pa = _f64(np.asarray(poses, dtype=np.float64).reshape(F, 3))
+        thr_c = C.c_double(thr)
+
+        def launch():
+            rc = L.slam_b200_assoc_bulk_frames_dev(F, hs, cp, na, _dp(pa), thr_c, gate, algo, ip)
+            if rc < 0:
+                raise SlamB200Error(f"assoc_bulk_frames_dev failed ({rc}): {L.slam_b200_last_error(ctxs[0].h)}")
+            return rc
+        launch.keep = (hs, cp, ip, na, pa)
+        return launch
 
     # ---- graph -----------------------------------------------------------------------------------
     def graph_clear(self):

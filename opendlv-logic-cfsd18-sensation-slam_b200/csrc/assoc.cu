@@ -25,27 +25,42 @@ __device__ __forceinline__ double ref_deg2rad() { return 0.017453292522222; }   
 __device__ __forceinline__ double ref_rad2deg() { return 57.295779513082325; }  // slam.hpp:135
 __device__ __forceinline__ double ref_pi() { return (double)3.14159265f; }      // slam.hpp:136
 
-// slam.cpp:513-523
+// slam.cpp:513-523.  The angle leaves in degrees, as in the reference: the rad->deg->rad round trip
+// rescales it by RAD2DEG*DEG2RAD != 1 (slam.hpp:134-135) and that is part of the result.  sin and cos
+// of one argument come from one sincos() (one range reduction); `angle / fabs(angle)` is +-1 for
+// every finite non-zero angle and NaN otherwise.
 __device__ __forceinline__ void transform_cone_to_cog(double angle, double distance, double& angOut,
                                                       double& distOut) {
   const double lidarDistToCoG = 1.5;
-  double sign = angle / fabs(angle);
+  double sign = (angle != 0.0 && isfinite(angle)) ? copysign(1.0, angle) : __longlong_as_double(0x7ff8000000000000LL);
   angle = ref_pi() - fabs(angle * ref_deg2rad());
+  double sa, ca;
+  sincos(angle, &sa, &ca);
   double distanceNew = sqrt(lidarDistToCoG * lidarDistToCoG + distance * distance -
-                            2 * lidarDistToCoG * distance * cos(angle));
-  double angleNew = asin((sin(angle) * distance) / distanceNew) * ref_rad2deg();
+                            2 * lidarDistToCoG * distance * ca);
+  double angleNew = asin((sa * distance) / distanceNew) * ref_rad2deg();
   angOut = angleNew * sign;
   distOut = distanceNew;
 }
 
-// slam.cpp:637-654
+// slam.cpp:637-654.  zenith == 0 (every lidar cone of the 2-D pipeline): cos = 1 and sin = +-0
+// exactly, so the products below are unchanged bit for bit and one sincos is saved.
 __device__ __forceinline__ void spherical2cartesian(double az, double zen, double dist, double& x,
                                                     double& y, double& z) {
   double a, d;
   transform_cone_to_cog(az, dist, a, d);
-  x = d * cos(zen * ref_deg2rad()) * cos(a * ref_deg2rad());
-  y = d * cos(zen * ref_deg2rad()) * sin(a * ref_deg2rad());
-  z = d * sin(zen * ref_deg2rad());
+  double sa, ca, sz, cz;
+  sincos(a * ref_deg2rad(), &sa, &ca);
+  const double zr = zen * ref_deg2rad();
+  if (zr == 0.0) {
+    sz = zr;
+    cz = 1.0;
+  } else {
+    sincos(zr, &sz, &cz);
+  }
+  x = d * cz * ca;
+  y = d * cz * sa;
+  z = d * sz;
 }
 
 // slam.cpp:499-510 (pose trig hoisted by the callers: cp = cos(pose.theta), sp = sin(pose.theta))
@@ -450,39 +465,23 @@ __global__ void grid_fill_kernel(const double* __restrict__ x, const double* __r
 // bucketed: one thread per observation.  Cells are 2*h wide (h = threshold plus a 1e-9 relative
 // margin), so the disc of radius thr around the observation overlaps at most 2 x 2 cells = two
 // contiguous runs of the cell-sorted map.  Every cone is one aligned 32-byte record (one DRAM
-// sector); the records of a run are fetched four at a time before any is tested, so the dependent
-// chain per observation is: observation -> cell table -> records.  The answer is the minimum
+// sector); both runs are walked as one sequence whose records are fetched GRID_BATCH at a time before
+// any is tested, so the dependent chain per observation is: observation -> cell table -> records.  The answer is the minimum
 // ORIGINAL index over the gated candidates (= the reference's first fit, slam.cpp:575-607).
-template <int GATE>
-__device__ __forceinline__ void scan_run(const GridRec* __restrict__ rec, int s, int e, double gx, double gy,
-                                         double ot, int oti, double thr2x, int& best) {
-  for (int k = s; k < e; k += 4) {
-    double2 xy[4];
-    int4 ti[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      if (k + q < e) {
-        const double2* p = reinterpret_cast<const double2*>(rec + k + q);
-        xy[q] = __ldg(p);
-        ti[q] = __ldg(reinterpret_cast<const int4*>(p + 1));
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      if (k + q < e) {
-        if (type_gate<GATE>(ti[q].x, ot, oti) && ti[q].y < best &&
-            cone_distance2(xy[q].x, xy[q].y, gx, gy) < thr2x)
-          best = ti[q].y;
-      }
-    }
-  }
-}
+constexpr int GRID_BATCH = 8;  // records fetched before any is tested
 
-template <int GATE>
+//
+// EARLY (SLAM_B200_ALGO_GRID_PIPELINED): the kernel is latency-bound -- one wave of threads, each
+// a chain of three dependent memory round trips -- and leaves most of the machine idle, so frames
+// against the frozen map are launched with programmatic stream serialisation and every CTA
+// releases the next frame's launch at once (griddepcontrol.launch_dependents, no
+// griddepcontrol.wait: the frames are independent); successive frames overlap on one stream.
+template <int GATE, bool EARLY>
 __global__ void __launch_bounds__(BULK_THREADS)
 assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, double thr2x, GridParams gp,
                        const int* __restrict__ cell_start, const GridRec* __restrict__ rec,
                        int* __restrict__ idx) {
+  if (EARLY) asm volatile("griddepcontrol.launch_dependents;");
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double gx, gy, ot;
@@ -496,16 +495,35 @@ assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, dou
     if (fx1 >= 0.0 && fx0 <= (double)(gp.nx - 1) && fy1 >= 0.0 && fy0 <= (double)(gp.ny - 1)) {
       const int cx0 = (int)fmax(fx0, 0.0), cx1 = (int)fmin(fx1, (double)(gp.nx - 1));
       const int cy0 = (int)fmax(fy0, 0.0), cy1 = (int)fmin(fy1, (double)(gp.ny - 1));
-      const size_t b0 = (size_t)cy0 * gp.nx;
+      const size_t b0 = (size_t)cy0 * gp.nx, b1 = (size_t)cy1 * gp.nx;
+      // four independent cell-table reads (the second row repeats the first when the disc stays
+      // inside one row of cells; its run is then emptied)
       const int s0 = __ldg(cell_start + b0 + cx0), e0 = __ldg(cell_start + b0 + cx1 + 1);
-      int s1 = 0, e1 = 0;
-      if (cy1 > cy0) {
-        const size_t b1 = (size_t)cy1 * gp.nx;
-        s1 = __ldg(cell_start + b1 + cx0);
-        e1 = __ldg(cell_start + b1 + cx1 + 1);
+      const int s1 = __ldg(cell_start + b1 + cx0);
+      const int e1 = cy1 > cy0 ? __ldg(cell_start + b1 + cx1 + 1) : s1;
+      // the two runs are walked as one sequence, GRID_BATCH records in flight at a time
+      const int len0 = e0 - s0, len = len0 + (e1 - s1);
+      for (int k = 0; k < len; k += GRID_BATCH) {
+        double2 xy[GRID_BATCH];
+        int2 ti[GRID_BATCH];
+#pragma unroll
+        for (int q = 0; q < GRID_BATCH; q++) {
+          const int kk = k + q;
+          if (kk < len) {
+            const GridRec* r = rec + (kk < len0 ? s0 + kk : s1 + (kk - len0));
+            xy[q] = __ldg(reinterpret_cast<const double2*>(r));
+            ti[q] = __ldg(reinterpret_cast<const int2*>(r) + 2);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < GRID_BATCH; q++) {
+          if (k + q < len) {
+            if (type_gate<GATE>(ti[q].x, ot, oti) && ti[q].y < best &&
+                cone_distance2(xy[q].x, xy[q].y, gx, gy) < thr2x)
+              best = ti[q].y;
+          }
+        }
       }
-      scan_run<GATE>(rec, s0, e0, gx, gy, ot, oti, thr2x, best);
-      scan_run<GATE>(rec, s1, e1, gx, gy, ot, oti, thr2x, best);
     }
   }
   idx[i] = best == 0x7fffffff ? -1 : best;
@@ -758,7 +776,8 @@ int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, c
                              double thr, int gate, int algo, int32_t* idx_dev) {
   if (!c || !pose || n < 0 || (n > 0 && (!cones_dev || !idx_dev))) return SLAM_B200_E_ARG;
   if (gate != SLAM_B200_GATE_MAPPING && gate != SLAM_B200_GATE_LOCALIZER) return SLAM_B200_E_ARG;
-  if (algo != SLAM_B200_ALGO_BRUTE && algo != SLAM_B200_ALGO_GRID) return SLAM_B200_E_ARG;
+  if (algo != SLAM_B200_ALGO_BRUTE && algo != SLAM_B200_ALGO_GRID && algo != SLAM_B200_ALGO_GRID_PIPELINED)
+    return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n == 0) return 0;
   PoseTrig pt{pose[0], pose[1], std::cos(pose[2]), std::sin(pose[2])};
@@ -787,16 +806,46 @@ int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, c
     gp.ny = c->grid_ny;
     gp.inv = c->grid_inv;  // the exact values the index was built with
     gp.h = c->grid_h;
-    if (gate == SLAM_B200_GATE_MAPPING)
-      assoc_bulk_grid_kernel<SLAM_B200_GATE_MAPPING><<<blocks, BULK_THREADS, 0, c->stream>>>(
-          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_rec.p, idx_dev);
-    else
-      assoc_bulk_grid_kernel<SLAM_B200_GATE_LOCALIZER><<<blocks, BULK_THREADS, 0, c->stream>>>(
-          cones_dev, n, pt, thr2x, gp, c->grid_cell_start.p, c->grid_rec.p, idx_dev);
+    const int* cs = c->grid_cell_start.p;
+    const GridRec* rec = c->grid_rec.p;
+    if (algo == SLAM_B200_ALGO_GRID_PIPELINED) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(blocks);
+      cfg.blockDim = dim3(BULK_THREADS);
+      cfg.stream = c->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (gate == SLAM_B200_GATE_MAPPING)
+        SLAM_CUDA_TRY(c, cudaLaunchKernelEx(&cfg, assoc_bulk_grid_kernel<SLAM_B200_GATE_MAPPING, true>, cones_dev, n, pt,
+                                            thr2x, gp, cs, rec, (int*)idx_dev));
+      else
+        SLAM_CUDA_TRY(c, cudaLaunchKernelEx(&cfg, assoc_bulk_grid_kernel<SLAM_B200_GATE_LOCALIZER, true>, cones_dev, n, pt,
+                                            thr2x, gp, cs, rec, (int*)idx_dev));
+    } else if (gate == SLAM_B200_GATE_MAPPING) {
+      assoc_bulk_grid_kernel<SLAM_B200_GATE_MAPPING, false><<<blocks, BULK_THREADS, 0, c->stream>>>(
+          cones_dev, n, pt, thr2x, gp, cs, rec, idx_dev);
+    } else {
+      assoc_bulk_grid_kernel<SLAM_B200_GATE_LOCALIZER, false><<<blocks, BULK_THREADS, 0, c->stream>>>(
+          cones_dev, n, pt, thr2x, gp, cs, rec, idx_dev);
+    }
   }
   c->launches++;
   SLAM_CUDA_TRY(c, cudaGetLastError());
   return 0;
+}
+
+int slam_b200_assoc_bulk_frames_dev(int n_frames, slam_b200_ctx* const* ctxs, const double* const* cones_dev,
+                                    const int* n, const double* poses, double thr, int gate, int algo,
+                                    int32_t* const* idx_dev) {
+  if (n_frames < 0 || (n_frames > 0 && (!ctxs || !cones_dev || !n || !poses || !idx_dev))) return SLAM_B200_E_ARG;
+  for (int f = 0; f < n_frames; f++) {
+    int rc = slam_b200_assoc_bulk_dev(ctxs[f], cones_dev[f], n[f], poses + 3 * (size_t)f, thr, gate, algo, idx_dev[f]);
+    if (rc < 0) return rc;
+  }
+  return n_frames;
 }
 
 int slam_b200_assoc_bulk(slam_b200_ctx* c, const double* cones, int n, const double pose[3], double thr,

@@ -197,3 +197,38 @@ def test_bulk_full_size_c4_grid_equals_brute(ctx, orc, synth, pkg):
         o = orc.assoc_match_only(sample, f.pose, THR, gate, f.map_x, f.map_y, f.map_type)
         assert np.array_equal(grid[:1500], o["idx"])
     assert (grid >= 0).mean() > 0.85
+
+
+@pytest.mark.parametrize("gate", [0, 1])
+def test_bulk_pipelined_train_equals_single_frames(ctx, orc, synth, pkg, gate):
+    """SLAM_B200_ALGO_GRID_PIPELINED: a train of independent frames (different observation sets and
+    poses) overlapping on one stream gives, frame by frame, what ALGO_GRID and the oracle give."""
+    import torch
+    f = synth.cone_field(n_map=200_000, n_obs=24_000, seed=9)
+    ctx.map_clear()
+    ctx.map_append(f.map_x, f.map_y, f.map_type)
+    ctx.map_build_grid(THR)
+    F, n = 12, 2000
+    dev = torch.device("cuda", 0)
+    poses = np.tile(f.pose, (F, 1))
+    poses[:, 0] += np.arange(F) * 0.37          # shifted poses: every frame has its own answer
+    poses[:, 2] += np.arange(F) * 0.01
+    frames = [np.asfortranarray(f.frame[:, k * n:(k + 1) * n]) for k in range(F)]
+    d_in = [torch.from_numpy(np.ascontiguousarray(fr.T)).to(dev) for fr in frames]
+    d_out = [torch.full((n,), -7, dtype=torch.int32, device=dev) for _ in range(F)]
+    torch.cuda.synchronize()
+    launch = pkg.capi.Context.assoc_bulk_frames_dev([ctx] * F, [t.data_ptr() for t in d_in], [n] * F, poses, THR, gate,
+                                                    pkg.capi.ALGO_GRID_PIPELINED, [t.data_ptr() for t in d_out])
+    for _ in range(3):
+        assert launch() == F
+    ctx.sync()
+    matched = 0
+    for k in range(F):
+        got = d_out[k].cpu().numpy()
+        single = ctx.assoc_bulk(frames[k], poses[k], THR, gate, pkg.capi.ALGO_GRID).copy()
+        assert np.array_equal(got, single), f"frame {k}"
+        if k % 4 == 0:
+            o = orc.assoc_match_only(frames[k], poses[k], THR, gate, f.map_x, f.map_y, f.map_type)
+            assert np.array_equal(got, o["idx"]), f"frame {k} vs oracle"
+        matched += int((got >= 0).sum())
+    assert matched > 1000
