@@ -72,11 +72,19 @@ constexpr int ASM_WARPS = ASM_THREADS / 32;
 // minBlocksPerSM = 6 caps the kernel at 80 registers: the register-hungry part (3x3 algebra of the
 // pose-pose edges) runs once per pose and may spill; the per-edge loop needs the occupancy to hide
 // the latency of the landmark gather
-template <bool CHI2_ONLY>
+//
+// COALESCE: the blocks a warp step produces are contiguous in V (slots are handed out in edge
+// order: 32 edges -> 192 consecutive doubles; 32 poses -> 96 + 288), but a lane holds one whole
+// block, so direct stores are strided (every store instruction touches 12-18 lines).  The blocks
+// are therefore transposed through shared memory and written with unit-stride stores whenever the
+// step's slots are in fact contiguous (warp-uniform test; anything else -- duplicates, inactive or
+// fixed vertices, transposed storage is fine -- falls back to the direct stores).
+template <bool CHI2_ONLY, bool COALESCE>
 __global__ void __launch_bounds__(ASM_THREADS, 6)
 assemble_pose_kernel(AsmArgs a, int p0, int p1) {
   __shared__ double s_pose[ASM_WARPS][4][32];   // x, y, sin, cos of the warp's poses
   __shared__ double s_acc[ASM_WARPS][9][32];    // h00 h01 h02 h11 h12 h22 b0 b1 b2 per pose
+  __shared__ double s_o[COALESCE ? ASM_WARPS : 1][COALESCE ? 288 : 1];  // one step's blocks, block-major
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r = blockIdx.y;
   const double* est = a.est + (size_t)r * a.estStride;
@@ -115,6 +123,7 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
       int fl = 0;
       double o[6];
       int slot = 0;
+      bool wr = false;  // this lane stores o[] at V + slot
       if (valid) {
         fl = a.el_flags[e];
         pl = a.el_pose[e] - pw0;
@@ -153,12 +162,35 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
 #pragma unroll
               for (int k = 0; k < 6; k++) o[k] = B[k];
             }
-            if (fl & EF_FIRST) {
+            if (!COALESCE && (fl & EF_FIRST)) {
               double* hv = V + slot;
 #pragma unroll
               for (int k = 0; k < 6; k++) hv[k] = o[k];
             }
+            wr = (fl & EF_FIRST) != 0;
           }
+        }
+      }
+      if (COALESCE && !CHI2_ONLY) {
+        const int nvalid = min(32, e_end - base);
+        const int slot0 = __shfl_sync(0xffffffffu, slot, 0);
+        // every valid lane stores a first-of-its-pair block and the slots are consecutive
+        const bool contig = __all_sync(0xffffffffu, !valid || (wr && slot == slot0 + 6 * lane));
+        if (contig) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) s_o[wid][6 * lane + k] = o[k];
+          __syncwarp();
+          double* hv = V + slot0;
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const int q = j * 32 + lane;
+            if (q < 6 * nvalid) hv[q] = s_o[wid][q];
+          }
+          __syncwarp();
+        } else if (wr) {
+          double* hv = V + slot;
+#pragma unroll
+          for (int k = 0; k < 6; k++) hv[k] = o[k];
         }
       }
       if (!CHI2_ONLY) {
@@ -196,6 +228,7 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
       }
     }
   }
+  double fb[3] = {0, 0, 0}, fh[6] = {0, 0, 0, 0, 0, 0};  // finished pose rhs / block (COALESCE)
   if (p < p1) {
     double h00 = s_acc[wid][0][lane], h01 = s_acc[wid][1][lane], h02 = s_acc[wid][2][lane];
     double h11 = s_acc[wid][3][lane], h12 = s_acc[wid][4][lane], h22 = s_acc[wid][5][lane];
@@ -294,13 +327,47 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
           }
       }
     }
-    if (!CHI2_ONLY && free) {
+    if (!CHI2_ONLY && !COALESCE && free) {
       double* bp = V + 6 * (size_t)L + 3 * (size_t)p;
       bp[0] = b0; bp[1] = b1; bp[2] = b2;
       double* hp = V + 6 * (size_t)L + 3 * (size_t)P + 9 * (size_t)p;
       hp[0] = h00; hp[1] = h01; hp[2] = h02;
       hp[3] = h01; hp[4] = h11; hp[5] = h12;
       hp[6] = h02; hp[7] = h12; hp[8] = h22;
+    }
+    if (COALESCE) { fb[0] = b0; fb[1] = b1; fb[2] = b2; fh[0] = h00; fh[1] = h01; fh[2] = h02; fh[3] = h11; fh[4] = h12; fh[5] = h22; }
+  }
+  if (COALESCE && !CHI2_ONLY && pw0 < p1) {  // warp-uniform
+    const int np = min(32, p1 - pw0);
+    const bool allfree = __all_sync(0xffffffffu, p >= p1 || free);
+    if (allfree) {
+      double* bp = V + 6 * (size_t)L + 3 * (size_t)pw0;
+      double* hp = V + 6 * (size_t)L + 3 * (size_t)P + 9 * (size_t)pw0;
+      s_o[wid][3 * lane] = fb[0]; s_o[wid][3 * lane + 1] = fb[1]; s_o[wid][3 * lane + 2] = fb[2];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int q = j * 32 + lane;
+        if (q < 3 * np) bp[q] = s_o[wid][q];
+      }
+      __syncwarp();
+      double* so = &s_o[wid][9 * lane];
+      so[0] = fh[0]; so[1] = fh[1]; so[2] = fh[2];
+      so[3] = fh[1]; so[4] = fh[3]; so[5] = fh[4];
+      so[6] = fh[2]; so[7] = fh[4]; so[8] = fh[5];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const int q = j * 32 + lane;
+        if (q < 9 * np) hp[q] = s_o[wid][q];
+      }
+    } else if (p < p1 && free) {
+      double* bp = V + 6 * (size_t)L + 3 * (size_t)p;
+      bp[0] = fb[0]; bp[1] = fb[1]; bp[2] = fb[2];
+      double* hp = V + 6 * (size_t)L + 3 * (size_t)P + 9 * (size_t)p;
+      hp[0] = fh[0]; hp[1] = fh[1]; hp[2] = fh[2];
+      hp[3] = fh[1]; hp[4] = fh[3]; hp[5] = fh[4];
+      hp[6] = fh[2]; hp[7] = fh[4]; hp[8] = fh[5];
     }
   }
   // chi2: fixed-order block reduction -> one partial per block
@@ -322,7 +389,7 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
 // exchanged through memory.
 constexpr int LM_PER_BLOCK = ASM_THREADS / 32;
 
-template <bool CHI2_ONLY>
+template <bool CHI2_ONLY, bool UNROLL2>
 __global__ void __launch_bounds__(ASM_THREADS)
 assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_first, int l_end) {
   const int lane = threadIdx.x & 31;
@@ -350,23 +417,45 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
     }
     const double* trig = a.trig + (size_t)r * 2 * P;
     const double* mlm = meas + 2 * (size_t)El + 3 * (size_t)a.Eo;  // measurements in landmark order
-    for (int q = q0 + lane; q < q1; q += 32) {
-      // everything indexed by q is laid out in landmark order: coalesced across the lanes
-      const int p = a.lmo_pose[q];
-      if (p < 0) continue;  // inactive edge
-      const double s = trig[p], c = trig[P + p];
-      const double dx = lx - est[p], dy = ly - est[P + p];
-      const double ex = c * dx + s * dy - mlm[q];
-      const double ey = -s * dx + c * dy - mlm[El + q];
-      const double i00 = a.lmo_info[q], i01 = a.lmo_info[El + q], i11 = a.lmo_info[2 * (size_t)El + q];
-      // A = Jl^T Omega, Jl = [[c, s], [-s, c]]
-      const double a00 = c * i00 - s * i01, a01 = c * i01 - s * i11;
-      const double a10 = s * i00 + c * i01, a11 = s * i01 + c * i11;
-      b0 -= a00 * ex + a01 * ey;
-      b1 -= a10 * ex + a11 * ey;
-      h00 += a00 * c - a01 * s;
-      h01 += a00 * s + a01 * c;
-      h11 += a10 * s + a11 * c;
+    // everything indexed by q is laid out in landmark order: coalesced across the lanes.  Two
+    // 32-edge steps are loaded together (index -> gathers -> payload for both) before either is
+    // evaluated, so the two dependent round trips of a step overlap with those of the next.
+    const double* io0 = a.lmo_info;
+    const double* io1 = a.lmo_info + El;
+    const double* io2 = a.lmo_info + 2 * (size_t)El;
+    const double* m0 = mlm;
+    const double* m1 = mlm + El;
+    const double* ex_ = est;
+    const double* ey_ = est + P;
+    const double* tc_ = trig + P;
+    for (int qb = q0 + lane; qb < q1; qb += (UNROLL2 ? 64 : 32)) {
+      const int qa = qb, qc = qb + 32;
+      const bool va = true, vc = UNROLL2 && qc < q1;
+      const int pa = __ldg(a.lmo_pose + qa);
+      const int pc = vc ? __ldg(a.lmo_pose + qc) : -1;
+      const bool aa = va && pa >= 0, ac = pc >= 0;  // p < 0: inactive edge
+      double sa = 0, ca = 0, xa = 0, ya = 0, sc = 0, cc = 0, xc = 0, yc = 0;
+      if (aa) { sa = trig[pa]; ca = tc_[pa]; xa = ex_[pa]; ya = ey_[pa]; }
+      if (ac) { sc = trig[pc]; cc = tc_[pc]; xc = ex_[pc]; yc = ey_[pc]; }
+      double za0 = 0, za1 = 0, ia0 = 0, ia1 = 0, ia2 = 0, zc0 = 0, zc1 = 0, ic0 = 0, ic1 = 0, ic2 = 0;
+      if (aa) { za0 = __ldg(m0 + qa); za1 = __ldg(m1 + qa); ia0 = __ldg(io0 + qa); ia1 = __ldg(io1 + qa); ia2 = __ldg(io2 + qa); }
+      if (ac) { zc0 = __ldg(m0 + qc); zc1 = __ldg(m1 + qc); ic0 = __ldg(io0 + qc); ic1 = __ldg(io1 + qc); ic2 = __ldg(io2 + qc); }
+      auto accumulate = [&](double s, double c, double px, double py, double z0, double z1, double i00, double i01,
+                            double i11) {
+        const double dx = lx - px, dy = ly - py;
+        const double ex = c * dx + s * dy - z0;
+        const double ey = -s * dx + c * dy - z1;
+        // A = Jl^T Omega, Jl = [[c, s], [-s, c]]
+        const double a00 = c * i00 - s * i01, a01 = c * i01 - s * i11;
+        const double a10 = s * i00 + c * i01, a11 = s * i01 + c * i11;
+        b0 -= a00 * ex + a01 * ey;
+        b1 -= a10 * ex + a11 * ey;
+        h00 += a00 * c - a01 * s;
+        h01 += a00 * s + a01 * c;
+        h11 += a10 * s + a11 * c;
+      };
+      if (aa) accumulate(sa, ca, xa, ya, za0, za1, ia0, ia1, ia2);
+      if (ac) accumulate(sc, cc, xc, yc, zc0, zc1, ic0, ic1, ic2);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -480,8 +569,8 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
   int nblk = (np + ASM_THREADS - 1) / ASM_THREADS;
   if (nblk > 0) {
     dim3 grid(nblk, D.R);
-    if (chi2_only) assemble_pose_kernel<true><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
-    else assemble_pose_kernel<false><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
+    if (chi2_only) assemble_pose_kernel<true, false><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
+    else assemble_pose_kernel<false, true><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
     c->launches++;
   }
   // landmarks touched by this pose range (a shard of a large graph sees a small, contiguous-ish part
@@ -501,8 +590,12 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
     SLAM_CUDA_TRY(c, cudaMemsetAsync(D.V.p, 0, sizeof(double) * 6 * (size_t)D.L, c->stream));
   }
   dim3 gl(std::max(1, (l_end - l_first + LM_PER_BLOCK - 1) / LM_PER_BLOCK), D.R);
-  if (chi2_only) assemble_landmark_kernel<true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
-  else assemble_landmark_kernel<false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
+  // a landmark with more than one 32-edge step of observers (long tracks, many laps) is worth the
+  // two-steps-in-flight loop; with 20-30 observers per landmark the plain loop is faster (measured)
+  const bool unroll2 = D.El > 32L * std::max(D.L, 1);
+  if (chi2_only) assemble_landmark_kernel<true, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
+  else if (unroll2) assemble_landmark_kernel<false, true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
+  else assemble_landmark_kernel<false, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
   c->launches++;
   SLAM_CUDA_TRY(c, cudaGetLastError());
   if (!chi2_only) D.assembled = true;

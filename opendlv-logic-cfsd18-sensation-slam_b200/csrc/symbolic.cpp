@@ -346,6 +346,122 @@ static void min_degree_eliminate(std::vector<std::vector<int>>& adj, const int* 
   }
 }
 
+// The same elimination on a dense bit-matrix adjacency (one row of ceil(nb/64) words per vertex),
+// for graphs of at most a few thousand vertices -- every nested-dissection region with its halo and
+// the separator graph are that small.  Merging the pivot's neighbourhood into a neighbour's row is a
+// word-wise OR, and only the bits that are new cost anything beyond that, so an elimination is
+// O(|N| * nb/64) instead of O(|N|^2 log) sorted-vector searches.  Same buckets, same visiting order
+// (ascending neighbours) => the very same elimination order as min_degree_eliminate.
+static void min_degree_eliminate_dense(std::vector<std::vector<int>>& adj, const int* dim, const std::vector<int>& rank,
+                                       int max_rank, std::vector<int>& order) {
+  const int nb = (int)adj.size();
+  const int W = (nb + 63) >> 6;
+  std::vector<uint64_t> bits((size_t)nb * W, 0);
+  int nrank = 1;
+  for (int v = 0; v < nb; v++)
+    if (rank[v] <= max_rank) nrank = std::max(nrank, rank[v] + 1);
+  std::vector<long> wdeg(nb, 0);
+  std::vector<std::vector<int>> head(nrank);
+  std::vector<int> nxt(nb, -1), prv(nb, -1), remaining(nrank, 0), mindeg(nrank, 0);
+  std::vector<char> gone(nb, 0);
+  auto in_play = [&](int v) { return rank[v] <= max_rank; };
+  auto bucket_insert = [&](int v) {
+    std::vector<int>& h = head[rank[v]];
+    long d = wdeg[v];
+    if ((long)h.size() <= d) h.resize(d + 1 + (d >> 2), -1);
+    nxt[v] = h[d];
+    prv[v] = -1;
+    if (h[d] >= 0) prv[h[d]] = v;
+    h[d] = v;
+    if (d < mindeg[rank[v]]) mindeg[rank[v]] = (int)d;
+  };
+  auto bucket_remove = [&](int v) {
+    std::vector<int>& h = head[rank[v]];
+    if (prv[v] >= 0) nxt[prv[v]] = nxt[v];
+    else h[wdeg[v]] = nxt[v];
+    if (nxt[v] >= 0) prv[nxt[v]] = prv[v];
+  };
+  for (int v = 0; v < nb; v++) {
+    uint64_t* row = bits.data() + (size_t)v * W;
+    for (int u : adj[v]) {
+      wdeg[v] += dim[u];
+      row[u >> 6] |= 1ull << (u & 63);
+    }
+    if (in_play(v)) remaining[rank[v]]++;
+  }
+  for (int v = nb - 1; v >= 0; v--)
+    if (in_play(v)) bucket_insert(v);  // ties resolved towards the lower index
+  std::vector<int> N;
+  std::vector<uint64_t> Nb(W);
+  for (int rk = 0; rk < nrank; rk++) {
+    while (remaining[rk] > 0) {
+      std::vector<int>& h = head[rk];
+      int d = mindeg[rk];
+      while (d < (int)h.size() && h[d] < 0) d++;
+      mindeg[rk] = d;
+      const int v = h[d];
+      bucket_remove(v);
+      remaining[rk]--;
+      order.push_back(v);
+      gone[v] = 1;
+      uint64_t* rv = bits.data() + (size_t)v * W;
+      N.clear();
+      for (int k = 0; k < W; k++) {
+        uint64_t w = Nb[k] = rv[k];
+        rv[k] = 0;
+        while (w) {
+          N.push_back((k << 6) + __builtin_ctzll(w));
+          w &= w - 1;
+        }
+      }
+      const int vk = v >> 6;
+      const uint64_t vbit = 1ull << (v & 63);
+      for (int u : N) {
+        const bool play = in_play(u);
+        if (play) bucket_remove(u);
+        uint64_t* ru = bits.data() + (size_t)u * W;
+        long w = wdeg[u];
+        if (ru[vk] & vbit) { ru[vk] &= ~vbit; w -= dim[v]; }
+        const int uk = u >> 6;
+        const uint64_t ubit = 1ull << (u & 63);
+        for (int k = 0; k < W; k++) {
+          uint64_t nw = Nb[k] & ~ru[k];
+          if (k == uk) nw &= ~ubit;
+          if (!nw) continue;
+          ru[k] |= nw;
+          while (nw) {
+            w += dim[(k << 6) + __builtin_ctzll(nw)];
+            nw &= nw - 1;
+          }
+        }
+        wdeg[u] = w;
+        if (play) bucket_insert(u);
+      }
+    }
+  }
+  // hand the elimination graph of the remaining vertices back as sorted lists
+  for (int v = 0; v < nb; v++) {
+    adj[v].clear();
+    if (gone[v]) { adj[v].shrink_to_fit(); continue; }
+    const uint64_t* row = bits.data() + (size_t)v * W;
+    for (int k = 0; k < W; k++) {
+      uint64_t w = row[k];
+      while (w) {
+        adj[v].push_back((k << 6) + __builtin_ctzll(w));
+        w &= w - 1;
+      }
+    }
+  }
+}
+
+constexpr int MD_DENSE_LIMIT = 4096;  // vertices; a 4096 x 4096 bit matrix is 2 MB
+
+static void min_degree_dispatch(std::vector<std::vector<int>>& adj, const int* dim, const std::vector<int>& rank,
+                                int max_rank, std::vector<int>& order) {
+  if ((int)adj.size() <= MD_DENSE_LIMIT && !getenv("SLAM_B200_MD_SPARSE")) min_degree_eliminate_dense(adj, dim, rank, max_rank, order);
+  else min_degree_eliminate(adj, dim, rank, max_rank, order);
+}
+
 // Constrained minimum degree.  The interiors of the nested-dissection regions (rank 0) do not touch
 // each other -- only the separators around them -- so every region is ordered independently on its
 // own copy of (interior + halo) by a pool of host threads; the fill each region leaves among its
@@ -362,28 +478,22 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
   auto do_region = [&](int ri) {
     auto tr0 = std::chrono::steady_clock::now();
     const std::vector<int>& R = regions[ri];
-    // local numbering: interior first, then halo
+    // local numbering: interior first (region order), then halo (ascending global id); the
+    // global -> local map is a per-thread scratch array that is reset entry by entry afterwards
+    static thread_local std::vector<int> g2l;
+    if ((int)g2l.size() < nb) g2l.assign(nb, -1);
     std::vector<int> loc2g(R);
-    std::vector<std::pair<int, int>> g2l;  // sorted (global, local)
-    g2l.reserve(R.size() * 2);
-    for (size_t k = 0; k < R.size(); k++) g2l.push_back({R[k], (int)k});
-    std::sort(g2l.begin(), g2l.end());
-    auto find_local = [&](int gv) -> int {
-      auto it = std::lower_bound(g2l.begin(), g2l.end(), std::make_pair(gv, -1));
-      return (it != g2l.end() && it->first == gv) ? it->second : -1;
-    };
     const int nint = (int)R.size();
-    // discover the halo
+    for (int k = 0; k < nint; k++) g2l[R[k]] = k;
+    auto find_local = [&](int gv) -> int { return g2l[gv]; };
     std::vector<int> halo;
     for (int v : R)
       for (int p = xadj[v]; p < xadj[v + 1]; p++) {
         int u = adjv[p];
-        if (find_local(u) < 0) halo.push_back(u);
+        if (g2l[u] == -1) { g2l[u] = -2; halo.push_back(u); }
       }
     std::sort(halo.begin(), halo.end());
-    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
-    for (int hv : halo) { g2l.push_back({hv, (int)loc2g.size()}); loc2g.push_back(hv); }
-    std::sort(g2l.begin(), g2l.end());
+    for (int hv : halo) { g2l[hv] = (int)loc2g.size(); loc2g.push_back(hv); }
     const int nloc = (int)loc2g.size();
     std::vector<std::vector<int>> ladj(nloc);
     std::vector<int> ldim(nloc), lrank(nloc);
@@ -402,12 +512,13 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
     }
     std::vector<int> lord;
     lord.reserve(nint);
-    min_degree_eliminate(ladj, ldim.data(), lrank, 0, lord);
+    min_degree_dispatch(ladj, ldim.data(), lrank, 0, lord);
     reg_order[ri].reserve(nint);
     for (int k : lord) reg_order[ri].push_back(loc2g[k]);
     for (int k = nint; k < nloc; k++)
       for (int u : ladj[k])
         if (u > k) reg_fill[ri].push_back({loc2g[k], loc2g[u]});
+    for (int gv : loc2g) g2l[gv] = -1;
     if (getenv("SLAM_B200_SYM_DEBUG"))
       fprintf(stderr, "[symbolic] region %d: %d interior, %d halo, start %.4f dur %.4f s\n", ri, nint, nloc - nint, std::chrono::duration<double>(tr0 - tdbg0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count());
   };
@@ -441,16 +552,29 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
     std::sort(adj[v].begin(), adj[v].end());
     adj[v].erase(std::unique(adj[v].begin(), adj[v].end()), adj[v].end());
   }
-  // remaining vertices by rank; already-eliminated ones get a rank beyond the limit
-  std::vector<int> rank2(rank);
+  // the separator graph on its own compact numbering (ascending global id, so ties break the same
+  // way as on the full numbering)
   int maxr = 0;
   for (int v = 0; v < nb; v++) maxr = std::max(maxr, rank[v]);
+  std::vector<int> loc(nb, -1), glob;
   for (int v = 0; v < nb; v++)
-    if (gone[v]) rank2[v] = maxr + 1;
+    if (!gone[v]) { loc[v] = (int)glob.size(); glob.push_back(v); }
+  const int ns = (int)glob.size();
+  std::vector<std::vector<int>> sadj(ns);
+  std::vector<int> sdim(ns), srank(ns);
+  for (int k = 0; k < ns; k++) {
+    const int v = glob[k];
+    sdim[k] = dim[v];
+    srank[k] = rank[v];
+    sadj[k].reserve(adj[v].size());
+    for (int u : adj[v]) sadj[k].push_back(loc[u]);  // ascending: loc is monotone
+  }
   if (getenv("SLAM_B200_SYM_DEBUG"))
     fprintf(stderr, "[symbolic] regions+merge %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tdbg0).count());
   std::vector<int> rest;
-  min_degree_eliminate(adj, dim, rank2, maxr, rest);
+  rest.reserve(ns);
+  min_degree_dispatch(sadj, sdim.data(), srank, maxr, rest);
+  for (int& k : rest) k = glob[k];
   if (getenv("SLAM_B200_SYM_DEBUG"))
     fprintf(stderr, "[symbolic] +separators %.4f s (%zu vertices)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tdbg0).count(), rest.size());
   order.insert(order.end(), rest.begin(), rest.end());
@@ -518,6 +642,13 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   std::vector<int> epos(nb);
   for (int k = 0; k < nb; k++) epos[order[k]] = k;
   // ---- stage 3: block elimination tree + column structures, postorder, supernodes ----
+  auto tdb = std::chrono::steady_clock::now();
+  auto dbg = [&](const char* what) {
+    if (!getenv("SLAM_B200_SYM_DEBUG")) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[symbolic] stage3 %-24s %.4f s\n", what, std::chrono::duration<double>(now - tdb).count());
+    tdb = now;
+  };
   std::vector<std::vector<int>> cstruct(nb);  // struct of column k: positions > k, sorted
   std::vector<int> eparent(nb, -1);
   {
@@ -575,6 +706,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     cstruct.swap(cstruct2);
     for (int k = 0; k < nb; k++) epos[order[k]] = k;
   }
+  dbg("cstruct+postorder");
   // supernodes: fundamental (parent[k] == k+1 and struct(k) == {k+1} U struct(k+1)), then relaxed
   // amalgamation of a last child into its parent when the padding it introduces is small
   std::vector<int> snode_first;  // first column of every supernode
@@ -622,6 +754,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
       }
     }
   }
+  dbg("supernodes");
   // ---- pass 1: update sets of every front and the assembly tree ----
   std::vector<std::vector<int>> U(nf);       // update blocks of every node (sorted by ppos)
   std::vector<std::vector<int>> akids(nf);   // assembly-tree children
@@ -648,6 +781,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
       }
     }
   }
+  dbg("pass1 update sets");
   // ---- pass 2: levels of the assembly tree, level-major renumbering ----
   std::vector<int> level(nf, 0);
   for (int f : post)
@@ -701,6 +835,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     for (int g = 0; g < nf; g++)
       if (S.parent[g] >= 0) S.children[cur[S.parent[g]]++] = g;
   }
+  dbg("pass2 levels/positions");
   // update rows (scalar), sorted by final position
   S.rows_ptr.assign(nf + 1, 0);
   for (int g = 0; g < nf; g++) {
@@ -737,6 +872,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     }
     fill_rowpos(p, false);
   }
+  dbg("rows+rel");
   // storage offsets, statistics
   S.lptr.assign(nf + 1, 0);
   S.uptr.assign(nf + 1, 0);
@@ -754,6 +890,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     }
     S.max_front = std::max<int>(S.max_front, (int)fs);
   }
+  dbg("offsets/stats");
   // ---- assembly entries: every H block lands in the front of its earlier-eliminated vertex ----
   std::vector<std::vector<AsmEntry>> per(nf);
   for (int b = 0; b < nb; b++) {
@@ -791,6 +928,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
       fill_rowpos(g, false);
     }
   }
+  dbg("asm entries");
   S.asm_ptr.assign(nf + 1, 0);
   for (int g = 0; g < nf; g++) S.asm_ptr[g + 1] = S.asm_ptr[g] + (int)per[g].size();
   S.asm_entries.reserve(S.asm_ptr[nf]);

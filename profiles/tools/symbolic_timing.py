@@ -18,6 +18,7 @@ capi = pkg.capi
 d = capi._i32(dims); a = capi._i32(pa); b = capi._i32(pb)
 for rep in range(3):
     h = C.c_void_p(L.slam_b200_symbolic_create(len(d), capi._ip(d), len(a), capi._ip(a), capi._ip(b), 1024))
-    print("total %.4f s  nd %.4f  md %.4f" % (L.slam_b200_symbolic_stat(h, 3), L.slam_b200_symbolic_stat(h, 5),
-                                              L.slam_b200_symbolic_stat(h, 6)))
+    print("total %.4f s  nd %.4f  md %.4f   nnz(L) %d  flops %.4g  max front %d" % (
+        L.slam_b200_symbolic_stat(h, 3), L.slam_b200_symbolic_stat(h, 5), L.slam_b200_symbolic_stat(h, 6),
+        L.slam_b200_symbolic_stat(h, 0), L.slam_b200_symbolic_stat(h, 1), L.slam_b200_symbolic_stat(h, 2)))
     L.slam_b200_symbolic_destroy(h)
