@@ -238,12 +238,36 @@ int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids,
     if (!g.id2v.emplace(pose_ids[p], p << 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
   for (int l = 0; l < n_landmarks; l++)
     if (!g.id2v.emplace(lm_ids[l], (l << 1) | 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+  // ids of a bulk load are looked up ~2 (E_o + E_l) times: when they span a small range (the
+  // reference numbers landmarks from 0 and poses from 1000, slam.cpp:434,527) a flat table replaces
+  // the hash map for the edge loops below
+  std::vector<int> flat;
+  int id_lo = 0;
+  {
+    int lo = INT32_MAX, hi = INT32_MIN;
+    for (int p = 0; p < n_poses; p++) { lo = std::min(lo, pose_ids[p]); hi = std::max(hi, pose_ids[p]); }
+    for (int l = 0; l < n_landmarks; l++) { lo = std::min(lo, lm_ids[l]); hi = std::max(hi, lm_ids[l]); }
+    const long span = (n_poses + n_landmarks) ? (long)hi - lo + 1 : 0;
+    if (span > 0 && span <= 8L * (n_poses + n_landmarks) + 4096) {
+      flat.assign((size_t)span, -1);
+      id_lo = lo;
+      for (int p = 0; p < n_poses; p++) flat[pose_ids[p] - lo] = p << 1;
+      for (int l = 0; l < n_landmarks; l++) flat[lm_ids[l] - lo] = (l << 1) | 1;
+    }
+  }
+  auto find = [&](int id, bool want_lm, int* local) -> int {
+    if (flat.empty()) return lookup(c, id, want_lm, local);
+    const long k = (long)id - id_lo;
+    if (k < 0 || k >= (long)flat.size() || flat[k] < 0 || ((flat[k] & 1) != 0) != want_lm) return SLAM_B200_E_ARG;
+    *local = flat[k] >> 1;
+    return 0;
+  };
   g.eo_i.resize(n_eo); g.eo_j.resize(n_eo);
   g.eo_z.assign(eo_z3, eo_z3 + 3 * (size_t)n_eo);
   g.eo_info.resize(6 * (size_t)n_eo);
   for (int e = 0; e < n_eo; e++) {
     int i, j;
-    if (lookup(c, eo_from[e], false, &i) || lookup(c, eo_to[e], false, &j) || i == j) {
+    if (find(eo_from[e], false, &i) || find(eo_to[e], false, &j) || i == j) {
       c->fail("EdgeSE2: unknown or identical pose ids");
       return SLAM_B200_E_ARG;
     }
@@ -257,7 +281,7 @@ int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids,
   g.el_info.resize(3 * (size_t)n_el);
   for (int e = 0; e < n_el; e++) {
     int p, l;
-    if (lookup(c, el_pose[e], false, &p) || lookup(c, el_lm[e], true, &l)) {
+    if (find(el_pose[e], false, &p) || find(el_lm[e], true, &l)) {
       c->fail("EdgeSE2PointXY: unknown pose or landmark id");
       return SLAM_B200_E_ARG;
     }

@@ -79,9 +79,10 @@ struct Nd {
         roots.push_back((int)nodes.size() - 1);
         continue;
       }
-      // pseudo-peripheral start: two sweeps
-      int r = comp[0];
-      for (int sweep = 0; sweep < 2; sweep++) {
+      // pseudo-peripheral start: two sweeps; the first is the breadth-first search that found the
+      // component (comp is its visit order from comp[0]), so only the second one is run here
+      int r = comp.back();
+      {
         for (int v : comp) lvl[v] = -1;
         bfs(r, lab, order, level_start);
         r = order.back();
@@ -649,80 +650,94 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     fprintf(stderr, "[symbolic] stage3 %-24s %.4f s\n", what, std::chrono::duration<double>(now - tdb).count());
     tdb = now;
   };
-  std::vector<std::vector<int>> cstruct(nb);  // struct of column k: positions > k, sorted
+  // Elimination tree first (Liu's algorithm with path compression -- no column structures needed),
+  // then its postorder, and only then the column structures, once, in the final numbering.
   std::vector<int> eparent(nb, -1);
   {
-    std::vector<std::vector<int>> ekids(nb);
-    std::vector<int> mark(nb, -1);
+    std::vector<int> anc(nb, -1);
     for (int k = 0; k < nb; k++) {
-      int v = order[k];
-      std::vector<int>& st = cstruct[k];
+      const int v = order[k];
       for (int p = nd.xadj[v]; p < nd.xadj[v + 1]; p++) {
-        int q = epos[nd.adj[p]];
-        if (q > k && mark[q] != k) { mark[q] = k; st.push_back(q); }
-      }
-      for (int c : ekids[k])
-        for (int q : cstruct[c])
-          if (q != k && mark[q] != k) { mark[q] = k; st.push_back(q); }
-      std::sort(st.begin(), st.end());
-      if (!st.empty()) {
-        eparent[k] = st[0];
-        ekids[st[0]].push_back(k);
+        int j = epos[nd.adj[p]];
+        if (j >= k) continue;
+        while (anc[j] != -1 && anc[j] != k) {  // climb to the root of j's subtree, compressing
+          const int t = anc[j];
+          anc[j] = k;
+          j = t;
+        }
+        if (anc[j] == -1) { anc[j] = k; eparent[j] = k; }
       }
     }
-    // postorder of the elimination tree (children in ascending order); relabel positions
-    std::vector<int> postpos(nb, -1), seq;
-    seq.reserve(nb);
-    std::vector<std::pair<int, int>> st;
+    // postorder (children in ascending order); relabel positions
+    std::vector<int> kid_ptr(nb + 1, 0), kid(nb);
+    for (int k = 0; k < nb; k++)
+      if (eparent[k] >= 0) kid_ptr[eparent[k] + 1]++;
+    for (int k = 0; k < nb; k++) kid_ptr[k + 1] += kid_ptr[k];
+    {
+      std::vector<int> cur(kid_ptr.begin(), kid_ptr.end() - 1);
+      for (int k = 0; k < nb; k++)
+        if (eparent[k] >= 0) kid[cur[eparent[k]]++] = k;
+    }
+    std::vector<int> postpos(nb, -1), next_kid(kid_ptr.begin(), kid_ptr.end() - 1), stack;
+    int cnt = 0;
     for (int r = 0; r < nb; r++) {
       if (eparent[r] >= 0) continue;
-      st.push_back({r, 0});
-      while (!st.empty()) {
-        auto& top = st.back();
-        if (top.second < (int)ekids[top.first].size()) {
-          int k = ekids[top.first][top.second++];
-          st.push_back({k, 0});
-        } else {
-          postpos[top.first] = (int)seq.size();
-          seq.push_back(top.first);
-          st.pop_back();
-        }
+      stack.push_back(r);
+      while (!stack.empty()) {
+        const int t = stack.back();
+        if (next_kid[t] < kid_ptr[t + 1]) stack.push_back(kid[next_kid[t]++]);
+        else { postpos[t] = cnt++; stack.pop_back(); }
       }
     }
-    // apply: new order, new parents, new structures
     std::vector<int> order2(nb), eparent2(nb, -1);
-    std::vector<std::vector<int>> cstruct2(nb);
     for (int k = 0; k < nb; k++) {
-      int nk = postpos[k];
-      order2[nk] = order[k];
-      eparent2[nk] = eparent[k] >= 0 ? postpos[eparent[k]] : -1;
-      std::vector<int>& d = cstruct2[nk];
-      d.reserve(cstruct[k].size());
-      for (int q : cstruct[k]) d.push_back(postpos[q]);
-      std::sort(d.begin(), d.end());
+      order2[postpos[k]] = order[k];
+      eparent2[postpos[k]] = eparent[k] >= 0 ? postpos[eparent[k]] : -1;
     }
     order.swap(order2);
     eparent.swap(eparent2);
-    cstruct.swap(cstruct2);
     for (int k = 0; k < nb; k++) epos[order[k]] = k;
   }
-  dbg("cstruct+postorder");
+  // column structures (positions > k, sorted) in one flat pool: struct(k) = later neighbours of the
+  // vertex united with the structures of k's etree children minus k itself.  A child always precedes
+  // its parent in the postorder, so its structure is already in the pool.
+  std::vector<int> cs_ptr(nb + 1, 0), cs;
+  cs.reserve((size_t)nd.adj.size() * 2);
+  {
+    std::vector<int> mark(nb, -1), kid_head(nb, -1), kid_next(nb, -1);
+    for (int k = nb - 1; k >= 0; k--)  // child lists in ascending order
+      if (eparent[k] >= 0) { kid_next[k] = kid_head[eparent[k]]; kid_head[eparent[k]] = k; }
+    for (int k = 0; k < nb; k++) {
+      const int v = order[k];
+      const size_t s0 = cs.size();
+      for (int p = nd.xadj[v]; p < nd.xadj[v + 1]; p++) {
+        const int q = epos[nd.adj[p]];
+        if (q > k && mark[q] != k) { mark[q] = k; cs.push_back(q); }
+      }
+      for (int c = kid_head[k]; c >= 0; c = kid_next[c])
+        for (int t = cs_ptr[c]; t < cs_ptr[c + 1]; t++) {
+          const int q = cs[t];
+          if (q != k && mark[q] != k) { mark[q] = k; cs.push_back(q); }
+        }
+      std::sort(cs.begin() + s0, cs.end());
+      cs_ptr[k + 1] = (int)cs.size();
+    }
+  }
+  auto cs_size = [&](int k) { return cs_ptr[k + 1] - cs_ptr[k]; };
+  dbg("etree+postorder+cstruct");
   // supernodes: fundamental (parent[k] == k+1 and struct(k) == {k+1} U struct(k+1)), then relaxed
   // amalgamation of a last child into its parent when the padding it introduces is small
   std::vector<int> snode_first;  // first column of every supernode
   {
-    std::vector<int> nkids(nb, 0);
-    for (int k = 0; k < nb; k++)
-      if (eparent[k] >= 0) nkids[eparent[k]]++;
     snode_first.push_back(0);
     for (int k = 0; k + 1 < nb; k++) {
-      bool merge = eparent[k] == k + 1 && cstruct[k].size() == cstruct[k + 1].size() + 1;
+      bool merge = eparent[k] == k + 1 && cs_size(k) == cs_size(k + 1) + 1;
       if (!merge && eparent[k] == k + 1) {
         // relaxed: column k+1 starts a supernode whose first column has struct(k+1); padding if k
         // joins = rows of (k+1's front) not in struct(k)
         long sk = 0, sk1 = 0;
-        for (int q : cstruct[k]) sk += dim[order[q]];
-        for (int q : cstruct[k + 1]) sk1 += dim[order[q]];
+        for (int t = cs_ptr[k]; t < cs_ptr[k + 1]; t++) sk += dim[order[cs[t]]];
+        for (int t = cs_ptr[k + 1]; t < cs_ptr[k + 2]; t++) sk1 += dim[order[cs[t]]];
         long pad = (sk1 + dim[order[k + 1]]) - sk;  // extra rows carried by the columns merged so far
         long cols = 0;
         for (int c = snode_first.back(); c <= k; c++) cols += dim[order[c]];
@@ -737,48 +752,33 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   for (size_t sidx = 0; sidx < snode_first.size(); sidx++) {
     int c0 = snode_first[sidx], c1 = sidx + 1 < snode_first.size() ? snode_first[sidx + 1] : nb;
     NdNode node;
-    for (int c = c0; c < c1; c++) node.verts.push_back(order[c]);
-    nd.nodes.push_back(node);
+    node.verts.assign(order.begin() + c0, order.begin() + c1);
+    nd.nodes.push_back(std::move(node));
   }
   const int nf = (int)nd.nodes.size();
   S.nf = nf;
   std::vector<int> post(nf);
   std::iota(post.begin(), post.end(), 0);
-  std::vector<int> ppos(nb, -1), front_of(nb, -1);  // provisional position, owning node
-  {
-    int p = 0;
-    for (int f : post) {
-      for (int v : nd.nodes[f].verts) {
-        ppos[v] = p++;
-        front_of[v] = f;
-      }
-    }
-  }
+  std::vector<int> front_of(nb, -1);  // owning node of every block
+  for (int f = 0; f < nf; f++)
+    for (int v : nd.nodes[f].verts) front_of[v] = f;
   dbg("supernodes");
   // ---- pass 1: update sets of every front and the assembly tree ----
-  std::vector<std::vector<int>> U(nf);       // update blocks of every node (sorted by ppos)
+  // The update set of a supernode is the column structure of its LAST column (every earlier column of
+  // the chain, and every child subtree, has its structure beyond the chain contained in it), already
+  // sorted by elimination position; its first entry names the parent front.
+  std::vector<std::vector<int>> U(nf);       // update blocks of every node (sorted by position)
   std::vector<std::vector<int>> akids(nf);   // assembly-tree children
   std::vector<int> aparent(nf, -1);
-  {
-    std::vector<int> mark(nb, -1);
-    for (int f : post) {
-      std::vector<int>& u = U[f];
-      int last = -1;
-      for (int v : nd.nodes[f].verts) last = std::max(last, ppos[v]);
-      for (int v : nd.nodes[f].verts)
-        for (int p = nd.xadj[v]; p < nd.xadj[v + 1]; p++) {
-          int w = nd.adj[p];
-          if (ppos[w] > last && mark[w] != f) { mark[w] = f; u.push_back(w); }
-        }
-      for (int c : akids[f])
-        for (int w : U[c])
-          if (front_of[w] != f && mark[w] != f) { mark[w] = f; u.push_back(w); }
-      std::sort(u.begin(), u.end(), [&](int a, int b) { return ppos[a] < ppos[b]; });
-      if (!u.empty()) {
-        int p = front_of[u[0]];
-        aparent[f] = p;
-        akids[p].push_back(f);
-      }
+  for (int f = 0; f < nf; f++) {
+    const int last = (f + 1 < nf ? snode_first[f + 1] : nb) - 1;
+    std::vector<int>& u = U[f];
+    u.reserve(cs_size(last));
+    for (int t = cs_ptr[last]; t < cs_ptr[last + 1]; t++) u.push_back(order[cs[t]]);
+    if (!u.empty()) {
+      const int pf = front_of[u[0]];
+      aparent[f] = pf;
+      akids[pf].push_back(f);
     }
   }
   dbg("pass1 update sets");
@@ -892,47 +892,51 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   }
   dbg("offsets/stats");
   // ---- assembly entries: every H block lands in the front of its earlier-eliminated vertex ----
-  std::vector<std::vector<AsmEntry>> per(nf);
-  for (int b = 0; b < nb; b++) {
-    int g = fof[b];
-    AsmEntry e;
-    e.hoff = hoff_diag[b];
-    e.r = e.c = S.boff[b] - S.piv0[g];
-    e.meta = dim[b] | (dim[b] << 8) | (1 << 17);
-    per[g].push_back(e);
+  // counting sort by front (diagonal blocks first, then the off-diagonal blocks in input order); the
+  // row of the later vertex inside the front is looked up in a per-front scratch map
+  S.asm_ptr.assign(nf + 1, 0);
+  std::vector<int> off_front(nnb);
+  for (int b = 0; b < nb; b++) S.asm_ptr[fof[b] + 1]++;
+  for (int k = 0; k < nnb; k++) {
+    const int a = off_a[k], b = off_b[k];
+    const int g = fof[S.pos[a] < S.pos[b] ? a : b];
+    off_front[k] = g;
+    S.asm_ptr[g + 1]++;
   }
+  for (int g = 0; g < nf; g++) S.asm_ptr[g + 1] += S.asm_ptr[g];
+  S.asm_entries.resize(S.asm_ptr[nf]);
   {
-    // group off-diagonal blocks by the front of the earlier vertex, resolve row positions per front
-    std::vector<std::vector<int>> byFront(nf);
-    for (int k = 0; k < nnb; k++) {
-      int a = off_a[k], b = off_b[k];
-      int e = S.pos[a] < S.pos[b] ? a : b;
-      byFront[fof[e]].push_back(k);
+    std::vector<int> cur(S.asm_ptr.begin(), S.asm_ptr.end() - 1);
+    for (int b = 0; b < nb; b++) {
+      const int g = fof[b];
+      AsmEntry& e = S.asm_entries[cur[g]++];
+      e.hoff = hoff_diag[b];
+      e.r = e.c = S.boff[b] - S.piv0[g];
+      e.meta = dim[b] | (dim[b] << 8) | (1 << 17);
     }
+    // off-diagonal blocks grouped by front, so the row map is filled once per front
+    std::vector<int> oc(cur), olist(S.asm_ptr[nf]), obase(cur);  // olist is indexed in entry space
+    for (int k = 0; k < nnb; k++) olist[oc[off_front[k]]++] = k;
     for (int g = 0; g < nf; g++) {
-      if (byFront[g].empty()) continue;
+      const int q0 = obase[g], q1 = S.asm_ptr[g + 1];
+      if (q0 == q1) continue;
       fill_rowpos(g, true);
-      for (int k : byFront[g]) {
-        int a = off_a[k], b = off_b[k];
-        bool aEarlier = S.pos[a] < S.pos[b];
-        int e = aEarlier ? a : b, l = aEarlier ? b : a;
-        AsmEntry en;
+      for (int q = q0; q < q1; q++) {
+        const int k = olist[q];
+        const int a = off_a[k], b = off_b[k];
+        const bool aEarlier = S.pos[a] < S.pos[b];
+        const int e = aEarlier ? a : b, l = aEarlier ? b : a;
+        AsmEntry& en = S.asm_entries[q];
         en.hoff = hoff_off[k];
         en.c = S.boff[e] - S.piv0[g];
         en.r = rowpos[l];
         // stored block is dim[a] x dim[b] (rows a).  We need rows l, columns e.
-        int trans = (l == a) ? 0 : 1;
+        const int trans = (l == a) ? 0 : 1;
         en.meta = dim[a] | (dim[b] << 8) | (trans << 16);
-        per[g].push_back(en);
       }
       fill_rowpos(g, false);
     }
   }
   dbg("asm entries");
-  S.asm_ptr.assign(nf + 1, 0);
-  for (int g = 0; g < nf; g++) S.asm_ptr[g + 1] = S.asm_ptr[g] + (int)per[g].size();
-  S.asm_entries.reserve(S.asm_ptr[nf]);
-  for (int g = 0; g < nf; g++)
-    for (auto& e : per[g]) S.asm_entries.push_back(e);
   S.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
