@@ -588,6 +588,15 @@ int slam_b200_debug_phase_clocks(slam_b200_ctx* c, long long out[10]) {
   SLAM_CUDA_TRY(c, cudaMemcpy(out, c->sys->dbg_clocks.p, sizeof(long long) * 10, cudaMemcpyDeviceToHost));
   return 0;
 }
+// Debug: SM cycles summed over every warp of the warp-per-front factor kernel since the graph was
+// prepared (same switch): out[0..5] = zero, scatter H, extend-add, LDL^T, fused forward, write; out[6] = fronts.
+int slam_b200_debug_tiny_clocks(slam_b200_ctx* c, long long out[8]) {
+  if (!c || !c->sys || !out || !c->sys->dbg_clocks.p) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpy(out, c->sys->dbg_clocks.p + 16, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 // ---- symbolic analysis without a device (host logic; testable on a CPU-only box) ----------------
 struct SymHandle {

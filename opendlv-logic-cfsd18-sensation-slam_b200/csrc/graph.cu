@@ -975,7 +975,10 @@ int graph_alloc_values(slam_b200_ctx* c, int R) {
     SLAM_CUDA_TRY(c, D.chi2.exact(r * D.chi2_cap));
     SLAM_CUDA_TRY(c, D.chi2_part.exact(r * D.chi2_blocks));
     SLAM_CUDA_TRY(c, D.status.exact(2 * r));
-    if (getenv("SLAM_B200_PHASE_CLOCKS")) SLAM_CUDA_TRY(c, D.dbg_clocks.exact(16));
+    if (getenv("SLAM_B200_PHASE_CLOCKS")) {
+      SLAM_CUDA_TRY(c, D.dbg_clocks.exact(32));
+      SLAM_CUDA_TRY(c, cudaMemsetAsync(D.dbg_clocks.p, 0, sizeof(long long) * 32, c->stream));
+    }
     SLAM_CUDA_TRY(c, D.est0.exact(r * D.estStride));
     SLAM_CUDA_TRY(c, D.trig.exact(r * 2 * (size_t)D.P));
     D.R = R;

@@ -321,8 +321,10 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
   double* Uv = Uv_all + (size_t)r * nU;
   double* F = smem + (size_t)wid * slab;  // packed lower triangle: F[tri_off(j, fs) + i], i >= j
   const int ntri = (fs * (fs + 1)) >> 1;
+  long long tclk = S.dbg ? clock64() : 0;
   for (int t = lane; t < ntri; t += 32) F[t] = 0.0;
   __syncwarp();
+  if (S.dbg && lane == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&S.dbg[16 + 0], (unsigned long long)(t_ - tclk)); tclk = t_; }
   for (int q = S.asm_ptr[g] + lane; q < S.asm_ptr[g + 1]; q += 32) {
     const AsmEntry en = S.asm_entries[q];
     const double* hv = V + en.hoff;
@@ -340,6 +342,7 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
     }
   }
   __syncwarp();
+  if (S.dbg && lane == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&S.dbg[16 + 1], (unsigned long long)(t_ - tclk)); tclk = t_; }
   // extend-add the children's Schur complements (children of a small front are small: uc <= 64)
   for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
     const int ch = S.children[ci];
@@ -348,16 +351,31 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
     const int* rel = S.rel + S.rows_ptr[ch];
     const int i0 = lane, i1 = lane + 32;
     const int rl0 = i0 < uc ? rel[i0] : 0, rl1 = i1 < uc ? rel[i1] : 0;
-    for (int j = 0; j < uc; j++) {
-      const int ra = __shfl_sync(0xffffffffu, rl0, j & 31), rb = __shfl_sync(0xffffffffu, rl1, j & 31);
-      const int relj = j < 32 ? ra : rb;
-      const double* col = Uc + j * uc;
-      double* dst = F + tri_off(relj, fs);
-      if (i0 >= j && i0 < uc) dst[rl0] += col[i0];
-      if (i1 >= j && i1 < uc) dst[rl1] += col[i1];
+    // four columns per step, all eight global loads issued before the first shared-memory update:
+    // the loop is bound by the latency of these loads, not by their volume
+    for (int j = 0; j < uc; j += 4) {
+      double v0[4], v1[4];
+      int relj[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int jj = j + q;
+        const int ra = __shfl_sync(0xffffffffu, rl0, jj & 31), rb = __shfl_sync(0xffffffffu, rl1, jj & 31);
+        relj[q] = jj < 32 ? ra : rb;
+        const double* col = Uc + (size_t)jj * uc;
+        v0[q] = (jj < uc && i0 >= jj && i0 < uc) ? __ldg(col + i0) : 0.0;
+        v1[q] = (jj < uc && i1 >= jj && i1 < uc) ? __ldg(col + i1) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int jj = j + q;
+        double* dst = F + tri_off(relj[q], fs);
+        if (jj < uc && i0 >= jj && i0 < uc) dst[rl0] += v0[q];
+        if (jj < uc && i1 >= jj && i1 < uc) dst[rl1] += v1[q];
+      }
     }
     __syncwarp();
   }
+  if (S.dbg && lane == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&S.dbg[16 + 2], (unsigned long long)(t_ - tclk)); tclk = t_; }
   // right-looking LDL^T, panels of TNB pivots held in registers; the panel's triangle and the
   // column factors travel between lanes by shuffle
   bool bad = false;
@@ -383,66 +401,65 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
         a1[q] -= a1[p] * f;
       }
     }
-#pragma unroll
-    for (int p = 1; p < TNB; p++) {
-      if (p < nb) {
-        if (r0 < fs && r0 >= k0 + p) F[tri_off(k0 + p, fs) + r0] = a0[p];
-        if (r1 < fs) F[tri_off(k0 + p, fs) + r1] = a1[p];
-      }
-    }
-    double c0[TNB], c1[TNB];
+    // the panel's columns go back SCALED (l_ip = a_ip / d_p, the entries of L; d_p stays on the
+    // diagonal): the trailing update below needs a_ip (in registers) times l_jp, and reads l_jp of its
+    // column j from here with broadcast loads -- no shuffles, no scratch; shuffles and shared-memory
+    // accesses share one pipe, and the write of L at the end needs no division any more
 #pragma unroll
     for (int p = 0; p < TNB; p++) {
-      c0[p] = (p < nb) ? a0[p] * inv[p] : 0.0;
-      c1[p] = (p < nb) ? a1[p] * inv[p] : 0.0;
+      if (p < nb) {
+        if (r0 < fs && r0 >= k0 + p) F[tri_off(k0 + p, fs) + r0] = (r0 == k0 + p) ? a0[p] : a0[p] * inv[p];
+        if (r1 < fs) F[tri_off(k0 + p, fs) + r1] = a1[p] * inv[p];
+      }
     }
-    const int jend0 = min(fs, k0 + 32);
+    __syncwarp();
+    const double* pc[TNB];  // the panel's columns (row index added on use)
+#pragma unroll
+    for (int p = 0; p < TNB; p++) {
+      pc[p] = F + tri_off(k0 + min(p, nb - 1), fs);
+      if (p >= nb) { a0[p] = 0.0; a1[p] = 0.0; }  // padding pivots of a short last panel contribute nothing
+    }
     int j = k0 + nb;
-    for (; j + 1 < jend0; j += 2) {  // two independent columns per step; row factors in slot 0 of lanes j-k0, j+1-k0
-      const int src = j - k0;
+    for (; j + 1 < fs; j += 2) {  // two independent columns per step
       double* cA = F + tri_off(j, fs);
       double* cB = F + tri_off(j + 1, fs);
-      const bool wA0 = r0 >= j && r0 < fs, wB0 = r0 >= j + 1 && r0 < fs, w1 = r1 < fs;
-      double aA0 = wA0 ? cA[r0] : 0.0, aA1 = w1 ? cA[r1] : 0.0;
-      double aB0 = wB0 ? cB[r0] : 0.0, aB1 = w1 ? cB[r1] : 0.0;
+      const bool wA0 = r0 >= j && r0 < fs, wB0 = r0 >= j + 1 && r0 < fs;
+      const bool wA1 = r1 >= j && r1 < fs, wB1 = r1 >= j + 1 && r1 < fs;
+      double aA0 = wA0 ? cA[r0] : 0.0, aA1 = wA1 ? cA[r1] : 0.0;
+      double aB0 = wB0 ? cB[r0] : 0.0, aB1 = wB1 ? cB[r1] : 0.0;
+      double fa[TNB], fb[TNB];
+#pragma unroll
+      for (int p = 0; p < TNB; p++) {  // broadcast reads; pivots beyond nb contribute a_ip = 0
+        fa[p] = pc[p][j];
+        fb[p] = pc[p][j + 1];
+      }
 #pragma unroll
       for (int p = 0; p < TNB; p++) {
-        const double cjA = __shfl_sync(0xffffffffu, c0[p], src);
-        const double cjB = __shfl_sync(0xffffffffu, c0[p], src + 1);
-        aA0 -= a0[p] * cjA; aA1 -= a1[p] * cjA;
-        aB0 -= a0[p] * cjB; aB1 -= a1[p] * cjB;
+        aA0 -= a0[p] * fa[p]; aA1 -= a1[p] * fa[p];
+        aB0 -= a0[p] * fb[p]; aB1 -= a1[p] * fb[p];
       }
       if (wA0) cA[r0] = aA0;
-      if (w1) cA[r1] = aA1;
+      if (wA1) cA[r1] = aA1;
       if (wB0) cB[r0] = aB0;
-      if (w1) cB[r1] = aB1;
+      if (wB1) cB[r1] = aB1;
     }
-    for (; j < jend0; j++) {
-      const int src = j - k0;
+    for (; j < fs; j++) {
       double* cA = F + tri_off(j, fs);
-      const bool wA0 = r0 >= j && r0 < fs, w1 = r1 < fs;
-      double acc0 = wA0 ? cA[r0] : 0.0, acc1 = w1 ? cA[r1] : 0.0;
+      const bool wA0 = r0 >= j && r0 < fs, wA1 = r1 >= j && r1 < fs;
+      double acc0 = wA0 ? cA[r0] : 0.0, acc1 = wA1 ? cA[r1] : 0.0;
 #pragma unroll
       for (int p = 0; p < TNB; p++) {
-        const double cj = __shfl_sync(0xffffffffu, c0[p], src);
+        const double cj = pc[p][j];
         acc0 -= a0[p] * cj;
         acc1 -= a1[p] * cj;
       }
       if (wA0) cA[r0] = acc0;
-      if (w1) cA[r1] = acc1;
-    }
-    for (j = max(k0 + nb, k0 + 32); j < fs; j++) {  // row factor in slot 1 of lane j - k0 - 32
-      const int src = j - k0 - 32;
-      const bool w1 = r1 >= j && r1 < fs;
-      double* cA = F + tri_off(j, fs);
-      double acc1 = w1 ? cA[r1] : 0.0;
-#pragma unroll
-      for (int p = 0; p < TNB; p++) acc1 -= a1[p] * __shfl_sync(0xffffffffu, c1[p], src);
-      if (w1) cA[r1] = acc1;
+      if (wA1) cA[r1] = acc1;
     }
     __syncwarp();
   }
   if (bad && lane == 0) status[2 * r] = 1;
+  if (S.dbg && lane == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&S.dbg[16 + 3], (unsigned long long)(t_ - tclk)); tclk = t_; }
   // ---- fused forward solve (see factor_kernel): lane l owns rows l and l + 32 of w ----
   {
     const int p0 = S.piv0[g];
@@ -459,26 +476,25 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
       for (int q = gp[i1]; q < gp[i1 + 1]; q++) w1 += uvecr[S.gather_src[q]];
     }
     for (int k = 0; k < s; k++) {
-      const double* col = F + tri_off(k, fs);
+      const double* col = F + tri_off(k, fs);  // l_ik below the diagonal, d_k on it
       const double dk = col[k];
       const double wa = __shfl_sync(0xffffffffu, w0, k & 31), wb = __shfl_sync(0xffffffffu, w1, k & 31);
-      const double zk = (k < 32 ? wa : wb) * __drcp_rn(dk);  // y_k / d_k; l_ik = col[i] / d_k
-      if (i0 > k && i0 < fs) w0 -= col[i0] * zk;
-      if (i1 > k && i1 < fs) w1 -= col[i1] * zk;
-      if (lane == (k & 31)) { if (k < 32) w0 = zk; else w1 = zk; }  // keep z in the pivot's slot
+      const double yk = k < 32 ? wa : wb;
+      if (i0 > k && i0 < fs) w0 -= col[i0] * yk;
+      if (i1 > k && i1 < fs) w1 -= col[i1] * yk;
+      if (lane == (k & 31)) { if (k < 32) w0 = yk * __drcp_rn(dk); else w1 = yk * __drcp_rn(dk); }  // z_k = y_k / d_k
     }
     double* xr = x_all + (size_t)r * n;
     double* uo = uvec_all + (size_t)r * nUvec + S.rows_ptr[g];
     if (i0 < s) xr[p0 + i0] = w0; else if (i0 < fs) uo[i0 - s] = w0;
     if (i1 < s) xr[p0 + i1] = w1; else if (i1 < fs) uo[i1 - s] = w1;
   }
+  if (S.dbg && lane == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&S.dbg[16 + 4], (unsigned long long)(t_ - tclk)); tclk = t_; }
   double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
   for (int j = 0; j < s; j++) {
     const double* col = F + tri_off(j, fs);
-    const double d = col[j];
-    const double iv = __drcp_rn(d);
     double* out = Lg + (size_t)j * fs;
-    for (int i = lane; i < fs; i += 32) out[i] = i < j ? 0.0 : (i == j ? d : col[i] * iv);
+    for (int i = lane; i < fs; i += 32) out[i] = i < j ? 0.0 : col[i];
   }
   double* Ug = Uv + S.uptr[g];
   for (int j = 0; j < u; j++) {
@@ -486,6 +502,7 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
     double* out = Ug + (size_t)j * u;
     for (int i = j + lane; i < u; i += 32) out[i] = col[i];
   }
+  if (S.dbg && lane == 0) { const long long t_ = clock64(); atomicAdd((unsigned long long*)&S.dbg[16 + 5], (unsigned long long)(t_ - tclk)); atomicAdd((unsigned long long*)&S.dbg[16 + 6], 1ull); }
 }
 
 __global__ void __launch_bounds__(TINY_WARPS * 32)
