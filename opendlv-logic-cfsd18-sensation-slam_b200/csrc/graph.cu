@@ -853,6 +853,16 @@ int graph_build_structure(slam_b200_ctx* c) {
       size_t sneed = (fs * S.npiv[f] + fs) * sizeof(double);
       LL.smem_solve = std::max(LL.smem_solve, std::min(sneed, smem_limit));
     }
+    {
+      auto fsz = [&](int f) { return S.npiv[f] + S.nupd[f]; };
+      std::stable_sort(launch_list.begin() + LL.list_off, launch_list.end(), [&](int a, int b) { return fsz(a) < fsz(b); });
+      for (size_t q = LL.list_off; q < launch_list.size(); q++) {
+        const int fs = fsz(launch_list[q]);
+        const int cls = fs <= 40 ? 0 : fs <= 48 ? 1 : fs <= 56 ? 2 : 3;
+        LL.tiny_cls_n[cls]++;
+        LL.tiny_cls_fs[cls] = std::max(LL.tiny_cls_fs[cls], fs);
+      }
+    }
     for (int f : small) launch_list.push_back(f);
     for (int f : big) launch_list.push_back(f);
     LL.n_small = (int)small.size();

@@ -34,6 +34,10 @@ struct LevelLaunch {
   int list_off = 0, n_tiny = 0, n_small = 0, n_big = 0;
   size_t smem_tiny = 0, smem_factor = 0, smem_solve = 0;
   int max_fs = 0, max_fs_tiny = 0;
+  // the tiny fronts are listed by ascending size and launched in up to four size classes
+  // (<= 40, <= 48, <= 56, <= 64 rows): the warp-per-front kernels are bound by how many fronts fit
+  // in an SM's shared memory, so a class must not pay for the largest front of the whole level
+  int tiny_cls_n[4] = {0, 0, 0, 0}, tiny_cls_fs[4] = {0, 0, 0, 0};
 };
 
 struct DeviceSystem {

@@ -801,12 +801,17 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
     if (LL.n_tiny && warp_kernels(c, D, LL)) {
-      dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
-      const int slab = (LL.max_fs_tiny * (LL.max_fs_tiny + 1)) / 2;
-      factor_tiny_kernel<<<grid, TINY_WARPS * 32, (size_t)TINY_WARPS * slab * sizeof(double), c->stream>>>(
-          S, LL.list_off, LL.n_tiny, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.status.p, D.uvec.p, D.nUvec,
-          D.x.p, D.n);
-      c->launches++;
+      int off = LL.list_off;
+      for (int cls = 0; cls < 4; cls++) {
+        const int cn = LL.tiny_cls_n[cls];
+        if (!cn) continue;
+        dim3 grid((cn + TINY_WARPS - 1) / TINY_WARPS, D.R);
+        const int slab = (LL.tiny_cls_fs[cls] * (LL.tiny_cls_fs[cls] + 1)) / 2;
+        factor_tiny_kernel<<<grid, TINY_WARPS * 32, (size_t)TINY_WARPS * slab * sizeof(double), c->stream>>>(
+            S, off, cn, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n);
+        c->launches++;
+        off += cn;
+      }
     } else if (LL.n_tiny) {
       dim3 grid(LL.n_tiny, D.R);
       factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
@@ -942,7 +947,12 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
       // (assemble 2 + per level factor/forward/backward + update)
       int n = 2 + 1;
       for (const LevelLaunch& LL : D.levels) {
-        n += (LL.n_tiny ? 1 : 0) + (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);   // factor
+        int ntiny = LL.n_tiny ? 1 : 0;
+        if (LL.n_tiny && warp_kernels(c, D, LL)) {
+          ntiny = 0;
+          for (int cls = 0; cls < 4; cls++) ntiny += LL.tiny_cls_n[cls] ? 1 : 0;
+        }
+        n += ntiny + (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);   // factor
         n += (LL.n_tiny ? 1 : 0) + ((LL.n_small + LL.n_big) ? 1 : 0);            // backward (forward is fused)
       }
       D.launches_per_iter = n;

@@ -25,11 +25,22 @@ struct Nd {
   int nb;
   const int* dim;
   std::vector<int> xadj, adj;
-  std::vector<int> region;  // current region label of every vertex
-  std::vector<int> lvl;     // BFS level scratch
+  std::vector<int> region_store;  // current region label of every vertex
+  std::vector<int> lvl_store;     // BFS level scratch
+  // views used by the algorithm: a sub-dissection running on a pool thread shares the arrays of its
+  // parent (its vertices, and the labels it hands out, are disjoint from everybody else's)
+  const int* xa = nullptr;
+  const int* ad = nullptr;
+  int* region = nullptr;
+  int* lvl = nullptr;
   std::vector<NdNode> nodes;
   int leaf_size;
   int next_label = 1;
+  // recursion below `defer_depth` is not run but recorded (vertex set, label, parent node): the
+  // caller runs those sub-dissections in parallel and splices their trees in, in this order
+  struct Deferred { std::vector<int> verts; int lab; int parent; };
+  int defer_depth = -1;
+  std::vector<Deferred> deferred;
 
   // BFS inside region `lab` from r; fills order (visit order) and lvl[]; returns number of levels
   int bfs(int r, int lab, std::vector<int>& order, std::vector<int>& level_start) {
@@ -47,8 +58,8 @@ struct Nd {
         level_start.push_back((int)head);
       }
       head++;
-      for (int p = xadj[v]; p < xadj[v + 1]; p++) {
-        int u = adj[p];
+      for (int p = xa[v]; p < xa[v + 1]; p++) {
+        int u = ad[p];
         if (region[u] == lab && lvl[u] < 0) {
           lvl[u] = lvl[v] + 1;
           order.push_back(u);
@@ -61,7 +72,7 @@ struct Nd {
 
   // orders the vertex set `verts` (all carrying region label `lab`); appends the resulting
   // subtree roots to `roots`
-  void order_region(std::vector<int>& verts, int lab, std::vector<int>& roots) {
+  void order_region(std::vector<int>& verts, int lab, std::vector<int>& roots, int depth = 0) {
     // split into connected components
     for (int v : verts) lvl[v] = -1;
     std::vector<int> order, level_start;
@@ -96,8 +107,8 @@ struct Nd {
           int v = order[q];
           w[l] += dim[v];
           bool hn = false, hp = false;
-          for (int p = xadj[v]; p < xadj[v + 1]; p++) {
-            int u = adj[p];
+          for (int p = xa[v]; p < xa[v + 1]; p++) {
+            int u = ad[p];
             if (region[u] != lab) continue;
             if (lvl[u] == l + 1) hn = true;
             else if (lvl[u] == l - 1) hp = true;
@@ -163,8 +174,8 @@ struct Nd {
         int l = lvl[v];
         bool inSep = false;
         if (l == sepLevel) {
-          for (int p = xadj[v]; p < xadj[v + 1]; p++) {
-            int u = adj[p];
+          for (int p = xa[v]; p < xa[v + 1]; p++) {
+            int u = ad[p];
             if (region[u] == lab && lvl[u] == other) { inSep = true; break; }
           }
         }
@@ -181,8 +192,13 @@ struct Nd {
       nodes.push_back(nd);
       int me = (int)nodes.size() - 1;
       std::vector<int> kids;
-      order_region(A, la, kids);
-      order_region(B, lb, kids);
+      if (depth == defer_depth) {
+        deferred.push_back({std::move(A), la, me});
+        deferred.push_back({std::move(B), lb, me});
+      } else {
+        order_region(A, la, kids, depth + 1);
+        order_region(B, lb, kids, depth + 1);
+      }
       nodes[me].kids = kids;
       roots.push_back(me);
     }
@@ -609,12 +625,40 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   }
   // ---- stage 1: coarse nested dissection (regions of <= leaf_size vertices) gives the group
   // ranks: all region interiors first, then separators from the deepest level up to the root
-  nd.region.assign(nb, 1);
-  nd.lvl.assign(nb, -1);
+  nd.region_store.assign(nb, 1);
+  nd.lvl_store.assign(nb, -1);
+  nd.xa = nd.xadj.data();
+  nd.ad = nd.adj.data();
+  nd.region = nd.region_store.data();
+  nd.lvl = nd.lvl_store.data();
   nd.next_label = 2;
   std::vector<int> all(nb), roots;
   std::iota(all.begin(), all.end(), 0);
-  nd.order_region(all, 1, roots);
+  // the two top levels of the dissection run here; the (up to four) parts below them are dissected
+  // on the pool threads.  The split depth is fixed, so the result does not depend on the thread count.
+  nd.defer_depth = nb >= 4096 ? 1 : -1;
+  nd.order_region(all, 1, roots, 0);
+  if (!nd.deferred.empty()) {
+    const int nt = (int)nd.deferred.size();
+    std::vector<Nd> sub(nt);
+    std::vector<std::vector<int>> sub_roots(nt);
+    HostPool::get().run(nt, [&](int t) {
+      Nd& q = sub[t];
+      q.nb = nb; q.dim = dim; q.leaf_size = nd.leaf_size;
+      q.xa = nd.xa; q.ad = nd.ad; q.region = nd.region; q.lvl = nd.lvl;
+      q.next_label = 2 + 2 * nb * (t + 1);  // label ranges never overlap (a dissection of n vertices hands out < 2n labels)
+      q.order_region(nd.deferred[t].verts, nd.deferred[t].lab, sub_roots[t], 0);
+    });
+    for (int t = 0; t < nt; t++) {
+      const int off = (int)nd.nodes.size();
+      for (NdNode& node : sub[t].nodes) {
+        for (int& k : node.kids) k += off;
+        nd.nodes.push_back(std::move(node));
+      }
+      for (int rt : sub_roots[t]) nd.nodes[nd.deferred[t].parent].kids.push_back(rt + off);
+    }
+    nd.deferred.clear();
+  }
   std::vector<int> rank(nb, 0);
   {
     // depth of every nested-dissection node; leaves (no kids) get rank 0, a separator at depth d

@@ -96,3 +96,33 @@ def test_symbolic_random_sparse(pkg):
     x = np.zeros(n)
     x[perm] = mf_emul.factor_solve(sym, hv, b[perm])
     assert np.allclose(H @ x, b, rtol=1e-9, atol=1e-10)
+
+
+def test_symbolic_is_independent_of_the_host_thread_count():
+    """Nested dissection below depth 1 and the region-wise minimum degree run on a pool of host threads;
+    the elimination order, the assembly tree and every index array must not depend on how many."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, hashlib, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import load_pkg
+import mf_emul
+pkg = load_pkg()
+g = pkg.synth.graph_from_drive(pkg.synth.trackdrive(5))
+ids, dims, pa, pb = mf_emul.block_pattern(g)
+S = pkg.capi.SymbolicAnalysis(dims, pa, pb, 512)
+h = hashlib.sha1()
+for k in ("pos", "boff", "level_ptr", "npiv", "nupd", "parent", "rel", "asm"):
+    h.update(np.ascontiguousarray(getattr(S, k)).tobytes())
+print("HASH", h.hexdigest(), int(S.nnzL))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    seen = set()
+    for threads in ("1", "2", "7"):
+        env = dict(os.environ, SLAM_B200_SYM_THREADS=threads)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        seen.add([ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][0])
+    assert len(seen) == 1, seen
