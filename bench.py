@@ -54,6 +54,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernel, from the
+    committed `ncu --set full` capture summarised in profiles/r01_traffic.json; None if not captured."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return float(json.load(open(p))[key]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -302,6 +312,9 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
     K = args.steps
     order = [k % ASSOC_COPIES for k in range(K)]
     trains = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    tw0 = time.time()
     for name, algo in (("train", pkg.capi.ALGO_GRID), ("pipelined", pkg.capi.ALGO_GRID_PIPELINED)):
         launch = pkg.capi.Context.assoc_bulk_frames_dev([ctxs[q] for q in order], [d_ins[q].data_ptr() for q in order],
                                                         [n] * K, np.tile(field.pose, (K, 1)), THR, pkg.capi.GATE_MAPPING, algo,
@@ -316,6 +329,14 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
         med = max_over_ranks(float(np.median(ms)), world, dev)
         same = all(bool(torch.equal(d_outs[q], ref_idx)) for q in range(min(ASSOC_COPIES, K)))
         trains[name] = dict(ms_per_frame=med / K, assoc_per_s=n_total * K / (med * 1e-3), identical_to_single_launch=same)
+    # keep the GPU under the same load until nvidia-smi has sampled it a few times (a train lasts ~0.1 ms)
+    t_end = time.time() + 0.6
+    while time.time() < t_end:
+        with torch.cuda.stream(stream):
+            launch()
+        stream.synchronize()
+    tw1 = time.time()
+    clocks = sampler.stop(tw0, tw1)
     # end to end: pinned host frame in, host indices out, copies inside the timed region
     hin = host_in.numpy().T   # 4 x n view, column-major
     hout = host_out.numpy()
@@ -349,11 +370,11 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
         roofline={"bound": "hbm", "kernel": "assoc_bulk_grid_kernel", "achieved": roof(tp["ms_per_frame"]),
                   "peak": hbm, "unit": "GB/s", "frac": roof(tp["ms_per_frame"]) / hbm,
                   "frac_single_launch": roof(g["ms_per_frame"]) / hbm, "frac_train_unpipelined": roof(trains["train"]["ms_per_frame"]) / hbm,
-                  "traffic": None, "algorithmic_bytes_per_launch": bytes_alg, "peak_source": how},
+                  "traffic": measured_traffic("c4_assoc_bulk_grid_kernel"), "algorithmic_bytes_per_launch": bytes_alg, "peak_source": how},
         brute_force={"assoc_per_s": out["brute"]["assoc_per_s"], "ms_per_frame": out["brute"]["ms_per_frame"],
                      "pair_tests_per_s": float(n) * M / (out["brute"]["ms_per_frame"] * 1e-3) * world,
                      "note": "fp64-issue-bound variant (N*M pair tests), identical indices"},
-        grid_build_ms=grid_build_s * 1e3)
+        grid_build_ms=grid_build_s * 1e3, clocks=clocks)
     for c in ctxs:
         c.close()
     return res
@@ -436,7 +457,8 @@ def bench_c5(pkg, torch, args, world, rank, local, synth):
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "assemble_pose_kernel + assemble_landmark_kernel (this rank's shard)",
                          "achieved": bytes_rank / (local_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": bytes_rank / (local_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                         "frac": bytes_rank / (local_ms * 1e-3) / 1e9 / hbm,
+                         "traffic": measured_traffic("c5_assemble_kernels") if world == 1 else None,
                          "algorithmic_bytes_per_launch": bytes_rank, "peak_source": how}}
     ctx.close()
     return line
@@ -514,7 +536,7 @@ def run_ours(args):
             "clocks": r["clocks"],
             "roofline": {"bound": "hbm", "kernel": "factor_kernel (all assembly-tree levels of one factorisation)",
                          "achieved": bytes_fac / fac_s / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": bytes_fac / fac_s / 1e9 / hbm, "traffic": None,
+                         "frac": bytes_fac / fac_s / 1e9 / hbm, "traffic": measured_traffic("c2_factor_kernels"),
                          "algorithmic_bytes_per_launch": bytes_fac, "peak_source": how,
                          "note": "latency-bound: ~%d dependent levels of small fronts" % int(st["n_levels"])},
             "phases_ms_per_iteration": {k: prof[k] / nit for k in ("assemble_ms", "factor_ms", "forward_ms", "backward_ms", "update_ms")},
@@ -572,7 +594,8 @@ def run_ours(args):
                 "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "assemble_pose_kernel + assemble_landmark_kernel",
                              "achieved": asm_bytes / asm_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": asm_bytes / asm_s / 1e9 / hbm,
-                             "traffic": None, "algorithmic_bytes_per_launch": asm_bytes, "peak_source": how},
+                             "traffic": measured_traffic("c3_assemble_kernels") if world == 1 else None,
+                             "algorithmic_bytes_per_launch": asm_bytes, "peak_source": how},
                 "phases_ms_per_iteration": {k: prof[k] / nit for k in ("assemble_ms", "factor_ms", "forward_ms", "backward_ms", "update_ms")},
                 "parity_in_run": {"iterations_done_ok": r["done_ok"], "chi2_final_mean": r["chi2_last"]}}
         r["ctx"].close()
@@ -584,7 +607,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": a["workload"]},
                 "e2e": a["e2e"], "roofline": a["roofline"], "brute_force": a["brute_force"], "gpu_launches": args.steps,
                 "timing": a["timing"], "single_launch": a["single_launch"], "train_unpipelined": a["train_unpipelined"],
-                "identical_to_single_launch": a["identical_to_single_launch"]}
+                "identical_to_single_launch": a["identical_to_single_launch"], "clocks": a["clocks"]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
