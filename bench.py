@@ -350,7 +350,11 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
     e2e_s = (time.perf_counter() - t0) / args.steps
     e2e_s = max_over_ranks(e2e_s * 1e3, world, dev) * 1e-3
     hbm, how = peaks()
-    bytes_alg = 36.0 * n + 20.0 * M   # per frame, per rank (map replicated)
+    # 36 N + 20 M per frame.  With the observation batch split over `world` ranks the
+    # frame's algorithmic bytes stay those of the WHOLE frame (a rank's part of the batch only touches
+    # the map cells near its own observations, not the whole replicated map), so the job-level figure
+    # is frame bytes / frame time against world x the per-GPU peak; per rank that is bytes / world.
+    bytes_alg = (36.0 * n_total + 20.0 * M) / world
     g, tp = out["grid"], trains["pipelined"]
 
     def roof(ms_per_frame):
