@@ -200,6 +200,22 @@ int slam_b200_graph_assemble_async(slam_b200_ctx* ctx, int p0, int p1);
  * which: 0 = landmark diagonal blocks + landmark rhs (contiguous, the part that needs a
  * reduction across pose shards), 1 = full H value array, 2 = rhs b.  Returns element count. */
 long slam_b200_graph_system_dev(slam_b200_ctx* ctx, int which, double** ptr);
+/* Peer-memory exchange of that landmark part between the pose-range shards of one graph (one process
+ * per GPU of one node; replaces the all-reduce).  Collective set-up, once per graph and shard layout:
+ *   shard_landmarks : [l0,l1) = landmarks the edges of pose range [p0,p1) touch;
+ *   xchg_create     : allocates this rank's exchange region for `cap` >= max over ranks of (l1-l0)
+ *                     landmarks and returns its 64-byte CUDA IPC handle;
+ *   xchg_connect    : handles = world x 64 bytes, ranges = world x [l0,l1) (both gathered over ranks).
+ * graph_assemble_exchange_async(p0,p1) then enqueues linearise + assemble of the shard with the
+ * landmark kernel storing its partial blocks straight into every rank's region over NVLink, followed
+ * by a kernel that waits for all ranks and sums the partials in rank order into the landmark part of
+ * V -- every rank ends up with the complete landmark part, bit-identical on all ranks.
+ * xchg_error: synchronises and returns 1 if a rank ever timed out waiting for a peer. */
+int slam_b200_graph_shard_landmarks(slam_b200_ctx* ctx, int p0, int p1, int32_t* l0, int32_t* l1);
+int slam_b200_xchg_create(slam_b200_ctx* ctx, int world, int rank, int cap, unsigned char handle_out[64]);
+int slam_b200_xchg_connect(slam_b200_ctx* ctx, const unsigned char* handles, const int32_t* ranges);
+int slam_b200_graph_assemble_exchange_async(slam_b200_ctx* ctx, int p0, int p1);
+int slam_b200_xchg_error(slam_b200_ctx* ctx);
 /* Enqueues factorise + solve + update for the system currently assembled. */
 int slam_b200_graph_solve_async(slam_b200_ctx* ctx);
 /* Device-side copy of all estimates (every replica) and its restoration, so repeated runs start

@@ -63,6 +63,11 @@ def lib():
         L.slam_b200_batch_iterate_async.argtypes = [C.c_void_p, C.c_int]
         L.slam_b200_graph_finish.argtypes = [C.c_void_p, c_dp, C.c_int]
         L.slam_b200_graph_assemble_async.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.slam_b200_graph_assemble_exchange_async.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.slam_b200_graph_shard_landmarks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.slam_b200_xchg_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
+        L.slam_b200_xchg_connect.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), c_ip]
+        L.slam_b200_xchg_error.argtypes = [C.c_void_p]
         L.slam_b200_map_build_grid.argtypes = [C.c_void_p, C.c_double]
         L.slam_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.slam_b200_profile_read.argtypes = [C.c_void_p, c_dp]
@@ -320,6 +325,29 @@ class Context:
 
     def graph_assemble_async(self, p0, p1):
         self._ck(self.L.slam_b200_graph_assemble_async(self.h, int(p0), int(p1)), "graph_assemble_async")
+
+    def graph_shard_landmarks(self, p0, p1):
+        l0 = C.c_int32(0); l1 = C.c_int32(0)
+        self._ck(self.L.slam_b200_graph_shard_landmarks(self.h, int(p0), int(p1), C.byref(l0), C.byref(l1)), "shard_landmarks")
+        return l0.value, l1.value
+
+    def xchg_create(self, world, rank, cap):
+        """Allocates this rank's peer-exchange region; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.L.slam_b200_xchg_create(self.h, int(world), int(rank), int(cap), buf), "xchg_create")
+        return bytes(buf)
+
+    def xchg_connect(self, handles, ranges):
+        """handles: world x 64 bytes (rank order); ranges: world x 2 int32 landmark ranges."""
+        hb = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        rg = _i32(np.asarray(ranges).reshape(-1))
+        self._ck(self.L.slam_b200_xchg_connect(self.h, hb, _ip(rg)), "xchg_connect")
+
+    def graph_assemble_exchange_async(self, p0, p1):
+        self._ck(self.L.slam_b200_graph_assemble_exchange_async(self.h, int(p0), int(p1)), "graph_assemble_exchange_async")
+
+    def xchg_error(self):
+        return self._ck(self.L.slam_b200_xchg_error(self.h), "xchg_error")
 
     def graph_solve_async(self):
         self._ck(self.L.slam_b200_graph_solve_async(self.h), "graph_solve_async")

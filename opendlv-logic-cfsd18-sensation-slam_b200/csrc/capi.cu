@@ -445,6 +445,80 @@ int slam_b200_graph_assemble_async(slam_b200_ctx* c, int p0, int p1) {
   return graph_enqueue_assemble(c, p0, p1, false);
 }
 
+// ---- peer exchange of the landmark part (config 5, one process per GPU) -------------------------
+int slam_b200_graph_shard_landmarks(slam_b200_ctx* c, int p0, int p1, int32_t* l0, int32_t* l1) {
+  if (!c || !c->sys || !l0 || !l1) return SLAM_B200_E_STATE;
+  DeviceSystem& D = *c->sys;
+  if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
+  int a, b;
+  graph_shard_landmarks(D, p0, p1, &a, &b);
+  *l0 = a; *l1 = b;
+  return 0;
+}
+
+int slam_b200_xchg_create(slam_b200_ctx* c, int world, int rank, int cap, unsigned char handle_out[64]) {
+  if (!c || !c->sys || !handle_out || world < 1 || world > 64 || rank < 0 || rank >= world || cap < 1) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceSystem& D = *c->sys;
+  xchg_release(D);
+  PeerExchange& X = D.xchg;
+  X.world = world; X.rank = rank; X.cap = cap;
+  X.bytes = 1024 + sizeof(double) * 2 * (size_t)world * 6 * (size_t)cap;
+  SLAM_CUDA_TRY(c, cudaMalloc(&X.local, X.bytes));
+  SLAM_CUDA_TRY(c, cudaMemset(X.local, 0, X.bytes));
+  cudaIpcMemHandle_t h;
+  SLAM_CUDA_TRY(c, cudaIpcGetMemHandle(&h, X.local));
+  std::memcpy(handle_out, &h, 64);
+  return 0;
+}
+
+int slam_b200_xchg_connect(slam_b200_ctx* c, const unsigned char* handles, const int32_t* ranges) {
+  if (!c || !c->sys || !handles || !ranges || !c->sys->xchg.local) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  PeerExchange& X = c->sys->xchg;
+  X.peers.assign(X.world, nullptr);
+  for (int r = 0; r < X.world; r++) {
+    if (r == X.rank) { X.peers[r] = X.local; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    SLAM_CUDA_TRY(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    X.peers[r] = static_cast<char*>(p);
+  }
+  X.ranges_host.assign(ranges, ranges + 2 * (size_t)X.world);
+  for (int r = 0; r < X.world; r++)
+    if (ranges[2 * r + 1] - ranges[2 * r] > X.cap || ranges[2 * r] < 0 || ranges[2 * r + 1] > c->sys->L) return SLAM_B200_E_ARG;
+  SLAM_CUDA_TRY(c, X.peer_tab.exact(X.world));
+  SLAM_CUDA_TRY(c, X.ranges.exact(2 * (size_t)X.world));
+  SLAM_CUDA_TRY(c, X.err.exact(1));
+  SLAM_CUDA_TRY(c, X.done.exact(1));
+  SLAM_CUDA_TRY(c, cudaMemcpy(X.peer_tab.p, X.peers.data(), sizeof(char*) * X.world, cudaMemcpyHostToDevice));
+  SLAM_CUDA_TRY(c, cudaMemcpy(X.ranges.p, X.ranges_host.data(), sizeof(int) * 2 * X.world, cudaMemcpyHostToDevice));
+  SLAM_CUDA_TRY(c, cudaMemset(X.err.p, 0, sizeof(int)));
+  SLAM_CUDA_TRY(c, cudaMemset(X.done.p, 0, sizeof(unsigned)));
+  X.epoch = 0;
+  X.connected = true;
+  return 0;
+}
+
+int slam_b200_graph_assemble_exchange_async(slam_b200_ctx* c, int p0, int p1) {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  DeviceSystem& D = *c->sys;
+  if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
+  return graph_enqueue_assemble(c, p0, p1, false, true);
+}
+
+int slam_b200_xchg_error(slam_b200_ctx* c) {
+  if (!c || !c->sys || !c->sys->xchg.connected) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  int e = 0;
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpy(&e, c->sys->xchg.err.p, sizeof(int), cudaMemcpyDeviceToHost));
+  return e;
+}
+
 long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) {
   if (!c || !c->sys || !ptr) return SLAM_B200_E_STATE;
   DeviceSystem& D = *c->sys;

@@ -389,9 +389,30 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
 // exchanged through memory.
 constexpr int LM_PER_BLOCK = ASM_THREADS / 32;
 
-template <bool CHI2_ONLY, bool UNROLL2>
+// Peer exchange of the landmark part between the pose-range shards of ONE graph (config 5, one
+// process per GPU).  Every rank owns a region of device memory opened by all the others through
+// CUDA IPC: [world 64-bit flags | 2 parities x world slots of 6*cap doubles].  PEER mode of the
+// landmark kernel stores the partial block + rhs of every landmark of this shard's range straight into
+// slot[parity][rank] of EVERY rank (lane d of the warp writes to rank d over NVLink) -- the all-gather
+// rides on the kernel's own stores --, and the last CTA to finish publishes `epoch` in every rank's
+// flag word.  lm_exchange_sum_kernel then waits for all flags and sums the slots in rank order
+// (deterministic, unlike a ring all-reduce) into the landmark part of V.  Two parities: a rank can
+// start pushing assembly k+1 while a slower rank still sums assembly k; it cannot reach k+2 before
+// every rank has pushed k+1, i.e. finished summing k.
+constexpr int XCHG_HEADER = 1024;  // bytes reserved for the flags
+struct PeerArgs {
+  char* const* peer_tab;  // region base of every rank (device array)
+  int world, rank, cap, parity;
+  unsigned long long epoch;
+  unsigned* done;         // CTA completion counter (this rank)
+};
+__device__ __forceinline__ double* xchg_slot(char* base, int world, int cap, int parity, int src) {
+  return reinterpret_cast<double*>(base + XCHG_HEADER) + ((size_t)parity * world + src) * 6 * (size_t)cap;
+}
+
+template <bool CHI2_ONLY, bool UNROLL2, bool PEER>
 __global__ void __launch_bounds__(ASM_THREADS)
-assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_first, int l_end) {
+assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_first, int l_end, PeerArgs px) {
   const int lane = threadIdx.x & 31;
   const int l = l_first + blockIdx.x * LM_PER_BLOCK + (threadIdx.x >> 5);
   const int r = blockIdx.y;
@@ -399,6 +420,14 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
   const double* meas = a.meas + (size_t)r * a.measStride;
   double* V = a.V + (size_t)r * a.nV;
   const int P = a.P, L = a.L, El = a.El;
+  if (PEER && !CHI2_ONLY && l < l_end && !a.lm_free[l] && lane < px.world) {
+    // fixed / inactive landmark inside the range: its slot entries must read as zero on every rank
+    double* slot = xchg_slot(px.peer_tab[lane], px.world, px.cap, px.parity, px.rank);
+    const int k = l - l_first;
+    slot[2 * k] = 0.0; slot[2 * k + 1] = 0.0;
+    double* hs = slot + 2 * (size_t)px.cap + 4 * (size_t)k;
+    hs[0] = 0.0; hs[1] = 0.0; hs[2] = 0.0; hs[3] = 0.0;
+  }
   if (!CHI2_ONLY && l < l_end && a.lm_free[l]) {  // warp-uniform
     const double lx = est[3 * P + l], ly = est[3 * P + L + l];
     double h00 = 0, h01 = 0, h11 = 0, b0 = 0, b1 = 0;
@@ -465,11 +494,34 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
       b0 += __shfl_xor_sync(0xffffffffu, b0, o);
       b1 += __shfl_xor_sync(0xffffffffu, b1, o);
     }
-    if (lane == 0) {
+    if (PEER) {
+      if (lane < px.world) {  // the butterfly left the sums in every lane: lane d stores to rank d
+        double* slot = xchg_slot(px.peer_tab[lane], px.world, px.cap, px.parity, px.rank);
+        const int k = l - l_first;
+        *reinterpret_cast<double2*>(slot + 2 * (size_t)k) = make_double2(b0, b1);
+        double2* hs = reinterpret_cast<double2*>(slot + 2 * (size_t)px.cap + 4 * (size_t)k);
+        hs[0] = make_double2(h00, h01);
+        hs[1] = make_double2(h01, h11);
+      }
+    } else if (lane == 0) {
       double* bl = V + 2 * (size_t)l;
       bl[0] = b0; bl[1] = b1;
       double* hl = V + 2 * (size_t)L + 4 * (size_t)l;
       hl[0] = h00; hl[1] = h01; hl[2] = h01; hl[3] = h11;
+    }
+  }
+  if (PEER) {
+    // completion: every CTA makes its peer stores visible system-wide, the last one raises the flags
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const unsigned total = gridDim.x * gridDim.y;
+      if (atomicAdd(px.done, 1u) == total - 1) {
+        *px.done = 0;
+        __threadfence_system();
+        for (int d = 0; d < px.world; d++)
+          reinterpret_cast<volatile unsigned long long*>(px.peer_tab[d])[px.rank] = px.epoch;
+      }
     }
   }
   // final chi2 of this replica: fixed-order sum of the pose kernel's block partials
@@ -481,6 +533,50 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
     const int slot = a.status[2 * r + 1];
     if (threadIdx.x == 0 && slot < a.chi2_cap) a.chi2[(size_t)r * a.chi2_cap + slot] = t;
   }
+}
+
+// Second half of the peer exchange: wait until every rank has published `epoch`, then
+// V[landmark part] = sum over ranks (ascending) of their partial blocks.  A rank that never arrives
+// (a peer died) is reported through *err after `timeout_ns` instead of hanging the GPU.
+__global__ void __launch_bounds__(256)
+lm_exchange_sum_kernel(char* local, int world, int cap, int parity, unsigned long long epoch,
+                       const int* __restrict__ ranges, int L, double* __restrict__ V, int* err,
+                       unsigned long long timeout_ns) {
+  __shared__ int go;
+  if (threadIdx.x == 0) {
+    const volatile unsigned long long* flags = reinterpret_cast<const volatile unsigned long long*>(local);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    int ok = 1;
+    for (int s = 0; s < world && ok; s++) {
+      while (flags[s] < epoch) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { ok = 0; break; }
+      }
+    }
+    if (!ok) *err = 1;
+    __threadfence_system();
+    go = ok;
+  }
+  __syncthreads();
+  if (!go) return;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double b0 = 0, b1 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+  for (int s = 0; s < world; s++) {
+    const int l0 = ranges[2 * s], l1 = ranges[2 * s + 1];
+    if (l < l0 || l >= l1) continue;
+    const double* slot = xchg_slot(local, world, cap, parity, s);
+    const int k = l - l0;
+    const double2 b = __ldcg(reinterpret_cast<const double2*>(slot + 2 * (size_t)k));
+    const double2* hs = reinterpret_cast<const double2*>(slot + 2 * (size_t)cap + 4 * (size_t)k);
+    const double2 ha = __ldcg(hs), hb = __ldcg(hs + 1);
+    b0 += b.x; b1 += b.y; h0 += ha.x; h1 += ha.y; h2 += hb.x; h3 += hb.y;
+  }
+  *reinterpret_cast<double2*>(V + 2 * (size_t)l) = make_double2(b0, b1);
+  double2* hv = reinterpret_cast<double2*>(V + 2 * (size_t)L + 4 * (size_t)l);
+  hv[0] = make_double2(h0, h1);
+  hv[1] = make_double2(h2, h3);
 }
 
 // SparseOptimizer::update: VertexSE2::oplusImpl (additive, normalised angle) / VertexPointXY
@@ -550,7 +646,20 @@ int graph_enqueue_update(slam_b200_ctx* c) {
   return 0;
 }
 
-int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
+void graph_shard_landmarks(DeviceSystem& D, int p0, int p1, int* l0, int* l1) {
+  if (D.shard_p0 != p0 || D.shard_p1 != p1) {
+    int lo = D.L, hi = -1;
+    const int e0 = D.el_start_host[p0], e1 = D.el_start_host[p1];
+    for (int e = e0; e < e1; e++) { lo = std::min(lo, D.s_lm_host[e]); hi = std::max(hi, D.s_lm_host[e]); }
+    D.shard_p0 = p0; D.shard_p1 = p1;
+    D.shard_l0 = hi < 0 ? 0 : lo;
+    D.shard_l1 = hi < 0 ? 0 : hi + 1;
+  }
+  *l0 = D.shard_l0;
+  *l1 = D.shard_l1;
+}
+
+int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, bool peer) {
   DeviceSystem& D = *c->sys;
   AsmArgs a;
   a.P = D.P; a.L = D.L; a.Eo = D.Eo; a.El = D.El;
@@ -576,27 +685,36 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only) {
   // landmarks touched by this pose range (a shard of a large graph sees a small, contiguous-ish part
   // of the landmarks); the untouched part of the landmark blocks must read as zero for the reduction
   int l_first = 0, l_end = D.L;
-  if (!chi2_only && (p0 > 0 || p1 < D.P) && D.R == 1) {
-    if (D.shard_p0 != p0 || D.shard_p1 != p1) {
-      int lo = D.L, hi = -1;
-      const int e0 = D.el_start_host[p0], e1 = D.el_start_host[p1];
-      for (int e = e0; e < e1; e++) { lo = std::min(lo, D.s_lm_host[e]); hi = std::max(hi, D.s_lm_host[e]); }
-      D.shard_p0 = p0; D.shard_p1 = p1;
-      D.shard_l0 = hi < 0 ? 0 : lo;
-      D.shard_l1 = hi < 0 ? 0 : hi + 1;
-    }
-    l_first = D.shard_l0;
-    l_end = D.shard_l1;
+  PeerArgs px = {};
+  if (peer) {
+    PeerExchange& X = D.xchg;
+    if (chi2_only || D.R != 1 || !X.connected) return SLAM_B200_E_STATE;
+    graph_shard_landmarks(D, p0, p1, &l_first, &l_end);
+    if (l_first != X.ranges_host[2 * X.rank] || l_end != X.ranges_host[2 * X.rank + 1] || l_end - l_first > X.cap)
+      return SLAM_B200_E_ARG;  // the pose range differs from the one the exchange was connected for
+    X.epoch++;
+    px.peer_tab = X.peer_tab.p; px.world = X.world; px.rank = X.rank; px.cap = X.cap;
+    px.parity = (int)(X.epoch & 1); px.epoch = X.epoch; px.done = X.done.p;
+  } else if (!chi2_only && (p0 > 0 || p1 < D.P) && D.R == 1) {
+    graph_shard_landmarks(D, p0, p1, &l_first, &l_end);
     SLAM_CUDA_TRY(c, cudaMemsetAsync(D.V.p, 0, sizeof(double) * 6 * (size_t)D.L, c->stream));
   }
   dim3 gl(std::max(1, (l_end - l_first + LM_PER_BLOCK - 1) / LM_PER_BLOCK), D.R);
   // a landmark with more than one 32-edge step of observers (long tracks, many laps) is worth the
   // two-steps-in-flight loop; with 20-30 observers per landmark the plain loop is faster (measured)
   const bool unroll2 = D.El > 32L * std::max(D.L, 1);
-  if (chi2_only) assemble_landmark_kernel<true, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
-  else if (unroll2) assemble_landmark_kernel<false, true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
-  else assemble_landmark_kernel<false, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end);
+  if (chi2_only) assemble_landmark_kernel<true, false, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
+  else if (peer && unroll2) assemble_landmark_kernel<false, true, true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
+  else if (peer) assemble_landmark_kernel<false, false, true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
+  else if (unroll2) assemble_landmark_kernel<false, true, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
+  else assemble_landmark_kernel<false, false, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
   c->launches++;
+  if (peer) {
+    PeerExchange& X = D.xchg;
+    lm_exchange_sum_kernel<<<(D.L + 255) / 256, 256, 0, c->stream>>>(X.local, X.world, X.cap, px.parity, X.epoch, X.ranges.p,
+                                                                   D.L, D.V.p, X.err.p, 200000000ull);
+    c->launches++;
+  }
   SLAM_CUDA_TRY(c, cudaGetLastError());
   if (!chi2_only) D.assembled = true;
   return 0;
@@ -1043,6 +1161,15 @@ int graph_upload_host_values(slam_b200_ctx* c) {
   return 0;
 }
 
+void xchg_release(DeviceSystem& D) {
+  PeerExchange& X = D.xchg;
+  for (int r = 0; r < (int)X.peers.size(); r++)
+    if (r != X.rank && X.peers[r]) cudaIpcCloseMemHandle(X.peers[r]);
+  if (X.local) cudaFree(X.local);
+  X.peer_tab.release(); X.ranges.release(); X.err.release(); X.done.release();
+  X = PeerExchange();
+}
+
 void graph_release(slam_b200_ctx* c) {
   if (!c->sys) return;
   DeviceSystem& D = *c->sys;
@@ -1059,6 +1186,7 @@ void graph_release(slam_b200_ctx* c) {
   D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
   D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
   D.est0.release(); D.trig.release(); D.dbg_clocks.release(); D.lmo_pose.release(); D.lmo_info.release();
+  xchg_release(D);
   D.drop_graph();
   delete c->sys;
   c->sys = nullptr;

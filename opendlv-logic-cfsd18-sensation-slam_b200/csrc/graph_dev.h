@@ -40,6 +40,20 @@ struct LevelLaunch {
   int tiny_cls_n[4] = {0, 0, 0, 0}, tiny_cls_fs[4] = {0, 0, 0, 0};
 };
 
+// Peer exchange of the landmark part between pose-range shards (graph.cu: PeerArgs); one per context
+struct PeerExchange {
+  int world = 0, rank = 0, cap = 0;  // cap = landmarks per slot (max shard range over the ranks)
+  bool connected = false;
+  unsigned long long epoch = 0;
+  char* local = nullptr;             // this rank's region (cudaMalloc, exported through CUDA IPC)
+  size_t bytes = 0;
+  std::vector<char*> peers;          // region base per rank; peers[rank] == local, others opened via IPC
+  std::vector<int> ranges_host;      // world x [l0, l1)
+  DevBuf<char*> peer_tab;
+  DevBuf<int> ranges, err;
+  DevBuf<unsigned> done;
+};
+
 struct DeviceSystem {
   uint64_t structure_version = 0;  // HostGraph version this was built from
   uint64_t values_version = 0;     // HostGraph values currently on the device (replica 0)
@@ -76,6 +90,7 @@ struct DeviceSystem {
   DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part, est0, trig;
   DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done (= chi2 slot)
   DevBuf<long long> dbg_clocks;    // optional (SLAM_B200_PHASE_CLOCKS): phase clocks of one factor CTA
+  PeerExchange xchg;
   int chi2_cap = 0, chi2_blocks = 0;
   int iters_enqueued = 0;
   bool assembled = false;
@@ -98,6 +113,8 @@ struct DeviceSystem {
 int graph_build_structure(slam_b200_ctx* c);            // host: index mapping, blocks, symbolic
 int graph_alloc_values(slam_b200_ctx* c, int R);        // device value arrays for R replicas
 int graph_upload_host_values(slam_b200_ctx* c);         // replica 0 <- HostGraph numbers
-int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only);
+int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, bool peer = false);
+void graph_shard_landmarks(DeviceSystem& D, int p0, int p1, int* l0, int* l1);  // landmark range a pose shard touches
+void xchg_release(DeviceSystem& D);
 int graph_enqueue_solve(slam_b200_ctx* c);              // factor + forward + backward + update
 int graph_enqueue_iteration(slam_b200_ctx* c);          // one GN iteration (CUDA graph replay when possible)

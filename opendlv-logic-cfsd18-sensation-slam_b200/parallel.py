@@ -37,12 +37,45 @@ def landmark_part_tensor(ctx, device):
     return torch.as_tensor(DeviceArray(ptr, n), device=device)
 
 
-def assemble_sharded(ctx, n_poses: int, rank: int, world: int, device=None, group=None):
+def gather_bytes(payload: bytes, world: int, device=None, group=None):
+    """All-gather of equal-length byte strings over the process group (rank order)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+
+def connect_peer_exchange(ctx, n_poses: int, rank: int, world: int, device=None, group=None):
+    """Collective set-up of the peer-memory exchange of the landmark part (one process per GPU of one
+    node): every rank computes the landmark range its pose shard touches, allocates its exchange region
+    and the CUDA IPC handles and ranges are gathered over the ranks.  Returns the gathered ranges."""
+    import numpy as np
+    lo, hi = shard_range(n_poses, rank, world)
+    l0, l1 = ctx.graph_shard_landmarks(lo, hi)
+    mine = np.array([l0, l1], dtype=np.int32)
+    ranges = np.frombuffer(gather_bytes(mine.tobytes(), world, device, group), dtype=np.int32).reshape(world, 2)
+    cap = int(max(1, (ranges[:, 1] - ranges[:, 0]).max()))
+    handle = ctx.xchg_create(world, rank, cap)
+    handles = gather_bytes(handle, world, device, group)
+    ctx.xchg_connect(handles, ranges)
+    return ranges
+
+
+def assemble_sharded(ctx, n_poses: int, rank: int, world: int, device=None, group=None, peer=False):
     """Edge-partitioned assembly of one large graph: this rank linearises the edges of its pose range,
-    then the landmark diagonal blocks and landmark rhs are summed over ranks (NCCL all-reduce over
-    NVLink).  The caller's stream must be the context's stream.  Returns the pose range."""
+    then the landmark diagonal blocks and landmark rhs are summed over ranks -- with an NCCL all-reduce
+    over NVLink, or (peer=True, after connect_peer_exchange) by the landmark kernel's own stores into
+    every rank's memory followed by a rank-ordered sum.  The caller's stream must be the context's
+    stream.  Returns the pose range."""
     import torch.distributed as dist
     lo, hi = shard_range(n_poses, rank, world)
+    if world > 1 and peer:
+        ctx.graph_assemble_exchange_async(lo, hi)
+        return lo, hi
     ctx.graph_assemble_async(lo, hi)
     if world > 1:
         t = landmark_part_tensor(ctx, device)

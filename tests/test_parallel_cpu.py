@@ -76,3 +76,37 @@ def test_edge_partitioned_reduction_world2_gloo(pkg):
         [p.join(120) for p in procs]
         assert all(p.exitcode == 0 for p in procs)
         assert dict(out) == {0: 1, 1: 1}
+
+
+def _gather_worker(rank, world, port, pkg_name, out):
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    par = importlib.import_module(pkg_name + ".parallel")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # what connect_peer_exchange gathers: fixed-size opaque handles and int32 landmark ranges, rank order
+    handle = bytes([(rank * 37 + k) % 256 for k in range(64)])
+    allh = par.gather_bytes(handle, world)
+    rng = np.array([100 * rank, 100 * rank + 130], dtype=np.int32)
+    allr = np.frombuffer(par.gather_bytes(rng.tobytes(), world), dtype=np.int32).reshape(world, 2)
+    ok = len(allh) == 64 * world and all(allh[64 * r:64 * (r + 1)] == bytes([(r * 37 + k) % 256 for k in range(64)])
+                                         for r in range(world))
+    ok = ok and allr.tolist() == [[100 * r, 100 * r + 130] for r in range(world)]
+    out[rank] = int(ok)
+    dist.destroy_process_group()
+
+
+def test_gather_bytes_world2_gloo(pkg):
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as m:
+        out = m.dict()
+        procs = [ctx.Process(target=_gather_worker, args=(r, world, port, pkg.__name__, out)) for r in range(world)]
+        [p.start() for p in procs]
+        [p.join(120) for p in procs]
+        assert all(p.exitcode == 0 for p in procs)
+        assert dict(out) == {0: 1, 1: 1}
