@@ -207,9 +207,10 @@ long slam_b200_graph_system_dev(slam_b200_ctx* ctx, int which, double** ptr);
  *                     landmarks and returns its 64-byte CUDA IPC handle;
  *   xchg_connect    : handles = world x 64 bytes, ranges = world x [l0,l1) (both gathered over ranks).
  * graph_assemble_exchange_async(p0,p1) then enqueues linearise + assemble of the shard with the
- * landmark kernel storing its partial blocks straight into every rank's region over NVLink, followed
- * by a kernel that waits for all ranks and sums the partials in rank order into the landmark part of
- * V -- every rank ends up with the complete landmark part, bit-identical on all ranks.
+ * landmark kernel writing its partial blocks into the rank's exported region and raising a flag in
+ * every peer's region, followed by a kernel that waits for all ranks and sums the partials in rank
+ * order, reading them straight from the peers' memory over NVLink, into the landmark part of V --
+ * every rank ends up with the complete landmark part, bit-identical on all ranks.
  * xchg_error: synchronises and returns 1 if a rank ever timed out waiting for a peer. */
 int slam_b200_graph_shard_landmarks(slam_b200_ctx* ctx, int p0, int p1, int32_t* l0, int32_t* l1);
 int slam_b200_xchg_create(slam_b200_ctx* ctx, int world, int rank, int cap, unsigned char handle_out[64]);

@@ -464,7 +464,7 @@ int slam_b200_xchg_create(slam_b200_ctx* c, int world, int rank, int cap, unsign
   xchg_release(D);
   PeerExchange& X = D.xchg;
   X.world = world; X.rank = rank; X.cap = cap;
-  X.bytes = 1024 + sizeof(double) * 2 * (size_t)world * 6 * (size_t)cap;
+  X.bytes = 1024 + sizeof(double) * 2 * 6 * (size_t)cap;
   SLAM_CUDA_TRY(c, cudaMalloc(&X.local, X.bytes));
   SLAM_CUDA_TRY(c, cudaMemset(X.local, 0, X.bytes));
   cudaIpcMemHandle_t h;

@@ -391,23 +391,24 @@ constexpr int LM_PER_BLOCK = ASM_THREADS / 32;
 
 // Peer exchange of the landmark part between the pose-range shards of ONE graph (config 5, one
 // process per GPU).  Every rank owns a region of device memory opened by all the others through
-// CUDA IPC: [world 64-bit flags | 2 parities x world slots of 6*cap doubles].  PEER mode of the
-// landmark kernel stores the partial block + rhs of every landmark of this shard's range straight into
-// slot[parity][rank] of EVERY rank (lane d of the warp writes to rank d over NVLink) -- the all-gather
-// rides on the kernel's own stores --, and the last CTA to finish publishes `epoch` in every rank's
-// flag word.  lm_exchange_sum_kernel then waits for all flags and sums the slots in rank order
-// (deterministic, unlike a ring all-reduce) into the landmark part of V.  Two parities: a rank can
-// start pushing assembly k+1 while a slower rank still sums assembly k; it cannot reach k+2 before
-// every rank has pushed k+1, i.e. finished summing k.
+// CUDA IPC: [world 64-bit flags | 2 parities x 6*cap doubles].  PEER mode of the landmark kernel
+// writes the partial block + rhs of every landmark of this shard's range into the rank's OWN slot
+// (b: 2 per landmark, then H: 4 per landmark) instead of V.  lm_exchange_sum_kernel, next on the
+// stream, publishes `epoch` in every rank's flag word (the only remote stores), waits for all flags
+// and PULLS: V[landmark part] = sum over ranks, ascending, of their slots, read straight
+// from the peers' memory over NVLink with unit-stride 16-byte loads (deterministic, unlike a ring
+// all-reduce; pushing 48-byte records from the landmark kernel's single writer lanes was measured
+// 2x slower than NCCL -- small remote stores do not fill NVLink packets).  Two parities: a rank can
+// start assembly k+1 while a slower rank still pulls assembly k from it; it cannot reach k+2 before
+// every rank has raised flag k+1, i.e. finished pulling k.
 constexpr int XCHG_HEADER = 1024;  // bytes reserved for the flags
 struct PeerArgs {
   char* const* peer_tab;  // region base of every rank (device array)
   int world, rank, cap, parity;
   unsigned long long epoch;
-  unsigned* done;         // CTA completion counter (this rank)
 };
-__device__ __forceinline__ double* xchg_slot(char* base, int world, int cap, int parity, int src) {
-  return reinterpret_cast<double*>(base + XCHG_HEADER) + ((size_t)parity * world + src) * 6 * (size_t)cap;
+__device__ __forceinline__ double* xchg_slot(char* base, int cap, int parity) {
+  return reinterpret_cast<double*>(base + XCHG_HEADER) + (size_t)parity * 6 * (size_t)cap;
 }
 
 template <bool CHI2_ONLY, bool UNROLL2, bool PEER>
@@ -420,9 +421,9 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
   const double* meas = a.meas + (size_t)r * a.measStride;
   double* V = a.V + (size_t)r * a.nV;
   const int P = a.P, L = a.L, El = a.El;
-  if (PEER && !CHI2_ONLY && l < l_end && !a.lm_free[l] && lane < px.world) {
-    // fixed / inactive landmark inside the range: its slot entries must read as zero on every rank
-    double* slot = xchg_slot(px.peer_tab[lane], px.world, px.cap, px.parity, px.rank);
+  if (PEER && !CHI2_ONLY && l < l_end && !a.lm_free[l] && lane == 0) {
+    // fixed / inactive landmark inside the range: its slot entries must read as zero
+    double* slot = xchg_slot(px.peer_tab[px.rank], px.cap, px.parity);
     const int k = l - l_first;
     slot[2 * k] = 0.0; slot[2 * k + 1] = 0.0;
     double* hs = slot + 2 * (size_t)px.cap + 4 * (size_t)k;
@@ -495,8 +496,8 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
       b1 += __shfl_xor_sync(0xffffffffu, b1, o);
     }
     if (PEER) {
-      if (lane < px.world) {  // the butterfly left the sums in every lane: lane d stores to rank d
-        double* slot = xchg_slot(px.peer_tab[lane], px.world, px.cap, px.parity, px.rank);
+      if (lane == 0) {
+        double* slot = xchg_slot(px.peer_tab[px.rank], px.cap, px.parity);
         const int k = l - l_first;
         *reinterpret_cast<double2*>(slot + 2 * (size_t)k) = make_double2(b0, b1);
         double2* hs = reinterpret_cast<double2*>(slot + 2 * (size_t)px.cap + 4 * (size_t)k);
@@ -508,20 +509,6 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
       bl[0] = b0; bl[1] = b1;
       double* hl = V + 2 * (size_t)L + 4 * (size_t)l;
       hl[0] = h00; hl[1] = h01; hl[2] = h01; hl[3] = h11;
-    }
-  }
-  if (PEER) {
-    // completion: every CTA makes its peer stores visible system-wide, the last one raises the flags
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      const unsigned total = gridDim.x * gridDim.y;
-      if (atomicAdd(px.done, 1u) == total - 1) {
-        *px.done = 0;
-        __threadfence_system();
-        for (int d = 0; d < px.world; d++)
-          reinterpret_cast<volatile unsigned long long*>(px.peer_tab[d])[px.rank] = px.epoch;
-      }
     }
   }
   // final chi2 of this replica: fixed-order sum of the pose kernel's block partials
@@ -539,12 +526,19 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
 // V[landmark part] = sum over ranks (ascending) of their partial blocks.  A rank that never arrives
 // (a peer died) is reported through *err after `timeout_ns` instead of hanging the GPU.
 __global__ void __launch_bounds__(256)
-lm_exchange_sum_kernel(char* local, int world, int cap, int parity, unsigned long long epoch,
-                       const int* __restrict__ ranges, int L, double* __restrict__ V, int* err,
-                       unsigned long long timeout_ns) {
+lm_exchange_sum_kernel(char* const* __restrict__ peer_tab, int world, int rank, int cap, int parity,
+                       unsigned long long epoch, const int* __restrict__ ranges, int L, double* __restrict__ V,
+                       int* err, unsigned long long timeout_ns) {
   __shared__ int go;
+  // This kernel follows the landmark kernel on the stream, so the rank's slot is complete: CTA 0
+  // publishes `epoch` in every rank's flag word (the only remote stores of the exchange; all CTAs of
+  // this grid are resident at once, so CTA 0 cannot be starved by the spinning ones).
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    reinterpret_cast<volatile unsigned long long*>(peer_tab[threadIdx.x])[rank] = epoch;
+  }
   if (threadIdx.x == 0) {
-    const volatile unsigned long long* flags = reinterpret_cast<const volatile unsigned long long*>(local);
+    const volatile unsigned long long* flags = reinterpret_cast<const volatile unsigned long long*>(peer_tab[rank]);
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     int ok = 1;
@@ -555,7 +549,7 @@ lm_exchange_sum_kernel(char* local, int world, int cap, int parity, unsigned lon
       }
     }
     if (!ok) *err = 1;
-    __threadfence_system();
+    __threadfence();
     go = ok;
   }
   __syncthreads();
@@ -566,7 +560,7 @@ lm_exchange_sum_kernel(char* local, int world, int cap, int parity, unsigned lon
   for (int s = 0; s < world; s++) {
     const int l0 = ranges[2 * s], l1 = ranges[2 * s + 1];
     if (l < l0 || l >= l1) continue;
-    const double* slot = xchg_slot(local, world, cap, parity, s);
+    const double* slot = xchg_slot(peer_tab[s], cap, parity);  // remote for s != rank: read over NVLink
     const int k = l - l0;
     const double2 b = __ldcg(reinterpret_cast<const double2*>(slot + 2 * (size_t)k));
     const double2* hs = reinterpret_cast<const double2*>(slot + 2 * (size_t)cap + 4 * (size_t)k);
@@ -694,7 +688,7 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, boo
       return SLAM_B200_E_ARG;  // the pose range differs from the one the exchange was connected for
     X.epoch++;
     px.peer_tab = X.peer_tab.p; px.world = X.world; px.rank = X.rank; px.cap = X.cap;
-    px.parity = (int)(X.epoch & 1); px.epoch = X.epoch; px.done = X.done.p;
+    px.parity = (int)(X.epoch & 1); px.epoch = X.epoch;
   } else if (!chi2_only && (p0 > 0 || p1 < D.P) && D.R == 1) {
     graph_shard_landmarks(D, p0, p1, &l_first, &l_end);
     SLAM_CUDA_TRY(c, cudaMemsetAsync(D.V.p, 0, sizeof(double) * 6 * (size_t)D.L, c->stream));
@@ -711,8 +705,8 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, boo
   c->launches++;
   if (peer) {
     PeerExchange& X = D.xchg;
-    lm_exchange_sum_kernel<<<(D.L + 255) / 256, 256, 0, c->stream>>>(X.local, X.world, X.cap, px.parity, X.epoch, X.ranges.p,
-                                                                   D.L, D.V.p, X.err.p, 200000000ull);
+    lm_exchange_sum_kernel<<<(D.L + 255) / 256, 256, 0, c->stream>>>(X.peer_tab.p, X.world, X.rank, X.cap, px.parity, X.epoch,
+                                                                   X.ranges.p, D.L, D.V.p, X.err.p, 200000000ull);
     c->launches++;
   }
   SLAM_CUDA_TRY(c, cudaGetLastError());

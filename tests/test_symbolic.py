@@ -120,8 +120,12 @@ for k in ("pos", "boff", "level_ptr", "npiv", "nupd", "parent", "rel", "asm"):
 print("HASH", h.hexdigest(), int(S.nnzL))
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     seen = set()
-    for threads in ("1", "2", "7"):
+    # ... nor on which minimum-degree implementation ran (dense bit matrix vs sorted adjacency lists)
+    for threads, sparse in (("1", None), ("2", None), ("7", None), ("3", "1")):
         env = dict(os.environ, SLAM_B200_SYM_THREADS=threads)
+        env.pop("SLAM_B200_MD_SPARSE", None)
+        if sparse:
+            env["SLAM_B200_MD_SPARSE"] = sparse
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
         seen.add([ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][0])
