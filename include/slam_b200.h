@@ -233,6 +233,7 @@ int slam_b200_profile_read(slam_b200_ctx* ctx, double out[8]);
  * of children).  Only recorded when SLAM_B200_PHASE_CLOCKS is set in the environment at prepare time. */
 int slam_b200_debug_phase_clocks(slam_b200_ctx* ctx, long long out[10]);
 int slam_b200_debug_tiny_clocks(slam_b200_ctx* ctx, long long out[8]);
+int slam_b200_debug_panel_clocks(slam_b200_ctx* ctx, long long out[8]);
 /* Measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator for the solve). */
 int slam_b200_fp64_peak(slam_b200_ctx* ctx, double* tflops);
 

@@ -672,6 +672,18 @@ int slam_b200_debug_tiny_clocks(slam_b200_ctx* c, long long out[8]) {
   return 0;
 }
 
+// Debug: cycles of thread 0 of the same CTA accumulated over the panels of its front (same switch):
+// out[0..5] = triangle (warp 0), wait, row elimination, wait, trailing update, wait; out[6..7] = fused
+// forward: warp-0 triangle solve, rest of the panel step.  Accumulates over launches until re-prepared.
+int slam_b200_debug_panel_clocks(slam_b200_ctx* c, long long out[8]) {
+  if (!c || !c->sys || !out || !c->sys->dbg_clocks.p) return SLAM_B200_E_STATE;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpy(out, c->sys->dbg_clocks.p + 24, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+  SLAM_CUDA_TRY(c, cudaMemset(c->sys->dbg_clocks.p + 24, 0, sizeof(long long) * 8));
+  return 0;
+}
+
 // ---- symbolic analysis without a device (host logic; testable on a CPU-only box) ----------------
 struct SymHandle {
   Symbolic S;

@@ -41,6 +41,7 @@ struct AsmArgs {
   const unsigned char* pose_free;
   const unsigned char* lm_free;
   const int *el_start, *el_pose, *el_lm, *el_slot, *el_flags;
+  const int4* el_rec;
   const double* el_info;
   const int *lm_start, *lm_edges, *lmo_pose;
   const double* lmo_info;
@@ -55,6 +56,7 @@ struct AsmArgs {
 };
 
 constexpr int ASM_THREADS = 128;
+constexpr int ASM_DEFAULT_VARIANT = 24;  // see graph_enqueue_assemble
 
 // Pose-centred assembly, one WARP per 32 consecutive poses ("warp-aggregated block scatter"):
 //  * the landmark edges of those poses are one contiguous range of the pose-sorted edge arrays, so
@@ -382,6 +384,346 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
   }
 }
 
+// ---- pipelined variant of the pose-centred assembly -------------------------------------------------
+// Same decomposition and the same arithmetic, operation for operation, as assemble_pose_kernel
+// <false, true> (so V is bit-identical), but the loads are restructured.  ncu on the kernel above:
+// 66 % of warp time is long_scoreboard spread over FOUR dependent load sites per 32-edge step
+// (flags -> landmark index / information / measurement -> landmark estimate -> slot), at 24 warps/SM;
+// no resource is saturated, the step is a chain of exposed round trips.  Here
+//  * the four ints of an edge are one 16-byte record (one load instead of four, and no load sits
+//    behind a branch on the flags of another);
+//  * the pose_free test of the edge loop is a ballot mask in a register;
+//  * DEPTH 1: the record + payload of step k+1 are loaded at the top of step k and the landmark
+//    estimate of step k+1 is gathered at its bottom: one exposed round trip per step instead of four;
+//    DEPTH 2: records run two steps ahead, so the gather of step k+1 is issued at the top of step k
+//    too and no load of the steady state is exposed;
+//  * the pose-pose epilogue loads the incidence entries of a pose two at a time (a trackdrive pose
+//    has exactly two: its odometry edges) with the dependent index loads of both in flight together,
+//    and reads the sin/cos of a neighbour inside the warp's pose range from the shared-memory cache.
+struct ElPay { double i00, i01, i11, m0, m1; };
+
+template <int DEPTH, int MINB>
+__global__ void __launch_bounds__(ASM_THREADS, MINB)
+assemble_pose_pipe_kernel(AsmArgs a, int p0, int p1) {
+  __shared__ double s_pose[ASM_WARPS][4][32];
+  __shared__ double s_acc[ASM_WARPS][9][32];
+  __shared__ double s_o[ASM_WARPS][288];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.y;
+  const double* __restrict__ est = a.est + (size_t)r * a.estStride;
+  const double* __restrict__ meas = a.meas + (size_t)r * a.measStride;
+  double* V = a.V + (size_t)r * a.nV;
+  const int P = a.P, L = a.L, El = a.El, Eo = a.Eo;
+  const int pw0 = p0 + (blockIdx.x * ASM_WARPS + wid) * 32;
+  const int p = pw0 + lane;
+  double chi = 0;
+  double px = 0, py = 0, pt = 0, s = 0, c = 1;
+  bool free = false;
+  int q0 = 0, q1 = 0;
+  if (p < p1) {
+    px = est[p]; py = est[P + p]; pt = est[2 * P + p];
+    free = a.pose_free[p] != 0;
+    q0 = a.po_start[p]; q1 = a.po_start[p + 1];
+    sincos(pt, &s, &c);
+    double* trig = a.trig + (size_t)r * 2 * P;
+    trig[p] = s;
+    trig[P + p] = c;
+  }
+  const unsigned freemask = __ballot_sync(0xffffffffu, free);
+  s_pose[wid][0][lane] = px; s_pose[wid][1][lane] = py; s_pose[wid][2][lane] = s; s_pose[wid][3][lane] = c;
+#pragma unroll
+  for (int k = 0; k < 9; k++) s_acc[wid][k][lane] = 0.0;
+  __syncwarp();
+  if (pw0 < p1) {  // warp-uniform
+    const int pw1 = min(pw0 + 32, p1);
+    const int e_begin = a.el_start[pw0], e_end = a.el_start[pw1];
+    const double* __restrict__ inf0 = a.el_info;
+    const double* __restrict__ inf1 = a.el_info + El;
+    const double* __restrict__ inf2 = a.el_info + 2 * (size_t)El;
+    const double* __restrict__ elx = est + 3 * (size_t)P;
+    const double* __restrict__ ely = est + 3 * (size_t)P + L;
+    auto ld_ix = [&](int e) -> int4 {  // idle lanes: unique pose key, flags 0
+      return e < e_end ? __ldg(a.el_rec + e) : make_int4(pw0 - 1 - lane, 0, 0, 0);
+    };
+    auto ld_pay = [&](int e) -> ElPay {
+      ElPay y = {0, 0, 0, 0, 0};
+      if (e < e_end) {
+        y.i00 = __ldg(inf0 + e); y.i01 = __ldg(inf1 + e); y.i11 = __ldg(inf2 + e);
+        y.m0 = __ldg(meas + e); y.m1 = __ldg(meas + El + e);
+      }
+      return y;
+    };
+    auto ld_est = [&](const int4& ix) -> double2 {
+      double2 v = make_double2(0, 0);
+      if (ix.w & EF_ACTIVE) { v.x = elx[ix.y]; v.y = ely[ix.y]; }
+      return v;
+    };
+    int4 ixA = ld_ix(e_begin + lane);
+    int4 ixB = make_int4(0, 0, 0, 0);
+    ElPay payA = ld_pay(e_begin + lane);
+    if (DEPTH >= 2) ixB = ld_ix(e_begin + 32 + lane);
+    double2 estA = ld_est(ixA);
+    for (int base = e_begin; base < e_end; base += 32) {
+      // ---- loads of the coming steps, issued before anything of this step is used ----
+      int4 ixC = make_int4(0, 0, 0, 0);
+      ElPay payB = {0, 0, 0, 0, 0};
+      double2 estB = make_double2(0, 0);
+      if (DEPTH == 1) { ixB = ld_ix(base + 32 + lane); payB = ld_pay(base + 32 + lane); }
+      if (DEPTH >= 2) { ixC = ld_ix(base + 64 + lane); payB = ld_pay(base + 32 + lane); estB = ld_est(ixB); }
+      // ---- this step ----
+      const bool valid = base + lane < e_end;
+      const int fl = ixA.w;
+      const int pl = ixA.x - pw0;
+      double v[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) v[k] = 0.0;
+      double o[6];
+      int slot = 0;
+      bool wr = false;
+      const bool pfree = valid && ((freemask >> (pl & 31)) & 1u);
+      if (valid && (fl & EF_ACTIVE)) {
+        const double qx = s_pose[wid][0][pl], qy = s_pose[wid][1][pl], qs = s_pose[wid][2][pl], qc = s_pose[wid][3][pl];
+        const double dx = estA.x - qx, dy = estA.y - qy;
+        const double i00 = payA.i00, i01 = payA.i01, i11 = payA.i11;
+        const double j02 = -qs * dx + qc * dy;
+        const double j12 = -qc * dx - qs * dy;
+        const double ex = qc * dx + qs * dy - payA.m0;
+        const double ey = j02 - payA.m1;
+        chi += ex * (i00 * ex + i01 * ey) + ey * (i01 * ex + i11 * ey);
+        if (pfree) {
+          const double a00 = -qc * i00 + qs * i01, a01 = -qc * i01 + qs * i11;
+          const double a10 = -qs * i00 - qc * i01, a11 = -qs * i01 - qc * i11;
+          const double a20 = j02 * i00 + j12 * i01, a21 = j02 * i01 + j12 * i11;
+          v[6] = -(a00 * ex + a01 * ey);
+          v[7] = -(a10 * ex + a11 * ey);
+          v[8] = -(a20 * ex + a21 * ey);
+          v[0] = a00 * (-qc) + a01 * qs;
+          v[1] = a00 * (-qs) + a01 * (-qc);
+          v[2] = a00 * j02 + a01 * j12;
+          v[3] = a10 * (-qs) + a11 * (-qc);
+          v[4] = a10 * j02 + a11 * j12;
+          v[5] = a20 * j02 + a21 * j12;
+          if (fl & EF_OFFDIAG) {
+            const double B[6] = {a00 * qc - a01 * qs, a00 * qs + a01 * qc, a10 * qc - a11 * qs,
+                                 a10 * qs + a11 * qc, a20 * qc - a21 * qs, a20 * qs + a21 * qc};
+            slot = ixA.z;
+            if (fl & EF_TRANS) {
+              o[0] = B[0]; o[1] = B[2]; o[2] = B[4]; o[3] = B[1]; o[4] = B[3]; o[5] = B[5];
+            } else {
+#pragma unroll
+              for (int k = 0; k < 6; k++) o[k] = B[k];
+            }
+            wr = (fl & EF_FIRST) != 0;
+          }
+        }
+      }
+      {
+        const int nvalid = min(32, e_end - base);
+        const int slot0 = __shfl_sync(0xffffffffu, slot, 0);
+        const bool contig = __all_sync(0xffffffffu, !valid || (wr && slot == slot0 + 6 * lane));
+        if (contig) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) s_o[wid][6 * lane + k] = o[k];
+          __syncwarp();
+          double* hv = V + slot0;
+#pragma unroll
+          for (int j = 0; j < 6; j++) {
+            const int q = j * 32 + lane;
+            if (q < 6 * nvalid) hv[q] = s_o[wid][q];
+          }
+          __syncwarp();
+        } else if (wr) {
+          double* hv = V + slot;
+#pragma unroll
+          for (int k = 0; k < 6; k++) hv[k] = o[k];
+        }
+      }
+      unsigned dup = __ballot_sync(0xffffffffu, valid && (fl & EF_ACTIVE) && (fl & EF_OFFDIAG) && !(fl & EF_FIRST) && pfree);
+      while (dup) {
+        __syncwarp();
+        const int src = __ffs(dup) - 1;
+        if (lane == src) {
+          double* hv = V + slot;
+#pragma unroll
+          for (int k = 0; k < 6; k++) hv[k] += o[k];
+        }
+        dup &= dup - 1;
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int plo = __shfl_up_sync(0xffffffffu, pl, d);
+        const bool take = lane >= d && plo == pl;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          const double t = __shfl_up_sync(0xffffffffu, v[k], d);
+          if (take) v[k] += t;
+        }
+      }
+      const int pln = __shfl_down_sync(0xffffffffu, pl, 1);
+      if (valid && (lane == 31 || pln != pl)) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) s_acc[wid][k][pl] += v[k];
+      }
+      __syncwarp();
+      // ---- rotate the pipeline ----
+      if (DEPTH == 0) { ixA = ld_ix(base + 32 + lane); payA = ld_pay(base + 32 + lane); estA = ld_est(ixA); }
+      if (DEPTH == 1) { ixA = ixB; payA = payB; estA = ld_est(ixA); }
+      if (DEPTH >= 2) { ixA = ixB; ixB = ixC; payA = payB; estA = estB; }
+    }
+  }
+  double fb[3] = {0, 0, 0}, fh[6] = {0, 0, 0, 0, 0, 0};
+  if (p < p1) {
+    double h00 = s_acc[wid][0][lane], h01 = s_acc[wid][1][lane], h02 = s_acc[wid][2][lane];
+    double h11 = s_acc[wid][3][lane], h12 = s_acc[wid][4][lane], h22 = s_acc[wid][5][lane];
+    double b0 = s_acc[wid][6][lane], b1 = s_acc[wid][7][lane], b2 = s_acc[wid][8][lane];
+    const double* __restrict__ mo = meas + 2 * (size_t)El;
+    // one pose-pose edge; (xo, yo, to) is the OTHER pose of the edge
+    auto po_edge = [&](int e, int side, int fl, int i, int j, int eslot, double xo, double yo, double to) {
+      double xi, yi, ti, xj, yj, tj, si, ci;
+      if (side == 0) {
+        xi = px; yi = py; ti = pt; si = s; ci = c;
+        xj = xo; yj = yo; tj = to;
+      } else {
+        xj = px; yj = py; tj = pt;
+        xi = xo; yi = yo; ti = to;
+        const int il = i - pw0;
+        if (il >= 0 && il < 32 && i < p1) { si = s_pose[wid][2][il]; ci = s_pose[wid][3][il]; }  // same sincos(ti), cached
+        else sincos(ti, &si, &ci);
+      }
+      const double zx = mo[e], zy = mo[Eo + e], zt = mo[2 * Eo + e];
+      const double o00 = a.eo_info[e], o01 = a.eo_info[Eo + e], o02 = a.eo_info[2 * Eo + e],
+                   o11 = a.eo_info[3 * Eo + e], o12 = a.eo_info[4 * Eo + e], o22 = a.eo_info[5 * Eo + e];
+      const double dtx = xj - xi, dty = yj - yi;
+      const double tx = ci * dtx + si * dty, ty = -si * dtx + ci * dty;
+      double sz, cz;
+      sincos(zt, &sz, &cz);
+      double err[3];
+      err[0] = cz * (tx - zx) + sz * (ty - zy);
+      err[1] = -sz * (tx - zx) + cz * (ty - zy);
+      err[2] = normalize_theta_dev(tj - ti - zt);
+      const double Om[3][3] = {{o00, o01, o02}, {o01, o11, o12}, {o02, o12, o22}};
+      double Oe[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) Oe[k] = Om[k][0] * err[0] + Om[k][1] * err[1] + Om[k][2] * err[2];
+      if (side == 0) chi += err[0] * Oe[0] + err[1] * Oe[1] + err[2] * Oe[2];
+      const double A0[3] = {-ci, -si, ty}, A1[3] = {si, -ci, -tx};
+      const double B0[3] = {ci, si, 0}, B1[3] = {-si, ci, 0};
+      double Ji[3][3], Jj[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        Ji[0][k] = cz * A0[k] + sz * A1[k];
+        Ji[1][k] = -sz * A0[k] + cz * A1[k];
+        Jj[0][k] = cz * B0[k] + sz * B1[k];
+        Jj[1][k] = -sz * B0[k] + cz * B1[k];
+      }
+      Ji[2][0] = 0; Ji[2][1] = 0; Ji[2][2] = -1;
+      Jj[2][0] = 0; Jj[2][1] = 0; Jj[2][2] = 1;
+      if (free) {
+        double AtO[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+            double jm0 = side == 0 ? Ji[0][k] : Jj[0][k];
+            double jm1 = side == 0 ? Ji[1][k] : Jj[1][k];
+            double jm2 = side == 0 ? Ji[2][k] : Jj[2][k];
+            AtO[k][m] = jm0 * Om[0][m] + jm1 * Om[1][m] + jm2 * Om[2][m];
+          }
+        b0 -= AtO[0][0] * err[0] + AtO[0][1] * err[1] + AtO[0][2] * err[2];
+        b1 -= AtO[1][0] * err[0] + AtO[1][1] * err[1] + AtO[1][2] * err[2];
+        b2 -= AtO[2][0] * err[0] + AtO[2][1] * err[1] + AtO[2][2] * err[2];
+        double Hm[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = k; m < 3; m++) {
+            double vv = 0;
+#pragma unroll
+            for (int t = 0; t < 3; t++) vv += AtO[k][t] * (side == 0 ? Ji[t][m] : Jj[t][m]);
+            Hm[k][m] = vv;
+          }
+        h00 += Hm[0][0]; h01 += Hm[0][1]; h02 += Hm[0][2];
+        h11 += Hm[1][1]; h12 += Hm[1][2]; h22 += Hm[2][2];
+      }
+      if ((fl & EF_OFFDIAG) && p == min(i, j)) {
+        double AtO[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = 0; m < 3; m++)
+            AtO[k][m] = Ji[0][k] * Om[0][m] + Ji[1][k] * Om[1][m] + Ji[2][k] * Om[2][m];
+        double* hv = V + eslot;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+            double vv = AtO[k][0] * Jj[0][m] + AtO[k][1] * Jj[1][m] + AtO[k][2] * Jj[2][m];
+            int oo = (fl & EF_TRANS) ? (m * 3 + k) : (k * 3 + m);
+            if (fl & EF_FIRST) hv[oo] = vv;
+            else hv[oo] += vv;
+          }
+      }
+    };
+    for (int q = q0; q < q1; q += 2) {
+      const bool two = q + 1 < q1;
+      const int entA = a.po_list[q], entB = two ? a.po_list[q + 1] : 0;
+      const int eA = entA >> 1, sideA = entA & 1, eB = entB >> 1, sideB = entB & 1;
+      const int flA = a.eo_flags[eA], iA = a.eo_i[eA], jA = a.eo_j[eA], slA = a.eo_slot[eA];
+      int flB = 0, iB = 0, jB = 0, slB = 0;
+      if (two) { flB = a.eo_flags[eB]; iB = a.eo_i[eB]; jB = a.eo_j[eB]; slB = a.eo_slot[eB]; }
+      const int oA = sideA == 0 ? jA : iA, oB = sideB == 0 ? jB : iB;
+      const double xA = est[oA], yA = est[P + oA], tA = est[2 * P + oA];
+      double xB = 0, yB = 0, tB = 0;
+      if (two) { xB = est[oB]; yB = est[P + oB]; tB = est[2 * P + oB]; }
+      if (flA & EF_ACTIVE) po_edge(eA, sideA, flA, iA, jA, slA, xA, yA, tA);
+      if (two && (flB & EF_ACTIVE)) po_edge(eB, sideB, flB, iB, jB, slB, xB, yB, tB);
+    }
+    fb[0] = b0; fb[1] = b1; fb[2] = b2; fh[0] = h00; fh[1] = h01; fh[2] = h02; fh[3] = h11; fh[4] = h12; fh[5] = h22;
+  }
+  if (pw0 < p1) {  // warp-uniform
+    const int np = min(32, p1 - pw0);
+    const bool allfree = __all_sync(0xffffffffu, p >= p1 || free);
+    if (allfree) {
+      double* bp = V + 6 * (size_t)L + 3 * (size_t)pw0;
+      double* hp = V + 6 * (size_t)L + 3 * (size_t)P + 9 * (size_t)pw0;
+      s_o[wid][3 * lane] = fb[0]; s_o[wid][3 * lane + 1] = fb[1]; s_o[wid][3 * lane + 2] = fb[2];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int q = j * 32 + lane;
+        if (q < 3 * np) bp[q] = s_o[wid][q];
+      }
+      __syncwarp();
+      double* so = &s_o[wid][9 * lane];
+      so[0] = fh[0]; so[1] = fh[1]; so[2] = fh[2];
+      so[3] = fh[1]; so[4] = fh[3]; so[5] = fh[4];
+      so[6] = fh[2]; so[7] = fh[4]; so[8] = fh[5];
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const int q = j * 32 + lane;
+        if (q < 9 * np) hp[q] = s_o[wid][q];
+      }
+    } else if (p < p1 && free) {
+      double* bp = V + 6 * (size_t)L + 3 * (size_t)p;
+      bp[0] = fb[0]; bp[1] = fb[1]; bp[2] = fb[2];
+      double* hp = V + 6 * (size_t)L + 3 * (size_t)P + 9 * (size_t)p;
+      hp[0] = fh[0]; hp[1] = fh[1]; hp[2] = fh[2];
+      hp[3] = fh[1]; hp[4] = fh[3]; hp[5] = fh[4];
+      hp[6] = fh[2]; hp[7] = fh[4]; hp[8] = fh[5];
+    }
+  }
+  __shared__ double red[ASM_THREADS / 32];
+  for (int o = 16; o; o >>= 1) chi += __shfl_down_sync(0xffffffffu, chi, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = chi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < ASM_THREADS / 32; w++) t += red[w];
+    a.chi2_part[(size_t)r * a.chi2_blocks + blockIdx.x] = t;
+  }
+}
+
 // one WARP per landmark: diagonal block + rhs over the edges (with pose in [p0,p1)) that see it.
 // A landmark is seen from tens to hundreds of poses (24 per lap on the trackdrive), so the edge list
 // is strided over the lanes and the five partial sums are combined with a fixed xor-shuffle tree
@@ -661,7 +1003,7 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, boo
   a.est = D.est.p; a.meas = D.meas.p; a.V = D.V.p;
   a.pose_free = D.pose_free.p; a.lm_free = D.lm_free.p;
   a.el_start = D.el_start.p; a.el_pose = D.el_pose.p; a.el_lm = D.el_lm.p; a.el_slot = D.el_slot.p;
-  a.el_flags = D.el_flags.p; a.el_info = D.el_info.p;
+  a.el_flags = D.el_flags.p; a.el_info = D.el_info.p; a.el_rec = D.el_rec.p;
   a.lm_start = D.lm_start.p; a.lm_edges = D.lm_edges.p; a.lmo_pose = D.lmo_pose.p; a.lmo_info = D.lmo_info.p;
   a.trig = D.trig.p;
   a.eo_i = D.eo_i.p; a.eo_j = D.eo_j.p; a.eo_slot = D.eo_slot.p; a.eo_flags = D.eo_flags.p;
@@ -673,7 +1015,19 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, boo
   if (nblk > 0) {
     dim3 grid(nblk, D.R);
     if (chi2_only) assemble_pose_kernel<true, false><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
-    else assemble_pose_kernel<false, true><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1);
+    else {
+      // SLAM_B200_ASM_VARIANT = 10 * depth + minBlocksPerSM selects a pipelined variant (default 24);
+      // 0 = the original kernel (kept for A/B measurements: profiles/tools/asm_ab.py).  Measured on
+      // B200 (profiles/r01_asm_ab.log): config 5 0.562 -> 0.484 ms, config 3 x 2,048 0.943 -> 0.882 ms;
+      // the variants capped at 80 registers (minBlocksPerSM 6) spill and are slower than the original.
+      const char* ev = getenv("SLAM_B200_ASM_VARIANT");  // read per call: the A/B tool switches it inside one process
+      const int variant = ev ? atoi(ev) : ASM_DEFAULT_VARIANT;
+      switch (variant) {
+        case 14: assemble_pose_pipe_kernel<1, 4><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1); break;
+        case 24: assemble_pose_pipe_kernel<2, 4><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1); break;
+        default: assemble_pose_kernel<false, true><<<grid, ASM_THREADS, 0, c->stream>>>(a, p0, p1); break;
+      }
+    }
     c->launches++;
   }
   // landmarks touched by this pose range (a shard of a large graph sees a small, contiguous-ish part
@@ -947,7 +1301,7 @@ int graph_build_structure(slam_b200_ctx* c) {
     std::vector<int> small, big;
     for (int f = S.level_ptr[lv]; f < S.level_ptr[lv + 1]; f++) {
       size_t fs = (size_t)S.npiv[f] + S.nupd[f];
-      size_t need = fs * fs * sizeof(double);
+      size_t need = fs * (fs + 1) * sizeof(double);  // + the right-hand-side row (solver.cu: factor2_kernel)
       LL.max_fs = std::max(LL.max_fs, (int)fs);
       if (fs <= 64 && need <= smem_limit) {
         launch_list.push_back(f);
@@ -960,7 +1314,7 @@ int graph_build_structure(slam_b200_ctx* c) {
       } else {
         big.push_back(f);
         fbig[f] = D.nFbig;
-        D.nFbig += (long)(fs * fs);
+        D.nFbig += (long)(fs * (fs + 1));
       }
       size_t sneed = (fs * S.npiv[f] + fs) * sizeof(double);
       LL.smem_solve = std::max(LL.smem_solve, std::min(sneed, smem_limit));
@@ -1036,6 +1390,9 @@ int graph_build_structure(slam_b200_ctx* c) {
   rc |= upload_vec(c, D.el_lm, s_lm);
   rc |= upload_vec(c, D.el_slot, s_slot);
   rc |= upload_vec(c, D.el_flags, s_flags);
+  std::vector<int4> el_rec_h(El);  // lives until flush_uploads below (uploads are deferred)
+  for (int q = 0; q < El; q++) el_rec_h[q] = make_int4(s_pose[q], s_lm[q], s_slot[q], s_flags[q]);
+  rc |= upload_vec(c, D.el_rec, el_rec_h);
   rc |= upload_vec(c, D.el_info, s_info);
   rc |= upload_vec(c, D.lm_start, lm_start);
   rc |= upload_vec(c, D.lm_edges, lm_edges);
@@ -1169,6 +1526,7 @@ void graph_release(slam_b200_ctx* c) {
   DeviceSystem& D = *c->sys;
   D.pose_free.release(); D.lm_free.release(); D.pose_boff.release(); D.lm_boff.release();
   D.el_start.release(); D.el_pose.release(); D.el_lm.release(); D.el_slot.release(); D.el_flags.release();
+  D.el_rec.release();
   D.el_info.release(); D.lm_start.release(); D.lm_edges.release();
   D.eo_i.release(); D.eo_j.release(); D.eo_slot.release(); D.eo_flags.release(); D.po_start.release();
   D.po_list.release(); D.eo_info.release();

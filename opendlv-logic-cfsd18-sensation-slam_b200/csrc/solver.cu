@@ -112,9 +112,13 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   double* Sp = reinterpret_cast<double*>(srel + ((fs + 1) & ~1));
   double* dinv = Sp + (size_t)NB * fs;  // 1/d of every pivot (s doubles), then w (fs) for the fused forward solve
   double* Tsm = dinv + 2 * (size_t)fs;   // current panel: NB x NB triangle + NB reciprocals, then NB forward values
+  const bool dbgc = S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;  // finer clocks, thread 0 (in warp 0)
+  long long dt_ = 0;
+  if (dbgc) for (int k = 24; k < 32; k++) S.dbg[k] = 0;  // like the stamps: the last launch (the root) wins
   for (int k0 = 0; k0 < s; k0 += NB) {
     const int nb = min(NB, s - k0);
     double* Pk = F + (size_t)k0 * fs;  // panel columns: Pk[p * fs + row]
+    if (dbgc) dt_ = clock64();
     // ---- (1a) warp 0 factorises the NB x NB diagonal triangle in registers (a dependent chain of
     // 8 reciprocals: one warp, not sixteen, pays its instruction stream) and publishes the final
     // triangle + reciprocals of the pivots in shared memory
@@ -151,7 +155,9 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
         }
       }
     }
+    if (dbgc) { const long long t_ = clock64(); S.dbg[24] += t_ - dt_; dt_ = t_; }
     __syncthreads();
+    if (dbgc) { const long long t_ = clock64(); S.dbg[25] += t_ - dt_; dt_ = t_; }
     // ---- (1b) one thread per row below the triangle eliminates that row's panel entries ----
     double invd[NB];
 #pragma unroll
@@ -178,7 +184,9 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
           if (p < nb) Pk[p * fs + i] = rr[p];
       }
     }
+    if (dbgc) { const long long t_ = clock64(); S.dbg[26] += t_ - dt_; dt_ = t_; }
     __syncthreads();
+    if (dbgc) { const long long t_ = clock64(); S.dbg[27] += t_ - dt_; dt_ = t_; }
     // ---- (2) trailing update ----
     const int c0 = k0 + nb;
     for (int jg = c0 + 4 * warp; jg < fs; jg += 4 * nw) {
@@ -214,7 +222,9 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
         }
       }
     }
+    if (dbgc) { const long long t_ = clock64(); S.dbg[28] += t_ - dt_; dt_ = t_; }
     __syncthreads();
+    if (dbgc) { const long long t_ = clock64(); S.dbg[29] += t_ - dt_; dt_ = t_; }
   }
   if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[4] = clock64();
   // ---- fused forward solve of this front (L y = b, z = D^-1 y): the factor is still in shared
@@ -236,6 +246,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
       const int nb = min(NB, s - k0);
       const double* Pk = F + (size_t)k0 * fs;
       double* ysm = Tsm + NB * NB + NB;  // NB forward values of this panel (z = y / d)
+      if (dbgc) dt_ = clock64();
       if (warp == 0) {
         double yd[NB];
 #pragma unroll
@@ -257,6 +268,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
           }
         }
       }
+      if (dbgc) { const long long t_ = clock64(); S.dbg[30] += t_ - dt_; dt_ = t_; }
       __syncthreads();
       for (int i = k0 + nb + tid; i < fs; i += nt) {
         double acc = w[i];
@@ -266,6 +278,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
         w[i] = acc;
       }
       __syncthreads();
+      if (dbgc) { const long long t_ = clock64(); S.dbg[31] += t_ - dt_; dt_ = t_; }
     }
     double* uo = uvec_all + (size_t)r * nUvec + S.rows_ptr[g];
     for (int i = s + tid; i < fs; i += nt) uo[i - s] = w[i];
@@ -289,6 +302,307 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
   __syncthreads();
   if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) S.dbg[6] = clock64();
   if (S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { S.dbg[7] = s; S.dbg[8] = fs; S.dbg[9] = S.child_ptr[g + 1] - S.child_ptr[g]; }
+}
+
+// LDL^T of one NB x NB diagonal triangle held (redundantly) in the registers of every lane of a warp;
+// publishes the factorised triangle (unscaled: t_qp = l_qp d_p, d on the diagonal) and the reciprocals
+// of the pivots to Tout[NB*NB + NB].  All lanes store the same values to the same addresses (one
+// wavefront per store, no lane predicate, no select chains).  Returns true on a zero / non-finite pivot
+// (SimplicialCholesky_impl.h:175-179).  Rows/columns >= nb are identity padding.
+__device__ __forceinline__ bool factor_triangle(const double* src, int sq, int sp, double* Tout, int nb) {
+  bool bad = false;
+  double T[NB][NB], iv[NB];  // entry (q, p) of the input at src[q * sq + p * sp]
+  // rectangular loops with compile-time guards: triangular bounds keep the unroller from scalarising T
+#pragma unroll
+  for (int p = 0; p < NB; p++)
+#pragma unroll
+    for (int q = 0; q < NB; q++)
+      if (q >= p) T[q][p] = (q < nb) ? src[q * sq + p * sp] : (q == p ? 1.0 : 0.0);
+#pragma unroll
+  for (int p = 0; p < NB; p++) {
+    const double d = T[p][p];
+    if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;
+    iv[p] = __drcp_rn(d);
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+      if (q > p) {
+        const double lqp = T[q][p] * iv[p];
+#pragma unroll
+        for (int q2 = 0; q2 < NB; q2++)
+          if (q2 >= q) T[q2][q] -= T[q2][p] * lqp;
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NB; p++) {
+    Tout[NB * NB + p] = iv[p];
+#pragma unroll
+    for (int q = 0; q < NB; q++)
+      if (q >= p) Tout[q * NB + p] = T[q][p];
+  }
+  return bad;
+}
+
+// ---- second generation of the CTA-per-front kernel -------------------------------------------------
+// Phase clocks of the root front of the 10-lap graph (138 pivots; profiles/tools/factor_phase_clocks.py)
+// for factor_kernel above: panels 65 % (trailing update 33 %, warp-0 triangle 21 %), fused forward
+// solve 15 %, extend-add 14 %.  Changes here, same mathematics and the same panel scheme:
+//  * the right-hand side rides along as ROW fs of the front (leading dimension fs + 1): eliminating
+//    the augmented matrix [[H, b], [b^T, .]] leaves y (L y = b) in that row under the pivots and the
+//    update vector for the parent under the update columns, so the forward solve costs one more row
+//    in steps (1b) and (2) instead of a second panel sweep with two barriers per panel;
+//  * look-ahead: while warps 1.. run the trailing update of panel k, warp 0 brings the 8 x 8 triangle of
+//    panel k+1 up to date, factorises it (a dependent chain of 8 reciprocals, ~1,400 cycles measured in
+//    isolation: profiles/tools/tri_lab.cu) and publishes it -- two barriers per panel instead of three
+//    and the chain is off the critical path;
+//  * extend-add keeps two columns (up to eight loads per lane) in flight (a shared-memory table of the
+//    children + four columns in flight was measured too: no change, the phase is not latency-chained);
+//  * the trailing update only touches its second 32-row chunk when one exists (fronts of <= 64 rows
+//    and the late panels of large fronts have none).
+template <bool SMEM>
+__global__ void __launch_bounds__(FACTOR_THREADS)
+factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV, double* Lv_all, long nL,
+               double* Uv_all, long nU, double* Fbig_all, long nFbig, int* status, double* uvec_all, long nUvec,
+               double* x_all, int n, int la_idle) {
+  extern __shared__ double smem[];
+  const int g = S.launch_list[list_off + blockIdx.x];
+  const int r = blockIdx.y;
+  const int s = S.npiv[g], u = S.nupd[g], fs = s + u;
+  const int ld = fs + 1;  // rows 0..fs-1: the front; row fs: the right-hand side
+  const double* V = V_all + (size_t)r * nV;
+  double* Uv = Uv_all + (size_t)r * nU;
+  double* F = SMEM ? smem : (Fbig_all + (size_t)r * nFbig + S.fbig[g]);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const bool dbgc = S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+  if (dbgc) { S.dbg[0] = clock64(); for (int k = 24; k < 32; k++) S.dbg[k] = 0; }
+  for (int t = tid; t < fs * ld; t += nt) F[t] = 0.0;
+  __syncthreads();
+  if (dbgc) S.dbg[1] = clock64();
+  for (int q = S.asm_ptr[g] + tid; q < S.asm_ptr[g + 1]; q += nt) {
+    const AsmEntry en = S.asm_entries[q];
+    const double* hv = V + en.hoff;
+    const int dr = en.meta & 0xff, dc = (en.meta >> 8) & 0xff;
+    const bool trans = (en.meta >> 16) & 1, diag = (en.meta >> 17) & 1;
+    if (diag) {
+      for (int i = 0; i < dr; i++)
+        for (int j = 0; j <= i; j++) F[(size_t)(en.c + j) * ld + en.r + i] = hv[i * dc + j];
+    } else if (!trans) {
+      for (int i = 0; i < dr; i++)
+        for (int j = 0; j < dc; j++) F[(size_t)(en.c + j) * ld + en.r + i] = hv[i * dc + j];
+    } else {
+      for (int i = 0; i < dc; i++)
+        for (int j = 0; j < dr; j++) F[(size_t)(en.c + j) * ld + en.r + i] = hv[j * dc + i];
+    }
+  }
+  {  // right-hand side row: rhs of the pivots + the children's update vectors, fixed (child) order
+    const int p0 = S.piv0[g];
+    const double* uvecr = uvec_all + (size_t)r * nUvec;
+    const int* gp = S.gather_ptr + S.frow_ptr[g];
+    for (int i = tid; i < fs; i += nt) {
+      double acc = i < s ? V[S.solver2v[p0 + i]] : 0.0;
+      for (int q = gp[i]; q < gp[i + 1]; q++) acc += uvecr[S.gather_src[q]];
+      F[(size_t)i * ld + fs] = acc;
+    }
+  }
+  __syncthreads();
+  if (dbgc) S.dbg[2] = clock64();
+  int* srel = reinterpret_cast<int*>(smem + (SMEM ? (size_t)fs * ld : 0));
+  for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
+    const int ch = S.children[ci];
+    const int uc = S.nupd[ch];
+    const double* __restrict__ Uc = Uv + S.uptr[ch];
+    const int* rel = S.rel + S.rows_ptr[ch];
+    for (int i = tid; i < uc; i += nt) srel[i] = rel[i];
+    __syncthreads();
+    for (int j = warp; j < uc; j += 2 * nw) {  // two columns, four row chunks each, loaded before any update
+      const int jb = j + nw;
+      const bool hb = jb < uc;
+      const double* colA = Uc + (size_t)j * uc;
+      const double* colB = Uc + (size_t)(hb ? jb : j) * uc;
+      double* dstA = F + (size_t)srel[j] * ld;
+      double* dstB = F + (size_t)srel[hb ? jb : j] * ld;
+      for (int i0 = 0; i0 < uc - j; i0 += 128) {
+        double va[4], vb[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int ia = j + i0 + 32 * c + lane, ib = jb + i0 + 32 * c + lane;
+          va[c] = ia < uc ? __ldg(colA + ia) : 0.0;
+          vb[c] = (hb && ib < uc) ? __ldg(colB + ib) : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int ia = j + i0 + 32 * c + lane, ib = jb + i0 + 32 * c + lane;
+          if (ia < uc) dstA[srel[ia]] += va[c];
+          if (hb && ib < uc) dstB[srel[ib]] += vb[c];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (dbgc) S.dbg[3] = clock64();
+  double* Sp = reinterpret_cast<double*>(srel + ((fs + 1) & ~1));  // NB x ld: scaled panel (incl. the rhs row)
+  double* dinv = Sp + (size_t)NB * ld;                             // 1/d of every pivot (s)
+  double* Tsm = dinv + fs;                                          // 2 x (NB x NB triangle + NB reciprocals)
+  constexpr int TSZ = NB * NB + NB;
+  const int nr = fs + 1;  // rows incl. the right-hand side
+  long long dt_ = 0;
+  // the first panel's triangle straight from the front; every later one is produced by warp 0 WHILE
+  // the other warps run the trailing update of the panel before it (look-ahead, step (2))
+  if (warp == 0) {
+    if (factor_triangle(F, 1, ld, Tsm, min(NB, s)) && lane == 0) status[2 * r] = 1;
+  }
+  __syncthreads();
+  for (int k0 = 0; k0 < s; k0 += NB) {
+    const int nb = min(NB, s - k0);
+    double* Pk = F + (size_t)k0 * ld;
+    const double* Tc = Tsm + ((k0 / NB) & 1) * TSZ;   // this panel's factorised triangle + reciprocals
+    double* Tn = Tsm + (((k0 / NB) & 1) ^ 1) * TSZ;   // the next panel's
+    if (dbgc) dt_ = clock64();
+    // ---- (1b) one thread per row below the triangle (the rhs row included); the last 64 threads
+    // put the triangle and the reciprocals where the later phases read them ----
+    {
+      const int e = nt - 1 - tid;
+      if (e < NB * NB) {
+        const int q = e / NB, pp = e % NB;
+        if (q >= pp && q < nb) Pk[pp * ld + k0 + q] = Tc[q * NB + pp];
+        if (q == 0 && pp < nb) dinv[k0 + pp] = Tc[NB * NB + pp];
+      }
+    }
+    if (k0 + nb + tid < nr) {
+      double T[NB][NB], invd[NB];
+#pragma unroll
+      for (int p = 0; p < NB; p++) {
+        invd[p] = Tc[NB * NB + p];
+#pragma unroll
+        for (int q = p + 1; q < NB; q++) T[q][p] = Tc[q * NB + p];
+      }
+      for (int i = k0 + nb + tid; i < nr; i += nt) {
+        double rr[NB];
+#pragma unroll
+        for (int p = 0; p < NB; p++) rr[p] = (p < nb) ? Pk[p * ld + i] : 0.0;
+#pragma unroll
+        for (int p = 0; p < NB; p++) {
+          const double rp = rr[p] * invd[p];
+          Sp[p * ld + i] = rp;
+#pragma unroll
+          for (int q = p + 1; q < NB; q++) rr[q] -= rp * T[q][p];
+        }
+#pragma unroll
+        for (int p = 1; p < NB; p++)
+          if (p < nb) Pk[p * ld + i] = rr[p];
+      }
+    }
+    if (dbgc) { const long long t_ = clock64(); S.dbg[26] += t_ - dt_; dt_ = t_; }
+    __syncthreads();
+    if (dbgc) { const long long t_ = clock64(); S.dbg[27] += t_ - dt_; dt_ = t_; }
+    // ---- (2) trailing update: columns c0..fs-1, rows j..fs (row fs = rhs); warp 0 instead brings the
+    // next panel's triangle up to date (36 entries, one or two per lane), factorises and publishes it ----
+    const int c0 = k0 + nb;
+    const bool ahead = c0 < s;
+    if (ahead && warp == 0) {
+      // wait (named barrier 1: this warp + the two producer warps) until the first two column groups
+      // -- the next panel's columns -- carry this panel's update, then factorise the triangle from F.
+      // (Measured and rejected: producers dropping the triangle into Tn packed for 16-byte loads: +5 %;
+      // warps 4/8/12 -- warp 0's scheduler mates -- sitting the step out: the chain drops from 4,500 to
+      // 1,700 cycles but the update with 12 instead of 15 warps loses as much.)
+      asm volatile("bar.sync 1, 96;" ::: "memory");
+      if (dbgc) { const long long t_ = clock64(); S.dbg[25] += t_ - dt_; dt_ = t_; }
+      if (factor_triangle(F + (size_t)c0 * ld + c0, 1, ld, Tn, min(NB, s - c0)) && lane == 0) status[2 * r] = 1;
+      if (dbgc) { const long long t_ = clock64(); S.dbg[24] += t_ - dt_; dt_ = t_; }
+    } else if (!ahead || !la_idle || (warp & 3) != 0) {
+      // la_idle: warps 4, 8, 12 share warp 0's scheduler and FP64 pipe and sit a look-ahead step out
+      int wi = warp, nwt = nw;
+      if (ahead) {
+        if (la_idle) { wi = (warp >> 2) * 3 + (warp & 3) - 1; nwt = (nw >> 2) * 3; }
+        else { wi = warp - 1; nwt = nw - 1; }
+      }
+      bool owe = ahead && wi < 2;  // producer of the next panel's columns: signal warp 0 after the first group
+      for (int jg = c0 + 4 * wi; jg < fs; jg += 4 * nwt) {
+        double B[4][NB];
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+#pragma unroll
+          for (int p = 0; p < NB; p++) B[b][p] = (jg + b < fs) ? Sp[p * ld + jg + b] : 0.0;
+        double* Cj = F + (size_t)jg * ld;
+        int i = jg + lane;
+        for (; i - lane + 32 < nr; i += 64) {  // warp-uniform: a second 32-row chunk exists
+          const int i2 = i + 32;
+          const bool v2 = i2 < nr;
+          double A[NB], A2[NB];
+#pragma unroll
+          for (int p = 0; p < NB; p++) {
+            A[p] = (p < nb) ? Pk[p * ld + i] : 0.0;
+            A2[p] = (p < nb && v2) ? Pk[p * ld + i2] : 0.0;
+          }
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (jg + b < fs) {
+              const bool w1 = i >= jg + b;
+              double acc = w1 ? Cj[b * ld + i] : 0.0;
+              double acc2 = v2 ? Cj[b * ld + i2] : 0.0;
+#pragma unroll
+              for (int p = 0; p < NB; p++) {
+                acc -= A[p] * B[b][p];
+                acc2 -= A2[p] * B[b][p];
+              }
+              if (w1) Cj[b * ld + i] = acc;
+              if (v2) Cj[b * ld + i2] = acc2;
+            }
+          }
+        }
+        if (i - lane < nr) {  // last, single chunk
+          const bool v1 = i < nr;
+          double A[NB];
+#pragma unroll
+          for (int p = 0; p < NB; p++) A[p] = (p < nb && v1) ? Pk[p * ld + i] : 0.0;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (jg + b < fs) {
+              const bool w1 = v1 && i >= jg + b;
+              double acc = w1 ? Cj[b * ld + i] : 0.0;
+#pragma unroll
+              for (int p = 0; p < NB; p++) acc -= A[p] * B[b][p];
+              if (w1) Cj[b * ld + i] = acc;
+            }
+          }
+        }
+        if (owe) { __threadfence_block(); asm volatile("bar.arrive 1, 96;" ::: "memory"); owe = false; }
+      }
+      if (owe) { __threadfence_block(); asm volatile("bar.arrive 1, 96;" ::: "memory"); }
+    }
+    if (dbgc) { const long long t_ = clock64(); S.dbg[28] += t_ - dt_; dt_ = t_; }
+    __syncthreads();
+    if (dbgc) { const long long t_ = clock64(); S.dbg[29] += t_ - dt_; dt_ = t_; }
+  }
+  if (dbgc) { S.dbg[4] = clock64(); S.dbg[5] = S.dbg[4]; }
+  // forward-solve results out of the rhs row: z = D^-1 y under the pivots, update vector for the parent
+  {
+    const int p0 = S.piv0[g];
+    double* xr = x_all + (size_t)r * n;
+    double* uo = uvec_all + (size_t)r * nUvec + S.rows_ptr[g];
+    for (int i = tid; i < fs; i += nt) {
+      const double v = F[(size_t)i * ld + fs];
+      if (i < s) xr[p0 + i] = v * dinv[i];
+      else uo[i - s] = v;
+    }
+  }
+  double* Lg = Lv_all + (size_t)r * nL + S.lptr[g];
+  for (int j = warp; j < s; j += nw) {
+    const double* col = F + (size_t)j * ld;
+    const double d = col[j];
+    const double inv = dinv[j];
+    double* out = Lg + (size_t)j * fs;
+    for (int i = lane; i < fs; i += 32) out[i] = i < j ? 0.0 : (i == j ? d : col[i] * inv);
+  }
+  double* Ug = Uv + S.uptr[g];
+  for (int j = warp; j < u; j += nw) {
+    const double* col = F + (size_t)(s + j) * ld + s;
+    double* out = Ug + (size_t)j * u;
+    for (int i = j + lane; i < u; i += 32) out[i] = col[i];
+  }
+  __syncthreads();
+  if (dbgc) { S.dbg[6] = clock64(); S.dbg[7] = s; S.dbg[8] = fs; S.dbg[9] = S.child_ptr[g + 1] - S.child_ptr[g]; }
 }
 
 // ================================================================================================
@@ -752,7 +1066,7 @@ bool warp_kernels(const slam_b200_ctx* c, const DeviceSystem& D, const LevelLaun
 }
 
 size_t factor_extra_smem(int max_fs) {  // srel (ints, even count) + scaled panel
-  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + ((size_t)(NB + 2) * max_fs + NB * NB + 2 * NB) * sizeof(double);
+  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + ((size_t)(NB + 2) * max_fs + 2 * (NB * NB + 2 * NB)) * sizeof(double);
 }
 
 SymArgs sym_args(const DeviceSystem& D) {
@@ -777,6 +1091,7 @@ static int solver_init_attrs(slam_b200_ctx* c) {
   if (!g_attr_set) {
     int lim = c->max_smem_optin;
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -798,6 +1113,9 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     cudaEventRecord(e, c->stream);
     D.prof_events.push_back(e);
   };
+  // SLAM_B200_FACTOR_VARIANT=1 selects the first-generation CTA-per-front kernel (A/B measurements)
+  static const bool gen2 = !(getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 1);
+  static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
     if (LL.n_tiny && warp_kernels(c, D, LL)) {
@@ -814,23 +1132,38 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       }
     } else if (LL.n_tiny) {
       dim3 grid(LL.n_tiny, D.R);
-      factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
-          S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
-          D.x.p, D.n);
+      if (gen2)
+        factor2_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
+            S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
+            D.x.p, D.n, la_idle);
+      else
+        factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
+            S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
+            D.x.p, D.n);
       c->launches++;
     }
     if (LL.n_small) {
       dim3 grid(LL.n_small, D.R);
-      factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
-          S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
-          D.nUvec, D.x.p, D.n);
+      if (gen2)
+        factor2_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
+            S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
+            D.nUvec, D.x.p, D.n, la_idle);
+      else
+        factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
+            S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
+            D.nUvec, D.x.p, D.n);
       c->launches++;
     }
     if (LL.n_big) {
       dim3 grid(LL.n_big, D.R);
-      factor_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
-          S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
-          D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n);
+      if (gen2)
+        factor2_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
+            S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
+            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n, la_idle);
+      else
+        factor_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
+            S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
+            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n);
       c->launches++;
     }
   }

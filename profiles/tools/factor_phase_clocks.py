@@ -24,3 +24,11 @@ tot = v[6] - v[0]
 for k, nm in enumerate(names):
     print("%-14s %8d cycles %5.1f%%" % (nm, v[k + 1] - v[k], 100.0 * (v[k + 1] - v[k]) / tot))
 print("total %d cycles" % tot)
+out8 = (C.c_longlong * 8)()
+ctx.L.slam_b200_debug_panel_clocks.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+rc = ctx.L.slam_b200_debug_panel_clocks(ctx.h, out8)
+w = list(out8)
+print("panel loop of that CTA, thread 0 (warp 0), cycles summed over its panels:")
+for nm, val in zip(["(1a) triangle, warp 0 (gen 2: look-ahead factorise+publish)", "wait at barrier 1 (gen 2: look-ahead update of the triangle)", "(1b) row elimination", "wait at barrier 2",
+                    "(2) trailing update", "wait at barrier 3", "forward: warp-0 triangle solve", "forward: rest of panel step"], w):
+    print("  %-64s %9.0f" % (nm, val))
