@@ -753,17 +753,26 @@ __device__ __forceinline__ double* xchg_slot(char* base, int cap, int parity) {
   return reinterpret_cast<double*>(base + XCHG_HEADER) + (size_t)parity * 6 * (size_t)cap;
 }
 
-template <bool CHI2_ONLY, bool UNROLL2, bool PEER>
+// G lanes per landmark (32, 16 or 8; 32/G landmarks per warp): with one warp per landmark the kernel
+// executed 437 warp instructions per landmark on the 1M-pose graph (36 observers per landmark: 28 of
+// the 64 lane slots of its two steps idle, a 5-value x 5-level shuffle tree per landmark) and was half
+// issue-bound (ncu: issue slots 50 % busy at 40 % occupancy).  Smaller groups fill the lanes and
+// shorten the tree; G is chosen from the mean number of observers per landmark (host, below).
+template <bool CHI2_ONLY, bool UNROLL2, bool PEER, int G>
 __global__ void __launch_bounds__(ASM_THREADS)
 assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_first, int l_end, PeerArgs px) {
   const int lane = threadIdx.x & 31;
-  const int l = l_first + blockIdx.x * LM_PER_BLOCK + (threadIdx.x >> 5);
+  const int gl = lane & (G - 1);
+  constexpr int GPW = 32 / G;  // landmarks per warp
+  const int l = l_first + (blockIdx.x * LM_PER_BLOCK + (threadIdx.x >> 5)) * GPW + lane / G;
   const int r = blockIdx.y;
   const double* est = a.est + (size_t)r * a.estStride;
   const double* meas = a.meas + (size_t)r * a.measStride;
   double* V = a.V + (size_t)r * a.nV;
   const int P = a.P, L = a.L, El = a.El;
-  if (PEER && !CHI2_ONLY && l < l_end && !a.lm_free[l] && lane == 0) {
+  const bool inrange = !CHI2_ONLY && l < l_end;
+  const bool active = inrange && a.lm_free[l];
+  if (PEER && inrange && !active && gl == 0) {
     // fixed / inactive landmark inside the range: its slot entries must read as zero
     double* slot = xchg_slot(px.peer_tab[px.rank], px.cap, px.parity);
     const int k = l - l_first;
@@ -771,26 +780,30 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
     double* hs = slot + 2 * (size_t)px.cap + 4 * (size_t)k;
     hs[0] = 0.0; hs[1] = 0.0; hs[2] = 0.0; hs[3] = 0.0;
   }
-  if (!CHI2_ONLY && l < l_end && a.lm_free[l]) {  // warp-uniform
-    const double lx = est[3 * P + l], ly = est[3 * P + L + l];
+  if (!CHI2_ONLY) {  // all lanes stay together (the reduction below shuffles across the warp)
+    double lx = 0, ly = 0;
     double h00 = 0, h01 = 0, h11 = 0, b0 = 0, b1 = 0;
-    int q0 = a.lm_start[l], q1 = a.lm_start[l + 1];
-    if (p0 > 0 || p1 < P) {
-      // pose-range shard: landmark edges are sorted by pose, so the shard's edges are the sorted
-      // positions [el_start[p0], el_start[p1]); the landmark's list is ascending -> two bisections
-      const int elo = a.el_start[p0], ehi = a.el_start[p1];
-      int lo = q0, hi = q1;
-      while (lo < hi) { int m = (lo + hi) >> 1; if (a.lm_edges[m] < elo) lo = m + 1; else hi = m; }
-      const int b0 = lo;
-      hi = q1;
-      while (lo < hi) { int m = (lo + hi) >> 1; if (a.lm_edges[m] < ehi) lo = m + 1; else hi = m; }
-      q0 = b0;
-      q1 = lo;
+    int q0 = 0, q1 = 0;
+    if (active) {
+      lx = est[3 * P + l]; ly = est[3 * P + L + l];
+      q0 = a.lm_start[l]; q1 = a.lm_start[l + 1];
+      if (p0 > 0 || p1 < P) {
+        // pose-range shard: landmark edges are sorted by pose, so the shard's edges are the sorted
+        // positions [el_start[p0], el_start[p1]); the landmark's list is ascending -> two bisections
+        const int elo = a.el_start[p0], ehi = a.el_start[p1];
+        int lo = q0, hi = q1;
+        while (lo < hi) { int m = (lo + hi) >> 1; if (a.lm_edges[m] < elo) lo = m + 1; else hi = m; }
+        const int b0_ = lo;
+        hi = q1;
+        while (lo < hi) { int m = (lo + hi) >> 1; if (a.lm_edges[m] < ehi) lo = m + 1; else hi = m; }
+        q0 = b0_;
+        q1 = lo;
+      }
     }
     const double* trig = a.trig + (size_t)r * 2 * P;
     const double* mlm = meas + 2 * (size_t)El + 3 * (size_t)a.Eo;  // measurements in landmark order
     // everything indexed by q is laid out in landmark order: coalesced across the lanes.  Two
-    // 32-edge steps are loaded together (index -> gathers -> payload for both) before either is
+    // G-edge steps are loaded together (index -> gathers -> payload for both) before either is
     // evaluated, so the two dependent round trips of a step overlap with those of the next.
     const double* io0 = a.lmo_info;
     const double* io1 = a.lmo_info + El;
@@ -800,21 +813,21 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
     const double* ex_ = est;
     const double* ey_ = est + P;
     const double* tc_ = trig + P;
-    for (int qb = q0 + lane; qb < q1; qb += (UNROLL2 ? 64 : 32)) {
-      const int qa = qb, qc = qb + 32;
-      const bool va = true, vc = UNROLL2 && qc < q1;
+    for (int qb = q0 + gl; qb < q1; qb += (UNROLL2 ? 2 * G : G)) {
+      const int qa = qb, qc = qb + G;
+      const bool vc = UNROLL2 && qc < q1;
       const int pa = __ldg(a.lmo_pose + qa);
       const int pc = vc ? __ldg(a.lmo_pose + qc) : -1;
-      const bool aa = va && pa >= 0, ac = pc >= 0;  // p < 0: inactive edge
+      const bool aa = pa >= 0, ac = pc >= 0;  // p < 0: inactive edge
       double sa = 0, ca = 0, xa = 0, ya = 0, sc = 0, cc = 0, xc = 0, yc = 0;
       if (aa) { sa = trig[pa]; ca = tc_[pa]; xa = ex_[pa]; ya = ey_[pa]; }
       if (ac) { sc = trig[pc]; cc = tc_[pc]; xc = ex_[pc]; yc = ey_[pc]; }
       double za0 = 0, za1 = 0, ia0 = 0, ia1 = 0, ia2 = 0, zc0 = 0, zc1 = 0, ic0 = 0, ic1 = 0, ic2 = 0;
       if (aa) { za0 = __ldg(m0 + qa); za1 = __ldg(m1 + qa); ia0 = __ldg(io0 + qa); ia1 = __ldg(io1 + qa); ia2 = __ldg(io2 + qa); }
       if (ac) { zc0 = __ldg(m0 + qc); zc1 = __ldg(m1 + qc); ic0 = __ldg(io0 + qc); ic1 = __ldg(io1 + qc); ic2 = __ldg(io2 + qc); }
-      auto accumulate = [&](double s, double c, double px, double py, double z0, double z1, double i00, double i01,
+      auto accumulate = [&](double s, double c, double px_, double py_, double z0, double z1, double i00, double i01,
                             double i11) {
-        const double dx = lx - px, dy = ly - py;
+        const double dx = lx - px_, dy = ly - py_;
         const double ex = c * dx + s * dy - z0;
         const double ey = -s * dx + c * dy - z1;
         // A = Jl^T Omega, Jl = [[c, s], [-s, c]]
@@ -829,28 +842,29 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
       if (aa) accumulate(sa, ca, xa, ya, za0, za1, ia0, ia1, ia2);
       if (ac) accumulate(sc, cc, xc, yc, zc0, zc1, ic0, ic1, ic2);
     }
+    __syncwarp();
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
+    for (int o = G / 2; o; o >>= 1) {  // fixed xor tree inside the group of G lanes
       h00 += __shfl_xor_sync(0xffffffffu, h00, o);
       h01 += __shfl_xor_sync(0xffffffffu, h01, o);
       h11 += __shfl_xor_sync(0xffffffffu, h11, o);
       b0 += __shfl_xor_sync(0xffffffffu, b0, o);
       b1 += __shfl_xor_sync(0xffffffffu, b1, o);
     }
-    if (PEER) {
-      if (lane == 0) {
+    if (active && gl == 0) {
+      if (PEER) {
         double* slot = xchg_slot(px.peer_tab[px.rank], px.cap, px.parity);
         const int k = l - l_first;
         *reinterpret_cast<double2*>(slot + 2 * (size_t)k) = make_double2(b0, b1);
         double2* hs = reinterpret_cast<double2*>(slot + 2 * (size_t)px.cap + 4 * (size_t)k);
         hs[0] = make_double2(h00, h01);
         hs[1] = make_double2(h01, h11);
+      } else {
+        double* bl = V + 2 * (size_t)l;
+        bl[0] = b0; bl[1] = b1;
+        double* hl = V + 2 * (size_t)L + 4 * (size_t)l;
+        hl[0] = h00; hl[1] = h01; hl[2] = h01; hl[3] = h11;
       }
-    } else if (lane == 0) {
-      double* bl = V + 2 * (size_t)l;
-      bl[0] = b0; bl[1] = b1;
-      double* hl = V + 2 * (size_t)L + 4 * (size_t)l;
-      hl[0] = h00; hl[1] = h01; hl[2] = h01; hl[3] = h11;
     }
   }
   // final chi2 of this replica: fixed-order sum of the pose kernel's block partials
@@ -1047,15 +1061,31 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, boo
     graph_shard_landmarks(D, p0, p1, &l_first, &l_end);
     SLAM_CUDA_TRY(c, cudaMemsetAsync(D.V.p, 0, sizeof(double) * 6 * (size_t)D.L, c->stream));
   }
-  dim3 gl(std::max(1, (l_end - l_first + LM_PER_BLOCK - 1) / LM_PER_BLOCK), D.R);
-  // a landmark with more than one 32-edge step of observers (long tracks, many laps) is worth the
-  // two-steps-in-flight loop; with 20-30 observers per landmark the plain loop is faster (measured)
-  const bool unroll2 = D.El > 32L * std::max(D.L, 1);
-  if (chi2_only) assemble_landmark_kernel<true, false, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
-  else if (peer && unroll2) assemble_landmark_kernel<false, true, true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
-  else if (peer) assemble_landmark_kernel<false, false, true><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
-  else if (unroll2) assemble_landmark_kernel<false, true, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
-  else assemble_landmark_kernel<false, false, false><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px);
+  // lanes per landmark from the mean number of observers (SLAM_B200_LM_GROUP overrides: 8, 16, 32)
+  int G = 32;
+  {
+    const double mean_obs = (double)D.El / std::max(D.L, 1);
+    // measured (profiles/r01_asm_ab.log): 36 observers (1M-pose graph) 0.489 / 0.437 / 0.417 ms and 24
+    // observers (1-lap replicas) 0.888 / 0.769 / 0.722 ms for G = 32 / 16 / 8 (4 lanes: no further gain);
+    // 279 observers (10-lap graph) 36 / 42 / 54 us
+    if (mean_obs <= 48.0) G = 8;
+    else if (mean_obs <= 128.0) G = 16;
+    if (const char* ev = getenv("SLAM_B200_LM_GROUP")) { int v = atoi(ev); if (v == 8 || v == 16 || v == 32) G = v; }
+  }
+  const int lm_per_block = LM_PER_BLOCK * (32 / G);
+  dim3 gl(std::max(1, (l_end - l_first + lm_per_block - 1) / lm_per_block), D.R);
+  // a landmark with more than one G-edge step of observers (long tracks, many laps) is worth the
+  // two-steps-in-flight loop; with fewer the plain loop is faster (measured)
+  const bool unroll2 = D.El > (long)G * std::max(D.L, 1);
+#define LM_LAUNCH(C, U, PE, GG) assemble_landmark_kernel<C, U, PE, GG><<<gl, ASM_THREADS, 0, c->stream>>>(a, p0, p1, nblk, l_first, l_end, px)
+#define LM_LAUNCH_G(C, U, PE) do { if (G == 8) LM_LAUNCH(C, U, PE, 8); else if (G == 16) LM_LAUNCH(C, U, PE, 16); else LM_LAUNCH(C, U, PE, 32); } while (0)
+  if (chi2_only) LM_LAUNCH(true, false, false, 32);
+  else if (peer && unroll2) LM_LAUNCH_G(false, true, true);
+  else if (peer) LM_LAUNCH_G(false, false, true);
+  else if (unroll2) LM_LAUNCH_G(false, true, false);
+  else LM_LAUNCH_G(false, false, false);
+#undef LM_LAUNCH_G
+#undef LM_LAUNCH
   c->launches++;
   if (peer) {
     PeerExchange& X = D.xchg;

@@ -15,6 +15,7 @@ pkg = load_package()
 par = __import__(pkg.__name__ + ".parallel", fromlist=["x"])
 synth = pkg.synth
 VARIANTS = [int(v) for v in os.environ.get("ASM_AB_VARIANTS", "0,14,24").split(",")]
+GROUPS = [int(v) for v in os.environ.get("ASM_AB_GROUPS", "32,16,8").split(",")]  # lanes per landmark
 REPS = int(os.environ.get("ASM_AB_REPS", "15"))
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev)
@@ -25,8 +26,9 @@ def measure(ctx, P, label, nV, R):
     ptr, _ = ctx.graph_system_dev(0)
     V = torch.as_tensor(par.DeviceArray(ptr, nV * R), device=dev)
     ref = None
-    for var in VARIANTS:
+    for var, grp in [(v, g_) for v in VARIANTS for g_ in GROUPS]:
         os.environ["SLAM_B200_ASM_VARIANT"] = str(var)
+        os.environ["SLAM_B200_LM_GROUP"] = str(grp)
         ts = []
         with torch.cuda.stream(stream):
             for _ in range(3):
@@ -45,8 +47,8 @@ def measure(ctx, P, label, nV, R):
             diff = 0.0
         else:
             diff = float((got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-300))
-        print("%s variant %2d: median %.4f ms  min %.4f ms  max|dV|/max|V| vs variant %d = %.3g"
-              % (label, var, float(np.median(ts)), float(np.min(ts)), VARIANTS[0], diff), flush=True)
+        print("%s pose-kernel variant %2d, %2d lanes per landmark: median %.4f ms  min %.4f ms  max|dV|/max|V| vs first = %.3g"
+              % (label, var, grp, float(np.median(ts)), float(np.min(ts)), diff), flush=True)
         del got
 
 
@@ -57,6 +59,14 @@ if "c5" in os.environ.get("ASM_AB_WORKLOADS", "c5,c3"):
     ctx.graph_prepare_assembly_only()
     st = ctx.graph_stats()
     measure(ctx, len(g.pose_ids), "c5", int(st["nV"]), 1)
+    ctx.close()
+if "c2" in os.environ.get("ASM_AB_WORKLOADS", "c5,c3"):
+    ctx = pkg.Context(0, stream=stream.cuda_stream)
+    g = synth.c2_graph()
+    ctx.graph_load(g)
+    ctx.graph_prepare_assembly_only()
+    st = ctx.graph_stats()
+    measure(ctx, len(g.pose_ids), "c2", int(st["nV"]), 1)
     ctx.close()
 if "c3" in os.environ.get("ASM_AB_WORKLOADS", "c5,c3"):
     R = int(os.environ.get("ASM_AB_REPLICAS", "2048"))
