@@ -216,6 +216,52 @@ def test_optimize_c2_full_size(ctx, orc, synth):
     assert abs(chi2[-1] - chi2[-2]) <= 1e-9 * chi2[-1]
 
 
+def test_fronts_beyond_shared_memory(ctx, orc, synth, monkeypatch):
+    """Fronts that do not fit an SM's shared memory (> 163 rows) are factorised in a global-memory slab
+    (factor2_kernel<false>, backward_kernel<false>).  The default ordering never produces them on the
+    trackdrive graphs, so the ordering is forced to leaf-level dissection (landmarks eliminated early,
+    one dense clique per landmark): 6 laps x 300 poses -> fronts of up to ~194 rows."""
+    monkeypatch.setenv("SLAM_B200_ND_LEAF", "8")
+    g = synth.c2_graph(n_laps=6, poses_per_lap=300)
+    ctx.graph_load(g)
+    n, chi2 = ctx.graph_optimize(10)
+    st = ctx.graph_stats()
+    assert st["max_front"] > 163 and st["nFbig"] > 0, st   # the path under test was really taken
+    G = orc.graph_from_soa(g)
+    no, chi2o = G.optimize(10)
+    assert n == no == 10
+    assert np.allclose(chi2, chi2o, rtol=1e-8)
+    pe, le = ctx.graph_get_estimates(); po, lo = G.estimates(g)
+    assert _rel_close(pe, po) and _rel_close(le, lo)
+    monkeypatch.delenv("SLAM_B200_ND_LEAF")
+    ctx.graph_load(small_graph(synth, 40))  # leave the context with a default-ordered structure
+    ctx.graph_optimize(1)
+
+
+@pytest.mark.parametrize("variant", ["1"])
+def test_first_generation_front_kernel_still_agrees(ctx, orc, synth, variant):
+    """SLAM_B200_FACTOR_VARIANT=1 (kept for A/B measurements) is read once per process, so it runs in a
+    child process: same graph, same tolerance."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import load_pkg, small_graph\n"
+        "from oracle import oracle\n"
+        "pkg = load_pkg(); orc = oracle.load('best'); g = small_graph(pkg.synth, 300)\n"
+        "ctx = pkg.Context(0); ctx.graph_load(g); n, chi2 = ctx.graph_optimize(10)\n"
+        "G = orc.graph_from_soa(g); no, chi2o = G.optimize(10)\n"
+        "pe, le = ctx.graph_get_estimates(); po, lo = G.estimates(g)\n"
+        "assert n == no == 10 and np.allclose(chi2, chi2o, rtol=1e-8)\n"
+        "assert np.max(np.abs(pe - po)) <= 1e-6 * max(1.0, np.max(np.abs(po)))\n"
+        "assert np.max(np.abs(le - lo)) <= 1e-6 * max(1.0, np.max(np.abs(lo)))\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)))
+    env = dict(os.environ, SLAM_B200_FACTOR_VARIANT=variant)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_sharded_assembly_partials_sum_to_full(ctx, pkg, synth):
     """Edge-partitioned assembly (config 5): assembling pose ranges separately gives pose blocks and
     off-diagonal blocks owned by exactly one shard and landmark partial sums that add up to the full
