@@ -599,7 +599,7 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
 }
 
 void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const int* off_b,
-                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S) {
+                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S, int amalgamate) {
   auto t0 = std::chrono::steady_clock::now();
   S = Symbolic();
   S.nb = nb;
@@ -799,10 +799,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     node.verts.assign(order.begin() + c0, order.begin() + c1);
     nd.nodes.push_back(std::move(node));
   }
-  const int nf = (int)nd.nodes.size();
-  S.nf = nf;
-  std::vector<int> post(nf);
-  std::iota(post.begin(), post.end(), 0);
+  int nf = (int)nd.nodes.size();
   std::vector<int> front_of(nb, -1);  // owning node of every block
   for (int f = 0; f < nf; f++)
     for (int v : nd.nodes[f].verts) front_of[v] = f;
@@ -826,6 +823,109 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     }
   }
   dbg("pass1 update sets");
+  // ---- latency-driven amalgamation: children on the critical path are absorbed by their parent ----
+  // On a GPU a front costs a fixed ~15 us (launch, index chain, zero, scatter, extend-add, write-out)
+  // however few pivots it has, and every level of the assembly tree is a dependent launch: the 10-lap
+  // trackdrive graph has three levels of fronts with 6 pivots each, the 1-lap graph a chain of a dozen
+  // fronts with ~17.  Unlike the chain merge above this also merges across siblings: the pivots of
+  // children in different subtrees do not touch each other, so eliminating [child A pivots, child B
+  // pivots, parent pivots] inside ONE dense front is the same factorisation with explicit zeros in the
+  // A-B block (they stay exactly zero).  The merged front has the parent's update set (struct(child)
+  // minus the parent's pivots is contained in it).  Greedy, bottom-up, on a cost model of the numeric
+  // kernels (microseconds; calibrated on the ncu launch list of the 10-lap graph,
+  // profiles/r01_c2_launches.md): finish(f) = max over children finish(c) + T(f); the children within
+  // 10 % of the latest finish are merged into f together whenever that makes f finish earlier.
+  // MEASURED AND SWITCHED OFF (symbolic.h): the model's fixed cost per front is too high -- on B200 the
+  // merged trees are slower.  Kept behind SLAM_B200_AMALG=t_fix,t_kid,t_panel0,t_panel2,t_area,max_rows
+  // (e.g. 14,1.5,0.9,2.0,4.0,150) for re-calibration; tests/test_symbolic.py runs it through the emulation.
+  if (amalgamate || getenv("SLAM_B200_AMALG")) {
+    double t_fix = 14.0, t_kid = 1.5, t_panel0 = 0.9, t_panel2 = 2.0, t_area = 4.0;
+    int max_fs = 150;
+    if (const char* e = getenv("SLAM_B200_AMALG")) {
+      double v[5];
+      int m = 0;
+      if (sscanf(e, "%lf,%lf,%lf,%lf,%lf,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &m) == 6) {
+        t_fix = v[0]; t_kid = v[1]; t_panel0 = v[2]; t_panel2 = v[3]; t_area = v[4]; max_fs = m;
+      }
+    }
+    auto cost = [&](int sp, int fs, int nk) {
+      const double a2 = (fs / 138.0) * (fs / 138.0);
+      return t_fix + t_kid * nk + ((sp + 7) / 8) * (t_panel0 + t_panel2 * a2) + t_area * a2;
+    };
+    std::vector<int> spiv(nf, 0), supd(nf, 0);
+    for (int f = 0; f < nf; f++) {
+      for (int v : nd.nodes[f].verts) spiv[f] += dim[v];
+      for (int w : U[f]) supd[f] += dim[w];
+    }
+    std::vector<double> fin(nf, 0.0);
+    std::vector<char> dead(nf, 0);
+    int ndead = 0;
+    for (int p = 0; p < nf && max_fs > 0; p++) {  // nodes are in elimination order: children first
+      for (;;) {
+        std::vector<int>& kids = akids[p];
+        double latest = 0.0;
+        for (int k : kids) latest = std::max(latest, fin[k]);
+        const double now = latest + cost(spiv[p], spiv[p] + supd[p], (int)kids.size());
+        if (kids.empty()) { fin[p] = now; break; }
+        // candidate: absorb every child within 10 % of the latest finish
+        int add = 0, nk = 0;
+        double rest = 0.0;
+        for (int k : kids) {
+          if (fin[k] >= 0.9 * latest) { add += spiv[k]; nk += (int)akids[k].size(); for (int q : akids[k]) rest = std::max(rest, fin[q]); }
+          else { nk++; rest = std::max(rest, fin[k]); }
+        }
+        const int fs2 = spiv[p] + add + supd[p];
+        const double then = rest + cost(spiv[p] + add, fs2, nk);
+        if (fs2 > max_fs || then >= now - 0.5) { fin[p] = now; break; }
+        std::vector<int> keep, front;  // absorbed children's pivots go first, in child order
+        for (int k : kids) {
+          if (fin[k] >= 0.9 * latest) {
+            front.insert(front.end(), nd.nodes[k].verts.begin(), nd.nodes[k].verts.end());
+            for (int q : akids[k]) { aparent[q] = p; keep.push_back(q); }
+            dead[k] = 1;
+            ndead++;
+            nd.nodes[k].verts.clear();
+            akids[k].clear();
+            U[k].clear();
+          } else {
+            keep.push_back(k);
+          }
+        }
+        std::vector<int>& pv = nd.nodes[p].verts;
+        pv.insert(pv.begin(), front.begin(), front.end());
+        spiv[p] += add;
+        std::sort(keep.begin(), keep.end());
+        kids.swap(keep);
+      }
+    }
+    if (ndead) {
+      std::vector<int> remap(nf, -1);
+      int m = 0;
+      for (int f = 0; f < nf; f++)
+        if (!dead[f]) remap[f] = m++;
+      std::vector<NdNode> nodes2(m);
+      std::vector<std::vector<int>> U2(m), kids2(m);
+      std::vector<int> par2(m, -1);
+      for (int f = 0; f < nf; f++) {
+        if (dead[f]) continue;
+        const int g = remap[f];
+        nodes2[g].verts.swap(nd.nodes[f].verts);
+        U2[g].swap(U[f]);
+        par2[g] = aparent[f] >= 0 ? remap[aparent[f]] : -1;
+        for (int k : akids[f]) kids2[g].push_back(remap[k]);
+        std::sort(kids2[g].begin(), kids2[g].end());
+      }
+      nd.nodes.swap(nodes2);
+      U.swap(U2);
+      akids.swap(kids2);
+      aparent.swap(par2);
+      nf = m;
+    }
+  }
+  S.nf = nf;
+  std::vector<int> post(nf);
+  std::iota(post.begin(), post.end(), 0);
+  dbg("amalgamation");
   // ---- pass 2: levels of the assembly tree, level-major renumbering ----
   std::vector<int> level(nf, 0);
   for (int f : post)

@@ -48,5 +48,9 @@ struct Symbolic {
 // offdiag: nnb pairs (a, b), a < b, distinct, block indices in g2o order; hoff_diag[b] / hoff_off[k]
 // give where the assembly kernels store each block (dims: diag d x d; off-diag dim[a] x dim[b]).
 // leaf_size: nested dissection stops at subgraphs of at most this many vertices.
+// amalgamate: 1 = latency-driven merging of critical-path children into their parents, 0 = none.
+// Off by default: measured on B200 it shortens the assembly tree (10-lap graph 10 -> 8 levels, 1-lap
+// graph 10 -> 5) but the GN iteration gets slower (507 -> 547 us, 315 -> 332 us): a panel of 8 pivots
+// costs more than the fixed cost of a front, so fewer, larger fronts lose.  SLAM_B200_AMALG enables it.
 void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const int* off_b,
-                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S);
+                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S, int amalgamate = 0);

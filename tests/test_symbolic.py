@@ -33,8 +33,13 @@ def _check_structure(sym, dims):
             assert lvl[sym.parent[f]] > lvl[f]
 
 
+@pytest.mark.parametrize("amalg", [None, "14,1.5,0.9,2.0,4.0,150"])
 @pytest.mark.parametrize("leaf", [1, 8, 64, 100000])
-def test_symbolic_solves_small_graph(pkg, synth, orc, leaf):
+def test_symbolic_solves_small_graph(pkg, synth, orc, leaf, amalg, monkeypatch):
+    """amalg: the optional latency-driven amalgamation (children merged into their parents across
+    siblings, symbolic.cpp) must give a structure that still factorises and solves exactly."""
+    if amalg:
+        monkeypatch.setenv("SLAM_B200_AMALG", amalg)
     g = small_graph(synth, 150)
     ids, dims, pa, pb = mf_emul.block_pattern(g)
     sym = pkg.SymbolicAnalysis(dims, pa, pb, leaf_size=leaf)
@@ -51,7 +56,9 @@ def test_symbolic_solves_small_graph(pkg, synth, orc, leaf):
     x = np.zeros(n)
     x[perm] = x_solver
     x_ref = spla.spsolve(sp.csc_matrix(H), sysm["b"])
-    assert np.allclose(x, x_ref, rtol=1e-9, atol=1e-12)
+    # normwise: cond(H) ~ 2e6 on this graph, so entries near zero carry ~1e-11 of absolute error in
+    # either solver; the elimination order (and with it the rounding) changes with the amalgamation
+    assert np.max(np.abs(x - x_ref)) <= 1e-9 * np.max(np.abs(x_ref))
 
 
 def test_symbolic_c1_quality(pkg, synth, c1_graph):
