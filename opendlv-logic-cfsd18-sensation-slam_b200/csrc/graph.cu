@@ -40,8 +40,8 @@ struct AsmArgs {
   double* V;
   const unsigned char* pose_free;
   const unsigned char* lm_free;
-  const int *el_start, *el_pose, *el_lm, *el_slot, *el_flags;
-  const int4* el_rec;
+  const int* el_start;
+  const int4* el_rec;  // {pose, landmark, block slot, flags} of every pose-sorted landmark edge
   const double* el_info;
   const int *lm_start, *lm_edges, *lmo_pose;
   const double* lmo_info;
@@ -127,11 +127,11 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
       int slot = 0;
       bool wr = false;  // this lane stores o[] at V + slot
       if (valid) {
-        fl = a.el_flags[e];
-        pl = a.el_pose[e] - pw0;
+        fl = a.el_rec[e].w;
+        pl = a.el_rec[e].x - pw0;
       }
       if (valid && (fl & EF_ACTIVE)) {
-        const int l = a.el_lm[e];
+        const int l = a.el_rec[e].y;
         const double qx = s_pose[wid][0][pl], qy = s_pose[wid][1][pl], qs = s_pose[wid][2][pl], qc = s_pose[wid][3][pl];
         const double dx = est[3 * P + l] - qx, dy = est[3 * P + L + l] - qy;
         const double i00 = a.el_info[e], i01 = a.el_info[El + e], i11 = a.el_info[2 * El + e];
@@ -157,7 +157,7 @@ assemble_pose_kernel(AsmArgs a, int p0, int p1) {
           if (fl & EF_OFFDIAG) {  // Ji^T Omega Jl, Jl = [[c, s], [-s, c]]
             const double B[6] = {a00 * qc - a01 * qs, a00 * qs + a01 * qc, a10 * qc - a11 * qs,
                                  a10 * qs + a11 * qc, a20 * qc - a21 * qs, a20 * qs + a21 * qc};
-            slot = a.el_slot[e];
+            slot = a.el_rec[e].z;
             if (fl & EF_TRANS) {  // stored landmark rows x pose columns (2x3)
               o[0] = B[0]; o[1] = B[2]; o[2] = B[4]; o[3] = B[1]; o[4] = B[3]; o[5] = B[5];
             } else {
@@ -1016,8 +1016,7 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, boo
   a.estStride = D.estStride; a.measStride = D.measStride; a.nV = D.nV;
   a.est = D.est.p; a.meas = D.meas.p; a.V = D.V.p;
   a.pose_free = D.pose_free.p; a.lm_free = D.lm_free.p;
-  a.el_start = D.el_start.p; a.el_pose = D.el_pose.p; a.el_lm = D.el_lm.p; a.el_slot = D.el_slot.p;
-  a.el_flags = D.el_flags.p; a.el_info = D.el_info.p; a.el_rec = D.el_rec.p;
+  a.el_start = D.el_start.p; a.el_info = D.el_info.p; a.el_rec = D.el_rec.p;
   a.lm_start = D.lm_start.p; a.lm_edges = D.lm_edges.p; a.lmo_pose = D.lmo_pose.p; a.lmo_info = D.lmo_info.p;
   a.trig = D.trig.p;
   a.eo_i = D.eo_i.p; a.eo_j = D.eo_j.p; a.eo_slot = D.eo_slot.p; a.eo_flags = D.eo_flags.p;
@@ -1370,21 +1369,29 @@ int graph_build_structure(slam_b200_ctx* c) {
   for (int f = 0; f < S.nf; f++) frow_ptr[f + 1] = frow_ptr[f] + S.npiv[f] + S.nupd[f] + 1;
   gather_ptr.assign(frow_ptr[S.nf], 0);
   {
-    std::vector<std::vector<int>> per_row;
+    // counting sort per front (children in order, rows ascending inside a child): every update row of
+    // a non-root front lands in exactly one row of its parent
+    gather_src.assign((size_t)S.rows_ptr[S.nf], 0);
+    std::vector<int> cur;
+    int base = 0;
     for (int f = 0; f < S.nf; f++) {
       const int fs = S.npiv[f] + S.nupd[f];
-      per_row.assign(fs, std::vector<int>());
+      int* gp = gather_ptr.data() + frow_ptr[f];  // fs + 1 entries
+      std::fill(gp, gp + fs + 1, 0);
       for (int ci = S.child_ptr[f]; ci < S.child_ptr[f + 1]; ci++) {
         const int ch = S.children[ci];
-        for (int q = S.rows_ptr[ch]; q < S.rows_ptr[ch + 1]; q++) per_row[S.rel[q]].push_back(q);
+        for (int q = S.rows_ptr[ch]; q < S.rows_ptr[ch + 1]; q++) gp[S.rel[q] + 1]++;
       }
-      int* gp = gather_ptr.data() + frow_ptr[f];
-      for (int i = 0; i < fs; i++) {
-        gp[i] = (int)gather_src.size();
-        gather_src.insert(gather_src.end(), per_row[i].begin(), per_row[i].end());
+      gp[0] = base;
+      for (int i = 0; i < fs; i++) gp[i + 1] += gp[i];
+      cur.assign(gp, gp + fs);
+      for (int ci = S.child_ptr[f]; ci < S.child_ptr[f + 1]; ci++) {
+        const int ch = S.children[ci];
+        for (int q = S.rows_ptr[ch]; q < S.rows_ptr[ch + 1]; q++) gather_src[cur[S.rel[q]]++] = q;
       }
-      gp[fs] = (int)gather_src.size();
+      base = gp[fs];
     }
+    gather_src.resize((size_t)base);
   }
   // solver scalar -> V offset of the rhs entry; vertex -> solver offset
   std::vector<int> solver2v(D.n), pose_boff(P, -1), lm_boff(L, -1);
@@ -1416,10 +1423,6 @@ int graph_build_structure(slam_b200_ctx* c) {
   rc |= upload_vec(c, D.pose_boff, pose_boff);
   rc |= upload_vec(c, D.lm_boff, lm_boff);
   rc |= upload_vec(c, D.el_start, el_start);
-  rc |= upload_vec(c, D.el_pose, s_pose);
-  rc |= upload_vec(c, D.el_lm, s_lm);
-  rc |= upload_vec(c, D.el_slot, s_slot);
-  rc |= upload_vec(c, D.el_flags, s_flags);
   std::vector<int4> el_rec_h(El);  // lives until flush_uploads below (uploads are deferred)
   for (int q = 0; q < El; q++) el_rec_h[q] = make_int4(s_pose[q], s_lm[q], s_slot[q], s_flags[q]);
   rc |= upload_vec(c, D.el_rec, el_rec_h);
@@ -1555,8 +1558,7 @@ void graph_release(slam_b200_ctx* c) {
   if (!c->sys) return;
   DeviceSystem& D = *c->sys;
   D.pose_free.release(); D.lm_free.release(); D.pose_boff.release(); D.lm_boff.release();
-  D.el_start.release(); D.el_pose.release(); D.el_lm.release(); D.el_slot.release(); D.el_flags.release();
-  D.el_rec.release();
+  D.el_start.release(); D.el_rec.release();
   D.el_info.release(); D.lm_start.release(); D.lm_edges.release();
   D.eo_i.release(); D.eo_j.release(); D.eo_slot.release(); D.eo_flags.release(); D.po_start.release();
   D.po_list.release(); D.eo_info.release();

@@ -75,8 +75,8 @@ struct DeviceSystem {
   // device structure
   DevBuf<unsigned char> pose_free, lm_free;
   DevBuf<int> pose_boff, lm_boff;  // solver scalar offset or -1
-  DevBuf<int> el_start, el_pose, el_lm, el_slot, el_flags;   // landmark edges sorted by pose
-  DevBuf<int4> el_rec;             // the same four ints as ONE 16-byte record per edge {pose, lm, slot, flags}
+  DevBuf<int> el_start;            // landmark edges sorted by pose: edge range of every pose
+  DevBuf<int4> el_rec;             // ONE 16-byte record per pose-sorted edge {pose, lm, block slot, flags}
   DevBuf<double> el_info;          // [3][El] SoA
   DevBuf<int> lm_start, lm_edges;  // CSR landmark -> sorted edge positions
   DevBuf<int> lmo_pose;            // landmark order: pose of the edge, -1 if inactive

@@ -992,30 +992,38 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   }
   S.upd_rows.assign(S.rows_ptr[nf], 0);
   S.rel.assign(S.rows_ptr[nf], -1);
-  // position of a block's first scalar inside front g (pivot or update row), -1 if absent
-  std::vector<int> rowpos(nb, -1);  // scratch, valid for one front at a time
-  auto fill_rowpos = [&](int g, bool set) {
-    int f = oldid[g];
-    int r = 0;
-    for (int v : nd.nodes[f].verts) { rowpos[v] = set ? r : -1; r += dim[v]; }
-    for (int w : U[f]) { rowpos[w] = set ? r : -1; r += dim[w]; }
-  };
   for (int g = 0; g < nf; g++) {
     int q = S.rows_ptr[g];
     for (int w : U[oldid[g]])
       for (int k = 0; k < dim[w]; k++) S.upd_rows[q++] = S.boff[w] + k;
   }
-  for (int p = 0; p < nf; p++) {  // rel of every child of p
-    if (S.child_ptr[p] == S.child_ptr[p + 1]) continue;
-    fill_rowpos(p, true);
-    for (int ci = S.child_ptr[p]; ci < S.child_ptr[p + 1]; ci++) {
-      int g = S.children[ci];
-      int q = S.rows_ptr[g];
-      for (int w : U[oldid[g]])
-        for (int k = 0; k < dim[w]; k++) S.rel[q++] = rowpos[w] + k;
+  // rel of every child of p / assembly entries of front g: independent per front, each job owns a
+  // scratch row map -- contiguous front ranges on the host pool (result independent of the thread count)
+  HostPool& pool = HostPool::get();
+  const int njobs = std::max(1, std::min(nf, 4 * pool.size()));
+  auto job_range = [&](int j, int& f0, int& f1) { f0 = (int)((long)nf * j / njobs); f1 = (int)((long)nf * (j + 1) / njobs); };
+  auto fill_pos = [&](std::vector<int>& rp, int g, bool set) {
+    const int f = oldid[g];
+    int r = 0;
+    for (int v : nd.nodes[f].verts) { rp[v] = set ? r : -1; r += dim[v]; }
+    for (int w : U[f]) { rp[w] = set ? r : -1; r += dim[w]; }
+  };
+  pool.run(njobs, [&](int j) {
+    int f0, f1;
+    job_range(j, f0, f1);
+    std::vector<int> rp(nb, -1);
+    for (int p = f0; p < f1; p++) {
+      if (S.child_ptr[p] == S.child_ptr[p + 1]) continue;
+      fill_pos(rp, p, true);
+      for (int ci = S.child_ptr[p]; ci < S.child_ptr[p + 1]; ci++) {
+        const int g = S.children[ci];
+        int q = S.rows_ptr[g];
+        for (int w : U[oldid[g]])
+          for (int k = 0; k < dim[w]; k++) S.rel[q++] = rp[w] + k;
+      }
+      fill_pos(rp, p, false);
     }
-    fill_rowpos(p, false);
-  }
+  });
   dbg("rows+rel");
   // storage offsets, statistics
   S.lptr.assign(nf + 1, 0);
@@ -1061,25 +1069,30 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     // off-diagonal blocks grouped by front, so the row map is filled once per front
     std::vector<int> oc(cur), olist(S.asm_ptr[nf]), obase(cur);  // olist is indexed in entry space
     for (int k = 0; k < nnb; k++) olist[oc[off_front[k]]++] = k;
-    for (int g = 0; g < nf; g++) {
-      const int q0 = obase[g], q1 = S.asm_ptr[g + 1];
-      if (q0 == q1) continue;
-      fill_rowpos(g, true);
-      for (int q = q0; q < q1; q++) {
-        const int k = olist[q];
-        const int a = off_a[k], b = off_b[k];
-        const bool aEarlier = S.pos[a] < S.pos[b];
-        const int e = aEarlier ? a : b, l = aEarlier ? b : a;
-        AsmEntry& en = S.asm_entries[q];
-        en.hoff = hoff_off[k];
-        en.c = S.boff[e] - S.piv0[g];
-        en.r = rowpos[l];
-        // stored block is dim[a] x dim[b] (rows a).  We need rows l, columns e.
-        const int trans = (l == a) ? 0 : 1;
-        en.meta = dim[a] | (dim[b] << 8) | (trans << 16);
+    pool.run(njobs, [&](int j) {
+      int f0, f1;
+      job_range(j, f0, f1);
+      std::vector<int> rp(nb, -1);
+      for (int g = f0; g < f1; g++) {
+        const int q0 = obase[g], q1 = S.asm_ptr[g + 1];
+        if (q0 == q1) continue;
+        fill_pos(rp, g, true);
+        for (int q = q0; q < q1; q++) {
+          const int k = olist[q];
+          const int a = off_a[k], b = off_b[k];
+          const bool aEarlier = S.pos[a] < S.pos[b];
+          const int e = aEarlier ? a : b, l = aEarlier ? b : a;
+          AsmEntry& en = S.asm_entries[q];
+          en.hoff = hoff_off[k];
+          en.c = S.boff[e] - S.piv0[g];
+          en.r = rp[l];
+          // stored block is dim[a] x dim[b] (rows a).  We need rows l, columns e.
+          const int trans = (l == a) ? 0 : 1;
+          en.meta = dim[a] | (dim[b] << 8) | (trans << 16);
+        }
+        fill_pos(rp, g, false);
       }
-      fill_rowpos(g, false);
-    }
+    });
   }
   dbg("asm entries");
   S.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
