@@ -638,6 +638,9 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   // on the pool threads.  The split depth is fixed, so the result does not depend on the thread count.
   nd.defer_depth = nb >= 4096 ? 1 : -1;
   nd.order_region(all, 1, roots, 0);
+  if (getenv("SLAM_B200_SYM_DEBUG"))
+    fprintf(stderr, "[symbolic] nd top levels done at %.4f s, %zu deferred parts\n",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), nd.deferred.size());
   if (!nd.deferred.empty()) {
     const int nt = (int)nd.deferred.size();
     std::vector<Nd> sub(nt);
@@ -659,6 +662,8 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     }
     nd.deferred.clear();
   }
+  if (getenv("SLAM_B200_SYM_DEBUG"))
+    fprintf(stderr, "[symbolic] nd parts done at %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   std::vector<int> rank(nb, 0);
   {
     // depth of every nested-dissection node; leaves (no kids) get rank 0, a separator at depth d
