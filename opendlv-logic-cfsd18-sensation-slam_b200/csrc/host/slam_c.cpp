@@ -6,6 +6,7 @@
 
 #include "frame_assembler.hpp"
 #include "slam.hpp"
+#include "wgs84.hpp"
 
 namespace {
 thread_local std::string g_err;
@@ -14,6 +15,11 @@ thread_local std::string g_err;
 extern "C" {
 
 const char* slamhost_last_error() { return g_err.c_str(); }
+
+// GNSS priors (wgs84.hpp): the conversions of Slam::nextPose / nextSplitPose / sendPose
+void slamhost_wgs84_to_cartesian(const double* ref2, const double* pos2, double* out2) { slamwgs84::toCartesian(ref2, pos2, out2); }
+void slamhost_wgs84_from_cartesian(const double* ref2, const double* xy2, double* out2) { slamwgs84::fromCartesian(ref2, xy2, out2); }
+double slamhost_heading_from_north(float northHeading) { return slamwgs84::headingFromNorth(northHeading); }
 
 void* slamhost_create(double sameConeThreshold, double coneMappingThreshold, int conesPerPacket, int cudaDevice) {
   try {

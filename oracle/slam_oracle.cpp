@@ -16,6 +16,9 @@
 // -DORACLE_USE_EIGEN, by running the *reference's own vendored* Eigen 3.3.4
 // SimplicialLDLT<Upper>+AMD (thirdparty/Eigen/src/SparseCholesky/SimplicialCholesky.h:156-238),
 // the solver g2o's LinearSolverEigen wraps.
+// One row is pinned by reference code proper: the WGS84 <-> Cartesian conversion (orc_wgs84_*) is
+// checked bit for bit against vectors produced by compiling src/WGS84toCartesian.hpp itself
+// (tests/golden/make_wgs84_golden.py -> tests/golden/wgs84_vectors.json).
 //
 // Build (see oracle/Makefile): g++ -std=c++14 -O2 -ffp-contract=off, no -march=native, i.e. the
 // reference's own flags (CMakeLists.txt:35-38) so nothing is contracted into FMA.
@@ -23,6 +26,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <limits>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -270,6 +274,87 @@ int orc_assoc_match_only(const double* cones4xN, int N, const double* pose3, dou
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// GNSS priors: WGS84 -> local Cartesian as Slam::nextPose / nextSplitPose apply it (slam.cpp:153-209)
+// and back as Slam::sendPose does (681-695), restated from the reference's vendored
+// src/WGS84toCartesian.hpp (toCartesian 40-118, fromCartesian 125-155).  This is the one row of the
+// path whose arithmetic lives in /root/reference itself, so it IS pinned by reference code:
+// tests/golden/wgs84_vectors.json is generated by compiling that header (make_wgs84_golden.py).
+// =============================================================================================
+namespace wgs84_restated {
+const double PI = 3.14159265358979323846, D2R = PI / 180.0, A = 6378137.0;
+const double F = 1.0 / 298.257223563, ES = 2.0 * F - F * F;
+
+// meridional arc (unit ellipsoid), series coefficients of WGS84toCartesian.hpp:52-72
+static double arc(double lat) {
+  const double q = ES;
+  const double R0 = 1.0 - q * (0.25 + q * (0.046875 + q * (0.01953125 + q * 0.01068115234375)));
+  const double R1 = q * (0.75 - q * (0.046875 + q * (0.01953125 + q * 0.01068115234375)));
+  const double R2T = q * q;
+  const double R2 = R2T * (0.46875 - q * (0.01302083333333333333 + q * 0.00712076822916666666));
+  const double R3T = R2T * q;
+  const double R3 = R3T * (0.36458333333333333333 - q * 0.00569661458333333333);
+  const double R4 = R3T * q * 0.3076171875;
+  const double s = std::sin(lat), cs = std::cos(lat) * s, s2 = s * s;
+  return R0 * lat - cs * (R1 + s2 * (R2 + s2 * (R3 + s2 * R4)));
+}
+
+static void to_cartesian(const double* ref, const double* pos, double* out) {
+  double lat = pos[0] * D2R, lon = pos[1] * D2R;
+  const double ml0 = arc(ref[0] * D2R);
+  const double over = std::abs(lat) - PI / 2.0;
+  if (over > 1.0e-12 || std::abs(lon) > 10.0) { out[0] = out[1] = 0.0; return; }   // :103-105
+  if (std::abs(over) < 1.0e-12) lat = lat < 0.0 ? -1.0 * (PI / 2.0) : PI / 2.0;
+  lon -= ref[1] * D2R;
+  double x = lon, y = -1.0 * ml0;                                                    // :86
+  if (!(std::abs(lat) < 1.0e-10)) {
+    const double sl = std::sin(lat);
+    const double ms = std::abs(sl) > 1.0e-10 ? (std::cos(lat) / std::sqrt(1.0 - ES * sl * sl)) / sl : 0.0;
+    lon *= sl;
+    x = ms * std::sin(lon);
+    y = (arc(lat) - ml0) + ms * (1.0 - std::cos(lon));
+  }
+  out[0] = A * x;
+  out[1] = A * y;
+}
+
+static void from_cartesian(const double* ref, const double* xy, double* out) {
+  double g[2] = {ref[0], ref[1]}, c[2];
+  to_cartesian(ref, g, c);
+  const int sLat = xy[1] < 0 ? -1 : 1, sLon = xy[0] < 0 ? -1 : 1;
+  double prev = std::numeric_limits<double>::max(), d = std::abs(xy[1] - c[1]);
+  while (d < prev && d > 1.0e-2) {          // latitude against the y residual (:137-143)
+    g[0] = g[0] + sLat * 1e-5;
+    to_cartesian(ref, g, c);
+    prev = d;
+    d = std::abs(xy[1] - c[1]);
+  }
+  prev = std::numeric_limits<double>::max();
+  d = std::abs(xy[0] - c[0]);
+  while (d < prev && d > 1.0e-2) {          // longitude against the x residual (:145-152)
+    g[1] = g[1] + sLon * 1e-5;
+    to_cartesian(ref, g, c);
+    prev = d;
+    d = std::abs(xy[0] - c[0]);
+  }
+  out[0] = g[0];
+  out[1] = g[1];
+}
+}  // namespace wgs84_restated
+
+extern "C" {
+void orc_wgs84_to_cartesian(const double* ref2, const double* pos2, double* out2) { wgs84_restated::to_cartesian(ref2, pos2, out2); }
+void orc_wgs84_from_cartesian(const double* ref2, const double* xy2, double* out2) { wgs84_restated::from_cartesian(ref2, xy2, out2); }
+// Slam::nextSplitPose (slam.cpp:176-181): GeodeticHeadingReading -> heading about PI (PI = 3.14159265f)
+double orc_heading_from_north(float northHeading) {
+  double heading = northHeading;
+  heading = heading - PI_REF;
+  heading = (heading > PI_REF) ? (heading - 2 * PI_REF) : (heading);
+  heading = (heading < -PI_REF) ? (heading + 2 * PI_REF) : (heading);
+  return heading;
+}
+}
 
 // =============================================================================================
 // mini-g2o: the Gauss-Newton back end the reference reaches through g2o (slam.hpp:26-35).
