@@ -264,6 +264,17 @@ class OracleSlam:
                 "last_iterations", "n_chi2", "n_edges"]
         return dict(zip(keys, out.tolist()))
 
+    def connectivity_row(self, k):
+        out = np.zeros(4096, dtype=np.int32)
+        n = self.L.orc_slam_connectivity_row(self.h, int(k), _ip(out), len(out))
+        return None if n < 0 else out[:n].copy()
+
+    def poses(self):
+        n = self.L.orc_slam_num_poses(self.h)
+        out = np.zeros((max(n, 1), 3))
+        self.L.orc_slam_get_poses(self.h, _dp(out))
+        return out[:n]
+
     def chi2_log(self):
         n = self.state()["n_chi2"]
         out = np.zeros(max(n, 1))

@@ -1,0 +1,103 @@
+// oracle/ref_slam_replay.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the reference's REAL `class Slam` (compiled from /root/reference/src/slam.cpp + cone.cpp where
+// they lie, g2o replaced by oracle/g2o_facade) through its back half, frame by frame, and records what
+// it decides: which map cones every frame was associated with (the row performSLAM appends to
+// m_connectivityGraph), map size, current-cone index, the loop-closure flags, the pose it stored, and at
+// the end the map, the stored poses and the optimised pose vertices.
+//
+// Slam::performSLAM is private and normally reached from a detached, wall-clock-gated thread
+// (slam.cpp:94,221-257); the harness reaches it with the usual test trick of re-declaring `private`
+// while including slam.hpp -- the reference sources are not modified.  m_odometryData is what
+// Slam::nextPose would have stored (slam.cpp:207-209); the yaw/geolocation stamps stay at their defaults,
+// so the heading correction of performSLAM (309-318) is inactive, as in the oracle's replay.
+//
+// input  (binary, argv[1]): int32 nframes, double sameConeThreshold, double coneMappingThreshold, then per
+//         frame: double pose[3], int32 N, double cones[4*N] (column-major az, zen, range, type)
+// output (text, argv[2]):   one line per frame + a trailer, parsed by tests/golden/make_c1_reference_replay.py
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "g2o_facade.hpp"
+#include <Eigen/Dense>
+#include "cluon-complete.hpp"
+#include "opendlv-standard-message-set.hpp"
+#include "cone.hpp"
+
+#define private public
+#include "slam.hpp"
+#undef private
+
+int main(int argc, char** argv) {
+  if (argc < 3) { std::fprintf(stderr, "usage: ref_slam_replay frames.bin out.txt\n"); return 2; }
+  std::ifstream in(argv[1], std::ios::binary);
+  int32_t nframes = 0;
+  double thr = 0, mapThr = 0;
+  in.read(reinterpret_cast<char*>(&nframes), 4);
+  in.read(reinterpret_cast<char*>(&thr), 8);
+  in.read(reinterpret_cast<char*>(&mapThr), 8);
+  std::map<std::string, std::string> args;
+  args["cid"] = "111";
+  args["gatheringTimeMs"] = "110";
+  args["sameConeThreshold"] = std::to_string(thr);
+  args["refLatitude"] = "57.70924648";
+  args["refLongitude"] = "11.9462";
+  args["timeBetweenKeyframes"] = "0.5";
+  args["coneMappingThreshold"] = std::to_string(mapThr);
+  args["conesPerPacket"] = "20";
+  args["id"] = "120";
+  // the reference prints per observation (slam.cpp:590 and friends): silence stdout for the replay
+  std::ofstream devnull("/dev/null");
+  std::streambuf* saved = std::cout.rdbuf(devnull.rdbuf());
+  cluon::OD4Session od4{111};
+  FILE* out = std::fopen(argv[2], "w");
+  {
+    Slam slam(args, od4);
+    for (int f = 0; f < nframes; f++) {
+      double pose[3];
+      int32_t N = 0;
+      in.read(reinterpret_cast<char*>(pose), 24);
+      in.read(reinterpret_cast<char*>(&N), 4);
+      Eigen::MatrixXd cones(4, N);
+      if (N) in.read(reinterpret_cast<char*>(cones.data()), (std::streamsize)sizeof(double) * 4 * N);
+      slam.m_odometryData << pose[0], pose[1], pose[2];
+      const size_t rows0 = slam.m_connectivityGraph.size();
+      slam.performSLAM(cones);
+      std::fprintf(out, "F %d %zu %u %d %d %d", f, slam.m_map.size(), slam.m_currentConeIndex, (int)slam.m_loopClosing,
+                   (int)slam.m_loopClosingComplete, slam.m_poseId);
+      if (slam.m_connectivityGraph.size() > rows0) {
+        const std::vector<int>& row = slam.m_connectivityGraph.back();
+        std::fprintf(out, " %zu", row.size());
+        for (int id : row) std::fprintf(out, " %d", id);
+      } else {
+        std::fprintf(out, " -1");
+      }
+      std::fprintf(out, "\n");
+    }
+    for (size_t j = 0; j < slam.m_map.size(); j++)
+      std::fprintf(out, "M %zu %a %a %d %d\n", j, slam.m_map[j].getX(), slam.m_map[j].getY(), slam.m_map[j].getType(),
+                   slam.m_map[j].getId());
+    for (size_t k = 0; k < slam.m_poses.size(); k++)
+      std::fprintf(out, "P %zu %a %a %a\n", k, slam.m_poses[k](0), slam.m_poses[k](1), slam.m_poses[k](2));
+    for (int id = 1000; id < slam.m_poseId; id++) {
+      g2o::VertexSE2* v = static_cast<g2o::VertexSE2*>(slam.m_optimizer.vertex(id));
+      const Eigen::Vector3d e = v->estimate().toVector();
+      std::fprintf(out, "V %d %a %a %a\n", id, e(0), e(1), e(2));
+    }
+    for (double c : slam.m_optimizer.last_chi2_) std::fprintf(out, "C %a\n", c);
+    std::fprintf(out, "S %a %a %a\n", slam.m_sendPose(0), slam.m_sendPose(1), slam.m_sendPose(2));
+  }
+  std::fclose(out);
+  std::cout.rdbuf(saved);
+  return 0;
+}

@@ -16,9 +16,12 @@
 // -DORACLE_USE_EIGEN, by running the *reference's own vendored* Eigen 3.3.4
 // SimplicialLDLT<Upper>+AMD (thirdparty/Eigen/src/SparseCholesky/SimplicialCholesky.h:156-238),
 // the solver g2o's LinearSolverEigen wraps.
-// One row is pinned by reference code proper: the WGS84 <-> Cartesian conversion (orc_wgs84_*) is
-// checked bit for bit against vectors produced by compiling src/WGS84toCartesian.hpp itself
-// (tests/golden/make_wgs84_golden.py -> tests/golden/wgs84_vectors.json).
+// Pinned by reference code proper (tests/test_pinned_by_reference.py): (a) the whole association /
+// conversion / graph-building half -- oracle/build_ref_slam.sh compiles the reference's REAL
+// src/slam.cpp with g2o replaced by oracle/g2o_facade (over the Gauss-Newton below) and the C1 replay
+// through it (tests/golden/c1_replay_reference.npz) is reproduced identically by orc_slam_perform;
+// (b) the WGS84 <-> Cartesian conversion (orc_wgs84_*), bit for bit against vectors produced by
+// compiling src/WGS84toCartesian.hpp itself.  What stays unpinned is the g2o arithmetic.
 //
 // Build (see oracle/Makefile): g++ -std=c++14 -O2 -ffp-contract=off, no -march=native, i.e. the
 // reference's own flags (CMakeLists.txt:35-38) so nothing is contracted into FMA.
@@ -1330,6 +1333,20 @@ void orc_slam_state(void* p, int* out8) {
   out8[0] = (int)S.currentConeIndex; out8[1] = S.poseId; out8[2] = S.loopClosing;
   out8[3] = S.loopClosingComplete; out8[4] = S.optimizeCalls; out8[5] = S.lastIterations;
   out8[6] = (int)S.chi2Log.size(); out8[7] = orc_graph_num_edges(S.graph);
+}
+// row k of the connectivity graph (cone ids addConeMeasurement recorded for pose 1000 + k, slam.cpp:549);
+// returns its length (ids are written up to cap), -1 if there is no such row
+int orc_slam_connectivity_row(void* p, int k, int* out, int cap) {
+  OracleSlam& S = *static_cast<OracleSlam*>(p);
+  if (k < 0 || k >= (int)S.connectivity.size()) return -1;
+  const std::vector<int>& r = S.connectivity[k];
+  for (size_t i = 0; i < r.size() && (int)i < cap; i++) out[i] = r[i];
+  return (int)r.size();
+}
+int orc_slam_num_poses(void* p) { return (int)(static_cast<OracleSlam*>(p)->poses.size() / 3); }
+void orc_slam_get_poses(void* p, double* out3n) {
+  OracleSlam& S = *static_cast<OracleSlam*>(p);
+  for (size_t k = 0; k < S.poses.size(); k++) out3n[k] = S.poses[k];
 }
 void orc_slam_chi2_log(void* p, double* out) {
   OracleSlam& S = *static_cast<OracleSlam*>(p);

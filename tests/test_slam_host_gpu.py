@@ -132,6 +132,34 @@ def test_c1_replay_through_slam_class(host, orc, synth, c1_drive):
     s.close()
 
 
+def test_c1_replay_equals_the_reference_slam_cpp(host, synth, c1_drive):
+    """The drop-in Slam (host mirror over the CUDA back end) against what the reference's REAL src/slam.cpp
+    produced on the same drive (tests/golden/c1_replay_reference.npz, made by compiling slam.cpp with the
+    g2o facade: tests/golden/make_c1_reference_replay.py): the cones every frame was associated with or
+    created (drawGraph rows, 8,381 entries), map size / current-cone index / loop-closure flags per frame
+    and the stored poses are identical; optimised map and pose vertices within 1e-6 relative."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_replay_reference.npz"))
+    s = HostSlam(host, synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    for k, (fr, p) in enumerate(zip(c1_drive.frames, c1_drive.poses_noisy)):
+        s.perform(fr, p)
+        st = s.state()
+        assert st[7] == g["frame_map_size"][k] and st[0] == g["frame_cci"][k], k
+        assert st[2] == g["frame_loop_closing"][k] and st[3] == g["frame_loop_closed"][k] and st[1] == g["frame_pose_id"][k], k
+    cnt, flat = s.graph()
+    assert np.array_equal(np.concatenate([[0], np.cumsum(cnt)]), g["row_ptr"])
+    assert np.array_equal(flat, g["row_ids"])
+    assert s.poses().tobytes() == np.ascontiguousarray(g["poses"]).tobytes()
+    x, y, t, ids = s.cones()
+    assert np.array_equal(t, g["map_type"]) and np.array_equal(ids, g["map_id"])
+    scale = max(1.0, np.abs(g["map_x"]).max(), np.abs(g["map_y"]).max())
+    assert np.max(np.abs(x - g["map_x"])) <= 1e-6 * scale and np.max(np.abs(y - g["map_y"])) <= 1e-6 * scale
+    for k in (0, 1, 2, 500, 973, 974, 999):
+        d, e = s.pose_estimate(1000 + k)
+        assert d == 3 and np.max(np.abs(e - g["vertices"][k])) <= 1e-6 * scale, k
+    s.close()
+
+
 def test_burst_of_optimise_calls_and_gates(host, orc, synth, c1_drive):
     """Closing column first in its frame -> one optimise per remaining column (slam.cpp:625-633);
     a pose outside +-200 m is rejected (300-303); the yaw-rate heading correction (315-317)."""
