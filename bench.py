@@ -399,8 +399,56 @@ def bench_frame_assoc(pkg, torch, local, drive, n_frames=300):
     dt = time.perf_counter() - t0
     M = ctx.map_size()
     ctx.close()
-    return {"frames_per_s": n_frames / dt, "assoc_per_s": n_obs / dt, "us_per_frame": dt / n_frames * 1e6,
-            "map_cones": M, "note": "C ABI call incl. H2D/D2H and stream sync per frame"}
+    out = {"frames_per_s": n_frames / dt, "assoc_per_s": n_obs / dt, "us_per_frame": dt / n_frames * 1e6,
+           "map_cones": M, "note": "C ABI call incl. H2D/D2H and stream sync per frame"}
+    # the same drive through the reference's real slam.cpp on a host core (cpu_baseline leg: the checker
+    # is only timed here, never on the product path); at ~8 columns x <= 300 map cones per frame the CPU
+    # loop is faster than a kernel launch + two copies -- the GPU path pays off from config-4 sizes on
+    try:
+        from oracle import oracle
+        ref = oracle.reference_replay_timing(drive.frames, drive.poses_noisy, THR, 50.0)
+    except Exception:  # noqa: BLE001 -- a missing checker must not break the bench line
+        ref = None
+    if ref is not None:
+        out["reference_cpu"] = ref
+    try:
+        out["slam_class"] = bench_slam_class(pkg, local, drive)
+    except Exception as e:  # noqa: BLE001
+        out["slam_class"] = {"error": str(e)[:200]}
+    return out
+
+
+def bench_slam_class(pkg, local, drive):
+    """The whole drive through the drop-in `Slam` class (csrc/host/slam.cpp over the C ABI), timed per frame
+    kind like reference_cpu above: mapping frames, the frame that closes the loop (burst of optimizeGraph
+    calls, slam.cpp:625-633) and the localiser frames after it."""
+    import ctypes as C
+    from importlib import import_module
+    b = import_module(pkg.__name__ + "._build")
+    L = C.CDLL(b.HOSTLIB)
+    c_dp, c_ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    L.slamhost_create.restype = C.c_void_p
+    L.slamhost_create.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+    L.slamhost_destroy.argtypes = [C.c_void_p]
+    L.slamhost_perform.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.c_float, C.c_double, c_ip, c_ip]
+    h = C.c_void_p(L.slamhost_create(THR, 50.0, 20, int(local)))
+    if not h:
+        raise RuntimeError("slamhost_create failed")
+    t = {0: [0.0, 0], 1: [0.0, 0], 2: [0.0, 0]}
+    idx = np.zeros(1024, dtype=np.int32); st = np.zeros(1024, dtype=np.int32)
+    for fr, p in zip(drive.frames, drive.poses_noisy):
+        fr = np.asfortranarray(fr, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64)
+        t0 = time.perf_counter()
+        rc = L.slamhost_perform(h, fr.ctypes.data_as(c_dp), fr.shape[1], p.ctypes.data_as(c_dp), 0.0, 0.0,
+                                idx.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip))
+        dt = time.perf_counter() - t0
+        if rc in t:
+            t[rc][0] += dt; t[rc][1] += 1
+    L.slamhost_destroy(h)
+    return {"mapping_frames": t[0][1], "us_per_mapping_frame": t[0][0] / max(t[0][1], 1) * 1e6,
+            "loop_closing_frames": t[1][1], "ms_per_loop_closing_frame": t[1][0] / max(t[1][1], 1) * 1e3,
+            "localiser_frames": t[2][1], "us_per_localiser_frame": t[2][0] / max(t[2][1], 1) * 1e6,
+            "what": "drop-in Slam class over the C ABI, host clock around performSLAM, whole C1 drive"}
 
 
 def bench_c5(pkg, torch, args, world, rank, local, synth):

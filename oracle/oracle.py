@@ -320,3 +320,36 @@ def load(kind="best") -> Oracle:
 
 def have_reference():
     return os.path.exists(_REF)
+
+
+def reference_replay_timing(frames, poses, thr, map_thr):
+    """Wall time the reference's REAL src/slam.cpp (oracle/_ref/ref_slam_replay, built by build_ref_slam.sh)
+    spends inside performSLAM on a drive, by frame kind.  None when the binary is not there."""
+    import struct
+    import tempfile
+    exe = os.path.join(_HERE, "_ref", "ref_slam_replay")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "frames.bin"), os.path.join(tmp, "out.txt")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<idd", len(frames), thr, map_thr))
+            for fr, p in zip(frames, poses):
+                fr = np.asfortranarray(fr, dtype=np.float64)
+                f.write(np.asarray(p, dtype=np.float64).tobytes())
+                f.write(struct.pack("<i", fr.shape[1]))
+                f.write(fr.tobytes(order="F"))
+        try:
+            subprocess.run([exe, fin, fout], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        except Exception:
+            return None
+        for ln in open(fout):
+            t = ln.split()
+            if t and t[0] == "T":
+                nm, sm, nc, sc, nl, sl = int(t[1]), float(t[2]), int(t[3]), float(t[4]), int(t[5]), float(t[6])
+                return {"mapping_frames": nm, "us_per_mapping_frame": sm / max(nm, 1) * 1e6,
+                        "loop_closing_frames": nc, "ms_per_loop_closing_frame": sc / max(nc, 1) * 1e3,
+                        "localiser_frames": nl, "us_per_localiser_frame": sl / max(nl, 1) * 1e6,
+                        "what": "the reference's real src/slam.cpp (g2o facade over the restated Gauss-Newton), 1 core, "
+                                "time inside performSLAM, its per-observation prints sent to /dev/null"}
+    return None

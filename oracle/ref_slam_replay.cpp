@@ -15,6 +15,7 @@
 // input  (binary, argv[1]): int32 nframes, double sameConeThreshold, double coneMappingThreshold, then per
 //         frame: double pose[3], int32 N, double cones[4*N] (column-major az, zen, range, type)
 // output (text, argv[2]):   one line per frame + a trailer, parsed by tests/golden/make_c1_reference_replay.py
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
@@ -63,6 +64,8 @@ int main(int argc, char** argv) {
   FILE* out = std::fopen(argv[2], "w");
   {
     Slam slam(args, od4);
+    double t_mapping = 0, t_closing = 0, t_localise = 0;  // seconds inside performSLAM, by frame kind
+    int n_mapping = 0, n_closing = 0, n_localise = 0;
     for (int f = 0; f < nframes; f++) {
       double pose[3];
       int32_t N = 0;
@@ -72,7 +75,13 @@ int main(int argc, char** argv) {
       if (N) in.read(reinterpret_cast<char*>(cones.data()), (std::streamsize)sizeof(double) * 4 * N);
       slam.m_odometryData << pose[0], pose[1], pose[2];
       const size_t rows0 = slam.m_connectivityGraph.size();
+      const bool closedBefore = slam.m_loopClosingComplete;
+      const auto c0 = std::chrono::steady_clock::now();
       slam.performSLAM(cones);
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
+      if (closedBefore) { t_localise += dt; n_localise++; }
+      else if (slam.m_loopClosingComplete) { t_closing += dt; n_closing++; }
+      else { t_mapping += dt; n_mapping++; }
       std::fprintf(out, "F %d %zu %u %d %d %d", f, slam.m_map.size(), slam.m_currentConeIndex, (int)slam.m_loopClosing,
                    (int)slam.m_loopClosingComplete, slam.m_poseId);
       if (slam.m_connectivityGraph.size() > rows0) {
@@ -96,6 +105,8 @@ int main(int argc, char** argv) {
     }
     for (double c : slam.m_optimizer.last_chi2_) std::fprintf(out, "C %a\n", c);
     std::fprintf(out, "S %a %a %a\n", slam.m_sendPose(0), slam.m_sendPose(1), slam.m_sendPose(2));
+    // wall time inside performSLAM (stdout of the reference's per-observation prints goes to /dev/null)
+    std::fprintf(out, "T %d %.9f %d %.9f %d %.9f\n", n_mapping, t_mapping, n_closing, t_closing, n_localise, t_localise);
   }
   std::fclose(out);
   std::cout.rdbuf(saved);

@@ -43,6 +43,7 @@ def replay(frames, poses, thr, map_thr, exe=None):
         lines = open(fout).read().split("\n")
     fx = lambda t: float.fromhex(t)
     F, rows, M, P, V, chi2 = [], [], [], [], [], []
+    timing = None
     for ln in lines:
         t = ln.split()
         if not t:
@@ -59,12 +60,16 @@ def replay(frames, poses, thr, map_thr, exe=None):
             V.append([fx(v) for v in t[2:5]])
         elif t[0] == "C":
             chi2.append(fx(t[1]))
+        elif t[0] == "T":
+            timing = dict(mapping_frames=int(t[1]), mapping_s=float(t[2]), closing_frames=int(t[3]), closing_s=float(t[4]),
+                          localise_frames=int(t[5]), localise_s=float(t[6]))
     F = np.array(F, dtype=np.int64).reshape(-1, 5)
     row_ptr = np.zeros(len(rows) + 1, dtype=np.int64)
     ids = []
     for k, r in enumerate(rows):
         ids += (r or [])
         row_ptr[k + 1] = len(ids)
+    replay.last_timing = timing   # not part of the fixture (machine dependent)
     return dict(frame_map_size=F[:, 0], frame_cci=F[:, 1], frame_loop_closing=F[:, 2], frame_loop_closed=F[:, 3],
                 frame_pose_id=F[:, 4], row_ptr=row_ptr, row_ids=np.array(ids, dtype=np.int64),
                 row_present=np.array([r is not None for r in rows]),
