@@ -21,7 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # reference's x86-64 -O2 build (no FMA contraction), to keep gate decisions bit-exact.
 EXTRA = {"assoc.cu": ["-fmad=false"]}
 SOURCES = ["capi.cu", "graph.cu", "solver.cu", "assoc.cu", "symbolic.cpp"]
-HOST_SOURCES = ["host/cone.cpp", "host/slam.cpp", "host/frame_assembler.cpp", "host/wgs84.cpp", "host/slam_c.cpp"]
+HOST_SOURCES = ["host/cone.cpp", "host/slam.cpp", "host/frame_assembler.cpp", "host/wgs84.cpp", "host/rec_reader.cpp", "host/slam_c.cpp"]
 
 
 def _nvcc():

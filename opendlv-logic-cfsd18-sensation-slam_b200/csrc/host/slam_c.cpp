@@ -5,6 +5,7 @@
 #include <string>
 
 #include "frame_assembler.hpp"
+#include "rec_reader.hpp"
 #include "slam.hpp"
 #include "wgs84.hpp"
 
@@ -157,6 +158,78 @@ void frameasm_state(void* h, int* out5) {
   FrameAssembler& a = *static_cast<FrameAssembler*>(h);
   out5[0] = a.frameOpen(); out5[1] = a.framesGathered(); out5[2] = a.framesDroppedByKeyframeGate();
   out5[3] = a.messagesOutOfRange(); out5[4] = a.capacity();
+}
+
+
+// ---- recordings (rec_reader.hpp) ----
+// Decodes every envelope of a .rec file: dataType, senderStamp, sample/sent time stamps, objectId (cone
+// messages) and up to four payload numbers (direction: az, zen; distance: d; type: type; geolocation: lat,
+// lon, altitude, heading; wgs84: lat, lon; heading: north; angular velocity: x, y, z).  Returns the number
+// of envelopes (arrays filled up to cap); stats3 = {bytes skipped, truncated tail bytes, envelopes}.
+int slamrec_read(const char* path, int cap, int32_t* dataType, uint32_t* sender, int64_t* sample_us, int64_t* sent_us,
+                 uint32_t* objectId, double* fields4, int64_t* stats3) {
+  slamrec::Reader r;
+  if (!r.open(path)) { g_err = "cannot open recording"; return -1; }
+  slamrec::Envelope e;
+  int n = 0;
+  while (r.next(e)) {
+    if (n < cap) {
+      dataType[n] = e.dataType; sender[n] = e.senderStamp; sample_us[n] = e.sample_us; sent_us[n] = e.sent_us;
+      uint32_t id = 0, ty = 0;
+      float a = 0, b = 0, c = 0;
+      double la = 0, lo = 0;
+      double* f = fields4 + 4 * (size_t)n;
+      f[0] = f[1] = f[2] = f[3] = 0;
+      switch (e.dataType) {
+        case slamrec::ID_OBJECT_DIRECTION: slamrec::decodeObjectDirection(e.payload, e.payload_len, id, a, b); f[0] = a; f[1] = b; break;
+        case slamrec::ID_OBJECT_DISTANCE: slamrec::decodeObjectDistance(e.payload, e.payload_len, id, a); f[0] = a; break;
+        case slamrec::ID_OBJECT_TYPE: slamrec::decodeObjectType(e.payload, e.payload_len, id, ty); f[0] = ty; break;
+        case slamrec::ID_GEOLOCATION: slamrec::decodeGeolocation(e.payload, e.payload_len, la, lo, a, b); f[0] = la; f[1] = lo; f[2] = a; f[3] = b; break;
+        case slamrec::ID_GEODETIC_WGS84: slamrec::decodeGeodeticWgs84(e.payload, e.payload_len, la, lo); f[0] = la; f[1] = lo; break;
+        case slamrec::ID_GEODETIC_HEADING: slamrec::decodeGeodeticHeading(e.payload, e.payload_len, a); f[0] = a; break;
+        case slamrec::ID_ANGULAR_VELOCITY: slamrec::decodeAngularVelocity(e.payload, e.payload_len, a, b, c); f[0] = a; f[1] = b; f[2] = c; break;
+        default: break;
+      }
+      objectId[n] = id;
+    }
+    n++;
+  }
+  if (stats3) { stats3[0] = (int64_t)r.bytesSkipped(); stats3[1] = (int64_t)r.truncatedTail(); stats3[2] = (int64_t)r.envelopesRead(); }
+  return n;
+}
+
+// Replays a recording through the front half (slamrec::replay).  Frames are returned flattened: ncols[k]
+// columns of frame k at cones + 4 * (sum of earlier ncols); odo3 / yaw / yawElapsed / time_us per frame.
+// stats9 = envelopes, coneMessages, poseMessages, ignoredSender, ignoredType, malformed, framesGathered,
+// framesDroppedByKeyframeGate, framesEmitted.  Returns the number of frames emitted.
+int slamrec_replay(const char* path, uint32_t detectConeId, uint32_t estimationId, int gatheringTimeMs,
+                   double timeBetweenKeyframes, double refLat, double refLon, int capFrames, int capCols, int32_t* ncols,
+                   double* cones, double* odo3, float* yaw, double* yawElapsed, int64_t* time_us, int64_t* stats9) {
+  slamrec::Reader r;
+  if (!r.open(path)) { g_err = "cannot open recording"; return -1; }
+  slamrec::ReplayConfig cfg;
+  cfg.detectConeId = detectConeId; cfg.estimationId = estimationId; cfg.gatheringTimeMs = gatheringTimeMs;
+  cfg.timeBetweenKeyframes = timeBetweenKeyframes; cfg.refLatitude = refLat; cfg.refLongitude = refLon;
+  int nf = 0;
+  long used = 0;
+  slamrec::ReplayStats st = slamrec::replay(r, cfg, [&](const slamrec::ReplayFrame& f) {
+    const int n = (int)f.cones.cols();
+    if (nf < capFrames && used + n <= capCols) {
+      ncols[nf] = n;
+      for (int j = 0; j < n; j++)
+        for (int q = 0; q < 4; q++) cones[4 * (used + j) + q] = f.cones(q, j);
+      odo3[3 * nf] = f.odometry[0]; odo3[3 * nf + 1] = f.odometry[1]; odo3[3 * nf + 2] = f.odometry[2];
+      yaw[nf] = f.yawRate; yawElapsed[nf] = f.yawElapsed; time_us[nf] = f.time_us;
+      used += n;
+    }
+    nf++;
+  });
+  if (stats9) {
+    const int64_t v[9] = {(int64_t)st.envelopes, (int64_t)st.coneMessages, (int64_t)st.poseMessages, (int64_t)st.ignoredSender,
+                          (int64_t)st.ignoredType, (int64_t)st.malformed, st.framesGathered, st.framesDroppedByKeyframeGate, st.framesEmitted};
+    for (int k = 0; k < 9; k++) stats9[k] = v[k];
+  }
+  return nf;
 }
 
 }  // extern "C"
