@@ -232,4 +232,30 @@ int slamrec_replay(const char* path, uint32_t detectConeId, uint32_t estimationI
   return nf;
 }
 
+// Recording -> front half on recorded time -> the drop-in Slam: every keyframe the replay releases goes
+// through setOdometry / setYawRate / performSLAM exactly as Slam::initializeCollection would hand it over
+// (slam.cpp:248-255).  Returns the number of frames performed, -1 if the file cannot be read, -100 on error.
+int slamrec_replay_into_slam(const char* path, void* slam, uint32_t detectConeId, uint32_t estimationId, int gatheringTimeMs,
+                             double timeBetweenKeyframes, double refLat, double refLon) {
+  try {
+    slamrec::Reader r;
+    if (!r.open(path)) { g_err = "cannot open recording"; return -1; }
+    slamrec::ReplayConfig cfg;
+    cfg.detectConeId = detectConeId; cfg.estimationId = estimationId; cfg.gatheringTimeMs = gatheringTimeMs;
+    cfg.timeBetweenKeyframes = timeBetweenKeyframes; cfg.refLatitude = refLat; cfg.refLongitude = refLon;
+    Slam& s = *static_cast<Slam*>(slam);
+    int n = 0;
+    slamrec::replay(r, cfg, [&](const slamrec::ReplayFrame& f) {
+      s.setOdometry(f.odometry[0], f.odometry[1], f.odometry[2]);
+      s.setYawRate(f.yawRate, f.yawElapsed);
+      s.performSLAM(f.cones);
+      n++;
+    });
+    return n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -100;
+  }
+}
+
 }  // extern "C"

@@ -195,6 +195,43 @@ def test_adversarial_replays_equal_the_reference_slam_cpp(host, synth):
         s.close()
 
 
+def test_recording_replay_into_slam_equals_direct_calls(host, synth):
+    """tests/golden/c1_head.rec (written by the reference's own cluon) replayed through the front half into the
+    drop-in Slam gives exactly the state that feeding the same keyframes to performSLAM by hand gives."""
+    import os
+    import sys
+    here = os.path.dirname(__file__)
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_rec_golden as gen
+    rec = os.path.join(here, "golden", "c1_head.rec").encode()
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    host.slamrec_replay.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                    i32p, c_dp, c_dp, C.POINTER(C.c_float), c_dp, i64p, i64p]
+    host.slamrec_replay_into_slam.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_double, C.c_double, C.c_double]
+    nc = np.zeros(256, dtype=np.int32); cones = np.zeros(4 * 8192); odo = np.zeros((256, 3)); yaw = np.zeros(256, dtype=np.float32)
+    el = np.zeros(256); tu = np.zeros(256, dtype=np.int64); st = np.zeros(9, dtype=np.int64)
+    n = host.slamrec_replay(rec, gen.DETECT_CONE_ID, gen.ESTIMATION_ID, 10, 0.5, gen.REF_LAT, gen.REF_LON, 256, 8192,
+                            nc.ctypes.data_as(i32p), cones.ctypes.data_as(c_dp), odo.ctypes.data_as(c_dp),
+                            yaw.ctypes.data_as(C.POINTER(C.c_float)), el.ctypes.data_as(c_dp), tu.ctypes.data_as(i64p), st.ctypes.data_as(i64p))
+    assert n == 40
+    a = HostSlam(host, synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    done = host.slamrec_replay_into_slam(rec, a.h, gen.DETECT_CONE_ID, gen.ESTIMATION_ID, 10, 0.5, gen.REF_LAT, gen.REF_LON)
+    assert done == 40, host.slamhost_last_error()
+    b = HostSlam(host, synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD)
+    off = 0
+    for k in range(n):
+        fr = cones[4 * off:4 * (off + nc[k])].reshape(nc[k], 4).T
+        off += nc[k]
+        b.perform(fr, odo[k], float(yaw[k]), float(el[k]))
+    assert np.array_equal(a.state(), b.state()) and a.state()[7] > 20            # same map size, indices, flags
+    for u, v in zip(a.cones(), b.cones()):
+        assert np.array_equal(u, v)
+    ca, fa = a.graph(); cb, fb = b.graph()
+    assert np.array_equal(ca, cb) and np.array_equal(fa, fb) and len(ca) == 40
+    assert a.poses().tobytes() == b.poses().tobytes()
+    a.close(); b.close()
+
+
 def test_burst_of_optimise_calls_and_gates(host, orc, synth, c1_drive):
     """Closing column first in its frame -> one optimise per remaining column (slam.cpp:625-633);
     a pose outside +-200 m is rejected (300-303); the yaw-rate heading correction (315-317)."""
