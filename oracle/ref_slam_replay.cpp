@@ -13,7 +13,10 @@
 // so the heading correction of performSLAM (309-318) is inactive, as in the oracle's replay.
 //
 // input  (binary, argv[1]): int32 nframes, double sameConeThreshold, double coneMappingThreshold, then per
-//         frame: double pose[3], int32 N, double cones[4*N] (column-major az, zen, range, type)
+//         frame: double pose[3], int32 N, double cones[4*N] (column-major az, zen, range, type).
+//         nframes < 0 = extended records: every frame additionally carries float yawRate, int64 elapsed_us
+//         BEFORE the pose; they become m_yawRate and the distance between m_yawReceivedTime and m_lastTimeStamp,
+//         which drives the heading correction of performSLAM (slam.cpp:309-318).
 // output (text, argv[2]):   one line per frame + a trailer, parsed by tests/golden/make_c1_reference_replay.py
 #include <chrono>
 #include <cstdint>
@@ -45,6 +48,8 @@ int main(int argc, char** argv) {
   int32_t nframes = 0;
   double thr = 0, mapThr = 0;
   in.read(reinterpret_cast<char*>(&nframes), 4);
+  const bool extended = nframes < 0;
+  if (extended) nframes = -nframes;
   in.read(reinterpret_cast<char*>(&thr), 8);
   in.read(reinterpret_cast<char*>(&mapThr), 8);
   std::map<std::string, std::string> args;
@@ -69,6 +74,17 @@ int main(int argc, char** argv) {
     for (int f = 0; f < nframes; f++) {
       double pose[3];
       int32_t N = 0;
+      if (extended) {
+        float yawRate = 0;
+        int64_t elapsed_us = 0;
+        in.read(reinterpret_cast<char*>(&yawRate), 4);
+        in.read(reinterpret_cast<char*>(&elapsed_us), 8);
+        slam.m_yawRate = yawRate;                                   // what Slam::nextYawRate stores (slam.cpp:216)
+        cluon::data::TimeStamp zero, later;
+        later.seconds((int32_t)(elapsed_us / 1000000)).microseconds((int32_t)(elapsed_us % 1000000));
+        slam.m_yawReceivedTime = zero;                              // 217
+        slam.m_lastTimeStamp = later;                               // nextCone, 73 / 102 / 129
+      }
       in.read(reinterpret_cast<char*>(pose), 24);
       in.read(reinterpret_cast<char*>(&N), 4);
       Eigen::MatrixXd cones(4, N);

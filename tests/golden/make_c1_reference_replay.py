@@ -28,14 +28,17 @@ sys.path.insert(0, ROOT)
 from conftest import load_pkg  # noqa: E402
 
 
-def replay(frames, poses, thr, map_thr, exe=None):
+def replay(frames, poses, thr, map_thr, exe=None, yaw=None):
+    """yaw: optional per-frame (float32 yawRate, int elapsed_us) -> extended records (heading correction)."""
     exe = exe or os.path.join(ROOT, "oracle", "_ref", "ref_slam_replay")
     with tempfile.TemporaryDirectory() as tmp:
         fin, fout = os.path.join(tmp, "frames.bin"), os.path.join(tmp, "out.txt")
         with open(fin, "wb") as f:
-            f.write(struct.pack("<idd", len(frames), thr, map_thr))
-            for fr, p in zip(frames, poses):
+            f.write(struct.pack("<idd", -len(frames) if yaw is not None else len(frames), thr, map_thr))
+            for k, (fr, p) in enumerate(zip(frames, poses)):
                 fr = np.asfortranarray(fr, dtype=np.float64)
+                if yaw is not None:
+                    f.write(struct.pack("<fq", float(yaw[k][0]), int(yaw[k][1])))
                 f.write(np.asarray(p, dtype=np.float64).tobytes())
                 f.write(struct.pack("<i", fr.shape[1]))
                 f.write(fr.tobytes(order="F"))

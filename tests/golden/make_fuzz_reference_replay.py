@@ -54,6 +54,26 @@ def scenarios(synth):
     return out
 
 
+def scenarios_yaw(synth):
+    """Replays that exercise the heading correction of performSLAM (slam.cpp:309-318): a yaw rate and the time
+    between the yaw reading and the last cone message per frame -- inside (0, 1) s the heading is corrected,
+    at 0 or beyond 1 s it is not.  Returns (name, frames, poses, thr, map_thr, yaw[(float32 rate, elapsed_us)])."""
+    out = []
+    for k in range(4):
+        rng = np.random.default_rng(300 + k)
+        trk = synth.ellipse_track(n_pairs=24 + 2 * k, a=20.0 + 2 * k, b=10.0 + k, half_width=1.5)
+        n = 240
+        d = synth.simulate_drive(trk, n, s_step=1.4 * trk.length / n, seed=90 + k, sigma_r=0.05, sigma_az=0.3)
+        frames = [np.asfortranarray(f, dtype=np.float64).copy() for f in d.frames]
+        yaw = []
+        for i in range(n):
+            rate = np.float32(rng.normal(0.0, 0.3))
+            el = int(rng.choice([0, 1, 999_999, 1_000_000, 1_000_001, 2_500_000, int(rng.integers(1, 1_000_000)), int(rng.integers(1, 1_000_000))]))
+            yaw.append((rate, el))
+        out.append(("yaw%d" % k, frames, d.poses_noisy.copy(), 1.2, 50.0, yaw))
+    return out
+
+
 def main():
     import subprocess
     from conftest import load_pkg
@@ -69,6 +89,15 @@ def main():
         print("%-6s frames %3d  map %3d cones  loop closed at %4d  %5d association entries  NaN cones %d"
               % (name, len(frames), len(r["map_x"]), closed, len(r["row_ids"]), int(np.isnan(r["map_x"]).sum())))
     np.savez_compressed(os.path.join(HERE, "fuzz_replay_reference.npz"), **store)
+    store = {}
+    for name, frames, poses, thr, map_thr, yaw in scenarios_yaw(pkg.synth):
+        r = replay(frames, poses, thr, map_thr, yaw=yaw)
+        for key, val in r.items():
+            store[name + "/" + key] = val
+        closed = int(np.argmax(r["frame_loop_closed"])) if r["frame_loop_closed"].any() else -1
+        print("%-6s frames %3d  map %3d cones  loop closed at %4d  %5d association entries"
+              % (name, len(frames), len(r["map_x"]), closed, len(r["row_ids"])))
+    np.savez_compressed(os.path.join(HERE, "fuzz_yaw_replay_reference.npz"), **store)
 
 
 if __name__ == "__main__":
