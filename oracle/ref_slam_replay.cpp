@@ -42,8 +42,41 @@
 #include "slam.hpp"
 #undef private
 
+// `ref_slam_replay --conv in.txt out.txt`: the reference's private conversion helpers on their own.  Input
+// lines "az zen range type px py ptheta" (hex floats); output per line: transformConeToCoG (2), Spherical2Cartesian
+// (3), coneToGlobal (3), all as hex floats.
+static int conversions(const char* fin, const char* fout) {
+  std::map<std::string, std::string> args;
+  args["gatheringTimeMs"] = "110"; args["sameConeThreshold"] = "1.2"; args["refLatitude"] = "57.70924648";
+  args["refLongitude"] = "11.9462"; args["timeBetweenKeyframes"] = "0.5"; args["coneMappingThreshold"] = "50";
+  args["conesPerPacket"] = "20"; args["id"] = "120";
+  std::ofstream devnull("/dev/null");
+  std::streambuf* saved = std::cout.rdbuf(devnull.rdbuf());
+  cluon::OD4Session od4{111};
+  FILE* in = std::fopen(fin, "r");
+  FILE* out = std::fopen(fout, "w");
+  if (!in || !out) return 2;
+  {
+    Slam slam(args, od4);
+    double az, zen, rng, type, px, py, pt;
+    while (std::fscanf(in, " %la %la %la %la %la %la %la", &az, &zen, &rng, &type, &px, &py, &pt) == 7) {
+      const Eigen::Vector2d cog = slam.transformConeToCoG(az, rng);
+      const Eigen::Vector3d xyz = slam.Spherical2Cartesian(az, zen, rng);
+      Eigen::MatrixXd col(4, 1);
+      col << az, zen, rng, type;
+      const Eigen::Vector3d g = slam.coneToGlobal(Eigen::Vector3d(px, py, pt), col);
+      std::fprintf(out, "%a %a %a %a %a %a %a %a\n", cog(0), cog(1), xyz(0), xyz(1), xyz(2), g(0), g(1), g(2));
+    }
+  }
+  std::fclose(in);
+  std::fclose(out);
+  std::cout.rdbuf(saved);
+  return 0;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 3) { std::fprintf(stderr, "usage: ref_slam_replay frames.bin out.txt\n"); return 2; }
+  if (argc == 4 && std::string(argv[1]) == "--conv") return conversions(argv[2], argv[3]);
+  if (argc < 3) { std::fprintf(stderr, "usage: ref_slam_replay frames.bin out.txt | --conv in.txt out.txt\n"); return 2; }
   std::ifstream in(argv[1], std::ios::binary);
   int32_t nframes = 0;
   double thr = 0, mapThr = 0;
