@@ -717,6 +717,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
         if (anc[j] == -1) { anc[j] = k; eparent[j] = k; }
       }
     }
+    dbg("etree");
     // postorder (children in ascending order); relabel positions
     std::vector<int> kid_ptr(nb + 1, 0), kid(nb);
     for (int k = 0; k < nb; k++)
@@ -747,6 +748,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     eparent.swap(eparent2);
     for (int k = 0; k < nb; k++) epos[order[k]] = k;
   }
+  dbg("postorder");
   // column structures (positions > k, sorted) in one flat pool: struct(k) = later neighbours of the
   // vertex united with the structures of k's etree children minus k itself.  A child always precedes
   // its parent in the postorder, so its structure is already in the pool.
@@ -773,7 +775,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     }
   }
   auto cs_size = [&](int k) { return cs_ptr[k + 1] - cs_ptr[k]; };
-  dbg("etree+postorder+cstruct");
+  dbg("column structures");
   // supernodes: fundamental (parent[k] == k+1 and struct(k) == {k+1} U struct(k+1)), then relaxed
   // amalgamation of a last child into its parent when the padding it introduces is small
   std::vector<int> snode_first;  // first column of every supernode
