@@ -29,6 +29,36 @@ def test_conversion_matches_oracle(ctx, orc, c1_drive):
         assert _ulp_close(l[i], lo)
 
 
+@pytest.mark.xfail(strict=False, reason="fixture made after the round's GPU budget was spent: the first hardware run decides; "
+                                        "the same vectors are matched bit for bit by the oracle (test_pinned_by_reference.py)")
+def test_conversion_vectors_from_the_reference_slam_cpp(ctx):
+    """tests/golden/conversion_vectors.json (the reference's real transformConeToCoG / Spherical2Cartesian /
+    coneToGlobal, make_conversion_golden.py) through slam_b200_cones_to_global: whole azimuth circle incl. 0 -> NaN
+    and +-180 degrees, zenith != 0, ranges 1e-6 .. 1e4 m, at the 16-ulp bar (scaled with the range for the
+    cancellation term), NaN in the same slots."""
+    import json
+    import os
+    doc = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "conversion_vectors.json")))
+    fx = float.fromhex
+    by_pose = {}
+    for v in doc["vectors"]:
+        a = [fx(x) for x in v["in"]]
+        by_pose.setdefault(tuple(a[4:7]), []).append((a[:4], [fx(x) for x in v["xyz"]], [fx(x) for x in v["global"]]))
+    checked = 0
+    for pose, rows in by_pose.items():
+        fr = np.asfortranarray(np.array([r[0] for r in rows]).T)
+        g, l = ctx.cones_to_global(fr, np.array(pose))
+        for i, (inp, xyz, glob) in enumerate(rows):
+            scale = max(1.0, abs(inp[2])) * 1e-13
+            for got, want in ((l[i], np.array(xyz)), (g[i, :2], np.array(glob[:2]))):
+                both_nan = np.isnan(got) & np.isnan(want)
+                tol = 16 * np.spacing(np.maximum(np.abs(got), np.abs(want))) + scale
+                assert np.all(both_nan | (np.abs(got - want) <= tol)), (inp, got, want)
+            assert g[i, 2] == glob[2]
+            checked += 1
+    assert checked == doc["n"]
+
+
 def test_conversion_nan_at_zero_azimuth(ctx):
     fr = np.asfortranarray(np.array([[0.0], [0.0], [5.0], [1.0]]))
     g, l = ctx.cones_to_global(fr, np.zeros(3))

@@ -232,6 +232,30 @@ def test_recording_replay_into_slam_equals_direct_calls(host, synth):
     a.close(); b.close()
 
 
+@pytest.mark.xfail(strict=False, reason="fixture made after the round's GPU budget was spent: the first hardware run decides; "
+                                        "the oracle reproduces it identically (test_pinned_by_reference.py)")
+def test_heading_correction_replays_equal_the_reference_slam_cpp(host, synth):
+    """performSLAM's heading correction (slam.cpp:309-318) through the drop-in Slam (setYawRate) against the
+    reference's real slam.cpp: tests/golden/fuzz_yaw_replay_reference.npz."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_fuzz_reference_replay import scenarios_yaw
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fuzz_yaw_replay_reference.npz"))
+    for name, frames, poses, thr, map_thr, yaw in scenarios_yaw(synth):
+        s = HostSlam(host, thr, map_thr)
+        for k, (fr, p) in enumerate(zip(frames, poses)):
+            s.perform(fr, p, float(yaw[k][0]), abs(float(yaw[k][1])) / 1000000)
+            st = s.state()
+            got = (int(st[7]), int(st[0]), int(st[2]), int(st[3]), int(st[1]))
+            want = tuple(int(g[name + "/" + key][k]) for key in ("frame_map_size", "frame_cci", "frame_loop_closing", "frame_loop_closed", "frame_pose_id"))
+            assert got == want, (name, k, got, want)
+        cnt, flat = s.graph()
+        assert np.array_equal(np.concatenate([[0], np.cumsum(cnt)]), g[name + "/row_ptr"]) and np.array_equal(flat, g[name + "/row_ids"]), name
+        assert s.poses().tobytes() == np.ascontiguousarray(g[name + "/poses"]).tobytes(), name
+        s.close()
+
+
 def test_burst_of_optimise_calls_and_gates(host, orc, synth, c1_drive):
     """Closing column first in its frame -> one optimise per remaining column (slam.cpp:625-633);
     a pose outside +-200 m is rejected (300-303); the yaw-rate heading correction (315-317)."""
