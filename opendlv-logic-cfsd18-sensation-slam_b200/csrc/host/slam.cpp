@@ -3,6 +3,7 @@
 // conversion, gating, linearisation, assembly and solve run in the CUDA library.
 #include "slam.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <iostream>
 #include <stdexcept>
@@ -26,6 +27,10 @@ Slam::Slam(std::map<std::string, std::string> commandlineArguments)
   int device = 0;
   auto it = commandlineArguments.find("cudaDevice");
   if (it != commandlineArguments.end()) device = std::stoi(it->second);
+  it = commandlineArguments.find("localizerWindow");
+  if (it != commandlineArguments.end()) m_localizerWindow = std::max(1, std::stoi(it->second));
+  it = commandlineArguments.find("localizerRepair");
+  if (it != commandlineArguments.end()) m_localizerRepair = std::stoi(it->second) != 0;
   // setupOptimizer (slam.cpp:53-65): the GN / block solver / linear solver stack lives in the backend
   int rc = slam_b200_create(device, nullptr, &m_ctx);
   if (rc != 0) throw std::runtime_error("slam_b200_create failed: no CUDA device (no CPU fallback)");
@@ -181,6 +186,24 @@ void Slam::optimizeGraph() {
   m_optimizeCalls++;
 }
 
+void Slam::setLocalizerRepair(bool on, int window) {
+  std::lock_guard<std::mutex> lockOptimizer(m_optimizerMutex);
+  m_localizerRepair = on;
+  m_localizerWindow = std::max(1, window);
+}
+
+// Repaired localiser only (opt-in): the optimise of slam.cpp:403 over the last m_localizerWindow poses
+// against the frozen map.  Landmarks are fixed once, poses leave the window for good as it moves on.
+void Slam::optimizeWindow() {
+  if (!m_landmarksFrozen) {
+    for (size_t j = 0; j < m_map.size(); j++) slam_b200_graph_set_fixed(m_ctx, (int)j, 1);
+    m_landmarksFrozen = true;
+  }
+  for (; m_nextPoseToFix < m_poseId - m_localizerWindow; m_nextPoseToFix++)
+    slam_b200_graph_set_fixed(m_ctx, m_nextPoseToFix, 1);
+  optimizeGraph();
+}
+
 // slam.cpp:713-732: landmark estimates -> map (host mirror and device map)
 void Slam::updateMap() {
   const size_t M = m_map.size();
@@ -216,7 +239,16 @@ void Slam::localizer(Vector3d pose, MatrixXd cones) {
                                             idx.data(), nullptr, &reobs, &send);
     check(m_ctx, rc, "assoc_localize_frame");
     std::lock_guard<std::mutex> lockOptimizer(m_optimizerMutex);
-    if (reobs > 0) {
+    if (m_localizerRepair) {
+      if (reobs > 0) {
+        // opt-in repair: the edge carries Spherical2Cartesian(observation), what 373 meant
+        std::vector<double> local(3 * (size_t)n);
+        check(m_ctx, slam_b200_cones_to_global(m_ctx, cones.data(), n, p, nullptr, local.data()), "cones_to_global");
+        for (int i = 0; i < n; i++)
+          if (idx[i] >= 0) addConeMeasurement(m_map[idx[i]], &local[3 * (size_t)i]);
+        optimizeWindow();
+      }
+    } else if (reobs > 0) {
       // 373: addConeMeasurement(m_map[j], pose) -- the reference hands the POSE where a measurement
       // (azimuth, zenith, range) is expected; reproduced: Spherical2Cartesian(pose) is the edge's z.
       const double asObs[4] = {pose(0), pose(1), pose(2), 0};

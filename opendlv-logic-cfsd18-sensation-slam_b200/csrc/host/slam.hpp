@@ -41,7 +41,8 @@ class Slam {
   // Same configuration map as the reference constructor (src/slam.cpp:25-51, setUp 736-756):
   // keys gatheringTimeMs, sameConeThreshold, refLatitude, refLongitude, timeBetweenKeyframes,
   // coneMappingThreshold, conesPerPacket, id.  Throws like std::stoi/std::stod on a missing key.
-  // Extra optional key "cudaDevice" (default 0).
+  // Extra optional keys: "cudaDevice" (default 0); "localizerRepair" (default 0) and "localizerWindow"
+  // (default 10), see setLocalizerRepair().
   explicit Slam(std::map<std::string, std::string> commandlineArguments);
   ~Slam();
 
@@ -59,6 +60,11 @@ class Slam {
   // The packet sendCones() emits: the next conesPerPacket map cones from m_currentConeIndex on, with
   // wrap-around (slam.cpp:666-677), bearing/range relative to the last sent pose.
   std::vector<ConePacketEntry> buildConePacket();
+  // SURVEY 8(f) rank 3 -- OPT-IN, off by default (off = the reference's behaviour, bug included).
+  // On: a localiser frame adds pose -> cone edges whose measurement is the OBSERVATION (slam.cpp:373
+  // hands addConeMeasurement the pose) and runs the optimise slam.cpp:403 leaves commented out, as a
+  // sliding window: map frozen (every landmark fixed), poses older than the last `window` fixed.
+  void setLocalizerRepair(bool on, int window);
 
   // ---- introspection for tests ----
   bool loopClosing() const { return m_loopClosing; }
@@ -80,6 +86,7 @@ class Slam {
   void tearDown();
   void addOdometryMeasurement(slamtypes::Vector3d pose);
   void optimizeGraph();
+  void optimizeWindow();
   void localizer(slamtypes::Vector3d pose, slamtypes::MatrixXd cones);
   slamtypes::Vector3d updatePoseFromGraph();
   void addPoseToGraph(slamtypes::Vector3d pose);
@@ -117,6 +124,11 @@ class Slam {
   uint32_t m_senderStamp = 0;
   float m_yawRate = 0.0f;
   double m_yawElapsed = 0.0;
+  // opt-in localiser repair (not in the reference)
+  bool m_localizerRepair = false;
+  int m_localizerWindow = 10;
+  bool m_landmarksFrozen = false;
+  int m_nextPoseToFix = 1000;
 
   // bookkeeping the tests read
   int m_optimizeCalls = 0, m_lastIterations = 0, m_lastFrameKind = 0;

@@ -54,6 +54,8 @@ int slamhost_create_missing_key_throws() {
 }
 
 void slamhost_destroy(void* h) { delete static_cast<Slam*>(h); }
+// opt-in localiser repair, see Slam::setLocalizerRepair
+void slamhost_set_localizer_repair(void* h, int on, int window) { static_cast<Slam*>(h)->setLocalizerRepair(on != 0, window); }
 
 // one frame: what initializeCollection hands to performSLAM (slam.cpp:254) after nextPose stored
 // the odometry.  Returns the frame kind (-1 rejected, 0 mapping, 1 loop closed, 2 localiser) or -100.

@@ -58,6 +58,7 @@ class Oracle:
         L.orc_graph_add_pose.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
         L.orc_graph_add_landmark.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.orc_slam_perform.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.c_double, C.c_double, c_ip, c_ip]
+        L.orc_slam_set_localizer_repair.argtypes = [C.c_void_p, C.c_int, C.c_int]
 
     # ---- conversions -----------------------------------------------------------------------
     def transform_cone_to_cog(self, angle, distance):
@@ -248,6 +249,10 @@ class OracleSlam:
         if getattr(self, "h", None):
             self.L.orc_slam_destroy(self.h)
             self.h = None
+
+    def set_localizer_repair(self, on=True, window=10):
+        """SURVEY 8(f) rank 3, opt-in: observation edges + sliding-window optimise in localiser frames."""
+        self.L.orc_slam_set_localizer_repair(self.h, int(bool(on)), int(window))
 
     def perform(self, frame, pose, yaw_rate=0.0, time_elapsed=0.0):
         frame = np.asfortranarray(frame, dtype=np.float64)

@@ -1209,6 +1209,10 @@ struct OracleSlam {
   int optimizeCalls = 0;
   std::vector<double> chi2Log;                     // chi2 of every GN iteration ever run
   int lastIterations = 0;
+  // SURVEY 8(f) rank 3, OPT-IN (default off = the reference's behaviour, bug included): see
+  // orc_slam_set_localizer_repair below.
+  int localizerRepair = 0, localizerWindow = 10;
+  int landmarksFrozen = 0, nextPoseToFix = 1000;
   ~OracleSlam() { orc_graph_destroy(graph); }
 
   void addConeMeasurement(int coneId, const double m3[3]) {  // 537-550
@@ -1227,6 +1231,17 @@ struct OracleSlam {
     lastIterations = orc_graph_optimize(graph, 10, chi2);
     for (int k = 0; k < lastIterations; k++) chi2Log.push_back(chi2[k]);
     optimizeCalls++;
+  }
+  // Repaired localiser only: the optimise slam.cpp:403 leaves commented out, as a sliding window.
+  // The map is frozen after loop closure (every landmark fixed, once), poses older than the last
+  // `localizerWindow` ones are fixed for good as the window moves on, the gauge is the reference's.
+  void optimizeWindow() {
+    if (!landmarksFrozen) {
+      for (size_t j = 0; j < map_x.size(); j++) orc_graph_set_fixed(graph, (int)j, 1);
+      landmarksFrozen = 1;
+    }
+    for (; nextPoseToFix < poseId - localizerWindow; nextPoseToFix++) orc_graph_set_fixed(graph, nextPoseToFix, 1);
+    optimizeGraph();
   }
   void updateMap() {  // 713-732
     for (size_t j = 0; j < map_x.size(); j++) {
@@ -1248,6 +1263,14 @@ void* orc_slam_create(double sameConeThreshold, double coneMappingThreshold) {
   return s;
 }
 void orc_slam_destroy(void* p) { delete static_cast<OracleSlam*>(p); }
+// SURVEY 8(f) rank 3 (behaviour change, hence opt-in): localiser frames add pose -> cone edges whose
+// measurement is the observation instead of the pose slam.cpp:373 passes, and run the optimise that
+// slam.cpp:403 comments out over the last `window` poses against the frozen map.
+void orc_slam_set_localizer_repair(void* p, int on, int window) {
+  OracleSlam& S = *static_cast<OracleSlam*>(p);
+  S.localizerRepair = on != 0;
+  S.localizerWindow = window > 0 ? window : 1;
+}
 
 // performSLAM.  idx/status (N each) receive the per-observation association records of this
 // frame (mapping phase: as orc_assoc_map_frame; localisation phase: status 0/2).
@@ -1310,8 +1333,15 @@ int orc_slam_perform(void* p, const double* cones4xN, int N, const double* pose_
     orc_assoc_localize_frame(cones4xN, N, pose, S.newConeThreshold, S.map_x.data(), S.map_y.data(),
                              S.map_type.data(), (int)S.map_x.size(), &S.currentConeIndex,
                              lidx.data(), g.data(), &reobs, &send);
-    for (int i = 0; i < N; i++)
-      if (lidx[i] >= 0) S.addConeMeasurement(lidx[i], pose);  // 373: passes the POSE (sic)
+    if (S.localizerRepair) {
+      // opt-in repair: the edge carries the OBSERVATION (what 373 meant), then the window optimise
+      for (int i = 0; i < N; i++)
+        if (lidx[i] >= 0) S.addConeMeasurement(lidx[i], cones4xN + 4 * (size_t)i);
+      if (reobs > 0) S.optimizeWindow();
+    } else {
+      for (int i = 0; i < N; i++)
+        if (lidx[i] >= 0) S.addConeMeasurement(lidx[i], pose);  // 373: passes the POSE (sic)
+    }
     if (ret == 0) {
       for (int i = 0; i < N; i++) { idx[i] = lidx[i]; status[i] = lidx[i] >= 0 ? 0 : 2; }
       ret = 2;

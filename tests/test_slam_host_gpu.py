@@ -290,3 +290,20 @@ def test_constructor_and_cone_accessors(host):
     assert dist.value == pytest.approx(5.0)
     want = np.degrees(np.arctan2(4.0, 3.0)) - 30.0 / 57.295779513082325      # src/cone.cpp:37-39
     assert az.value == pytest.approx(np.float32(want), rel=1e-6)
+
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in mode written after the round's GPU budget was spent: the first hardware run "
+                                        "decides; its semantics are held by tests/test_localizer_repair.py on the CPU")
+@pytest.mark.parametrize("window", [3, 10])
+def test_localizer_repair_equals_the_oracle(host, window):
+    """localiser frames with observation edges + sliding-window optimise through the
+    drop-in Slam (setLocalizerRepair) against the restated semantics in the oracle, two short laps.  Runs in its own
+    process (tests/gpu_case_localizer_repair.py) so that a device fault on this not-yet-measured path cannot poison
+    the CUDA context of the tests after it."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "gpu_case_localizer_repair.py"), str(window)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
