@@ -4,7 +4,9 @@
  * back-half methods of class Slam (src/slam.hpp:66-91) and its `g2o::SparseOptimizer m_optimizer`
  * member (src/slam.hpp:98).  Every entry point below names the reference interface it replaces.
  * Plain C types only; the handle is opaque; callers own every pointer they pass; nothing is
- * allocated across the ABI; nothing throws.  All floating point is fp64, all indices int32.
+ * allocated across the ABI; nothing throws (a C++ exception raised inside the library, e.g. a failed
+ * host allocation, is caught at the entry point and comes back as SLAM_B200_E_NOMEM / SLAM_B200_E_STATE
+ * with its message in slam_b200_last_error()).  All floating point is fp64, all indices int32.
  *
  * Return value: >= 0 success (meaning per function), < 0 one of the SLAM_B200_E_* codes;
  * slam_b200_last_error() gives a human-readable reason.  There is no CPU fallback: without a
@@ -32,7 +34,7 @@ typedef struct slam_b200_ctx slam_b200_ctx;
 #define SLAM_B200_E_CUDA (-100)     /* CUDA runtime error or no device */
 #define SLAM_B200_E_ARG (-101)      /* bad argument (null pointer, unknown id, duplicate id ...) */
 #define SLAM_B200_E_STATE (-102)    /* call not valid in the current state */
-#define SLAM_B200_E_NOMEM (-103)
+#define SLAM_B200_E_NOMEM (-103)    /* host allocation failed (std::bad_alloc caught at the entry point) */
 
 /* association result codes written to status[] */
 #define SLAM_B200_ASSOC_MATCHED 0   /* matched map cone idx[i]            (slam.cpp:584-592) */

@@ -567,7 +567,7 @@ int upload_frame(slam_b200_ctx* c, const double* cones, int n, const double pose
 extern "C" {
 
 int slam_b200_cones_to_global(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
-                              double* global3, double* local3) {
+                              double* global3, double* local3) try {
   if (!c || !cones || !pose || n < 0) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n == 0) return 0;
@@ -584,16 +584,16 @@ int slam_b200_cones_to_global(slam_b200_ctx* c, const double* cones, int n, cons
   if (global3) std::memcpy(global3, c->pin_d.p, sizeof(double) * 3 * (size_t)n);
   if (local3) std::memcpy(local3, c->pin_d.p + 3 * (size_t)n, sizeof(double) * 3 * (size_t)n);
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_map_clear(slam_b200_ctx* c) {
+int slam_b200_map_clear(slam_b200_ctx* c) try {
   if (!c) return SLAM_B200_E_ARG;
   c->map_n = 0;
   c->map_version++;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_map_append(slam_b200_ctx* c, const double* x, const double* y, const int32_t* type, int n) {
+int slam_b200_map_append(slam_b200_ctx* c, const double* x, const double* y, const int32_t* type, int n) try {
   if (!c || n < 0 || (n > 0 && (!x || !y || !type))) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n == 0) return c->map_n;
@@ -608,11 +608,11 @@ int slam_b200_map_append(slam_b200_ctx* c, const double* x, const double* y, con
   c->map_n += n;
   c->map_version++;
   return c->map_n;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_map_size(slam_b200_ctx* c) { return c ? c->map_n : SLAM_B200_E_ARG; }
 
-int slam_b200_map_read(slam_b200_ctx* c, int first, int n, double* x, double* y, int32_t* type) {
+int slam_b200_map_read(slam_b200_ctx* c, int first, int n, double* x, double* y, int32_t* type) try {
   if (!c || first < 0 || n < 0 || first + n > c->map_n) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n == 0) return 0;
@@ -621,9 +621,9 @@ int slam_b200_map_read(slam_b200_ctx* c, int first, int n, double* x, double* y,
   if (type) SLAM_CUDA_TRY(c, cudaMemcpyAsync(type, c->map_type.p + first, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return n;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_map_write_xy(slam_b200_ctx* c, int first, int n, const double* x, const double* y) {
+int slam_b200_map_write_xy(slam_b200_ctx* c, int first, int n, const double* x, const double* y) try {
   if (!c || first < 0 || n < 0 || first + n > c->map_n || (n > 0 && (!x || !y))) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n == 0) return 0;
@@ -632,12 +632,12 @@ int slam_b200_map_write_xy(slam_b200_ctx* c, int first, int n, const double* x, 
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->map_version++;
   return n;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_assoc_map_frame(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
                               double thr, double mapThr, uint32_t* cci, int32_t* loop_closing,
                               int32_t* idx, int32_t* status, double* z2, double* g3,
-                              int32_t* first_cone_created, int32_t* loop_closing_obs) {
+                              int32_t* first_cone_created, int32_t* loop_closing_obs) try {
   if (!c || !pose || !cci || !loop_closing || n < 0 || (n > 0 && (!cones || !idx || !status)))
     return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
@@ -672,11 +672,11 @@ int slam_b200_assoc_map_frame(slam_b200_ctx* c, const double* cones, int n, cons
   if (sc->map_n != c->map_n) c->map_version++;
   c->map_n = sc->map_n;
   return c->map_n;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_assoc_localize_frame(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
                                    double thr, uint32_t* cci, int32_t* idx, double* g3,
-                                   int32_t* n_reobserved, int32_t* send_cone_data) {
+                                   int32_t* n_reobserved, int32_t* send_cone_data) try {
   if (!c || !pose || !cci || n < 0 || (n > 0 && (!cones || !idx))) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n_reobserved) *n_reobserved = 0;
@@ -702,9 +702,9 @@ int slam_b200_assoc_localize_frame(slam_b200_ctx* c, const double* cones, int n,
   if (n_reobserved) *n_reobserved = sc->n_reobserved;
   if (send_cone_data) *send_cone_data = sc->send_cone_data;
   return sc->n_reobserved;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) {
+int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) try {
   if (!c || !(cell > 0)) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   int M = c->map_n;
@@ -770,10 +770,10 @@ int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) {
   c->grid_h = gp.h;
   c->grid_map_version = c->map_version;
   return (int)std::min<size_t>(ncell, 0x7fffffff);
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, const double pose[3],
-                             double thr, int gate, int algo, int32_t* idx_dev) {
+                             double thr, int gate, int algo, int32_t* idx_dev) try {
   if (!c || !pose || n < 0 || (n > 0 && (!cones_dev || !idx_dev))) return SLAM_B200_E_ARG;
   if (gate != SLAM_B200_GATE_MAPPING && gate != SLAM_B200_GATE_LOCALIZER) return SLAM_B200_E_ARG;
   if (algo != SLAM_B200_ALGO_BRUTE && algo != SLAM_B200_ALGO_GRID && algo != SLAM_B200_ALGO_GRID_PIPELINED)
@@ -835,7 +835,7 @@ int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, c
   c->launches++;
   SLAM_CUDA_TRY(c, cudaGetLastError());
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_assoc_bulk_frames_dev(int n_frames, slam_b200_ctx* const* ctxs, const double* const* cones_dev,
                                     const int* n, const double* poses, double thr, int gate, int algo,
@@ -849,7 +849,7 @@ int slam_b200_assoc_bulk_frames_dev(int n_frames, slam_b200_ctx* const* ctxs, co
 }
 
 int slam_b200_assoc_bulk(slam_b200_ctx* c, const double* cones, int n, const double pose[3], double thr,
-                         int gate, int algo, int32_t* idx) {
+                         int gate, int algo, int32_t* idx) try {
   if (!c || !pose || n < 0 || (n > 0 && (!cones || !idx))) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n == 0) return 0;
@@ -861,6 +861,6 @@ int slam_b200_assoc_bulk(slam_b200_ctx* c, const double* cones, int n, const dou
   SLAM_CUDA_TRY(c, cudaMemcpyAsync(idx, c->frame_outi.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 }  // extern "C"

@@ -3,6 +3,8 @@
 #include <chrono>
 #include <cmath>
 #include <map>
+#include <memory>
+#include <new>
 
 #include "graph_dev.h"
 
@@ -70,6 +72,28 @@ int refresh_host_estimates(slam_b200_ctx* c) {  // device replica 0 -> host grap
 
 }  // namespace
 
+// see SLAM_ABI_CATCH in ctx.h
+int slam_abi_caught(slam_b200_ctx* c) noexcept {
+  int rc = SLAM_B200_E_STATE;
+  const char* what = "unknown C++ exception";
+  try {
+    throw;
+  } catch (const std::bad_alloc&) {
+    rc = SLAM_B200_E_NOMEM;
+    what = "out of host memory";
+  } catch (const std::exception& e) {
+    what = e.what();
+  } catch (...) {
+  }
+  if (c) {
+    try {
+      c->fail(std::string("exception at the C ABI: ") + what);
+    } catch (...) {
+    }
+  }
+  return rc;
+}
+
 extern "C" {
 
 int slam_b200_version(void) { return 100; }
@@ -80,7 +104,8 @@ int slam_b200_create(int device, void* stream, slam_b200_ctx** out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SLAM_B200_E_CUDA;
   if (cudaSetDevice(device) != cudaSuccess) return SLAM_B200_E_CUDA;
-  slam_b200_ctx* c = new slam_b200_ctx();
+  slam_b200_ctx* c = new (std::nothrow) slam_b200_ctx();
+  if (!c) return SLAM_B200_E_NOMEM;
   c->device = device;
   if (stream) {
     c->stream = (cudaStream_t)stream;
@@ -114,28 +139,28 @@ int slam_b200_destroy(slam_b200_ctx* c) {
 
 const char* slam_b200_last_error(const slam_b200_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
-int slam_b200_sync(slam_b200_ctx* c) {
+int slam_b200_sync(slam_b200_ctx* c) try {
   if (!c) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 long slam_b200_launch_count(slam_b200_ctx* c) { return c ? c->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // graph construction (host mirror; uploaded by prepare)
 // ------------------------------------------------------------------------------------------------
-int slam_b200_graph_clear(slam_b200_ctx* c) {
+int slam_b200_graph_clear(slam_b200_ctx* c) try {
   if (!c) return SLAM_B200_E_ARG;
   uint64_t sv = c->g.structure_version + 1, vv = c->g.values_version + 1;
   c->g = HostGraph();
   c->g.structure_version = sv;
   c->g.values_version = vv;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_add_pose(slam_b200_ctx* c, int id, double x, double y, double theta) {
+int slam_b200_graph_add_pose(slam_b200_ctx* c, int id, double x, double y, double theta) try {
   if (!c) return SLAM_B200_E_ARG;
   HostGraph& g = c->g;
   if (g.id2v.count(id)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
@@ -146,9 +171,9 @@ int slam_b200_graph_add_pose(slam_b200_ctx* c, int id, double x, double y, doubl
   g.structure_version++;
   g.values_version++;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_add_landmark(slam_b200_ctx* c, int id, double x, double y) {
+int slam_b200_graph_add_landmark(slam_b200_ctx* c, int id, double x, double y) try {
   if (!c) return SLAM_B200_E_ARG;
   HostGraph& g = c->g;
   if (g.id2v.count(id)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
@@ -159,9 +184,9 @@ int slam_b200_graph_add_landmark(slam_b200_ctx* c, int id, double x, double y) {
   g.structure_version++;
   g.values_version++;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_add_edge_se2(slam_b200_ctx* c, int id_from, int id_to, const double z[3], const double info[9]) {
+int slam_b200_graph_add_edge_se2(slam_b200_ctx* c, int id_from, int id_to, const double z[3], const double info[9]) try {
   if (!c || !z || !info) return SLAM_B200_E_ARG;
   int i, j;
   if (lookup(c, id_from, false, &i) || lookup(c, id_to, false, &j) || i == j) {
@@ -178,18 +203,18 @@ int slam_b200_graph_add_edge_se2(slam_b200_ctx* c, int id_from, int id_to, const
   g.structure_version++;
   g.values_version++;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_add_odometry(slam_b200_ctx* c, int id_prev, int id_cur, const double pose[3], const double info[9]) {
+int slam_b200_graph_add_odometry(slam_b200_ctx* c, int id_prev, int id_cur, const double pose[3], const double info[9]) try {
   if (!c || !pose || !info) return SLAM_B200_E_ARG;
   int i;
   if (lookup(c, id_prev, false, &i)) { c->fail("odometry: unknown previous pose"); return SLAM_B200_E_ARG; }
   double z[3];
   se2_between(&c->g.pose_est[3 * (size_t)i], pose, z);
   return slam_b200_graph_add_edge_se2(c, id_prev, id_cur, z, info);
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_add_edge_se2_xy(slam_b200_ctx* c, int pose_id, int landmark_id, const double z[2], const double info[4]) {
+int slam_b200_graph_add_edge_se2_xy(slam_b200_ctx* c, int pose_id, int landmark_id, const double z[2], const double info[4]) try {
   if (!c || !z || !info) return SLAM_B200_E_ARG;
   int p, l;
   if (lookup(c, pose_id, false, &p) || lookup(c, landmark_id, true, &l)) {
@@ -204,9 +229,9 @@ int slam_b200_graph_add_edge_se2_xy(slam_b200_ctx* c, int pose_id, int landmark_
   g.structure_version++;
   g.values_version++;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_set_fixed(slam_b200_ctx* c, int id, int fixed) {
+int slam_b200_graph_set_fixed(slam_b200_ctx* c, int id, int fixed) try {
   if (!c) return SLAM_B200_E_ARG;
   auto it = c->g.id2v.find(id);
   if (it == c->g.id2v.end()) { c->fail("setFixed: unknown id"); return SLAM_B200_E_ARG; }
@@ -217,13 +242,13 @@ int slam_b200_graph_set_fixed(slam_b200_ctx* c, int id, int fixed) {
     c->g.structure_version++;
   }
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids, const double* pose_est3,
                          int n_landmarks, const int32_t* lm_ids, const double* lm_est2, int n_eo,
                          const int32_t* eo_from, const int32_t* eo_to, const double* eo_z3, const double* eo_info9,
                          int n_el, const int32_t* el_pose, const int32_t* el_lm, const double* el_z2,
-                         const double* el_info4, int n_fixed, const int32_t* fixed_ids) {
+                         const double* el_info4, int n_fixed, const int32_t* fixed_ids) try {
   if (!c || n_poses < 0 || n_landmarks < 0 || n_eo < 0 || n_el < 0 || n_fixed < 0) return SLAM_B200_E_ARG;
   slam_b200_graph_clear(c);
   HostGraph& g = c->g;
@@ -297,10 +322,10 @@ int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids,
   g.structure_version++;
   g.values_version++;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_set_values(slam_b200_ctx* c, const double* pose_est3, const double* lm_est2,
-                               const double* eo_z3, const double* el_z2) {
+                               const double* eo_z3, const double* el_z2) try {
   if (!c) return SLAM_B200_E_ARG;
   HostGraph& g = c->g;
   if (pose_est3) std::copy(pose_est3, pose_est3 + 3 * (size_t)g.P(), g.pose_est.begin());
@@ -309,13 +334,13 @@ int slam_b200_graph_set_values(slam_b200_ctx* c, const double* pose_est3, const 
   if (el_z2) std::copy(el_z2, el_z2 + 2 * (size_t)g.El(), g.el_z.begin());
   g.values_version++;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_num_poses(slam_b200_ctx* c) { return c ? c->g.P() : SLAM_B200_E_ARG; }
 int slam_b200_graph_num_landmarks(slam_b200_ctx* c) { return c ? c->g.L() : SLAM_B200_E_ARG; }
 int slam_b200_graph_num_edges(slam_b200_ctx* c) { return c ? c->g.Eo() + c->g.El() : SLAM_B200_E_ARG; }
 
-int slam_b200_graph_get_vertex(slam_b200_ctx* c, int id, double out[3]) {
+int slam_b200_graph_get_vertex(slam_b200_ctx* c, int id, double out[3]) try {
   if (!c || !out) return SLAM_B200_E_ARG;
   auto it = c->g.id2v.find(id);
   if (it == c->g.id2v.end()) return SLAM_B200_E_ARG;
@@ -326,19 +351,19 @@ int slam_b200_graph_get_vertex(slam_b200_ctx* c, int id, double out[3]) {
   }
   out[0] = c->g.pose_est[3 * (size_t)k]; out[1] = c->g.pose_est[3 * (size_t)k + 1]; out[2] = c->g.pose_est[3 * (size_t)k + 2];
   return 3;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_get_estimates(slam_b200_ctx* c, double* pose_est3, double* lm_est2) {
+int slam_b200_graph_get_estimates(slam_b200_ctx* c, double* pose_est3, double* lm_est2) try {
   if (!c) return SLAM_B200_E_ARG;
   if (pose_est3) std::copy(c->g.pose_est.begin(), c->g.pose_est.end(), pose_est3);
   if (lm_est2) std::copy(c->g.lm_est.begin(), c->g.lm_est.end(), lm_est2);
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 // ------------------------------------------------------------------------------------------------
 // optimisation
 // ------------------------------------------------------------------------------------------------
-int slam_b200_graph_prepare(slam_b200_ctx* c) {
+int slam_b200_graph_prepare(slam_b200_ctx* c) try {
   if (!c) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   int n = graph_build_structure(c);
@@ -351,25 +376,25 @@ int slam_b200_graph_prepare(slam_b200_ctx* c) {
     if (rc) return rc;
   }
   return n;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_prepare_assembly_only(slam_b200_ctx* c) {
+int slam_b200_graph_prepare_assembly_only(slam_b200_ctx* c) try {
   if (!c) return SLAM_B200_E_ARG;
   c->assembly_only = true;
   int n = slam_b200_graph_prepare(c);
   c->assembly_only = false;
   return n;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_reset_device(slam_b200_ctx* c) {
+int slam_b200_graph_reset_device(slam_b200_ctx* c) try {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   int rc = graph_alloc_values(c, 1);
   if (rc) return rc;
   return graph_upload_host_values(c);
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) {
+int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) try {
   if (!c || !c->sys || iters < 0 || c->sys->assembly_only) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -380,9 +405,9 @@ int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) {
   }
   D.iters_enqueued += iters;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_finish(slam_b200_ctx* c, double* chi2, int chi2_cap) {
+int slam_b200_graph_finish(slam_b200_ctx* c, double* chi2, int chi2_cap) try {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -408,9 +433,9 @@ int slam_b200_graph_finish(slam_b200_ctx* c, double* chi2, int chi2_cap) {
   D.iters_enqueued = 0;
   if (failed) return 0;
   return done;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_optimize(slam_b200_ctx* c, int iters, double* chi2) {
+int slam_b200_graph_optimize(slam_b200_ctx* c, int iters, double* chi2) try {
   if (!c || iters < 0) return SLAM_B200_E_ARG;
   int n = slam_b200_graph_prepare(c);
   if (n < 0) return n;
@@ -418,9 +443,9 @@ int slam_b200_graph_optimize(slam_b200_ctx* c, int iters, double* chi2) {
   int rc = slam_b200_graph_iterate_async(c, iters);
   if (rc) return rc;
   return slam_b200_graph_finish(c, chi2, iters);
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_chi2(slam_b200_ctx* c, double* chi2) {
+int slam_b200_graph_chi2(slam_b200_ctx* c, double* chi2) try {
   if (!c || !chi2) return SLAM_B200_E_ARG;
   int n = slam_b200_graph_prepare(c);
   if (n < 0) return n;
@@ -435,18 +460,18 @@ int slam_b200_graph_chi2(slam_b200_ctx* c, double* chi2) {
   SLAM_CUDA_TRY(c, cudaMemcpyAsync(chi2, D.chi2.p + slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_assemble_async(slam_b200_ctx* c, int p0, int p1) {
+int slam_b200_graph_assemble_async(slam_b200_ctx* c, int p0, int p1) try {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
   if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
   return graph_enqueue_assemble(c, p0, p1, false);
-}
+} SLAM_ABI_CATCH(c)
 
 // ---- peer exchange of the landmark part (config 5, one process per GPU) -------------------------
-int slam_b200_graph_shard_landmarks(slam_b200_ctx* c, int p0, int p1, int32_t* l0, int32_t* l1) {
+int slam_b200_graph_shard_landmarks(slam_b200_ctx* c, int p0, int p1, int32_t* l0, int32_t* l1) try {
   if (!c || !c->sys || !l0 || !l1) return SLAM_B200_E_STATE;
   DeviceSystem& D = *c->sys;
   if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
@@ -454,9 +479,9 @@ int slam_b200_graph_shard_landmarks(slam_b200_ctx* c, int p0, int p1, int32_t* l
   graph_shard_landmarks(D, p0, p1, &a, &b);
   *l0 = a; *l1 = b;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_xchg_create(slam_b200_ctx* c, int world, int rank, int cap, unsigned char handle_out[64]) {
+int slam_b200_xchg_create(slam_b200_ctx* c, int world, int rank, int cap, unsigned char handle_out[64]) try {
   if (!c || !c->sys || !handle_out || world < 1 || world > 64 || rank < 0 || rank >= world || cap < 1) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -471,9 +496,9 @@ int slam_b200_xchg_create(slam_b200_ctx* c, int world, int rank, int cap, unsign
   SLAM_CUDA_TRY(c, cudaIpcGetMemHandle(&h, X.local));
   std::memcpy(handle_out, &h, 64);
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_xchg_connect(slam_b200_ctx* c, const unsigned char* handles, const int32_t* ranges) {
+int slam_b200_xchg_connect(slam_b200_ctx* c, const unsigned char* handles, const int32_t* ranges) try {
   if (!c || !c->sys || !handles || !ranges || !c->sys->xchg.local) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   PeerExchange& X = c->sys->xchg;
@@ -500,26 +525,26 @@ int slam_b200_xchg_connect(slam_b200_ctx* c, const unsigned char* handles, const
   X.epoch = 0;
   X.connected = true;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_assemble_exchange_async(slam_b200_ctx* c, int p0, int p1) {
+int slam_b200_graph_assemble_exchange_async(slam_b200_ctx* c, int p0, int p1) try {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
   if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
   return graph_enqueue_assemble(c, p0, p1, false, true);
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_xchg_error(slam_b200_ctx* c) {
+int slam_b200_xchg_error(slam_b200_ctx* c) try {
   if (!c || !c->sys || !c->sys->xchg.connected) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   int e = 0;
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   SLAM_CUDA_TRY(c, cudaMemcpy(&e, c->sys->xchg.err.p, sizeof(int), cudaMemcpyDeviceToHost));
   return e;
-}
+} SLAM_ABI_CATCH(c)
 
-long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) {
+long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) try {
   if (!c || !c->sys || !ptr) return SLAM_B200_E_STATE;
   DeviceSystem& D = *c->sys;
   *ptr = D.V.p;
@@ -527,15 +552,15 @@ long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) {
   if (which == 1) return D.nV;
   if (which == 2) { *ptr = D.x.p; return D.n; }
   return SLAM_B200_E_ARG;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_solve_async(slam_b200_ctx* c) {
+int slam_b200_graph_solve_async(slam_b200_ctx* c) try {
   if (!c || !c->sys || !c->sys->assembled || c->sys->assembly_only) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   return graph_enqueue_solve(c);
-}
+} SLAM_ABI_CATCH(c)
 
-long slam_b200_graph_export_system(slam_b200_ctx* c, int* n_out, int32_t* Ap, int32_t* Ai, double* Ax, double* b) {
+long slam_b200_graph_export_system(slam_b200_ctx* c, int* n_out, int32_t* Ap, int32_t* Ai, double* Ax, double* b) try {
   if (!c || !n_out) return SLAM_B200_E_ARG;
   int n = slam_b200_graph_prepare(c);
   if (n < 0) return n;
@@ -584,9 +609,9 @@ long slam_b200_graph_export_system(slam_b200_ctx* c, int* n_out, int32_t* Ap, in
       }
     }
   return nnz;
-}
+} SLAM_ABI_CATCH(c)
 
-int slam_b200_graph_stats(slam_b200_ctx* c, double out[16]) {
+int slam_b200_graph_stats(slam_b200_ctx* c, double out[16]) try {
   if (!c || !c->sys || !out) return SLAM_B200_E_STATE;
   DeviceSystem& D = *c->sys;
   for (int k = 0; k < 16; k++) out[k] = 0;
@@ -600,12 +625,12 @@ int slam_b200_graph_stats(slam_b200_ctx* c, double out[16]) {
   out[11] = (double)D.nV; out[12] = (double)D.nFbig; out[13] = (double)D.off_a.size();
   out[14] = D.t_structure; out[15] = D.t_lists;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 long slam_b200_graph_export_symbolic(slam_b200_ctx* c, int what, int32_t* out, long cap);
 
 // ---- device-side snapshot of the estimates (bench: every timed step starts from the same state) --
-int slam_b200_graph_snapshot(slam_b200_ctx* c) {
+int slam_b200_graph_snapshot(slam_b200_ctx* c) try {
   if (!c || !c->sys || c->sys->R < 1) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -613,8 +638,8 @@ int slam_b200_graph_snapshot(slam_b200_ctx* c) {
   if (n) SLAM_CUDA_TRY(c, cudaMemcpyAsync(D.est0.p, D.est.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
   D.have_snapshot = true;
   return 0;
-}
-int slam_b200_graph_restore_async(slam_b200_ctx* c) {
+} SLAM_ABI_CATCH(c)
+int slam_b200_graph_restore_async(slam_b200_ctx* c) try {
   if (!c || !c->sys || !c->sys->have_snapshot) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -623,17 +648,17 @@ int slam_b200_graph_restore_async(slam_b200_ctx* c) {
   SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)D.R, c->stream));
   D.iters_enqueued = 0;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 // ---- per-phase timing with CUDA events (bench) ----------------------------------------------------
-int slam_b200_profile_enable(slam_b200_ctx* c, int on) {
+int slam_b200_profile_enable(slam_b200_ctx* c, int on) try {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   c->sys->profile = on != 0;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 // out[0..4] = milliseconds summed over the profiled iterations: assemble, factor, forward, backward,
 // update; out[5] = iterations profiled.  Synchronises the stream and clears the record.
-int slam_b200_profile_read(slam_b200_ctx* c, double out[8]) {
+int slam_b200_profile_read(slam_b200_ctx* c, double out[8]) try {
   if (!c || !c->sys || !out) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -650,39 +675,39 @@ int slam_b200_profile_read(slam_b200_ctx* c, double out[8]) {
   for (cudaEvent_t e : D.prof_events) cudaEventDestroy(e);
   D.prof_events.clear();
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 // Debug: phase clocks (SM cycles) of block 0 of the most recent CTA-per-front factor launch; needs
 // SLAM_B200_PHASE_CLOCKS=1 in the environment when the graph is prepared.  out[0..6] = clock64 at:
 // start, zeroed, H scattered, children added, factorised, forward done, written; out[7..9] = s, fs, children.
-int slam_b200_debug_phase_clocks(slam_b200_ctx* c, long long out[10]) {
+int slam_b200_debug_phase_clocks(slam_b200_ctx* c, long long out[10]) try {
   if (!c || !c->sys || !out || !c->sys->dbg_clocks.p) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   SLAM_CUDA_TRY(c, cudaMemcpy(out, c->sys->dbg_clocks.p, sizeof(long long) * 10, cudaMemcpyDeviceToHost));
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 // Debug: SM cycles summed over every warp of the warp-per-front factor kernel since the graph was
 // prepared (same switch): out[0..5] = zero, scatter H, extend-add, LDL^T, fused forward, write; out[6] = fronts.
-int slam_b200_debug_tiny_clocks(slam_b200_ctx* c, long long out[8]) {
+int slam_b200_debug_tiny_clocks(slam_b200_ctx* c, long long out[8]) try {
   if (!c || !c->sys || !out || !c->sys->dbg_clocks.p) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   SLAM_CUDA_TRY(c, cudaMemcpy(out, c->sys->dbg_clocks.p + 16, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 // Debug: cycles of thread 0 of the same CTA accumulated over the panels of its front (same switch):
 // out[0..5] = triangle (warp 0), wait, row elimination, wait, trailing update, wait; out[6..7] = fused
 // forward: warp-0 triangle solve, rest of the panel step.  Accumulates over launches until re-prepared.
-int slam_b200_debug_panel_clocks(slam_b200_ctx* c, long long out[8]) {
+int slam_b200_debug_panel_clocks(slam_b200_ctx* c, long long out[8]) try {
   if (!c || !c->sys || !out || !c->sys->dbg_clocks.p) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   SLAM_CUDA_TRY(c, cudaMemcpy(out, c->sys->dbg_clocks.p + 24, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
   SLAM_CUDA_TRY(c, cudaMemset(c->sys->dbg_clocks.p + 24, 0, sizeof(long long) * 8));
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 // ---- symbolic analysis without a device (host logic; testable on a CPU-only box) ----------------
 struct SymHandle {
@@ -691,16 +716,18 @@ struct SymHandle {
 };
 
 void* slam_b200_symbolic_create(int nb, const int32_t* dim, int n_pairs, const int32_t* a, const int32_t* b,
-                                int leaf_size) {
+                                int leaf_size) try {
   if (nb < 0 || n_pairs < 0 || (nb > 0 && !dim) || (n_pairs > 0 && (!a || !b))) return nullptr;
-  SymHandle* h = new SymHandle();
+  std::unique_ptr<SymHandle> h(new SymHandle());
   int cur = 0;
   h->hoff_diag.resize(nb);
   for (int k = 0; k < nb; k++) { h->hoff_diag[k] = cur; cur += dim[k] * dim[k]; }
   h->hoff_off.resize(n_pairs);
   for (int k = 0; k < n_pairs; k++) { h->hoff_off[k] = cur; cur += dim[a[k]] * dim[b[k]]; }
   symbolic_analyze(nb, dim, n_pairs, a, b, h->hoff_diag.data(), h->hoff_off.data(), leaf_size, h->S);
-  return h;
+  return h.release();
+} catch (...) {
+  return nullptr;  // no context to leave a message on
 }
 void slam_b200_symbolic_destroy(void* h) { delete static_cast<SymHandle*>(h); }
 
@@ -752,16 +779,16 @@ double slam_b200_symbolic_stat(void* h, int what) {
   }
 }
 
-long slam_b200_graph_export_symbolic(slam_b200_ctx* c, int what, int32_t* out, long cap) {
+long slam_b200_graph_export_symbolic(slam_b200_ctx* c, int what, int32_t* out, long cap) try {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   return export_symbolic(c->sys->sym, &c->sys->blk_hidx, what, out, cap);
-}
+} SLAM_ABI_CATCH(c)
 
 // ------------------------------------------------------------------------------------------------
 // batched replicas
 // ------------------------------------------------------------------------------------------------
 int slam_b200_batch_upload(slam_b200_ctx* c, int R, const double* pose_est3, const double* lm_est2,
-                           const double* eo_z3, const double* el_z2) {
+                           const double* eo_z3, const double* el_z2) try {
   if (!c || R < 1 || !pose_est3 || !lm_est2 || !eo_z3 || !el_z2) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   c->batch_ordering = true;
@@ -805,12 +832,12 @@ int slam_b200_batch_upload(slam_b200_ctx* c, int R, const double* pose_est3, con
   }
   D.values_version = 0;  // replica 0 no longer mirrors the host graph
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_batch_iterate_async(slam_b200_ctx* c, int iters) { return slam_b200_graph_iterate_async(c, iters); }
 
 int slam_b200_batch_download(slam_b200_ctx* c, double* pose_est3, double* lm_est2, double* chi2,
-                             int chi2_cap_per_replica, int32_t* iterations_done) {
+                             int chi2_cap_per_replica, int32_t* iterations_done) try {
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -852,17 +879,17 @@ int slam_b200_batch_download(slam_b200_ctx* c, double* pose_est3, double* lm_est
   SLAM_CUDA_TRY(c, cudaMemsetAsync(D.status.p, 0, sizeof(int) * 2 * (size_t)R, c->stream));
   D.iters_enqueued = 0;
   return 0;
-}
+} SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_optimize_batch(slam_b200_ctx* c, int R, double* pose_est3, double* lm_est2,
                                    const double* eo_z3, const double* el_z2, int iters, double* chi2,
-                                   int32_t* iterations_done) {
+                                   int32_t* iterations_done) try {
   int rc = slam_b200_batch_upload(c, R, pose_est3, lm_est2, eo_z3, el_z2);
   if (rc) return rc;
   rc = slam_b200_batch_iterate_async(c, iters);
   if (rc) return rc;
   return slam_b200_batch_download(c, pose_est3, lm_est2, chi2, iters, iterations_done);
-}
+} SLAM_ABI_CATCH(c)
 
 }  // extern "C"
 
@@ -881,7 +908,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 }
 }  // namespace
 
-extern "C" int slam_b200_fp64_peak(slam_b200_ctx* c, double* tflops) {
+extern "C" int slam_b200_fp64_peak(slam_b200_ctx* c, double* tflops) try {
   if (!c || !tflops) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   const int blocks = c->num_sms * 8, threads = 256, iters = 1 << 15;
@@ -908,4 +935,4 @@ extern "C" int slam_b200_fp64_peak(slam_b200_ctx* c, double* tflops) {
   SLAM_CUDA_TRY(c, cudaGetLastError());
   *tflops = best;
   return 0;
-}
+} SLAM_ABI_CATCH(c)

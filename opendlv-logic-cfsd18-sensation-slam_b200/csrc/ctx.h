@@ -20,6 +20,14 @@
     }                                                                                 \
   } while (0)
 
+// No C++ exception crosses the C ABI (include/slam_b200.h, "never throw across the ABI"): every entry
+// point that can allocate host memory is a function-try-block ending in SLAM_ABI_CATCH(ctx), which
+// turns std::bad_alloc into SLAM_B200_E_NOMEM and anything else into SLAM_B200_E_STATE, with the
+// message left on the context for slam_b200_last_error().
+struct slam_b200_ctx;
+int slam_abi_caught(slam_b200_ctx* c) noexcept;  // capi.cu; call only from inside a catch block
+#define SLAM_ABI_CATCH(ctx) catch (...) { return slam_abi_caught(ctx); }
+
 // growable device array; grow() keeps the first `keep` elements
 template <class T>
 struct DevBuf {
@@ -34,9 +42,11 @@ struct DevBuf {
     if (e != cudaSuccess) return e;
     if (keep && p) {
       e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return e;
-      e = cudaStreamSynchronize(s);
-      if (e != cudaSuccess) return e;
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+        cudaFree(q);
+        return e;
+      }
     }
     if (p) cudaFree(p);
     p = q;
