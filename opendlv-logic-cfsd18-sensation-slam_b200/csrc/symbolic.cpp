@@ -8,7 +8,6 @@
 #include <cstdlib>
 #include <functional>
 #include <numeric>
-#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <set>
@@ -235,7 +234,7 @@ class HostPool {
       std::lock_guard<std::mutex> lk(m_);
       fn_ = &fn;
       njobs_ = njobs;
-      next_.store(0);
+      next_ = 0;
       pending_ = njobs;
       generation_++;
     }
@@ -244,6 +243,7 @@ class HostPool {
     std::unique_lock<std::mutex> lk(m_);
     done_.wait(lk, [&] { return pending_ == 0; });
     fn_ = nullptr;
+    njobs_ = 0;
   }
 
  private:
@@ -262,12 +262,19 @@ class HostPool {
     cv_.notify_all();
     for (auto& t : workers_) t.join();
   }
+  // Jobs are claimed under the mutex, together with the function they belong to: a worker that is
+  // still on its way out of the previous run when the next one is being set up either sees the old
+  // run exhausted or a complete new one -- never the new job count against the old counter (which
+  // would run a job twice and let run() return early).  Jobs are coarse (a region, a slice of the
+  // fronts), the lock is not on any hot path.
   void work() {
-    for (;;) {
-      int j = next_.fetch_add(1);
-      if (j >= njobs_) break;
-      (*fn_)(j);
-      std::lock_guard<std::mutex> lk(m_);
+    std::unique_lock<std::mutex> lk(m_);
+    while (next_ < njobs_) {
+      const int j = next_++;
+      const std::function<void(int)>* fn = fn_;
+      lk.unlock();
+      (*fn)(j);
+      lk.lock();
       if (--pending_ == 0) done_.notify_all();
     }
   }
@@ -287,8 +294,7 @@ class HostPool {
   std::mutex m_;
   std::condition_variable cv_, done_;
   const std::function<void(int)>* fn_ = nullptr;
-  int njobs_ = 0, pending_ = 0;
-  std::atomic<int> next_{0};
+  int njobs_ = 0, pending_ = 0, next_ = 0;  // all guarded by m_
   unsigned long generation_ = 0;
   bool stop_ = false;
 };

@@ -137,3 +137,22 @@ print("HASH", h.hexdigest(), int(S.nnzL))
         assert out.returncode == 0, out.stderr[-2000:]
         seen.add([ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][0])
     assert len(seen) == 1, seen
+
+
+@pytest.mark.parametrize("san", ["address,undefined", "thread"])
+def test_symbolic_phase_under_sanitizers(pkg, tmp_path, san):
+    """csrc/symbolic.cpp under AddressSanitizer + UBSan and under ThreadSanitizer (the phase runs on a pool of host
+    threads): SLAM-shaped and adversarial patterns, two repetitions whose results must be identical."""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(os.path.dirname(here), pkg.__name__, "csrc")
+    exe = str(tmp_path / "sanitize_symbolic")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=" + san, "-fno-sanitize-recover=all", "-I" + csrc,
+           os.path.join(here, "sanitize_symbolic_driver.cpp"), os.path.join(csrc, "symbolic.cpp"), "-o", exe, "-lpthread"]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + b.stderr[-300:])
+    env = dict(os.environ, SLAM_B200_SYM_THREADS="8", TSAN_OPTIONS="halt_on_error=1")
+    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == "ok 0", r.stdout[-500:] + r.stderr[-3000:]
