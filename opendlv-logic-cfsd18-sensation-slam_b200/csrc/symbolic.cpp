@@ -230,6 +230,8 @@ class HostPool {
       for (int j = 0; j < njobs; j++) fn(j);
       return;
     }
+    // one parallel section at a time: contexts used from different host threads share this pool
+    std::lock_guard<std::mutex> one_run(run_m_);
     {
       std::lock_guard<std::mutex> lk(m_);
       fn_ = &fn;
@@ -291,7 +293,7 @@ class HostPool {
     }
   }
   std::vector<std::thread> workers_;
-  std::mutex m_;
+  std::mutex m_, run_m_;
   std::condition_variable cv_, done_;
   const std::function<void(int)>* fn_ = nullptr;
   int njobs_ = 0, pending_ = 0, next_ = 0;  // all guarded by m_

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <random>
 #include <set>
+#include <thread>
 #include <utility>
 // slam-like pattern: L landmarks (dim 2) then P poses (dim 3) in g2o order; chain + each pose sees k landmarks
 static void slam_pattern(int P, int L, int laps, std::mt19937& rng, std::vector<int>& dim, std::vector<int>& a, std::vector<int>& b) {
@@ -53,6 +54,19 @@ int main(int argc, char** argv) {
     { std::vector<int> d, a, b; H ^= run(d, a, b, 8) * 13; }                                                             // empty
     { std::vector<int> d(500, 2), a, b; H ^= run(d, a, b, 8) * 17; }                                                     // no edges
     { std::vector<int> d, a, b; std::mt19937 g(6); random_pattern(5000, 1, g, d, a, b); H ^= run(d, a, b, 64) * 19; }    // many components
+  }
+  // two host threads analysing different graphs at the same time (two contexts share the process-wide pool):
+  // each must get what it gets alone
+  {
+    std::vector<int> d1, a1, b1, d2, a2, b2;
+    { std::mt19937 g(1); slam_pattern(6000, 300, 6, g, d1, a1, b1); }
+    { std::mt19937 g(3); random_pattern(6000, 4, g, d2, a2, b2); }
+    const unsigned long s1 = run(d1, a1, b1, 600), s2 = run(d2, a2, b2, 256);
+    unsigned long c1 = 0, c2 = 0;
+    std::thread t1([&] { for (int k = 0; k < 3; k++) c1 = run(d1, a1, b1, 600); });
+    std::thread t2([&] { for (int k = 0; k < 3; k++) c2 = run(d2, a2, b2, 256); });
+    t1.join(); t2.join();
+    if (c1 != s1 || c2 != s2) { printf("concurrent analysis differs from serial\n"); return 1; }
   }
   printf("ok %lx\n", H);
 }

@@ -154,5 +154,5 @@ def test_symbolic_phase_under_sanitizers(pkg, tmp_path, san):
     if b.returncode != 0:
         pytest.skip("sanitizer runtime not available: " + b.stderr[-300:])
     env = dict(os.environ, SLAM_B200_SYM_THREADS="8", TSAN_OPTIONS="halt_on_error=1")
-    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600, env=env)
+    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0 and r.stdout.strip() == "ok 0", r.stdout[-500:] + r.stderr[-3000:]
