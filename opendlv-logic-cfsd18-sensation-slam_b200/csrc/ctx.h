@@ -132,6 +132,7 @@ struct slam_b200_ctx {
   long launches = 0;
   int num_sms = 148;
   int max_smem_optin = 0;
+  bool solver_attrs_set = false;  // solver.cu: cudaFuncSetAttribute done for this context's device
 
   // ---- cone map ----
   DevBuf<double> map_x, map_y;

@@ -958,8 +958,10 @@ __global__ void update_kernel(int P, int L, long estStride, double* est_all, con
 
 // Structure arrays go up through ONE pinned staging buffer: ~40 small copies from pageable vectors
 // would each be staged synchronously by the driver (measured 16 ms for the 10-lap graph).
+// The list is filled and flushed inside one graph_build_structure call; thread_local so that contexts
+// prepared from different host threads do not share it.
 struct PendingUpload { void* dst; const void* src; size_t bytes; };
-std::vector<PendingUpload> g_uploads;
+thread_local std::vector<PendingUpload> g_uploads;
 
 template <class T>
 int upload_vec(slam_b200_ctx* c, DevBuf<T>& d, const std::vector<T>& h) {

@@ -1081,21 +1081,23 @@ SymArgs sym_args(const DeviceSystem& D) {
   return a;
 }
 
-bool g_attr_set = false;
-
 }  // namespace
 
 int graph_enqueue_update(slam_b200_ctx* c);  // graph.cu
 
+// Opt-in shared-memory limits of the front kernels.  Function attributes belong to the device the
+// call is made on, so the flag lives in the context (a process may hold contexts on several devices)
+// and not in a process-wide global.  Always reached outside stream capture first
+// (graph_enqueue_iteration calls it before cudaStreamBeginCapture).
 static int solver_init_attrs(slam_b200_ctx* c) {
-  if (!g_attr_set) {
+  if (!c->solver_attrs_set) {
     int lim = c->max_smem_optin;
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    g_attr_set = true;
+    c->solver_attrs_set = true;
   }
   return 0;
 }
