@@ -293,3 +293,20 @@ def test_sharded_assembly_partials_sum_to_full(ctx, pkg, synth):
     assert int(owners.max()) <= 1
     lm, n = ctx.graph_system_dev(0)
     assert n == 6 * L and lm == ptr
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent (with the host-pool fixes it guards): "
+                                        "the first hardware run decides")
+def test_two_contexts_on_two_host_threads():
+    """Two contexts used from two host threads at the same time (own process: tests/gpu_case_two_contexts.py) give
+    bit for bit what each gives alone -- the process-wide host pool of the symbolic phase, the structure upload
+    list and the kernel attributes are the shared pieces this guards."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "gpu_case_two_contexts.py")], capture_output=True, text=True, timeout=420)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
