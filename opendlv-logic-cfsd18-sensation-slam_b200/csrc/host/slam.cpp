@@ -104,7 +104,13 @@ void Slam::performSLAM(MatrixXd cones) {
 void Slam::addPoseToGraph(Vector3d pose) {
   check(m_ctx, slam_b200_graph_add_pose(m_ctx, m_poseId, pose(0), pose(1), pose(2)), "graph_add_pose");
   addOdometryMeasurement(pose);
-  m_connectivityGraph.push_back(std::vector<int>());
+  {
+    // drawGraph() copies m_connectivityGraph under map + sensor mutex (slam.cpp:780-784) while the reference
+    // grows it here under the optimizer mutex only: a viewer-thread read racing a reallocation.  The sensor
+    // mutex is a leaf lock everywhere else, so taking it for the push_back cannot invert an order.
+    std::lock_guard<std::mutex> lockSensor(m_sensorMutex);
+    m_connectivityGraph.push_back(std::vector<int>());
+  }
   m_poseId++;
 }
 
@@ -267,8 +273,15 @@ void Slam::localizer(Vector3d pose, MatrixXd cones) {
       m_lastStatus[i] = idx[i] >= 0 ? SLAM_B200_ASSOC_MATCHED : SLAM_B200_ASSOC_NONE;
     }
   }
-  std::lock_guard<std::mutex> lockOptimizer(m_optimizerMutex);
-  Vector3d updatedPoseVectorGraph = updatePoseFromGraph();  // 404 (optimizeGraph() is commented out at 403)
+  // The reference keeps m_optimizerMutex from 402 to the end of the function, i.e. through sendCones()
+  // (optimizer -> send -> map, 402 -> 660 -> 663), while addConesToMap takes map -> optimizer (553 -> 586):
+  // an ABBA pair between two detached frame threads.  Here the lock covers the graph
+  // read only; nothing the senders touch is guarded by it.
+  Vector3d updatedPoseVectorGraph;
+  {
+    std::lock_guard<std::mutex> lockOptimizer(m_optimizerMutex);
+    updatedPoseVectorGraph = updatePoseFromGraph();  // 404 (optimizeGraph() is commented out at 403)
+  }
   {
     std::lock_guard<std::mutex> lockSend(m_sendMutex);
     m_sendPose = updatedPoseVectorGraph;

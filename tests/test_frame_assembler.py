@@ -132,3 +132,24 @@ def test_host_mirror_compiles_against_the_reference_eigen(pkg):
                         os.path.join(src, "frame_assembler.cpp"), os.path.join(src, "slam_c.cpp")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_slam_lock_discipline_under_tsan(pkg, tmp_path):
+    """The drop-in Slam class (csrc/host/slam.cpp) under ThreadSanitizer: a frame thread running performSLAM through
+    mapping, loop closure and localiser frames (reference mode and opt-in repair) while a viewer thread calls draw* /
+    buildConePacket, over a stub of the sixteen C-ABI calls it makes (tests/tsan_slam_stub_backend.cpp -- canned
+    records, test infrastructure only).  The reference's own discipline fails this: addPoseToGraph grows
+    m_connectivityGraph under the optimizer mutex while drawGraph copies it under map + sensor (slam.cpp:440, 780-784),
+    and localizer -> sendCones takes optimizer -> map against addConesToMap's map -> optimizer."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    host = os.path.join(os.path.dirname(here), pkg.__name__, "csrc", "host")
+    exe = str(tmp_path / "tsan_slam")
+    cmd = ["g++", "-std=c++14", "-O1", "-g", "-fsanitize=thread", "-I" + host, os.path.join(here, "tsan_slam_driver.cpp"),
+           os.path.join(here, "tsan_slam_stub_backend.cpp"), os.path.join(host, "slam.cpp"), os.path.join(host, "cone.cpp"),
+           "-o", exe, "-lpthread"]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0:
+        pytest.skip("sanitizer runtime not available: " + b.stderr[-300:])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=240, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout[-500:] + r.stderr[-3000:]
