@@ -568,6 +568,7 @@ extern "C" {
 
 int slam_b200_cones_to_global(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
                               double* global3, double* local3) try {
+  NvtxRange nvtx_range("slam_b200/cones_to_global");
   if (!c || !cones || !pose || n < 0) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n == 0) return 0;
@@ -638,6 +639,7 @@ int slam_b200_assoc_map_frame(slam_b200_ctx* c, const double* cones, int n, cons
                               double thr, double mapThr, uint32_t* cci, int32_t* loop_closing,
                               int32_t* idx, int32_t* status, double* z2, double* g3,
                               int32_t* first_cone_created, int32_t* loop_closing_obs) try {
+  NvtxRange nvtx_range("slam_b200/assoc_map_frame");
   if (!c || !pose || !cci || !loop_closing || n < 0 || (n > 0 && (!cones || !idx || !status)))
     return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
@@ -677,6 +679,7 @@ int slam_b200_assoc_map_frame(slam_b200_ctx* c, const double* cones, int n, cons
 int slam_b200_assoc_localize_frame(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
                                    double thr, uint32_t* cci, int32_t* idx, double* g3,
                                    int32_t* n_reobserved, int32_t* send_cone_data) try {
+  NvtxRange nvtx_range("slam_b200/assoc_localize_frame");
   if (!c || !pose || !cci || n < 0 || (n > 0 && (!cones || !idx))) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   if (n_reobserved) *n_reobserved = 0;
@@ -705,6 +708,7 @@ int slam_b200_assoc_localize_frame(slam_b200_ctx* c, const double* cones, int n,
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) try {
+  NvtxRange nvtx_range("slam_b200/map_build_grid");
   if (!c || !(cell > 0)) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   int M = c->map_n;
@@ -774,6 +778,7 @@ int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) try {
 
 int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, const double pose[3],
                              double thr, int gate, int algo, int32_t* idx_dev) try {
+  NvtxRange nvtx_range("slam_b200/assoc_bulk");
   if (!c || !pose || n < 0 || (n > 0 && (!cones_dev || !idx_dev))) return SLAM_B200_E_ARG;
   if (gate != SLAM_B200_GATE_MAPPING && gate != SLAM_B200_GATE_LOCALIZER) return SLAM_B200_E_ARG;
   if (algo != SLAM_B200_ALGO_BRUTE && algo != SLAM_B200_ALGO_GRID && algo != SLAM_B200_ALGO_GRID_PIPELINED)

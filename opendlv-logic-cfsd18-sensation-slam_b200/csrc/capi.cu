@@ -249,6 +249,7 @@ int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids,
                          const int32_t* eo_from, const int32_t* eo_to, const double* eo_z3, const double* eo_info9,
                          int n_el, const int32_t* el_pose, const int32_t* el_lm, const double* el_z2,
                          const double* el_info4, int n_fixed, const int32_t* fixed_ids) try {
+  NvtxRange nvtx_range("slam_b200/graph_load");
   if (!c || n_poses < 0 || n_landmarks < 0 || n_eo < 0 || n_el < 0 || n_fixed < 0) return SLAM_B200_E_ARG;
   slam_b200_graph_clear(c);
   HostGraph& g = c->g;
@@ -364,6 +365,7 @@ int slam_b200_graph_get_estimates(slam_b200_ctx* c, double* pose_est3, double* l
 // optimisation
 // ------------------------------------------------------------------------------------------------
 int slam_b200_graph_prepare(slam_b200_ctx* c) try {
+  NvtxRange nvtx_range("slam_b200/graph_prepare");
   if (!c) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   int n = graph_build_structure(c);
@@ -395,6 +397,7 @@ int slam_b200_graph_reset_device(slam_b200_ctx* c) try {
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) try {
+  NvtxRange nvtx_range("slam_b200/graph_iterate");
   if (!c || !c->sys || iters < 0 || c->sys->assembly_only) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -408,6 +411,7 @@ int slam_b200_graph_iterate_async(slam_b200_ctx* c, int iters) try {
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_finish(slam_b200_ctx* c, double* chi2, int chi2_cap) try {
+  NvtxRange nvtx_range("slam_b200/graph_finish");
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -436,6 +440,7 @@ int slam_b200_graph_finish(slam_b200_ctx* c, double* chi2, int chi2_cap) try {
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_optimize(slam_b200_ctx* c, int iters, double* chi2) try {
+  NvtxRange nvtx_range("slam_b200/graph_optimize");
   if (!c || iters < 0) return SLAM_B200_E_ARG;
   int n = slam_b200_graph_prepare(c);
   if (n < 0) return n;
@@ -463,6 +468,7 @@ int slam_b200_graph_chi2(slam_b200_ctx* c, double* chi2) try {
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_assemble_async(slam_b200_ctx* c, int p0, int p1) try {
+  NvtxRange nvtx_range("slam_b200/graph_assemble");
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -528,6 +534,7 @@ int slam_b200_xchg_connect(slam_b200_ctx* c, const unsigned char* handles, const
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_assemble_exchange_async(slam_b200_ctx* c, int p0, int p1) try {
+  NvtxRange nvtx_range("slam_b200/graph_assemble_exchange");
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;
@@ -555,6 +562,7 @@ long slam_b200_graph_system_dev(slam_b200_ctx* c, int which, double** ptr) try {
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_graph_solve_async(slam_b200_ctx* c) try {
+  NvtxRange nvtx_range("slam_b200/graph_solve");
   if (!c || !c->sys || !c->sys->assembled || c->sys->assembly_only) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   return graph_enqueue_solve(c);
@@ -789,6 +797,7 @@ long slam_b200_graph_export_symbolic(slam_b200_ctx* c, int what, int32_t* out, l
 // ------------------------------------------------------------------------------------------------
 int slam_b200_batch_upload(slam_b200_ctx* c, int R, const double* pose_est3, const double* lm_est2,
                            const double* eo_z3, const double* el_z2) try {
+  NvtxRange nvtx_range("slam_b200/batch_upload");
   if (!c || R < 1 || !pose_est3 || !lm_est2 || !eo_z3 || !el_z2) return SLAM_B200_E_ARG;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   c->batch_ordering = true;
@@ -838,6 +847,7 @@ int slam_b200_batch_iterate_async(slam_b200_ctx* c, int iters) { return slam_b20
 
 int slam_b200_batch_download(slam_b200_ctx* c, double* pose_est3, double* lm_est2, double* chi2,
                              int chi2_cap_per_replica, int32_t* iterations_done) try {
+  NvtxRange nvtx_range("slam_b200/batch_download");
   if (!c || !c->sys) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   DeviceSystem& D = *c->sys;

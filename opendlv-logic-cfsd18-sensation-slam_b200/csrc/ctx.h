@@ -8,8 +8,20 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: a pointer check per call when no tool is attached
+
 #include "../../include/slam_b200.h"
 #include "symbolic.h"
+
+// Named range for profilers (Nsight Systems timelines, `ncu --nvtx --nvtx-include "slam_b200/..."`): one per
+// ABI-level phase.  Host-side only -- kernels replayed from the captured CUDA graph are attributed to the
+// range of the call that launches the graph.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 #define SLAM_CUDA_TRY(ctx, expr)                                                      \
   do {                                                                                \

@@ -1114,6 +1114,14 @@ int graph_build_structure(slam_b200_ctx* c) {
   auto t0 = std::chrono::steady_clock::now();
   const int P = g.P(), L = g.L(), Eo = g.Eo(), El = g.El();
   D.P = P; D.L = L; D.Eo = Eo; D.El = El;
+  // profiler ranges of the three host phases (they share locals, hence push/pop instead of scopes); the
+  // guard pops whatever is open on any return
+  struct PhaseRanges {
+    int open = 0;
+    void next(const char* name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = 1; }
+    ~PhaseRanges() { if (open) nvtxRangePop(); }
+  } phase;
+  phase.next("slam_b200/host structure pass");
   // ---- active set (initializeOptimization): edges whose vertices are not all fixed ----
   std::vector<char> pose_act(P, 0), lm_act(L, 0);
   std::vector<int> el_flags(El, 0), eo_flags(Eo, 0);
@@ -1286,6 +1294,7 @@ int graph_build_structure(slam_b200_ctx* c) {
     for (int k = 0; k < 6; k++) eo_info[(size_t)k * Eo + e] = g.eo_info[6 * (size_t)e + k];
   D.nV = cursor;
   D.t_structure = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  phase.next("slam_b200/symbolic analysis + launch lists");
   // ---- symbolic analysis ----
   // Nested-dissection region size: about a tenth of the graph (measured optimum on the 1-lap and
   // 10-lap trackdrive graphs: short assembly tree, still enough regions to order in parallel), but
@@ -1416,6 +1425,7 @@ int graph_build_structure(slam_b200_ctx* c) {
   }
   D.t_lists = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - D.t_structure - S.seconds;
   // ---- upload structure ----
+  phase.next("slam_b200/structure upload");
   auto tu0 = std::chrono::steady_clock::now();
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   g_uploads.clear();

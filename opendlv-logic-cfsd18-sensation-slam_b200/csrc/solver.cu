@@ -1265,6 +1265,7 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
     return graph_enqueue_solve(c);
   }
   if (!D.iter_graph) {
+    NvtxRange nvtx_range("slam_b200/capture GN iteration graph");
     long before = c->launches;
     cudaGraph_t graph = nullptr;
     SLAM_CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
