@@ -310,3 +310,26 @@ def test_two_contexts_on_two_host_threads():
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, os.path.join(here, "gpu_case_two_contexts.py")], capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: the first hardware run decides")
+@pytest.mark.parametrize("tool", ["memcheck", "racecheck"])
+def test_kernels_under_compute_sanitizer(tool):
+    """compute-sanitizer memcheck / racecheck over a small end-to-end case (profiles/tools/sanitizer_case.py:
+    association frames, grid and brute-force bulk association, one graph optimisation through the CTA and warp
+    front kernels, a replica batch) in its own process: no invalid access, no shared-memory hazard."""
+    import shutil
+    import subprocess
+    import sys
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cs = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(cs):
+        pytest.skip("compute-sanitizer not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SLAM_B200_SANITIZER_SMALL="1")
+    r = subprocess.run([cs, "--tool", tool, "--error-exitcode", "3", sys.executable,
+                        os.path.join(root, "profiles", "tools", "sanitizer_case.py")],
+                       capture_output=True, text=True, timeout=420, env=env, cwd=root)
+    assert r.returncode == 0 and "ERROR SUMMARY: 0 errors" in (r.stdout + r.stderr), (r.stdout + r.stderr)[-3000:]
