@@ -74,6 +74,42 @@ def scenarios_yaw(synth):
     return out
 
 
+def scenarios_gate(synth):
+    """Replays shifted so that part of the loop lies beyond the 200 m sanity gate of performSLAM (slam.cpp:300-303:
+    the frame is dropped before a pose is added), with big-orange (4) and negative cone types, zero ranges,
+    azimuths beyond the half circle, zenith != 0 and single-column frames (which the localiser skips, slam.cpp:332,
+    while the mapping phase does not) mixed in.  One drive never closes its loop, two close and localise."""
+    out = []
+    for k in range(3):
+        rng = np.random.default_rng(400 + k)
+        trk = synth.ellipse_track(n_pairs=24 + 2 * k, a=20.0 + 2 * k, b=10.0 + k, half_width=1.5)
+        n = 300
+        d = synth.simulate_drive(trk, n, s_step=1.5 * trk.length / n, seed=120 + k, sigma_r=0.05, sigma_az=0.3)
+        poses = d.poses_noisy.copy()
+        shift = [(188.0, 0.0), (0.0, -193.0), (-186.0, 190.0)][k]
+        poses[:, 0] += shift[0]
+        poses[:, 1] += shift[1]
+        frames = [np.asfortranarray(f, dtype=np.float64).copy() for f in d.frames]
+        for i, f in enumerate(frames):
+            if i == 0 or f.shape[1] == 0:
+                continue
+            if i % 19 == 4:
+                f[3, rng.integers(f.shape[1])] = 4.0                                  # big orange
+            if i % 21 == 6:
+                f[3, rng.integers(f.shape[1])] = -1.0                                 # negative type
+            if i % 27 == 8:
+                f[2, rng.integers(f.shape[1])] = 0.0                                  # zero range
+            if i % 33 == 10:
+                f[0, rng.integers(f.shape[1])] = [181.0, -270.0, 359.5][k]            # azimuth beyond the half circle
+            if i % 7 == 3:
+                f = f[:, :1]                                                          # single column
+            if i % 37 == 12:
+                f[1, rng.integers(f.shape[1])] = 5.0                                  # zenith != 0
+            frames[i] = np.asfortranarray(f)
+        out.append(("gate%d" % k, frames, poses, 1.2, 50.0))
+    return out
+
+
 def main():
     import subprocess
     from conftest import load_pkg
@@ -98,6 +134,16 @@ def main():
         print("%-6s frames %3d  map %3d cones  loop closed at %4d  %5d association entries"
               % (name, len(frames), len(r["map_x"]), closed, len(r["row_ids"])))
     np.savez_compressed(os.path.join(HERE, "fuzz_yaw_replay_reference.npz"), **store)
+
+    store = {}
+    for name, frames, poses, thr, map_thr in scenarios_gate(pkg.synth):
+        r = replay(frames, poses, thr, map_thr)
+        for key, val in r.items():
+            store[name + "/" + key] = val
+        closed = int(np.argmax(r["frame_loop_closed"])) if r["frame_loop_closed"].any() else -1
+        print("%-6s frames %3d  map %3d cones  loop closed at %4d  %5d association entries  %3d frames rejected by the 200 m gate"
+              % (name, len(frames), len(r["map_x"]), closed, len(r["row_ids"]), int((~r["row_present"]).sum())))
+    np.savez_compressed(os.path.join(HERE, "fuzz_gate_replay_reference.npz"), **store)
 
 
 if __name__ == "__main__":

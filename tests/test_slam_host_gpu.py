@@ -307,3 +307,34 @@ def test_localizer_repair_equals_the_oracle(host, window):
     r = subprocess.run([sys.executable, os.path.join(here, "gpu_case_localizer_repair.py"), str(window)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.xfail(strict=False, reason="fixture made after the round's GPU budget was spent: the first hardware run decides; "
+                                        "the oracle reproduces it identically (test_pinned_by_reference.py)")
+def test_gate_replays_equal_the_reference_slam_cpp(host, synth):
+    """The drop-in Slam on tests/golden/fuzz_gate_replay_reference.npz (the reference's real slam.cpp): loops that
+    partly lie beyond the 200 m gate of performSLAM (frames dropped before a pose is added), odd cone types, zero
+    ranges, azimuths beyond the half circle, zenith != 0, single-column frames."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_fuzz_reference_replay import scenarios_gate
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fuzz_gate_replay_reference.npz"))
+    for name, frames, poses, thr, map_thr in scenarios_gate(synth):
+        s = HostSlam(host, thr, map_thr)
+        present = g[name + "/row_present"]
+        for k, (fr, p) in enumerate(zip(frames, poses)):
+            rc, _, _ = s.perform(fr, p)
+            st = s.state()
+            got = (int(st[7]), int(st[0]), int(st[2]), int(st[3]), int(st[1]))
+            want = tuple(int(g[name + "/" + key][k]) for key in ("frame_map_size", "frame_cci", "frame_loop_closing", "frame_loop_closed", "frame_pose_id"))
+            assert got == want, (name, k, got, want)
+            assert (rc == -1) == (not present[k]), (name, k, rc)
+        cnt, flat = s.graph()
+        assert np.array_equal(np.concatenate([[0], np.cumsum(cnt)]), g[name + "/row_ptr"][np.concatenate([[True], present])]), name
+        assert np.array_equal(flat, g[name + "/row_ids"]), name
+        x, y, t, ids = s.cones()
+        assert np.array_equal(t, g[name + "/map_type"]), name
+        gx, gy = g[name + "/map_x"], g[name + "/map_y"]
+        tol = 1e-6 * max(1.0, np.abs(gx).max(), np.abs(gy).max()) if g[name + "/frame_loop_closed"].any() else 1e-9
+        assert np.max(np.abs(x - gx)) <= tol and np.max(np.abs(y - gy)) <= tol, name
+        s.close()
