@@ -1,0 +1,67 @@
+"""Body of test_abi.py::test_host_code_over_a_stub_runtime (own process, LD_PRELOAD=<stub_cudart.so>): drives the
+host code behind the C ABI on a box without a GPU -- see tests/stub_cudart.cpp.  Prints one JSON line.
+SLAM_LIB overrides the library (profiles/tools/host_sanitize.sh points it at an ASan build)."""
+import ctypes as C
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+from conftest import load_pkg, small_graph  # noqa: E402
+
+pkg = load_pkg()
+if os.environ.get("SLAM_LIB"):
+    importlib.import_module(pkg.__name__ + "._build").LIB = os.environ["SLAM_LIB"]
+stub = C.CDLL(os.environ["SLAM_STUB_CUDART"])
+stub.stub_h2d_hash.restype = C.c_ulong
+stub.stub_h2d_bytes.restype = C.c_size_t
+synth = pkg.synth
+ctx = pkg.Context(0)
+L = ctx.L
+c_dp = C.POINTER(C.c_double)
+out = {"uploads": {}, "rc": {}}
+
+
+def prepare(g, label):
+    stub.stub_reset()
+    ctx.graph_load(g)
+    n = ctx.graph_prepare()
+    st = ctx.graph_stats()
+    out["uploads"][label] = {"n": int(n), "bytes": int(stub.stub_h2d_bytes()), "hash": "%x" % stub.stub_h2d_hash(),
+                             "fronts": int(st["n_fronts"]), "nnz_L": int(st["nnz_L"])}
+
+
+prepare(synth.graph_from_drive(synth.trackdrive(1)), "c1")
+prepare(synth.graph_from_drive(synth.trackdrive(3, poses_per_lap=1500, seed=5)), "three_laps")   # >= 4096 blocks: pool path
+prepare(small_graph(synth, 150), "small")
+# incremental API, gauge flags, error paths (int status, message on the context, nothing thrown)
+ctx.graph_clear()
+z = np.zeros(3)
+info = np.eye(3).ravel().copy()
+rc = out["rc"]
+rc["add_pose"] = L.slam_b200_graph_add_pose(ctx.h, 1000, 0.0, 0.0, 0.0)
+rc["add_pose_duplicate"] = L.slam_b200_graph_add_pose(ctx.h, 1000, 0.0, 0.0, 0.0)
+rc["add_landmark"] = L.slam_b200_graph_add_landmark(ctx.h, 0, 1.0, 1.0)
+rc["edge_unknown_landmark"] = L.slam_b200_graph_add_edge_se2_xy(ctx.h, 1000, 7, z.ctypes.data_as(c_dp), info.ctypes.data_as(c_dp))
+rc["edge_null_pointers"] = L.slam_b200_graph_add_edge_se2_xy(ctx.h, 1000, 0, None, None)
+rc["set_fixed_unknown"] = L.slam_b200_graph_set_fixed(ctx.h, 4242, 1)
+rc["last_error_set"] = int(bool(L.slam_b200_last_error(ctx.h)))
+rc["prepare_no_edges"] = L.slam_b200_graph_prepare(ctx.h)
+rc["optimize_nothing_to_do"] = ctx.graph_optimize_rc(3)[0]           # g2o: -1
+# map + frame staging paths (kernels are no-ops; buffers, growth and copies are real)
+f = synth.cone_field(n_map=5000, n_obs=700, seed=4)
+ctx.map_clear()
+ctx.map_append(f.map_x, f.map_y, f.map_type)
+rc["map_size"] = ctx.map_size()
+x, y, t = ctx.map_read()
+rc["map_roundtrip"] = int(np.array_equal(x, f.map_x) and np.array_equal(y, f.map_y) and np.array_equal(t, f.map_type))
+fr = np.asfortranarray(np.random.default_rng(0).normal(size=(4, 900)))
+ctx.cones_to_global(fr, np.zeros(3))
+ctx.assoc_localize_frame(fr, np.zeros(3), 1.2, 0)
+ctx.close()
+print(json.dumps(out))

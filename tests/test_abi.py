@@ -34,3 +34,53 @@ def test_product_does_not_link_or_import_the_oracle(pkg):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
                 assert "orc_" not in txt, f
+
+
+def test_host_code_over_a_stub_runtime(pkg, tmp_path):
+    """The HOST code behind the C ABI (argument checks and status codes, graph_load, structure pass, symbolic
+    phase, launch lists, packing of the structure upload, map / frame staging) on a box without a GPU: a
+    subprocess with tests/stub_cudart.cpp LD_PRELOADed in place of the CUDA runtime (device memory = host heap,
+    kernels = no-ops, nothing computed -- test infrastructure, the product never sees it).  The bytes uploaded for a
+    graph must not depend on the size of the host pool; error paths return SLAM_B200_E_ARG with a message and
+    g2o's -1 for "nothing to optimise"."""
+    import json
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    pkg.build()
+    stub = str(tmp_path / "stub_cudart.so")
+    b = subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-o", stub, os.path.join(here, "stub_cudart.cpp")], capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr[-2000:]
+    runs = []
+    for threads in ("1", "8"):
+        env = dict(os.environ, LD_PRELOAD=stub, SLAM_STUB_CUDART=stub, SLAM_B200_SYM_THREADS=threads)
+        r = subprocess.run([sys.executable, os.path.join(here, "host_case_stub_runtime.py")], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-3000:]
+        runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert runs[0]["uploads"] == runs[1]["uploads"]                       # same structure bit for bit, 1 or 8 host threads
+    up = runs[0]["uploads"]
+    assert up["c1"]["n"] == 3590 and up["three_laps"]["n"] == 14090 and all(v["bytes"] > 0 for v in up.values())
+    rc = runs[0]["rc"]
+    E_ARG = -101
+    assert rc["add_pose"] == 0 and rc["add_landmark"] == 0 and rc["prepare_no_edges"] == 0
+    assert rc["add_pose_duplicate"] == rc["edge_unknown_landmark"] == rc["edge_null_pointers"] == rc["set_fixed_unknown"] == E_ARG
+    assert rc["last_error_set"] == 1 and rc["optimize_nothing_to_do"] == -1
+    assert rc["map_size"] == 5000 and rc["map_roundtrip"] == 1
+
+
+def test_host_code_under_sanitizers(tmp_path):
+    """profiles/tools/host_sanitize.sh: the same host case on an AddressSanitizer + UBSan build of the library's
+    host code (device code untouched), over the stub runtime whose "device" buffers are heap blocks ASan guards --
+    an out-of-bounds structure array, a mis-sized staging buffer or a signed overflow in the index arithmetic of
+    graph_load / the structure pass / the symbolic phase / the upload packing aborts with a report."""
+    import json
+    import shutil
+    import subprocess
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["sh", os.path.join(root, "profiles", "tools", "host_sanitize.sh")], capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, OUT=str(tmp_path)))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-4000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["uploads"]["three_laps"]["n"] == 14090 and out["rc"]["map_roundtrip"] == 1
