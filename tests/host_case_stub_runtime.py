@@ -39,6 +39,21 @@ def prepare(g, label):
 prepare(synth.graph_from_drive(synth.trackdrive(1)), "c1")
 prepare(synth.graph_from_drive(synth.trackdrive(3, poses_per_lap=1500, seed=5)), "three_laps")   # >= 4096 blocks: pool path
 prepare(small_graph(synth, 150), "small")
+# the topology of the opt-in localiser repair: every landmark and all but the last W poses fixed --
+# thousands of inactive edges, a handful of free blocks, landmark edges with only their pose end free
+g1 = synth.graph_from_drive(synth.trackdrive(1))
+out["window"] = {}
+for W in (1, 3, 10, 50):
+    ctx.graph_load(g1)
+    for v in list(g1.lm_ids) + list(g1.pose_ids[:len(g1.pose_ids) - W]):
+        ctx.graph_set_fixed(int(v), True)
+    n = ctx.graph_prepare()
+    st = ctx.graph_stats()
+    out["window"][str(W)] = {"n": int(n), "blocks": int(st["n_blocks"]), "offdiag": int(st["n_offdiag_blocks"]), "fronts": int(st["n_fronts"])}
+ctx.graph_load(g1)
+for v in list(g1.lm_ids) + list(g1.pose_ids):
+    ctx.graph_set_fixed(int(v), True)
+out["window"]["all_fixed"] = {"prepare": int(ctx.graph_prepare()), "optimize": int(ctx.graph_optimize_rc(2)[0])}
 # incremental API, gauge flags, error paths (int status, message on the context, nothing thrown)
 ctx.graph_clear()
 z = np.zeros(3)

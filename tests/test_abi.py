@@ -60,6 +60,10 @@ def test_host_code_over_a_stub_runtime(pkg, tmp_path):
     assert runs[0]["uploads"] == runs[1]["uploads"]                       # same structure bit for bit, 1 or 8 host threads
     up = runs[0]["uploads"]
     assert up["c1"]["n"] == 3590 and up["three_laps"]["n"] == 14090 and all(v["bytes"] > 0 for v in up.values())
+    for W in (1, 3, 10, 50):                                              # the sliding window of the localiser repair
+        w = runs[0]["window"][str(W)]
+        assert w["n"] == 3 * W and w["blocks"] == W and w["offdiag"] == W - 1 and w["fronts"] >= 1, (W, w)
+    assert runs[0]["window"]["all_fixed"] == {"prepare": 0, "optimize": -1}   # g2o: nothing to optimise
     rc = runs[0]["rc"]
     E_ARG = -101
     assert rc["add_pose"] == 0 and rc["add_landmark"] == 0 and rc["prepare_no_edges"] == 0
