@@ -16,8 +16,8 @@ typedef void* cudaEvent_t;
 typedef void* cudaGraph_t;
 typedef void* cudaGraphExec_t;
 struct dim3 { unsigned x, y, z; };
-static unsigned long g_h2d_hash = 1469598103934665603ull;
-static size_t g_h2d_bytes = 0;
+static thread_local unsigned long g_h2d_hash = 1469598103934665603ull;
+static thread_local size_t g_h2d_bytes = 0;  // per host thread: the copies of one ABI call happen on the calling thread
 extern "C" {
 unsigned long stub_h2d_hash() { return g_h2d_hash; }
 size_t stub_h2d_bytes() { return g_h2d_bytes; }

@@ -88,3 +88,19 @@ def test_host_code_under_sanitizers(tmp_path):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-4000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["uploads"]["three_laps"]["n"] == 14090 and out["rc"]["map_roundtrip"] == 1
+
+
+def test_two_contexts_on_two_host_threads_under_tsan(tmp_path):
+    """profiles/tools/host_sanitize.sh tsan: a ThreadSanitizer build of the library's host code over the stub runtime;
+    two host threads, each with its own context and graph, run graph_load / graph_prepare / graph_optimize / map
+    staging at the same time (tests/tsan_two_contexts_driver.cpp).  No data race, no hang, and each thread's analysis
+    equals what it gets alone -- the threading contract of include/slam_b200.h on everything but the kernels (the
+    GPU half is test_graph_gpu.py::test_two_contexts_on_two_host_threads)."""
+    import shutil
+    import subprocess
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["sh", os.path.join(root, "profiles", "tools", "host_sanitize.sh"), "tsan"], capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, OUT=str(tmp_path)))
+    assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("ok "), r.stdout[-1500:] + r.stderr[-4000:]
