@@ -11,6 +11,7 @@
 // for what nextPose()/nextYawRate() store, and the senders are optional callbacks.
 #pragma once
 #include <array>
+#include <atomic>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -118,7 +119,9 @@ class Slam {
   bool m_sendConeData = false;
   bool m_sendPoseData = false;
   bool m_loopClosing = false;
-  bool m_loopClosingComplete = false;
+  // read without a lock by drawCurrentPose() on the viewer thread (slam.cpp:769, as in the reference) while a
+  // frame thread sets it under map + optimizer mutex (632): atomic here, a plain bool there
+  std::atomic<bool> m_loopClosingComplete{false};
   slamtypes::Vector3d m_sendPose;
   std::mutex m_sendMutex;
   uint32_t m_senderStamp = 0;

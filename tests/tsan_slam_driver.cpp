@@ -23,14 +23,16 @@ int main() {
     slam.onSendCones = [&](const std::vector<Cone>& m, uint32_t, const slamtypes::Vector3d&) { sends += (int)m.size() > 0; };
     std::atomic<bool> done{false};
     long seen = 0;
+    std::atomic<int> looks{0};
     std::thread viewer([&] {
       while (!done.load()) {
+        looks++;
         seen += (long)slam.drawCones().size() + (long)slam.drawPoses().size() + (long)slam.drawGraph().size();
         seen += (long)slam.buildConePacket().size();
         seen += slam.drawCurrentPose()(0) > 1e300;
       }
     });
-    for (int k = 0; k < 400; k++) {
+    for (int k = 0; k < 400 || (looks.load() < 200 && k < 200000); k++) {   // until the viewer has really looked
       slamtypes::MatrixXd cones(4, 3 + k % 5);
       for (int j = 0; j < cones.cols(); j++) { cones(0, j) = 5 + j; cones(1, j) = 0; cones(2, j) = 4 + j; cones(3, j) = 1 + (j & 1); }
       slam.setOdometry(0.1 * k, 0.05 * k, 0.01 * k);
