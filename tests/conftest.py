@@ -70,3 +70,12 @@ def small_graph(synth, n_poses=120, seed=7):
     trk = synth.ellipse_track()
     d = synth.simulate_drive(trk, n_poses, s_step=trk.length / 1000, seed=seed, closed=True)
     return synth.graph_from_drive(d)
+
+
+def skip_if_sanitizer_runtime_unusable(output):
+    """Sanitizer runtimes refuse to start on some kernels / container settings (ASLR entropy, ptrace limits);
+    that is an environment limit, not a finding."""
+    for marker in ("unexpected memory mapping", "Shadow memory range interleaves", "ReserveShadowMemoryRange failed",
+                   "LeakSanitizer has encountered a fatal error", "failed to intercept"):
+        if marker in output:
+            pytest.skip("sanitizer runtime cannot start here: " + marker)

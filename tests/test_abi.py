@@ -5,6 +5,8 @@ import os
 
 import pytest
 
+from conftest import skip_if_sanitizer_runtime_unusable
+
 
 def test_library_exports_every_declared_symbol(pkg):
     L = pkg.capi.lib()
@@ -85,6 +87,7 @@ def test_host_code_under_sanitizers(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run(["sh", os.path.join(root, "profiles", "tools", "host_sanitize.sh")], capture_output=True, text=True,
                        timeout=900, env=dict(os.environ, OUT=str(tmp_path)))
+    skip_if_sanitizer_runtime_unusable(r.stdout + r.stderr)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-4000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["uploads"]["three_laps"]["n"] == 14090 and out["rc"]["map_roundtrip"] == 1
@@ -103,4 +106,5 @@ def test_two_contexts_on_two_host_threads_under_tsan(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run(["sh", os.path.join(root, "profiles", "tools", "host_sanitize.sh"), "tsan"], capture_output=True, text=True,
                        timeout=900, env=dict(os.environ, OUT=str(tmp_path)))
+    skip_if_sanitizer_runtime_unusable(r.stdout + r.stderr)
     assert r.returncode == 0 and r.stdout.strip().splitlines()[-1].startswith("ok "), r.stdout[-1500:] + r.stderr[-4000:]

@@ -7,6 +7,8 @@ import os
 import numpy as np
 import pytest
 
+from conftest import skip_if_sanitizer_runtime_unusable
+
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
 
@@ -131,6 +133,7 @@ def test_host_mirror_compiles_against_the_reference_eigen(pkg):
                         os.path.join(src, "slam.cpp"), os.path.join(src, "cone.cpp"),
                         os.path.join(src, "frame_assembler.cpp"), os.path.join(src, "slam_c.cpp")],
                        capture_output=True, text=True)
+    skip_if_sanitizer_runtime_unusable(r.stdout + r.stderr)
     assert r.returncode == 0, r.stderr
 
 
@@ -152,4 +155,5 @@ def test_slam_lock_discipline_under_tsan(pkg, tmp_path):
     if b.returncode != 0:
         pytest.skip("sanitizer runtime not available: " + b.stderr[-300:])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=240, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
+    skip_if_sanitizer_runtime_unusable(r.stdout + r.stderr)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout[-500:] + r.stderr[-3000:]

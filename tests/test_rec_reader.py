@@ -11,6 +11,8 @@ import sys
 import numpy as np
 import pytest
 
+from conftest import skip_if_sanitizer_runtime_unusable
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 REC = os.path.join(HERE, "golden", "c1_head.rec")
 sys.path.insert(0, os.path.join(HERE, "golden"))
@@ -152,6 +154,7 @@ def test_mutated_streams_under_sanitizers(pkg, tmp_path):
     if b.returncode != 0:
         pytest.skip("sanitizer runtime not available: " + b.stderr[-300:])
     r = subprocess.run([exe, os.path.join(here, "golden", "c1_head.rec"), "7", "3000"], capture_output=True, text=True, timeout=600)
+    skip_if_sanitizer_runtime_unusable(r.stdout + r.stderr)
     assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout[-500:] + r.stderr[-3000:]
 
 

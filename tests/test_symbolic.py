@@ -5,7 +5,7 @@ import pytest
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from conftest import small_graph
+from conftest import small_graph, skip_if_sanitizer_runtime_unusable
 import mf_emul
 
 
@@ -155,4 +155,5 @@ def test_symbolic_phase_under_sanitizers(pkg, tmp_path, san):
         pytest.skip("sanitizer runtime not available: " + b.stderr[-300:])
     env = dict(os.environ, SLAM_B200_SYM_THREADS="8", TSAN_OPTIONS="halt_on_error=1")
     r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=240, env=env)
+    skip_if_sanitizer_runtime_unusable(r.stdout + r.stderr)
     assert r.returncode == 0 and r.stdout.strip() == "ok 0", r.stdout[-500:] + r.stderr[-3000:]
