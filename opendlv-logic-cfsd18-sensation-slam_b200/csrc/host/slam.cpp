@@ -100,6 +100,14 @@ void Slam::performSLAM(MatrixXd cones) {
   if (m_loopClosingComplete && cones.cols() > 1) localizer(pose, cones);  // 332-334
 }
 
+// The host mirror and the device map grow in lock step; an association record that points outside the mirror
+// means they have come apart (a backend fault) -- fail loudly instead of reading past m_map.
+void Slam::checkMapIndex(int32_t j) const {
+  if (j < 0 || (size_t)j >= m_map.size())
+    throw std::runtime_error("association index " + std::to_string(j) + " outside the map of " +
+                             std::to_string(m_map.size()) + " cones");
+}
+
 // slam.cpp:433-443
 void Slam::addPoseToGraph(Vector3d pose) {
   check(m_ctx, slam_b200_graph_add_pose(m_ctx, m_poseId, pose(0), pose(1), pose(2)), "graph_add_pose");
@@ -158,6 +166,7 @@ void Slam::addConesToMap(MatrixXd cones, Vector3d pose) {
     }
     for (int i = 0; i < n; i++) {
       if (m_lastStatus[i] == SLAM_B200_ASSOC_MATCHED) {            // 584-592
+        checkMapIndex(m_lastIdx[i]);
         addConeMeasurement(m_map[m_lastIdx[i]], &z[2 * (size_t)i]);
       } else if (m_lastStatus[i] == SLAM_B200_ASSOC_NEW) {         // 608-619
         Cone cone(g[3 * (size_t)i], g[3 * (size_t)i + 1], (int)g[3 * (size_t)i + 2], (int)m_map.size());
@@ -251,7 +260,10 @@ void Slam::localizer(Vector3d pose, MatrixXd cones) {
         std::vector<double> local(3 * (size_t)n);
         check(m_ctx, slam_b200_cones_to_global(m_ctx, cones.data(), n, p, nullptr, local.data()), "cones_to_global");
         for (int i = 0; i < n; i++)
-          if (idx[i] >= 0) addConeMeasurement(m_map[idx[i]], &local[3 * (size_t)i]);
+          if (idx[i] >= 0) {
+            checkMapIndex(idx[i]);
+            addConeMeasurement(m_map[idx[i]], &local[3 * (size_t)i]);
+          }
         optimizeWindow();
       }
     } else if (reobs > 0) {
@@ -262,7 +274,10 @@ void Slam::localizer(Vector3d pose, MatrixXd cones) {
       double local[3];
       check(m_ctx, slam_b200_cones_to_global(m_ctx, asObs, 1, zero, nullptr, local), "cones_to_global");
       for (int i = 0; i < n; i++)
-        if (idx[i] >= 0) addConeMeasurement(m_map[idx[i]], local);
+        if (idx[i] >= 0) {
+          checkMapIndex(idx[i]);
+          addConeMeasurement(m_map[idx[i]], local);
+        }
     }
     m_sendConeData = send != 0;  // 385
   }

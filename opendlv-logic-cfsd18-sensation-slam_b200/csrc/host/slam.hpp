@@ -88,6 +88,7 @@ class Slam {
   void addOdometryMeasurement(slamtypes::Vector3d pose);
   void optimizeGraph();
   void optimizeWindow();
+  void checkMapIndex(int32_t j) const;
   void localizer(slamtypes::Vector3d pose, slamtypes::MatrixXd cones);
   slamtypes::Vector3d updatePoseFromGraph();
   void addPoseToGraph(slamtypes::Vector3d pose);
