@@ -54,6 +54,21 @@ ctx.graph_load(g1)
 for v in list(g1.lm_ids) + list(g1.pose_ids):
     ctx.graph_set_fixed(int(v), True)
 out["window"]["all_fixed"] = {"prepare": int(ctx.graph_prepare()), "optimize": int(ctx.graph_optimize_rc(2)[0])}
+# host side of the replica batch (value interleaving, upload / download staging) and of the sharded assembly
+gs = small_graph(synth, 150)
+pe, le, ez, oz = synth.perturb_replicas(gs, 8, seed=18)
+ctx.graph_load(gs)
+res = ctx.graph_optimize_batch(pe, le, oz, ez, iters=2)
+out["batch"] = {"replicas": int(np.asarray(res[0]).shape[0])}
+ctx.graph_load(g1)
+ctx.graph_prepare_assembly_only()
+P1 = len(g1.pose_ids)
+out["shards"] = []
+for p0, p1 in ((0, P1 // 2), (P1 // 2, P1)):
+    l0, l1 = ctx.graph_shard_landmarks(p0, p1)
+    ctx.graph_assemble_async(p0, p1)
+    out["shards"].append([int(l0), int(l1)])
+ctx.sync()
 # incremental API, gauge flags, error paths (int status, message on the context, nothing thrown)
 ctx.graph_clear()
 z = np.zeros(3)

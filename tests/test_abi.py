@@ -66,6 +66,8 @@ def test_host_code_over_a_stub_runtime(pkg, tmp_path):
         w = runs[0]["window"][str(W)]
         assert w["n"] == 3 * W and w["blocks"] == W and w["offdiag"] == W - 1 and w["fronts"] >= 1, (W, w)
     assert runs[0]["window"]["all_fixed"] == {"prepare": 0, "optimize": -1}   # g2o: nothing to optimise
+    assert runs[0]["batch"] == {"replicas": 8} and len(runs[0]["shards"]) == 2   # batch and sharded-assembly host paths ran
+    assert all(0 <= l0 <= l1 for l0, l1 in runs[0]["shards"])
     rc = runs[0]["rc"]
     E_ARG = -101
     assert rc["add_pose"] == 0 and rc["add_landmark"] == 0 and rc["prepare_no_edges"] == 0
