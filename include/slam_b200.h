@@ -213,11 +213,15 @@ long slam_b200_graph_system_dev(slam_b200_ctx* ctx, int which, double** ptr);
  * every peer's region, followed by a kernel that waits for all ranks and sums the partials in rank
  * order, reading them straight from the peers' memory over NVLink, into the landmark part of V --
  * every rank ends up with the complete landmark part, bit-identical on all ranks.
+ * A rank that waits longer than the time-out for a peer (default 10 s; xchg_set_timeout_ms) gives up:
+ * the landmark part of V is zeroed, the graph's fail flag is raised (factorise / update leave the
+ * state alone, graph_finish / graph_optimize return 0 iterations) and xchg_error turns 1 for good.
  * xchg_error: synchronises and returns 1 if a rank ever timed out waiting for a peer. */
 int slam_b200_graph_shard_landmarks(slam_b200_ctx* ctx, int p0, int p1, int32_t* l0, int32_t* l1);
 int slam_b200_xchg_create(slam_b200_ctx* ctx, int world, int rank, int cap, unsigned char handle_out[64]);
 int slam_b200_xchg_connect(slam_b200_ctx* ctx, const unsigned char* handles, const int32_t* ranges);
 int slam_b200_graph_assemble_exchange_async(slam_b200_ctx* ctx, int p0, int p1);
+int slam_b200_xchg_set_timeout_ms(slam_b200_ctx* ctx, double ms);
 int slam_b200_xchg_error(slam_b200_ctx* ctx);
 /* Enqueues factorise + solve + update for the system currently assembled. */
 int slam_b200_graph_solve_async(slam_b200_ctx* ctx);

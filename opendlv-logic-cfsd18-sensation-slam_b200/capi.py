@@ -68,6 +68,7 @@ def lib():
         L.slam_b200_xchg_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
         L.slam_b200_xchg_connect.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), c_ip]
         L.slam_b200_xchg_error.argtypes = [C.c_void_p]
+        L.slam_b200_xchg_set_timeout_ms.argtypes = [C.c_void_p, C.c_double]
         L.slam_b200_map_build_grid.argtypes = [C.c_void_p, C.c_double]
         L.slam_b200_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.slam_b200_profile_read.argtypes = [C.c_void_p, c_dp]
@@ -345,6 +346,9 @@ class Context:
 
     def graph_assemble_exchange_async(self, p0, p1):
         self._ck(self.L.slam_b200_graph_assemble_exchange_async(self.h, int(p0), int(p1)), "graph_assemble_exchange_async")
+
+    def xchg_set_timeout_ms(self, ms):
+        self._ck(self.L.slam_b200_xchg_set_timeout_ms(self.h, float(ms)), "xchg_set_timeout_ms")
 
     def xchg_error(self):
         return self._ck(self.L.slam_b200_xchg_error(self.h), "xchg_error")

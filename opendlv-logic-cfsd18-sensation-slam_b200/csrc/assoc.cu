@@ -11,8 +11,17 @@
 // computes (ascending scans that stop at the first hit, or an explicit min over bucket candidates).
 //
 // Compiled with -fmad=false: the reference build (x86-64 -O2, CMakeLists.txt:35-38) has no fused
-// multiply-add, and the gate decisions must be bit-exact, so products and sums are rounded
-// separately exactly like the CPU does.  sqrt is IEEE correctly rounded on both sides.
+// multiply-add, so products and sums are rounded separately exactly like the CPU does, and sqrt is
+// IEEE correctly rounded on both sides: the gate arithmetic itself (coneToGlobal's rotation,
+// distanceBetweenCones, the exact `d^2 < D*` test) is bit-identical to the reference's.
+// What is NOT bit-identical is the polar -> Cartesian conversion in front of it: device sincos() /
+// asin() are accurate to 1-2 ulp, glibc's libm (what the reference links) to < 1 ulp, and they do not
+// round the same way.  The real guarantee therefore is: IDENTICAL association decisions unless an
+// observation's distance to a candidate lies within a few ulp (relative 1e-15, i.e. ~1e-15 m) of
+// sameConeThreshold or of the 1 m loop-closure gate; tests assert that no decision of any fixture
+// sits within 1e-9 m of a gate (tests/test_assoc_gpu.py), and the converted coordinates themselves
+// are checked at a 16-ulp bar against 424 vectors from the reference's compiled slam.cpp.
+// The heading's cos/sin (coneToGlobal) are taken from the HOST's libm for exactly this reason.
 #include <cub/device/device_scan.cuh>
 #include <cmath>
 #include <cfloat>

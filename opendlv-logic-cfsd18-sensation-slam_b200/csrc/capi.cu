@@ -251,7 +251,19 @@ int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids,
                          const double* el_info4, int n_fixed, const int32_t* fixed_ids) try {
   NvtxRange nvtx_range("slam_b200/graph_load");
   if (!c || n_poses < 0 || n_landmarks < 0 || n_eo < 0 || n_el < 0 || n_fixed < 0) return SLAM_B200_E_ARG;
+  // every array whose count is > 0 must be there: E_ARG, not a crash
+  if ((n_poses && (!pose_ids || !pose_est3)) || (n_landmarks && (!lm_ids || !lm_est2)) ||
+      (n_eo && (!eo_from || !eo_to || !eo_z3 || !eo_info9)) || (n_el && (!el_pose || !el_lm || !el_z2 || !el_info4)) ||
+      (n_fixed && !fixed_ids)) {
+    c->fail("graph_load: null array with a non-zero count");
+    return SLAM_B200_E_ARG;
+  }
   slam_b200_graph_clear(c);
+  // any error below leaves an EMPTY graph behind, never a half-built one a later optimise would run on
+  struct ClearOnError {
+    slam_b200_ctx* c; bool armed = true;
+    ~ClearOnError() { if (armed) { std::string keep = c->err; slam_b200_graph_clear(c); c->err = keep; } }
+  } guard{c};
   HostGraph& g = c->g;
   g.id2v.reserve((size_t)n_poses + n_landmarks);
   g.pose_id.assign(pose_ids, pose_ids + n_poses);
@@ -322,6 +334,7 @@ int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids,
   }
   g.structure_version++;
   g.values_version++;
+  guard.armed = false;
   return 0;
 } SLAM_ABI_CATCH(c)
 
@@ -508,18 +521,30 @@ int slam_b200_xchg_connect(slam_b200_ctx* c, const unsigned char* handles, const
   if (!c || !c->sys || !handles || !ranges || !c->sys->xchg.local) return SLAM_B200_E_STATE;
   if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   PeerExchange& X = c->sys->xchg;
+  // validate BEFORE any handle is opened, so an argument error leaves nothing to close
+  for (int r = 0; r < X.world; r++)
+    if (ranges[2 * r] < 0 || ranges[2 * r + 1] < ranges[2 * r] || ranges[2 * r + 1] - ranges[2 * r] > X.cap ||
+        ranges[2 * r + 1] > c->sys->L) return SLAM_B200_E_ARG;
+  for (int r = 0; r < (int)X.peers.size(); r++)  // a second connect: drop the first one's mappings
+    if (r != X.rank && X.peers[r]) cudaIpcCloseMemHandle(X.peers[r]);
+  X.connected = false;
   X.peers.assign(X.world, nullptr);
   for (int r = 0; r < X.world; r++) {
     if (r == X.rank) { X.peers[r] = X.local; continue; }
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handles + 64 * (size_t)r, 64);
     void* p = nullptr;
-    SLAM_CUDA_TRY(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; q++)
+        if (q != X.rank && X.peers[q]) cudaIpcCloseMemHandle(X.peers[q]);
+      X.peers.assign(X.world, nullptr);
+      c->fail(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      return SLAM_B200_E_CUDA;
+    }
     X.peers[r] = static_cast<char*>(p);
   }
   X.ranges_host.assign(ranges, ranges + 2 * (size_t)X.world);
-  for (int r = 0; r < X.world; r++)
-    if (ranges[2 * r + 1] - ranges[2 * r] > X.cap || ranges[2 * r] < 0 || ranges[2 * r + 1] > c->sys->L) return SLAM_B200_E_ARG;
   SLAM_CUDA_TRY(c, X.peer_tab.exact(X.world));
   SLAM_CUDA_TRY(c, X.ranges.exact(2 * (size_t)X.world));
   SLAM_CUDA_TRY(c, X.err.exact(1));
@@ -540,6 +565,13 @@ int slam_b200_graph_assemble_exchange_async(slam_b200_ctx* c, int p0, int p1) tr
   DeviceSystem& D = *c->sys;
   if (p0 < 0 || p1 > D.P || p0 > p1) return SLAM_B200_E_ARG;
   return graph_enqueue_assemble(c, p0, p1, false, true);
+} SLAM_ABI_CATCH(c)
+
+int slam_b200_xchg_set_timeout_ms(slam_b200_ctx* c, double ms) try {
+  if (!c || !c->sys) return SLAM_B200_E_STATE;
+  if (!(ms > 0.0) || ms > 3.6e6) return SLAM_B200_E_ARG;
+  c->sys->xchg.timeout_ns = (unsigned long long)(ms * 1e6);
+  return 0;
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_xchg_error(slam_b200_ctx* c) try {

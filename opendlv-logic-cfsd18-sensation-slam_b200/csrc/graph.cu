@@ -880,15 +880,21 @@ assemble_landmark_kernel(AsmArgs a, int p0, int p1, int chi2_nblocks, int l_firs
 
 // Second half of the peer exchange: wait until every rank has published `epoch`, then
 // V[landmark part] = sum over ranks (ascending) of their partial blocks.  A rank that never arrives
-// (a peer died) is reported through *err after `timeout_ns` instead of hanging the GPU.
+// (a peer died) does not hang the GPU: after `timeout_ns` the kernel sets *err (sticky, read by
+// slam_b200_xchg_error), raises the fail flag of the graph (status[0]: factorise/update then leave the
+// state alone and graph_finish / graph_optimize report 0 iterations, the g2o failure convention) and
+// writes ZEROS into the landmark part of V instead of stale or partial blocks.
 __global__ void __launch_bounds__(256)
 lm_exchange_sum_kernel(char* const* __restrict__ peer_tab, int world, int rank, int cap, int parity,
                        unsigned long long epoch, const int* __restrict__ ranges, int L, double* __restrict__ V,
-                       int* err, unsigned long long timeout_ns) {
+                       int* err, int* status, unsigned long long timeout_ns) {
   __shared__ int go;
   // This kernel follows the landmark kernel on the stream, so the rank's slot is complete: CTA 0
-  // publishes `epoch` in every rank's flag word (the only remote stores of the exchange; all CTAs of
-  // this grid are resident at once, so CTA 0 cannot be starved by the spinning ones).
+  // publishes `epoch` in every rank's flag word (the only remote stores of the exchange).  The grid
+  // may exceed what is resident at once (L above ~300k landmarks): correctness does not need full
+  // residency, only that CTA 0 gets an SM -- thread blocks are dispatched in index order, so CTA 0 is
+  // among the first wave and never waits behind the spinning ones; every spinning CTA only waits for
+  // stores made by the CTA 0s of the OTHER ranks' grids.
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
     reinterpret_cast<volatile unsigned long long*>(peer_tab[threadIdx.x])[rank] = epoch;
@@ -904,16 +910,15 @@ lm_exchange_sum_kernel(char* const* __restrict__ peer_tab, int world, int rank, 
         if (t1 - t0 > timeout_ns) { ok = 0; break; }
       }
     }
-    if (!ok) *err = 1;
+    if (!ok) { *err = 1; status[0] = 1; }
     __threadfence();
     go = ok;
   }
   __syncthreads();
-  if (!go) return;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;
   double b0 = 0, b1 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-  for (int s = 0; s < world; s++) {
+  for (int s = 0; go && s < world; s++) {
     const int l0 = ranges[2 * s], l1 = ranges[2 * s + 1];
     if (l < l0 || l >= l1) continue;
     const double* slot = xchg_slot(peer_tab[s], cap, parity);  // remote for s != rank: read over NVLink
@@ -1091,7 +1096,7 @@ int graph_enqueue_assemble(slam_b200_ctx* c, int p0, int p1, bool chi2_only, boo
   if (peer) {
     PeerExchange& X = D.xchg;
     lm_exchange_sum_kernel<<<(D.L + 255) / 256, 256, 0, c->stream>>>(X.peer_tab.p, X.world, X.rank, X.cap, px.parity, X.epoch,
-                                                                   X.ranges.p, D.L, D.V.p, X.err.p, 200000000ull);
+                                                                   X.ranges.p, D.L, D.V.p, X.err.p, D.status.p, X.timeout_ns);
     c->launches++;
   }
   SLAM_CUDA_TRY(c, cudaGetLastError());

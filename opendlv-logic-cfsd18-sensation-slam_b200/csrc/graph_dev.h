@@ -45,6 +45,9 @@ struct PeerExchange {
   int world = 0, rank = 0, cap = 0;  // cap = landmarks per slot (max shard range over the ranks)
   bool connected = false;
   unsigned long long epoch = 0;
+  // how long a rank waits for its peers before it gives up (slam_b200_xchg_set_timeout_ms; default 10 s:
+  // structure rebuilds, host jitter or a first launch on one rank must not look like a dead peer)
+  unsigned long long timeout_ns = 10000000000ull;
   char* local = nullptr;             // this rank's region (cudaMalloc, exported through CUDA IPC)
   size_t bytes = 0;
   std::vector<char*> peers;          // region base per rank; peers[rank] == local, others opened via IPC

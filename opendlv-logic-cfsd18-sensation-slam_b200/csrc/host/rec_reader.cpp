@@ -31,7 +31,7 @@ struct Cursor {
     return 0;
   }
   float fixed32() {
-    if (off + 4 > n) { ok = false; return 0.0f; }
+    if (n - off < 4) { ok = false; return 0.0f; }
     uint32_t u = (uint32_t)p[off] | (uint32_t)p[off + 1] << 8 | (uint32_t)p[off + 2] << 16 | (uint32_t)p[off + 3] << 24;
     off += 4;
     float f;
@@ -39,7 +39,7 @@ struct Cursor {
     return f;
   }
   double fixed64() {
-    if (off + 8 > n) { ok = false; return 0.0; }
+    if (n - off < 8) { ok = false; return 0.0; }
     uint64_t u = 0;
     for (int k = 0; k < 8; k++) u |= (uint64_t)p[off + k] << (8 * k);
     off += 8;
@@ -49,15 +49,17 @@ struct Cursor {
   }
   Cursor sub() {  // length-delimited field
     const uint64_t len = varint();
-    if (!ok || off + len > n) { ok = false; return Cursor(p, 0); }
+    // len is an untrusted 64-bit varint: compare against the bytes LEFT (off <= n always holds), never
+    // form off + len, which wraps for lengths near 2^64 and would pass the check
+    if (!ok || len > (uint64_t)(n - off)) { ok = false; return Cursor(p, 0); }
     Cursor c(p + off, (size_t)len);
     off += (size_t)len;
     return c;
   }
   void skip(int wire) {
     if (wire == VARINT) varint();
-    else if (wire == EIGHT_BYTES) { if (off + 8 > n) ok = false; else off += 8; }
-    else if (wire == FOUR_BYTES) { if (off + 4 > n) ok = false; else off += 4; }
+    else if (wire == EIGHT_BYTES) { if (n - off < 8) ok = false; else off += 8; }
+    else if (wire == FOUR_BYTES) { if (n - off < 4) ok = false; else off += 4; }
     else if (wire == LENGTH_DELIMITED) sub();
     else ok = false;
   }

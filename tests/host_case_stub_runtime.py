@@ -83,6 +83,39 @@ rc["set_fixed_unknown"] = L.slam_b200_graph_set_fixed(ctx.h, 4242, 1)
 rc["last_error_set"] = int(bool(L.slam_b200_last_error(ctx.h)))
 rc["prepare_no_edges"] = L.slam_b200_graph_prepare(ctx.h)
 rc["optimize_nothing_to_do"] = ctx.graph_optimize_rc(3)[0]           # g2o: -1
+# bulk load: a null array with a non-zero count is an argument error, and a load that fails half way (unknown id in
+# the last edge, duplicate vertex id) leaves an EMPTY graph, not one a later optimise would silently run on
+ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+dp = lambda a: a.ctypes.data_as(c_dp)
+pid = np.array([1000, 1001, 1002], dtype=np.int32); pest = np.zeros(9)
+lid = np.array([0, 1], dtype=np.int32); lest = np.ones(4)
+eof = np.array([1000, 1001], dtype=np.int32); eot = np.array([1001, 1002], dtype=np.int32)
+eoz = np.zeros(6); eoi = np.tile(np.eye(3).ravel(), 2)
+elp = np.array([1000, 1001, 1002], dtype=np.int32); ell = np.array([0, 1, 1], dtype=np.int32)
+elz = np.zeros(6); eli = np.tile(np.eye(2).ravel(), 3)
+fx = np.array([1000], dtype=np.int32)
+
+
+def load(pose_ids=pid, eo_z=eoz, el_lm=ell, fixed=fx, null_eo_info=False):
+    return L.slam_b200_graph_load(ctx.h, 3, None if pose_ids is None else ip(pose_ids), dp(pest), 2, ip(lid), dp(lest),
+                                  2, ip(eof), ip(eot), None if eo_z is None else dp(eo_z), None if null_eo_info else dp(eoi),
+                                  3, ip(elp), ip(el_lm), dp(elz), dp(eli), 1, None if fixed is None else ip(fixed))
+
+
+rc["load_ok"] = load()
+nverts = lambda: L.slam_b200_graph_num_poses(ctx.h) + L.slam_b200_graph_num_landmarks(ctx.h)
+rc["load_ok_vertices"] = nverts()
+rc["load_null_pose_ids"] = load(pose_ids=None)
+rc["load_null_eo_z"] = load(eo_z=None)
+rc["load_null_eo_info"] = load(null_eo_info=True)
+rc["load_null_fixed"] = load(fixed=None)
+rc["load_unknown_landmark_in_last_edge"] = load(el_lm=np.array([0, 1, 9], dtype=np.int32))
+rc["vertices_after_failed_load"] = nverts()
+rc["optimize_after_failed_load"] = ctx.graph_optimize_rc(2)[0]        # empty graph: nothing to optimise, -1
+rc["load_duplicate_id"] = load(pose_ids=np.array([1000, 1001, 1001], dtype=np.int32))
+rc["vertices_after_duplicate"] = nverts()
+rc["load_unknown_fixed_id"] = load(fixed=np.array([77], dtype=np.int32))
+rc["vertices_after_unknown_fixed"] = nverts()
 # map + frame staging paths (kernels are no-ops; buffers, growth and copies are real)
 f = synth.cone_field(n_map=5000, n_obs=700, seed=4)
 ctx.map_clear()

@@ -74,6 +74,12 @@ def test_host_code_over_a_stub_runtime(pkg, tmp_path):
     assert rc["add_pose_duplicate"] == rc["edge_unknown_landmark"] == rc["edge_null_pointers"] == rc["set_fixed_unknown"] == E_ARG
     assert rc["last_error_set"] == 1 and rc["optimize_nothing_to_do"] == -1
     assert rc["map_size"] == 5000 and rc["map_roundtrip"] == 1
+    # bulk load: null arrays -> E_ARG (no crash); a load failing half way leaves an empty graph
+    assert rc["load_ok"] == 0 and rc["load_ok_vertices"] == 5
+    assert rc["load_null_pose_ids"] == rc["load_null_eo_z"] == rc["load_null_eo_info"] == rc["load_null_fixed"] == E_ARG
+    assert rc["load_unknown_landmark_in_last_edge"] == rc["load_duplicate_id"] == rc["load_unknown_fixed_id"] == E_ARG
+    assert rc["vertices_after_failed_load"] == rc["vertices_after_duplicate"] == rc["vertices_after_unknown_fixed"] == 0
+    assert rc["optimize_after_failed_load"] == -1
 
 
 def test_host_code_under_sanitizers(tmp_path):
