@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--replicas", type=int, default=4096, help="c3: total Monte-Carlo replicas")
     ap.add_argument("--no-assoc", action="store_true", help="skip the association section of the default run")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the c3 / c5 sections of the default run")
     return ap.parse_args()
 
 
@@ -112,6 +113,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def hold_load(torch, stream, launch, t_start, min_seconds=0.7):
+    """nvidia-smi samples every 100 ms; a timed region of a few milliseconds would carry no clock sample.
+    Keeps launching the SAME step (untimed) until `min_seconds` have passed since t_start, so the sampler
+    window [t_start, now] holds several samples taken under exactly the timed region's load."""
+    while time.time() - t_start < min_seconds:
+        with torch.cuda.stream(stream):
+            launch()
+        stream.synchronize()
+
+
 def dist_setup(n):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,8 +185,9 @@ def timed_steps(torch, stream, flush, steps, body):
     return [a.elapsed_time(b) for a, b in evs]
 
 
-def bench_gn(pkg, torch, args, world, rank, local, graph, R=1, batch=None, label="c2"):
+def bench_gn(pkg, torch, args, world, rank, local, graph, R=1, batch=None, label="c2", steps=None):
     """Resident GN iterations/s (+ profile, roofline, e2e) for one graph topology on this rank."""
+    steps = args.steps if steps is None else steps
     dev = torch.device("cuda", local)
     stream = torch.cuda.Stream(device=dev)
     ctx = pkg.Context(local, stream=stream.cuda_stream)
@@ -204,11 +216,12 @@ def bench_gn(pkg, torch, args, world, rank, local, graph, R=1, batch=None, label
     sampler.start()
     barrier(world)
     tw0 = time.time()
-    ms = timed_steps(torch, stream, flush, args.steps, step)
+    ms = timed_steps(torch, stream, flush, steps, step)
     barrier(world)
+    launches = ctx.launch_count() - l0
+    hold_load(torch, stream, step, tw0)
     tw1 = time.time()
     clocks = sampler.stop(tw0, tw1)
-    launches = ctx.launch_count() - l0
     total_ms = max_over_ranks(float(np.sum(ms)), world, dev)
     # correctness spot check of the timed configuration (not timed): iterations done, chi2
     if batch is None:
@@ -217,9 +230,13 @@ def bench_gn(pkg, torch, args, world, rank, local, graph, R=1, batch=None, label
         chi2_last = float(chi2[-1]) if len(chi2) else None
     else:
         P, L = len(graph.pose_ids), len(graph.lm_ids)
-        _, _, chi2, done = ctx.batch_download(R, P, L, ITERS_PER_STEP)
+        with torch.cuda.stream(stream):   # the hold loop ran further steps; they all end in the same state
+            step()
+        stream.synchronize()
+        bpe, ble, chi2, done = ctx.batch_download(R, P, L, ITERS_PER_STEP)
         done_ok = bool(np.all(done == ITERS_PER_STEP))
         chi2_last = float(np.mean(chi2[:, -1]))
+        batch_out = (bpe, ble, chi2)
     # per-phase profile (separate pass, kernel-by-kernel launches with events in between)
     ctx.profile_enable(True)
     with torch.cuda.stream(stream):
@@ -229,7 +246,8 @@ def bench_gn(pkg, torch, args, world, rank, local, graph, R=1, batch=None, label
     prof = ctx.profile_read()
     ctx.profile_enable(False)
     return dict(ctx=ctx, stream=stream, flush=flush, ms=ms, total_ms=total_ms, launches=launches, clocks=clocks,
-                stats=st, prof=prof, done_ok=done_ok, chi2_last=chi2_last, setup_s=setup_s)
+                stats=st, prof=prof, done_ok=done_ok, chi2_last=chi2_last, setup_s=setup_s, steps=steps,
+                batch_out=batch_out if batch is not None else None)
 
 
 def bench_gn_e2e(pkg, torch, ctx, graph, steps, cold=True):
@@ -374,7 +392,9 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
         roofline={"bound": "hbm", "kernel": "assoc_bulk_grid_kernel", "achieved": roof(tp["ms_per_frame"]),
                   "peak": hbm, "unit": "GB/s", "frac": roof(tp["ms_per_frame"]) / hbm,
                   "frac_single_launch": roof(g["ms_per_frame"]) / hbm, "frac_train_unpipelined": roof(trains["train"]["ms_per_frame"]) / hbm,
-                  "traffic": measured_traffic("c4_assoc_bulk_grid_kernel"), "algorithmic_bytes_per_launch": bytes_alg, "peak_source": how},
+                  "traffic": measured_traffic("c4_assoc_bulk_grid_kernel") if world == 1 else None,
+                  "per_rank_note": None if world == 1 else "algorithmic bytes are the whole frame's / N (this rank's share); the 1-GPU ncu traffic figure does not apply",
+                  "algorithmic_bytes_per_launch": bytes_alg, "peak_source": how},
         brute_force={"assoc_per_s": out["brute"]["assoc_per_s"], "ms_per_frame": out["brute"]["ms_per_frame"],
                      "pair_tests_per_s": float(n) * M / (out["brute"]["ms_per_frame"] * 1e-3) * world,
                      "note": "fp64-issue-bound variant (N*M pair tests), identical indices"},
@@ -485,9 +505,12 @@ def bench_c5(pkg, torch, args, world, rank, local, synth):
     tw0 = time.time()
     ms = timed_steps(torch, stream, flush, args.steps, step)
     barrier(world)
+    launches = ctx.launch_count() - l0
+    # a step lasts a fraction of a millisecond: keep the same load up until nvidia-smi has sampled it (the
+    # hold loop runs the rank-local part only -- a collective inside it would need matching call counts)
+    hold_load(torch, stream, step_local, tw0)
     tw1 = time.time()
     clocks = sampler.stop(tw0, tw1)
-    launches = ctx.launch_count() - l0
     total_ms = max_over_ranks(float(np.sum(ms)), world, dev)
     ms_local = timed_steps(torch, stream, flush, args.steps, step_local)
     local_ms = max_over_ranks(float(np.sum(ms_local)), world, dev) / args.steps
@@ -544,6 +567,70 @@ def bench_c5(pkg, torch, args, world, rank, local, synth):
     return line
 
 
+def bench_c3(pkg, torch, args, world, rank, local, synth, replicas, steps=None):
+    """Config 3: `replicas` Monte-Carlo replicas of the 1-lap trackdrive graph (one topology, one symbolic
+    analysis, replica-major value arrays), sharded replicas/world per GPU, no collective: STRONG scaling.
+    A step = optimize(10) of every replica from the same initial estimates.  parity_in_run: 8 replicas of rank 0's
+    shard re-optimised by the CPU oracle (the checker; not on the timed path)."""
+    steps = max(3, min(args.steps, 10)) if steps is None else steps
+    hbm, how = peaks()
+    g = synth.graph_from_drive(synth.trackdrive(1))
+    R = replicas // world
+    first = rank * R
+    pe0, le0, ez0, oz0 = synth.perturb_replicas(g, R, seed=18, first=first)
+    batch = (pe0, le0, oz0, ez0)   # pose_est, lm_est, eo_z, el_z
+    r = bench_gn(pkg, torch, args, world, rank, local, g, R=R, batch=batch, label="c3", steps=steps)
+    st, prof = r["stats"], r["prof"]
+    nit = max(prof["iterations"], 1)
+    value = world * R * steps * ITERS_PER_STEP / (r["total_ms"] * 1e-3)
+    P, L, Eo, El = len(g.pose_ids), len(g.lm_ids), len(g.eo_from), len(g.el_pose)
+    asm_bytes = R * (88.0 * El + 128.0 * Eo + 8.0 * st["nV"])
+    asm_s = prof["assemble_ms"] / nit * 1e-3
+    fac_s = prof["factor_ms"] / nit * 1e-3
+    fac_bytes = R * 8.0 * (st["nnz_H_upper"] + st["nnz_L"])
+    fac_flops = R * st["factor_flops"]
+    fp64_peak = r["ctx"].fp64_peak_tflops()
+    parity = {"iterations_done_ok": r["done_ok"], "chi2_final_mean": r["chi2_last"]}
+    if rank == 0:
+        import copy
+        from oracle import oracle
+        o = oracle.load("best")
+        bpe, ble, bchi2 = r["batch_out"]
+        dp = dl = dc = 0.0
+        sample = sorted(set(int(q) for q in np.linspace(0, R - 1, 8)))
+        for q in sample:
+            gq = copy.copy(g)
+            gq.pose_est, gq.lm_est, gq.el_z, gq.eo_z = pe0[q], le0[q], ez0[q], oz0[q]
+            G = o.graph_from_soa(gq)
+            _, chi2o = G.optimize(ITERS_PER_STEP)
+            po, lo = G.estimates(gq)
+            dp = max(dp, float(np.max(np.abs(bpe[q] - po)))); dl = max(dl, float(np.max(np.abs(ble[q] - lo))))
+            dc = max(dc, float(np.max(np.abs(bchi2[q] - chi2o) / np.maximum(np.abs(chi2o), 1e-300))))
+        scale = max(1.0, float(np.max(np.abs(bpe[sample]))))
+        parity.update({"replicas_checked_vs_cpu": [first + q for q in sample], "max_abs_pose_diff_vs_cpu": dp,
+                       "max_abs_landmark_diff_vs_cpu": dl, "max_rel_chi2_diff_vs_cpu": dc,
+                       "within_1e-6_relative": bool(dp <= 1e-6 * scale and dl <= 1e-6 * scale)})
+    line = {"metric": "GN iterations/s (fp64), batched Monte-Carlo replicas", "value": value, "unit": "replica GN it/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": r["total_ms"] / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"c3: {replicas} Monte-Carlo replicas of the 1-lap trackdrive graph, {R} per GPU",
+                       "poses": P, "landmarks": L, "unknowns": int(st["n"]), "l2": "working set > L2, flushed anyway"},
+            "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
+            "roofline": {"bound": "hbm", "kernel": "assemble_pose_pipe_kernel + assemble_landmark_kernel",
+                         "achieved": asm_bytes / asm_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": asm_bytes / asm_s / 1e9 / hbm,
+                         "traffic": measured_traffic("c3_assemble_kernels") if world == 1 else None,
+                         "algorithmic_bytes_per_launch": asm_bytes, "peak_source": how},
+            "factor_roofline": {"kernel": "batched front factorisation (all levels of one factorisation, forward solve fused)",
+                                "ms": fac_s * 1e3, "algorithmic_bytes": fac_bytes, "GBps": fac_bytes / fac_s / 1e9,
+                                "frac_of_hbm": fac_bytes / fac_s / 1e9 / hbm, "flops": fac_flops,
+                                "tflops": fac_flops / fac_s / 1e12, "fp64_peak_tflops_measured": fp64_peak,
+                                "frac_of_fp64_peak": fac_flops / fac_s / 1e12 / max(fp64_peak, 1e-9)},
+            "phases_ms_per_iteration": {k: prof[k] / nit for k in ("assemble_ms", "factor_ms", "forward_ms", "backward_ms", "update_ms")},
+            "parity_in_run": parity}
+    r["ctx"].close()
+    return line
+
+
 def cpu_baseline_gn(graph, kind="best"):
     from oracle import oracle
     o = oracle.load(kind)
@@ -555,6 +642,19 @@ def cpu_baseline_gn(graph, kind="best"):
     pe, le = G.estimates(graph)
     return dict(value=n / dt, sec=dt, chi2=chi2, kind=("reference" if o.kind == "reference" else "port"), stats=s,
                 pe=pe, le=le)
+
+
+def c2_config(graph, world):
+    """`config` of the default workload -- the SAME dict on both arms (ours and --impl reference)."""
+    P, L, Eo, El = len(graph.pose_ids), len(graph.lm_ids), len(graph.eo_from), len(graph.el_pose)
+    fixed = set(int(v) for v in graph.fixed_ids)
+    free_p = sum(1 for v in graph.pose_ids if int(v) not in fixed)
+    free_l = sum(1 for v in graph.lm_ids if int(v) not in fixed)
+    return {"workload": "c2: trackdrive x10 laps, single graph", "poses": P, "landmarks": L, "edges_odometry": Eo,
+            "edges_landmark": El, "unknowns": 3 * free_p + 2 * free_l, "gn_iterations_per_step": ITERS_PER_STEP,
+            "multi_gpu": "replicas only (one graph per rank / host thread)" if world > 1 else "single graph",
+            "l2": "GPU arm: flushed between steps (256 MiB write), working set < L2; CPU arm: not applicable",
+            "launch": "GPU arm: one CUDA-graph replay per GN iteration; CPU arm: one optimize(10) call"}
 
 
 def cpu_baseline_assoc(field, n_sample=1500, kind="best"):
@@ -601,11 +701,7 @@ def run_ours(args):
             "metric": "GN iterations/s (fp64) [+ cone assoc/s in 'assoc']", "value": value, "unit": "GN it/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl, "poses": P, "landmarks": L, "edges_odometry": Eo, "edges_landmark": El,
-                       "unknowns": int(st["n"]), "gn_iterations_per_step": ITERS_PER_STEP,
-                       "multi_gpu": "replicas only (one graph per rank)" if world > 1 else "single graph",
-                       "l2": "flushed between steps (256 MiB write); working set < L2",
-                       "launch": "one CUDA-graph replay per GN iteration"},
+            "config": c2_config(graph, world),
             "e2e": {"value": world * ITERS_PER_STEP / e2e["sec_per_step"], "unit": "GN it/s",
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "what": ("graph_load + graph_optimize(10) + get_estimates per step (topology re-analysed)" if e2e_cold
@@ -653,32 +749,21 @@ def run_ours(args):
                 a["cpu_baseline"] = {"value": ca["value"], "unit": "assoc/s", "cores": 1, "kind": "port", "sample": ca["sample"]}
                 a["frame_path"] = bench_frame_assoc(pkg, torch, local, synth.trackdrive(1))
             line["assoc"] = a
+        if args.workload == "c2" and not args.no_sharded:
+            # the configurations that actually shard ride in the default line at EVERY N (N = 1 included, so
+            # the N = 1 line of a scaling run equals the plain bench line): strong scaling, own clocks each
+            def trimmed(full):
+                drop = ("n_gpus", "higher_is_better", "vs_baseline", "dtype", "data", "warmup")
+                return {k: v for k, v in full.items() if k not in drop}
+            line["c3"] = trimmed(bench_c3(pkg, torch, args, world, rank, local, synth, args.replicas))
+            line["c5"] = trimmed(bench_c5(pkg, torch, args, world, rank, local, synth))
+            line["sharded_configs"] = ("'c3' (4,096 Monte-Carlo replicas split over the GPUs) and 'c5' (one 1M-pose graph, "
+                                                 "edges partitioned by pose range, landmark part exchanged) are STRONG-scaling "
+                                                 "measurements at this N; 'assoc' splits the observation batch (strong); the "
+                                                 "headline value is a single small graph, which does not shard: N independent "
+                                                 "copies, not a scaling curve")
     elif args.workload == "c3":
-        g = synth.graph_from_drive(synth.trackdrive(1))
-        R = args.replicas // world
-        first = rank * R
-        batch = synth.perturb_replicas(g, R, seed=18, first=first)
-        batch = (batch[0], batch[1], batch[3], batch[2])   # pose_est, lm_est, eo_z, el_z
-        r = bench_gn(pkg, torch, args, world, rank, local, g, R=R, batch=batch, label="c3")
-        st, prof = r["stats"], r["prof"]
-        nit = max(prof["iterations"], 1)
-        value = world * R * args.steps * ITERS_PER_STEP / (r["total_ms"] * 1e-3)
-        P, L, Eo, El = len(g.pose_ids), len(g.lm_ids), len(g.eo_from), len(g.el_pose)
-        asm_bytes = R * (88.0 * El + 128.0 * Eo + 8.0 * st["nV"])
-        asm_s = prof["assemble_ms"] / nit * 1e-3
-        line = {"metric": "GN iterations/s (fp64), batched Monte-Carlo replicas", "value": value, "unit": "replica GN it/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["total_ms"] / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"c3: {args.replicas} Monte-Carlo replicas of the 1-lap trackdrive graph, {R} per GPU",
-                           "poses": P, "landmarks": L, "unknowns": int(st["n"]), "l2": "working set > L2, flushed anyway"},
-                "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
-                "roofline": {"bound": "hbm", "kernel": "assemble_pose_pipe_kernel + assemble_landmark_kernel",
-                             "achieved": asm_bytes / asm_s / 1e9, "peak": hbm, "unit": "GB/s", "frac": asm_bytes / asm_s / 1e9 / hbm,
-                             "traffic": measured_traffic("c3_assemble_kernels") if world == 1 else None,
-                             "algorithmic_bytes_per_launch": asm_bytes, "peak_source": how},
-                "phases_ms_per_iteration": {k: prof[k] / nit for k in ("assemble_ms", "factor_ms", "forward_ms", "backward_ms", "update_ms")},
-                "parity_in_run": {"iterations_done_ok": r["done_ok"], "chi2_final_mean": r["chi2_last"]}}
-        r["ctx"].close()
+        line = bench_c3(pkg, torch, args, world, rank, local, synth, args.replicas)
     elif args.workload == "c4":
         field = synth.cone_field()
         a = bench_assoc(pkg, torch, args, world, rank, local, field, field.frame.shape[1])
@@ -724,16 +809,17 @@ def run_reference(args):
         dt = time.perf_counter() - t0
         assert all(v == ITERS_PER_STEP for v in out)
         return dt
-    for _ in range(min(args.warmup, 1)):
+    # exactly --warmup / --steps as passed (a step is ~0.4 s of CPU work per replica thread: the default
+    # 20 steps + 3 warm-ups end in about ten seconds)
+    for _ in range(args.warmup):
         one_step()
-    steps = max(1, min(args.steps, 10))   # bounded: ~1 s of CPU work per step
+    steps = max(1, args.steps)
     tot = sum(one_step() for _ in range(steps))
     value = n_threads * steps * ITERS_PER_STEP / tot
     line = {"impl": "reference", "metric": "GN iterations/s (fp64) [+ cone assoc/s in 'assoc']", "value": value,
-            "unit": "GN it/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": tot / steps * 1e3,
+            "unit": "GN it/s", "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": tot / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c2: trackdrive x10 laps, single graph", "gn_iterations_per_step": ITERS_PER_STEP,
-                       "multi_gpu": "replicas only (one graph per host thread)" if world > 1 else "single graph"},
+            "config": c2_config(graph, world),
             "cpu_baseline": {"value": value, "unit": "GN it/s", "cores": n_threads,
                              "kind": "reference" if o.kind == "reference" else "port",
                              "sample": f"{steps} x (initializeOptimization + optimize(10)) on the full workload graph, "

@@ -240,6 +240,12 @@ int slam_b200_profile_read(slam_b200_ctx* ctx, double out[8]);
 int slam_b200_debug_phase_clocks(slam_b200_ctx* ctx, long long out[10]);
 int slam_b200_debug_tiny_clocks(slam_b200_ctx* ctx, long long out[8]);
 int slam_b200_debug_panel_clocks(slam_b200_ctx* ctx, long long out[8]);
+/* Guard-band mode (environment SLAM_B200_GUARD=1 before the first context; tests and debugging): every
+ * device array is allocated with 4 KiB of 0xFF in front of and behind it and is itself filled with 0xFF
+ * (fp64 NaN / int32 -1), so out-of-bounds and uninitialised READS poison the results the parity tests
+ * compare and out-of-bounds WRITES are counted by this call: returns the number of band bytes that
+ * changed over all live arrays of the process (0 = clean), -1 when the mode is off. */
+long slam_b200_debug_guard_check(slam_b200_ctx* ctx, long* n_arrays);
 /* Measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator for the solve). */
 int slam_b200_fp64_peak(slam_b200_ctx* ctx, double* tflops);
 

@@ -347,6 +347,14 @@ class Context:
     def graph_assemble_exchange_async(self, p0, p1):
         self._ck(self.L.slam_b200_graph_assemble_exchange_async(self.h, int(p0), int(p1)), "graph_assemble_exchange_async")
 
+    def debug_guard_check(self):
+        """(band bytes changed, arrays checked); (-1, 0) when SLAM_B200_GUARD is off."""
+        n = C.c_long(0)
+        self.L.slam_b200_debug_guard_check.restype = C.c_long
+        self.L.slam_b200_debug_guard_check.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+        bad = self.L.slam_b200_debug_guard_check(self.h, C.byref(n))
+        return int(bad), int(n.value)
+
     def xchg_set_timeout_ms(self, ms):
         self._ck(self.L.slam_b200_xchg_set_timeout_ms(self.h, float(ms)), "xchg_set_timeout_ms")
 

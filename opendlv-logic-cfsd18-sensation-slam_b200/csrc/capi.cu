@@ -4,9 +4,31 @@
 #include <cmath>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 
 #include "graph_dev.h"
+
+// ---- guard-band mode (ctx.h): registry of live device arrays --------------------------------------
+namespace {
+std::mutex g_guard_mu;
+std::unordered_map<void*, size_t>& guard_tab() {
+  static std::unordered_map<void*, size_t> t;
+  return t;
+}
+}  // namespace
+bool guard_mode() {
+  static const bool on = [] { const char* e = getenv("SLAM_B200_GUARD"); return e && atoi(e) != 0; }();
+  return on;
+}
+void guard_register(void* raw, size_t payload_bytes) {
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  guard_tab()[raw] = payload_bytes;
+}
+void guard_unregister(void* raw) {
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  guard_tab().erase(raw);
+}
 
 int ctx_set_device(slam_b200_ctx* c) {
   cudaError_t e = cudaSetDevice(c->device);
@@ -949,6 +971,31 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 }  // namespace
+
+// Guard-band check (SLAM_B200_GUARD=1): re-reads the 0xFF bands in front of and behind every live device
+// array of this process and counts the bytes that changed.  Returns that count (0 = no out-of-bounds
+// write within 4 KiB of any array), -1 when the mode is off; *n_arrays = arrays checked.
+extern "C" long slam_b200_debug_guard_check(slam_b200_ctx* c, long* n_arrays) try {
+  if (!c) return SLAM_B200_E_ARG;
+  if (!guard_mode()) return -1;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  SLAM_CUDA_TRY(c, cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  std::vector<unsigned char> h(2 * GUARD_BYTES + 256);
+  long bad = 0, n = 0;
+  for (const auto& kv : guard_tab()) {
+    const char* raw = static_cast<const char*>(kv.first);
+    const size_t bytes = kv.second, padded = (bytes + 255) & ~(size_t)255;
+    SLAM_CUDA_TRY(c, cudaMemcpy(h.data(), raw, GUARD_BYTES, cudaMemcpyDeviceToHost));
+    // behind the payload: the alignment padding belongs to the band too
+    const size_t tail = GUARD_BYTES + (padded - bytes);
+    SLAM_CUDA_TRY(c, cudaMemcpy(h.data() + GUARD_BYTES, raw + GUARD_BYTES + bytes, tail, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < GUARD_BYTES + tail; k++) bad += h[k] != 0xFF;
+    n++;
+  }
+  if (n_arrays) *n_arrays = n;
+  return bad;
+} SLAM_ABI_CATCH(c)
 
 extern "C" int slam_b200_fp64_peak(slam_b200_ctx* c, double* tflops) try {
   if (!c || !tflops) return SLAM_B200_E_ARG;

@@ -40,43 +40,82 @@ struct slam_b200_ctx;
 int slam_abi_caught(slam_b200_ctx* c) noexcept;  // capi.cu; call only from inside a catch block
 #define SLAM_ABI_CATCH(ctx) catch (...) { return slam_abi_caught(ctx); }
 
+// ---- guard-band mode (SLAM_B200_GUARD=1; debugging and tests only) ------------------------------------
+// compute-sanitizer is closed on the pool this was developed on, so the library carries its own check:
+// with the variable set, every device array is allocated with GUARD_BYTES of 0xFF in front of and behind
+// the payload and the payload itself is filled with 0xFF as well (as fp64 a NaN, as int32 -1), so
+//  * an out-of-bounds WRITE within the band is caught by slam_b200_debug_guard_check (bands re-read
+//    and compared byte for byte),
+//  * an out-of-bounds or uninitialised READ brings a NaN / -1 into the arithmetic and shows up in the
+//    parity tests (NaN estimates, index -1 faults),
+// while the default build pays one predictable branch per allocation.
+constexpr size_t GUARD_BYTES = 4096;
+bool guard_mode();                                                  // capi.cu
+void guard_register(void* raw, size_t payload_bytes);               // capi.cu
+void guard_unregister(void* raw);                                   // capi.cu
+inline cudaError_t guarded_malloc(void** p, void** raw, size_t bytes) {
+  if (!guard_mode()) {
+    cudaError_t e = cudaMalloc(raw, bytes);
+    *p = *raw;
+    return e;
+  }
+  const size_t padded = (bytes + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc(raw, padded + 2 * GUARD_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaMemset(*raw, 0xFF, padded + 2 * GUARD_BYTES);
+  if (e != cudaSuccess) { cudaFree(*raw); *raw = nullptr; return e; }
+  *p = static_cast<char*>(*raw) + GUARD_BYTES;
+  guard_register(*raw, bytes);
+  return cudaSuccess;
+}
+inline void guarded_free(void* raw) {
+  if (!raw) return;
+  if (guard_mode()) guard_unregister(raw);
+  cudaFree(raw);
+}
+
 // growable device array; grow() keeps the first `keep` elements
 template <class T>
 struct DevBuf {
   T* p = nullptr;
+  void* raw = nullptr;  // what cudaMalloc returned (== p unless guard-band mode is on)
   size_t cap = 0;
   cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
     if (n <= cap) return cudaSuccess;
     size_t ncap = cap ? cap : 256;
     while (ncap < n) ncap *= 2;
-    T* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+    void *q = nullptr, *qraw = nullptr;
+    cudaError_t e = guarded_malloc(&q, &qraw, ncap * sizeof(T));
     if (e != cudaSuccess) return e;
     if (keep && p) {
       e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
       if (e == cudaSuccess) e = cudaStreamSynchronize(s);
       if (e != cudaSuccess) {
-        cudaFree(q);
+        guarded_free(qraw);
         return e;
       }
     }
-    if (p) cudaFree(p);
-    p = q;
+    guarded_free(raw);
+    p = static_cast<T*>(q);
+    raw = qraw;
     cap = ncap;
     return cudaSuccess;
   }
   cudaError_t exact(size_t n) {  // (re)allocate exactly, contents dropped
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    guarded_free(raw);
     p = nullptr;
+    raw = nullptr;
     cap = 0;
-    cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
-    if (e == cudaSuccess) cap = n ? n : 1;
+    void* q = nullptr;
+    cudaError_t e = guarded_malloc(&q, &raw, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) { p = static_cast<T*>(q); cap = n ? n : 1; }
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    guarded_free(raw);
     p = nullptr;
+    raw = nullptr;
     cap = 0;
   }
 };

@@ -29,8 +29,6 @@ def test_conversion_matches_oracle(ctx, orc, c1_drive):
         assert _ulp_close(l[i], lo)
 
 
-@pytest.mark.xfail(strict=False, reason="fixture made after the round's GPU budget was spent: the first hardware run decides; "
-                                        "the same vectors are matched bit for bit by the oracle (test_pinned_by_reference.py)")
 def test_conversion_vectors_from_the_reference_slam_cpp(ctx):
     """tests/golden/conversion_vectors.json (the reference's real transformConeToCoG / Spherical2Cartesian /
     coneToGlobal, make_conversion_golden.py) through slam_b200_cones_to_global: whole azimuth circle incl. 0 -> NaN

@@ -295,8 +295,6 @@ def test_sharded_assembly_partials_sum_to_full(ctx, pkg, synth):
     assert n == 6 * L and lm == ptr
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent (with the host-pool fixes it guards): "
-                                        "the first hardware run decides")
 def test_two_contexts_on_two_host_threads():
     """Two contexts used from two host threads at the same time (own process: tests/gpu_case_two_contexts.py) give
     bit for bit what each gives alone -- the process-wide host pool of the symbolic phase, the structure upload
@@ -312,26 +310,64 @@ def test_two_contexts_on_two_host_threads():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: the first hardware run decides")
-@pytest.mark.parametrize("tool", ["memcheck", "racecheck"])
-def test_kernels_under_compute_sanitizer(tool):
-    """compute-sanitizer memcheck / racecheck over a small end-to-end case (profiles/tools/sanitizer_case.py:
-    association frames, grid and brute-force bulk association, one graph optimisation through the CTA and warp
-    front kernels, a replica batch) in its own process: no invalid access, no shared-memory hazard."""
-    import shutil
+def _run_case(env_extra, prefix=()):
     import subprocess
     import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SLAM_B200_SANITIZER_SMALL="1", **env_extra)
+    return subprocess.run(list(prefix) + [sys.executable, os.path.join(root, "tests", "gpu_case_sanitizer.py")],
+                          capture_output=True, text=True, timeout=420, env=env, cwd=root)
+
+
+@pytest.mark.parametrize("tool", ["memcheck", "racecheck"])
+def test_kernels_under_compute_sanitizer(tool):
+    """compute-sanitizer memcheck / racecheck over a small end-to-end case (tests/gpu_case_sanitizer.py:
+    association frames, grid and brute-force bulk association, one graph optimisation through the CTA and warp
+    front kernels, a replica batch) in its own process: no invalid access, no shared-memory hazard.
+    On the pool this repo is measured on the tool is CLOSED by the operators (it exits 86 with a notice;
+    profiles/r02_compute_sanitizer_closed.log): the test then skips and test_kernels_under_guard_bands /
+    test_case_is_bit_reproducible below are the checks that run."""
+    import shutil
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     cs = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
     if not os.path.exists(cs):
         pytest.skip("compute-sanitizer not installed")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SLAM_B200_SANITIZER_SMALL="1")
-    r = subprocess.run([cs, "--tool", tool, "--error-exitcode", "3", sys.executable,
-                        os.path.join(root, "profiles", "tools", "sanitizer_case.py")],
-                       capture_output=True, text=True, timeout=420, env=env, cwd=root)
+    r = _run_case({}, prefix=(cs, "--tool", tool, "--error-exitcode", "3"))
     out = r.stdout + r.stderr
+    if "closed on this pool" in out:
+        pytest.skip("compute-sanitizer is closed on this pool by its operators: " + out.strip()[:160])
     # --error-exitcode makes any finding a non-zero exit; the banner proves the tool really ran
     assert r.returncode == 0 and "COMPUTE-SANITIZER" in out and "batch" in out, out[-3000:]
+
+
+def _verdict(r):
+    import json
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_kernels_under_guard_bands():
+    """The library's own memory check (SLAM_B200_GUARD=1, csrc/ctx.h): every device array sits between two 4 KiB
+    bands of 0xFF and starts out as 0xFF itself (fp64 NaN / int32 -1).  The case compares every result with the
+    CPU oracle, so an out-of-bounds or uninitialised read poisons a comparison, and at the end no band byte may
+    have changed (no out-of-bounds write)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    v = _verdict(_run_case({"SLAM_B200_GUARD": "1"}))
+    assert v["guard_mode"] and v["arrays_checked"] > 40 and v["guard_bytes_changed"] == 0, v
+
+
+def test_case_is_bit_reproducible():
+    """No atomics on any value path and fixed summation orders: two runs of the case (one of them with the guard
+    bands, i.e. with a different memory layout and NaN-filled fresh allocations) must give bit-identical results --
+    a shared-memory or global-memory race is the only thing that could make them differ."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    a = _verdict(_run_case({}))
+    b = _verdict(_run_case({}))
+    c = _verdict(_run_case({"SLAM_B200_GUARD": "1"}))
+    assert a["hash"] == b["hash"] == c["hash"], (a, b, c)

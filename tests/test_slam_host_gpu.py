@@ -232,8 +232,6 @@ def test_recording_replay_into_slam_equals_direct_calls(host, synth):
     a.close(); b.close()
 
 
-@pytest.mark.xfail(strict=False, reason="fixture made after the round's GPU budget was spent: the first hardware run decides; "
-                                        "the oracle reproduces it identically (test_pinned_by_reference.py)")
 def test_heading_correction_replays_equal_the_reference_slam_cpp(host, synth):
     """performSLAM's heading correction (slam.cpp:309-318) through the drop-in Slam (setYawRate) against the
     reference's real slam.cpp: tests/golden/fuzz_yaw_replay_reference.npz."""
@@ -293,8 +291,6 @@ def test_constructor_and_cone_accessors(host):
 
 
 
-@pytest.mark.xfail(strict=False, reason="opt-in mode written after the round's GPU budget was spent: the first hardware run "
-                                        "decides; its semantics are held by tests/test_localizer_repair.py on the CPU")
 @pytest.mark.parametrize("window", [3, 10])
 def test_localizer_repair_equals_the_oracle(host, window):
     """localiser frames with observation edges + sliding-window optimise through the
@@ -309,8 +305,6 @@ def test_localizer_repair_equals_the_oracle(host, window):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="fixture made after the round's GPU budget was spent: the first hardware run decides; "
-                                        "the oracle reproduces it identically (test_pinned_by_reference.py)")
 def test_gate_replays_equal_the_reference_slam_cpp(host, synth):
     """The drop-in Slam on tests/golden/fuzz_gate_replay_reference.npz (the reference's real slam.cpp): loops that
     partly lie beyond the 200 m gate of performSLAM (frames dropped before a pose is added), odd cone types, zero
