@@ -269,6 +269,9 @@ void* slam_b200_symbolic_create(int nb, const int32_t* dim, int n_pairs, const i
 long slam_b200_symbolic_export(void* handle, int what, int32_t* out, long cap);
 /* what: 0 nnz(L), 1 factor flops, 2 max front, 3 seconds, 4 front storage (doubles) */
 double slam_b200_symbolic_stat(void* handle, int what);
+/* Host plan of the tiled batched factorisation for the analysed pattern (csrc/tileplan.h): 0 = {ok, nf, max_T,
+ * n_items, front storage per replica, nH}, 1 = T, 2 = KT, 3 = fptr, 4 = item_ptr, 5 = item_nv, 6 = items. */
+long slam_b200_symbolic_tileplan(void* handle, int what, int32_t* out, long cap);
 void slam_b200_symbolic_destroy(void* handle);
 
 /* ---- batched Monte-Carlo replicas of the loaded topology (BASELINE config 3) ----------------- */

@@ -20,7 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # per-file extra flags: the association kernels must round products and sums separately, like the
 # reference's x86-64 -O2 build (no FMA contraction), to keep gate decisions bit-exact.
 EXTRA = {"assoc.cu": ["-fmad=false"]}
-SOURCES = ["capi.cu", "graph.cu", "solver.cu", "assoc.cu", "symbolic.cpp"]
+SOURCES = ["capi.cu", "graph.cu", "solver.cu", "assoc.cu", "symbolic.cpp", "tileplan.cpp"]
 HOST_SOURCES = ["host/cone.cpp", "host/slam.cpp", "host/frame_assembler.cpp", "host/wgs84.cpp", "host/rec_reader.cpp", "host/slam_c.cpp"]
 
 

@@ -43,6 +43,8 @@ def lib():
         L.slam_b200_symbolic_create.restype = C.c_void_p
         L.slam_b200_symbolic_export.restype = C.c_long
         L.slam_b200_symbolic_export.argtypes = [C.c_void_p, C.c_int, c_ip, C.c_long]
+        L.slam_b200_symbolic_tileplan.restype = C.c_long
+        L.slam_b200_symbolic_tileplan.argtypes = [C.c_void_p, C.c_int, c_ip, C.c_long]
         L.slam_b200_symbolic_stat.restype = C.c_double
         L.slam_b200_symbolic_stat.argtypes = [C.c_void_p, C.c_int]
         L.slam_b200_symbolic_destroy.argtypes = [C.c_void_p]
@@ -460,5 +462,19 @@ class SymbolicAnalysis:
             ho = hd[-1] + np.concatenate([[0], np.cumsum(dims[a].astype(np.int64) * dims[b])])
             self.hoff_off = ho[:-1]
             self.nH = int(ho[-1])
+            # host plan of the tiled batched factorisation (csrc/tileplan.h)
+
+            def tget(what):
+                n = L.slam_b200_symbolic_tileplan(h, what, None, 0)
+                out = np.zeros(max(n, 1), dtype=np.int32)
+                L.slam_b200_symbolic_tileplan(h, what, _ip(out), n)
+                return out[:n]
+            info = tget(0)
+            self.tile_ok = bool(info[0])
+            if self.tile_ok:
+                self.tile_max_T, self.tile_nF, self.tile_rhs_base = int(info[2]), int(info[4]), int(info[5])
+                self.tile_T, self.tile_KT, self.tile_fptr = tget(1), tget(2), tget(3)
+                self.tile_item_ptr, self.tile_item_nv = tget(4), tget(5)
+                self.tile_items = tget(6).reshape(-1, 2)
         finally:
             L.slam_b200_symbolic_destroy(h)

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "graph_dev.h"
+#include "tileplan.h"
 
 // ---- guard-band mode (ctx.h): registry of live device arrays --------------------------------------
 namespace {
@@ -826,6 +827,42 @@ long slam_b200_symbolic_export(void* h, int what, int32_t* out, long cap) {
   if (!h) return SLAM_B200_E_ARG;
   return export_symbolic(static_cast<SymHandle*>(h)->S, nullptr, what, out, cap);
 }
+// Tile plan of the batched factorisation (tileplan.h) for the analysed pattern, with the rhs of solver scalar k
+// taken to sit at V offset nH + k (nH = number of H values): host logic, checked on the CPU by a numpy emulation of
+// the kernel (tests/mf_emul.py).  what: 0 = {ok, nf, max_T, n_items, nF}, 1 = T, 2 = KT, 3 = fptr, 4 = item_ptr,
+// 5 = item_nv, 6 = items as (src, dst) pairs.
+long slam_b200_symbolic_tileplan(void* h, int what, int32_t* out, long cap) try {
+  if (!h) return SLAM_B200_E_ARG;
+  SymHandle* H = static_cast<SymHandle*>(h);
+  const Symbolic& S = H->S;
+  int nH = 0;
+  for (int b = 0; b < S.nb; b++) nH += S.dim[b] * S.dim[b];
+  {
+    // off-diagonal blocks follow the diagonal ones (slam_b200_symbolic_create lays them out back to back)
+    long last = nH;
+    for (const AsmEntry& e : S.asm_entries) last = std::max(last, (long)e.hoff + (e.meta & 0xff) * ((e.meta >> 8) & 0xff));
+    nH = (int)last;
+  }
+  std::vector<int> solver2v(S.n);
+  for (int k = 0; k < S.n; k++) solver2v[k] = nH + k;
+  TilePlan P;
+  tile_plan_build(S, solver2v, P);
+  std::vector<int> tmp;
+  const std::vector<int>* v = &tmp;
+  switch (what) {
+    case 0: tmp = {P.ok ? 1 : 0, P.nf, P.max_T, (int)P.items.size(), (int)P.nF(), nH}; break;
+    case 1: v = &P.T; break;
+    case 2: v = &P.KT; break;
+    case 3: for (long x : P.fptr) tmp.push_back((int)x); break;
+    case 4: v = &P.item_ptr; break;
+    case 5: v = &P.item_nv; break;
+    case 6: for (const TileItem& it : P.items) { tmp.push_back(it.src); tmp.push_back(it.dst); } break;
+    default: return SLAM_B200_E_ARG;
+  }
+  if (out) std::copy(v->begin(), v->begin() + std::min<long>((long)v->size(), cap), out);
+  return (long)v->size();
+} catch (...) { return SLAM_B200_E_NOMEM; }
+
 double slam_b200_symbolic_stat(void* h, int what) {
   if (!h) return -1;
   const Symbolic& S = static_cast<SymHandle*>(h)->S;

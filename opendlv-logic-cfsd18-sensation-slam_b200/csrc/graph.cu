@@ -18,6 +18,8 @@
 #include <cmath>
 #include <unordered_map>
 
+#include <climits>
+
 #include "graph_dev.h"
 
 namespace {
@@ -1428,6 +1430,44 @@ int graph_build_structure(slam_b200_ctx* c) {
       for (int k = 0; k < 3; k++) solver2v[so + k] = 6 * L + 3 * p + k;
     }
   }
+  // ---- tiled path for replica batches (tileplan.h) ----
+  D.tile_path = false;
+  D.tile = TilePlan();
+  D.tile_launches.clear();
+  std::vector<int> tile_list;
+  std::vector<int2> tile_items_h;
+  if (c->batch_ordering && !c->assembly_only && !getenv("SLAM_B200_NO_TILE_PATH")) {
+    tile_plan_build(S, solver2v, D.tile);
+    if (D.tile.ok && D.nV <= (long)INT32_MAX) {
+      D.tile_path = true;
+      D.nL = D.tile.nF();   // Lv = tile storage of every front (L tiles + Schur-complement tiles)
+      D.nU = 0;
+      D.nUvec = 0;
+      // classes of tile rows: a launch sizes its shared memory for the largest front of its class
+      auto cls_of = [](int T) { return T <= 5 ? 0 : T <= 8 ? T - 5 : T <= 10 ? 4 : 5; };
+      for (int lv = 0; lv < S.nlevels; lv++) {
+        std::vector<int> fr;
+        for (int f = S.level_ptr[lv]; f < S.level_ptr[lv + 1]; f++) fr.push_back(f);
+        std::stable_sort(fr.begin(), fr.end(), [&](int a, int b) { return D.tile.T[a] < D.tile.T[b]; });
+        size_t q = 0;
+        while (q < fr.size()) {
+          TileLaunch TL;
+          TL.level = lv;
+          TL.list_off = (int)tile_list.size();
+          const int cls = cls_of(D.tile.T[fr[q]]);
+          while (q < fr.size() && cls_of(D.tile.T[fr[q]]) == cls) {
+            TL.T = std::max(TL.T, D.tile.T[fr[q]]);
+            tile_list.push_back(fr[q]);
+            TL.count++;
+            q++;
+          }
+          D.tile_launches.push_back(TL);
+        }
+      }
+      tile_items_h.resize(D.tile.items.size());
+      for (size_t k = 0; k < D.tile.items.size(); k++) tile_items_h[k] = make_int2(D.tile.items[k].src, D.tile.items[k].dst);
+    }
+  }
   D.t_lists = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - D.t_structure - S.seconds;
   // ---- upload structure ----
   phase.next("slam_b200/structure upload");
@@ -1473,6 +1513,13 @@ int graph_build_structure(slam_b200_ctx* c) {
   rc |= upload_vec(c, D.ds.frow_ptr, frow_ptr);
   rc |= upload_vec(c, D.ds.gather_ptr, gather_ptr);
   rc |= upload_vec(c, D.ds.gather_src, gather_src);
+  if (D.tile_path) {
+    rc |= upload_vec(c, D.tile_list, tile_list);
+    rc |= upload_vec(c, D.tile_item_ptr, D.tile.item_ptr);
+    rc |= upload_vec(c, D.tile_item_nv, D.tile.item_nv);
+    rc |= upload_vec(c, D.tile_fptr, D.tile.fptr);
+    rc |= upload_vec(c, D.tile_items, tile_items_h);
+  }
   if (rc) { g_uploads.clear(); return SLAM_B200_E_CUDA; }
   if (int frc = flush_uploads(c)) return frc;
   D.structure_version = g.structure_version;
@@ -1584,6 +1631,7 @@ void graph_release(slam_b200_ctx* c) {
   D.ds.asm_ptr.release(); D.ds.solver2v.release(); D.ds.lptr.release(); D.ds.uptr.release();
   D.ds.fbig.release(); D.ds.asm_entries.release(); D.ds.launch_list.release();
   D.ds.frow_ptr.release(); D.ds.gather_ptr.release(); D.ds.gather_src.release();
+  D.tile_list.release(); D.tile_item_ptr.release(); D.tile_item_nv.release(); D.tile_fptr.release(); D.tile_items.release();
   D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
   D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
   D.est0.release(); D.trig.release(); D.dbg_clocks.release(); D.lmo_pose.release(); D.lmo_info.release();

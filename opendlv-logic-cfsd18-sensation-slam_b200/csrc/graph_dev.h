@@ -15,6 +15,7 @@
 // Information matrices, topology, gauge and the symbolic analysis are shared by all replicas.
 #pragma once
 #include "ctx.h"
+#include "tileplan.h"
 
 enum : int { EF_ACTIVE = 1, EF_OFFDIAG = 2, EF_FIRST = 4, EF_TRANS = 8 };
 
@@ -38,6 +39,11 @@ struct LevelLaunch {
   // (<= 40, <= 48, <= 56, <= 64 rows): the warp-per-front kernels are bound by how many fronts fit
   // in an SM's shared memory, so a class must not pay for the largest front of the whole level
   int tiny_cls_n[4] = {0, 0, 0, 0}, tiny_cls_fs[4] = {0, 0, 0, 0};
+};
+
+// Tiled batched factorisation (tileplan.h): one launch per (level, class of tile rows)
+struct TileLaunch {
+  int level = 0, list_off = 0, count = 0, T = 0;  // T = largest number of tile rows in the class
 };
 
 // Peer exchange of the landmark part between pose-range shards (graph.cu: PeerArgs); one per context
@@ -90,6 +96,15 @@ struct DeviceSystem {
   DevBuf<int> eo_i, eo_j, eo_slot, eo_flags, po_start, po_list;
   DevBuf<double> eo_info;          // [6][Eo] SoA
   DevSym ds;
+  // tiled path for replica batches (solver.cu: factor_tile_kernel / backward_tile_kernel): chosen at structure
+  // time when the graph is analysed for a batch and every front has <= TILE_MAX_ROWS local rows.  Lv then holds
+  // the fronts' tile storage (L and Schur-complement tiles together), Uv / uvec are unused.
+  bool tile_path = false;
+  TilePlan tile;
+  std::vector<TileLaunch> tile_launches;   // factor order (levels ascending); the backward sweep walks it in reverse
+  DevBuf<int> tile_list, tile_item_ptr, tile_item_nv;
+  DevBuf<long> tile_fptr;
+  DevBuf<int2> tile_items;
   // device values
   DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part, est0, trig;
   DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done (= chi2 slot)

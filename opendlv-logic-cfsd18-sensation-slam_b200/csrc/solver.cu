@@ -906,6 +906,256 @@ backward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restric
   if (i1 < s) x[p0 + i1] = x1;
 }
 
+// ================================================================================================
+// TILED kernels for replica batches (tileplan.h): one warp per (front, replica); the front is kept as
+// 8 x 8 fp64 tiles in shared memory, the accumulator shape of mma.sync.m8n8k4.f64, so a tile update
+// C -= X L^T is two tensor-pipe instructions instead of 64 predicated DFMA + their loads.  (The fp64 MMA
+// runs at the rate of the DFMA pipe on B200 -- profiles/r02_dmma_lab.log: 36.7 TFLOP/s either way -- the
+// gain is the instruction count: ncu counted 12,000 warp instructions per front for factor_tiny_kernel,
+// 350 of them useful FMAs.)  The four warps of a CTA work on the SAME front of four consecutive
+// replicas: the assembly list is read once from L2 and three times from L1.
+//
+// Per front (local layout and storage: tileplan.h):
+//   zero the tile triangle, 1.0 on the padding pivots; V items are stored, children's items added;
+//   for every pivot tile column K:
+//     (a) every lane factorises the 8 x 8 diagonal tile redundantly in registers (LDL^T, unscaled
+//         right-looking, SimplicialCholesky_impl.h:122-191 restricted to the tile), lane j < 8 then
+//         solves column j of inv(L11) (28 FMA, lane-independent code); W = inv(L11)^T goes to scratch;
+//     (b) for every tile row I below: X = A_IK W (2 MMA; = L_IK D), L_IK = X D^-1 stored in place,
+//         -X to scratch (accumulator layout -> A-operand layout), then C_IJ += (-X) L_JK^T for
+//         K < J <= I (2 MMA per tile).
+//   The rhs row is just a row of the last tile row: it leaves as z = D^-1 L^-1 b under the pivots and as
+//   the update vector under the update columns.  Finally the whole triangle is copied to HBM (unit
+//   stride, 16-byte stores) and z goes to x.
+// ================================================================================================
+constexpr int TILE_WARPS = 4;
+constexpr int TILE_SCRATCH = 64 + 64 + 8;  // W, -X, 1/d (doubles per warp, behind the tile triangle)
+
+struct TileArgs {
+  const int *npiv, *nupd, *piv0, *rows_ptr, *upd_rows, *list, *item_ptr, *item_nv;
+  const long* fptr;
+  const int2* items;
+};
+
+__device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int tile_base(int I, int J) { return (((I * (I + 1)) >> 1) + J) << 6; }
+__device__ __forceinline__ int tile_at(int i, int j) { return tile_base(i >> 3, j >> 3) + ((i & 7) << 3) + (j & 7); }
+
+__global__ void __launch_bounds__(TILE_WARPS * 32, 4)
+factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __restrict__ V_all, long nV,
+                   double* F_all, long nF, int* status, double* x_all, int n) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.y * TILE_WARPS + wid;
+  if (r >= R) return;  // no block-wide barrier below
+  const int f = A.list[list_off + blockIdx.x];
+  const int s = A.npiv[f], u = A.nupd[f];
+  const int sp = (s + 7) & ~7, nloc = sp + u + 1, T = (nloc + 7) >> 3, KT = sp >> 3;
+  const int ntile = (T * (T + 1)) >> 1;
+  double* F = smem + (size_t)wid * slab;
+  double* Wsm = F + (ntile << 6);
+  double* Xs = Wsm + 64;
+  double* dinv = Xs + 64;
+  double2* F2 = reinterpret_cast<double2*>(F);
+  for (int q = lane; q < (ntile << 5); q += 32) F2[q] = make_double2(0.0, 0.0);
+  __syncwarp();
+  if (lane < sp - s) F[tile_at(s + lane, s + lane)] = 1.0;  // padding pivots: identity
+  // ---- assembly ----
+  const double* V = V_all + (size_t)r * nV;
+  double* Fr = F_all + (size_t)r * nF;
+  const int a0 = A.item_ptr[f], a1 = A.item_ptr[f + 1], av = a0 + A.item_nv[f];
+  for (int q0 = a0; q0 < av; q0 += 128) {  // H and b: destinations are distinct over the whole group
+    int2 it[4];
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int q = q0 + 32 * k + lane;
+      it[k] = q < av ? __ldg(A.items + q) : make_int2(-1, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = it[k].x >= 0 ? __ldg(V + it[k].x) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (it[k].x >= 0) F[it[k].y] = v[k];
+  }
+  __syncwarp();
+  for (int q0 = av; q0 < a1; q0 += 128) {  // children: 32 items of one step never share a destination
+    int2 it[4];
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int q = q0 + 32 * k + lane;
+      it[k] = q < a1 ? __ldg(A.items + q) : make_int2(-1, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = it[k].x >= 0 ? Fr[it[k].x] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (it[k].x >= 0) F[it[k].y] += v[k];
+      __syncwarp();
+    }
+  }
+  // ---- factorisation ----
+  const int g = lane >> 2, t = lane & 3;
+  bool bad = false;
+  for (int K = 0; K < KT; K++) {
+    double* Dk = F + tile_base(K, K);
+    double di0, di1, w0, w1;
+    {
+      double Tm[8][8], iv[8];
+#pragma unroll
+      for (int p = 0; p < 8; p++)
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (q >= p) Tm[q][p] = Dk[q * 8 + p];
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        const double d = Tm[p][p];
+        if (d == 0.0 || !isfinite(d)) bad = true;  // SimplicialCholesky_impl.h:175-179
+        iv[p] = __drcp_rn(d);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          if (q > p) {
+            const double lqp = Tm[q][p] * iv[p];
+#pragma unroll
+            for (int q2 = 0; q2 < 8; q2++)
+              if (q2 >= q) Tm[q2][q] -= Tm[q2][p] * lqp;
+            Tm[q][p] = lqp;  // from here on the scaled entry of L
+          }
+        }
+      }
+      __syncwarp();  // every lane has read the tile
+      // final diagonal tile: unit lower L with D on the diagonal (all lanes store the same values)
+#pragma unroll
+      for (int p = 0; p < 8; p++) {
+        dinv[p] = iv[p];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (q > p) Dk[q * 8 + p] = Tm[q][p];
+      }
+      // column (lane & 7) of inv(L11): x = e_j, x_i -= sum_{k<i} l_ik x_k
+      double xi[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) xi[i] = (i == (lane & 7)) ? 1.0 : 0.0;
+#pragma unroll
+      for (int i = 1; i < 8; i++)
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < i) xi[i] -= Tm[i][k] * xi[k];
+      if (lane < 8) {  // W = inv(L11)^T: row j of W = column j of inv(L11)
+#pragma unroll
+        for (int i = 0; i < 8; i++) Wsm[lane * 8 + i] = xi[i];
+      }
+    }
+    __syncwarp();
+    w0 = Wsm[t * 8 + g];
+    w1 = Wsm[(4 + t) * 8 + g];
+    di0 = dinv[2 * t];
+    di1 = dinv[2 * t + 1];
+    for (int I = K + 1; I < T; I++) {
+      double* P = F + tile_base(I, K);
+      const double pa0 = P[g * 8 + t], pa1 = P[g * 8 + 4 + t];
+      double x0 = 0.0, x1 = 0.0;
+      dmma_acc(x0, x1, pa0, w0);
+      dmma_acc(x0, x1, pa1, w1);
+      __syncwarp();  // all lanes hold their A-operand entries before the tile is overwritten
+      *reinterpret_cast<double2*>(P + g * 8 + 2 * t) = make_double2(x0 * di0, x1 * di1);
+      *reinterpret_cast<double2*>(Xs + g * 8 + 2 * t) = make_double2(-x0, -x1);
+      __syncwarp();
+      const double xa0 = Xs[g * 8 + t], xa1 = Xs[g * 8 + 4 + t];
+      const int rowI = tile_base(I, 0);
+#pragma unroll 2
+      for (int J = K + 1; J <= I; J++) {
+        const double* Lj = F + tile_base(J, K);
+        const double b0 = Lj[g * 8 + t], b1 = Lj[g * 8 + 4 + t];
+        double2* C = reinterpret_cast<double2*>(F + rowI + (J << 6) + g * 8 + 2 * t);
+        double2 cv = *C;
+        dmma_acc(cv.x, cv.y, xa0, b0);
+        dmma_acc(cv.x, cv.y, xa1, b1);
+        *C = cv;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  // ---- results: the tile triangle (L, Schur complement, update vector) and z ----
+  double2* G2 = reinterpret_cast<double2*>(Fr + A.fptr[f]);
+  for (int q = lane; q < (ntile << 5); q += 32) G2[q] = F2[q];
+  double* xr = x_all + (size_t)r * n + A.piv0[f];
+  const int rr = sp + u;
+  for (int p = lane; p < s; p += 32) xr[p] = F[tile_at(rr, p)];
+  if (bad && lane == 0) status[2 * r] = 1;
+}
+
+// Backward sweep (L^T x = z, root -> leaves) from the stored L tiles: per pivot tile column the tiles below
+// are read once (16-byte loads, unit stride), multiplied with the already-known x of their rows and reduced
+// over the 8 rows of the accumulator layout by shuffles; the 8 x 8 unit triangle is then solved redundantly.
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__ F_all, long nF, double* x_all, int n) {
+  __shared__ double xs_all[TILE_WARPS][TILE_MAX_ROWS + 8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.y * TILE_WARPS + wid;
+  if (r >= R) return;
+  const int f = A.list[list_off + blockIdx.x];
+  const int s = A.npiv[f], u = A.nupd[f], p0 = A.piv0[f];
+  const int sp = (s + 7) & ~7, nloc = sp + u + 1, T = (nloc + 7) >> 3, KT = sp >> 3;
+  double* xs = xs_all[wid];
+  double* x = x_all + (size_t)r * n;
+  const int* rows = A.upd_rows + A.rows_ptr[f];
+  for (int i = lane; i < (T << 3); i += 32) {
+    double v = 0.0;  // padding pivots, the rhs row and the rows behind it contribute nothing
+    if (i < s) v = x[p0 + i];
+    else if (i >= sp && i < sp + u) v = x[rows[i - sp]];
+    xs[i] = v;
+  }
+  __syncwarp();
+  const double* Fg = F_all + (size_t)r * nF + A.fptr[f];
+  const int g = lane >> 2, t = lane & 3;
+  for (int K = KT - 1; K >= 0; K--) {
+    const double* Dg = Fg + tile_base(K, K);
+    double l[8][8];  // the unit triangle, issued before the tile sweep so the loads overlap it
+#pragma unroll
+    for (int i = 1; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < i) l[i][j] = Dg[i * 8 + j];
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int I = K + 1; I < T; I++) {
+      const double2 lv = *reinterpret_cast<const double2*>(Fg + tile_base(I, K) + g * 8 + 2 * t);
+      const double xi = xs[8 * I + g];
+      acc0 += lv.x * xi;
+      acc1 += lv.y * xi;
+    }
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) {
+      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+    }
+    if (g == 0) {
+      xs[8 * K + 2 * t] -= acc0;
+      xs[8 * K + 2 * t + 1] -= acc1;
+    }
+    __syncwarp();
+    double w[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) w[c] = xs[8 * K + c];
+#pragma unroll
+    for (int i = 7; i >= 1; i--)
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < i) w[j] -= l[i][j] * w[i];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      if (lane == c) xs[8 * K + c] = w[c];
+    __syncwarp();
+  }
+  for (int i = lane; i < s; i += 32) x[p0 + i] = xs[i];
+}
+
 // L panel (fs x s, leading dimension fs) from global into shared memory with leading dimension ld:
 // one warp per column, lanes over rows, up to five independent loads in flight per lane
 __device__ __forceinline__ void stage_panel(double* Ls, const double* __restrict__ Lg, int fs, int s, int ld,
@@ -1097,6 +1347,7 @@ static int solver_init_attrs(slam_b200_ctx* c) {
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     c->solver_attrs_set = true;
   }
   return 0;
@@ -1115,6 +1366,33 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     cudaEventRecord(e, c->stream);
     D.prof_events.push_back(e);
   };
+  if (D.tile_path) {
+    TileArgs TA;
+    TA.npiv = D.ds.npiv.p; TA.nupd = D.ds.nupd.p; TA.piv0 = D.ds.piv0.p; TA.rows_ptr = D.ds.rows_ptr.p;
+    TA.upd_rows = D.ds.upd_rows.p; TA.list = D.tile_list.p; TA.item_ptr = D.tile_item_ptr.p;
+    TA.item_nv = D.tile_item_nv.p; TA.fptr = D.tile_fptr.p; TA.items = D.tile_items.p;
+    const int gy = (D.R + TILE_WARPS - 1) / TILE_WARPS;
+    for (const TileLaunch& TL : D.tile_launches) {
+      const int slab = ((TL.T * (TL.T + 1)) / 2) * 64 + TILE_SCRATCH;
+      dim3 grid(TL.count, gy);
+      factor_tile_kernel<<<grid, TILE_WARPS * 32, (size_t)TILE_WARPS * slab * sizeof(double), c->stream>>>(
+          TA, TL.list_off, D.R, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n);
+      c->launches++;
+    }
+    mark();  // factored
+    mark();  // forward (fused)
+    for (int k = (int)D.tile_launches.size() - 1; k >= 0; k--) {
+      const TileLaunch& TL = D.tile_launches[k];
+      dim3 grid(TL.count, gy);
+      backward_tile_kernel<<<grid, TILE_WARPS * 32, 0, c->stream>>>(TA, TL.list_off, D.R, D.Lv.p, D.nL, D.x.p, D.n);
+      c->launches++;
+    }
+    SLAM_CUDA_TRY(c, cudaGetLastError());
+    mark();  // backward done
+    int rc = graph_enqueue_update(c);
+    mark();  // updated
+    return rc;
+  }
   // SLAM_B200_FACTOR_VARIANT=1 selects the first-generation CTA-per-front kernel (A/B measurements)
   static const bool gen2 = !(getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 1);
   static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
@@ -1282,7 +1560,8 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
       // count the kernel nodes once: bookkeeping for slam_b200_launch_count
       // (assemble 2 + per level factor/forward/backward + update)
       int n = 2 + 1;
-      for (const LevelLaunch& LL : D.levels) {
+      if (D.tile_path) n += 2 * (int)D.tile_launches.size();
+      else for (const LevelLaunch& LL : D.levels) {
         int ntiny = LL.n_tiny ? 1 : 0;
         if (LL.n_tiny && warp_kernels(c, D, LL)) {
           ntiny = 0;

@@ -16,7 +16,7 @@ if [ "$MODE" = tsan ]; then
 else
   SAN="-Xcompiler -fsanitize=address -Xcompiler -fsanitize=undefined -Xcompiler -fno-sanitize-recover=undefined"
 fi
-for f in capi.cu graph.cu solver.cu assoc.cu symbolic.cpp; do
+for f in capi.cu graph.cu solver.cu assoc.cu symbolic.cpp tileplan.cpp; do
   extra=""; [ "$f" = assoc.cu ] && extra="-fmad=false"
   nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -Xcompiler -fPIC $SAN $extra -c "$S/$f" -o "$OUT/$f.o" &
 done

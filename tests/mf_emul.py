@@ -110,3 +110,83 @@ def solver_perm(sym, dims):
         for k in range(dims[b]):
             perm[sym.boff[b] + k] = off[b] + k
     return perm
+
+
+# ------------------------------------------------------------------------------------------------
+# Tiled batched factorisation (csrc/tileplan.h, solver.cu: factor_tile_kernel / backward_tile_kernel)
+# ------------------------------------------------------------------------------------------------
+def _tile_off(i, j):
+    I, J = i >> 3, j >> 3
+    return ((I * (I + 1)) // 2 + J) * 64 + (i & 7) * 8 + (j & 7)
+
+
+def tile_factor_solve(sym, hv, b_solver):
+    """Emulates, front by front, exactly what one warp of the tiled kernels does with the host plan: zero the tile
+    storage, identity on the padding pivots, add the plan's items (first from V = [H values | rhs], then from the
+    children's stored fronts), eliminate the KT pivot tile columns of the augmented front (rhs = last local row),
+    store the whole tile triangle, read z from the rhs row; then the backward sweep from the stored L tiles."""
+    assert sym.tile_ok
+    V = np.concatenate([hv, np.zeros(max(0, sym.tile_rhs_base - len(hv))), b_solver])
+    Fv = np.zeros(sym.tile_nF)
+    x = np.zeros(sym.n)
+    nf = sym.nf
+
+    def dense_from_tiles(st, nloc):
+        A = np.zeros((nloc, nloc))
+        for i in range(nloc):
+            for j in range(i + 1):
+                A[i, j] = st[_tile_off(i, j)]
+        return A
+
+    for f in range(nf):
+        s, u = int(sym.npiv[f]), int(sym.nupd[f])
+        sp = (s + 7) & ~7
+        nloc = sp + u + 1
+        T, KT = int(sym.tile_T[f]), int(sym.tile_KT[f])
+        assert T == (nloc + 7) // 8 and KT == sp // 8
+        ntile = T * (T + 1) // 2
+        st = np.zeros(ntile * 64)
+        for p in range(s, sp):
+            st[_tile_off(p, p)] = 1.0
+        a0, a1, nv = int(sym.tile_item_ptr[f]), int(sym.tile_item_ptr[f + 1]), int(sym.tile_item_nv[f])
+        assert nv % 32 == 0 and (a1 - a0) % 32 == 0
+        for g0 in range(a0, a1, 32):   # one warp step: 32 items, destinations must be distinct
+            grp = sym.tile_items[g0:g0 + 32]
+            live = grp[grp[:, 0] >= 0]
+            assert len(set(live[:, 1].tolist())) == len(live), "two items of one warp step share a destination"
+            src = V if g0 < a0 + nv else Fv
+            for sidx, d in live:
+                assert 0 <= d < ntile * 64
+                st[d] += src[sidx]
+        A = dense_from_tiles(st, nloc)           # lower triangle of the augmented local front
+        for k in range(sp):                       # pivot columns (padding pivots: d = 1, column 0)
+            d = A[k, k]
+            col = A[k + 1:, k].copy()
+            A[k + 1:, k + 1:] -= np.tril(np.outer(col, col / d))
+            A[k + 1:, k] = col / d                # scaled: unit lower L, D stays on the diagonal
+        for i in range(nloc):
+            for j in range(i + 1):
+                st[_tile_off(i, j)] = A[i, j]
+        Fv[sym.tile_fptr[f]:sym.tile_fptr[f] + ntile * 64] = st
+        p0 = int(sym.piv0[f])
+        x[p0:p0 + s] = A[sp + u, :s]              # z = D^-1 L^-1 b sits in the rhs row
+    for f in range(nf - 1, -1, -1):
+        s, u = int(sym.npiv[f]), int(sym.nupd[f])
+        sp = (s + 7) & ~7
+        nloc = sp + u + 1
+        st = Fv[sym.tile_fptr[f]:]
+        p0 = int(sym.piv0[f])
+        rows = sym.upd_rows[sym.rows_ptr[f]:sym.rows_ptr[f + 1]]
+        xs = np.zeros(nloc)
+        xs[:s] = x[p0:p0 + s]
+        xs[sp:sp + u] = x[rows]
+        Lm = dense_from_tiles(st, nloc)
+        for K in range(sp // 8 - 1, -1, -1):
+            k0 = 8 * K
+            w = xs[k0:k0 + 8] - Lm[k0 + 8:, k0:k0 + 8].T @ xs[k0 + 8:]   # xs[rhs row] = 0: the z row drops out
+            for i in range(7, -1, -1):
+                for j in range(i):
+                    w[j] -= Lm[k0 + i, k0 + j] * w[i]
+            xs[k0:k0 + 8] = w
+        x[p0:p0 + s] = xs[:s]
+    return x

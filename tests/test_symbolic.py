@@ -157,3 +157,40 @@ def test_symbolic_phase_under_sanitizers(pkg, tmp_path, san):
     r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=240, env=env)
     skip_if_sanitizer_runtime_unusable(r.stdout + r.stderr)
     assert r.returncode == 0 and r.stdout.strip() == "ok 0", r.stdout[-500:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n_poses,leaf", [(150, 1024), (60, 8), (400, 1024), (1000, 1024), (1000, 64)])
+def test_tile_plan_solves(pkg, synth, orc, n_poses, leaf):
+    """Host plan of the tiled batched factorisation (csrc/tileplan.cpp): local layout with identity padding and the
+    rhs as an extra row, tile-major storage, assembly items from V and from the children's stored fronts -- run through
+    the numpy emulation of what one warp of factor_tile_kernel / backward_tile_kernel does, it must solve H x = b."""
+    g = small_graph(synth, n_poses)
+    ids, dims, pa, pb = mf_emul.block_pattern(g)
+    sym = pkg.SymbolicAnalysis(dims, pa, pb, leaf_size=leaf)
+    if not sym.tile_ok:
+        pytest.skip("a front of this ordering exceeds 96 local rows")
+    G = orc.graph_from_soa(g)
+    sysm = G.build_system()
+    n = sysm["n"]
+    U = sp.csc_matrix((sysm["Ax"], sysm["Ai"], sysm["Ap"]), shape=(n, n))
+    H = (U + sp.triu(U, 1).T).toarray()
+    hv = mf_emul.hvals_from_dense(H, dims, pa, pb, sym)
+    assert sym.tile_rhs_base == len(hv)
+    perm = mf_emul.solver_perm(sym, dims)
+    x_solver = mf_emul.tile_factor_solve(sym, hv, sysm["b"][perm])
+    x = np.zeros(n)
+    x[perm] = x_solver
+    x_ref = spla.spsolve(sp.csc_matrix(H), sysm["b"])
+    assert np.max(np.abs(x - x_ref)) <= 1e-9 * np.max(np.abs(x_ref))
+    # the same answer as the general front schedule
+    x_gen = np.zeros(n)
+    x_gen[perm] = mf_emul.factor_solve(sym, hv, sysm["b"][perm])
+    assert np.max(np.abs(x - x_gen)) <= 1e-9 * np.max(np.abs(x_ref))
+
+
+def test_tile_plan_c1(pkg, synth, c1_graph):
+    """Config 3's topology (the 1-lap graph, batch ordering) must be a tiled topology, with fronts of <= 64 local rows."""
+    ids, dims, pa, pb = mf_emul.block_pattern(c1_graph)
+    sym = pkg.SymbolicAnalysis(dims, pa, pb, leaf_size=1024)
+    assert sym.tile_ok and sym.tile_max_T <= 8
+    assert np.all(sym.tile_item_nv % 32 == 0) and np.all(np.diff(sym.tile_item_ptr) % 32 == 0)
