@@ -120,6 +120,7 @@ struct DeviceSystem {
   // ~40 dependent small launches replayed with one host call per iteration
   cudaGraphExec_t iter_graph = nullptr;
   int launches_per_iter = 0;
+  long launches_captured = 0;  // kernel launches counted while the iteration was captured
   void drop_graph() {
     if (iter_graph) cudaGraphExecDestroy(iter_graph);
     iter_graph = nullptr;

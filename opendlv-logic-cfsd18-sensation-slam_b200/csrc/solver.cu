@@ -928,11 +928,10 @@ backward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restric
 //   the update vector under the update columns.  Finally the whole triangle is copied to HBM (unit
 //   stride, 16-byte stores) and z goes to x.
 // ================================================================================================
-constexpr int TILE_WARPS = 4;
-constexpr int TILE_SCRATCH = 64 + 64 + 8;  // W, -X, 1/d (doubles per warp, behind the tile triangle)
+constexpr int TILE_SCRATCH = 0;  // nothing behind the tile triangle any more
 
 struct TileArgs {
-  const int *npiv, *nupd, *piv0, *rows_ptr, *upd_rows, *list, *item_ptr, *item_nv;
+  const int *npiv, *nupd, *piv0, *rows_ptr, *upd_rows, *list, *item_ptr, *item_nv, *child_ptr, *children;
   const long* fptr;
   const int2* items;
 };
@@ -942,140 +941,195 @@ __device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, doubl
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ int tile_base(int I, int J) { return (((I * (I + 1)) >> 1) + J) << 6; }
-__device__ __forceinline__ int tile_at(int i, int j) { return tile_base(i >> 3, j >> 3) + ((i & 7) << 3) + (j & 7); }
+// element (i, j) of the tile triangle; rows 2, 3, 6, 7 of a tile keep their 4-column halves swapped (tileplan.h)
+__device__ __forceinline__ int tile_in(int gi, int cj) { return (gi << 3) + (cj ^ ((gi & 2) << 1)); }
+__device__ __forceinline__ int tile_at(int i, int j) { return tile_base(i >> 3, j >> 3) + tile_in(i & 7, j & 7); }
 
-__global__ void __launch_bounds__(TILE_WARPS * 32, 4)
-factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __restrict__ V_all, long nV,
-                   double* F_all, long nF, int* status, double* x_all, int n) {
+// 1/d to within an ulp or two: hardware seed (about 20 bits) + two Newton steps.  __drcp_rn is correctly rounded
+// but costs 35 instructions (ncu: 19 % of the kernel's instructions sat on that line); the result is compared with
+// the CPU at 1e-6, not bit for bit.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
+// zero / denormal / inf / nan pivot (SimplicialCholesky_impl.h:175-179 fails on an exactly zero pivot)
+__device__ __forceinline__ bool bad_pivot(double d) {
+  return (unsigned)((__double2hiint(d) >> 20) & 0x7ff) - 1u >= 0x7feu;
+}
+
+// LDL^T of one 8 x 8 tile held in the accumulator layout of the warp (lane (g, t): entries (g, 2t), (g, 2t+1)),
+// in place and WITHOUT redundancy: step p fetches the four entries of column p a lane needs (its row, the pivot,
+// the rows of its two columns) by shuffle.  Afterwards the lane holds the unit-lower L (d on the diagonal, whatever
+// the symmetric updates left above it) and 1/d of its two columns.  (The first version factorised the tile
+// redundantly in the registers of every lane: two thirds of the kernel's instructions.)
+__device__ __forceinline__ bool tile_ldlt(double& a0, double& a1, double& di0, double& di1, int g, int t) {
+  bool bad = false;
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int hp = p >> 1;
+    const double v = (p & 1) ? a1 : a0;
+    const double rgp = __shfl_sync(0xffffffffu, v, g * 4 + hp);      // T[g][p]
+    const double dp = __shfl_sync(0xffffffffu, v, p * 4 + hp);       // T[p][p]
+    const double c0 = __shfl_sync(0xffffffffu, v, 8 * t + hp);       // T[2t][p]
+    const double c1 = __shfl_sync(0xffffffffu, v, 8 * t + 4 + hp);   // T[2t+1][p]
+    bad |= bad_pivot(dp);
+    const double inv = fast_rcp(dp);
+    const double lgp = rgp * inv;
+    if (2 * t > p) a0 -= lgp * c0;
+    if (2 * t + 1 > p) a1 -= lgp * c1;
+    if (t == hp) {
+      if (p & 1) { di1 = inv; if (g > p) a1 = lgp; }
+      else { di0 = inv; if (g > p) a0 = lgp; }
+    }
+  }
+  return bad;
+}
+
+__global__ void __launch_bounds__(128)
+factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __restrict__ V_all, long nV, double* F_all,
+                   long nF, int* status, double* x_all, int n) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int r = blockIdx.y * TILE_WARPS + wid;
+  // consecutive warps / CTAs = consecutive replicas of ONE front: its item list stays in L1
+  const int r = blockIdx.x * (blockDim.x >> 5) + wid;
   if (r >= R) return;  // no block-wide barrier below
-  const int f = A.list[list_off + blockIdx.x];
+  const int f = A.list[list_off + blockIdx.y];
   const int s = A.npiv[f], u = A.nupd[f];
   const int sp = (s + 7) & ~7, nloc = sp + u + 1, T = (nloc + 7) >> 3, KT = sp >> 3;
   const int ntile = (T * (T + 1)) >> 1;
   double* F = smem + (size_t)wid * slab;
-  double* Wsm = F + (ntile << 6);
-  double* Xs = Wsm + 64;
-  double* dinv = Xs + 64;
   double2* F2 = reinterpret_cast<double2*>(F);
+  const double* V = V_all + (size_t)r * nV;
+  double* Fr = F_all + (size_t)r * nF;
+  // The assembly below is a chain item -> value -> add; the children's Schur complements were written by the
+  // previous launches and sit in HBM.  Ask for their tile rows (rows >= the child's KT are contiguous) now, so
+  // that they are on their way to L2 while the front is zeroed and the H entries are placed.
+  for (int ci = A.child_ptr[f]; ci < A.child_ptr[f + 1]; ci++) {
+    const int ch = A.children[ci];
+    const int spc = (A.npiv[ch] + 7) & ~7, KTc = spc >> 3;
+    const double* base = Fr + A.fptr[ch];
+    const long lo = tile_base(KTc, 0), hi = A.fptr[ch + 1] - A.fptr[ch];
+    for (long o = lo + 16 * lane; o < hi; o += 16 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+  }
+  // ---- assembly: 8 items per lane in flight; the index pairs of the next batch are requested before the
+  // values of the current one are used ----
+  const int a0 = A.item_ptr[f], a1 = A.item_ptr[f + 1], av = a0 + A.item_nv[f];
+  constexpr int IB = 8;
+  int2 it[IB];
+#pragma unroll
+  for (int k = 0; k < IB; k++) {
+    const int q = a0 + 32 * k + lane;
+    it[k] = q < av ? __ldg(A.items + q) : make_int2(-1, 0);
+  }
   for (int q = lane; q < (ntile << 5); q += 32) F2[q] = make_double2(0.0, 0.0);
   __syncwarp();
   if (lane < sp - s) F[tile_at(s + lane, s + lane)] = 1.0;  // padding pivots: identity
-  // ---- assembly ----
-  const double* V = V_all + (size_t)r * nV;
-  double* Fr = F_all + (size_t)r * nF;
-  const int a0 = A.item_ptr[f], a1 = A.item_ptr[f + 1], av = a0 + A.item_nv[f];
-  for (int q0 = a0; q0 < av; q0 += 128) {  // H and b: destinations are distinct over the whole group
-    int2 it[4];
-    double v[4];
+  for (int q0 = a0; q0 < av; q0 += 32 * IB) {  // H and b: destinations are distinct over the whole group
+    double v[IB];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int q = q0 + 32 * k + lane;
-      it[k] = q < av ? __ldg(A.items + q) : make_int2(-1, 0);
+    for (int k = 0; k < IB; k++) v[k] = it[k].x >= 0 ? __ldg(V + it[k].x) : 0.0;
+    int2 nx[IB];
+#pragma unroll
+    for (int k = 0; k < IB; k++) {
+      const int q = q0 + 32 * IB + 32 * k + lane;
+      nx[k] = q < av ? __ldg(A.items + q) : make_int2(-1, 0);
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = it[k].x >= 0 ? __ldg(V + it[k].x) : 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < IB; k++)
       if (it[k].x >= 0) F[it[k].y] = v[k];
+#pragma unroll
+    for (int k = 0; k < IB; k++) it[k] = nx[k];
+  }
+#pragma unroll
+  for (int k = 0; k < IB; k++) {
+    const int q = av + 32 * k + lane;
+    it[k] = q < a1 ? __ldg(A.items + q) : make_int2(-1, 0);
   }
   __syncwarp();
-  for (int q0 = av; q0 < a1; q0 += 128) {  // children: 32 items of one step never share a destination
-    int2 it[4];
-    double v[4];
+  for (int q0 = av; q0 < a1; q0 += 32 * IB) {  // children: the 32 items of one step never share a destination
+    double v[IB];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int q = q0 + 32 * k + lane;
-      it[k] = q < a1 ? __ldg(A.items + q) : make_int2(-1, 0);
+    for (int k = 0; k < IB; k++) v[k] = it[k].x >= 0 ? Fr[it[k].x] : 0.0;
+    int2 nx[IB];
+#pragma unroll
+    for (int k = 0; k < IB; k++) {
+      const int q = q0 + 32 * IB + 32 * k + lane;
+      nx[k] = q < a1 ? __ldg(A.items + q) : make_int2(-1, 0);
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = it[k].x >= 0 ? Fr[it[k].x] : 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < IB; k++) {
       if (it[k].x >= 0) F[it[k].y] += v[k];
       __syncwarp();
     }
+#pragma unroll
+    for (int k = 0; k < IB; k++) it[k] = nx[k];
   }
   // ---- factorisation ----
   const int g = lane >> 2, t = lane & 3;
+  const int sw = (g & 2) << 1;            // column-half swap of this lane's row (tileplan.h)
+  const int cl = g * 8 + ((2 * t) ^ sw);  // this lane's two entries of a tile (accumulator layout)
+  const int al0 = g * 8 + (t ^ sw);       // its entry of the first k-half as A / B operand: column t ...
+  const int al1 = g * 8 + ((4 + t) ^ sw); // ... and of the second: column 4 + t
   bool bad = false;
   for (int K = 0; K < KT; K++) {
     double* Dk = F + tile_base(K, K);
-    double di0, di1, w0, w1;
+    double di0 = 1.0, di1 = 1.0, w0, w1, nd0, nd1;
     {
-      double Tm[8][8], iv[8];
+      double2 dv = *reinterpret_cast<double2*>(Dk + cl);
+      bad |= tile_ldlt(dv.x, dv.y, di0, di1, g, t);
+      __syncwarp();
+      *reinterpret_cast<double2*>(Dk + cl) = dv;  // final: unit lower L, D on the diagonal
+      __syncwarp();
+      // row g of inv(L11): x_j = [j == g] - sum_{k > j} x_k l_kj, j descending (x_k = 0 for k > g by itself)
+      double x[8];
 #pragma unroll
-      for (int p = 0; p < 8; p++)
+      for (int j = 7; j >= 0; j--) {
+        double acc = (j == g) ? 1.0 : 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-          if (q >= p) Tm[q][p] = Dk[q * 8 + p];
-#pragma unroll
-      for (int p = 0; p < 8; p++) {
-        const double d = Tm[p][p];
-        if (d == 0.0 || !isfinite(d)) bad = true;  // SimplicialCholesky_impl.h:175-179
-        iv[p] = __drcp_rn(d);
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-          if (q > p) {
-            const double lqp = Tm[q][p] * iv[p];
-#pragma unroll
-            for (int q2 = 0; q2 < 8; q2++)
-              if (q2 >= q) Tm[q2][q] -= Tm[q2][p] * lqp;
-            Tm[q][p] = lqp;  // from here on the scaled entry of L
-          }
-        }
+        for (int k = 7; k > j; k--) acc -= x[k] * Dk[tile_in(k, j)];
+        x[j] = acc;
       }
-      __syncwarp();  // every lane has read the tile
-      // final diagonal tile: unit lower L with D on the diagonal (all lanes store the same values)
-#pragma unroll
-      for (int p = 0; p < 8; p++) {
-        dinv[p] = iv[p];
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-          if (q > p) Dk[q * 8 + p] = Tm[q][p];
-      }
-      // column (lane & 7) of inv(L11): x = e_j, x_i -= sum_{k<i} l_ik x_k
-      double xi[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) xi[i] = (i == (lane & 7)) ? 1.0 : 0.0;
-#pragma unroll
-      for (int i = 1; i < 8; i++)
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-          if (k < i) xi[i] -= Tm[i][k] * xi[k];
-      if (lane < 8) {  // W = inv(L11)^T: row j of W = column j of inv(L11)
-#pragma unroll
-        for (int i = 0; i < 8; i++) Wsm[lane * 8 + i] = xi[i];
-      }
+      // B operand of X = A W, W = inv(L11)^T: W[t][g] = inv(L11)[g][t], W[4+t][g] = inv(L11)[g][4+t]
+      w0 = t == 0 ? x[0] : t == 1 ? x[1] : t == 2 ? x[2] : x[3];
+      w1 = t == 0 ? x[4] : t == 1 ? x[5] : t == 2 ? x[6] : x[7];
+      // -d of the columns t and 4 + t: turns a stored L entry back into the (negated) entry of X = L D
+      nd0 = -Dk[tile_in(t, t)];
+      nd1 = -Dk[tile_in(4 + t, 4 + t)];
     }
-    __syncwarp();
-    w0 = Wsm[t * 8 + g];
-    w1 = Wsm[(4 + t) * 8 + g];
-    di0 = dinv[2 * t];
-    di1 = dinv[2 * t + 1];
     for (int I = K + 1; I < T; I++) {
       double* P = F + tile_base(I, K);
-      const double pa0 = P[g * 8 + t], pa1 = P[g * 8 + 4 + t];
+      const double pa0 = P[al0], pa1 = P[al1];
       double x0 = 0.0, x1 = 0.0;
-      dmma_acc(x0, x1, pa0, w0);
+      dmma_acc(x0, x1, pa0, w0);  // X = A_IK W = L_IK D
       dmma_acc(x0, x1, pa1, w1);
       __syncwarp();  // all lanes hold their A-operand entries before the tile is overwritten
-      *reinterpret_cast<double2*>(P + g * 8 + 2 * t) = make_double2(x0 * di0, x1 * di1);
-      *reinterpret_cast<double2*>(Xs + g * 8 + 2 * t) = make_double2(-x0, -x1);
+      *reinterpret_cast<double2*>(P + cl) = make_double2(x0 * di0, x1 * di1);  // L_IK, final
       __syncwarp();
-      const double xa0 = Xs[g * 8 + t], xa1 = Xs[g * 8 + 4 + t];
+      const double xa0 = P[al0] * nd0, xa1 = P[al1] * nd1;  // -X in A-operand layout
       const int rowI = tile_base(I, 0);
-#pragma unroll 2
-      for (int J = K + 1; J <= I; J++) {
-        const double* Lj = F + tile_base(J, K);
-        const double b0 = Lj[g * 8 + t], b1 = Lj[g * 8 + 4 + t];
-        double2* C = reinterpret_cast<double2*>(F + rowI + (J << 6) + g * 8 + 2 * t);
-        double2 cv = *C;
-        dmma_acc(cv.x, cv.y, xa0, b0);
-        dmma_acc(cv.x, cv.y, xa1, b1);
-        *C = cv;
+      for (int J0 = K + 1; J0 <= I; J0 += 4) {  // C_IJ -= X L_JK^T, four tiles in flight
+        double b0[4], b1[4];
+        double2 cv[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int J = min(J0 + q, I);
+          const double* Lj = F + tile_base(J, K);
+          b0[q] = Lj[al0];
+          b1[q] = Lj[al1];
+          cv[q] = *reinterpret_cast<const double2*>(F + rowI + (J << 6) + cl);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          dmma_acc(cv[q].x, cv[q].y, xa0, b0[q]);
+          dmma_acc(cv[q].x, cv[q].y, xa1, b1[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (J0 + q <= I) *reinterpret_cast<double2*>(F + rowI + ((J0 + q) << 6) + cl) = cv[q];
       }
       __syncwarp();
     }
@@ -1090,21 +1144,39 @@ factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __re
   if (bad && lane == 0) status[2 * r] = 1;
 }
 
-// Backward sweep (L^T x = z, root -> leaves) from the stored L tiles: per pivot tile column the tiles below
-// are read once (16-byte loads, unit stride), multiplied with the already-known x of their rows and reduced
-// over the 8 rows of the accumulator layout by shuffles; the 8 x 8 unit triangle is then solved redundantly.
-__global__ void __launch_bounds__(TILE_WARPS * 32)
+// Backward sweep (L^T x = z, root -> leaves) from the stored L tiles: per pivot tile column all tiles below
+// and the diagonal tile are requested at once (16-byte loads, unit stride), multiplied with the already-known
+// x of their rows and reduced over the 8 rows of the accumulator layout by shuffles; the 8 x 8 unit triangle
+// goes through shared memory and is solved redundantly by every lane.
+constexpr int TILE_MAX_T = TILE_MAX_ROWS / 8;
+
+constexpr int BACK_SLAB = TILE_MAX_ROWS + 8 + 64;  // x of the front's rows + the current unit triangle, per warp
+
+__global__ void __launch_bounds__(128)
 backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__ F_all, long nF, double* x_all, int n) {
-  __shared__ double xs_all[TILE_WARPS][TILE_MAX_ROWS + 8];
+  extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int r = blockIdx.y * TILE_WARPS + wid;
+  const int r = blockIdx.x * (blockDim.x >> 5) + wid;
   if (r >= R) return;
-  const int f = A.list[list_off + blockIdx.x];
+  const int f = A.list[list_off + blockIdx.y];
+  double* tri = smem + (size_t)wid * BACK_SLAB;  // 64 doubles, 16-byte aligned (BACK_SLAB is even)
+  double* xs = tri + 64;
   const int s = A.npiv[f], u = A.nupd[f], p0 = A.piv0[f];
   const int sp = (s + 7) & ~7, nloc = sp + u + 1, T = (nloc + 7) >> 3, KT = sp >> 3;
-  double* xs = xs_all[wid];
   double* x = x_all + (size_t)r * n;
   const int* rows = A.upd_rows + A.rows_ptr[f];
+  const double* Fg = F_all + (size_t)r * nF + A.fptr[f];
+  const int g = lane >> 2, t = lane & 3;
+  const int cl = g * 8 + ((2 * t) ^ ((g & 2) << 1));  // this lane's two entries of a tile (accumulator layout, tileplan.h)
+  // the last pivot column's tiles do not depend on x: request them before the gather of x
+  double2 lv[TILE_MAX_T - 1], dg;
+  {
+    const int K = KT - 1;
+    dg = *reinterpret_cast<const double2*>(Fg + tile_base(K, K) + cl);
+#pragma unroll
+    for (int d = 0; d < TILE_MAX_T - 1; d++)
+      if (K + 1 + d < T) lv[d] = *reinterpret_cast<const double2*>(Fg + tile_base(K + 1 + d, K) + cl);
+  }
   for (int i = lane; i < (T << 3); i += 32) {
     double v = 0.0;  // padding pivots, the rhs row and the rows behind it contribute nothing
     if (i < s) v = x[p0 + i];
@@ -1112,22 +1184,22 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
     xs[i] = v;
   }
   __syncwarp();
-  const double* Fg = F_all + (size_t)r * nF + A.fptr[f];
-  const int g = lane >> 2, t = lane & 3;
   for (int K = KT - 1; K >= 0; K--) {
-    const double* Dg = Fg + tile_base(K, K);
-    double l[8][8];  // the unit triangle, issued before the tile sweep so the loads overlap it
-#pragma unroll
-    for (int i = 1; i < 8; i++)
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j < i) l[i][j] = Dg[i * 8 + j];
+    *reinterpret_cast<double2*>(tri + cl) = dg;
     double acc0 = 0.0, acc1 = 0.0;
-    for (int I = K + 1; I < T; I++) {
-      const double2 lv = *reinterpret_cast<const double2*>(Fg + tile_base(I, K) + g * 8 + 2 * t);
-      const double xi = xs[8 * I + g];
-      acc0 += lv.x * xi;
-      acc1 += lv.y * xi;
+#pragma unroll
+    for (int d = 0; d < TILE_MAX_T - 1; d++) {
+      if (K + 1 + d < T) {
+        const double xi = xs[8 * (K + 1 + d) + g];
+        acc0 += lv[d].x * xi;
+        acc1 += lv[d].y * xi;
+      }
+    }
+    if (K > 0) {  // the next column's tiles while this one is reduced and solved
+      dg = *reinterpret_cast<const double2*>(Fg + tile_base(K - 1, K - 1) + cl);
+#pragma unroll
+      for (int d = 0; d < TILE_MAX_T - 1; d++)
+        if (K + d < T) lv[d] = *reinterpret_cast<const double2*>(Fg + tile_base(K + d, K - 1) + cl);
     }
 #pragma unroll
     for (int o = 4; o <= 16; o <<= 1) {
@@ -1146,7 +1218,7 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
     for (int i = 7; i >= 1; i--)
 #pragma unroll
       for (int j = 0; j < 8; j++)
-        if (j < i) w[j] -= l[i][j] * w[i];
+        if (j < i) w[j] -= tri[tile_in(i, j)] * w[i];
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 8; c++)
@@ -1371,21 +1443,51 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     TA.npiv = D.ds.npiv.p; TA.nupd = D.ds.nupd.p; TA.piv0 = D.ds.piv0.p; TA.rows_ptr = D.ds.rows_ptr.p;
     TA.upd_rows = D.ds.upd_rows.p; TA.list = D.tile_list.p; TA.item_ptr = D.tile_item_ptr.p;
     TA.item_nv = D.tile_item_nv.p; TA.fptr = D.tile_fptr.p; TA.items = D.tile_items.p;
-    const int gy = (D.R + TILE_WARPS - 1) / TILE_WARPS;
-    for (const TileLaunch& TL : D.tile_launches) {
-      const int slab = ((TL.T * (TL.T + 1)) / 2) * 64 + TILE_SCRATCH;
-      dim3 grid(TL.count, gy);
-      factor_tile_kernel<<<grid, TILE_WARPS * 32, (size_t)TILE_WARPS * slab * sizeof(double), c->stream>>>(
-          TA, TL.list_off, D.R, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n);
-      c->launches++;
+    TA.child_ptr = D.ds.child_ptr.p; TA.children = D.ds.children.p;
+    // one launch per (level, class of tile rows) sizes the shared memory for its class; a level with less
+    // than two waves of CTAs is launch- and latency-bound instead, so its classes go out as ONE launch.
+    // grid = (replica, front): consecutive CTAs are consecutive replicas of one front.
+    const long small_level = 2L * c->num_sms * 16;
+    const int nTL = (int)D.tile_launches.size();
+    // warps (= replicas) per CTA: measurement switches SLAM_B200_TILE_WPC_F / _B (1, 2 or 4)
+    static const int wpc_f = [] { const char* e = getenv("SLAM_B200_TILE_WPC_F"); int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();
+    static const int wpc_b = [] { const char* e = getenv("SLAM_B200_TILE_WPC_B"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
+    auto launch_factor = [&](int list_off, int count, int Tmax) {
+      const int slab = ((Tmax * (Tmax + 1)) / 2) * 64 + TILE_SCRATCH;
+      for (int o = 0; o < count; o += 65535) {
+        dim3 grid((D.R + wpc_f - 1) / wpc_f, std::min(65535, count - o));
+        factor_tile_kernel<<<grid, 32 * wpc_f, (size_t)wpc_f * slab * sizeof(double), c->stream>>>(
+            TA, list_off + o, D.R, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n);
+        c->launches++;
+      }
+    };
+    for (int k = 0; k < nTL;) {
+      int k1 = k + 1;
+      while (k1 < nTL && D.tile_launches[k1].level == D.tile_launches[k].level) k1++;
+      long ctas = 0;
+      for (int q = k; q < k1; q++) ctas += (long)D.tile_launches[q].count * D.R;
+      const int step = ctas <= small_level ? k1 - k : 1;
+      for (int q = k; q < k1; q += step) {
+        int count = 0, Tmax = 0;
+        for (int q2 = q; q2 < q + step; q2++) { count += D.tile_launches[q2].count; Tmax = std::max(Tmax, D.tile_launches[q2].T); }
+        launch_factor(D.tile_launches[q].list_off, count, Tmax);
+      }
+      k = k1;
     }
     mark();  // factored
     mark();  // forward (fused)
-    for (int k = (int)D.tile_launches.size() - 1; k >= 0; k--) {
-      const TileLaunch& TL = D.tile_launches[k];
-      dim3 grid(TL.count, gy);
-      backward_tile_kernel<<<grid, TILE_WARPS * 32, 0, c->stream>>>(TA, TL.list_off, D.R, D.Lv.p, D.nL, D.x.p, D.n);
-      c->launches++;
+    for (int k1 = nTL; k1 > 0;) {  // root -> leaves, one launch per level (no dynamic shared memory: no classes)
+      int k = k1 - 1;
+      while (k > 0 && D.tile_launches[k - 1].level == D.tile_launches[k1 - 1].level) k--;
+      int count = 0;
+      for (int q = k; q < k1; q++) count += D.tile_launches[q].count;
+      for (int o = 0; o < count; o += 65535) {
+        dim3 grid((D.R + wpc_b - 1) / wpc_b, std::min(65535, count - o));
+        backward_tile_kernel<<<grid, 32 * wpc_b, (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream>>>(
+            TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n);
+        c->launches++;
+      }
+      k1 = k;
     }
     SLAM_CUDA_TRY(c, cudaGetLastError());
     mark();  // backward done
@@ -1550,6 +1652,7 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
     int rc = graph_enqueue_assemble(c, 0, D.P, false);
     if (!rc) rc = graph_enqueue_solve(c);
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    D.launches_captured = c->launches - before;
     c->launches = before;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     SLAM_CUDA_TRY(c, e);
@@ -1560,7 +1663,7 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
       // count the kernel nodes once: bookkeeping for slam_b200_launch_count
       // (assemble 2 + per level factor/forward/backward + update)
       int n = 2 + 1;
-      if (D.tile_path) n += 2 * (int)D.tile_launches.size();
+      if (D.tile_path) n = (int)(D.launches_captured);
       else for (const LevelLaunch& LL : D.levels) {
         int ntiny = LL.n_tiny ? 1 : 0;
         if (LL.n_tiny && warp_kernels(c, D, LL)) {

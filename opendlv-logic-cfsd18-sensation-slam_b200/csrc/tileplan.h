@@ -8,7 +8,8 @@
 //     side (the forward solve rides along as a row of the augmented matrix); nloc = sp + u + 1 <= 96,
 //     T = ceil(nloc / 8) tile rows, KT = sp / 8 pivot tile columns;
 //   * the storage of a front, in shared memory while it is factorised and in HBM afterwards: the lower
-//     triangle of tiles, tile (I, J), I >= J, at ((I (I+1)) / 2 + J) * 64 doubles, row-major inside a tile.
+//     triangle of tiles, tile (I, J), I >= J, at ((I (I+1)) / 2 + J) * 64 doubles, row-major inside a tile (with the
+//     two column halves of rows 2, 3, 6, 7 swapped, see tile_off).
 //     After the factorisation the tiles of columns J < KT hold L (unit lower, D on the diagonal; the rhs
 //     row holds z = D^-1 L^-1 b), the tiles J >= KT hold the Schur complement and the update vector (rhs row);
 //   * the assembly list of every front: {source offset, destination offset in the front} pairs, first the
@@ -39,9 +40,13 @@ struct TilePlan {
 };
 
 inline int tile_sp(int s) { return (s + 7) & ~7; }
-inline int tile_off(int i, int j) {  // local (i, j), i >= j -> offset inside the front's tile storage
+// Local (i, j), i >= j -> offset inside the front's tile storage.  Inside a tile the rows with bit 1 set store
+// their two 4-column halves swapped ((j & 7) ^ 4): the MMA A/B-operand reads (lane (g, t) takes column 4h + t of
+// row g) then touch every shared-memory bank exactly twice (2 wavefronts, the minimum for 256 bytes) instead of
+// four times, while the accumulator-layout reads (16 bytes per lane, two rows per 128 bytes) stay conflict-free.
+inline int tile_off(int i, int j) {
   const int I = i >> 3, J = j >> 3;
-  return ((I * (I + 1)) / 2 + J) * 64 + (i & 7) * 8 + (j & 7);
+  return ((I * (I + 1)) / 2 + J) * 64 + (i & 7) * 8 + ((j & 7) ^ ((i & 2) << 1));
 }
 
 // solver2v[k]: offset in V of the rhs entry of solver scalar k.

@@ -117,7 +117,7 @@ def solver_perm(sym, dims):
 # ------------------------------------------------------------------------------------------------
 def _tile_off(i, j):
     I, J = i >> 3, j >> 3
-    return ((I * (I + 1)) // 2 + J) * 64 + (i & 7) * 8 + (j & 7)
+    return ((I * (I + 1)) // 2 + J) * 64 + (i & 7) * 8 + ((j & 7) ^ ((i & 2) << 1))   # tileplan.h: tile_off
 
 
 def tile_factor_solve(sym, hv, b_solver):
