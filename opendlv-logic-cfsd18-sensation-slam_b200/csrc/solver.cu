@@ -1111,25 +1111,29 @@ factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __re
       __syncwarp();
       const double xa0 = P[al0] * nd0, xa1 = P[al1] * nd1;  // -X in A-operand layout
       const int rowI = tile_base(I, 0);
-      for (int J0 = K + 1; J0 <= I; J0 += 4) {  // C_IJ -= X L_JK^T, four tiles in flight
+      for (int J0 = K + 1; J0 <= I; J0 += 4) {  // C_IJ -= X L_JK^T, up to four tiles in flight
         double b0[4], b1[4];
         double2 cv[4];
+        const int nq = min(4, I - J0 + 1);  // warp-uniform
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          const int J = min(J0 + q, I);
-          const double* Lj = F + tile_base(J, K);
-          b0[q] = Lj[al0];
-          b1[q] = Lj[al1];
-          cv[q] = *reinterpret_cast<const double2*>(F + rowI + (J << 6) + cl);
+          if (q < nq) {
+            const double* Lj = F + tile_base(J0 + q, K);
+            b0[q] = Lj[al0];
+            b1[q] = Lj[al1];
+            cv[q] = *reinterpret_cast<const double2*>(F + rowI + ((J0 + q) << 6) + cl);
+          }
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          dmma_acc(cv[q].x, cv[q].y, xa0, b0[q]);
-          dmma_acc(cv[q].x, cv[q].y, xa1, b1[q]);
+          if (q < nq) {
+            dmma_acc(cv[q].x, cv[q].y, xa0, b0[q]);
+            dmma_acc(cv[q].x, cv[q].y, xa1, b1[q]);
+          }
         }
 #pragma unroll
         for (int q = 0; q < 4; q++)
-          if (J0 + q <= I) *reinterpret_cast<double2*>(F + rowI + ((J0 + q) << 6) + cl) = cv[q];
+          if (q < nq) *reinterpret_cast<double2*>(F + rowI + ((J0 + q) << 6) + cl) = cv[q];
       }
       __syncwarp();
     }
