@@ -1444,7 +1444,8 @@ int graph_build_structure(slam_b200_ctx* c) {
       D.nU = 0;
       D.nUvec = 0;
       // classes of tile rows: a launch sizes its shared memory for the largest front of its class
-      auto cls_of = [](int T) { return T <= 5 ? 0 : T <= 8 ? T - 5 : T <= 10 ? 4 : 5; };
+      // fronts of <= 8 tile rows: one class per T (the register-resident kernel is instantiated per T)
+      auto cls_of = [](int T) { return T <= 8 ? T : T <= 10 ? 9 : 10; };
       for (int lv = 0; lv < S.nlevels; lv++) {
         std::vector<int> fr;
         for (int f = S.level_ptr[lv]; f < S.level_ptr[lv + 1]; f++) fr.push_back(f);

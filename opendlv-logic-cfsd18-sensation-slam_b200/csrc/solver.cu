@@ -989,22 +989,11 @@ __device__ __forceinline__ bool tile_ldlt(double& a0, double& a1, double& di0, d
   return bad;
 }
 
-__global__ void __launch_bounds__(128)
-factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __restrict__ V_all, long nV, double* F_all,
-                   long nF, int* status, double* x_all, int n) {
-  extern __shared__ double smem[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  // consecutive warps / CTAs = consecutive replicas of ONE front: its item list stays in L1
-  const int r = blockIdx.x * (blockDim.x >> 5) + wid;
-  if (r >= R) return;  // no block-wide barrier below
-  const int f = A.list[list_off + blockIdx.y];
-  const int s = A.npiv[f], u = A.nupd[f];
-  const int sp = (s + 7) & ~7, nloc = sp + u + 1, T = (nloc + 7) >> 3, KT = sp >> 3;
-  const int ntile = (T * (T + 1)) >> 1;
-  double* F = smem + (size_t)wid * slab;
+// Zeroes the tile triangle of front f in shared memory (1.0 on the padding pivots) and adds the plan's items: H and b
+// from V, then the children's Schur complements / update vectors from the replica's front storage.
+__device__ __forceinline__ void tile_assemble(const TileArgs& A, int f, double* F, int ntile, const double* __restrict__ V,
+                                              const double* Fr, int lane, int s, int sp) {
   double2* F2 = reinterpret_cast<double2*>(F);
-  const double* V = V_all + (size_t)r * nV;
-  double* Fr = F_all + (size_t)r * nF;
   // The assembly below is a chain item -> value -> add; the children's Schur complements were written by the
   // previous launches and sit in HBM.  Ask for their tile rows (rows >= the child's KT are contiguous) now, so
   // that they are on their way to L2 while the front is zeroed and the H entries are placed.
@@ -1068,6 +1057,25 @@ factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __re
 #pragma unroll
     for (int k = 0; k < IB; k++) it[k] = nx[k];
   }
+}
+
+__global__ void __launch_bounds__(128)
+factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __restrict__ V_all, long nV, double* F_all,
+                   long nF, int* status, double* x_all, int n) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // consecutive warps / CTAs = consecutive replicas of ONE front: its item list stays in L1
+  const int r = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (r >= R) return;  // no block-wide barrier below
+  const int f = A.list[list_off + blockIdx.y];
+  const int s = A.npiv[f], u = A.nupd[f];
+  const int sp = (s + 7) & ~7, nloc = sp + u + 1, T = (nloc + 7) >> 3, KT = sp >> 3;
+  const int ntile = (T * (T + 1)) >> 1;
+  double* F = smem + (size_t)wid * slab;
+  double2* F2 = reinterpret_cast<double2*>(F);
+  const double* V = V_all + (size_t)r * nV;
+  double* Fr = F_all + (size_t)r * nF;
+  tile_assemble(A, f, F, ntile, V, Fr, lane, s, sp);
   // ---- factorisation ----
   const int g = lane >> 2, t = lane & 3;
   const int sw = (g & 2) << 1;            // column-half swap of this lane's row (tileplan.h)
@@ -1145,6 +1153,108 @@ factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __re
   double* xr = x_all + (size_t)r * n + A.piv0[f];
   const int rr = sp + u;
   for (int p = lane; p < s; p += 32) xr[p] = F[tile_at(rr, p)];
+  if (bad && lane == 0) status[2 * r] = 1;
+}
+
+// The same factorisation with the WHOLE front in registers (accumulator layout: tile q = two doubles per lane),
+// one instantiation per number of tile rows T <= 8.  ncu on the shared-memory-resident kernel above: L1/TEX data
+// pipe 88 % busy (990 shared-memory wavefronts per front: every tile update loads and stores its C tile and
+// re-reads both operands), issue slots 55 %.  Here a tile update is two MMAs on registers; shared memory is only
+// the assembly buffer and the place where a freshly computed L tile changes from the accumulator layout to the
+// A/B-operand layout (one store + two loads per panel tile; the same operand registers serve as the row's -X d
+// and as every later row's L^T), and the front goes to HBM straight from the registers.
+template <int T>
+__global__ void __launch_bounds__(128)
+factor_tile_reg_kernel(TileArgs A, int list_off, int R, const double* __restrict__ V_all, long nV, double* F_all,
+                       long nF, int* status, double* x_all, int n) {
+  constexpr int NT = (T * (T + 1)) / 2;
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (r >= R) return;  // no block-wide barrier below
+  const int f = A.list[list_off + blockIdx.y];  // every front of this launch has exactly T tile rows
+  const int s = A.npiv[f], u = A.nupd[f];
+  const int sp = (s + 7) & ~7, KT = sp >> 3, rr = sp + u;
+  double* F = smem + (size_t)wid * (NT * 64);
+  const double* V = V_all + (size_t)r * nV;
+  double* Fr = F_all + (size_t)r * nF;
+  tile_assemble(A, f, F, NT, V, Fr, lane, s, sp);
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  const int sw = (g & 2) << 1;
+  const int cl = g * 8 + ((2 * t) ^ sw), al0 = g * 8 + (t ^ sw), al1 = g * 8 + ((4 + t) ^ sw);
+  double2 c[NT];
+#pragma unroll
+  for (int q = 0; q < NT; q++) c[q] = *reinterpret_cast<const double2*>(F + q * 64 + cl);
+  __syncwarp();
+  bool bad = false;
+#pragma unroll
+  for (int K = 0; K < T - 1; K++) {  // KT <= T - 1: the rhs row lies behind the pivots
+    if (K < KT) {
+      const int dkk = (K * (K + 1)) / 2 + K;
+      double di0 = 1.0, di1 = 1.0;
+      bad |= tile_ldlt(c[dkk].x, c[dkk].y, di0, di1, g, t);
+      double* Dk = F + dkk * 64;
+      *reinterpret_cast<double2*>(Dk + cl) = c[dkk];
+#pragma unroll
+      for (int I = K + 1; I < T; I++) *reinterpret_cast<double2*>(F + ((I * (I + 1)) / 2 + K) * 64 + cl) = c[(I * (I + 1)) / 2 + K];
+      __syncwarp();
+      double x[8];
+#pragma unroll
+      for (int j = 7; j >= 0; j--) {
+        double acc = (j == g) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 7; k > j; k--) acc -= x[k] * Dk[tile_in(k, j)];
+        x[j] = acc;
+      }
+      const double w0 = t == 0 ? x[0] : t == 1 ? x[1] : t == 2 ? x[2] : x[3];
+      const double w1 = t == 0 ? x[4] : t == 1 ? x[5] : t == 2 ? x[6] : x[7];
+      const double nd0 = -Dk[tile_in(t, t)], nd1 = -Dk[tile_in(4 + t, 4 + t)];
+#pragma unroll
+      for (int I = K + 1; I < T; I++) {
+        const double* P = F + ((I * (I + 1)) / 2 + K) * 64;
+        double x0 = 0.0, x1 = 0.0;
+        dmma_acc(x0, x1, P[al0], w0);  // X = A_IK W = L_IK D
+        dmma_acc(x0, x1, P[al1], w1);
+        c[(I * (I + 1)) / 2 + K] = make_double2(x0 * di0, x1 * di1);  // L_IK, final
+      }
+      __syncwarp();  // every A-operand read is done before the staged tiles are overwritten with L
+#pragma unroll
+      for (int I = K + 1; I < T; I++) *reinterpret_cast<double2*>(F + ((I * (I + 1)) / 2 + K) * 64 + cl) = c[(I * (I + 1)) / 2 + K];
+      __syncwarp();
+      double la0[T], la1[T];  // L_IK in operand layout: B operand of every row >= I, and (times -d) A operand of row I
+#pragma unroll
+      for (int I = K + 1; I < T; I++) {
+        const double* P = F + ((I * (I + 1)) / 2 + K) * 64;
+        la0[I] = P[al0];
+        la1[I] = P[al1];
+      }
+#pragma unroll
+      for (int I = K + 1; I < T; I++) {
+        const double xa0 = la0[I] * nd0, xa1 = la1[I] * nd1;
+#pragma unroll
+        for (int J = K + 1; J <= I; J++) {
+          dmma_acc(c[(I * (I + 1)) / 2 + J].x, c[(I * (I + 1)) / 2 + J].y, xa0, la0[J]);
+          dmma_acc(c[(I * (I + 1)) / 2 + J].x, c[(I * (I + 1)) / 2 + J].y, xa1, la1[J]);
+        }
+      }
+    }
+  }
+  // ---- results straight from the registers: the tile triangle (16-byte stores, 512 bytes per tile) and z ----
+  double* Fg = Fr + A.fptr[f];
+#pragma unroll
+  for (int q = 0; q < NT; q++) *reinterpret_cast<double2*>(Fg + q * 64 + cl) = c[q];
+  double* xr = x_all + (size_t)r * n + A.piv0[f];
+  if (g == (rr & 7)) {  // the rhs row lives in tile row T - 1
+#pragma unroll
+    for (int K = 0; K < T - 1; K++) {
+      if (K < KT) {
+        const double2 z = c[((T - 1) * T) / 2 + K];
+        if (8 * K + 2 * t < s) xr[8 * K + 2 * t] = z.x;
+        if (8 * K + 2 * t + 1 < s) xr[8 * K + 2 * t + 1] = z.y;
+      }
+    }
+  }
   if (bad && lane == 0) status[2 * r] = 1;
 }
 
@@ -1424,6 +1534,10 @@ static int solver_init_attrs(slam_b200_ctx* c) {
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     c->solver_attrs_set = true;
   }
   return 0;
@@ -1456,8 +1570,20 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     // warps (= replicas) per CTA: measurement switches SLAM_B200_TILE_WPC_F / _B (1, 2 or 4)
     static const int wpc_f = [] { const char* e = getenv("SLAM_B200_TILE_WPC_F"); int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();
     static const int wpc_b = [] { const char* e = getenv("SLAM_B200_TILE_WPC_B"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
-    auto launch_factor = [&](int list_off, int count, int Tmax) {
+    static const bool reg_path = getenv("SLAM_B200_TILE_NO_REG") == nullptr;
+    auto launch_factor = [&](int list_off, int count, int Tmax, bool uniform_T) {
       const int slab = ((Tmax * (Tmax + 1)) / 2) * 64 + TILE_SCRATCH;
+      if (reg_path && uniform_T && Tmax <= 8) {  // whole front in registers, one instantiation per T
+        for (int o = 0; o < count; o += 65535) {
+          dim3 grid((D.R + wpc_f - 1) / wpc_f, std::min(65535, count - o));
+          const size_t sm = (size_t)wpc_f * slab * sizeof(double);
+#define REG_LAUNCH(TT) case TT: factor_tile_reg_kernel<TT><<<grid, 32 * wpc_f, sm, c->stream>>>(TA, list_off + o, D.R, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n); break
+          switch (Tmax) { REG_LAUNCH(1); REG_LAUNCH(2); REG_LAUNCH(3); REG_LAUNCH(4); REG_LAUNCH(5); REG_LAUNCH(6); REG_LAUNCH(7); REG_LAUNCH(8); default: break; }
+#undef REG_LAUNCH
+          c->launches++;
+        }
+        return;
+      }
       for (int o = 0; o < count; o += 65535) {
         dim3 grid((D.R + wpc_f - 1) / wpc_f, std::min(65535, count - o));
         factor_tile_kernel<<<grid, 32 * wpc_f, (size_t)wpc_f * slab * sizeof(double), c->stream>>>(
@@ -1470,11 +1596,15 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       while (k1 < nTL && D.tile_launches[k1].level == D.tile_launches[k].level) k1++;
       long ctas = 0;
       for (int q = k; q < k1; q++) ctas += (long)D.tile_launches[q].count * D.R;
-      const int step = ctas <= small_level ? k1 - k : 1;
+      // classes of <= 8 tile rows hold exactly one T (graph.cu) and run the register-resident kernel; the others
+      // share the shared-memory-resident kernel and may be merged
+      bool all_big = true;
+      for (int q = k; q < k1; q++) all_big = all_big && (D.tile_launches[q].T > 8 || !reg_path);
+      const int step = (all_big && ctas <= small_level) ? k1 - k : 1;
       for (int q = k; q < k1; q += step) {
         int count = 0, Tmax = 0;
         for (int q2 = q; q2 < q + step; q2++) { count += D.tile_launches[q2].count; Tmax = std::max(Tmax, D.tile_launches[q2].T); }
-        launch_factor(D.tile_launches[q].list_off, count, Tmax);
+        launch_factor(D.tile_launches[q].list_off, count, Tmax, step == 1);
       }
       k = k1;
     }
