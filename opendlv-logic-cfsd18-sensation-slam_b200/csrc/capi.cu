@@ -155,6 +155,9 @@ int slam_b200_destroy(slam_b200_ctx* c) {
   c->grid_bbox.release(); c->grid_tmp.release();
   c->frame_in.release(); c->frame_outd.release(); c->frame_outi.release();
   c->pin_d.release(); c->pin_i.release(); c->pin_stage.release();
+  for (cudaStream_t& a : c->aux_stream) if (a) { cudaStreamDestroy(a); a = nullptr; }
+  for (cudaEvent_t e : c->fork_events) cudaEventDestroy(e);
+  c->fork_events.clear();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;

@@ -184,6 +184,11 @@ struct slam_b200_ctx {
   int num_sms = 148;
   int max_smem_optin = 0;
   bool solver_attrs_set = false;  // solver.cu: cudaFuncSetAttribute done for this context's device
+  // solver.cu: side streams + events that let the size classes of one tree level run side by side (fork / join
+  // around the context's stream; inside a stream capture they become parallel branches of the CUDA graph)
+  static constexpr int kAuxStreams = 3;
+  cudaStream_t aux_stream[kAuxStreams] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> fork_events;
 
   // ---- cone map ----
   DevBuf<double> map_x, map_y;

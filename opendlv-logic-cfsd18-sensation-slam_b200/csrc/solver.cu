@@ -1571,13 +1571,32 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     static const int wpc_f = [] { const char* e = getenv("SLAM_B200_TILE_WPC_F"); int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();
     static const int wpc_b = [] { const char* e = getenv("SLAM_B200_TILE_WPC_B"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
     static const bool reg_path = getenv("SLAM_B200_TILE_NO_REG") == nullptr;
-    auto launch_factor = [&](int list_off, int count, int Tmax, bool uniform_T) {
+    // The size classes of one level touch disjoint fronts, so they may run side by side: class i > 0 goes to a side
+    // stream between a fork and a join event (parallel branches once the iteration is captured into a CUDA graph).
+    // Levels near the root hold one to three fronts per class -- less than a wave of warps each -- and would otherwise
+    // pay one front latency per class.  SLAM_B200_TILE_NO_FORK=1 keeps everything on the context's stream.
+    static const bool fork_classes = getenv("SLAM_B200_TILE_NO_FORK") == nullptr;
+    size_t ev_used = 0;
+    auto next_event = [&]() -> cudaEvent_t {
+      if (ev_used == c->fork_events.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        c->fork_events.push_back(e);
+      }
+      return c->fork_events[ev_used++];
+    };
+    auto side_stream = [&](int i) -> cudaStream_t {
+      cudaStream_t& a = c->aux_stream[i % slam_b200_ctx::kAuxStreams];
+      if (!a) cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking);
+      return a;
+    };
+    auto launch_factor = [&](cudaStream_t st, int list_off, int count, int Tmax, bool uniform_T) {
       const int slab = ((Tmax * (Tmax + 1)) / 2) * 64 + TILE_SCRATCH;
       if (reg_path && uniform_T && Tmax <= 8) {  // whole front in registers, one instantiation per T
         for (int o = 0; o < count; o += 65535) {
           dim3 grid((D.R + wpc_f - 1) / wpc_f, std::min(65535, count - o));
           const size_t sm = (size_t)wpc_f * slab * sizeof(double);
-#define REG_LAUNCH(TT) case TT: factor_tile_reg_kernel<TT><<<grid, 32 * wpc_f, sm, c->stream>>>(TA, list_off + o, D.R, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n); break
+#define REG_LAUNCH(TT) case TT: factor_tile_reg_kernel<TT><<<grid, 32 * wpc_f, sm, st>>>(TA, list_off + o, D.R, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n); break
           switch (Tmax) { REG_LAUNCH(1); REG_LAUNCH(2); REG_LAUNCH(3); REG_LAUNCH(4); REG_LAUNCH(5); REG_LAUNCH(6); REG_LAUNCH(7); REG_LAUNCH(8); default: break; }
 #undef REG_LAUNCH
           c->launches++;
@@ -1586,7 +1605,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       }
       for (int o = 0; o < count; o += 65535) {
         dim3 grid((D.R + wpc_f - 1) / wpc_f, std::min(65535, count - o));
-        factor_tile_kernel<<<grid, 32 * wpc_f, (size_t)wpc_f * slab * sizeof(double), c->stream>>>(
+        factor_tile_kernel<<<grid, 32 * wpc_f, (size_t)wpc_f * slab * sizeof(double), st>>>(
             TA, list_off + o, D.R, slab, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n);
         c->launches++;
       }
@@ -1601,10 +1620,31 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       bool all_big = true;
       for (int q = k; q < k1; q++) all_big = all_big && (D.tile_launches[q].T > 8 || !reg_path);
       const int step = (all_big && ctas <= small_level) ? k1 - k : 1;
-      for (int q = k; q < k1; q += step) {
+      const bool fork = fork_classes && (k1 - k + step - 1) / step > 1;
+      cudaEvent_t ev_fork = nullptr;
+      if (fork) {
+        ev_fork = next_event();
+        SLAM_CUDA_TRY(c, cudaEventRecord(ev_fork, c->stream));
+      }
+      int branch = 0;
+      std::vector<cudaStream_t> used;
+      for (int q = k; q < k1; q += step, branch++) {
         int count = 0, Tmax = 0;
         for (int q2 = q; q2 < q + step; q2++) { count += D.tile_launches[q2].count; Tmax = std::max(Tmax, D.tile_launches[q2].T); }
-        launch_factor(D.tile_launches[q].list_off, count, Tmax, step == 1);
+        cudaStream_t st = c->stream;
+        if (fork && branch > 0) {
+          st = side_stream(branch - 1);
+          if (branch - 1 < slam_b200_ctx::kAuxStreams) {  // first use of this side stream in this level
+            SLAM_CUDA_TRY(c, cudaStreamWaitEvent(st, ev_fork, 0));
+            used.push_back(st);
+          }
+        }
+        launch_factor(st, D.tile_launches[q].list_off, count, Tmax, step == 1);
+      }
+      for (cudaStream_t st : used) {  // join
+        cudaEvent_t ej = next_event();
+        SLAM_CUDA_TRY(c, cudaEventRecord(ej, st));
+        SLAM_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, ej, 0));
       }
       k = k1;
     }

@@ -60,6 +60,8 @@ cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
 cudaError_t cudaFuncGetAttributes(void* a, const void*) { memset(a, 0, 64); return 0; }
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 1; return 0; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (void*)0x20; return 0; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)0x20; return 0; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
