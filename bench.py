@@ -438,7 +438,7 @@ def bench_frame_assoc(pkg, torch, local, drive, n_frames=300):
     return out
 
 
-def bench_slam_class(pkg, local, drive):
+def bench_slam_class(pkg, local, drive, n_drives=5):
     """The whole drive through the drop-in `Slam` class (csrc/host/slam.cpp over the C ABI), timed per frame
     kind like reference_cpu above: mapping frames, the frame that closes the loop (burst of optimizeGraph
     calls, slam.cpp:625-633) and the localiser frames after it."""
@@ -450,25 +450,36 @@ def bench_slam_class(pkg, local, drive):
     L.slamhost_create.restype = C.c_void_p
     L.slamhost_create.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
     L.slamhost_destroy.argtypes = [C.c_void_p]
-    L.slamhost_perform.argtypes = [C.c_void_p, c_dp, C.c_int, c_dp, C.c_float, C.c_double, c_ip, c_ip]
-    h = C.c_void_p(L.slamhost_create(THR, 50.0, 20, int(local)))
-    if not h:
-        raise RuntimeError("slamhost_create failed")
-    t = {0: [0.0, 0], 1: [0.0, 0], 2: [0.0, 0]}
-    idx = np.zeros(1024, dtype=np.int32); st = np.zeros(1024, dtype=np.int32)
-    for fr, p in zip(drive.frames, drive.poses_noisy):
-        fr = np.asfortranarray(fr, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64)
-        t0 = time.perf_counter()
-        rc = L.slamhost_perform(h, fr.ctypes.data_as(c_dp), fr.shape[1], p.ctypes.data_as(c_dp), 0.0, 0.0,
-                                idx.ctypes.data_as(c_ip), st.ctypes.data_as(c_ip))
-        dt = time.perf_counter() - t0
-        if rc in t:
-            t[rc][0] += dt; t[rc][1] += 1
-    L.slamhost_destroy(h)
-    return {"mapping_frames": t[0][1], "us_per_mapping_frame": t[0][0] / max(t[0][1], 1) * 1e6,
-            "loop_closing_frames": t[1][1], "ms_per_loop_closing_frame": t[1][0] / max(t[1][1], 1) * 1e3,
-            "localiser_frames": t[2][1], "us_per_localiser_frame": t[2][0] / max(t[2][1], 1) * 1e6,
-            "what": "drop-in Slam class over the C ABI, host clock around performSLAM, whole C1 drive"}
+    L.slamhost_replay_timed.argtypes = [C.c_void_p, C.c_int, c_dp, c_ip, c_dp, c_dp]
+    frames = [np.asfortranarray(fr, dtype=np.float64) for fr in drive.frames]
+    flat = np.concatenate([fr.ravel(order="F") for fr in frames]) if frames else np.zeros(0)
+    ncols = np.array([fr.shape[1] for fr in frames], dtype=np.int32)
+    poses = np.ascontiguousarray(drive.poses_noisy, dtype=np.float64)
+    runs = []
+    for _ in range(n_drives):
+        h = C.c_void_p(L.slamhost_create(THR, 50.0, 20, int(local)))
+        if not h:
+            raise RuntimeError("slamhost_create failed")
+        out6 = np.zeros(6)
+        rc = L.slamhost_replay_timed(h, len(frames), flat.ctypes.data_as(c_dp), ncols.ctypes.data_as(c_ip),
+                                     poses.ctypes.data_as(c_dp), out6.ctypes.data_as(c_dp))
+        L.slamhost_destroy(h)
+        if rc < 0:
+            raise RuntimeError("slamhost_replay_timed failed")
+        runs.append(out6)
+    runs = np.array(runs)
+    med = np.median(runs, axis=0)
+    per = lambda a, b: float(a) / max(float(b), 1.0)
+    return {"mapping_frames": int(med[1]), "us_per_mapping_frame": per(med[0], med[1]) * 1e6,
+            "loop_closing_frames": int(med[3]), "ms_per_loop_closing_frame": per(med[2], med[3]) * 1e3,
+            "localiser_frames": int(med[5]), "us_per_localiser_frame": per(med[4], med[5]) * 1e6,
+            "whole_drive_ms": float(med[0] + med[2] + med[4]) * 1e3,
+            "drives": n_drives,
+            "us_per_mapping_frame_all_drives": [per(r[0], r[1]) * 1e6 for r in runs],
+            "ms_per_loop_closing_frame_all_drives": [per(r[2], r[3]) * 1e3 for r in runs],
+            "what": "drop-in Slam class over the C ABI, steady_clock inside the library around performSLAM (as the "
+                    "reference replay times its own), whole C1 drive, median of %d drives, a fresh Slam object "
+                    "(constructor warm-up included in construction, not in the frames) per drive" % n_drives}
 
 
 def bench_c5(pkg, torch, args, world, rank, local, synth):

@@ -65,6 +65,13 @@ const char* slam_b200_last_error(const slam_b200_ctx* ctx);
 int slam_b200_version(void);
 /* blocks until all work issued on the context's stream has finished */
 int slam_b200_sync(slam_b200_ctx* ctx);
+/* Optional, once after create (the reference pays its set-up in Slam::setupOptimizer, slam.cpp:53-65, before the
+ * first frame as well): takes every first-use cost out of the frames -- loads the kernels, sets their attributes,
+ * allocates the frame mailbox and the device arrays of a graph of about poses_hint poses / landmarks_hint
+ * landmarks by optimising a synthetic ring of that size once, and runs one mapping and one localiser frame.  The
+ * context must be empty (no vertices, no map cones) and is empty again afterwards.  Without it the first
+ * optimizeGraph() of a drive -- the loop-closing frame -- carries tens of milliseconds of one-off work. */
+int slam_b200_warmup(slam_b200_ctx* ctx, int poses_hint, int landmarks_hint);
 
 /* ------------------------------------------------------------------------------------------------
  * polar -> Cartesian conversion on the device

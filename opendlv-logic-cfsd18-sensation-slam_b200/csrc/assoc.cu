@@ -103,6 +103,34 @@ __device__ __forceinline__ bool type_gate(int mapType, double obsType, int obsTy
 constexpr int FRAME_THREADS = 512;
 constexpr int FRAME_TILE = 2048;  // map cones staged in shared memory per pass (40 KB)
 
+// Per-frame mailbox in mapped pinned host memory (slam_b200_assoc_map_frame / _localize_frame).  The reference's
+// frames are ~8 columns against <= 300 cones: the kernel itself is a few microseconds, so two or three copy-engine
+// operations and a stream synchronisation per frame (the first version: 50 us per call) cost more than the work.
+// With a mailbox the kernel fetches its 4n + 5 input doubles from host memory once (one PCIe round trip), works in
+// device memory as before, copies its records to the mailbox, and publishes the frame's sequence number behind a
+// system-scope fence; the host spins on that word.  All pointers null = the copy path (SLAM_B200_FRAME_COPIES=1).
+struct FrameMailbox {
+  const double* in;   // 4n + 5 doubles
+  int* outi;          // 2n + 8 ints
+  double* outd;       // 5n doubles
+  unsigned* flag;
+  unsigned seq;
+};
+__device__ __forceinline__ void mailbox_fetch(const FrameMailbox& mb, double* in, int n) {
+  if (!mb.in) return;
+  for (int i = threadIdx.x; i < 4 * n + 5; i += blockDim.x) in[i] = mb.in[i];
+  __syncthreads();
+}
+__device__ __forceinline__ void mailbox_publish(const FrameMailbox& mb, const int* outi, int ni, const double* outd, int nd) {
+  if (!mb.in) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < ni; i += blockDim.x) mb.outi[i] = outi[i];
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) mb.outd[i] = outd[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(mb.flag) = mb.seq;
+}
+
 struct FrameScalars {  // ints at the head of the int output buffer
   int first_cone_created, loop_closing_obs, map_n, current_cone_index, loop_closing, n_reobserved,
       send_cone_data, pad;
@@ -147,11 +175,12 @@ __device__ void frame_first_fit(const double* __restrict__ gx, const double* __r
 
 // Mapping-phase frame (slam.cpp:552-623).  in: 4n frame doubles then pose(3).
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
-assoc_map_frame_kernel(const double* __restrict__ in, int n, double thr, double mapThr, double* map_x,
+assoc_map_frame_kernel(double* in, int n, double thr, double mapThr, double* map_x,
                        double* map_y, int* map_type, int M0, unsigned cci_in, int lc_in,
-                       double* __restrict__ outd, int* __restrict__ outi) {
+                       double* outd, int* outi, FrameMailbox mb) {
   __shared__ double sx[FRAME_TILE], sy[FRAME_TILE];
   __shared__ int st[FRAME_TILE];
+  mailbox_fetch(mb, in, n);
   FrameScalars* sc = reinterpret_cast<FrameScalars*>(outi);
   int* idx = outi + 8;
   int* status = outi + 8 + n;
@@ -275,15 +304,17 @@ assoc_map_frame_kernel(const double* __restrict__ in, int n, double thr, double 
       sc->pad = 0;
     }
   }
+  mailbox_publish(mb, outi, 2 * n + 8, outd, 5 * n);
 }
 
 // Localisation-phase frame (slam.cpp:350-387)
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
-assoc_localize_frame_kernel(const double* __restrict__ in, int n, double thr, const double* map_x,
+assoc_localize_frame_kernel(double* in, int n, double thr, const double* map_x,
                             const double* map_y, const int* map_type, int M, unsigned cci_in,
-                            double* __restrict__ outd, int* __restrict__ outi) {
+                            double* outd, int* outi, FrameMailbox mb) {
   __shared__ double sx[FRAME_TILE], sy[FRAME_TILE];
   __shared__ int st[FRAME_TILE];
+  mailbox_fetch(mb, in, n);
   FrameScalars* sc = reinterpret_cast<FrameScalars*>(outi);
   int* idx = outi + 8;
   double* g3 = outd + 2 * (size_t)n;
@@ -322,6 +353,7 @@ assoc_localize_frame_kernel(const double* __restrict__ in, int n, double thr, co
     sc->loop_closing = 0;
     sc->pad = 0;
   }
+  mailbox_publish(mb, outi, n + 8, outd, 5 * n);
 }
 
 // conversion only (slam_b200_cones_to_global)
@@ -568,6 +600,76 @@ int upload_frame(slam_b200_ctx* c, const double* cones, int n, const double pose
   return 0;
 }
 
+// ---- mailbox (host side) ----
+bool frame_copies() {
+  static const bool v = getenv("SLAM_B200_FRAME_COPIES") != nullptr;
+  return v;
+}
+inline size_t mbox_off_in() { return 64; }
+inline size_t mbox_off_outi(size_t cap) { return mbox_off_in() + sizeof(double) * (4 * cap + 8); }
+inline size_t mbox_off_outd(size_t cap) { return mbox_off_outi(cap) + sizeof(int) * (2 * cap + 8); }
+inline size_t mbox_bytes(size_t cap) { return mbox_off_outd(cap) + sizeof(double) * (5 * cap + 8); }
+
+int mailbox_reserve(slam_b200_ctx* c, int n) {
+  if (c->mbox_h && (size_t)n <= c->mbox_cap) return 0;
+  size_t cap = c->mbox_cap ? c->mbox_cap : 64;
+  while (cap < (size_t)n) cap *= 2;
+  if (c->mbox_h) {
+    SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFreeHost(c->mbox_h);
+    c->mbox_h = c->mbox_d = nullptr;
+    c->mbox_cap = 0;
+  }
+  void *h = nullptr, *d = nullptr;
+  SLAM_CUDA_TRY(c, cudaHostAlloc(&h, mbox_bytes(cap), cudaHostAllocMapped));
+  cudaError_t e = cudaHostGetDevicePointer(&d, h, 0);
+  if (e != cudaSuccess) { cudaFreeHost(h); SLAM_CUDA_TRY(c, e); }
+  std::memset(h, 0, mbox_bytes(cap));
+  c->mbox_h = static_cast<char*>(h);
+  c->mbox_d = static_cast<char*>(d);
+  c->mbox_cap = cap;
+  c->mbox_seq = 0;
+  return 0;
+}
+
+// writes the frame into the mailbox and returns the kernel-side view of it
+FrameMailbox mailbox_fill(slam_b200_ctx* c, const double* cones, int n, const double pose[3]) {
+  double* in = reinterpret_cast<double*>(c->mbox_h + mbox_off_in());
+  std::memcpy(in, cones, sizeof(double) * 4 * (size_t)n);
+  std::memcpy(in + 4 * (size_t)n, pose, sizeof(double) * 3);
+  in[4 * (size_t)n + 3] = std::cos(pose[2]);  // host libm, like upload_frame
+  in[4 * (size_t)n + 4] = std::sin(pose[2]);
+  FrameMailbox mb;
+  mb.in = reinterpret_cast<const double*>(c->mbox_d + mbox_off_in());
+  mb.outi = reinterpret_cast<int*>(c->mbox_d + mbox_off_outi(c->mbox_cap));
+  mb.outd = reinterpret_cast<double*>(c->mbox_d + mbox_off_outd(c->mbox_cap));
+  mb.flag = reinterpret_cast<unsigned*>(c->mbox_d);
+  mb.seq = ++c->mbox_seq;
+  if (mb.seq == 0) mb.seq = ++c->mbox_seq;  // 0 is the cleared word
+  return mb;
+}
+
+// spins until the kernel has published mb.seq; a kernel that ended without publishing (a fault) is reported
+int mailbox_wait(slam_b200_ctx* c, unsigned seq) {
+  volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(c->mbox_h);
+  for (unsigned long spins = 1;; spins++) {
+    if (*flag == seq) break;
+    if ((spins & 0xfff) == 0) {
+      cudaError_t q = cudaStreamQuery(c->stream);
+      if (q != cudaErrorNotReady) {
+        if (*flag == seq) break;
+        if (q == cudaSuccess) { c->fail("frame kernel ended without publishing its records"); return SLAM_B200_E_CUDA; }
+        SLAM_CUDA_TRY(c, q);
+      }
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  return 0;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -660,22 +762,40 @@ int slam_b200_assoc_map_frame(slam_b200_ctx* c, const double* cones, int n, cons
   SLAM_CUDA_TRY(c, c->map_x.reserve(need, c->map_n, c->stream));
   SLAM_CUDA_TRY(c, c->map_y.reserve(need, c->map_n, c->stream));
   SLAM_CUDA_TRY(c, c->map_type.reserve(need, c->map_n, c->stream));
-  if (int rc = upload_frame(c, cones, n, pose)) return rc;
-  assoc_map_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, mapThr, c->map_x.p,
-                                                            c->map_y.p, c->map_type.p, c->map_n, *cci,
-                                                            *loop_closing, c->frame_outd.p, c->frame_outi.p);
-  c->launches++;
-  SLAM_CUDA_TRY(c, cudaGetLastError());
-  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_i.p, c->frame_outi.p, sizeof(int) * (2 * (size_t)n + 8),
-                                   cudaMemcpyDeviceToHost, c->stream));
-  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, c->frame_outd.p, sizeof(double) * 5 * (size_t)n,
-                                   cudaMemcpyDeviceToHost, c->stream));
-  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  const FrameScalars* sc = reinterpret_cast<const FrameScalars*>(c->pin_i.p);
-  std::memcpy(idx, c->pin_i.p + 8, sizeof(int) * n);
-  std::memcpy(status, c->pin_i.p + 8 + n, sizeof(int) * n);
-  if (z2) std::memcpy(z2, c->pin_d.p, sizeof(double) * 2 * (size_t)n);
-  if (g3) std::memcpy(g3, c->pin_d.p + 2 * (size_t)n, sizeof(double) * 3 * (size_t)n);
+  const int* ri;      // records: ints (8 scalars, idx, status) and doubles (z2, g3)
+  const double* rd;
+  if (!frame_copies()) {
+    if (int rc = mailbox_reserve(c, n)) return rc;
+    const FrameMailbox mb = mailbox_fill(c, cones, n, pose);
+    assoc_map_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, mapThr, c->map_x.p,
+                                                              c->map_y.p, c->map_type.p, c->map_n, *cci,
+                                                              *loop_closing, c->frame_outd.p, c->frame_outi.p, mb);
+    c->launches++;
+    SLAM_CUDA_TRY(c, cudaGetLastError());
+    if (int rc = mailbox_wait(c, mb.seq)) return rc;
+    ri = reinterpret_cast<const int*>(c->mbox_h + mbox_off_outi(c->mbox_cap));
+    rd = reinterpret_cast<const double*>(c->mbox_h + mbox_off_outd(c->mbox_cap));
+  } else {
+    if (int rc = upload_frame(c, cones, n, pose)) return rc;
+    assoc_map_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, mapThr, c->map_x.p,
+                                                              c->map_y.p, c->map_type.p, c->map_n, *cci,
+                                                              *loop_closing, c->frame_outd.p, c->frame_outi.p,
+                                                              FrameMailbox{nullptr, nullptr, nullptr, nullptr, 0});
+    c->launches++;
+    SLAM_CUDA_TRY(c, cudaGetLastError());
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_i.p, c->frame_outi.p, sizeof(int) * (2 * (size_t)n + 8),
+                                     cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, c->frame_outd.p, sizeof(double) * 5 * (size_t)n,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ri = c->pin_i.p;
+    rd = c->pin_d.p;
+  }
+  const FrameScalars* sc = reinterpret_cast<const FrameScalars*>(ri);
+  std::memcpy(idx, ri + 8, sizeof(int) * n);
+  std::memcpy(status, ri + 8 + n, sizeof(int) * n);
+  if (z2) std::memcpy(z2, rd, sizeof(double) * 2 * (size_t)n);
+  if (g3) std::memcpy(g3, rd + 2 * (size_t)n, sizeof(double) * 3 * (size_t)n);
   if (first_cone_created) *first_cone_created = sc->first_cone_created;
   if (loop_closing_obs) *loop_closing_obs = sc->loop_closing_obs;
   *cci = (uint32_t)sc->current_cone_index;
@@ -695,21 +815,39 @@ int slam_b200_assoc_localize_frame(slam_b200_ctx* c, const double* cones, int n,
   if (send_cone_data) *send_cone_data = 0;
   if (n == 0) return 0;
   if (int rc = ensure_frame_buffers(c, n)) return rc;
-  if (int rc = upload_frame(c, cones, n, pose)) return rc;
-  assoc_localize_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, c->map_x.p, c->map_y.p,
-                                                                 c->map_type.p, c->map_n, *cci,
-                                                                 c->frame_outd.p, c->frame_outi.p);
-  c->launches++;
-  SLAM_CUDA_TRY(c, cudaGetLastError());
-  SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_i.p, c->frame_outi.p, sizeof(int) * ((size_t)n + 8),
-                                   cudaMemcpyDeviceToHost, c->stream));
-  if (g3)
-    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, c->frame_outd.p + 2 * (size_t)n, sizeof(double) * 3 * (size_t)n,
+  const int* ri;
+  const double* rg3;
+  if (!frame_copies()) {
+    if (int rc = mailbox_reserve(c, n)) return rc;
+    const FrameMailbox mb = mailbox_fill(c, cones, n, pose);
+    assoc_localize_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, c->map_x.p, c->map_y.p,
+                                                                   c->map_type.p, c->map_n, *cci,
+                                                                   c->frame_outd.p, c->frame_outi.p, mb);
+    c->launches++;
+    SLAM_CUDA_TRY(c, cudaGetLastError());
+    if (int rc = mailbox_wait(c, mb.seq)) return rc;
+    ri = reinterpret_cast<const int*>(c->mbox_h + mbox_off_outi(c->mbox_cap));
+    rg3 = reinterpret_cast<const double*>(c->mbox_h + mbox_off_outd(c->mbox_cap)) + 2 * (size_t)n;
+  } else {
+    if (int rc = upload_frame(c, cones, n, pose)) return rc;
+    assoc_localize_frame_kernel<<<1, FRAME_THREADS, 0, c->stream>>>(c->frame_in.p, n, thr, c->map_x.p, c->map_y.p,
+                                                                   c->map_type.p, c->map_n, *cci,
+                                                                   c->frame_outd.p, c->frame_outi.p,
+                                                                   FrameMailbox{nullptr, nullptr, nullptr, nullptr, 0});
+    c->launches++;
+    SLAM_CUDA_TRY(c, cudaGetLastError());
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_i.p, c->frame_outi.p, sizeof(int) * ((size_t)n + 8),
                                      cudaMemcpyDeviceToHost, c->stream));
-  SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-  const FrameScalars* sc = reinterpret_cast<const FrameScalars*>(c->pin_i.p);
-  std::memcpy(idx, c->pin_i.p + 8, sizeof(int) * n);
-  if (g3) std::memcpy(g3, c->pin_d.p, sizeof(double) * 3 * (size_t)n);
+    if (g3)
+      SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->pin_d.p, c->frame_outd.p + 2 * (size_t)n, sizeof(double) * 3 * (size_t)n,
+                                       cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    ri = c->pin_i.p;
+    rg3 = c->pin_d.p;
+  }
+  const FrameScalars* sc = reinterpret_cast<const FrameScalars*>(ri);
+  std::memcpy(idx, ri + 8, sizeof(int) * n);
+  if (g3) std::memcpy(g3, rg3, sizeof(double) * 3 * (size_t)n);
   *cci = (uint32_t)sc->current_cone_index;
   if (n_reobserved) *n_reobserved = sc->n_reobserved;
   if (send_cone_data) *send_cone_data = sc->send_cone_data;

@@ -155,6 +155,8 @@ int slam_b200_destroy(slam_b200_ctx* c) {
   c->grid_bbox.release(); c->grid_tmp.release();
   c->frame_in.release(); c->frame_outd.release(); c->frame_outi.release();
   c->pin_d.release(); c->pin_i.release(); c->pin_stage.release();
+  if (c->mbox_h) cudaFreeHost(c->mbox_h);
+  c->mbox_h = c->mbox_d = nullptr;
   for (cudaStream_t& a : c->aux_stream) if (a) { cudaStreamDestroy(a); a = nullptr; }
   for (cudaEvent_t e : c->fork_events) cudaEventDestroy(e);
   c->fork_events.clear();
@@ -162,6 +164,61 @@ int slam_b200_destroy(slam_b200_ctx* c) {
   delete c;
   return 0;
 }
+
+int slam_b200_warmup(slam_b200_ctx* c, int poses_hint, int landmarks_hint) try {
+  NvtxRange nvtx_range("slam_b200/warmup");
+  if (!c) return SLAM_B200_E_ARG;
+  if (c->g.P() || c->g.L() || c->map_n) { c->fail("warmup needs an empty context"); return SLAM_B200_E_STATE; }
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  const int P = std::max(8, poses_hint), L = std::max(8, landmarks_hint) & ~1, half = L / 2;
+  const int base = std::max(1000, L);  // pose ids behind the landmark ids, like the reference (slam.hpp:118)
+  const double two_pi = 6.283185307179586, R = std::max(4.0, P * 0.45 / two_pi);
+  const double info3[9] = {5, 0, 0, 0, 5, 0, 0, 0, 5}, info2[4] = {0.01, 0, 0, 0.01};
+  int rc = 0;
+  std::vector<double> lx(L), ly(L);
+  for (int j = 0; j < L && rc >= 0; j++) {  // cone pairs left and right of the ring
+    const double a = two_pi * (j / 2) / half, r = R + ((j & 1) ? 1.5 : -1.5);
+    lx[j] = r * std::cos(a);
+    ly[j] = r * std::sin(a);
+    rc = slam_b200_graph_add_landmark(c, j, lx[j], ly[j]);
+  }
+  for (int k = 0; k < P && rc >= 0; k++) {
+    const double a = two_pi * k / P, pose[3] = {R * std::cos(a), R * std::sin(a), a + 0.5 * 3.141592653589793};
+    rc = slam_b200_graph_add_pose(c, base + k, pose[0], pose[1], pose[2] > 3.141592653589793 ? pose[2] - two_pi : pose[2]);
+    if (rc >= 0 && k > 0) rc = slam_b200_graph_add_odometry(c, base + k - 1, base + k, pose, info3);
+    const int pair0 = (int)((long)k * half / P);
+    const double ct = std::cos(pose[2]), st = std::sin(pose[2]);
+    for (int q = 0; q < 8 && rc >= 0; q++) {  // the four pairs ahead: eight observations per pose, like a trackdrive frame
+      const int j = (2 * (pair0 + 1 + q / 2) + (q & 1)) % L;
+      const double dx = lx[j] - pose[0], dy = ly[j] - pose[1], z[2] = {ct * dx + st * dy, -st * dx + ct * dy};
+      rc = slam_b200_graph_add_edge_se2_xy(c, base + k, j, z, info2);
+    }
+  }
+  if (rc >= 0) {
+    slam_b200_graph_set_fixed(c, base, 1);
+    slam_b200_graph_set_fixed(c, base + 1, 1);
+    slam_b200_graph_set_fixed(c, 0, 1);
+    slam_b200_graph_set_fixed(c, 1, 1);
+    double chi2[2];
+    rc = slam_b200_graph_optimize(c, 2, chi2);
+    if (rc >= -1) rc = 0;  // g2o's -1 / 0 are not errors of the warm-up
+  }
+  // one mapping frame into the empty map, one localiser frame against it
+  if (rc >= 0) {
+    const double cones[8] = {10.0, 0.0, 5.0, 1.0, -12.0, 0.0, 6.0, 2.0}, pose[3] = {0, 0, 0};
+    uint32_t cci = 0;
+    int32_t lc = 0, idx[2], status[2], first = 0, lcobs = -1, reobs = 0, send = 0;
+    double z2[4], g3[6];
+    rc = slam_b200_assoc_map_frame(c, cones, 2, pose, 1.2, 50.0, &cci, &lc, idx, status, z2, g3, &first, &lcobs);
+    if (rc >= 0) rc = slam_b200_assoc_localize_frame(c, cones, 2, pose, 1.2, &cci, idx, g3, &reobs, &send);
+    if (rc >= 0) rc = slam_b200_cones_to_global(c, cones, 2, pose, g3, nullptr);
+  }
+  const std::string keep = c->err;
+  slam_b200_graph_clear(c);
+  slam_b200_map_clear(c);
+  c->err = keep;
+  return rc < 0 ? rc : 0;
+} SLAM_ABI_CATCH(c)
 
 const char* slam_b200_last_error(const slam_b200_ctx* c) { return c ? c->err.c_str() : "null context"; }
 

@@ -212,6 +212,12 @@ struct slam_b200_ctx {
   PinBuf<double> pin_d;
   PinBuf<int> pin_i;
   PinBuf<char> pin_stage;        // structure uploads
+  // per-frame mailbox (assoc.cu): mapped pinned memory the frame kernels read their input from and publish their
+  // records + a completion word into, so a frame is one launch and no copy / stream synchronisation
+  char* mbox_h = nullptr;        // host address
+  char* mbox_d = nullptr;        // device address of the same memory
+  size_t mbox_cap = 0;           // columns it is sized for
+  unsigned mbox_seq = 0;         // completion word the next frame publishes
 
   // ---- graph ----
   HostGraph g;

@@ -1,5 +1,6 @@
 // slam_c.cpp -- flat C wrappers around the C++ Slam mirror so the Python tests can drive it the way
 // the reference's frame-gathering thread drives Slam::performSLAM.
+#include <chrono>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -73,6 +74,35 @@ int slamhost_perform(void* h, const double* cones4xN, int n, const double* pose3
       status[i] = s.lastStatus()[i];
     }
     return s.lastFrameKind();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -100;
+  }
+}
+
+// A whole drive with the clock INSIDE (steady_clock around performSLAM, like the reference replay harness times
+// the reference's performSLAM): out6 = {mapping s, mapping frames, loop-closing s, frames, localiser s, frames}.
+// cones_flat: the frames' 4 x ncols[k] column-major matrices one after another.  Returns frames run or -100.
+int slamhost_replay_timed(void* h, int nframes, const double* cones_flat, const int32_t* ncols, const double* poses3,
+                          double* out6) {
+  try {
+    Slam& s = *static_cast<Slam*>(h);
+    for (int q = 0; q < 6; q++) out6[q] = 0;
+    size_t off = 0;
+    for (int k = 0; k < nframes; k++) {
+      const int n = ncols[k];
+      slamtypes::MatrixXd m(4, n);
+      if (n) std::memcpy(m.data(), cones_flat + off, sizeof(double) * 4 * (size_t)n);
+      off += 4 * (size_t)n;
+      s.setOdometry(poses3[3 * k], poses3[3 * k + 1], poses3[3 * k + 2]);
+      s.setYawRate(0.0f, 0.0);
+      const auto t0 = std::chrono::steady_clock::now();
+      s.performSLAM(m);
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      const int kind = s.lastFrameKind();
+      if (kind >= 0 && kind <= 2) { out6[2 * kind] += dt; out6[2 * kind + 1] += 1; }
+    }
+    return nframes;
   } catch (const std::exception& e) {
     g_err = e.what();
     return -100;

@@ -132,7 +132,7 @@ factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV
 #pragma unroll
       for (int p = 0; p < NB; p++) {
         const double d = T[p][p];
-        if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;  // SimplicialCholesky_impl.h:175-179
+        if (p < nb && d == 0.0) bad = true;  // SimplicialCholesky_impl.h:175-179: an exactly zero pivot fails, NaN / inf flow on
         iv[p] = __drcp_rn(d);
 #pragma unroll
         for (int q = p + 1; q < NB; q++) {
@@ -321,7 +321,7 @@ __device__ __forceinline__ bool factor_triangle(const double* src, int sq, int s
 #pragma unroll
   for (int p = 0; p < NB; p++) {
     const double d = T[p][p];
-    if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;
+    if (p < nb && d == 0.0) bad = true;  // exactly zero only (SimplicialCholesky_impl.h:175-179); NaN / inf flow on like there
     iv[p] = __drcp_rn(d);
 #pragma unroll
     for (int q = 0; q < NB; q++) {
@@ -706,7 +706,7 @@ factor_tiny_kernel(SymArgs S, int list_off, int count, int slab, const double* _
 #pragma unroll
     for (int p = 0; p < TNB; p++) {
       const double d = __shfl_sync(0xffffffffu, a0[p], p);
-      if (p < nb && (d == 0.0 || !isfinite(d))) bad = true;  // SimplicialCholesky_impl.h:175-179
+      if (p < nb && d == 0.0) bad = true;  // SimplicialCholesky_impl.h:175-179: an exactly zero pivot fails, NaN / inf flow on
       inv[p] = __drcp_rn(d);
 #pragma unroll
       for (int q = p + 1; q < TNB; q++) {
@@ -956,9 +956,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
   e = fma(-d, x, 1.0);
   return fma(x, e, x);
 }
-// zero / denormal / inf / nan pivot (SimplicialCholesky_impl.h:175-179 fails on an exactly zero pivot)
+// SimplicialCholesky_impl.h:175-179 fails on an exactly zero pivot and on nothing else: a NaN or infinite pivot flows
+// on and poisons everything connected to it, which is what the reference's map looks like after an optimise over a
+// graph that holds a NaN cone (an absent objectId: azimuth 0).  A denormal pivot counts as zero here: the seeded
+// reciprocal flushes it.
 __device__ __forceinline__ bool bad_pivot(double d) {
-  return (unsigned)((__double2hiint(d) >> 20) & 0x7ff) - 1u >= 0x7feu;
+  return ((__double2hiint(d) >> 20) & 0x7ff) == 0;
 }
 
 // LDL^T of one 8 x 8 tile held in the accumulator layout of the warp (lane (g, t): entries (g, 2t), (g, 2t+1)),

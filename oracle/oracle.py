@@ -355,6 +355,7 @@ def reference_replay_timing(frames, poses, thr, map_thr):
                 return {"mapping_frames": nm, "us_per_mapping_frame": sm / max(nm, 1) * 1e6,
                         "loop_closing_frames": nc, "ms_per_loop_closing_frame": sc / max(nc, 1) * 1e3,
                         "localiser_frames": nl, "us_per_localiser_frame": sl / max(nl, 1) * 1e6,
+                        "whole_drive_ms": (sm + sc + sl) * 1e3,
                         "what": "the reference's real src/slam.cpp (g2o facade over the restated Gauss-Newton), 1 core, "
                                 "time inside performSLAM, its per-observation prints sent to /dev/null"}
     return None

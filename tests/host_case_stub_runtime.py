@@ -125,6 +125,9 @@ x, y, t = ctx.map_read()
 rc["map_roundtrip"] = int(np.array_equal(x, f.map_x) and np.array_equal(y, f.map_y) and np.array_equal(t, f.map_type))
 fr = np.asfortranarray(np.random.default_rng(0).normal(size=(4, 900)))
 ctx.cones_to_global(fr, np.zeros(3))
+# kernels are no-ops under the stub: nothing would ever publish the frame's completion word, so the frame calls go
+# through the copy path here (the staging buffers and status codes are what this case covers)
+os.environ["SLAM_B200_FRAME_COPIES"] = "1"
 ctx.assoc_localize_frame(fr, np.zeros(3), 1.2, 0)
 ctx.close()
 print(json.dumps(out))

@@ -41,6 +41,8 @@ cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 cudaError_t cudaFree(void* p) { free(p); return 0; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return 0; }
+cudaError_t cudaStreamQuery(cudaStream_t) { return 0; }
 cudaError_t cudaMallocHost(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 static void note(const void* src, size_t n, int kind) {

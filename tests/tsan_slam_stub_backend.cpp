@@ -17,6 +17,7 @@ struct slam_b200_ctx {
 extern "C" {
 int slam_b200_create(int, void*, slam_b200_ctx** out) { *out = new slam_b200_ctx(); return 0; }
 int slam_b200_destroy(slam_b200_ctx* c) { delete c; return 0; }
+int slam_b200_warmup(slam_b200_ctx*, int, int) { return 0; }
 const char* slam_b200_last_error(const slam_b200_ctx*) { return "stub"; }
 int slam_b200_graph_clear(slam_b200_ctx*) { return 0; }
 int slam_b200_map_clear(slam_b200_ctx* c) { c->map_n = 0; return 0; }
