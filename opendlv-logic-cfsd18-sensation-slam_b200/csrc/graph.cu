@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <exception>
+#include <thread>
 #include <unordered_map>
 
 #include <climits>
@@ -1129,6 +1131,14 @@ int graph_build_structure(slam_b200_ctx* c) {
     ~PhaseRanges() { if (open) nvtxRangePop(); }
   } phase;
   phase.next("slam_b200/host structure pass");
+  static const bool dbg_on = getenv("SLAM_B200_SYM_DEBUG") != nullptr;
+  auto tdb = t0;
+  auto dbg = [&](const char* what) {
+    if (!dbg_on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[structure] %-28s %.4f s\n", what, std::chrono::duration<double>(now - tdb).count());
+    tdb = now;
+  };
   // ---- active set (initializeOptimization): edges whose vertices are not all fixed ----
   std::vector<char> pose_act(P, 0), lm_act(L, 0);
   std::vector<int> el_flags(El, 0), eo_flags(Eo, 0);
@@ -1145,11 +1155,14 @@ int graph_build_structure(slam_b200_ctx* c) {
     }
   // ---- Hessian index mapping (buildIndexMapping): non-fixed active vertices by ascending id ----
   std::vector<std::pair<int, int>> byId;  // (id, (local<<1)|is_lm)
-  for (int p = 0; p < P; p++)
-    if (pose_act[p] && !g.pose_fixed[p]) byId.push_back({g.pose_id[p], p << 1});
+  byId.reserve((size_t)P + L);
+  // landmarks first: in the reference's numbering (cone ids from 0, pose ids from 1000 up) that is already the
+  // ascending order, and the sort below is skipped
   for (int l = 0; l < L; l++)
     if (lm_act[l] && !g.lm_fixed[l]) byId.push_back({g.lm_id[l], (l << 1) | 1});
-  std::sort(byId.begin(), byId.end());
+  for (int p = 0; p < P; p++)
+    if (pose_act[p] && !g.pose_fixed[p]) byId.push_back({g.pose_id[p], p << 1});
+  if (!std::is_sorted(byId.begin(), byId.end())) std::sort(byId.begin(), byId.end());
   const int nb = (int)byId.size();
   D.nb = nb;
   D.pose_b.assign(P, -1);
@@ -1169,6 +1182,7 @@ int graph_build_structure(slam_b200_ctx* c) {
     }
     D.n = off;
   }
+  dbg("active set + index map");
   // ---- V layout ----
   const long base_off = 6L * L + 12L * P;
   D.hoff_diag.assign(nb, 0);
@@ -1177,17 +1191,13 @@ int graph_build_structure(slam_b200_ctx* c) {
     D.hoff_diag[b] = (kl & 1) ? (int)(2L * L + 4L * (kl >> 1)) : (int)(6L * L + 3L * P + 9L * (kl >> 1));
   }
   // ---- block structure (buildStructure): one slot per distinct free vertex pair ----
-  std::unordered_map<uint64_t, int> slotOf;
-  slotOf.reserve((size_t)Eo * 2);
+  // Only what fixes the PATTERN is computed before the symbolic analysis is started (it runs on a helper
+  // thread from then on); payload arrays, incidence lists and the first part of the upload follow while it runs.
   D.off_a.clear(); D.off_b.clear(); D.hoff_off.clear();
   long cursor = base_off;
-  auto slot = [&](int ba, int bb) -> int {
+  auto new_slot = [&](int ba, int bb) -> int {
     int lo = std::min(ba, bb), hi = std::max(ba, bb);
-    uint64_t key = ((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi;
-    auto it = slotOf.find(key);
-    if (it != slotOf.end()) return it->second;
     int k = (int)D.off_a.size();
-    slotOf.emplace(key, k);
     D.off_a.push_back(lo);
     D.off_b.push_back(hi);
     D.hoff_off.push_back((int)cursor);
@@ -1204,20 +1214,10 @@ int graph_build_structure(slam_b200_ctx* c) {
     for (int e = 0; e < El; e++) D.el_perm[cur[g.el_p[e]]++] = e;
   }
   std::vector<int> s_pose(El), s_lm(El), s_slot(El, -1), s_flags(El, 0);
-  std::vector<double> s_info(3 * (size_t)El);
   {
     // A (pose, landmark) pair can only repeat inside one pose's run of edges, so duplicates are found
     // by a linear look-back over that run (a handful of edges) -- no global hash for the 10^5..10^7
-    // pose-landmark blocks; only pose-pose pairs go through the hash map below.
-    auto new_slot = [&](int ba, int bb) -> int {
-      int lo = std::min(ba, bb), hi = std::max(ba, bb);
-      int k = (int)D.off_a.size();
-      D.off_a.push_back(lo);
-      D.off_b.push_back(hi);
-      D.hoff_off.push_back((int)cursor);
-      cursor += dim[lo] * dim[hi];
-      return k;
-    };
+    // pose-landmark blocks.
     D.off_a.reserve((size_t)El + Eo);
     D.off_b.reserve((size_t)El + Eo);
     D.hoff_off.reserve((size_t)El + Eo);
@@ -1244,10 +1244,109 @@ int graph_build_structure(slam_b200_ctx* c) {
         if (D.lm_b[l] < D.pose_b[p]) fl |= EF_TRANS;
       }
       s_flags[q] = fl;
-      s_info[q] = g.el_info[3 * (size_t)e];
-      s_info[El + (size_t)q] = g.el_info[3 * (size_t)e + 1];
-      s_info[2 * (size_t)El + q] = g.el_info[3 * (size_t)e + 2];
     }
+  }
+  dbg("landmark edges: sort + slots");
+  // pose-pose edges: incidence lists, slots, owner = min(i, j).  Edges of one pair are all processed by thread
+  // min(i, j) in incidence (= edge) order, so "has this pair been seen" is a look-back over the owner's earlier
+  // incidence entries (two or three for a pose chain) -- no hash map; a hub pose falls back to one.
+  std::vector<int> po_start(P + 1, 0), po_list(2 * (size_t)Eo), eo_slot(Eo, -1);
+  for (int e = 0; e < Eo; e++) { po_start[g.eo_i[e] + 1]++; po_start[g.eo_j[e] + 1]++; }
+  for (int p = 0; p < P; p++) po_start[p + 1] += po_start[p];
+  {
+    std::vector<int> cur(po_start.begin(), po_start.end() - 1);
+    for (int e = 0; e < Eo; e++) {
+      po_list[cur[g.eo_i[e]]++] = (e << 1);
+      po_list[cur[g.eo_j[e]]++] = (e << 1) | 1;
+    }
+    std::vector<int> eo_k(Eo, -1);  // slot index of every edge that has one
+    std::unordered_map<uint64_t, int> hub;  // only for owners with long incidence lists
+    for (int e = 0; e < Eo; e++) {
+      int i = g.eo_i[e], j = g.eo_j[e];
+      if ((eo_flags[e] & EF_ACTIVE) && D.pose_b[i] >= 0 && D.pose_b[j] >= 0) {
+        const int owner = std::min(i, j), partner = std::max(i, j);
+        int k = -1;
+        const int deg = po_start[owner + 1] - po_start[owner];
+        if (deg <= 32) {
+          for (int t = po_start[owner]; t < po_start[owner + 1]; t++) {
+            const int e2 = po_list[t] >> 1;
+            if (e2 >= e) break;  // incidence entries are in edge order
+            if (eo_k[e2] >= 0 && std::min(g.eo_i[e2], g.eo_j[e2]) == owner && std::max(g.eo_i[e2], g.eo_j[e2]) == partner) { k = eo_k[e2]; break; }
+          }
+        } else {
+          const uint64_t key = ((uint64_t)(uint32_t)owner << 32) | (uint32_t)partner;
+          auto it = hub.find(key);
+          if (it != hub.end()) k = it->second;
+        }
+        if (k < 0) {
+          k = new_slot(D.pose_b[i], D.pose_b[j]);
+          eo_flags[e] |= EF_FIRST;
+          if (deg > 32) hub.emplace(((uint64_t)(uint32_t)owner << 32) | (uint32_t)partner, k);
+        }
+        eo_k[e] = k;
+        eo_slot[e] = D.hoff_off[k];
+        eo_flags[e] |= EF_OFFDIAG;
+        if (D.pose_b[j] < D.pose_b[i]) eo_flags[e] |= EF_TRANS;
+      }
+    }
+  }
+  dbg("pose-pose edges");
+  D.nV = cursor;
+  D.t_structure = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  // ---- symbolic analysis (helper thread) ----
+  // Nested-dissection region size: about a tenth of the graph (measured optimum on the 1-lap and
+  // 10-lap trackdrive graphs: short assembly tree, still enough regions to order in parallel), but
+  // never so small that a hub vertex (a landmark seen from hundreds of poses) dominates a region --
+  // below ~2.5x the largest degree the separators degenerate and fill explodes (DESIGN.md section 4).
+  int leaf;
+  {
+    std::vector<int> deg(nb, 0);
+    for (size_t k = 0; k < D.off_a.size(); k++) { deg[D.off_a[k]]++; deg[D.off_b[k]]++; }
+    int maxdeg = 0;
+    for (int b = 0; b < nb; b++) maxdeg = std::max(maxdeg, deg[b]);
+    leaf = std::min(std::max(std::max(nb / 10, 3 * maxdeg), 64), 2048);
+    // a batch of replicas is throughput-bound, not latency-bound: prefer the ordering with the least
+    // fill (larger regions, more of the graph ordered by minimum degree)
+    if (c->batch_ordering) leaf = std::min(std::max(1024, 3 * maxdeg), 2048);
+  }
+  if (const char* s = getenv("SLAM_B200_ND_LEAF")) leaf = std::max(1, atoi(s));
+  std::thread sym_thread;
+  std::exception_ptr sym_error;
+  struct JoinGuard {  // an early return below must not leave the helper running on locals of this frame
+    std::thread& t;
+    ~JoinGuard() { if (t.joinable()) t.join(); }
+  } join_guard{sym_thread};
+  static const bool no_overlap = getenv("SLAM_B200_NO_HOST_OVERLAP") != nullptr;
+  if (c->assembly_only) {
+    // linearise + assemble only (config 5 measures the edge-partitioned assembly; the solve is
+    // reported separately): no ordering, no fronts
+    D.sym = Symbolic();
+    D.sym.nb = nb;
+    D.sym.n = D.n;
+    D.sym.boff = D.blk_hidx;  // solver order = g2o order
+  } else {
+    auto run_symbolic = [&]() {
+      try {
+        nvtxRangePushA("slam_b200/symbolic analysis");
+        symbolic_analyze(nb, dim.data(), (int)D.off_a.size(), D.off_a.data(), D.off_b.data(), D.hoff_diag.data(),
+                         D.hoff_off.data(), leaf, D.sym);
+        nvtxRangePop();
+      } catch (...) {
+        sym_error = std::current_exception();
+      }
+    };
+    if (no_overlap) run_symbolic();
+    else sym_thread = std::thread(run_symbolic);
+  }
+  // ---- while the analysis runs: payload arrays of the assembly kernels and their upload ----
+  phase.next("slam_b200/assembly structure + upload (overlaps the symbolic analysis)");
+  auto tov0 = std::chrono::steady_clock::now();
+  std::vector<double> s_info(3 * (size_t)El);
+  for (int q = 0; q < El; q++) {
+    const int e = D.el_perm[q];
+    s_info[q] = g.el_info[3 * (size_t)e];
+    s_info[El + (size_t)q] = g.el_info[3 * (size_t)e + 1];
+    s_info[2 * (size_t)El + q] = g.el_info[3 * (size_t)e + 2];
   }
   // CSR landmark -> sorted edge positions
   std::vector<int> lm_start(L + 1, 0), lm_edges(El);
@@ -1272,64 +1371,47 @@ int graph_build_structure(slam_b200_ctx* c) {
   D.s_lm_host = s_lm;
   D.el_start_host = el_start;
   D.shard_p0 = D.shard_p1 = -1;
-  // pose-pose edges: incidence lists, slots, owner = min(i, j)
-  std::vector<int> po_start(P + 1, 0), po_list(2 * (size_t)Eo), eo_slot(Eo, -1);
-  for (int e = 0; e < Eo; e++) { po_start[g.eo_i[e] + 1]++; po_start[g.eo_j[e] + 1]++; }
-  for (int p = 0; p < P; p++) po_start[p + 1] += po_start[p];
-  {
-    std::vector<int> cur(po_start.begin(), po_start.end() - 1);
-    for (int e = 0; e < Eo; e++) {
-      po_list[cur[g.eo_i[e]]++] = (e << 1);
-      po_list[cur[g.eo_j[e]]++] = (e << 1) | 1;
-    }
-    std::unordered_map<uint64_t, int> seen;  // (owner, slot) first-writer detection
-    for (int e = 0; e < Eo; e++) {
-      int i = g.eo_i[e], j = g.eo_j[e];
-      if ((eo_flags[e] & EF_ACTIVE) && D.pose_b[i] >= 0 && D.pose_b[j] >= 0) {
-        int k = slot(D.pose_b[i], D.pose_b[j]);
-        eo_slot[e] = D.hoff_off[k];
-        eo_flags[e] |= EF_OFFDIAG;
-        if (D.pose_b[j] < D.pose_b[i]) eo_flags[e] |= EF_TRANS;
-        // edges of one pair are all processed by thread min(i,j) in incidence (= edge) order
-        uint64_t key = ((uint64_t)(uint32_t)std::min(i, j) << 32) | (uint32_t)k;
-        if (seen.emplace(key, 1).second) eo_flags[e] |= EF_FIRST;
-      }
-    }
-  }
   std::vector<double> eo_info(6 * (size_t)Eo);
   for (int e = 0; e < Eo; e++)
     for (int k = 0; k < 6; k++) eo_info[(size_t)k * Eo + e] = g.eo_info[6 * (size_t)e + k];
-  D.nV = cursor;
-  D.t_structure = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  phase.next("slam_b200/symbolic analysis + launch lists");
-  // ---- symbolic analysis ----
-  // Nested-dissection region size: about a tenth of the graph (measured optimum on the 1-lap and
-  // 10-lap trackdrive graphs: short assembly tree, still enough regions to order in parallel), but
-  // never so small that a hub vertex (a landmark seen from hundreds of poses) dominates a region --
-  // below ~2.5x the largest degree the separators degenerate and fill explodes (DESIGN.md section 4).
-  int leaf;
+  std::vector<unsigned char> pose_free(P, 0), lm_free(L, 0);
+  for (int b = 0; b < nb; b++) {
+    const int kl = D.blk_kind_local[b];
+    if (kl & 1) lm_free[kl >> 1] = 1;
+    else pose_free[kl >> 1] = 1;
+  }
+  std::vector<int4> el_rec_h(El);
+  for (int q = 0; q < El; q++) el_rec_h[q] = make_int4(s_pose[q], s_lm[q], s_slot[q], s_flags[q]);
+  dbg("assembly payload (overlapped)");
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  g_uploads.clear();
   {
-    std::vector<int> deg(nb, 0);
-    for (size_t k = 0; k < D.off_a.size(); k++) { deg[D.off_a[k]]++; deg[D.off_b[k]]++; }
-    int maxdeg = 0;
-    for (int b = 0; b < nb; b++) maxdeg = std::max(maxdeg, deg[b]);
-    leaf = std::min(std::max(std::max(nb / 10, 3 * maxdeg), 64), 2048);
-    // a batch of replicas is throughput-bound, not latency-bound: prefer the ordering with the least
-    // fill (larger regions, more of the graph ordered by minimum degree)
-    if (c->batch_ordering) leaf = std::min(std::max(1024, 3 * maxdeg), 2048);
+    int rc = 0;
+    rc |= upload_vec(c, D.pose_free, pose_free);
+    rc |= upload_vec(c, D.lm_free, lm_free);
+    rc |= upload_vec(c, D.el_start, el_start);
+    rc |= upload_vec(c, D.el_rec, el_rec_h);
+    rc |= upload_vec(c, D.el_info, s_info);
+    rc |= upload_vec(c, D.lm_start, lm_start);
+    rc |= upload_vec(c, D.lm_edges, lm_edges);
+    rc |= upload_vec(c, D.lmo_pose, lmo_pose);
+    rc |= upload_vec(c, D.lmo_info, lmo_info);
+    rc |= upload_vec(c, D.eo_i, g.eo_i);
+    rc |= upload_vec(c, D.eo_j, g.eo_j);
+    rc |= upload_vec(c, D.eo_slot, eo_slot);
+    rc |= upload_vec(c, D.eo_flags, eo_flags);
+    rc |= upload_vec(c, D.po_start, po_start);
+    rc |= upload_vec(c, D.po_list, po_list);
+    rc |= upload_vec(c, D.eo_info, eo_info);
+    if (rc) { g_uploads.clear(); return SLAM_B200_E_CUDA; }
+    if (int frc = flush_uploads(c)) return frc;
   }
-  if (const char* s = getenv("SLAM_B200_ND_LEAF")) leaf = std::max(1, atoi(s));
-  if (c->assembly_only) {
-    // linearise + assemble only (config 5 measures the edge-partitioned assembly; the solve is
-    // reported separately): no ordering, no fronts
-    D.sym = Symbolic();
-    D.sym.nb = nb;
-    D.sym.n = D.n;
-    D.sym.boff = D.blk_hidx;  // solver order = g2o order
-  } else {
-    symbolic_analyze(nb, dim.data(), (int)D.off_a.size(), D.off_a.data(), D.off_b.data(), D.hoff_diag.data(),
-                     D.hoff_off.data(), leaf, D.sym);
-  }
+  dbg("assembly upload (overlapped)");
+  const double t_overlapped = std::chrono::duration<double>(std::chrono::steady_clock::now() - tov0).count();
+  if (sym_thread.joinable()) sym_thread.join();
+  if (sym_error) std::rethrow_exception(sym_error);
+  dbg("wait for the symbolic analysis");
+  phase.next("slam_b200/launch lists");
   Symbolic& S = D.sym;
   if (S.lptr.empty()) { S.lptr.assign(1, 0); S.uptr.assign(1, 0); S.rows_ptr.assign(1, 0); S.child_ptr.assign(1, 0); S.asm_ptr.assign(1, 0); }
   D.nL = S.lptr[S.nf];
@@ -1413,20 +1495,17 @@ int graph_build_structure(slam_b200_ctx* c) {
   }
   // solver scalar -> V offset of the rhs entry; vertex -> solver offset
   std::vector<int> solver2v(D.n), pose_boff(P, -1), lm_boff(L, -1);
-  std::vector<unsigned char> pose_free(P, 0), lm_free(L, 0);
   for (int b = 0; b < nb; b++) {
     int kl = D.blk_kind_local[b];
     int so = S.boff[b];
     if (kl & 1) {
       int l = kl >> 1;
       lm_boff[l] = so;
-      lm_free[l] = 1;
       solver2v[so] = 2 * l;
       solver2v[so + 1] = 2 * l + 1;
     } else {
       int p = kl >> 1;
       pose_boff[p] = so;
-      pose_free[p] = 1;
       for (int k = 0; k < 3; k++) solver2v[so + k] = 6 * L + 3 * p + k;
     }
   }
@@ -1469,33 +1548,16 @@ int graph_build_structure(slam_b200_ctx* c) {
       for (size_t k = 0; k < D.tile.items.size(); k++) tile_items_h[k] = make_int2(D.tile.items[k].src, D.tile.items[k].dst);
     }
   }
-  D.t_lists = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - D.t_structure - S.seconds;
-  // ---- upload structure ----
+  D.t_lists = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - D.t_structure -
+              std::max(S.seconds, t_overlapped);
+  dbg("launch lists");
+  // ---- upload the analysis ----
   phase.next("slam_b200/structure upload");
   auto tu0 = std::chrono::steady_clock::now();
-  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
   g_uploads.clear();
   int rc = 0;
-  rc |= upload_vec(c, D.pose_free, pose_free);
-  rc |= upload_vec(c, D.lm_free, lm_free);
   rc |= upload_vec(c, D.pose_boff, pose_boff);
   rc |= upload_vec(c, D.lm_boff, lm_boff);
-  rc |= upload_vec(c, D.el_start, el_start);
-  std::vector<int4> el_rec_h(El);  // lives until flush_uploads below (uploads are deferred)
-  for (int q = 0; q < El; q++) el_rec_h[q] = make_int4(s_pose[q], s_lm[q], s_slot[q], s_flags[q]);
-  rc |= upload_vec(c, D.el_rec, el_rec_h);
-  rc |= upload_vec(c, D.el_info, s_info);
-  rc |= upload_vec(c, D.lm_start, lm_start);
-  rc |= upload_vec(c, D.lm_edges, lm_edges);
-  rc |= upload_vec(c, D.lmo_pose, lmo_pose);
-  rc |= upload_vec(c, D.lmo_info, lmo_info);
-  rc |= upload_vec(c, D.eo_i, g.eo_i);
-  rc |= upload_vec(c, D.eo_j, g.eo_j);
-  rc |= upload_vec(c, D.eo_slot, eo_slot);
-  rc |= upload_vec(c, D.eo_flags, eo_flags);
-  rc |= upload_vec(c, D.po_start, po_start);
-  rc |= upload_vec(c, D.po_list, po_list);
-  rc |= upload_vec(c, D.eo_info, eo_info);
   rc |= upload_vec(c, D.ds.piv0, S.piv0);
   rc |= upload_vec(c, D.ds.npiv, S.npiv);
   rc |= upload_vec(c, D.ds.nupd, S.nupd);
@@ -1522,13 +1584,16 @@ int graph_build_structure(slam_b200_ctx* c) {
     rc |= upload_vec(c, D.tile_items, tile_items_h);
   }
   if (rc) { g_uploads.clear(); return SLAM_B200_E_CUDA; }
+  dbg("upload: allocations + records");
   if (int frc = flush_uploads(c)) return frc;
+  dbg("upload: staging + copies");
   D.structure_version = g.structure_version;
   D.values_version = 0;
   D.R = 0;  // value arrays must be (re)allocated for the new sizes
   D.drop_graph();
   D.assembled = false;
   D.upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tu0).count();
+  D.overlapped_seconds = t_overlapped;
   return D.n;
 }
 

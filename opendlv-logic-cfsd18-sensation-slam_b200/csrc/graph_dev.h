@@ -80,7 +80,7 @@ struct DeviceSystem {
   Symbolic sym;
   std::vector<LevelLaunch> levels;
   std::vector<int> launch_list_host;
-  double upload_seconds = 0, t_structure = 0, t_lists = 0;
+  double upload_seconds = 0, t_structure = 0, t_lists = 0, overlapped_seconds = 0;
   // device structure
   DevBuf<unsigned char> pose_free, lm_free;
   DevBuf<int> pose_boff, lm_boff;  // solver scalar offset or -1

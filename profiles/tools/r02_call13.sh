@@ -1,0 +1,9 @@
+#!/bin/bash
+# cold optimise call: host phases overlapped with the symbolic analysis vs not
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_graph_gpu.py tests/test_slam_host_gpu.py -m gpu -q -x -rxXs > gpurun_out/r02_call13_tests.log 2>&1
+python profiles/tools/e2e_breakdown.py > gpurun_out/r02_call13_e2e_overlap.log 2>&1
+SLAM_B200_NO_HOST_OVERLAP=1 python profiles/tools/e2e_breakdown.py > gpurun_out/r02_call13_e2e_no_overlap.log 2>&1
+SLAM_B200_SYM_DEBUG=1 python profiles/tools/e2e_breakdown.py 2>&1 | grep -v "region [0-9]" | tail -60 > gpurun_out/r02_call13_e2e_debug.log
+nproc > gpurun_out/r02_call13_nproc.log; lscpu | head -20 >> gpurun_out/r02_call13_nproc.log
