@@ -575,7 +575,106 @@ def bench_c5(pkg, torch, args, world, rank, local, synth):
                          "traffic": measured_traffic("c5_assemble_kernels") if world == 1 else None,
                          "algorithmic_bytes_per_launch": bytes_rank, "peak_source": how}}
     ctx.close()
+    if world == 1:
+        try:
+            line["solve"] = bench_c5_solve(pkg, torch, local, synth, graph)
+        except Exception as e:  # noqa: BLE001 -- the assembly line must survive a failing solve leg
+            line["solve"] = {"error": str(e)[:300]}
     return line
+
+
+def bench_c5_solve(pkg, torch, local, synth, graph, iters=3):
+    """SURVEY 8(d) C5 "solve reported separately" (1 GPU): the whole Gauss-Newton iteration of the 1M-pose corridor
+    -- host analysis (ordering + assembly tree; the reference: Eigen analyzePattern with AMD, BASELINE.md 10.8 s),
+    then per iteration assemble + multifrontal LDL^T + solves + update (the reference: factorize 3.39 s + solve
+    0.8 s).  parity_in_run: the 100k-pose corridor optimised by this path and by the CPU oracle (the checker)."""
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = pkg.Context(local, stream=stream.cuda_stream)
+    t0 = time.perf_counter()
+    ctx.graph_load(graph)
+    t1 = time.perf_counter()
+    n = ctx.graph_prepare()
+    t2 = time.perf_counter()
+    st = ctx.graph_stats()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 2)]
+    with torch.cuda.stream(stream):
+        ctx.graph_iterate_async(1)          # warm-up: first launch of every kernel of this topology, graph capture
+        ev[0].record(stream)
+        for k in range(iters):
+            ctx.graph_iterate_async(1)
+            ev[k + 1].record(stream)
+    stream.synchronize()
+    it_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(iters)]
+    rc, chi2 = ctx.graph_finish()
+    ctx.profile_enable(True)
+    with torch.cuda.stream(stream):
+        ctx.graph_iterate_async(2)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    nit = max(prof["iterations"], 1)
+    ctx.close()
+    ms = float(np.median(it_ms))
+    fac_ms = prof["factor_ms"] / nit
+    sol_ms = (prof["factor_ms"] + prof["forward_ms"] + prof["backward_ms"]) / nit
+    bytes_solve = 8.0 * (st["nnz_H_upper"] + 3.0 * st["nnz_L"] + 4.0 * n)       # SURVEY 8(d), for the ordering used
+    hbm, how = peaks()
+    out = {"unknowns": int(n), "fronts": int(st["n_fronts"]), "tree_levels": int(st["n_levels"]), "max_front": int(st["max_front"]),
+           "nnz_L": int(st["nnz_L"]), "factor_flops": float(st["factor_flops"]),
+           "ordering": "nested dissection (BFS level-set separators, regions <= 2,048 vertices) + constrained minimum degree",
+           "host_analysis_s": {"graph_load": t1 - t0, "graph_prepare": t2 - t1, "symbolic": st["symbolic_seconds"],
+                               "structure_pass": st["structure_seconds"], "upload": st["upload_seconds"]},
+           "ms_per_gn_iteration": ms, "ms_all": it_ms, "iterations_done": int(rc),
+           "chi2": [float(v) for v in chi2[-4:]],
+           "phases_ms": {k: prof[k] / nit for k in ("assemble_ms", "factor_ms", "forward_ms", "backward_ms", "update_ms")},
+           "factor_gflops": st["factor_flops"] / (fac_ms * 1e-3) / 1e9 if fac_ms > 0 else None,
+           "solve_GBps": bytes_solve / (sol_ms * 1e-3) / 1e9 if sol_ms > 0 else None,
+           "solve_frac_of_hbm": bytes_solve / (sol_ms * 1e-3) / 1e9 / hbm if sol_ms > 0 else None,
+           "algorithmic_bytes": bytes_solve,
+           "reference_cpu_published": {"analyse_s": 10.8, "factorise_s": 3.39, "solve_s": 0.8,
+                                       "source": "BASELINE.md section 3 (Eigen SimplicialLDLT + AMD on this pattern, other host)"}}
+    # parity on the 30k-pose corridor (see the note below for why not a longer one)
+    try:
+        from oracle import oracle
+        orc = oracle.load("best")
+        g2 = synth.c5_graph(n_poses=30_000, n_pairs=3_000)
+        c2 = pkg.Context(local)
+        c2.graph_load(g2)
+        n_it, chi2_g = c2.graph_optimize(6)
+        pe, le = c2.graph_get_estimates()
+        c2.close()
+        G = orc.graph_from_soa(g2)
+        n_o, chi2_o = G.optimize(6)
+        po, lo = G.estimates(g2)
+        import copy
+        g3 = copy.copy(g2)
+        g3.pose_est, g3.lm_est = pe.copy(), le.copy()
+        chi2_ours_by_cpu = float(orc.graph_from_soa(g3).chi2())
+
+        def increments(p):
+            d = p[1:, :2] - p[:-1, :2]
+            c, s = np.cos(p[:-1, 2]), np.sin(p[:-1, 2])
+            dth = (p[1:, 2] - p[:-1, 2] + np.pi) % (2 * np.pi) - np.pi
+            return np.stack([c * d[:, 0] + s * d[:, 1], -s * d[:, 0] + c * d[:, 1], dth], axis=1)
+        inc = float(np.max(np.abs(increments(pe) - increments(po))))
+        out["parity_in_run"] = {"graph": "30k-pose corridor (9 km), 101,990 unknowns, 6 GN iterations", "iterations": [int(n_it), int(n_o)],
+                                "chi2_gpu": [float(v) for v in chi2_g], "chi2_cpu": [float(v) for v in chi2_o],
+                                "rel_chi2_diff_last_iteration": float(abs(chi2_g[-1] - chi2_o[-1]) / abs(chi2_o[-1])),
+                                "cpu_chi2_of_gpu_estimates_rel_diff": abs(chi2_ours_by_cpu - float(chi2_o[-1])) / abs(float(chi2_o[-1])),
+                                "max_abs_pose_increment_diff_vs_cpu": inc,
+                                "max_abs_pose_diff_vs_cpu": float(np.max(np.abs(pe - po))),
+                                "max_abs_landmark_diff_vs_cpu": float(np.max(np.abs(le - lo))),
+                                "within_1e-6_on_determined_quantities": bool(inc <= 1e-6 and abs(chi2_ours_by_cpu - float(chi2_o[-1])) <= 1e-9 * abs(float(chi2_o[-1]))),
+                                "note": "an open chain held at one end is ill-conditioned along its bending modes: absolute coordinates of "
+                                        "two elimination orders differ by far more than 1e-6 while chi2 and every locally determined quantity "
+                                        "agree (one solve against a refined sparse LU: this path 2.4e-4 relative, the reference's Eigen LDLT "
+                                        "9.5e-4, profiles/r02_corridor_solve_accuracy.md); at 100k poses the reference's own iteration no "
+                                        "longer converges (chi2 rises after the third iteration) while this path's does; the closed-track "
+                                        "configs (C1-C3) are compared on absolute coordinates",
+                                "oracle_kind": orc.kind}
+    except Exception as e:  # noqa: BLE001
+        out["parity_in_run"] = {"error": str(e)[:200]}
+    return out
 
 
 def bench_c3(pkg, torch, args, world, rank, local, synth, replicas, steps=None):

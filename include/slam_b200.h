@@ -54,6 +54,10 @@ typedef struct slam_b200_ctx slam_b200_ctx;
                                       * flight its own idx buffer and reads results after a stream
                                       * synchronisation, an event, or any ordinary launch/copy     */
 
+#define SLAM_B200_ALGO_GRID_BATCHED 3 /* slam_b200_assoc_bulk_frames_dev only: ALGO_GRID with up to eight
+                                      * independent frames per launch (frozen maps), all on the stream of the
+                                      * first frame's context; same results, same rules for the idx buffers   */
+
 /* ------------------------------------------------------------------------------------------------
  * context
  * ---------------------------------------------------------------------------------------------- */
@@ -94,6 +98,15 @@ int slam_b200_map_size(slam_b200_ctx* ctx);
 int slam_b200_map_read(slam_b200_ctx* ctx, int first, int n, double* x, double* y, int32_t* type);
 /* Slam::updateMap (slam.cpp:713-732) with caller-provided coordinates */
 int slam_b200_map_write_xy(slam_b200_ctx* ctx, int first, int n, const double* x, const double* y);
+/* Slam::updateMap (slam.cpp:713-732) on the device: every map cone j whose landmark vertex (id j, slam.cpp:556,610)
+ * is in the graph takes the vertex estimate -- a kernel behind the optimise on the context's stream, no host round
+ * trip -- and the map is copied to a pinned host mirror asynchronously (an event marks the copy).  Falls back to the
+ * host estimates when they are newer than the device's.  Returns the number of cones updated. */
+int slam_b200_map_update_from_graph(slam_b200_ctx* ctx);
+/* The pinned host mirror of the cone map (what sendCones / drawCones read).  Waits for the copy
+ * that refreshes it only, not for other work on the stream; refreshes first if the map has changed since.  The
+ * pointers stay valid until the next call that changes the map.  Returns the number of cones. */
+int slam_b200_map_mirror(slam_b200_ctx* ctx, const double** x, const double** y, const int32_t** type);
 
 /* ------------------------------------------------------------------------------------------------
  * association
@@ -133,8 +146,9 @@ int slam_b200_assoc_bulk_dev(slam_b200_ctx* ctx, const double* cones4xN_dev, int
                              double threshold, int gate, int algo, int32_t* idx_dev);
 /* A train of independent frames (frame f: context ctxs[f] -- the same handle or replicas sharing
  * one stream --, cones_dev[f] = 4 x n[f] doubles, poses[3f..3f+2], idx_dev[f]); one launch each,
- * back to back.  With SLAM_B200_ALGO_GRID_PIPELINED the frames overlap on the device.  Returns
- * n_frames. */
+ * back to back.  With SLAM_B200_ALGO_GRID_PIPELINED the frames overlap on the device; with
+ * SLAM_B200_ALGO_GRID_BATCHED eight frames share one launch (contexts on one device; the work goes to the stream
+ * of ctxs[0]).  Returns n_frames. */
 int slam_b200_assoc_bulk_frames_dev(int n_frames, slam_b200_ctx* const* ctxs, const double* const* cones4xN_dev,
                                     const int* n, const double* poses3, double threshold, int gate, int algo,
                                     int32_t* const* idx_dev);

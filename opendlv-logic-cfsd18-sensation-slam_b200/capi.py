@@ -35,6 +35,10 @@ def lib():
         L = C.CDLL(_build.LIB)
         L.slam_b200_last_error.restype = C.c_char_p
         L.slam_b200_last_error.argtypes = [C.c_void_p]
+        L.slam_b200_map_update_from_graph.argtypes = [C.c_void_p]
+        L.slam_b200_map_mirror.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)),
+                                           C.POINTER(C.POINTER(C.c_int32))]
+        L.slam_b200_warmup.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.slam_b200_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.slam_b200_launch_count.restype = C.c_long
         L.slam_b200_graph_export_system.restype = C.c_long
@@ -169,6 +173,22 @@ class Context:
     def map_write_xy(self, first, x, y):
         x = _f64(x); y = _f64(y)
         self._ck(self.L.slam_b200_map_write_xy(self.h, int(first), len(x), _dp(x), _dp(y)), "map_write_xy")
+
+    def map_update_from_graph(self):
+        """Slam::updateMap on the device: map cone j <- landmark vertex j; returns the cones updated."""
+        return self._ck(self.L.slam_b200_map_update_from_graph(self.h), "map_update_from_graph")
+
+    def map_mirror(self):
+        """Copies of the pinned host mirror of the cone map: x, y, type."""
+        px = C.POINTER(C.c_double)(); py = C.POINTER(C.c_double)(); pt = C.POINTER(C.c_int32)()
+        n = self._ck(self.L.slam_b200_map_mirror(self.h, C.byref(px), C.byref(py), C.byref(pt)), "map_mirror")
+        if n == 0:
+            return np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int32)
+        return (np.ctypeslib.as_array(px, shape=(n,)).copy(), np.ctypeslib.as_array(py, shape=(n,)).copy(),
+                np.ctypeslib.as_array(pt, shape=(n,)).copy())
+
+    def warmup(self, poses_hint=1024, landmarks_hint=340):
+        self._ck(self.L.slam_b200_warmup(self.h, int(poses_hint), int(landmarks_hint)), "warmup")
 
     def map_build_grid(self, cell):
         return self._ck(self.L.slam_b200_map_build_grid(self.h, float(cell)), "map_build_grid")

@@ -356,6 +356,18 @@ assoc_localize_frame_kernel(double* in, int n, double thr, const double* map_x,
   mailbox_publish(mb, outi, n + 8, outd, 5 * n);
 }
 
+// Slam::updateMap on the device (slam.cpp:713-732): map cone j <- estimate of its landmark vertex.
+// est = x[P] | y[P] | theta[P] | lx[L] | ly[L] (graph_dev.h)
+__global__ void map_from_graph_kernel(const double* __restrict__ est, int P, int L, const int* __restrict__ lm_of_map,
+                                      double* map_x, double* map_y, int M) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int l = lm_of_map[j];
+  if (l < 0) return;
+  map_x[j] = est[3 * (size_t)P + l];
+  map_y[j] = est[3 * (size_t)P + L + l];
+}
+
 // conversion only (slam_b200_cones_to_global)
 __global__ void convert_kernel(const double* __restrict__ in, int n, double* __restrict__ g3,
                                double* __restrict__ l3) {
@@ -517,14 +529,10 @@ constexpr int GRID_BATCH = 8;  // records fetched before any is tested
 // against the frozen map are launched with programmatic stream serialisation and every CTA
 // releases the next frame's launch at once (griddepcontrol.launch_dependents, no
 // griddepcontrol.wait: the frames are independent); successive frames overlap on one stream.
-template <int GATE, bool EARLY>
-__global__ void __launch_bounds__(BULK_THREADS)
-assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, double thr2x, GridParams gp,
-                       const int* __restrict__ cell_start, const GridRec* __restrict__ rec,
-                       int* __restrict__ idx) {
-  if (EARLY) asm volatile("griddepcontrol.launch_dependents;");
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+template <int GATE>
+__device__ __forceinline__ void grid_match_one(const double* __restrict__ cones, int i, const PoseTrig& pt, double thr2x,
+                                               const GridParams& gp, const int* __restrict__ cell_start,
+                                               const GridRec* __restrict__ rec, int* __restrict__ idx) {
   double gx, gy, ot;
   load_obs(cones, i, pt, gx, gy, ot);
   int oti = (int)ot;
@@ -568,6 +576,43 @@ assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, dou
     }
   }
   idx[i] = best == 0x7fffffff ? -1 : best;
+}
+
+template <int GATE, bool EARLY>
+__global__ void __launch_bounds__(BULK_THREADS)
+assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, double thr2x, GridParams gp,
+                       const int* __restrict__ cell_start, const GridRec* __restrict__ rec,
+                       int* __restrict__ idx) {
+  if (EARLY) asm volatile("griddepcontrol.launch_dependents;");
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  grid_match_one<GATE>(cones, i, pt, thr2x, gp, cell_start, rec, idx);
+}
+
+// SLAM_B200_ALGO_GRID_BATCHED: up to BATCH_FRAMES independent frames against frozen maps in ONE launch
+// (blockIdx.y = frame).  A single frame is one sub-wave of threads on a three-deep dependent-load chain and cannot
+// fill the memory system however it is written; several frames in one grid can, without
+// the per-launch cost the pipelined train still pays for every frame (about 2 us each: what caps a rank that holds
+// an eighth of the observations).
+constexpr int BATCH_FRAMES = 8;
+struct BatchFrame {
+  const double* cones;
+  const int* cell_start;
+  const GridRec* rec;
+  int* idx;
+  PoseTrig pt;
+  GridParams gp;
+  int n;
+};
+struct BatchParams { BatchFrame f[BATCH_FRAMES]; };
+
+template <int GATE>
+__global__ void __launch_bounds__(BULK_THREADS)
+assoc_bulk_grid_batched_kernel(const __grid_constant__ BatchParams bp, double thr2x) {
+  const BatchFrame& F = bp.f[blockIdx.y];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F.n) return;
+  grid_match_one<GATE>(F.cones, i, F.pt, thr2x, F.gp, F.cell_start, F.rec, F.idx);
 }
 
 // smallest double s with sqrt(s) >= thr  (host; IEEE sqrt on both sides)
@@ -744,6 +789,84 @@ int slam_b200_map_write_xy(slam_b200_ctx* c, int first, int n, const double* x, 
   SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   c->map_version++;
   return n;
+} SLAM_ABI_CATCH(c)
+
+// enqueues the copy of the device map into the pinned mirror and records the event readers wait for
+static int mirror_refresh_async(slam_b200_ctx* c) {
+  const size_t M = (size_t)c->map_n;
+  if (M > c->mirror_cap) {
+    if (c->mirror_event) SLAM_CUDA_TRY(c, cudaEventSynchronize(c->mirror_event));
+    size_t cap = c->mirror_cap ? c->mirror_cap : 512;
+    while (cap < M) cap *= 2;
+    SLAM_CUDA_TRY(c, c->mirror_xy.reserve(2 * cap));
+    SLAM_CUDA_TRY(c, c->mirror_type.reserve(cap));
+    c->mirror_cap = cap;
+  }
+  if (!c->mirror_event) SLAM_CUDA_TRY(c, cudaEventCreateWithFlags(&c->mirror_event, cudaEventDisableTiming));
+  if (M) {
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->mirror_xy.p, c->map_x.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->mirror_xy.p + c->mirror_cap, c->map_y.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->mirror_type.p, c->map_type.p, sizeof(int) * M, cudaMemcpyDeviceToHost, c->stream));
+  }
+  SLAM_CUDA_TRY(c, cudaEventRecord(c->mirror_event, c->stream));
+  c->mirror_n = (int)M;
+  c->mirror_version = c->map_version;
+  return 0;
+}
+
+int slam_b200_map_update_from_graph(slam_b200_ctx* c) try {
+  NvtxRange nvtx_range("slam_b200/map_update_from_graph");
+  if (!c) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  const int M = c->map_n;
+  if (M == 0) return 0;
+  HostGraph& g = c->g;
+  // landmark behind every map cone: the reference numbers landmark vertices by map index (slam.cpp:556,610)
+  std::vector<int> lm(M, -1);
+  int found = 0;
+  for (int j = 0; j < M; j++) {
+    auto it = g.id2v.find(j);
+    if (it != g.id2v.end() && (it->second & 1)) { lm[j] = it->second >> 1; found++; }
+  }
+  if (found == 0) return 0;
+  double *est_dev = nullptr;
+  int P = 0, L = 0;
+  if (graph_device_estimates(c, &est_dev, &P, &L)) {
+    // device estimates are current (the usual case: right after an optimise): cone <- vertex on the device
+    SLAM_CUDA_TRY(c, c->lm_of_map.exact((size_t)M));
+    SLAM_CUDA_TRY(c, c->pin_i.reserve((size_t)M));
+    std::memcpy(c->pin_i.p, lm.data(), sizeof(int) * (size_t)M);
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->lm_of_map.p, c->pin_i.p, sizeof(int) * (size_t)M, cudaMemcpyHostToDevice, c->stream));
+    map_from_graph_kernel<<<(M + 255) / 256, 256, 0, c->stream>>>(est_dev, P, L, c->lm_of_map.p, c->map_x.p, c->map_y.p, M);
+    c->launches++;
+    SLAM_CUDA_TRY(c, cudaGetLastError());
+  } else {
+    // the host graph holds newer values than the device (set_values / add_* since the last optimise): write them
+    std::vector<double> x(M), y(M);
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(x.data(), c->map_x.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(y.data(), c->map_y.p, sizeof(double) * M, cudaMemcpyDeviceToHost, c->stream));
+    SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < M; j++)
+      if (lm[j] >= 0) { x[j] = g.lm_est[2 * (size_t)lm[j]]; y[j] = g.lm_est[2 * (size_t)lm[j] + 1]; }
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->map_x.p, x.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+    SLAM_CUDA_TRY(c, cudaMemcpyAsync(c->map_y.p, y.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+    SLAM_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
+  c->map_version++;
+  if (int rc = mirror_refresh_async(c)) return rc;
+  return found;
+} SLAM_ABI_CATCH(c)
+
+int slam_b200_map_mirror(slam_b200_ctx* c, const double** x, const double** y, const int32_t** type) try {
+  if (!c) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (c->mirror_version != c->map_version || c->mirror_n != c->map_n)
+    if (int rc = mirror_refresh_async(c)) return rc;
+  if (c->mirror_event) SLAM_CUDA_TRY(c, cudaEventSynchronize(c->mirror_event));
+  if (x) *x = c->mirror_xy.p;
+  if (y) *y = c->mirror_xy.p + c->mirror_cap;
+  if (type) *type = c->mirror_type.p;
+  return c->mirror_n;
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_assoc_map_frame(slam_b200_ctx* c, const double* cones, int n, const double pose[3],
@@ -991,14 +1114,60 @@ int slam_b200_assoc_bulk_dev(slam_b200_ctx* c, const double* cones_dev, int n, c
 
 int slam_b200_assoc_bulk_frames_dev(int n_frames, slam_b200_ctx* const* ctxs, const double* const* cones_dev,
                                     const int* n, const double* poses, double thr, int gate, int algo,
-                                    int32_t* const* idx_dev) {
+                                    int32_t* const* idx_dev) try {
   if (n_frames < 0 || (n_frames > 0 && (!ctxs || !cones_dev || !n || !poses || !idx_dev))) return SLAM_B200_E_ARG;
-  for (int f = 0; f < n_frames; f++) {
-    int rc = slam_b200_assoc_bulk_dev(ctxs[f], cones_dev[f], n[f], poses + 3 * (size_t)f, thr, gate, algo, idx_dev[f]);
-    if (rc < 0) return rc;
+  if (algo != SLAM_B200_ALGO_GRID_BATCHED) {
+    for (int f = 0; f < n_frames; f++) {
+      int rc = slam_b200_assoc_bulk_dev(ctxs[f], cones_dev[f], n[f], poses + 3 * (size_t)f, thr, gate, algo, idx_dev[f]);
+      if (rc < 0) return rc;
+    }
+    return n_frames;
+  }
+  if (gate != SLAM_B200_GATE_MAPPING && gate != SLAM_B200_GATE_LOCALIZER) return SLAM_B200_E_ARG;
+  if (n_frames == 0) return 0;
+  slam_b200_ctx* c0 = ctxs[0];
+  if (!c0) return SLAM_B200_E_ARG;
+  if (ctx_set_device(c0)) return SLAM_B200_E_CUDA;
+  const double thr2x = sqrt_gate_threshold(thr);
+  for (int f0 = 0; f0 < n_frames; f0 += BATCH_FRAMES) {
+    BatchParams bp;
+    std::memset(&bp, 0, sizeof(bp));
+    int nb = 0, nmax = 0;
+    for (int f = f0; f < n_frames && f < f0 + BATCH_FRAMES; f++) {
+      slam_b200_ctx* c = ctxs[f];
+      if (!c || c->device != c0->device || n[f] < 0 || (n[f] > 0 && (!cones_dev[f] || !idx_dev[f]))) return SLAM_B200_E_ARG;
+      if (n[f] == 0) continue;
+      if (c->map_n == 0 || !(thr > 0)) {  // nothing can match
+        SLAM_CUDA_TRY(c0, cudaMemsetAsync(idx_dev[f], 0xff, sizeof(int) * (size_t)n[f], c0->stream));
+        continue;
+      }
+      if (c->grid_map_version != c->map_version || !(c->grid_cell >= thr)) {
+        int rc = slam_b200_map_build_grid(c, thr);  // on c's own stream, synchronised before it returns
+        if (rc < 0) return rc;
+      }
+      BatchFrame& F = bp.f[nb++];
+      const double* pose = poses + 3 * (size_t)f;
+      F.cones = cones_dev[f];
+      F.cell_start = c->grid_cell_start.p;
+      F.rec = c->grid_rec.p;
+      F.idx = idx_dev[f];
+      F.pt = PoseTrig{pose[0], pose[1], std::cos(pose[2]), std::sin(pose[2])};
+      F.gp.x0 = c->grid_x0; F.gp.y0 = c->grid_y0; F.gp.nx = c->grid_nx; F.gp.ny = c->grid_ny;
+      F.gp.inv = c->grid_inv; F.gp.h = c->grid_h;
+      F.n = n[f];
+      nmax = std::max(nmax, n[f]);
+    }
+    if (nb == 0) continue;
+    dim3 grid((nmax + BULK_THREADS - 1) / BULK_THREADS, nb);
+    if (gate == SLAM_B200_GATE_MAPPING)
+      assoc_bulk_grid_batched_kernel<SLAM_B200_GATE_MAPPING><<<grid, BULK_THREADS, 0, c0->stream>>>(bp, thr2x);
+    else
+      assoc_bulk_grid_batched_kernel<SLAM_B200_GATE_LOCALIZER><<<grid, BULK_THREADS, 0, c0->stream>>>(bp, thr2x);
+    c0->launches++;
+    SLAM_CUDA_TRY(c0, cudaGetLastError());
   }
   return n_frames;
-}
+} catch (...) { return SLAM_B200_E_STATE; }
 
 int slam_b200_assoc_bulk(slam_b200_ctx* c, const double* cones, int n, const double pose[3], double thr,
                          int gate, int algo, int32_t* idx) try {

@@ -155,6 +155,9 @@ int slam_b200_destroy(slam_b200_ctx* c) {
   c->grid_bbox.release(); c->grid_tmp.release();
   c->frame_in.release(); c->frame_outd.release(); c->frame_outi.release();
   c->pin_d.release(); c->pin_i.release(); c->pin_stage.release();
+  c->mirror_xy.release(); c->mirror_type.release(); c->lm_of_map.release();
+  if (c->mirror_event) cudaEventDestroy(c->mirror_event);
+  c->mirror_event = nullptr;
   if (c->mbox_h) cudaFreeHost(c->mbox_h);
   c->mbox_h = c->mbox_d = nullptr;
   for (cudaStream_t& a : c->aux_stream) if (a) { cudaStreamDestroy(a); a = nullptr; }

@@ -205,6 +205,16 @@ struct slam_b200_ctx {
   int grid_nx = 0, grid_ny = 0;
   uint64_t grid_map_version = 0;
 
+  // pinned host mirror of the cone map, refreshed by an asynchronous copy behind an event (assoc.cu:
+  // slam_b200_map_update_from_graph / slam_b200_map_mirror): readers wait for that copy only, never for the stream
+  PinBuf<double> mirror_xy;      // x[cap] | y[cap]
+  PinBuf<int> mirror_type;
+  size_t mirror_cap = 0;         // cones the two buffers are laid out for
+  int mirror_n = 0;              // cones of the last refresh
+  uint64_t mirror_version = 0;   // map_version of the last refresh
+  cudaEvent_t mirror_event = nullptr;
+  DevBuf<int> lm_of_map;         // landmark (local index) behind every map cone, -1 = none
+
   // ---- frame staging ----
   DevBuf<double> frame_in;       // 4n + 3
   DevBuf<double> frame_outd;     // 5n doubles: z2, g3
@@ -230,3 +240,6 @@ struct slam_b200_ctx {
 
 int ctx_set_device(slam_b200_ctx* c);
 void graph_release(slam_b200_ctx* c);  // graph.cu
+// graph.cu: device estimates of replica 0 (x[P] | y[P] | theta[P] | lx[L] | ly[L]) if they are current, i.e. the
+// host graph has not changed since the device last wrote them back; false otherwise
+bool graph_device_estimates(slam_b200_ctx* c, double** est, int* P, int* L);

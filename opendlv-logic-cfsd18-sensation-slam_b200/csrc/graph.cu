@@ -1684,6 +1684,18 @@ void xchg_release(DeviceSystem& D) {
   X = PeerExchange();
 }
 
+bool graph_device_estimates(slam_b200_ctx* c, double** est, int* P, int* L) {
+  if (!c->sys) return false;
+  DeviceSystem& D = *c->sys;
+  if (D.R != 1 || !D.est.p || D.structure_version != c->g.structure_version || D.values_version != c->g.values_version ||
+      D.P != c->g.P() || D.L != c->g.L())
+    return false;
+  *est = D.est.p;
+  *P = D.P;
+  *L = D.L;
+  return true;
+}
+
 void graph_release(slam_b200_ctx* c) {
   if (!c->sys) return;
   DeviceSystem& D = *c->sys;

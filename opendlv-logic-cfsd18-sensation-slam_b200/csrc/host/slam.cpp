@@ -224,20 +224,25 @@ void Slam::optimizeWindow() {
   optimizeGraph();
 }
 
-// slam.cpp:713-732: landmark estimates -> map (host mirror and device map)
+// slam.cpp:713-732: landmark estimates -> map.  The device map takes them on the device, behind the optimise on the
+// back end's stream; the host-side m_map follows from the pinned mirror the back end refreshes asynchronously, and
+// only when somebody reads it (the frame loop does not wait for a device -> host copy).
 void Slam::updateMap() {
-  const size_t M = m_map.size();
-  std::vector<double> x(M), y(M);
-  for (size_t j = 0; j < M; j++) {
-    double e[3];
-    if (slam_b200_graph_get_vertex(m_ctx, (int)j, e) == 2) {
-      m_map[j].setX(e[0]);
-      m_map[j].setY(e[1]);
-    }
-    x[j] = m_map[j].getX();
-    y[j] = m_map[j].getY();
+  check(m_ctx, slam_b200_map_update_from_graph(m_ctx), "map_update_from_graph");
+  m_mapMirrorPending = true;
+}
+
+// called with m_mapMutex held, by everything that hands m_map's coordinates out
+void Slam::refreshMapFromMirror() {
+  if (!m_mapMirrorPending) return;
+  const double *x = nullptr, *y = nullptr;
+  const int n = slam_b200_map_mirror(m_ctx, &x, &y, nullptr);
+  check(m_ctx, n, "map_mirror");
+  for (size_t j = 0; j < m_map.size() && j < (size_t)n; j++) {
+    m_map[j].setX(x[j]);
+    m_map[j].setY(y[j]);
   }
-  if (M) check(m_ctx, slam_b200_map_write_xy(m_ctx, 0, (int)M, x.data(), y.data()), "map_write_xy");
+  m_mapMirrorPending = false;
 }
 
 // slam.cpp:416-422
@@ -325,6 +330,7 @@ void Slam::sendCones() {
     pose = m_sendPose;
   }
   std::lock_guard<std::mutex> lockMap(m_mapMutex);
+  refreshMapFromMirror();
   onSendCones(m_map, m_currentConeIndex, pose);
 }
 
@@ -338,6 +344,7 @@ std::vector<ConePacketEntry> Slam::buildConePacket() {
     pose = m_sendPose;
   }
   std::lock_guard<std::mutex> lockMap(m_mapMutex);
+  refreshMapFromMirror();
   std::vector<ConePacketEntry> out;
   const size_t size = m_map.size();
   for (uint32_t i = 0; i < m_conesPerPacket; i++) {
@@ -363,6 +370,7 @@ std::vector<Vector3d> Slam::drawPoses() {
 
 std::vector<Cone> Slam::drawCones() {
   std::lock_guard<std::mutex> lock(m_mapMutex);
+  refreshMapFromMirror();
   return m_map;
 }
 

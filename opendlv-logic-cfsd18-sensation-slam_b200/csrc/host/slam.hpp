@@ -96,6 +96,7 @@ class Slam {
   void addConeMeasurement(Cone cone, const double xyMeasurement[2]);
   void addConeToGraph(Cone cone, const double xyMeasurement[2]);
   void updateMap();
+  void refreshMapFromMirror();
   void sendCones();
   void sendPose();
 
@@ -120,6 +121,7 @@ class Slam {
   bool m_sendConeData = false;
   bool m_sendPoseData = false;
   bool m_loopClosing = false;
+  bool m_mapMirrorPending = false;  // m_map's coordinates are behind the back end's pinned mirror (guarded by m_mapMutex)
   // read without a lock by drawCurrentPose() on the viewer thread (slam.cpp:769, as in the reference) while a
   // frame thread sets it under map + optimizer mutex (632): atomic here, a plain bool there
   std::atomic<bool> m_loopClosingComplete{false};

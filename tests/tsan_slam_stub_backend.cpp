@@ -35,6 +35,15 @@ int slam_b200_graph_get_vertex(slam_b200_ctx*, int id, double out[3]) {
   return id < 1000 ? 2 : 3;
 }
 int slam_b200_map_write_xy(slam_b200_ctx*, int, int n, const double*, const double*) { return n; }
+int slam_b200_map_update_from_graph(slam_b200_ctx*) { return 0; }
+int slam_b200_map_mirror(slam_b200_ctx*, const double** x, const double** y, const int32_t** t) {
+  static const double zero = 0;
+  static const int32_t zt = 0;
+  if (x) *x = &zero;
+  if (y) *y = &zero;
+  if (t) *t = &zt;
+  return 0;
+}
 int slam_b200_cones_to_global(slam_b200_ctx*, const double*, int n, const double*, double* g3, double* l3) {
   if (g3) std::memset(g3, 0, sizeof(double) * 3 * (size_t)n);
   if (l3) std::memset(l3, 0, sizeof(double) * 3 * (size_t)n);
