@@ -333,7 +333,7 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
     sampler = ClockSampler(local)
     sampler.start()
     tw0 = time.time()
-    for name, algo in (("train", pkg.capi.ALGO_GRID), ("pipelined", pkg.capi.ALGO_GRID_PIPELINED)):
+    for name, algo in (("train", pkg.capi.ALGO_GRID), ("batched", pkg.capi.ALGO_GRID_BATCHED), ("pipelined", pkg.capi.ALGO_GRID_PIPELINED)):
         launch = pkg.capi.Context.assoc_bulk_frames_dev([ctxs[q] for q in order], [d_ins[q].data_ptr() for q in order],
                                                         [n] * K, np.tile(field.pose, (K, 1)), THR, pkg.capi.GATE_MAPPING, algo,
                                                         [d_outs[q].data_ptr() for q in order])
@@ -373,21 +373,34 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
     # the map cells near its own observations, not the whole replicated map), so the job-level figure
     # is frame bytes / frame time against world x the per-GPU peak; per rank that is bytes / world.
     bytes_alg = (36.0 * n_total + 20.0 * M) / world
-    g, tp = out["grid"], trains["pipelined"]
+    g = out["grid"]
+    # `value`: the faster of the two multi-frame schedules (frames overlapped by programmatic dependent launch, or
+    # eight frames per launch); a rank that holds 1/N of the observations is launch-bound with the former
+    best_train = "pipelined" if trains["pipelined"]["assoc_per_s"] >= trains["batched"]["assoc_per_s"] else "batched"
+    tp = trains[best_train]
 
     def roof(ms_per_frame):
         return bytes_alg / (ms_per_frame * 1e-3) / 1e9
     res = dict(
         workload=f"c4: {M} map cones, {n_total} observations/frame, match-only, mapping gate", value=tp["assoc_per_s"],
         unit="assoc/s", ms_per_frame=tp["ms_per_frame"], matched_fraction=g["matched"] / max(n, 1),
-        timing=f"median of 7 trains of {K} frames launched back to back with SLAM_B200_ALGO_GRID_PIPELINED, one event pair "
+        schedule=best_train,
+        train_pipelined={"ms_per_frame": trains["pipelined"]["ms_per_frame"], "assoc_per_s": trains["pipelined"]["assoc_per_s"]},
+        timing=f"median of 7 trains of {K} frames launched back to back ({best_train}: SLAM_B200_ALGO_GRID_"
+               f"{best_train.upper()}), one event pair "
                f"per train, L2 flushed before each train; the train rotates through {ASSOC_COPIES} replicas of map index "
                f"+ frame ({ASSOC_COPIES} x {(32.0 * M + 4.0 * M * 1.75 + 36.0 * n) / 1e6:.0f} MB > L2)",
         single_launch={"ms_per_frame": g["ms_per_frame"], "assoc_per_s": g["assoc_per_s"],
                        "note": "one launch between two events after an L2 flush (includes the event/launch floor, "
                                "~5 us for an empty kernel)"},
         train_unpipelined={"ms_per_frame": trains["train"]["ms_per_frame"], "assoc_per_s": trains["train"]["assoc_per_s"]},
-        identical_to_single_launch=bool(tp["identical_to_single_launch"] and trains["train"]["identical_to_single_launch"]),
+        train_batched={"ms_per_frame": trains["batched"]["ms_per_frame"], "assoc_per_s": trains["batched"]["assoc_per_s"],
+                       "frac_of_hbm": roof(trains["batched"]["ms_per_frame"]) / hbm,
+                       "identical_to_single_launch": trains["batched"]["identical_to_single_launch"],
+                       "note": "SLAM_B200_ALGO_GRID_BATCHED: eight frames per launch (blockIdx.y = frame), no programmatic "
+                               "dependent launch; the same train, timed the same way"},
+        identical_to_single_launch=bool(tp["identical_to_single_launch"] and trains["train"]["identical_to_single_launch"]
+                                        and trains["batched"]["identical_to_single_launch"]),
         e2e={"value": n_total / e2e_s, "unit": "assoc/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 4 * n},
         roofline={"bound": "hbm", "kernel": "assoc_bulk_grid_kernel", "achieved": roof(tp["ms_per_frame"]),
                   "peak": hbm, "unit": "GB/s", "frac": roof(tp["ms_per_frame"]) / hbm,
@@ -738,7 +751,72 @@ def bench_c3(pkg, torch, args, world, rank, local, synth, replicas, steps=None):
             "phases_ms_per_iteration": {k: prof[k] / nit for k in ("assemble_ms", "factor_ms", "forward_ms", "backward_ms", "update_ms")},
             "parity_in_run": parity}
     r["ctx"].close()
+    if rank == 0:
+        try:
+            line["whole_drives"] = bench_c3_drives(pkg, local, synth, max(64, min(512, replicas // world)))
+        except Exception as e:  # noqa: BLE001
+            line["whole_drives"] = {"error": str(e)[:300]}
     return line
+
+
+def bench_c3_drives(pkg, local, synth, R):
+    """SURVEY 8(d) config 3, 'optional second variant': whole Monte-Carlo DRIVES per replica, association included --
+    one thread block per replica runs the mapping phase of performSLAM over the whole lap, frame state on the device
+    (slam_b200_drive_replicas).  R replicas of the C1 drive with their own observation / pose noise; two of them are
+    replayed through the oracle (the checker) frame by frame."""
+    d = synth.trackdrive(1)
+    F = len(d.frames)
+    nmax = max(int(np.asarray(fr).reshape(4, -1, order="F").shape[1]) for fr in d.frames)
+    base = np.zeros((F, 4, nmax)); ncols = np.zeros(F, dtype=np.int32)
+    for f, fr in enumerate(d.frames):
+        fr = np.asarray(fr, dtype=np.float64).reshape(4, -1, order="F")
+        base[f, :, :fr.shape[1]] = fr
+        ncols[f] = fr.shape[1]
+    rng = np.random.default_rng(18)
+    frames = np.repeat(base[None], R, axis=0)
+    frames[:, :, 0, :] = (frames[:, :, 0, :] + rng.normal(0, 0.05, (R, F, nmax))).astype(np.float32)   # wire type: float
+    frames[:, :, 2, :] = (frames[:, :, 2, :] + rng.normal(0, 0.01, (R, F, nmax))).astype(np.float32)
+    mask = np.arange(nmax)[None, :] < ncols[:, None]
+    frames *= mask[None, :, None, :]
+    poses = np.repeat(np.asarray(d.poses_noisy, dtype=np.float64)[None], R, axis=0) + rng.normal(0, 0.01, (R, F, 3)) * np.array([1, 1, 0.1])
+    nc = np.repeat(ncols[None], R, axis=0)
+    ctx = pkg.Context(local)
+    ctx.drive_replicas(frames[:8], nc[:8], poses[:8], THR, 50.0)          # warm-up: kernel load
+    t0 = time.perf_counter()
+    out = ctx.drive_replicas(frames, nc, poses, THR, 50.0)
+    wall = time.perf_counter() - t0
+    ctx.close()
+    run = out["scalars"][:, :, 5] >= 0
+    frames_run = int(run.sum())
+    obs_run = int((nc * run).sum())
+    ks = out["kernel_ms"] * 1e-3
+    res = {"replicas": R, "frames_per_replica": F, "frames_run": frames_run, "observations": obs_run,
+           "kernel_ms": out["kernel_ms"], "replica_frames_per_s": frames_run / ks, "assoc_per_s": obs_run / ks,
+           "us_per_frame_per_replica_stream": ks / F * 1e6,
+           "wall_s_with_packing_and_copies": wall,
+           "loop_closed_at": {"min": int(out["closed_at"].min()), "median": int(np.median(out["closed_at"])), "max": int(out["closed_at"].max())},
+           "map_cones": {"min": int(out["map_n"].min()), "max": int(out["map_n"].max())},
+           "what": "one thread block per replica, the body of the single-frame mapping kernel looped over the lap; a replica "
+                   "stops at the frame that closes its loop"}
+    try:
+        from oracle import oracle
+        orc = oracle.load("best")
+        same = True
+        for r in (0, R - 1):
+            mx = np.zeros(512); my = np.zeros(512); mt = np.zeros(512, dtype=np.int32)
+            M = cci = lc = 0
+            for f in range(F):
+                n = int(nc[r, f])
+                if lc or n == 0:
+                    continue
+                o = orc.assoc_map_frame(frames[r, f, :, :n], poses[r, f], THR, 50.0, mx, my, mt, M, cci, lc)
+                same = same and np.array_equal(out["idx"][r, f, :n], o["idx"]) and np.array_equal(out["status"][r, f, :n], o["status"])
+                M, cci, lc = o["M"], o["cci"], o["loop_closing"]
+            same = same and int(out["map_n"][r]) == M
+        res["parity_in_run"] = {"replicas_checked_vs_cpu": [0, R - 1], "identical_association_records_and_map_size": bool(same)}
+    except Exception as e:  # noqa: BLE001
+        res["parity_in_run"] = {"error": str(e)[:200]}
+    return res
 
 
 def cpu_baseline_gn(graph, kind="best"):
@@ -881,7 +959,8 @@ def run_ours(args):
                 "warmup": 3, "ms_per_step": a["ms_per_frame"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": a["workload"]},
                 "e2e": a["e2e"], "roofline": a["roofline"], "brute_force": a["brute_force"], "gpu_launches": args.steps,
-                "timing": a["timing"], "single_launch": a["single_launch"], "train_unpipelined": a["train_unpipelined"],
+                "timing": a["timing"], "single_launch": a["single_launch"], "train_unpipelined": a["train_unpipelined"], "train_batched": a["train_batched"],
+                "train_pipelined": a["train_pipelined"], "schedule": a["schedule"],
                 "identical_to_single_launch": a["identical_to_single_launch"], "clocks": a["clocks"]}
     if rank == 0:
         print(json.dumps(line))

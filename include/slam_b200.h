@@ -136,6 +136,20 @@ int slam_b200_assoc_localize_frame(slam_b200_ctx* ctx, const double* cones4xN, i
                                    double threshold, uint32_t* current_cone_index, int32_t* idx,
                                    double* g3, int32_t* n_reobserved, int32_t* send_cone_data);
 
+/* Whole Monte-Carlo drives, one replica per thread block: the mapping phase of
+ * Slam::performSLAM (slam.cpp:298-338 -> addConesToMap 552-623) for n_frames frames of each of n_replicas replicas,
+ * frame state carried on the device, every replica with its own map of at most `cap` cones.  A replica stops at the
+ * frame that closes its loop (closed_at[r], -1 = never, -2 = map or frame capacity exceeded).
+ *   frames4: [R][F][4 * nmax] column-major cone columns, ncols: [R][F] columns of every frame (<= nmax),
+ *   poses3: [R][F][3];  records: [R][F][2 * nmax + 8] int32 = the 8 frame scalars (first_cone_created,
+ *   loop_closing_obs, map_n, current_cone_index, loop_closing, n_reobserved (-1 = frame not run), -, -) followed by
+ *   idx[n] and status[n] exactly as slam_b200_assoc_map_frame returns them;  map_x / map_y / map_type: [R][cap]
+ *   (may be NULL), map_n: [R].  Returns n_replicas. */
+int slam_b200_drive_replicas(slam_b200_ctx* ctx, int n_replicas, int n_frames, int nmax, const double* frames4,
+                             const int32_t* ncols, const double* poses3, double same_cone_threshold,
+                             double cone_mapping_threshold, int cap, int32_t* records, double* map_x, double* map_y,
+                             int32_t* map_type, int32_t* map_n, int32_t* closed_at, double* kernel_ms);
+
 /* Match-only association of a large observation batch against the frozen device map (phase 1 of
  * addConesToMap / the localizer loop; BASELINE config "large cone field").  gate, algo: see above.
  * Host variant copies cones in and idx out; _dev variant works on device pointers (cones4xN_dev:

@@ -18,7 +18,7 @@ c_ip = C.POINTER(C.c_int32)
 E_CUDA, E_ARG, E_STATE = -100, -101, -102
 ASSOC_MATCHED, ASSOC_NEW, ASSOC_NONE, ASSOC_SKIPPED = 0, 1, 2, 3
 GATE_MAPPING, GATE_LOCALIZER = 0, 1
-ALGO_BRUTE, ALGO_GRID, ALGO_GRID_PIPELINED = 0, 1, 2
+ALGO_BRUTE, ALGO_GRID, ALGO_GRID_PIPELINED, ALGO_GRID_BATCHED = 0, 1, 2, 3
 
 _lib = None
 
@@ -39,6 +39,8 @@ def lib():
         L.slam_b200_map_mirror.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)),
                                            C.POINTER(C.POINTER(C.c_int32))]
         L.slam_b200_warmup.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.slam_b200_drive_replicas.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_double, C.c_double,
+                                               C.c_int, c_ip, c_dp, c_dp, c_ip, c_ip, c_ip, C.POINTER(C.c_double)]
         L.slam_b200_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
         L.slam_b200_launch_count.restype = C.c_long
         L.slam_b200_graph_export_system.restype = C.c_long
@@ -189,6 +191,31 @@ class Context:
 
     def warmup(self, poses_hint=1024, landmarks_hint=340):
         self._ck(self.L.slam_b200_warmup(self.h, int(poses_hint), int(landmarks_hint)), "warmup")
+
+    def drive_replicas(self, frames, ncols, poses, thr, map_thr, cap=512):
+        """Whole drives per replica (slam_b200_drive_replicas).  frames: (R, F, 4, nmax) with the columns of every
+        frame in [..., :n]; ncols: (R, F); poses: (R, F, 3).  Returns a dict: scalars (R, F, 8), idx / status (R, F, nmax),
+        map_x / map_y / map_type (R, cap), map_n (R,), closed_at (R,), kernel_ms."""
+        frames = np.asarray(frames, dtype=np.float64)
+        R, F, four, nmax = frames.shape
+        assert four == 4
+        packed = np.ascontiguousarray(np.transpose(frames, (0, 1, 3, 2)))     # (R, F, nmax, 4): column-major 4 x nmax
+        ncols = np.ascontiguousarray(ncols, dtype=np.int32); poses = np.ascontiguousarray(poses, dtype=np.float64)
+        rec = np.zeros((R, F, 2 * nmax + 8), dtype=np.int32)
+        mx = np.zeros((R, cap)); my = np.zeros((R, cap)); mt = np.zeros((R, cap), dtype=np.int32)
+        mn = np.zeros(R, dtype=np.int32); closed = np.zeros(R, dtype=np.int32)
+        ms = C.c_double(0)
+        self._ck(self.L.slam_b200_drive_replicas(self.h, R, F, nmax, _dp(packed), _ip(ncols), _dp(poses), float(thr),
+                                                 float(map_thr), int(cap), _ip(rec), _dp(mx), _dp(my), _ip(mt), _ip(mn),
+                                                 _ip(closed), C.byref(ms)), "drive_replicas")
+        idx = np.full((R, F, nmax), -1, dtype=np.int32); status = np.zeros((R, F, nmax), dtype=np.int32)
+        for r in range(R):
+            for f in range(F):
+                n = min(int(ncols[r, f]), nmax)
+                idx[r, f, :n] = rec[r, f, 8:8 + n]
+                status[r, f, :n] = rec[r, f, 8 + n:8 + 2 * n]
+        return dict(scalars=rec[:, :, :8].copy(), idx=idx, status=status, map_x=mx, map_y=my, map_type=mt, map_n=mn,
+                    closed_at=closed, kernel_ms=ms.value)
 
     def map_build_grid(self, cell):
         return self._ck(self.L.slam_b200_map_build_grid(self.h, float(cell)), "map_build_grid")

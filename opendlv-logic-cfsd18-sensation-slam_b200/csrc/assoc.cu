@@ -174,13 +174,9 @@ __device__ void frame_first_fit(const double* __restrict__ gx, const double* __r
 }
 
 // Mapping-phase frame (slam.cpp:552-623).  in: 4n frame doubles then pose(3).
-__global__ void __launch_bounds__(FRAME_THREADS, 1)
-assoc_map_frame_kernel(double* in, int n, double thr, double mapThr, double* map_x,
-                       double* map_y, int* map_type, int M0, unsigned cci_in, int lc_in,
-                       double* outd, int* outi, FrameMailbox mb) {
-  __shared__ double sx[FRAME_TILE], sy[FRAME_TILE];
-  __shared__ int st[FRAME_TILE];
-  mailbox_fetch(mb, in, n);
+__device__ __forceinline__ void map_frame_body(const double* in, int n, double thr, double mapThr, double* map_x,
+                                               double* map_y, int* map_type, int M0, unsigned cci_in, int lc_in,
+                                               double* outd, int* outi, double* sx, double* sy, int* st) {
   FrameScalars* sc = reinterpret_cast<FrameScalars*>(outi);
   int* idx = outi + 8;
   int* status = outi + 8 + n;
@@ -304,7 +300,73 @@ assoc_map_frame_kernel(double* in, int n, double thr, double mapThr, double* map
       sc->pad = 0;
     }
   }
+}
+
+__global__ void __launch_bounds__(FRAME_THREADS, 1)
+assoc_map_frame_kernel(double* in, int n, double thr, double mapThr, double* map_x,
+                       double* map_y, int* map_type, int M0, unsigned cci_in, int lc_in,
+                       double* outd, int* outi, FrameMailbox mb) {
+  __shared__ double sx[FRAME_TILE], sy[FRAME_TILE];
+  __shared__ int st[FRAME_TILE];
+  mailbox_fetch(mb, in, n);
+  map_frame_body(in, n, thr, mapThr, map_x, map_y, map_type, M0, cci_in, lc_in, outd, outi, sx, sy, st);
   mailbox_publish(mb, outi, 2 * n + 8, outd, 5 * n);
+}
+
+// Whole Monte-Carlo DRIVES per replica (SURVEY section 7 step 6, 8(d) "optional second variant" of config 3): one CTA
+// per replica runs the mapping phase of performSLAM (slam.cpp:298-338 -> addConesToMap) frame after frame -- the body
+// of the single-frame kernel above, unchanged -- with the replica's map in its own slice of the map arrays and the
+// frame state (map size, m_currentConeIndex, m_loopClosing) carried from frame to frame on the device.  A replica
+// stops at the frame that closes its loop (the reference then optimises and switches to the localiser); the records
+// of every frame (scalars, idx, status -- the layout of slam_b200_assoc_map_frame) stay in HBM for the graph builder.
+//   frames: [R][F][DRIVE_IN_STRIDE(nmax)] doubles: 4n cone values, pose(3), cos, sin at 4n (n = ncols[r][f])
+__host__ __device__ inline size_t drive_in_stride(int nmax) { return 4 * (size_t)nmax + 8; }
+__host__ __device__ inline size_t drive_rec_stride(int nmax) { return 2 * (size_t)nmax + 8; }
+
+__global__ void __launch_bounds__(FRAME_THREADS, 2)
+drive_replicas_kernel(const double* __restrict__ frames, const int* __restrict__ ncols, int F, int nmax, double thr,
+                      double mapThr, double* map_x, double* map_y, int* map_type, int cap, double* scratch,
+                      int* records, int* map_n_out, int* closed_at) {
+  __shared__ double sx[FRAME_TILE], sy[FRAME_TILE];
+  __shared__ int st[FRAME_TILE];
+  const int r = blockIdx.x;
+  double* mx = map_x + (size_t)r * cap;
+  double* my = map_y + (size_t)r * cap;
+  int* mt = map_type + (size_t)r * cap;
+  double* outd = scratch + (size_t)r * (8 * (size_t)nmax + 8);
+  int M = 0, lc = 0, closed = -1, overflow = 0;
+  unsigned cci = 0;
+  for (int f = 0; f < F; f++) {
+    const int n = ncols[(size_t)r * F + f];
+    int* outi = records + ((size_t)r * F + f) * drive_rec_stride(nmax);
+    const bool run = !lc && !overflow && n > 0 && n <= nmax && M + n + 1 <= cap;
+    if (!run) {  // block-uniform: the frame is recorded as not run (n_reobserved = -1)
+      if (!lc && n > 0 && (n > nmax || M + n + 1 > cap)) overflow = 1;
+      if (threadIdx.x == 0) {
+        FrameScalars* sc = reinterpret_cast<FrameScalars*>(outi);
+        sc->first_cone_created = 0; sc->loop_closing_obs = -1; sc->map_n = M; sc->current_cone_index = (int)cci;
+        sc->loop_closing = lc; sc->n_reobserved = -1; sc->send_cone_data = overflow; sc->pad = 0;
+      }
+      for (int i = threadIdx.x; i < min(n, nmax); i += blockDim.x) {
+        outi[8 + i] = -1;
+        outi[8 + min(n, nmax) + i] = SLAM_B200_ASSOC_SKIPPED;
+      }
+      continue;
+    }
+    const double* in = frames + ((size_t)r * F + f) * drive_in_stride(nmax);
+    map_frame_body(in, n, thr, mapThr, mx, my, mt, M, cci, lc, outd, outi, sx, sy, st);
+    __syncthreads();  // the frame's scalars (written by lane 0) are the next frame's state
+    const FrameScalars* sc = reinterpret_cast<const FrameScalars*>(outi);
+    M = sc->map_n;
+    cci = (unsigned)sc->current_cone_index;
+    lc = sc->loop_closing;
+    if (lc && closed < 0) closed = f;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    map_n_out[r] = M;
+    closed_at[r] = overflow ? -2 : closed;
+  }
 }
 
 // Localisation-phase frame (slam.cpp:350-387)
@@ -975,6 +1037,78 @@ int slam_b200_assoc_localize_frame(slam_b200_ctx* c, const double* cones, int n,
   if (n_reobserved) *n_reobserved = sc->n_reobserved;
   if (send_cone_data) *send_cone_data = sc->send_cone_data;
   return sc->n_reobserved;
+} SLAM_ABI_CATCH(c)
+
+// Whole drives per replica: see drive_replicas_kernel.  Host buffers in and out; kernel_ms (optional) = device time
+// of the drive kernel alone (events on the context's stream).
+int slam_b200_drive_replicas(slam_b200_ctx* c, int n_replicas, int n_frames, int nmax, const double* frames4,
+                             const int32_t* ncols, const double* poses3, double thr, double mapThr, int cap,
+                             int32_t* records, double* map_x, double* map_y, int32_t* map_type, int32_t* map_n,
+                             int32_t* closed_at, double* kernel_ms) try {
+  NvtxRange nvtx_range("slam_b200/drive_replicas");
+  if (!c || n_replicas < 0 || n_frames < 0 || nmax < 1 || cap < 2 || !frames4 || !ncols || !poses3 || !records ||
+      !map_n || !closed_at)
+    return SLAM_B200_E_ARG;
+  if (ctx_set_device(c)) return SLAM_B200_E_CUDA;
+  if (n_replicas == 0 || n_frames == 0) return 0;
+  const size_t R = (size_t)n_replicas, F = (size_t)n_frames, si = drive_in_stride(nmax), sr = drive_rec_stride(nmax);
+  // pack: cone columns, pose, cos / sin of the heading from the host libm (like upload_frame)
+  std::vector<double> packed(R * F * si, 0.0);
+  for (size_t q = 0; q < R * F; q++) {
+    const int n = ncols[q];
+    if (n < 0) return SLAM_B200_E_ARG;
+    const int m = std::min(n, nmax);
+    double* o = packed.data() + q * si;
+    std::memcpy(o, frames4 + q * 4 * (size_t)nmax, sizeof(double) * 4 * (size_t)m);
+    const double* p = poses3 + 3 * q;
+    o[4 * (size_t)m] = p[0]; o[4 * (size_t)m + 1] = p[1]; o[4 * (size_t)m + 2] = p[2];
+    o[4 * (size_t)m + 3] = std::cos(p[2]);
+    o[4 * (size_t)m + 4] = std::sin(p[2]);
+  }
+  DevBuf<double> d_frames, d_mx, d_my, d_scratch;
+  DevBuf<int> d_ncols, d_mt, d_rec, d_mn, d_closed;
+  struct Release {
+    DevBuf<double>&a, &b, &c2, &d; DevBuf<int>&e, &f, &g, &h, &i;
+    ~Release() { a.release(); b.release(); c2.release(); d.release(); e.release(); f.release(); g.release(); h.release(); i.release(); }
+  } rel{d_frames, d_mx, d_my, d_scratch, d_ncols, d_mt, d_rec, d_mn, d_closed};
+  SLAM_CUDA_TRY(c, d_frames.exact(R * F * si));
+  SLAM_CUDA_TRY(c, d_ncols.exact(R * F));
+  SLAM_CUDA_TRY(c, d_mx.exact(R * (size_t)cap));
+  SLAM_CUDA_TRY(c, d_my.exact(R * (size_t)cap));
+  SLAM_CUDA_TRY(c, d_mt.exact(R * (size_t)cap));
+  SLAM_CUDA_TRY(c, d_scratch.exact(R * (8 * (size_t)nmax + 8)));
+  SLAM_CUDA_TRY(c, d_rec.exact(R * F * sr));
+  SLAM_CUDA_TRY(c, d_mn.exact(R));
+  SLAM_CUDA_TRY(c, d_closed.exact(R));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(d_frames.p, packed.data(), sizeof(double) * R * F * si, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemcpyAsync(d_ncols.p, ncols, sizeof(int) * R * F, cudaMemcpyHostToDevice, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(d_mx.p, 0, sizeof(double) * R * (size_t)cap, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(d_my.p, 0, sizeof(double) * R * (size_t)cap, c->stream));
+  SLAM_CUDA_TRY(c, cudaMemsetAsync(d_mt.p, 0, sizeof(int) * R * (size_t)cap, c->stream));
+  cudaEvent_t e0, e1;
+  SLAM_CUDA_TRY(c, cudaEventCreate(&e0));
+  SLAM_CUDA_TRY(c, cudaEventCreate(&e1));
+  cudaEventRecord(e0, c->stream);
+  drive_replicas_kernel<<<n_replicas, FRAME_THREADS, 0, c->stream>>>(d_frames.p, d_ncols.p, n_frames, nmax, thr, mapThr,
+                                                                     d_mx.p, d_my.p, d_mt.p, cap, d_scratch.p, d_rec.p,
+                                                                     d_mn.p, d_closed.p);
+  c->launches++;
+  cudaEventRecord(e1, c->stream);
+  cudaError_t le = cudaGetLastError();
+  if (le == cudaSuccess) le = cudaMemcpyAsync(records, d_rec.p, sizeof(int) * R * F * sr, cudaMemcpyDeviceToHost, c->stream);
+  if (le == cudaSuccess && map_x) le = cudaMemcpyAsync(map_x, d_mx.p, sizeof(double) * R * (size_t)cap, cudaMemcpyDeviceToHost, c->stream);
+  if (le == cudaSuccess && map_y) le = cudaMemcpyAsync(map_y, d_my.p, sizeof(double) * R * (size_t)cap, cudaMemcpyDeviceToHost, c->stream);
+  if (le == cudaSuccess && map_type) le = cudaMemcpyAsync(map_type, d_mt.p, sizeof(int) * R * (size_t)cap, cudaMemcpyDeviceToHost, c->stream);
+  if (le == cudaSuccess) le = cudaMemcpyAsync(map_n, d_mn.p, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream);
+  if (le == cudaSuccess) le = cudaMemcpyAsync(closed_at, d_closed.p, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream);
+  if (le == cudaSuccess) le = cudaStreamSynchronize(c->stream);
+  float ms = 0;
+  if (le == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  SLAM_CUDA_TRY(c, le);
+  if (kernel_ms) *kernel_ms = ms;
+  return n_replicas;
 } SLAM_ABI_CATCH(c)
 
 int slam_b200_map_build_grid(slam_b200_ctx* c, double cell) try {

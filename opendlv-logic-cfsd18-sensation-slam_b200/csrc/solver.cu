@@ -10,6 +10,9 @@
 // eliminates its pivot columns and hands its own Schur complement to the parent.  Landmark and pose
 // blocks are ordered inside this factorisation; each update matrix IS the Schur complement of the
 // eliminated variables, it is just never formed globally.
+#include <array>
+#include <cstring>
+
 #include "graph_dev.h"
 
 namespace {
@@ -1167,8 +1170,7 @@ factor_tile_kernel(TileArgs A, int list_off, int R, int slab, const double* __re
 // A/B-operand layout (one store + two loads per panel tile; the same operand registers serve as the row's -X d
 // and as every later row's L^T), and the front goes to HBM straight from the registers.
 template <int T>
-__global__ void __launch_bounds__(128)
-factor_tile_reg_kernel(TileArgs A, int list_off, int R, const double* __restrict__ V_all, long nV, double* F_all,
+__device__ __forceinline__ void factor_tile_reg_body(const TileArgs& A, int list_off, int R, const double* __restrict__ V_all, long nV, double* F_all,
                        long nF, int* status, double* x_all, int n) {
   constexpr int NT = (T * (T + 1)) / 2;
   extern __shared__ double smem[];
@@ -1261,6 +1263,27 @@ factor_tile_reg_kernel(TileArgs A, int list_off, int R, const double* __restrict
   if (bad && lane == 0) status[2 * r] = 1;
 }
 
+template <int T>
+__global__ void __launch_bounds__(128)
+factor_tile_reg_kernel(TileArgs A, int list_off, int R, const double* __restrict__ V_all, long nV, double* F_all,
+                       long nF, int* status, double* x_all, int n) {
+  factor_tile_reg_body<T>(A, list_off, R, V_all, nV, F_all, nF, status, x_all, n);
+}
+// Register caps for more resident warps: the kernel is latency-bound at the 12-16 warps per SM the compiler's own
+// register count allows, and spilling a few dozen registers costs less than the extra warps bring (measured, C3:
+// 415k -> 425k replica GN it/s with the level-1 caps).  One warp per CTA.  SLAM_B200_TILE_TIGHT = 0 (none) ... 3.
+constexpr int tile_reg_min_blocks(int T, int lvl) {
+  return lvl == 1 ? (T <= 5 ? 20 : T == 6 ? 18 : T == 7 ? 14 : 9)
+       : lvl == 2 ? (T <= 5 ? 24 : T == 6 ? 20 : T == 7 ? 16 : 11)
+                  : (T <= 5 ? 28 : T == 6 ? 24 : T == 7 ? 18 : 12);
+}
+template <int T, int LVL>
+__global__ void __launch_bounds__(32, tile_reg_min_blocks(T, LVL))
+factor_tile_reg_tight_kernel(TileArgs A, int list_off, int R, const double* __restrict__ V_all, long nV, double* F_all,
+                             long nF, int* status, double* x_all, int n) {
+  factor_tile_reg_body<T>(A, list_off, R, V_all, nV, F_all, nF, status, x_all, n);
+}
+
 // Backward sweep (L^T x = z, root -> leaves) from the stored L tiles: per pivot tile column all tiles below
 // and the diagonal tile are requested at once (16-byte loads, unit stride), multiplied with the already-known
 // x of their rows and reduced over the 8 rows of the accumulator layout by shuffles; the 8 x 8 unit triangle
@@ -1269,7 +1292,10 @@ constexpr int TILE_MAX_T = TILE_MAX_ROWS / 8;
 
 constexpr int BACK_SLAB = TILE_MAX_ROWS + 8 + 64;  // x of the front's rows + the current unit triangle, per warp
 
-__global__ void __launch_bounds__(128)
+// TMAXT: the most tile rows any front of the launch has (8 for the trackdrive topologies: 28 instead of 44 registers of
+// tile buffers, 24 instead of 20 resident warps per SM)
+template <int TMAXT>
+__global__ void __launch_bounds__(128, TMAXT <= 8 ? 6 : 5)
 backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__ F_all, long nF, double* x_all, int n) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1286,12 +1312,12 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
   const int g = lane >> 2, t = lane & 3;
   const int cl = g * 8 + ((2 * t) ^ ((g & 2) << 1));  // this lane's two entries of a tile (accumulator layout, tileplan.h)
   // the last pivot column's tiles do not depend on x: request them before the gather of x
-  double2 lv[TILE_MAX_T - 1], dg;
+  double2 lv[TMAXT - 1], dg;
   {
     const int K = KT - 1;
     dg = *reinterpret_cast<const double2*>(Fg + tile_base(K, K) + cl);
 #pragma unroll
-    for (int d = 0; d < TILE_MAX_T - 1; d++)
+    for (int d = 0; d < TMAXT - 1; d++)
       if (K + 1 + d < T) lv[d] = *reinterpret_cast<const double2*>(Fg + tile_base(K + 1 + d, K) + cl);
   }
   for (int i = lane; i < (T << 3); i += 32) {
@@ -1305,7 +1331,7 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
     *reinterpret_cast<double2*>(tri + cl) = dg;
     double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-    for (int d = 0; d < TILE_MAX_T - 1; d++) {
+    for (int d = 0; d < TMAXT - 1; d++) {
       if (K + 1 + d < T) {
         const double xi = xs[8 * (K + 1 + d) + g];
         acc0 += lv[d].x * xi;
@@ -1315,7 +1341,7 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
     if (K > 0) {  // the next column's tiles while this one is reduced and solved
       dg = *reinterpret_cast<const double2*>(Fg + tile_base(K - 1, K - 1) + cl);
 #pragma unroll
-      for (int d = 0; d < TILE_MAX_T - 1; d++)
+      for (int d = 0; d < TMAXT - 1; d++)
         if (K + d < T) lv[d] = *reinterpret_cast<const double2*>(Fg + tile_base(K + d, K - 1) + cl);
     }
 #pragma unroll
@@ -1538,9 +1564,21 @@ static int solver_init_attrs(slam_b200_ctx* c) {
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<7, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tile_reg_tight_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     c->solver_attrs_set = true;
   }
   return 0;
@@ -1574,6 +1612,21 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     static const int wpc_f = [] { const char* e = getenv("SLAM_B200_TILE_WPC_F"); int v = e ? atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();
     static const int wpc_b = [] { const char* e = getenv("SLAM_B200_TILE_WPC_B"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4) ? v : 4; }();
     static const bool reg_path = getenv("SLAM_B200_TILE_NO_REG") == nullptr;
+    // level of the register caps per number of tile rows (tile_reg_min_blocks): one digit for all T, or one digit each
+    // for T = 5, 6, 7, 8 (e.g. SLAM_B200_TILE_TIGHT=2110)
+    static const std::array<int, 9> tight_of = [] {
+      std::array<int, 9> a;
+      a.fill(1);
+      if (const char* e = getenv("SLAM_B200_TILE_TIGHT")) {
+        const size_t len = strlen(e);
+        for (int T = 0; T <= 8; T++) {
+          const size_t k = len == 1 ? 0 : (T >= 5 ? (size_t)(T - 5) : 0);
+          const char ch = k < len ? e[k] : '1';
+          a[T] = (ch >= '0' && ch <= '3') ? ch - '0' : 1;
+        }
+      }
+      return a;
+    }();
     // The size classes of one level touch disjoint fronts, so they may run side by side: class i > 0 goes to a side
     // stream between a fork and a join event (parallel branches once the iteration is captured into a CUDA graph).
     // Levels near the root hold one to three fronts per class -- less than a wave of warps each -- and would otherwise
@@ -1596,12 +1649,20 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     auto launch_factor = [&](cudaStream_t st, int list_off, int count, int Tmax, bool uniform_T) {
       const int slab = ((Tmax * (Tmax + 1)) / 2) * 64 + TILE_SCRATCH;
       if (reg_path && uniform_T && Tmax <= 8) {  // whole front in registers, one instantiation per T
+        const int tight = tight_of[Tmax];
         for (int o = 0; o < count; o += 65535) {
           dim3 grid((D.R + wpc_f - 1) / wpc_f, std::min(65535, count - o));
           const size_t sm = (size_t)wpc_f * slab * sizeof(double);
-#define REG_LAUNCH(TT) case TT: factor_tile_reg_kernel<TT><<<grid, 32 * wpc_f, sm, st>>>(TA, list_off + o, D.R, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n); break
+#define REG_ARGS (TA, list_off + o, D.R, D.V.p, D.nV, D.Lv.p, D.nL, D.status.p, D.x.p, D.n)
+#define REG_LAUNCH(TT) case TT: \
+            if (wpc_f != 1 || tight == 0) factor_tile_reg_kernel<TT><<<grid, 32 * wpc_f, sm, st>>> REG_ARGS; \
+            else if (tight == 1) factor_tile_reg_tight_kernel<TT, 1><<<grid, 32, sm, st>>> REG_ARGS; \
+            else if (tight == 2) factor_tile_reg_tight_kernel<TT, 2><<<grid, 32, sm, st>>> REG_ARGS; \
+            else factor_tile_reg_tight_kernel<TT, 3><<<grid, 32, sm, st>>> REG_ARGS; \
+            break
           switch (Tmax) { REG_LAUNCH(1); REG_LAUNCH(2); REG_LAUNCH(3); REG_LAUNCH(4); REG_LAUNCH(5); REG_LAUNCH(6); REG_LAUNCH(7); REG_LAUNCH(8); default: break; }
 #undef REG_LAUNCH
+#undef REG_ARGS
           c->launches++;
         }
         return;
@@ -1660,8 +1721,12 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       for (int q = k; q < k1; q++) count += D.tile_launches[q].count;
       for (int o = 0; o < count; o += 65535) {
         dim3 grid((D.R + wpc_b - 1) / wpc_b, std::min(65535, count - o));
-        backward_tile_kernel<<<grid, 32 * wpc_b, (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream>>>(
-            TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n);
+        if (D.tile.max_T <= 8)
+          backward_tile_kernel<8><<<grid, 32 * wpc_b, (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream>>>(
+              TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n);
+        else
+          backward_tile_kernel<TILE_MAX_T><<<grid, 32 * wpc_b, (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream>>>(
+              TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n);
         c->launches++;
       }
       k1 = k;

@@ -227,10 +227,12 @@ def test_bulk_full_size_c4_grid_equals_brute(ctx, orc, synth, pkg):
     assert (grid >= 0).mean() > 0.85
 
 
+@pytest.mark.parametrize("algo_name", ["ALGO_GRID_PIPELINED", "ALGO_GRID_BATCHED"])
 @pytest.mark.parametrize("gate", [0, 1])
-def test_bulk_pipelined_train_equals_single_frames(ctx, orc, synth, pkg, gate):
-    """SLAM_B200_ALGO_GRID_PIPELINED: a train of independent frames (different observation sets and
-    poses) overlapping on one stream gives, frame by frame, what ALGO_GRID and the oracle give."""
+def test_bulk_pipelined_train_equals_single_frames(ctx, orc, synth, pkg, gate, algo_name):
+    """SLAM_B200_ALGO_GRID_PIPELINED / _BATCHED: a train of independent frames (different observation sets and
+    poses) overlapping on one stream / sharing launches of eight gives, frame by frame, what ALGO_GRID and the
+    oracle give (12 frames: one full batch of eight and a ragged one of four; ragged frame sizes in the batch)."""
     import torch
     f = synth.cone_field(n_map=200_000, n_obs=24_000, seed=9)
     ctx.map_clear()
@@ -246,7 +248,7 @@ def test_bulk_pipelined_train_equals_single_frames(ctx, orc, synth, pkg, gate):
     d_out = [torch.full((n,), -7, dtype=torch.int32, device=dev) for _ in range(F)]
     torch.cuda.synchronize()
     launch = pkg.capi.Context.assoc_bulk_frames_dev([ctx] * F, [t.data_ptr() for t in d_in], [n] * F, poses, THR, gate,
-                                                    pkg.capi.ALGO_GRID_PIPELINED, [t.data_ptr() for t in d_out])
+                                                    getattr(pkg.capi, algo_name), [t.data_ptr() for t in d_out])
     for _ in range(3):
         assert launch() == F
     ctx.sync()
@@ -260,3 +262,54 @@ def test_bulk_pipelined_train_equals_single_frames(ctx, orc, synth, pkg, gate):
             assert np.array_equal(got, o["idx"]), f"frame {k} vs oracle"
         matched += int((got >= 0).sum())
     assert matched > 1000
+
+
+def test_whole_drives_per_replica_equal_the_oracle(ctx, orc, synth):
+    """SURVEY section 7 step 6 / 8(d) 'optional second variant' of config 3: whole Monte-Carlo drives, one replica per
+    thread block, frame state carried on the device (slam_b200_drive_replicas).  Seven noisy replicas of a small
+    loop (each with its own pose / observation noise, so their maps and the frame that closes the loop differ) + one
+    replica with an empty frame, a NaN cone (azimuth 0) and a column beyond the mapping threshold: every frame's
+    records, the map and the closing frame must be what the oracle's addConesToMap gives frame by frame."""
+    R, F, nmax, cap = 8, 230, 16, 256
+    frames = np.zeros((R, F, 4, nmax)); ncols = np.zeros((R, F), dtype=np.int32); poses = np.zeros((R, F, 3))
+    for r in range(R):
+        trk = synth.ellipse_track(n_pairs=22 + 2 * (r % 3), a=18.0 + 2 * (r % 3), b=9.0 + (r % 3), half_width=1.5)
+        d = synth.simulate_drive(trk, F, s_step=1.45 * trk.length / F, seed=100 + r, sigma_xy=0.05 + 0.01 * r, sigma_th=0.005)
+        for f, (fr, p) in enumerate(zip(d.frames, d.poses_noisy)):
+            fr = np.asarray(fr, dtype=np.float64).reshape(4, -1, order="F")[:, :nmax]
+            if r == R - 1:
+                if f == 5:
+                    fr = fr[:, :0]
+                elif f == 9 and fr.shape[1] > 1:
+                    fr = fr.copy(); fr[0, 1] = 0.0            # azimuth 0 -> NaN cone
+                elif f == 12 and fr.shape[1] > 1:
+                    fr = fr.copy(); fr[2, 0] = np.float32(75.0)
+            n = fr.shape[1]
+            frames[r, f, :, :n] = fr
+            ncols[r, f] = n
+            poses[r, f] = p
+    out = ctx.drive_replicas(frames, ncols, poses, synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD, cap=cap)
+    closed_seen = set()
+    for r in range(R):
+        mx = np.zeros(cap); my = np.zeros(cap); mt = np.zeros(cap, dtype=np.int32)
+        M = cci = lc = 0
+        closed = -1
+        for f in range(F):
+            n = int(ncols[r, f])
+            sc = out["scalars"][r, f]
+            if lc or n == 0:
+                assert sc[5] == -1 and sc[2] == M and sc[4] == lc, (r, f)   # recorded as not run, state unchanged
+                continue
+            o = orc.assoc_map_frame(frames[r, f, :, :n], poses[r, f], synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD,
+                                    mx, my, mt, M, cci, lc)
+            assert np.array_equal(out["idx"][r, f, :n], o["idx"]) and np.array_equal(out["status"][r, f, :n], o["status"]), (r, f)
+            M, cci, lc = o["M"], o["cci"], o["loop_closing"]
+            assert sc[2] == M and sc[3] == cci and sc[4] == lc and sc[5] == 0, (r, f)
+            if lc and closed < 0:
+                closed = f
+        assert out["closed_at"][r] == closed and out["map_n"][r] == M, r
+        ok = ~np.isnan(mx[:M])
+        assert np.array_equal(np.isnan(out["map_x"][r, :M]), ~ok)
+        assert np.allclose(out["map_x"][r, :M][ok], mx[:M][ok], rtol=0, atol=1e-9) and np.array_equal(out["map_type"][r, :M], mt[:M])
+        closed_seen.add(closed)
+    assert len(closed_seen) > 2 and -1 not in closed_seen        # the replicas really differ, and all of them close
