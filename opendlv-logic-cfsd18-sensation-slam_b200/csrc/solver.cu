@@ -1215,13 +1215,29 @@ __device__ __forceinline__ void factor_tile_reg_body(const TileArgs& A, int list
       const double w0 = t == 0 ? x[0] : t == 1 ? x[1] : t == 2 ? x[2] : x[3];
       const double w1 = t == 0 ? x[4] : t == 1 ? x[5] : t == 2 ? x[6] : x[7];
       const double nd0 = -Dk[tile_in(t, t)], nd1 = -Dk[tile_in(4 + t, 4 + t)];
+      // X = A_IK W = L_IK D.  The two MMAs of a tile depend on each other (k = 0..3, then k = 4..7 into the same
+      // accumulator) and a warp issues in order: all first halves go out before any second half, so no MMA waits
+      // for the one in front of it.
+      {
+        double pb[T];
 #pragma unroll
-      for (int I = K + 1; I < T; I++) {
-        const double* P = F + ((I * (I + 1)) / 2 + K) * 64;
-        double x0 = 0.0, x1 = 0.0;
-        dmma_acc(x0, x1, P[al0], w0);  // X = A_IK W = L_IK D
-        dmma_acc(x0, x1, P[al1], w1);
-        c[(I * (I + 1)) / 2 + K] = make_double2(x0 * di0, x1 * di1);  // L_IK, final
+        for (int I = K + 1; I < T; I++) {
+          const double* P = F + ((I * (I + 1)) / 2 + K) * 64;
+          double2& q = c[(I * (I + 1)) / 2 + K];
+          pb[I] = P[al1];
+          q = make_double2(0.0, 0.0);
+          dmma_acc(q.x, q.y, P[al0], w0);
+        }
+#pragma unroll
+        for (int I = K + 1; I < T; I++) {
+          double2& q = c[(I * (I + 1)) / 2 + K];
+          dmma_acc(q.x, q.y, pb[I], w1);
+        }
+#pragma unroll
+        for (int I = K + 1; I < T; I++) {
+          double2& q = c[(I * (I + 1)) / 2 + K];
+          q = make_double2(q.x * di0, q.y * di1);  // L_IK, final
+        }
       }
       __syncwarp();  // every A-operand read is done before the staged tiles are overwritten with L
 #pragma unroll
@@ -1235,13 +1251,16 @@ __device__ __forceinline__ void factor_tile_reg_body(const TileArgs& A, int list
         la1[I] = P[al1];
       }
 #pragma unroll
-      for (int I = K + 1; I < T; I++) {
-        const double xa0 = la0[I] * nd0, xa1 = la1[I] * nd1;
+      for (int I = K + 1; I < T; I++) {  // first k-half of every tile update, then the second (see above)
+        const double xa0 = la0[I] * nd0;
 #pragma unroll
-        for (int J = K + 1; J <= I; J++) {
-          dmma_acc(c[(I * (I + 1)) / 2 + J].x, c[(I * (I + 1)) / 2 + J].y, xa0, la0[J]);
-          dmma_acc(c[(I * (I + 1)) / 2 + J].x, c[(I * (I + 1)) / 2 + J].y, xa1, la1[J]);
-        }
+        for (int J = K + 1; J <= I; J++) dmma_acc(c[(I * (I + 1)) / 2 + J].x, c[(I * (I + 1)) / 2 + J].y, xa0, la0[J]);
+      }
+#pragma unroll
+      for (int I = K + 1; I < T; I++) {
+        const double xa1 = la1[I] * nd1;
+#pragma unroll
+        for (int J = K + 1; J <= I; J++) dmma_acc(c[(I * (I + 1)) / 2 + J].x, c[(I * (I + 1)) / 2 + J].y, xa1, la1[J]);
       }
     }
   }
@@ -1370,6 +1389,8 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
   }
   for (int i = lane; i < s; i += 32) x[p0 + i] = xs[i];
 }
+
+#include "factor3.cuh"
 
 // L panel (fs x s, leading dimension fs) from global into shared memory with leading dimension ld:
 // one warp per column, lanes over rows, up to five independent loads in flight per lane
@@ -1559,6 +1580,7 @@ static int solver_init_attrs(slam_b200_ctx* c) {
     int lim = c->max_smem_optin;
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+    SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
     SLAM_CUDA_TRY(c, cudaFuncSetAttribute(factor_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -1739,6 +1761,8 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   }
   // SLAM_B200_FACTOR_VARIANT=1 selects the first-generation CTA-per-front kernel (A/B measurements)
   static const bool gen2 = !(getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 1);
+  // SLAM_B200_FACTOR_VARIANT=2: large fronts by factor2_kernel too (A/B against the register-resident factor3_kernel)
+  static const bool gen3 = !getenv("SLAM_B200_FACTOR_VARIANT");
   static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
@@ -1768,7 +1792,16 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     }
     if (LL.n_small) {
       dim3 grid(LL.n_small, D.R);
-      if (gen2)
+      // register-resident 16-warp kernel when every front of the class fits its 20 x 20 tile grid
+      int max_nloc = 0;
+      for (int q = LL.n_tiny; q < LL.n_tiny + LL.n_small; q++) {
+        const int f = D.launch_list_host[LL.list_off + q];
+        max_nloc = std::max(max_nloc, f3_local_rows(D.sym.npiv[f], D.sym.nupd[f]));
+      }
+      if (gen3 && max_nloc <= 8 * F3_MAX_T && f3_smem_bytes(max_nloc) <= smem_limit) {
+        factor3_kernel<<<grid, F3_THREADS, f3_smem_bytes(max_nloc), c->stream>>>(
+            S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n);
+      } else if (gen2)
         factor2_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
             S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
             D.nUvec, D.x.p, D.n, la_idle);
