@@ -14,7 +14,14 @@
 // the column's tiles turn them into L | barrier | every warp updates its tiles.  Inputs and outputs are exactly
 // factor2_kernel's (assembly entries, children's Schur complements through rel[], gathered update vectors; L panels
 // column-major, Schur complement, update vector, z), so the backward kernels and the parents do not notice which
-// kernel produced a front.  Arithmetic: SimplicialCholesky_impl.h:122-191 (LDL^T without pivoting, failure iff a
+// kernel produced a front.
+//
+// MEASURED (C2, B200, profiles/r02_factor3.md): correct (parity 1.6e-13, the whole GPU suite passes with it) but NOT
+// faster than factor2_kernel -- 0.431 against 0.435 ms of factorisation per iteration, launch by launch within 5 %:
+// the per-panel chain (one warp factorises the diagonal tile, four warps form the column's L tiles, two block
+// barriers) costs what factor2_kernel's shared-memory traffic costs, and at 512 threads the kernel sits exactly at
+// its 128-register limit.  It is therefore OFF by default (SLAM_B200_FACTOR_VARIANT=3 selects it); what it would
+// need next is written down in DESIGN.md section 8.  Arithmetic: SimplicialCholesky_impl.h:122-191 (LDL^T without pivoting, failure iff a
 // pivot is exactly zero), blocked by tiles.
 #pragma once
 
@@ -170,56 +177,28 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
       }
     }
     __syncthreads();
-    // (2) the owners of the column's tiles: X = A W (= L D), L = X D^-1, final; published as update operands.
-    // The two MMAs of a tile depend on each other and a warp issues in order, so every first k-half goes out before
-    // any second one (here and in step (3)).
+    // (2) the owners of the column's tiles: X = A W (= L D), L = X D^-1, final; published as update operands
     if (wb == (K & 3)) {
       const double w0 = Wb[g * 8 + t], w1 = Wb[g * 8 + 4 + t];
       const double di0 = dinvb[2 * t], di1 = dinvb[2 * t + 1];
       const int jk = K >> 2;
-      // accumulator layout -> A-operand layout through the tile's own slot
-#pragma unroll
-      for (int i = 0; i < F3_NI; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          const int I = wa + 4 * (i + sh);
-          if (j == jk && I > K && I < T) *reinterpret_cast<double2*>(F + tile_base(I, K) + cl) = c[(i * (i + 1)) / 2 + j];
-        }
-      __syncwarp();
-      double pb[F3_NI];
 #pragma unroll
       for (int i = 0; i < F3_NI; i++)
 #pragma unroll
         for (int j = 0; j <= i; j++) {
           const int I = wa + 4 * (i + sh);
           if (j == jk && I > K && I < T) {  // warp-uniform
-            const double* P = F + tile_base(I, K);
+            double* P = F + tile_base(I, K);
             double2& q = c[(i * (i + 1)) / 2 + j];
-            pb[i] = P[al1];
-            q = make_double2(0.0, 0.0);
-            dmma_acc(q.x, q.y, P[al0], w0);
-          }
-        }
-#pragma unroll
-      for (int i = 0; i < F3_NI; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          const int I = wa + 4 * (i + sh);
-          if (j == jk && I > K && I < T) {
-            double2& q = c[(i * (i + 1)) / 2 + j];
-            dmma_acc(q.x, q.y, pb[i], w1);
-          }
-        }
-      __syncwarp();  // every A-operand read is done before the slots take the finished L tiles
-#pragma unroll
-      for (int i = 0; i < F3_NI; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          const int I = wa + 4 * (i + sh);
-          if (j == jk && I > K && I < T) {
-            double2& q = c[(i * (i + 1)) / 2 + j];
-            q = make_double2(q.x * di0, q.y * di1);
-            *reinterpret_cast<double2*>(F + tile_base(I, K) + cl) = q;
+            *reinterpret_cast<double2*>(P + cl) = q;  // accumulator layout -> A-operand layout through the tile's slot
+            __syncwarp();
+            const double pa0 = P[al0], pa1 = P[al1];
+            double x0 = 0.0, x1 = 0.0;
+            dmma_acc(x0, x1, pa0, w0);
+            dmma_acc(x0, x1, pa1, w1);
+            q = make_double2(x0 * di0, x1 * di1);
+            __syncwarp();
+            *reinterpret_cast<double2*>(P + cl) = q;
           }
         }
     }
@@ -239,6 +218,9 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
         lb0[i] = vj ? Pj[al0] : 0.0;
         lb1[i] = vj ? Pj[al1] : 0.0;
       }
+      // (both k-halves of a tile back to back: issuing all first halves before any second one -- the two MMAs of a
+      // tile depend on each other -- was measured and lost: it pushes the kernel over its 128 registers, 56 bytes
+      // of spills, panels 114k -> 167k cycles on the root front)
 #pragma unroll
       for (int i = 0; i < F3_NI; i++)
 #pragma unroll
@@ -247,15 +229,6 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
           if (J > K && J <= I && I < T) {  // warp-uniform
             double2& q = c[(i * (i + 1)) / 2 + j];
             dmma_acc(q.x, q.y, la0[i], lb0[j]);
-          }
-        }
-#pragma unroll
-      for (int i = 0; i < F3_NI; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          const int I = wa + 4 * (i + sh), J = wb + 4 * j;
-          if (J > K && J <= I && I < T) {
-            double2& q = c[(i * (i + 1)) / 2 + j];
             dmma_acc(q.x, q.y, la1[i], lb1[j]);
           }
         }

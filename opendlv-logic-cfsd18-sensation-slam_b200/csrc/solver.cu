@@ -1761,8 +1761,8 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   }
   // SLAM_B200_FACTOR_VARIANT=1 selects the first-generation CTA-per-front kernel (A/B measurements)
   static const bool gen2 = !(getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 1);
-  // SLAM_B200_FACTOR_VARIANT=2: large fronts by factor2_kernel too (A/B against the register-resident factor3_kernel)
-  static const bool gen3 = !getenv("SLAM_B200_FACTOR_VARIANT");
+  // SLAM_B200_FACTOR_VARIANT=3: large fronts by the register-resident factor3_kernel (measured: no faster, factor3.cuh)
+  static const bool gen3 = getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 3;
   static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];

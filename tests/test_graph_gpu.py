@@ -356,6 +356,32 @@ def test_first_generation_front_kernel_still_agrees(ctx, orc, synth, variant):
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
+def test_register_resident_large_front_kernel_agrees(ctx, orc, synth):
+    """SLAM_B200_FACTOR_VARIANT=3: the large fronts (more than 64 rows) of a single graph by factor3_kernel -- the tile
+    triangle in the registers of 16 warps, DMMA updates (csrc/factor3.cuh; measured no faster than factor2_kernel and
+    therefore off by default).  Read once per process, so it runs in a child process: a 4-lap graph whose root fronts
+    have ~100 rows, same tolerances as the default path."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import load_pkg\n"
+        "from oracle import oracle\n"
+        "pkg = load_pkg(); orc = oracle.load('best'); g = pkg.synth.c2_graph(n_laps=4, poses_per_lap=400)\n"
+        "ctx = pkg.Context(0); ctx.graph_load(g); n, chi2 = ctx.graph_optimize(10)\n"
+        "st = ctx.graph_stats(); assert st['max_front'] > 64, st\n"
+        "G = orc.graph_from_soa(g); no, chi2o = G.optimize(10)\n"
+        "pe, le = ctx.graph_get_estimates(); po, lo = G.estimates(g)\n"
+        "assert n == no == 10 and np.allclose(chi2, chi2o, rtol=1e-8)\n"
+        "assert np.max(np.abs(pe - po)) <= 1e-6 * max(1.0, np.max(np.abs(po)))\n"
+        "assert np.max(np.abs(le - lo)) <= 1e-6 * max(1.0, np.max(np.abs(lo)))\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)))
+    env = dict(os.environ, SLAM_B200_FACTOR_VARIANT="3")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_sharded_assembly_partials_sum_to_full(ctx, pkg, synth):
     """Edge-partitioned assembly (config 5): assembling pose ranges separately gives pose blocks and
     off-diagonal blocks owned by exactly one shard and landmark partial sums that add up to the full
