@@ -887,8 +887,8 @@ int slam_b200_map_update_from_graph(slam_b200_ctx* c) try {
   std::vector<int> lm(M, -1);
   int found = 0;
   for (int j = 0; j < M; j++) {
-    auto it = g.id2v.find(j);
-    if (it != g.id2v.end() && (it->second & 1)) { lm[j] = it->second >> 1; found++; }
+    const int v = g.id2v.get(j);
+    if (v >= 0 && (v & 1)) { lm[j] = v >> 1; found++; }
   }
   if (found == 0) return 0;
   double *est_dev = nullptr;

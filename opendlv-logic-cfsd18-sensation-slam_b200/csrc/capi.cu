@@ -64,10 +64,10 @@ void se2_between(const double* prev, const double* cur, double* z) {
 }
 
 int lookup(slam_b200_ctx* c, int id, bool want_lm, int* local) {
-  auto it = c->g.id2v.find(id);
-  if (it == c->g.id2v.end()) return SLAM_B200_E_ARG;
-  if (((it->second & 1) != 0) != want_lm) return SLAM_B200_E_ARG;
-  *local = it->second >> 1;
+  const int v = c->g.id2v.get(id);
+  if (v < 0) return SLAM_B200_E_ARG;
+  if (((v & 1) != 0) != want_lm) return SLAM_B200_E_ARG;
+  *local = v >> 1;
   return 0;
 }
 
@@ -249,8 +249,7 @@ int slam_b200_graph_clear(slam_b200_ctx* c) try {
 int slam_b200_graph_add_pose(slam_b200_ctx* c, int id, double x, double y, double theta) try {
   if (!c) return SLAM_B200_E_ARG;
   HostGraph& g = c->g;
-  if (g.id2v.count(id)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
-  g.id2v[id] = g.P() << 1;
+  if (!g.id2v.put(id, g.P() << 1)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
   g.pose_id.push_back(id);
   g.pose_est.push_back(x); g.pose_est.push_back(y); g.pose_est.push_back(theta);
   g.pose_fixed.push_back(0);
@@ -262,8 +261,7 @@ int slam_b200_graph_add_pose(slam_b200_ctx* c, int id, double x, double y, doubl
 int slam_b200_graph_add_landmark(slam_b200_ctx* c, int id, double x, double y) try {
   if (!c) return SLAM_B200_E_ARG;
   HostGraph& g = c->g;
-  if (g.id2v.count(id)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
-  g.id2v[id] = (g.L() << 1) | 1;
+  if (!g.id2v.put(id, (g.L() << 1) | 1)) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
   g.lm_id.push_back(id);
   g.lm_est.push_back(x); g.lm_est.push_back(y);
   g.lm_fixed.push_back(0);
@@ -319,10 +317,10 @@ int slam_b200_graph_add_edge_se2_xy(slam_b200_ctx* c, int pose_id, int landmark_
 
 int slam_b200_graph_set_fixed(slam_b200_ctx* c, int id, int fixed) try {
   if (!c) return SLAM_B200_E_ARG;
-  auto it = c->g.id2v.find(id);
-  if (it == c->g.id2v.end()) { c->fail("setFixed: unknown id"); return SLAM_B200_E_ARG; }
+  const int v = c->g.id2v.get(id);
+  if (v < 0) { c->fail("setFixed: unknown id"); return SLAM_B200_E_ARG; }
   char f = fixed ? 1 : 0;
-  char& cur = (it->second & 1) ? c->g.lm_fixed[it->second >> 1] : c->g.pose_fixed[it->second >> 1];
+  char& cur = (v & 1) ? c->g.lm_fixed[v >> 1] : c->g.pose_fixed[v >> 1];
   if (cur != f) {
     cur = f;
     c->g.structure_version++;
@@ -351,41 +349,45 @@ int slam_b200_graph_load(slam_b200_ctx* c, int n_poses, const int32_t* pose_ids,
     ~ClearOnError() { if (armed) { std::string keep = c->err; slam_b200_graph_clear(c); c->err = keep; } }
   } guard{c};
   HostGraph& g = c->g;
-  g.id2v.reserve((size_t)n_poses + n_landmarks);
   g.pose_id.assign(pose_ids, pose_ids + n_poses);
   g.pose_est.assign(pose_est3, pose_est3 + 3 * (size_t)n_poses);
   g.pose_fixed.assign(n_poses, 0);
   g.lm_id.assign(lm_ids, lm_ids + n_landmarks);
   g.lm_est.assign(lm_est2, lm_est2 + 2 * (size_t)n_landmarks);
   g.lm_fixed.assign(n_landmarks, 0);
-  for (int p = 0; p < n_poses; p++)
-    if (!g.id2v.emplace(pose_ids[p], p << 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
-  for (int l = 0; l < n_landmarks; l++)
-    if (!g.id2v.emplace(lm_ids[l], (l << 1) | 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
-  // ids of a bulk load are looked up ~2 (E_o + E_l) times: when they span a small range (the
-  // reference numbers landmarks from 0 and poses from 1000, slam.cpp:434,527) a flat table replaces
-  // the hash map for the edge loops below
-  std::vector<int> flat;
-  int id_lo = 0;
   {
-    int lo = INT32_MAX, hi = INT32_MIN;
-    for (int p = 0; p < n_poses; p++) { lo = std::min(lo, pose_ids[p]); hi = std::max(hi, pose_ids[p]); }
-    for (int l = 0; l < n_landmarks; l++) { lo = std::min(lo, lm_ids[l]); hi = std::max(hi, lm_ids[l]); }
-    const long span = (n_poses + n_landmarks) ? (long)hi - lo + 1 : 0;
-    if (span > 0 && span <= 8L * (n_poses + n_landmarks) + 4096) {
-      flat.assign((size_t)span, -1);
-      id_lo = lo;
-      for (int p = 0; p < n_poses; p++) flat[pose_ids[p] - lo] = p << 1;
-      for (int l = 0; l < n_landmarks; l++) flat[lm_ids[l] - lo] = (l << 1) | 1;
+    // the id index in one go: a flat table over the id range when the ids are dense (IdIndex, ctx.h)
+    long lo = INT32_MAX, hi = INT32_MIN;
+    for (int p = 0; p < n_poses; p++) { lo = std::min<long>(lo, pose_ids[p]); hi = std::max<long>(hi, pose_ids[p]); }
+    for (int l = 0; l < n_landmarks; l++) { lo = std::min<long>(lo, lm_ids[l]); hi = std::max<long>(hi, lm_ids[l]); }
+    const size_t count = (size_t)n_poses + n_landmarks;
+    IdIndex& ix = g.id2v;
+    ix.clear();
+    if (count && IdIndex::dense(hi - lo + 1, count)) {
+      ix.lo = lo;
+      ix.flat.assign((size_t)(hi - lo + 1), -1);
+      for (int p = 0; p < n_poses; p++) {
+        int& slot = ix.flat[(size_t)(pose_ids[p] - lo)];
+        if (slot >= 0) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+        slot = p << 1;
+      }
+      for (int l = 0; l < n_landmarks; l++) {
+        int& slot = ix.flat[(size_t)(lm_ids[l] - lo)];
+        if (slot >= 0) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+        slot = (l << 1) | 1;
+      }
+      ix.n = count;
+    } else {
+      ix.hashed = count > 0;
+      ix.map.reserve(count);
+      for (int p = 0; p < n_poses; p++)
+        if (!ix.map.emplace(pose_ids[p], p << 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+      for (int l = 0; l < n_landmarks; l++)
+        if (!ix.map.emplace(lm_ids[l], (l << 1) | 1).second) { c->fail("duplicate vertex id"); return SLAM_B200_E_ARG; }
+      ix.n = count;
     }
   }
-  auto find = [&](int id, bool want_lm, int* local) -> int {
-    if (flat.empty()) return lookup(c, id, want_lm, local);
-    const long k = (long)id - id_lo;
-    if (k < 0 || k >= (long)flat.size() || flat[k] < 0 || ((flat[k] & 1) != 0) != want_lm) return SLAM_B200_E_ARG;
-    *local = flat[k] >> 1;
-    return 0;
-  };
+  auto find = [&](int id, bool want_lm, int* local) -> int { return lookup(c, id, want_lm, local); };
   g.eo_i.resize(n_eo); g.eo_j.resize(n_eo);
   g.eo_z.assign(eo_z3, eo_z3 + 3 * (size_t)n_eo);
   g.eo_info.resize(6 * (size_t)n_eo);
@@ -442,10 +444,10 @@ int slam_b200_graph_num_edges(slam_b200_ctx* c) { return c ? c->g.Eo() + c->g.El
 
 int slam_b200_graph_get_vertex(slam_b200_ctx* c, int id, double out[3]) try {
   if (!c || !out) return SLAM_B200_E_ARG;
-  auto it = c->g.id2v.find(id);
-  if (it == c->g.id2v.end()) return SLAM_B200_E_ARG;
-  int k = it->second >> 1;
-  if (it->second & 1) {
+  const int v = c->g.id2v.get(id);
+  if (v < 0) return SLAM_B200_E_ARG;
+  int k = v >> 1;
+  if (v & 1) {
     out[0] = c->g.lm_est[2 * (size_t)k]; out[1] = c->g.lm_est[2 * (size_t)k + 1]; out[2] = 0;
     return 2;
   }

@@ -1,6 +1,7 @@
 // ctx.h -- context object behind the opaque slam_b200_ctx handle (include/slam_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -148,6 +149,58 @@ struct alignas(32) GridRec {
   int type, idx, pad0, pad1;
 };
 
+// vertex id -> (local index << 1) | is_landmark.  The reference numbers cones from 0 and poses from 1000 upwards
+// (slam.cpp:434,527), so the ids of a graph span a range about as large as their count: a flat table then, a hash map
+// only when the ids are sparse (10,300 hash inserts were a third of graph_load on the 10-lap graph).
+struct IdIndex {
+  std::vector<int> flat;                 // -1 = absent
+  long lo = 0;                           // id of flat[0]
+  size_t n = 0;                          // ids stored
+  bool hashed = false;
+  std::unordered_map<int, int> map;
+  static bool dense(long span, size_t count) { return span <= 8L * (long)count + 4096; }
+  void clear() { flat.clear(); map.clear(); lo = 0; n = 0; hashed = false; }
+  int get(int id) const {
+    if (hashed) { auto it = map.find(id); return it == map.end() ? -1 : it->second; }
+    const long k = (long)id - lo;
+    return (k < 0 || k >= (long)flat.size()) ? -1 : flat[(size_t)k];
+  }
+  bool put(int id, int v) {              // false: the id is there already
+    if (!hashed) {
+      if (flat.empty()) { lo = id; flat.assign(64, -1); }
+      long k = (long)id - lo;
+      if (k < 0 || k >= (long)flat.size()) {
+        const long nlo = std::min<long>(lo, id), nhi = std::max<long>(lo + (long)flat.size() - 1, id);
+        if (dense(nhi - nlo + 1, n + 1)) {
+          // grow geometrically on the side the id fell off
+          const long span = nhi - nlo + 1, cap = std::max<long>(span, 2 * (long)flat.size());
+          const long flo = id < lo ? nhi - cap + 1 : nlo;
+          std::vector<int> g((size_t)cap, -1);
+          std::copy(flat.begin(), flat.end(), g.begin() + (lo - flo));
+          flat.swap(g);
+          lo = flo;
+          k = (long)id - lo;
+        } else {
+          hashed = true;
+          map.reserve(2 * n + 16);
+          for (size_t q = 0; q < flat.size(); q++)
+            if (flat[q] >= 0) map.emplace((int)(lo + (long)q), flat[q]);
+          flat.clear();
+        }
+      }
+      if (!hashed) {
+        if (flat[(size_t)k] >= 0) return false;
+        flat[(size_t)k] = v;
+        n++;
+        return true;
+      }
+    }
+    if (!map.emplace(id, v).second) return false;
+    n++;
+    return true;
+  }
+};
+
 // ---- host-side graph (insertion order preserved; the reference's g2o graph owns the same data) --
 struct HostGraph {
   // vertices
@@ -155,7 +208,7 @@ struct HostGraph {
   std::vector<double> pose_est;  // 3 per pose
   std::vector<double> lm_est;    // 2 per landmark
   std::vector<char> pose_fixed, lm_fixed;
-  std::unordered_map<int, int> id2v;  // id -> (local index << 1) | is_landmark
+  IdIndex id2v;  // id -> (local index << 1) | is_landmark
   // pose-pose edges (EdgeSE2)
   std::vector<int> eo_i, eo_j;     // local pose indices
   std::vector<double> eo_z;        // 3 per edge

@@ -3,6 +3,7 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -639,33 +640,60 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   nd.next_label = 2;
   std::vector<int> all(nb), roots;
   std::iota(all.begin(), all.end(), 0);
-  // the two top levels of the dissection run here; the (up to four) parts below them are dissected
-  // on the pool threads.  The split depth is fixed, so the result does not depend on the thread count.
-  nd.defer_depth = nb >= 4096 ? 1 : -1;
+  // Only the top bisection runs here; its two halves are bisected side by side on the pool threads, and the (up
+  // to four) quarters below them are dissected side by side after that.  The split depths are fixed and every part
+  // gets its own label range from its position, so the result does not depend on the thread count.
+  nd.defer_depth = nb >= 4096 ? 0 : -1;
   nd.order_region(all, 1, roots, 0);
   if (getenv("SLAM_B200_SYM_DEBUG"))
-    fprintf(stderr, "[symbolic] nd top levels done at %.4f s, %zu deferred parts\n",
+    fprintf(stderr, "[symbolic] nd top level done at %.4f s, %zu deferred parts\n",
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), nd.deferred.size());
   if (!nd.deferred.empty()) {
-    const int nt = (int)nd.deferred.size();
-    std::vector<Nd> sub(nt);
-    std::vector<std::vector<int>> sub_roots(nt);
-    HostPool::get().run(nt, [&](int t) {
-      Nd& q = sub[t];
+    auto init_sub = [&](Nd& q, int label_block, int defer) {
       q.nb = nb; q.dim = dim; q.leaf_size = nd.leaf_size;
       q.xa = nd.xa; q.ad = nd.ad; q.region = nd.region; q.lvl = nd.lvl;
-      q.next_label = 2 + 2 * nb * (t + 1);  // label ranges never overlap (a dissection of n vertices hands out < 2n labels)
-      q.order_region(nd.deferred[t].verts, nd.deferred[t].lab, sub_roots[t], 0);
-    });
-    for (int t = 0; t < nt; t++) {
-      const int off = (int)nd.nodes.size();
-      for (NdNode& node : sub[t].nodes) {
-        for (int& k : node.kids) k += off;
-        nd.nodes.push_back(std::move(node));
+      q.next_label = 2 + 2 * nb * label_block;  // label ranges never overlap (a dissection of n vertices hands out < 2n labels)
+      q.defer_depth = defer;
+    };
+    auto splice = [](Nd& into, std::vector<Nd>& subs, std::vector<std::vector<int>>& sub_roots) {
+      for (size_t t = 0; t < subs.size(); t++) {
+        const int off = (int)into.nodes.size();
+        for (NdNode& node : subs[t].nodes) {
+          for (int& k : node.kids) k += off;
+          into.nodes.push_back(std::move(node));
+        }
+        for (int rt : sub_roots[t]) into.nodes[into.deferred[t].parent].kids.push_back(rt + off);
       }
-      for (int rt : sub_roots[t]) nd.nodes[nd.deferred[t].parent].kids.push_back(rt + off);
+      into.deferred.clear();
+    };
+    // halves: one more bisection each, their own parts deferred again
+    const int n1 = (int)nd.deferred.size();
+    std::vector<Nd> half(n1);
+    std::vector<std::vector<int>> half_roots(n1);
+    HostPool::get().run(n1, [&](int t) {
+      init_sub(half[t], 1 + t, 0);
+      half[t].order_region(nd.deferred[t].verts, nd.deferred[t].lab, half_roots[t], 0);
+    });
+    // quarters of all halves, flattened
+    std::vector<std::pair<int, int>> parts;
+    for (int h = 0; h < n1; h++)
+      for (int k = 0; k < (int)half[h].deferred.size(); k++) parts.push_back({h, k});
+    const int n2 = (int)parts.size();
+    std::vector<Nd> quarter(n2);
+    std::vector<std::vector<int>> quarter_roots(n2);
+    HostPool::get().run(n2, [&](int t) {
+      Nd::Deferred& d = half[parts[t].first].deferred[parts[t].second];
+      init_sub(quarter[t], 1 + n1 + t, -1);
+      quarter[t].order_region(d.verts, d.lab, quarter_roots[t], 0);
+    });
+    for (int h = 0, t0q = 0; h < n1; h++) {
+      const int cnt = (int)half[h].deferred.size();
+      std::vector<Nd> subs(std::make_move_iterator(quarter.begin() + t0q), std::make_move_iterator(quarter.begin() + t0q + cnt));
+      std::vector<std::vector<int>> sr(quarter_roots.begin() + t0q, quarter_roots.begin() + t0q + cnt);
+      splice(half[h], subs, sr);
+      t0q += cnt;
     }
-    nd.deferred.clear();
+    splice(nd, half, half_roots);
   }
   if (getenv("SLAM_B200_SYM_DEBUG"))
     fprintf(stderr, "[symbolic] nd parts done at %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
@@ -758,25 +786,73 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
   // vertex united with the structures of k's etree children minus k itself.  A child always precedes
   // its parent in the postorder, so its structure is already in the pool.
   std::vector<int> cs_ptr(nb + 1, 0), cs;
-  cs.reserve((size_t)nd.adj.size() * 2);
   {
-    std::vector<int> mark(nb, -1), kid_head(nb, -1), kid_next(nb, -1);
+    // Subtrees of the elimination tree are contiguous in the postorder and independent of each other: the maximal
+    // subtrees of at most nb / 16 columns are built side by side on the pool, each into its own pool of entries, the
+    // columns above them (the tops of the tree) afterwards; then one flat array.  Which subtree a column belongs to is
+    // a property of the tree, so the result does not depend on the thread count.
+    std::vector<int> kid_head(nb, -1), kid_next(nb, -1), first_desc(nb);
     for (int k = nb - 1; k >= 0; k--)  // child lists in ascending order
       if (eparent[k] >= 0) { kid_next[k] = kid_head[eparent[k]]; kid_head[eparent[k]] = k; }
+    for (int k = 0; k < nb; k++) first_desc[k] = kid_head[k] >= 0 ? first_desc[kid_head[k]] : k;  // subtree of k = [first_desc[k], k]
+    const int cap = std::max(64, nb / 16);
+    std::vector<int> task_root, owner(nb, -1);  // owner[k] = task that builds column k, -1 = the sequential top
     for (int k = 0; k < nb; k++) {
+      const int p = eparent[k];
+      const bool fits = k - first_desc[k] + 1 <= cap;
+      const bool parent_fits = p >= 0 && p - first_desc[p] + 1 <= cap;
+      if (fits && !parent_fits) {
+        for (int q = first_desc[k]; q <= k; q++) owner[q] = (int)task_root.size();
+        task_root.push_back(k);
+      }
+    }
+    const int ntask = (int)task_root.size();
+    std::vector<std::vector<int>> tcs(ntask);            // entries of every task, columns in order
+    std::vector<int> col_off(nb + 1, 0), col_len(nb, 0);  // offset of column k inside its owner's pool
+    auto build = [&](int k, std::vector<int>& out, std::vector<int>& mark, const std::vector<int>* const* pools) {
       const int v = order[k];
-      const size_t s0 = cs.size();
+      const size_t s0 = out.size();
       for (int p = nd.xadj[v]; p < nd.xadj[v + 1]; p++) {
         const int q = epos[nd.adj[p]];
-        if (q > k && mark[q] != k) { mark[q] = k; cs.push_back(q); }
+        if (q > k && mark[q] != k) { mark[q] = k; out.push_back(q); }
       }
-      for (int c = kid_head[k]; c >= 0; c = kid_next[c])
-        for (int t = cs_ptr[c]; t < cs_ptr[c + 1]; t++) {
-          const int q = cs[t];
-          if (q != k && mark[q] != k) { mark[q] = k; cs.push_back(q); }
+      for (int c = kid_head[k]; c >= 0; c = kid_next[c]) {
+        const std::vector<int>& src = *pools[owner[c] + 1];  // may be `out` itself: index, never keep a pointer
+        const size_t e0 = (size_t)col_off[c];
+        for (int t = 0; t < col_len[c]; t++) {
+          const int q = src[e0 + t];
+          if (q != k && mark[q] != k) { mark[q] = k; out.push_back(q); }
         }
-      std::sort(cs.begin() + s0, cs.end());
-      cs_ptr[k + 1] = (int)cs.size();
+      }
+      std::sort(out.begin() + s0, out.end());
+      col_off[k] = (int)s0;
+      col_len[k] = (int)(out.size() - s0);
+    };
+    std::vector<int> top;  // entries of the sequential top columns
+    std::vector<const std::vector<int>*> pools(ntask + 1);
+    pools[0] = &top;
+    for (int t = 0; t < ntask; t++) pools[t + 1] = &tcs[t];
+    static std::atomic<unsigned long long> analysis_counter{0};
+    const unsigned long long epoch = ++analysis_counter;
+    HostPool::get().run(ntask, [&](int t) {
+      // one scratch array per pool thread and analysis, not per task (a task marks with its column numbers, which
+      // are unique within one analysis)
+      thread_local std::vector<int> mark;
+      thread_local unsigned long long mark_epoch = 0;
+      if (mark_epoch != epoch || (int)mark.size() != nb) { mark.assign(nb, -1); mark_epoch = epoch; }
+      tcs[t].reserve(1024);
+      for (int k = first_desc[task_root[t]]; k <= task_root[t]; k++) build(k, tcs[t], mark, pools.data());
+    });
+    {
+      std::vector<int> mark(nb, -1);
+      for (int k = 0; k < nb; k++)
+        if (owner[k] < 0) build(k, top, mark, pools.data());
+    }
+    for (int k = 0; k < nb; k++) cs_ptr[k + 1] = cs_ptr[k] + col_len[k];
+    cs.resize((size_t)cs_ptr[nb]);
+    for (int k = 0; k < nb; k++) {
+      const int* e = pools[owner[k] + 1]->data() + col_off[k];
+      std::copy(e, e + col_len[k], cs.begin() + cs_ptr[k]);
     }
   }
   auto cs_size = [&](int k) { return cs_ptr[k + 1] - cs_ptr[k]; };
