@@ -176,6 +176,12 @@ class Context:
         x = _f64(x); y = _f64(y)
         self._ck(self.L.slam_b200_map_write_xy(self.h, int(first), len(x), _dp(x), _dp(y)), "map_write_xy")
 
+    def graph_num_poses(self):
+        return self._ck(self.L.slam_b200_graph_num_poses(self.h), "graph_num_poses")
+
+    def graph_num_landmarks(self):
+        return self._ck(self.L.slam_b200_graph_num_landmarks(self.h), "graph_num_landmarks")
+
     def map_update_from_graph(self):
         """Slam::updateMap on the device: map cone j <- landmark vertex j; returns the cones updated."""
         return self._ck(self.L.slam_b200_map_update_from_graph(self.h), "map_update_from_graph")

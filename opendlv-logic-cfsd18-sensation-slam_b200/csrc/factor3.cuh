@@ -55,6 +55,7 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   auto loc = [&](int p) { return p < s ? p : sp + (p - s); };
   const bool dbgc = S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;  // SLAM_B200_PHASE_CLOCKS
   if (dbgc) { S.dbg[0] = clock64(); for (int q = 24; q < 32; q++) S.dbg[q] = 0; }
+  long long dt_ = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck4 = 0, ck5 = 0;  // panel-step clocks, in registers until the end
   // ---- assembly in shared memory ----
   {
     double2* F2 = reinterpret_cast<double2*>(F);
@@ -149,6 +150,7 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   bool bad = false;
   for (int K = 0; K < KT; K++) {
     double* Dk = F + tile_base(K, K);
+    if (dbgc) dt_ = clock64();
     // (1) the owner of the diagonal tile factorises it and publishes the inverse of its unit triangle + 1/d
     if (wa == (K & 3) && wb == (K & 3)) {
       const int ik = K >> 2;  // sh == 0 on the diagonal of the warp grid
@@ -176,7 +178,9 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
         for (int k = 0; k < 8; k++) Wb[g * 8 + k] = x[k];
       }
     }
+    if (dbgc) { const long long t_ = clock64(); ck1 += t_ - dt_; dt_ = t_; }
     __syncthreads();
+    if (dbgc) { const long long t_ = clock64(); ck2 += t_ - dt_; dt_ = t_; }
     // (2) the owners of the column's tiles: X = A W (= L D), L = X D^-1, final; published as update operands
     if (wb == (K & 3)) {
       const double w0 = Wb[g * 8 + t], w1 = Wb[g * 8 + 4 + t];
@@ -202,21 +206,26 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
           }
         }
     }
+    if (dbgc) { const long long t_ = clock64(); ck3 += t_ - dt_; dt_ = t_; }
     __syncthreads();
+    if (dbgc) { const long long t_ = clock64(); ck4 += t_ - dt_; dt_ = t_; }
     // (3) every warp updates its tiles right of the column: C_IJ -= (L_IK D) L_JK^T
     {
       const double nd0 = -Dk[tile_in(t, t)], nd1 = -Dk[tile_in(4 + t, 4 + t)];
       double la0[F3_NI], la1[F3_NI], lb0[F3_NI], lb1[F3_NI];
+      const int k64 = K << 6;
 #pragma unroll
       for (int i = 0; i < F3_NI; i++) {
         const int I = wa + 4 * (i + sh), J = wb + 4 * i;
-        const bool vi = I > K && I < T, vj = J > K && J < T;
-        const double* Pi = F + tile_base(vi ? I : K, K);
-        const double* Pj = F + tile_base(vj ? J : K, K);
-        la0[i] = vi ? Pi[al0] * nd0 : 0.0;
-        la1[i] = vi ? Pi[al1] * nd1 : 0.0;
-        lb0[i] = vj ? Pj[al0] : 0.0;
-        lb1[i] = vj ? Pj[al1] : 0.0;
+        const bool vi = (I > K) & (I < T), vj = (J > K) & (J < T);
+        const int oi = (((I * (I + 1)) >> 1) << 6) + k64, oj = (((J * (J + 1)) >> 1) << 6) + k64;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        if (vi) { a0 = F[oi + al0]; a1 = F[oi + al1]; }
+        if (vj) { b0 = F[oj + al0]; b1 = F[oj + al1]; }
+        la0[i] = a0 * nd0;
+        la1[i] = a1 * nd1;
+        lb0[i] = b0;
+        lb1[i] = b1;
       }
       // (both k-halves of a tile back to back: issuing all first halves before any second one -- the two MMAs of a
       // tile depend on each other -- was measured and lost: it pushes the kernel over its 128 registers, 56 bytes
@@ -233,6 +242,7 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
           }
         }
     }
+    if (dbgc) { const long long t_ = clock64(); ck5 += t_ - dt_; dt_ = t_; }
     // no barrier here: step (1) of the next column touches the owner's registers, its own diagonal slot and the
     // W / 1/d buffers, which nobody reads after the barrier in front of step (3)
   }
@@ -268,5 +278,6 @@ factor3_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
     for (int i = j + lane; i < u; i += 32) out[i] = F[tile_at(sp + i, sp + j)];
   }
   __syncthreads();
+  if (dbgc) { S.dbg[24] = ck1; S.dbg[25] = ck2; S.dbg[26] = ck3; S.dbg[27] = ck4; S.dbg[28] = ck5; }
   if (dbgc) { S.dbg[6] = clock64(); S.dbg[7] = s; S.dbg[8] = fs; S.dbg[9] = S.child_ptr[f + 1] - S.child_ptr[f]; }
 }

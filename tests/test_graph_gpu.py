@@ -491,3 +491,52 @@ def test_case_is_bit_reproducible():
     b = _verdict(_run_case({}))
     c = _verdict(_run_case({"SLAM_B200_GUARD": "1"}))
     assert a["hash"] == b["hash"] == c["hash"], (a, b, c)
+
+
+def test_sparse_vertex_ids_and_warmup_do_not_change_results(pkg, synth):
+    """The id index is a flat table while the ids are dense and a hash map when they are sparse (csrc/ctx.h: IdIndex);
+    slam_b200_warmup optimises a synthetic ring first and must leave the context empty.  The same graph with the
+    reference's numbering, with ids scattered over 2^30 (bulk load and incremental API), and after a warm-up gives
+    bit-identical estimates: none of this touches the arithmetic."""
+    import copy
+    g = small_graph(synth, 120)
+    ctx = pkg.Context(0)
+    ctx.graph_load(g)
+    n0, chi0 = ctx.graph_optimize(5)
+    pe0, le0 = ctx.graph_get_estimates()
+    ctx.close()
+    rng = np.random.default_rng(3)
+    # order-preserving sparse renumbering (the Hessian order is by ascending id)
+    all_ids = np.sort(np.concatenate([g.lm_ids, g.pose_ids]))
+    new = np.sort(rng.choice(np.arange(1, 1 << 30), size=len(all_ids), replace=False)).astype(np.int32)
+    remap = dict(zip(all_ids.tolist(), new.tolist()))
+    m = np.vectorize(remap.get)
+    g2 = copy.copy(g)
+    g2.lm_ids, g2.pose_ids = m(g.lm_ids).astype(np.int32), m(g.pose_ids).astype(np.int32)
+    g2.eo_from, g2.eo_to = m(g.eo_from).astype(np.int32), m(g.eo_to).astype(np.int32)
+    g2.el_pose, g2.el_lm = m(g.el_pose).astype(np.int32), m(g.el_lm).astype(np.int32)
+    g2.fixed_ids = m(g.fixed_ids).astype(np.int32)
+    ctx = pkg.Context(0)
+    ctx.warmup(256, 80)
+    assert ctx.graph_num_poses() == 0 and ctx.graph_num_landmarks() == 0 and ctx.map_size() == 0
+    ctx.graph_load(g2)
+    n1, chi1 = ctx.graph_optimize(5)
+    pe1, le1 = ctx.graph_get_estimates()
+    assert n0 == n1 == 5 and np.array_equal(chi0, chi1) and np.array_equal(pe0, pe1) and np.array_equal(le0, le1)
+    assert np.array_equal(ctx.graph_get_vertex(int(g2.pose_ids[7])), pe1[7])
+    # incremental API with the sparse ids, poses first (the id range grows downwards and upwards)
+    ctx.graph_clear()
+    for i, vid in enumerate(g2.pose_ids):
+        ctx.graph_add_pose(int(vid), *g2.pose_est[i])
+    for i, vid in enumerate(g2.lm_ids):
+        ctx.graph_add_landmark(int(vid), *g2.lm_est[i])
+    for e in range(len(g2.eo_from)):
+        ctx.graph_add_edge_se2(int(g2.eo_from[e]), int(g2.eo_to[e]), g2.eo_z[e], g2.eo_info[e])
+    for e in range(len(g2.el_pose)):
+        ctx.graph_add_edge_se2_xy(int(g2.el_pose[e]), int(g2.el_lm[e]), g2.el_z[e], g2.el_info[e])
+    for vid in g2.fixed_ids:
+        ctx.graph_set_fixed(int(vid), True)
+    n2, chi2 = ctx.graph_optimize(5)
+    pe2, le2 = ctx.graph_get_estimates()
+    assert n2 == 5 and np.allclose(chi2, chi0, rtol=1e-12) and np.allclose(pe2, pe0, rtol=0, atol=1e-12)
+    ctx.close()
