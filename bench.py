@@ -397,7 +397,7 @@ def bench_assoc(pkg, torch, args, world, rank, local, field, n_total):
         train_batched={"ms_per_frame": trains["batched"]["ms_per_frame"], "assoc_per_s": trains["batched"]["assoc_per_s"],
                        "frac_of_hbm": roof(trains["batched"]["ms_per_frame"]) / hbm,
                        "identical_to_single_launch": trains["batched"]["identical_to_single_launch"],
-                       "note": "SLAM_B200_ALGO_GRID_BATCHED: eight frames per launch (blockIdx.y = frame), no programmatic "
+                       "note": "SLAM_B200_ALGO_GRID_BATCHED: up to 32 frames per launch (blockIdx.y = frame), no programmatic "
                                "dependent launch; the same train, timed the same way"},
         identical_to_single_launch=bool(tp["identical_to_single_launch"] and trains["train"]["identical_to_single_launch"]
                                         and trains["batched"]["identical_to_single_launch"]),

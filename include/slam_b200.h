@@ -54,7 +54,7 @@ typedef struct slam_b200_ctx slam_b200_ctx;
                                       * flight its own idx buffer and reads results after a stream
                                       * synchronisation, an event, or any ordinary launch/copy     */
 
-#define SLAM_B200_ALGO_GRID_BATCHED 3 /* slam_b200_assoc_bulk_frames_dev only: ALGO_GRID with up to eight
+#define SLAM_B200_ALGO_GRID_BATCHED 3 /* slam_b200_assoc_bulk_frames_dev only: ALGO_GRID with up to 32
                                       * independent frames per launch (frozen maps), all on the stream of the
                                       * first frame's context; same results, same rules for the idx buffers   */
 
@@ -161,7 +161,7 @@ int slam_b200_assoc_bulk_dev(slam_b200_ctx* ctx, const double* cones4xN_dev, int
 /* A train of independent frames (frame f: context ctxs[f] -- the same handle or replicas sharing
  * one stream --, cones_dev[f] = 4 x n[f] doubles, poses[3f..3f+2], idx_dev[f]); one launch each,
  * back to back.  With SLAM_B200_ALGO_GRID_PIPELINED the frames overlap on the device; with
- * SLAM_B200_ALGO_GRID_BATCHED eight frames share one launch (contexts on one device; the work goes to the stream
+ * SLAM_B200_ALGO_GRID_BATCHED up to 32 frames share one launch (contexts on one device; the work goes to the stream
  * of ctxs[0]).  Returns n_frames. */
 int slam_b200_assoc_bulk_frames_dev(int n_frames, slam_b200_ctx* const* ctxs, const double* const* cones4xN_dev,
                                     const int* n, const double* poses3, double threshold, int gate, int algo,

@@ -651,12 +651,12 @@ assoc_bulk_grid_kernel(const double* __restrict__ cones, int n, PoseTrig pt, dou
   grid_match_one<GATE>(cones, i, pt, thr2x, gp, cell_start, rec, idx);
 }
 
-// SLAM_B200_ALGO_GRID_BATCHED: up to BATCH_FRAMES independent frames against frozen maps in ONE launch
+// SLAM_B200_ALGO_GRID_BATCHED: up to BATCH_FRAMES (32) independent frames against frozen maps in ONE launch
 // (blockIdx.y = frame).  A single frame is one sub-wave of threads on a three-deep dependent-load chain and cannot
 // fill the memory system however it is written; several frames in one grid can, without
 // the per-launch cost the pipelined train still pays for every frame (about 2 us each: what caps a rank that holds
 // an eighth of the observations).
-constexpr int BATCH_FRAMES = 8;
+constexpr int BATCH_FRAMES = 32;  // 32 x 112 bytes of per-frame parameters: inside the 4 KB kernel-parameter block
 struct BatchFrame {
   const double* cones;
   const int* cell_start;

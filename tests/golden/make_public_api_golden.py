@@ -116,9 +116,23 @@ def main():
     yaw0 = [(0.0, 500 * 1000000)] * len(d.frames)   # far outside the (0, 1 s) window: no heading correction
     drives = {"c1": (d.frames, d.poses_noisy, yaw0)}
     drives["odd"] = odd_drive(synth)
-    for name, (frames, poses, yaw) in drives.items():
+    # six of the adversarial replays that pin the back half directly (make_fuzz_reference_replay.py), now through the
+    # Envelopes: other gates (sameConeThreshold 0.8 / 2.0, coneMappingThreshold 9), repeated and scrambled columns,
+    # non-integer types (truncated by the uint32 wire field), NaN cones in open drives, random yaw rates
+    from make_fuzz_reference_replay import scenarios, scenarios_yaw
+    extra = {}
+    far = (0.0, 500 * 1000000)
+    for name, frames, poses, thr, map_thr in scenarios(synth):
+        if name in ("loop1", "loop2", "loop5", "nan0", "nan2"):
+            extra[name] = (frames, poses, [far] * len(frames), thr, map_thr)
+    for name, frames, poses, thr, map_thr, yaw in scenarios_yaw(synth):
+        if name == "yaw1":
+            extra[name] = (frames, poses, yaw, thr, map_thr)
+    drives = {k: v + (synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD) for k, v in drives.items()}
+    drives.update(extra)
+    for name, (frames, poses, yaw, thr, map_thr) in drives.items():
         path = os.path.join(HERE, "public_api_drive_%s.bin" % name)
-        write_drive(path, frames, poses, synth.SAME_CONE_THRESHOLD, synth.CONE_MAPPING_THRESHOLD, yaw)
+        write_drive(path, frames, poses, thr, map_thr, yaw)
         r = run(exe, path)
         r2 = run(exe, path)   # the front half runs on the wall clock: the result must not depend on it
         for k in r:

@@ -95,7 +95,7 @@ def test_public_api_c1_equals_the_direct_replay():
     assert np.array_equal(g["c1_map"][:, 2], r["map_type"]) and np.array_equal(g["c1_map"][:, 3], r["map_id"])
 
 
-@pytest.mark.parametrize("name", ["odd", "c1"])
+@pytest.mark.parametrize("name", ["odd", "c1", "loop1", "loop2", "loop5", "nan0", "nan2", "yaw1"])
 def test_frame_assembler_and_oracle_equal_the_reference_front_and_back_half(pkg, orc, name):
     """the messages the harness sent, assembled by FrameAssembler on injected time stamps and run
     through the oracle's performSLAM, against what the reference's own nextCone / initializeCollection / isKeyframe /

@@ -22,7 +22,7 @@ EXE = os.path.join(ROOT, "integration", "_build", "patched_public_replay")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["odd", "c1"])
+@pytest.mark.parametrize("name", ["odd", "c1", "loop1", "loop2", "loop5", "nan0", "nan2", "yaw1"])
 def test_patched_reference_tree_equals_the_reference_through_the_public_api(pkg, name):
     import make_public_api_golden as mk
     if not os.path.exists(EXE):
