@@ -45,6 +45,25 @@ struct SymArgs {
 // Two barriers per NB pivots.  Columns stay unscaled (F[i,k] = l_ik d_k) until the write-out.
 constexpr int NB = 8;
 
+// ---- programmatic dependent launch (single-graph path) ---------------------------------------------
+// The levels of the assembly tree are dependent launches of 7-70 us each; a quarter of a level is spent before the
+// first byte of the previous level's output is needed (launch latency, the index chain launch list -> front sizes ->
+// assembly entries, zeroing the front, scattering the H blocks / staging the L panel).  The front kernels are
+// therefore launched with cudaLaunchAttributeProgrammaticStreamSerialization and follow ONE protocol:
+//   prologue (reads only the static structure and data of kernels at least TWO launches back) ->
+//   griddepcontrol.wait (the previous launch has completed, its writes are visible) ->
+//   griddepcontrol.launch_dependents (the next launch may become resident and run its prologue) -> body.
+// Because a CTA releases its dependents only after its own wait, a prologue never overlaps anything older than the
+// launch directly before it: what it reads (V from the assembly kernels, L from the factor kernels) is complete unless
+// that launch is the producer itself -- the first factor launch (V) and the first backward launch (L) get early = 0
+// and wait before they touch anything.  Data of the previous launch (children's Schur complements and update
+// vectors, the parents' x) is read after the wait with ld.global.cg.  Without the launch attribute both
+// instructions are no-ops.  SLAM_B200_NO_PDL=1 launches everything the plain way (A/B measurements).
+__device__ __forceinline__ void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(FACTOR_THREADS)
 factor_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV, double* Lv_all, long nL,
@@ -366,7 +385,7 @@ template <bool SMEM>
 __global__ void __launch_bounds__(FACTOR_THREADS)
 factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV, double* Lv_all, long nL,
                double* Uv_all, long nU, double* Fbig_all, long nFbig, int* status, double* uvec_all, long nUvec,
-               double* x_all, int n, int la_idle) {
+               double* x_all, int n, int la_idle, int early) {
   extern __shared__ double smem[];
   const int g = S.launch_list[list_off + blockIdx.x];
   const int r = blockIdx.y;
@@ -379,6 +398,8 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const bool dbgc = S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
   if (dbgc) { S.dbg[0] = clock64(); for (int k = 24; k < 32; k++) S.dbg[k] = 0; }
+  // the global scratch slab of a front beyond shared memory may still be in use by the previous launch
+  if (!SMEM || !early) pdl_wait_then_release();
   for (int t = tid; t < fs * ld; t += nt) F[t] = 0.0;
   __syncthreads();
   if (dbgc) S.dbg[1] = clock64();
@@ -389,22 +410,23 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
     const bool trans = (en.meta >> 16) & 1, diag = (en.meta >> 17) & 1;
     if (diag) {
       for (int i = 0; i < dr; i++)
-        for (int j = 0; j <= i; j++) F[(size_t)(en.c + j) * ld + en.r + i] = hv[i * dc + j];
+        for (int j = 0; j <= i; j++) F[(size_t)(en.c + j) * ld + en.r + i] = __ldcg(hv + i * dc + j);
     } else if (!trans) {
       for (int i = 0; i < dr; i++)
-        for (int j = 0; j < dc; j++) F[(size_t)(en.c + j) * ld + en.r + i] = hv[i * dc + j];
+        for (int j = 0; j < dc; j++) F[(size_t)(en.c + j) * ld + en.r + i] = __ldcg(hv + i * dc + j);
     } else {
       for (int i = 0; i < dc; i++)
-        for (int j = 0; j < dr; j++) F[(size_t)(en.c + j) * ld + en.r + i] = hv[j * dc + i];
+        for (int j = 0; j < dr; j++) F[(size_t)(en.c + j) * ld + en.r + i] = __ldcg(hv + j * dc + i);
     }
   }
+  if (SMEM && early) pdl_wait_then_release();  // everything below reads what the previous launch wrote
   {  // right-hand side row: rhs of the pivots + the children's update vectors, fixed (child) order
     const int p0 = S.piv0[g];
     const double* uvecr = uvec_all + (size_t)r * nUvec;
     const int* gp = S.gather_ptr + S.frow_ptr[g];
     for (int i = tid; i < fs; i += nt) {
-      double acc = i < s ? V[S.solver2v[p0 + i]] : 0.0;
-      for (int q = gp[i]; q < gp[i + 1]; q++) acc += uvecr[S.gather_src[q]];
+      double acc = i < s ? __ldcg(V + S.solver2v[p0 + i]) : 0.0;
+      for (int q = gp[i]; q < gp[i + 1]; q++) acc += __ldcg(uvecr + S.gather_src[q]);
       F[(size_t)i * ld + fs] = acc;
     }
   }
@@ -430,8 +452,8 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           const int ia = j + i0 + 32 * c + lane, ib = jb + i0 + 32 * c + lane;
-          va[c] = ia < uc ? __ldg(colA + ia) : 0.0;
-          vb[c] = (hb && ib < uc) ? __ldg(colB + ib) : 0.0;
+          va[c] = ia < uc ? __ldcg(colA + ia) : 0.0;
+          vb[c] = (hb && ib < uc) ? __ldcg(colB + ib) : 0.0;
         }
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -882,9 +904,11 @@ backward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restric
   double* x = x_all + (size_t)r * n;
   const int* rows = S.upd_rows + S.rows_ptr[g];
   const int i0 = lane, i1 = lane + 32;
+  const int r0 = (i0 >= s && i0 < fs) ? rows[i0 - s] : 0, r1 = (i1 >= s && i1 < fs) ? rows[i1 - s] : 0;
+  pdl_wait_then_release();  // the parents' x comes from the previous launch
   double x0 = 0.0, x1 = 0.0;
-  if (i0 < fs) x0 = i0 < s ? x[p0 + i0] : x[rows[i0 - s]];
-  if (i1 < fs) x1 = i1 < s ? x[p0 + i1] : x[rows[i1 - s]];
+  if (i0 < fs) x0 = __ldcg(i0 < s ? x + p0 + i0 : x + r0);
+  if (i1 < fs) x1 = __ldcg(i1 < s ? x + p0 + i1 : x + r1);
   for (int kb = ((s - 1) / 4) * 4; kb >= 0; kb -= 4) {
     double l0[4], l1[4];
 #pragma unroll
@@ -1482,7 +1506,7 @@ forward_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
 // ---- backward solve: L^T x = z, root -> leaves ----------------------------------------------------
 template <bool SMEM>
 __global__ void __launch_bounds__(SOLVE_THREADS)
-backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long nL, double* x_all, int n) {
+backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long nL, double* x_all, int n, int early) {
   extern __shared__ double smem[];
   const int g = S.launch_list[list_off + blockIdx.x];
   const int r = blockIdx.y;
@@ -1496,8 +1520,12 @@ backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long
   double* xo = smem + fs;       // s
   double* Ls = smem + fs + s;
   const int* rows = S.upd_rows + S.rows_ptr[g];
-  for (int i = tid; i < fs; i += nt) xs[i] = i < s ? x[p0 + i] : x[rows[i - s]];
+  // early: this front's L panel was written at least two launches back and is staged while the previous backward
+  // launch still runs (the first backward launch follows the root's factor launch directly: early = 0)
+  if (!early) pdl_wait_then_release();
   if (SMEM) stage_panel(Ls, Lg, fs, s, ld, warp, nw, lane);
+  if (early) pdl_wait_then_release();
+  for (int i = tid; i < fs; i += nt) xs[i] = __ldcg(i < s ? x + p0 + i : x + rows[i - s]);
   __syncthreads();
   const double* Lp = SMEM ? Ls : Lg;
   // contribution of the already-solved ancestor rows: xs[k] -= sum_{i>=s} L[i,k] xs[i]
@@ -1553,6 +1581,28 @@ bool warp_kernels(const slam_b200_ctx* c, const DeviceSystem& D, const LevelLaun
 
 size_t factor_extra_smem(int max_fs) {  // srel (ints, even count) + scaled panel
   return (size_t)((max_fs + 1) & ~1) * sizeof(int) + ((size_t)(NB + 2) * max_fs + 2 * (NB * NB + 2 * NB)) * sizeof(double);
+}
+
+// Launch with programmatic stream serialisation (see pdl_wait_then_release): the kernel may become resident as soon as
+// every CTA of the launch before it on the stream has released its dependents.  Captured into the iteration's CUDA
+// graph the attribute becomes a programmatic dependency edge.
+bool pdl_enabled() {
+  static const bool on = getenv("SLAM_B200_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_front(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 SymArgs sym_args(const DeviceSystem& D) {
@@ -1764,6 +1814,9 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   // SLAM_B200_FACTOR_VARIANT=3: large fronts by the register-resident factor3_kernel (measured: no faster, factor3.cuh)
   static const bool gen3 = getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 3;
   static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
+  // programmatic dependent launch: 0 until a launch of this enqueue has gone out whose wait proves that the assembly
+  // kernels (V) / the factor kernels (L) are complete -- see pdl_wait_then_release
+  int early_v = 0, early_l = 0;
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
     if (LL.n_tiny && warp_kernels(c, D, LL)) {
@@ -1780,11 +1833,12 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       }
     } else if (LL.n_tiny) {
       dim3 grid(LL.n_tiny, D.R);
-      if (gen2)
-        factor2_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
+      if (gen2) {
+        SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(128), LL.smem_tiny + factor_extra_smem(64), c->stream,
             S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
-            D.x.p, D.n, la_idle);
-      else
+            D.x.p, D.n, la_idle, early_v));
+        early_v = 1;
+      } else
         factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
             S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
             D.x.p, D.n);
@@ -1801,11 +1855,12 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       if (gen3 && max_nloc <= 8 * F3_MAX_T && f3_smem_bytes(max_nloc) <= smem_limit) {
         factor3_kernel<<<grid, F3_THREADS, f3_smem_bytes(max_nloc), c->stream>>>(
             S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n);
-      } else if (gen2)
-        factor2_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
+      } else if (gen2) {
+        SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(FACTOR_THREADS), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
             S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
-            D.nUvec, D.x.p, D.n, la_idle);
-      else
+            D.nUvec, D.x.p, D.n, la_idle, early_v));
+        early_v = 1;
+      } else
         factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
             S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
             D.nUvec, D.x.p, D.n);
@@ -1813,11 +1868,12 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     }
     if (LL.n_big) {
       dim3 grid(LL.n_big, D.R);
-      if (gen2)
-        factor2_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
+      if (gen2) {
+        SLAM_CUDA_TRY(c, launch_front(factor2_kernel<false>, grid, dim3(FACTOR_THREADS), factor_extra_smem(LL.max_fs), c->stream,
             S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
-            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n, la_idle);
-      else
+            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n, la_idle, early_v));
+        early_v = 1;
+      } else
         factor_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
             S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
             D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n);
@@ -1875,14 +1931,16 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       bool fits;
       rest_smem(lv, need, wneed, fits);
       if (fits)
-        backward_kernel<true><<<grid, SOLVE_THREADS, need, c->stream>>>(S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n);
+        SLAM_CUDA_TRY(c, launch_front(backward_kernel<true>, grid, dim3(SOLVE_THREADS), need, c->stream, S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n, early_l));
       else
-        backward_kernel<false><<<grid, SOLVE_THREADS, wneed, c->stream>>>(S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n);
+        SLAM_CUDA_TRY(c, launch_front(backward_kernel<false>, grid, dim3(SOLVE_THREADS), wneed, c->stream, S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n, early_l));
+      early_l = 1;
       c->launches++;
     }
     if (LL.n_tiny) {
       dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
-      backward_tiny_kernel<<<grid, TINY_WARPS * 32, 0, c->stream>>>(S, LL.list_off, LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n);
+      SLAM_CUDA_TRY(c, launch_front(backward_tiny_kernel, grid, dim3(TINY_WARPS * 32), 0, c->stream, S, LL.list_off, LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n));
+      early_l = 1;
       c->launches++;
     }
   }
