@@ -59,6 +59,8 @@ constexpr int NB = 8;
 // and wait before they touch anything.  Data of the previous launch (children's Schur complements and update
 // vectors, the parents' x) is read after the wait with ld.global.cg.  Without the launch attribute both
 // instructions are no-ops.  SLAM_B200_NO_PDL=1 launches everything the plain way (A/B measurements).
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void pdl_wait_then_release() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -419,7 +421,26 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
         for (int j = 0; j < dr; j++) F[(size_t)(en.c + j) * ld + en.r + i] = __ldcg(hv + j * dc + i);
     }
   }
-  if (SMEM && early) pdl_wait_then_release();  // everything below reads what the previous launch wrote
+  if (SMEM && early) {
+    // still in the shadow of the previous launch: pull the static lists the body walks right after the wait (gather
+    // list of the right-hand side, the children's sizes, offsets and row maps) into L1, so that each of them costs an
+    // L1 hit instead of one more L2 / HBM round trip on the front's dependent chain
+    const int* gp = S.gather_ptr + S.frow_ptr[g];
+    for (int i = tid; i <= fs; i += nt) prefetch_l1(gp + i);
+    {
+      const int q0 = gp[0], q1 = gp[fs];
+      for (int q = q0 + 32 * tid; q < q1; q += 32 * nt) prefetch_l1(S.gather_src + q);
+    }
+    if (tid < fs) prefetch_l1(S.solver2v + S.piv0[g] + tid);
+    for (int ci = S.child_ptr[g] + warp; ci < S.child_ptr[g + 1]; ci += nw) {
+      const int ch = S.children[ci];
+      const int uc = S.nupd[ch];
+      const int* rel = S.rel + S.rows_ptr[ch];
+      if (lane == 0) prefetch_l1(S.uptr + ch);
+      for (int i = 32 * lane; i < uc; i += 32 * 32) prefetch_l1(rel + i);
+    }
+    pdl_wait_then_release();  // everything below reads what the previous launch wrote
+  }
   {  // right-hand side row: rhs of the pivots + the children's update vectors, fixed (child) order
     const int p0 = S.piv0[g];
     const double* uvecr = uvec_all + (size_t)r * nUvec;
@@ -430,40 +451,72 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
       F[(size_t)i * ld + fs] = acc;
     }
   }
-  __syncthreads();
-  if (dbgc) S.dbg[2] = clock64();
+  // ---- extend-add ----
+  // The row maps (rel) of ALL children go to shared memory first -- into the panel scratch behind the front, which is
+  // idle until the panel loop (>= 21 fs + 320 ints, factor_extra_smem) -- together with the right-hand side above: one
+  // barrier.  A child's Schur complement (uc x uc, lower part valid) is then walked with up to ECB columns x
+  // ERC row chunks per warp requested before the first entry is added: one L2 round trip per child for uc <= 96 on 16
+  // warps instead of one per 32 columns (uc = 92: 3 rounds + the row map's before; 4 warps, uc = 47: 2 instead of 6).
+  // Children stay sequential with a barrier between them: two children may add to the same entry, and the order of
+  // the sum is fixed.
+  constexpr int ECB = 6, ERC = 3;
   int* srel = reinterpret_cast<int*>(smem + (SMEM ? (size_t)fs * ld : 0));
+  const int srel_cap = ((fs + 1) & ~1) + 2 * ((NB + 2) * fs + 2 * (NB * NB + 2 * NB));
+  int rel_total = 0;
   for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
     const int ch = S.children[ci];
     const int uc = S.nupd[ch];
-    const double* __restrict__ Uc = Uv + S.uptr[ch];
-    const int* rel = S.rel + S.rows_ptr[ch];
-    for (int i = tid; i < uc; i += nt) srel[i] = rel[i];
-    __syncthreads();
-    for (int j = warp; j < uc; j += 2 * nw) {  // two columns, four row chunks each, loaded before any update
-      const int jb = j + nw;
-      const bool hb = jb < uc;
-      const double* colA = Uc + (size_t)j * uc;
-      const double* colB = Uc + (size_t)(hb ? jb : j) * uc;
-      double* dstA = F + (size_t)srel[j] * ld;
-      double* dstB = F + (size_t)srel[hb ? jb : j] * ld;
-      for (int i0 = 0; i0 < uc - j; i0 += 128) {
-        double va[4], vb[4];
+    if (rel_total + uc <= srel_cap) {
+      const int* rel = S.rel + S.rows_ptr[ch];
+      for (int i = tid; i < uc; i += nt) srel[rel_total + i] = rel[i];
+    }
+    rel_total += uc;
+  }
+  const bool staged = rel_total <= srel_cap;  // block-uniform
+  __syncthreads();
+  if (dbgc) S.dbg[2] = clock64();
+  int roff = 0;
+  for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
+    const int ch = S.children[ci];
+    const int uc = S.nupd[ch];
+    const double* Uc = Uv + S.uptr[ch];
+    const int* sr = srel + roff;
+    if (!staged) {  // more children than the scratch holds (not seen on SLAM graphs): one map at a time
+      const int* rel = S.rel + S.rows_ptr[ch];
+      sr = srel;
+      for (int i = tid; i < uc; i += nt) srel[i] = rel[i];
+      __syncthreads();
+    }
+    // warp w takes the columns w, w + nw, ...: ECB columns x ERC chunks of 32 rows requested before the first add
+    for (int jb = warp; jb < uc; jb += nw * ECB) {
+      for (int i0 = 0; i0 < uc - jb; i0 += 32 * ERC) {
+        double v[ECB][ERC];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int ia = j + i0 + 32 * c + lane, ib = jb + i0 + 32 * c + lane;
-          va[c] = ia < uc ? __ldcg(colA + ia) : 0.0;
-          vb[c] = (hb && ib < uc) ? __ldcg(colB + ib) : 0.0;
+        for (int c = 0; c < ECB; c++) {
+          const int j = jb + c * nw;
+          const double* col = Uc + (size_t)j * uc;
+#pragma unroll
+          for (int rc = 0; rc < ERC; rc++) {
+            const int i = j + i0 + 32 * rc + lane;
+            v[c][rc] = (j < uc && i < uc) ? __ldcg(col + i) : 0.0;
+          }
         }
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          const int ia = j + i0 + 32 * c + lane, ib = jb + i0 + 32 * c + lane;
-          if (ia < uc) dstA[srel[ia]] += va[c];
-          if (hb && ib < uc) dstB[srel[ib]] += vb[c];
+        for (int c = 0; c < ECB; c++) {
+          const int j = jb + c * nw;
+          if (j < uc) {  // warp-uniform
+            double* dcol = F + (size_t)sr[j] * ld;
+#pragma unroll
+            for (int rc = 0; rc < ERC; rc++) {
+              const int i = j + i0 + 32 * rc + lane;
+              if (i < uc) dcol[sr[i]] += v[c][rc];
+            }
+          }
         }
       }
     }
     __syncthreads();
+    roff += uc;
   }
   if (dbgc) S.dbg[3] = clock64();
   double* Sp = reinterpret_cast<double*>(srel + ((fs + 1) & ~1));  // NB x ld: scaled panel (incl. the rhs row)
@@ -535,11 +588,13 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
       if (dbgc) { const long long t_ = clock64(); S.dbg[25] += t_ - dt_; dt_ = t_; }
       if (factor_triangle(F + (size_t)c0 * ld + c0, 1, ld, Tn, min(NB, s - c0)) && lane == 0) status[2 * r] = 1;
       if (dbgc) { const long long t_ = clock64(); S.dbg[24] += t_ - dt_; dt_ = t_; }
-    } else if (!ahead || !la_idle || (warp & 3) != 0) {
-      // la_idle: warps 4, 8, 12 share warp 0's scheduler and FP64 pipe and sit a look-ahead step out
+    } else if (!ahead || !(la_idle > 0 && fs - c0 <= la_idle) || (warp & 3) != 0) {
+      // la_idle (rows): warps 4, 8, 12 share warp 0's scheduler and FP64 pipe and sit a look-ahead step out when the
+      // trailing matrix has at most that many rows (a short update: the triangle chain is what the panel waits for)
+      const bool idle_mates = la_idle > 0 && fs - c0 <= la_idle;
       int wi = warp, nwt = nw;
       if (ahead) {
-        if (la_idle) { wi = (warp >> 2) * 3 + (warp & 3) - 1; nwt = (nw >> 2) * 3; }
+        if (idle_mates) { wi = (warp >> 2) * 3 + (warp & 3) - 1; nwt = (nw >> 2) * 3; }
         else { wi = warp - 1; nwt = nw - 1; }
       }
       bool owe = ahead && wi < 2;  // producer of the next panel's columns: signal warp 0 after the first group
@@ -1524,8 +1579,10 @@ backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long
   // launch still runs (the first backward launch follows the root's factor launch directly: early = 0)
   if (!early) pdl_wait_then_release();
   if (SMEM) stage_panel(Ls, Lg, fs, s, ld, warp, nw, lane);
+  const int xi0 = tid < fs ? (tid < s ? p0 + tid : rows[tid - s]) : 0;  // static: fetched before the wait
   if (early) pdl_wait_then_release();
-  for (int i = tid; i < fs; i += nt) xs[i] = __ldcg(i < s ? x + p0 + i : x + rows[i - s]);
+  if (tid < fs) xs[tid] = __ldcg(x + xi0);
+  for (int i = tid + nt; i < fs; i += nt) xs[i] = __ldcg(i < s ? x + p0 + i : x + rows[i - s]);
   __syncthreads();
   const double* Lp = SMEM ? Ls : Lg;
   // contribution of the already-solved ancestor rows: xs[k] -= sum_{i>=s} L[i,k] xs[i]
