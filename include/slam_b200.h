@@ -275,6 +275,10 @@ int slam_b200_profile_read(slam_b200_ctx* ctx, double out[8]);
 int slam_b200_debug_phase_clocks(slam_b200_ctx* ctx, long long out[10]);
 int slam_b200_debug_tiny_clocks(slam_b200_ctx* ctx, long long out[8]);
 int slam_b200_debug_panel_clocks(slam_b200_ctx* ctx, long long out[8]);
+/* Debug aid: front timeline of the last Gauss-Newton iteration (SLAM_B200_TIMELINE set at prepare time): six
+ * %globaltimer stamps (ns) per front -- factor kernel entry / after its dependency wait / end, backward kernel entry /
+ * after its wait / end.  Returns 6 x fronts (query with out == NULL), -1 when the mode is off. */
+long slam_b200_debug_timeline(slam_b200_ctx* ctx, long long* out, long cap);
 /* Guard-band mode (environment SLAM_B200_GUARD=1 before the first context; tests and debugging): every
  * device array is allocated with 4 KiB of 0xFF in front of and behind it and is itself filled with 0xFF
  * (fp64 NaN / int32 -1), so out-of-bounds and uninitialised READS poison the results the parity tests

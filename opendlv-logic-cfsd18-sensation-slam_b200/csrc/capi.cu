@@ -837,6 +837,19 @@ int slam_b200_debug_panel_clocks(slam_b200_ctx* c, long long out[8]) try {
   return 0;
 } SLAM_ABI_CATCH(c)
 
+// Debug: front timeline (SLAM_B200_TIMELINE=1 at prepare time): six %globaltimer stamps (ns) per front of the last
+// iteration -- factor kernel entry / after its wait / end, backward kernel entry / after its wait / end -- in the
+// front numbering of slam_b200_graph_export_symbolic.  Returns the number of values (6 x fronts), copies min(cap, that).
+long slam_b200_debug_timeline(slam_b200_ctx* c, long long* out, long cap) try {
+  if (!c || !c->sys || !c->sys->timeline.p) return -1;
+  if (ctx_set_device(c)) return -1;
+  const long n = 12L * c->sys->sym.nf;
+  if (!out) return n;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(out, c->sys->timeline.p, sizeof(long long) * (size_t)std::min(n, cap), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
+} catch (...) { return -1; }
+
 // ---- symbolic analysis without a device (host logic; testable on a CPU-only box) ----------------
 struct SymHandle {
   Symbolic S;

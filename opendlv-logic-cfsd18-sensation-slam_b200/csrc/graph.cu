@@ -1621,6 +1621,10 @@ int graph_alloc_values(slam_b200_ctx* c, int R) {
       SLAM_CUDA_TRY(c, D.dbg_clocks.exact(32));
       SLAM_CUDA_TRY(c, cudaMemsetAsync(D.dbg_clocks.p, 0, sizeof(long long) * 32, c->stream));
     }
+    if (getenv("SLAM_B200_TIMELINE") && D.sym.nf > 0) {
+      SLAM_CUDA_TRY(c, D.timeline.exact(12 * (size_t)D.sym.nf));
+      SLAM_CUDA_TRY(c, cudaMemsetAsync(D.timeline.p, 0, sizeof(long long) * 12 * (size_t)D.sym.nf, c->stream));
+    }
     SLAM_CUDA_TRY(c, D.est0.exact(r * D.estStride));
     SLAM_CUDA_TRY(c, D.trig.exact(r * 2 * (size_t)D.P));
     D.R = R;
@@ -1712,7 +1716,7 @@ void graph_release(slam_b200_ctx* c) {
   D.tile_list.release(); D.tile_item_ptr.release(); D.tile_item_nv.release(); D.tile_fptr.release(); D.tile_items.release();
   D.est.release(); D.meas.release(); D.V.release(); D.Lv.release(); D.Uv.release(); D.uvec.release();
   D.x.release(); D.Fbig.release(); D.chi2.release(); D.chi2_part.release(); D.status.release();
-  D.est0.release(); D.trig.release(); D.dbg_clocks.release(); D.lmo_pose.release(); D.lmo_info.release();
+  D.est0.release(); D.trig.release(); D.dbg_clocks.release(); D.timeline.release(); D.lmo_pose.release(); D.lmo_info.release();
   xchg_release(D);
   D.drop_graph();
   delete c->sys;

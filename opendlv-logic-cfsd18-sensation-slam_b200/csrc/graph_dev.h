@@ -109,6 +109,7 @@ struct DeviceSystem {
   DevBuf<double> est, meas, V, Lv, Uv, uvec, x, Fbig, chi2, chi2_part, est0, trig;
   DevBuf<int> status;              // per replica: [0] fail flag, [1] iterations done (= chi2 slot)
   DevBuf<long long> dbg_clocks;    // optional (SLAM_B200_PHASE_CLOCKS): phase clocks of one factor CTA
+  DevBuf<long long> timeline;      // optional (SLAM_B200_TIMELINE): %globaltimer stamps per front, 6 per front
   PeerExchange xchg;
   int chi2_cap = 0, chi2_blocks = 0;
   int iters_enqueued = 0;

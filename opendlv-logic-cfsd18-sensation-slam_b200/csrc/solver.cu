@@ -26,6 +26,9 @@ struct SymArgs {
   const int *piv0, *npiv, *nupd, *rows_ptr, *upd_rows, *rel, *child_ptr, *children, *asm_ptr, *solver2v;
   const int *frow_ptr, *gather_ptr, *gather_src;
   long long* dbg;  // optional phase clocks of the last-launched CTA-per-front kernel (SLAM_B200_PHASE_CLOCKS)
+  int dbg_front;   // front whose CTA records the phase clocks (-1: block 0 of every launch, the last one wins)
+  long long* tl;   // optional front timeline (SLAM_B200_TIMELINE): per front %globaltimer at factor entry / after the
+                   // wait / end, backward entry / after the wait / end
   const long *lptr, *uptr, *fbig;
   const AsmEntry* asm_entries;
   const int* launch_list;
@@ -59,6 +62,14 @@ constexpr int NB = 8;
 // and wait before they touch anything.  Data of the previous launch (children's Schur complements and update
 // vectors, the parents' x) is read after the wait with ld.global.cg.  Without the launch attribute both
 // instructions are no-ops.  SLAM_B200_NO_PDL=1 launches everything the plain way (A/B measurements).
+constexpr int TLS = 12;  // stamps per front in the timeline: factor entry / wait passed / rhs + row maps staged /
+                         // children added / panels done / end, backward entry / wait passed / end, 3 spare
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void pdl_wait_then_release() {
@@ -387,9 +398,12 @@ template <bool SMEM>
 __global__ void __launch_bounds__(FACTOR_THREADS)
 factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long nV, double* Lv_all, long nL,
                double* Uv_all, long nU, double* Fbig_all, long nFbig, int* status, double* uvec_all, long nUvec,
-               double* x_all, int n, int la_idle, int early) {
+               double* x_all, int n, int la_idle, int flags) {
   extern __shared__ double smem[];
-  const int g = S.launch_list[list_off + blockIdx.x];
+  // flags & 2: walk the launch list backwards -- the fronts of a class are listed by ascending size, and a level of
+  // more than one wave of CTAs ends earlier when its largest fronts start first
+  const int early = flags & 1;
+  const int g = S.launch_list[list_off + ((flags & 2) ? gridDim.x - 1 - blockIdx.x : blockIdx.x)];
   const int r = blockIdx.y;
   const int s = S.npiv[g], u = S.nupd[g], fs = s + u;
   const int ld = fs + 1;  // rows 0..fs-1: the front; row fs: the right-hand side
@@ -398,10 +412,13 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   double* F = SMEM ? smem : (Fbig_all + (size_t)r * nFbig + S.fbig[g]);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  const bool dbgc = S.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+  // phase clocks: block 0 of the last launch (the root), or the front SLAM_B200_DBG_FRONT names
+  const bool dbgc = S.dbg && blockIdx.y == 0 && tid == 0 && (S.dbg_front >= 0 ? g == S.dbg_front : blockIdx.x == 0);
   if (dbgc) { S.dbg[0] = clock64(); for (int k = 24; k < 32; k++) S.dbg[k] = 0; }
+  const bool tlc = S.tl && blockIdx.y == 0 && tid == 0;
+  if (tlc) S.tl[TLS * g] = global_ns();
   // the global scratch slab of a front beyond shared memory may still be in use by the previous launch
-  if (!SMEM || !early) pdl_wait_then_release();
+  if (!SMEM || !early) { pdl_wait_then_release(); if (tlc) S.tl[TLS * g + 1] = global_ns(); }
   for (int t = tid; t < fs * ld; t += nt) F[t] = 0.0;
   __syncthreads();
   if (dbgc) S.dbg[1] = clock64();
@@ -421,104 +438,137 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
         for (int j = 0; j < dr; j++) F[(size_t)(en.c + j) * ld + en.r + i] = __ldcg(hv + j * dc + i);
     }
   }
+  // ---- the children's row maps, the right-hand side, extend-add ----
+  // The row maps (rel) of ALL children go to shared memory at once -- into the panel scratch behind the front, which is
+  // idle until the panel loop (>= 21 fs + 320 ints, factor_extra_smem).  They are static, like the rhs of the pivots
+  // (V, complete two launches back): with early set both are in place BEFORE the wait, and the lists the rhs gather
+  // walks are pulled into L1, so that after the wait only the data of the previous launch is still to be fetched.
+  constexpr int ECB = 6, ERC = 3;
+  int* srel = reinterpret_cast<int*>(smem + (SMEM ? (size_t)fs * ld : 0));
+  const int srel_cap = ((fs + 1) & ~1) + 2 * ((NB + 2) * fs + 2 * (NB * NB + 2 * NB));
+  const int c_first = S.child_ptr[g], c_end = S.child_ptr[g + 1];
+  auto stage_maps = [&]() {
+    int total = 0;
+    for (int ci = c_first; ci < c_end; ci++) {
+      const int ch = S.children[ci];
+      const int uc = S.nupd[ch];
+      if (total + uc <= srel_cap) {
+        const int* rel = S.rel + S.rows_ptr[ch];
+        for (int i = tid; i < uc; i += nt) srel[total + i] = rel[i];
+      }
+      total += uc;
+    }
+    return total;
+  };
+  const int p0 = S.piv0[g];
+  const int* gp = S.gather_ptr + S.frow_ptr[g];
+  int rel_total = -1;
   if (SMEM && early) {
-    // still in the shadow of the previous launch: pull the static lists the body walks right after the wait (gather
-    // list of the right-hand side, the children's sizes, offsets and row maps) into L1, so that each of them costs an
-    // L1 hit instead of one more L2 / HBM round trip on the front's dependent chain
-    const int* gp = S.gather_ptr + S.frow_ptr[g];
+    for (int i = tid; i < s; i += nt) F[(size_t)i * ld + fs] = __ldcg(V + S.solver2v[p0 + i]);
+    rel_total = stage_maps();
     for (int i = tid; i <= fs; i += nt) prefetch_l1(gp + i);
     {
       const int q0 = gp[0], q1 = gp[fs];
       for (int q = q0 + 32 * tid; q < q1; q += 32 * nt) prefetch_l1(S.gather_src + q);
     }
-    if (tid < fs) prefetch_l1(S.solver2v + S.piv0[g] + tid);
-    for (int ci = S.child_ptr[g] + warp; ci < S.child_ptr[g + 1]; ci += nw) {
-      const int ch = S.children[ci];
-      const int uc = S.nupd[ch];
-      const int* rel = S.rel + S.rows_ptr[ch];
-      if (lane == 0) prefetch_l1(S.uptr + ch);
-      for (int i = 32 * lane; i < uc; i += 32 * 32) prefetch_l1(rel + i);
-    }
+    for (int ci = c_first + tid; ci < c_end; ci += nt) prefetch_l1(S.uptr + S.children[ci]);
     pdl_wait_then_release();  // everything below reads what the previous launch wrote
+    if (tlc) S.tl[TLS * g + 1] = global_ns();
   }
   {  // right-hand side row: rhs of the pivots + the children's update vectors, fixed (child) order
-    const int p0 = S.piv0[g];
     const double* uvecr = uvec_all + (size_t)r * nUvec;
-    const int* gp = S.gather_ptr + S.frow_ptr[g];
-    for (int i = tid; i < fs; i += nt) {
-      double acc = i < s ? __ldcg(V + S.solver2v[p0 + i]) : 0.0;
+    for (int i = tid; i < fs; i += nt) {  // thread i wrote the pivot part of entry i itself
+      double acc = (SMEM && early) ? F[(size_t)i * ld + fs] : (i < s ? __ldcg(V + S.solver2v[p0 + i]) : 0.0);
       for (int q = gp[i]; q < gp[i + 1]; q++) acc += __ldcg(uvecr + S.gather_src[q]);
       F[(size_t)i * ld + fs] = acc;
     }
   }
-  // ---- extend-add ----
-  // The row maps (rel) of ALL children go to shared memory first -- into the panel scratch behind the front, which is
-  // idle until the panel loop (>= 21 fs + 320 ints, factor_extra_smem) -- together with the right-hand side above: one
-  // barrier.  A child's Schur complement (uc x uc, lower part valid) is then walked with up to ECB columns x
-  // ERC row chunks per warp requested before the first entry is added: one L2 round trip per child for uc <= 96 on 16
-  // warps instead of one per 32 columns (uc = 92: 3 rounds + the row map's before; 4 warps, uc = 47: 2 instead of 6).
-  // Children stay sequential with a barrier between them: two children may add to the same entry, and the order of
-  // the sum is fixed.
-  constexpr int ECB = 6, ERC = 3;
-  int* srel = reinterpret_cast<int*>(smem + (SMEM ? (size_t)fs * ld : 0));
-  const int srel_cap = ((fs + 1) & ~1) + 2 * ((NB + 2) * fs + 2 * (NB * NB + 2 * NB));
-  int rel_total = 0;
-  for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
-    const int ch = S.children[ci];
-    const int uc = S.nupd[ch];
-    if (rel_total + uc <= srel_cap) {
-      const int* rel = S.rel + S.rows_ptr[ch];
-      for (int i = tid; i < uc; i += nt) srel[rel_total + i] = rel[i];
-    }
-    rel_total += uc;
-  }
+  if (rel_total < 0) rel_total = stage_maps();
   const bool staged = rel_total <= srel_cap;  // block-uniform
   __syncthreads();
   if (dbgc) S.dbg[2] = clock64();
-  int roff = 0;
-  for (int ci = S.child_ptr[g]; ci < S.child_ptr[g + 1]; ci++) {
-    const int ch = S.children[ci];
-    const int uc = S.nupd[ch];
-    const double* Uc = Uv + S.uptr[ch];
-    const int* sr = srel + roff;
-    if (!staged) {  // more children than the scratch holds (not seen on SLAM graphs): one map at a time
-      const int* rel = S.rel + S.rows_ptr[ch];
-      sr = srel;
-      for (int i = tid; i < uc; i += nt) srel[i] = rel[i];
-      __syncthreads();
+  if (tlc) S.tl[TLS * g + 2] = global_ns();
+  // A child's Schur complement (uc x uc, lower part valid): warp w takes the columns w, w + nw, ..., up to ECB columns x
+  // ERC chunks of 32 rows requested before the first entry is added -- one L2 round trip per child for uc <= 96 on 16
+  // warps instead of one per 32 columns (uc = 92: 3 rounds + the row map's before; 4 warps, uc = 47: 2 instead of 6).
+  // Children stay sequential with a barrier between them (two children may add to the same entry; the order of the
+  // sum is fixed), but the entries of the NEXT child are requested before the current one is added whenever both fit
+  // one batch: a front near the leaves has ten and more small children and paid one round trip for each.
+  auto load_batch = [&](double (&v)[ECB][ERC], const double* Uc, int uc, int jb, int i0) {
+#pragma unroll
+    for (int c = 0; c < ECB; c++) {
+      const int j = jb + c * nw;
+      const double* col = Uc + (size_t)j * uc;
+#pragma unroll
+      for (int rc = 0; rc < ERC; rc++) {
+        const int i = j + i0 + 32 * rc + lane;
+        v[c][rc] = (j < uc && i < uc) ? __ldcg(col + i) : 0.0;
+      }
     }
-    // warp w takes the columns w, w + nw, ...: ECB columns x ERC chunks of 32 rows requested before the first add
-    for (int jb = warp; jb < uc; jb += nw * ECB) {
-      for (int i0 = 0; i0 < uc - jb; i0 += 32 * ERC) {
-        double v[ECB][ERC];
+  };
+  auto add_batch = [&](const double (&v)[ECB][ERC], const int* sr, int uc, int jb, int i0) {
 #pragma unroll
-        for (int c = 0; c < ECB; c++) {
-          const int j = jb + c * nw;
-          const double* col = Uc + (size_t)j * uc;
+    for (int c = 0; c < ECB; c++) {
+      const int j = jb + c * nw;
+      if (j < uc) {  // warp-uniform
+        double* dcol = F + (size_t)sr[j] * ld;
 #pragma unroll
-          for (int rc = 0; rc < ERC; rc++) {
-            const int i = j + i0 + 32 * rc + lane;
-            v[c][rc] = (j < uc && i < uc) ? __ldcg(col + i) : 0.0;
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < ECB; c++) {
-          const int j = jb + c * nw;
-          if (j < uc) {  // warp-uniform
-            double* dcol = F + (size_t)sr[j] * ld;
-#pragma unroll
-            for (int rc = 0; rc < ERC; rc++) {
-              const int i = j + i0 + 32 * rc + lane;
-              if (i < uc) dcol[sr[i]] += v[c][rc];
-            }
-          }
+        for (int rc = 0; rc < ERC; rc++) {
+          const int i = j + i0 + 32 * rc + lane;
+          if (i < uc) dcol[sr[i]] += v[c][rc];
         }
       }
     }
-    __syncthreads();
-    roff += uc;
+  };
+  auto one_batch = [&](int uc) { return staged && uc <= nw * ECB && uc <= 32 * ERC; };
+  {
+    int roff = 0;
+    bool have = false;  // va holds the current child already
+    double va[ECB][ERC];
+    for (int ci = c_first; ci < c_end; ci++) {
+      const int ch = S.children[ci];
+      const int uc = S.nupd[ch];
+      const double* Uc = Uv + S.uptr[ch];
+      if (one_batch(uc)) {
+        if (!have) load_batch(va, Uc, uc, warp, 0);
+        double vb[ECB][ERC];
+        bool next = false;
+        if (ci + 1 < c_end) {
+          const int ch2 = S.children[ci + 1];
+          const int uc2 = S.nupd[ch2];
+          next = one_batch(uc2);
+          if (next) load_batch(vb, Uv + S.uptr[ch2], uc2, warp, 0);
+        }
+        add_batch(va, srel + roff, uc, warp, 0);
+        __syncthreads();
+        if (next) {
+#pragma unroll
+          for (int c = 0; c < ECB; c++)
+#pragma unroll
+            for (int rc = 0; rc < ERC; rc++) va[c][rc] = vb[c][rc];
+        }
+        have = next;
+      } else {
+        const int* sr = srel + roff;
+        if (!staged) {  // more children than the scratch holds (not seen on SLAM graphs): one map at a time
+          const int* rel = S.rel + S.rows_ptr[ch];
+          sr = srel;
+          for (int i = tid; i < uc; i += nt) srel[i] = rel[i];
+          __syncthreads();
+        }
+        for (int jb = warp; jb < uc; jb += nw * ECB)
+          for (int i0 = 0; i0 < uc - jb; i0 += 32 * ERC) {
+            load_batch(va, Uc, uc, jb, i0);
+            add_batch(va, sr, uc, jb, i0);
+          }
+        __syncthreads();
+        have = false;
+      }
+      roff += uc;
+    }
   }
   if (dbgc) S.dbg[3] = clock64();
+  if (tlc) S.tl[TLS * g + 3] = global_ns();
   double* Sp = reinterpret_cast<double*>(srel + ((fs + 1) & ~1));  // NB x ld: scaled panel (incl. the rhs row)
   double* dinv = Sp + (size_t)NB * ld;                             // 1/d of every pivot (s)
   double* Tsm = dinv + fs;                                          // 2 x (NB x NB triangle + NB reciprocals)
@@ -656,6 +706,7 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
     if (dbgc) { const long long t_ = clock64(); S.dbg[29] += t_ - dt_; dt_ = t_; }
   }
   if (dbgc) { S.dbg[4] = clock64(); S.dbg[5] = S.dbg[4]; }
+  if (tlc) S.tl[TLS * g + 4] = global_ns();
   // forward-solve results out of the rhs row: z = D^-1 y under the pivots, update vector for the parent
   {
     const int p0 = S.piv0[g];
@@ -683,6 +734,7 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   }
   __syncthreads();
   if (dbgc) { S.dbg[6] = clock64(); S.dbg[7] = s; S.dbg[8] = fs; S.dbg[9] = S.child_ptr[g + 1] - S.child_ptr[g]; }
+  if (tlc) S.tl[TLS * g + 5] = global_ns();
 }
 
 // ================================================================================================
@@ -960,7 +1012,10 @@ backward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restric
   const int* rows = S.upd_rows + S.rows_ptr[g];
   const int i0 = lane, i1 = lane + 32;
   const int r0 = (i0 >= s && i0 < fs) ? rows[i0 - s] : 0, r1 = (i1 >= s && i1 < fs) ? rows[i1 - s] : 0;
+  const bool tlc = S.tl && r == 0 && lane == 0;
+  if (tlc) S.tl[TLS * g + 6] = global_ns();
   pdl_wait_then_release();  // the parents' x comes from the previous launch
+  if (tlc) S.tl[TLS * g + 7] = global_ns();
   double x0 = 0.0, x1 = 0.0;
   if (i0 < fs) x0 = __ldcg(i0 < s ? x + p0 + i0 : x + r0);
   if (i1 < fs) x1 = __ldcg(i1 < s ? x + p0 + i1 : x + r1);
@@ -986,6 +1041,7 @@ backward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restric
   }
   if (i0 < s) x[p0 + i0] = x0;
   if (i1 < s) x[p0 + i1] = x1;
+  if (tlc) S.tl[TLS * g + 8] = global_ns();
 }
 
 // ================================================================================================
@@ -1577,10 +1633,13 @@ backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long
   const int* rows = S.upd_rows + S.rows_ptr[g];
   // early: this front's L panel was written at least two launches back and is staged while the previous backward
   // launch still runs (the first backward launch follows the root's factor launch directly: early = 0)
+  const bool tlc = S.tl && r == 0 && tid == 0;
+  if (tlc) S.tl[TLS * g + 6] = global_ns();
   if (!early) pdl_wait_then_release();
   if (SMEM) stage_panel(Ls, Lg, fs, s, ld, warp, nw, lane);
   const int xi0 = tid < fs ? (tid < s ? p0 + tid : rows[tid - s]) : 0;  // static: fetched before the wait
   if (early) pdl_wait_then_release();
+  if (tlc) S.tl[TLS * g + 7] = global_ns();
   if (tid < fs) xs[tid] = __ldcg(x + xi0);
   for (int i = tid + nt; i < fs; i += nt) xs[i] = __ldcg(i < s ? x + p0 + i : x + rows[i - s]);
   __syncthreads();
@@ -1627,6 +1686,7 @@ backward_kernel(SymArgs S, int list_off, const double* __restrict__ Lv_all, long
     __syncthreads();
   }
   for (int i = tid; i < s; i += nt) x[p0 + i] = xo[i];
+  if (tlc) S.tl[TLS * g + 8] = global_ns();
 }
 
 // Small fronts (<= 64 rows): one warp per front when there are enough of them to fill the machine
@@ -1671,6 +1731,9 @@ SymArgs sym_args(const DeviceSystem& D) {
   a.asm_entries = D.ds.asm_entries.p; a.launch_list = D.ds.launch_list.p;
   a.frow_ptr = D.ds.frow_ptr.p; a.gather_ptr = D.ds.gather_ptr.p; a.gather_src = D.ds.gather_src.p;
   a.dbg = D.dbg_clocks.p;
+  a.tl = D.timeline.p;
+  static const int dbg_front = getenv("SLAM_B200_DBG_FRONT") ? atoi(getenv("SLAM_B200_DBG_FRONT")) : -1;
+  a.dbg_front = dbg_front;
   return a;
 }
 
@@ -1871,9 +1934,18 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   // SLAM_B200_FACTOR_VARIANT=3: large fronts by the register-resident factor3_kernel (measured: no faster, factor3.cuh)
   static const bool gen3 = getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 3;
   static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
+  static const bool merge_ok = getenv("SLAM_B200_NO_LEVEL_MERGE") == nullptr;
   // programmatic dependent launch: 0 until a launch of this enqueue has gone out whose wait proves that the assembly
   // kernels (V) / the factor kernels (L) are complete -- see pdl_wait_then_release
   int early_v = 0, early_l = 0;
+  // A level that holds both fronts of <= 64 rows and larger ones would go out as two dependent launches (128- and
+  // 512-thread CTAs), the second waiting for the first although they are independent (front timeline of the 10-lap
+  // graph: +12 us on each of its two mixed levels).  When the whole level fits one wave of 512-thread CTAs it is ONE
+  // launch of those; the launch list holds the small fronts first, by ascending size, and is walked backwards.
+  auto merge_classes = [&](const LevelLaunch& LL) {
+    return gen2 && !gen3 && merge_ok && D.R == 1 && LL.n_tiny > 0 && LL.n_small > 0 && !warp_kernels(c, D, LL) &&
+           LL.n_tiny + LL.n_small <= 2 * c->num_sms;
+  };
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
     if (LL.n_tiny && warp_kernels(c, D, LL)) {
@@ -1888,12 +1960,14 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
         c->launches++;
         off += cn;
       }
+    } else if (LL.n_tiny && merge_classes(LL)) {
+      // handled by the 512-thread launch below
     } else if (LL.n_tiny) {
       dim3 grid(LL.n_tiny, D.R);
       if (gen2) {
         SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(128), LL.smem_tiny + factor_extra_smem(64), c->stream,
             S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
-            D.x.p, D.n, la_idle, early_v));
+            D.x.p, D.n, la_idle, early_v | 2));
         early_v = 1;
       } else
         factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
@@ -1901,7 +1975,14 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
             D.x.p, D.n);
       c->launches++;
     }
-    if (LL.n_small) {
+    if (LL.n_small && merge_classes(LL)) {
+      dim3 grid(LL.n_tiny + LL.n_small, D.R);
+      SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(FACTOR_THREADS), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
+          S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
+          D.nUvec, D.x.p, D.n, la_idle, early_v | 2));
+      early_v = 1;
+      c->launches++;
+    } else if (LL.n_small) {
       dim3 grid(LL.n_small, D.R);
       // register-resident 16-warp kernel when every front of the class fits its 20 x 20 tile grid
       int max_nloc = 0;
@@ -1940,11 +2021,11 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   mark();  // factored
   // solves: small fronts by the warp kernels; per level the remaining fronts either all stage their
   // L panel in shared memory or none does
-  auto rest_smem = [&](int lv, size_t& need, size_t& wneed, bool& fits) {
+  auto rest_smem = [&](int lv, size_t& need, size_t& wneed, bool& fits, bool with_tiny = false) {
     const LevelLaunch& LL = D.levels[lv];
     need = wneed = 0;
     fits = true;
-    for (int q = LL.n_tiny; q < LL.n_tiny + LL.n_small + LL.n_big; q++) {
+    for (int q = with_tiny ? 0 : LL.n_tiny; q < LL.n_tiny + LL.n_small + LL.n_big; q++) {
       int f = D.launch_list_host[LL.list_off + q];
       size_t fs = (size_t)D.sym.npiv[f] + D.sym.nupd[f];
       size_t nd = ((fs | 1) * D.sym.npiv[f] + fs + D.sym.npiv[f]) * sizeof(double);
@@ -1982,19 +2063,21 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   for (int lv = nlv - 1; lv >= 0; lv--) {
     const LevelLaunch& LL = D.levels[lv];
     const int nrest = LL.n_small + LL.n_big;
+    const bool merged = nrest && LL.n_big == 0 && merge_classes(LL);  // one launch for a mixed level, as above
     if (nrest) {
-      dim3 grid(nrest, D.R);
+      dim3 grid(nrest + (merged ? LL.n_tiny : 0), D.R);
+      const int off = LL.list_off + (merged ? 0 : LL.n_tiny);
       size_t need, wneed;
       bool fits;
-      rest_smem(lv, need, wneed, fits);
+      rest_smem(lv, need, wneed, fits, merged);
       if (fits)
-        SLAM_CUDA_TRY(c, launch_front(backward_kernel<true>, grid, dim3(SOLVE_THREADS), need, c->stream, S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n, early_l));
+        SLAM_CUDA_TRY(c, launch_front(backward_kernel<true>, grid, dim3(SOLVE_THREADS), need, c->stream, S, off, D.Lv.p, D.nL, D.x.p, D.n, early_l));
       else
-        SLAM_CUDA_TRY(c, launch_front(backward_kernel<false>, grid, dim3(SOLVE_THREADS), wneed, c->stream, S, LL.list_off + LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n, early_l));
+        SLAM_CUDA_TRY(c, launch_front(backward_kernel<false>, grid, dim3(SOLVE_THREADS), wneed, c->stream, S, off, D.Lv.p, D.nL, D.x.p, D.n, early_l));
       early_l = 1;
       c->launches++;
     }
-    if (LL.n_tiny) {
+    if (LL.n_tiny && !merged) {
       dim3 grid((LL.n_tiny + TINY_WARPS - 1) / TINY_WARPS, D.R);
       SLAM_CUDA_TRY(c, launch_front(backward_tiny_kernel, grid, dim3(TINY_WARPS * 32), 0, c->stream, S, LL.list_off, LL.n_tiny, D.Lv.p, D.nL, D.x.p, D.n));
       early_l = 1;
@@ -2048,23 +2131,8 @@ int graph_enqueue_iteration(slam_b200_ctx* c) {
     SLAM_CUDA_TRY(c, e);
     SLAM_CUDA_TRY(c, cudaGraphInstantiate(&D.iter_graph, graph, 0));
     cudaGraphDestroy(graph);
-    D.launches_per_iter = 0;
-    {
-      // count the kernel nodes once: bookkeeping for slam_b200_launch_count
-      // (assemble 2 + per level factor/forward/backward + update)
-      int n = 2 + 1;
-      if (D.tile_path) n = (int)(D.launches_captured);
-      else for (const LevelLaunch& LL : D.levels) {
-        int ntiny = LL.n_tiny ? 1 : 0;
-        if (LL.n_tiny && warp_kernels(c, D, LL)) {
-          ntiny = 0;
-          for (int cls = 0; cls < 4; cls++) ntiny += LL.tiny_cls_n[cls] ? 1 : 0;
-        }
-        n += ntiny + (LL.n_small ? 1 : 0) + (LL.n_big ? 1 : 0);   // factor
-        n += (LL.n_tiny ? 1 : 0) + ((LL.n_small + LL.n_big) ? 1 : 0);            // backward (forward is fused)
-      }
-      D.launches_per_iter = n;
-    }
+    // kernel nodes of one replay (every enqueue counts its launches): bookkeeping for slam_b200_launch_count
+    D.launches_per_iter = (int)D.launches_captured;
   }
   SLAM_CUDA_TRY(c, cudaGraphLaunch(D.iter_graph, c->stream));
   c->launches += D.launches_per_iter;
