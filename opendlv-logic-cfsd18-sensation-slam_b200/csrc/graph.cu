@@ -1430,7 +1430,7 @@ int graph_build_structure(slam_b200_ctx* c) {
     std::vector<int> small, big;
     for (int f = S.level_ptr[lv]; f < S.level_ptr[lv + 1]; f++) {
       size_t fs = (size_t)S.npiv[f] + S.nupd[f];
-      size_t need = fs * (fs + 1) * sizeof(double);  // + the right-hand-side row (solver.cu: factor2_kernel)
+      size_t need = fs * (size_t)front_ld((int)fs) * sizeof(double);  // + the right-hand-side row, padded stride (factor2_kernel)
       LL.max_fs = std::max(LL.max_fs, (int)fs);
       if (fs <= 64 && need <= smem_limit) {
         launch_list.push_back(f);

@@ -29,6 +29,15 @@ struct DevSym {  // symbolic analysis on the device (see symbolic.h)
   DevBuf<int> frow_ptr, gather_ptr, gather_src;
 };
 
+// Leading dimension of a front held in shared memory by factor2_kernel: the front's rows + the right-hand-side row,
+// rounded up to 4 (mod 8) doubles.  With that stride the operand and accumulator fragments of mma.sync.m8n8k4.f64 (8 rows
+// x 4 columns, resp. 8 rows x every second of 8 columns per load) fall on every 8-byte bank exactly twice: two
+// wavefronts per 32-lane load, the minimum (an odd stride gives three to four).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int front_ld(int fs) { return ((fs + 1 + 3) & ~7) + 4; }
+
 struct LevelLaunch {
   // launch_list[list_off ..): n_tiny fronts (fs <= 64, 128-thread CTAs), then n_small (front fits in
   // shared memory, 256-thread CTAs), then n_big (front in a global scratch slab)

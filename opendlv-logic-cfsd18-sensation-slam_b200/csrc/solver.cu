@@ -72,6 +72,47 @@ __device__ __forceinline__ long long global_ns() {
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// D = A B + C on the fp64 tensor pipe: A 8 x 4 (lane l: row l / 4, column l % 4), B 4 x 8 (lane l: row l % 4, column
+// l / 4), C / D 8 x 8 (lane l: row l / 4, columns 2 (l % 4) and 2 (l % 4) + 1)
+__device__ __forceinline__ void dmma_upd(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// LDL^T of an 8 x 8 tile in the accumulator layout (lane (g, t) = (l / 4, l % 4): entries (g, 2t), (g, 2t + 1)), by
+// shuffles and without redundancy -- the routine of the batched tile kernels (tile_ldlt below) with the two
+// conventions of the CTA-per-front kernel: columns stay UNSCALED (l_qp d_p below the diagonal, d_p on it) and only an
+// exactly zero pivot among the first nb fails.  di0 / di1 = reciprocals of the pivots of the lane's two columns.
+__device__ __forceinline__ bool tile_ldlt_unscaled(double& a0, double& a1, double& di0, double& di1, int g, int t, int nb) {
+  bool bad = false;
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const int hp = p >> 1;
+    const double v = (p & 1) ? a1 : a0;
+    const double rgp = __shfl_sync(0xffffffffu, v, g * 4 + hp);      // T[g][p]
+    const double dp = __shfl_sync(0xffffffffu, v, p * 4 + hp);       // T[p][p]
+    const double c0 = __shfl_sync(0xffffffffu, v, 8 * t + hp);       // T[2t][p]
+    const double c1 = __shfl_sync(0xffffffffu, v, 8 * t + 4 + hp);   // T[2t+1][p]
+    bad |= (p < nb && dp == 0.0);
+    double inv;
+    {  // hardware seed + two Newton steps: within an ulp or two of 1 / dp (fast_rcp below)
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(dp));
+      double e = fma(-dp, inv, 1.0);
+      inv = fma(inv, e, inv);
+      e = fma(-dp, inv, 1.0);
+      inv = fma(inv, e, inv);
+    }
+    const double lgp = rgp * inv;
+    if (2 * t > p) a0 -= lgp * c0;
+    if (2 * t + 1 > p) a1 -= lgp * c1;
+    if (t == hp) {
+      if (p & 1) di1 = inv;
+      else di0 = inv;
+    }
+  }
+  return bad;
+}
+
 __device__ __forceinline__ void pdl_wait_then_release() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -403,10 +444,11 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   // flags & 2: walk the launch list backwards -- the fronts of a class are listed by ascending size, and a level of
   // more than one wave of CTAs ends earlier when its largest fronts start first
   const int early = flags & 1;
+  const bool mma_update = SMEM && (flags & 4);  // trailing update by mma.sync.m8n8k4.f64 on 8 x 8 tiles (step (2))
   const int g = S.launch_list[list_off + ((flags & 2) ? gridDim.x - 1 - blockIdx.x : blockIdx.x)];
   const int r = blockIdx.y;
   const int s = S.npiv[g], u = S.nupd[g], fs = s + u;
-  const int ld = fs + 1;  // rows 0..fs-1: the front; row fs: the right-hand side
+  const int ld = SMEM ? front_ld(fs) : fs + 1;  // rows 0..fs-1: the front; row fs: the right-hand side; padding
   const double* V = V_all + (size_t)r * nV;
   double* Uv = Uv_all + (size_t)r * nU;
   double* F = SMEM ? smem : (Fbig_all + (size_t)r * nFbig + S.fbig[g]);
@@ -440,12 +482,12 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   }
   // ---- the children's row maps, the right-hand side, extend-add ----
   // The row maps (rel) of ALL children go to shared memory at once -- into the panel scratch behind the front, which is
-  // idle until the panel loop (>= 21 fs + 320 ints, factor_extra_smem).  They are static, like the rhs of the pivots
+  // idle until the panel loop (>= 21 fs + 448 ints, factor_extra_smem).  They are static, like the rhs of the pivots
   // (V, complete two launches back): with early set both are in place BEFORE the wait, and the lists the rhs gather
   // walks are pulled into L1, so that after the wait only the data of the previous launch is still to be fetched.
   constexpr int ECB = 6, ERC = 3;
   int* srel = reinterpret_cast<int*>(smem + (SMEM ? (size_t)fs * ld : 0));
-  const int srel_cap = ((fs + 1) & ~1) + 2 * ((NB + 2) * fs + 2 * (NB * NB + 2 * NB));
+  const int srel_cap = ((fs + 1) & ~1) + 2 * ((NB + 2) * fs + 8 * NB + 2 * (NB * NB + 2 * NB));
   const int c_first = S.child_ptr[g], c_end = S.child_ptr[g + 1];
   auto stage_maps = [&]() {
     int total = 0;
@@ -634,10 +676,43 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
       // (Measured and rejected: producers dropping the triangle into Tn packed for 16-byte loads: +5 %;
       // warps 4/8/12 -- warp 0's scheduler mates -- sitting the step out: the chain drops from 4,500 to
       // 1,700 cycles but the update with 12 instead of 15 warps loses as much.)
+      if (mma_update) {
+        // tensor-pipe variant: warp 0 brings the tile that holds the next triangle up to date ITSELF (the first task
+        // of the update below: two fragments of the panel, two of the scaled panel, two MMAs -- no hand-over from a
+        // producer warp, no named barrier) and factorises it where it is, in the accumulator layout, by shuffles
+        const int lr = lane >> 2, lk = lane & 3, nb2 = min(NB, s - c0);
+        const bool pv0 = lk < nb, pv1 = lk + 4 < nb;
+        const double* Pa = Pk + (size_t)lk * ld + c0 + lr;
+        const double* Sb = Sp + (size_t)lk * ld + c0 + lr;
+        const bool rv = c0 + lr < nr, cv = c0 + lr < fs;
+        const double a0 = (rv && pv0) ? -Pa[0] : 0.0, a1 = (rv && pv1) ? -Pa[4 * (size_t)ld] : 0.0;
+        const double b0 = (cv && pv0) ? Sb[0] : 0.0, b1 = (cv && pv1) ? Sb[4 * (size_t)ld] : 0.0;
+        const int col = c0 + 2 * lk;
+        double* cp = F + (size_t)col * ld + c0 + lr;
+        const bool v0 = rv && col < fs, v1 = rv && col + 1 < fs;
+        double x0 = v0 ? cp[0] : 0.0, x1 = v1 ? cp[ld] : 0.0;
+        dmma_upd(x0, x1, a0, b0);
+        dmma_upd(x0, x1, a1, b1);
+        if (nb2 < NB) {  // the tile reaches beyond the pivots: those entries belong to the trailing matrix
+          if (v0) cp[0] = x0;
+          if (v1) cp[ld] = x1;
+          if (lr >= nb2 || 2 * lk >= nb2) x0 = (lr == 2 * lk) ? 1.0 : 0.0;
+          if (lr >= nb2 || 2 * lk + 1 >= nb2) x1 = (lr == 2 * lk + 1) ? 1.0 : 0.0;
+        }
+        if (dbgc) { const long long t_ = clock64(); S.dbg[25] += t_ - dt_; dt_ = t_; }
+        double di0 = 1.0, di1 = 1.0;
+        const bool bad = tile_ldlt_unscaled(x0, x1, di0, di1, lr, lk, nb2);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) status[2 * r] = 1;
+        if (lr >= 2 * lk) Tn[lr * NB + 2 * lk] = x0;
+        if (lr >= 2 * lk + 1) Tn[lr * NB + 2 * lk + 1] = x1;
+        if (lr == 0) { Tn[NB * NB + 2 * lk] = di0; Tn[NB * NB + 2 * lk + 1] = di1; }
+        if (dbgc) { const long long t_ = clock64(); S.dbg[24] += t_ - dt_; dt_ = t_; }
+      } else {
       asm volatile("bar.sync 1, 96;" ::: "memory");
       if (dbgc) { const long long t_ = clock64(); S.dbg[25] += t_ - dt_; dt_ = t_; }
       if (factor_triangle(F + (size_t)c0 * ld + c0, 1, ld, Tn, min(NB, s - c0)) && lane == 0) status[2 * r] = 1;
       if (dbgc) { const long long t_ = clock64(); S.dbg[24] += t_ - dt_; dt_ = t_; }
+      }
     } else if (!ahead || !(la_idle > 0 && fs - c0 <= la_idle) || (warp & 3) != 0) {
       // la_idle (rows): warps 4, 8, 12 share warp 0's scheduler and FP64 pipe and sit a look-ahead step out when the
       // trailing matrix has at most that many rows (a short update: the triangle chain is what the panel waits for)
@@ -647,6 +722,86 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
         if (idle_mates) { wi = (warp >> 2) * 3 + (warp & 3) - 1; nwt = (nw >> 2) * 3; }
         else { wi = warp - 1; nwt = nw - 1; }
       }
+      if (mma_update) {
+        // Trailing update on the fp64 tensor pipe, operands and accumulators straight from the front in shared memory.
+        // The scalar update below moves 96 shared-memory wavefronts per 64 x 4 x 8 block of multiply-adds (A 32, the
+        // broadcast B values 32, C in and out 32) and the ONE shared-memory pipe of the SM is what the panel step waits
+        // for (phase clocks of a 46-pivot / 138-row front: update and look-ahead triangle both ~5,400 cycles per panel,
+        // the triangle as slow with its scheduler mates idle).  As 8 x 8 tiles with the two column tiles of a pair
+        // sharing the A fragments the same work moves 28 wavefronts per 16 x 8 x 8 block: 56 for the work of 96.
+        // Tasks = (pair of column tiles, row tile) below or on the diagonal, dealt round-robin to the warps; task 0
+        // holds the next panel's triangle and is warp 0's own when it looks ahead (above).  Tiles on the diagonal are
+        // written whole: the strict upper triangle of a front is never read.
+        const int Tn = (nr - c0 + 7) >> 3, Tc = (fs - c0 + 7) >> 3;  // Tn >= Tc: the rhs row is one more row
+        const int lr = lane >> 2, lk = lane & 3;
+        // operand addresses of this lane relative to (row tile, column tile); k-halves beyond the panel's pivots read 0
+        const bool pv0 = lk < nb, pv1 = lk + 4 < nb;
+        const double* Pa0 = Pk + (size_t)lk * ld + c0 + lr;        // A, first k-half: panel column lk, row c0 + 8 I + lr
+        const double* Pa1 = Pa0 + 4 * (size_t)ld;
+        const double* Sb0 = Sp + (size_t)lk * ld + c0 + lr;        // B: scaled panel column lk, "row" = column c0 + 8 J + lr
+        const double* Sb1 = Sb0 + 4 * (size_t)ld;
+        double* Fc = F + (size_t)(c0 + 2 * lk) * ld + c0 + lr;     // C: column c0 + 8 J + 2 lk (+ 1), row c0 + 8 I + lr
+        // flat order of the tasks: Jp = 0: I = 0 .. Tn-1; Jp = 1: I = 2 .. Tn-1; ...  (position 0 = the next triangle's
+        // tile: warp 0's when it looks ahead).  A warp takes a CONTIGUOUS range of positions: consecutive row tiles of one
+        // pair of column tiles share the B fragments, and two row tiles go through loads -> MMAs -> stores together.
+        const int nJ = (Tc + 1) >> 1;
+        const int total = nJ * Tn - nJ * (nJ - 1);  // sum over Jp of (Tn - 2 Jp)
+        const int first = ahead ? 1 : 0;
+        const int chunk = (total - first + nwt - 1) / nwt;
+        int pos = first + wi * chunk;
+        const int pend = min(pos + chunk, total);
+        int Jp = 0, I = 0;
+        for (int n = pos; Jp < nJ; Jp++) {
+          const int left = Tn - 2 * Jp;
+          if (n < left) { I = 2 * Jp + n; break; }
+          n -= left;
+        }
+        while (pos < pend) {
+          const int len = min(pend - pos, Tn - I);
+          const int colr = 16 * Jp;  // relative to c0 (+ lr: in Sb0 / Sb1)
+          const bool cv0 = c0 + colr + lr < fs, cv1 = c0 + colr + lr + 8 < fs;
+          const double b00 = (cv0 && pv0) ? Sb0[colr] : 0.0, b01 = (cv0 && pv1) ? Sb1[colr] : 0.0;
+          const double b10 = (cv1 && pv0) ? Sb0[colr + 8] : 0.0, b11 = (cv1 && pv1) ? Sb1[colr + 8] : 0.0;
+          const bool two = 2 * Jp + 1 < Tc;
+          const int col0 = c0 + colr + 2 * lk;
+          const bool cA0 = col0 < fs, cA1 = col0 + 1 < fs, cB0 = two && col0 + 8 < fs, cB1 = two && col0 + 9 < fs;
+          for (int q = 0; q < len; q += 2) {
+            const int Ia = I + q;
+            const int ra = 8 * Ia, rb = ra + 8;
+            const bool ha = c0 + ra + lr < nr, hb = q + 1 < len && c0 + rb + lr < nr;
+            const bool sa = Ia > 2 * Jp;  // row tile Ia reaches the second column tile (Ia + 1 always does)
+            double* cpa = Fc + (size_t)colr * ld + ra;
+            double* cpb = cpa + 8;
+            double* cqa = cpa + 8 * (size_t)ld;
+            double* cqb = cqa + 8;
+            const bool va0 = ha && cA0, va1 = ha && cA1, vb0 = hb && cA0, vb1 = hb && cA1;
+            const bool wa0 = ha && sa && cB0, wa1 = ha && sa && cB1, wb0 = hb && cB0, wb1 = hb && cB1;
+            const double aa0 = (ha && pv0) ? -Pa0[ra] : 0.0, aa1 = (ha && pv1) ? -Pa1[ra] : 0.0;
+            const double ab0 = (hb && pv0) ? -Pa0[rb] : 0.0, ab1 = (hb && pv1) ? -Pa1[rb] : 0.0;
+            double xa0 = va0 ? cpa[0] : 0.0, xa1 = va1 ? cpa[ld] : 0.0, xb0 = vb0 ? cpb[0] : 0.0, xb1 = vb1 ? cpb[ld] : 0.0;
+            double ya0 = wa0 ? cqa[0] : 0.0, ya1 = wa1 ? cqa[ld] : 0.0, yb0 = wb0 ? cqb[0] : 0.0, yb1 = wb1 ? cqb[ld] : 0.0;
+            dmma_upd(xa0, xa1, aa0, b00);
+            dmma_upd(xb0, xb1, ab0, b00);
+            dmma_upd(ya0, ya1, aa0, b10);
+            dmma_upd(yb0, yb1, ab0, b10);
+            dmma_upd(xa0, xa1, aa1, b01);
+            dmma_upd(xb0, xb1, ab1, b01);
+            dmma_upd(ya0, ya1, aa1, b11);
+            dmma_upd(yb0, yb1, ab1, b11);
+            if (va0) cpa[0] = xa0;
+            if (va1) cpa[ld] = xa1;
+            if (vb0) cpb[0] = xb0;
+            if (vb1) cpb[ld] = xb1;
+            if (wa0) cqa[0] = ya0;
+            if (wa1) cqa[ld] = ya1;
+            if (wb0) cqb[0] = yb0;
+            if (wb1) cqb[ld] = yb1;
+          }
+          pos += len;
+          Jp++;
+          I = 2 * Jp;
+        }
+      } else {
       bool owe = ahead && wi < 2;  // producer of the next panel's columns: signal warp 0 after the first group
       for (int jg = c0 + 4 * wi; jg < fs; jg += 4 * nwt) {
         double B[4][NB];
@@ -700,6 +855,7 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
         if (owe) { __threadfence_block(); asm volatile("bar.arrive 1, 96;" ::: "memory"); owe = false; }
       }
       if (owe) { __threadfence_block(); asm volatile("bar.arrive 1, 96;" ::: "memory"); }
+      }
     }
     if (dbgc) { const long long t_ = clock64(); S.dbg[28] += t_ - dt_; dt_ = t_; }
     __syncthreads();
@@ -1697,7 +1853,7 @@ bool warp_kernels(const slam_b200_ctx* c, const DeviceSystem& D, const LevelLaun
 }
 
 size_t factor_extra_smem(int max_fs) {  // srel (ints, even count) + scaled panel
-  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + ((size_t)(NB + 2) * max_fs + 2 * (NB * NB + 2 * NB)) * sizeof(double);
+  return (size_t)((max_fs + 1) & ~1) * sizeof(int) + ((size_t)(NB + 2) * max_fs + 8 * NB + 2 * (NB * NB + 2 * NB)) * sizeof(double);
 }
 
 // Launch with programmatic stream serialisation (see pdl_wait_then_release): the kernel may become resident as soon as
@@ -1935,6 +2091,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   static const bool gen3 = getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 3;
   static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
   static const bool merge_ok = getenv("SLAM_B200_NO_LEVEL_MERGE") == nullptr;
+  static const int mma_flag = (getenv("SLAM_B200_UPDATE_MMA") ? atoi(getenv("SLAM_B200_UPDATE_MMA")) : 1) ? 4 : 0;
   // programmatic dependent launch: 0 until a launch of this enqueue has gone out whose wait proves that the assembly
   // kernels (V) / the factor kernels (L) are complete -- see pdl_wait_then_release
   int early_v = 0, early_l = 0;
@@ -1967,7 +2124,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       if (gen2) {
         SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(128), LL.smem_tiny + factor_extra_smem(64), c->stream,
             S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
-            D.x.p, D.n, la_idle, early_v | 2));
+            D.x.p, D.n, la_idle, early_v | 2 | mma_flag));
         early_v = 1;
       } else
         factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
@@ -1979,7 +2136,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       dim3 grid(LL.n_tiny + LL.n_small, D.R);
       SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(FACTOR_THREADS), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
           S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
-          D.nUvec, D.x.p, D.n, la_idle, early_v | 2));
+          D.nUvec, D.x.p, D.n, la_idle, early_v | 2 | mma_flag));
       early_v = 1;
       c->launches++;
     } else if (LL.n_small) {
@@ -1996,7 +2153,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       } else if (gen2) {
         SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(FACTOR_THREADS), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
             S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
-            D.nUvec, D.x.p, D.n, la_idle, early_v));
+            D.nUvec, D.x.p, D.n, la_idle, early_v | mma_flag));
         early_v = 1;
       } else
         factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
@@ -2009,7 +2166,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       if (gen2) {
         SLAM_CUDA_TRY(c, launch_front(factor2_kernel<false>, grid, dim3(FACTOR_THREADS), factor_extra_smem(LL.max_fs), c->stream,
             S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
-            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n, la_idle, early_v));
+            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n, la_idle, early_v | mma_flag));
         early_v = 1;
       } else
         factor_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
