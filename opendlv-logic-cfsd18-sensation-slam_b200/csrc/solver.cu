@@ -535,7 +535,8 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
   // warps instead of one per 32 columns (uc = 92: 3 rounds + the row map's before; 4 warps, uc = 47: 2 instead of 6).
   // Children stay sequential with a barrier between them (two children may add to the same entry; the order of the
   // sum is fixed), but the entries of the NEXT child are requested before the current one is added whenever both fit
-  // one batch: a front near the leaves has ten and more small children and paid one round trip for each.
+  // one batch: a front near the leaves has ten and more small children and paid one round trip for each.  (Warp-uniform
+  // branches around the slots a small child does not use were measured: slower -- the loads no longer issue back to back.)
   auto load_batch = [&](double (&v)[ECB][ERC], const double* Uc, int uc, int jb, int i0) {
 #pragma unroll
     for (int c = 0; c < ECB; c++) {
@@ -887,6 +888,49 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
     const double* col = F + (size_t)(s + j) * ld + s;
     double* out = Ug + (size_t)j * u;
     for (int i = j + lane; i < u; i += 32) out[i] = col[i];
+  }
+  if ((flags & 8) && u == 0) {
+    // A root (no update rows, no parent): its backward solve L^T x = z needs nothing but this front, which is still in
+    // shared memory -- done here, the level's backward launch (stage 150 KB of L again, 18 dependent panel steps in a
+    // CTA of its own: 22 us on the 10-lap graph) is not enqueued.  Same arithmetic, same order as backward_kernel:
+    // L[i][k] = F[i, k] / d_k exactly as it is written out above.
+    __syncthreads();  // the panel scratch (Sp) is free again; F's columns are only read from here on
+    double* xs = Sp;        // s
+    double* xo = Sp + ld;   // NB: the panel being solved
+    for (int i = tid; i < s; i += nt) xs[i] = F[(size_t)i * ld + fs] * dinv[i];
+    __syncthreads();
+    for (int pan = (s + NB - 1) / NB - 1; pan >= 0; pan--) {
+      const int k0 = pan * NB;
+      const int nb = min(NB, s - k0);
+      if (warp == 0) {
+        double xp[NB];
+#pragma unroll
+        for (int p = 0; p < NB; p++) xp[p] = (p < nb) ? xs[k0 + p] : 0.0;
+#pragma unroll
+        for (int p = NB - 1; p >= 0; p--)
+#pragma unroll
+          for (int q = 0; q < p; q++)
+            if (p < nb) xp[q] -= (F[(size_t)(k0 + q) * ld + k0 + p] * dinv[k0 + q]) * xp[p];
+        if (lane == 0) {
+#pragma unroll
+          for (int p = 0; p < NB; p++)
+            if (p < nb) { xo[p] = xp[p]; xs[k0 + p] = xp[p]; }
+        }
+      }
+      __syncthreads();
+      for (int k = tid; k < k0; k += nt) {
+        const double* col = F + (size_t)k * ld + k0;
+        const double inv = dinv[k];
+        double acc = xs[k];
+#pragma unroll
+        for (int p = 0; p < NB; p++)
+          if (p < nb) acc -= (col[p] * inv) * xo[p];
+        xs[k] = acc;
+      }
+      __syncthreads();
+    }
+    double* xr = x_all + (size_t)r * n + S.piv0[g];
+    for (int i = tid; i < s; i += nt) xr[i] = xs[i];
   }
   __syncthreads();
   if (dbgc) { S.dbg[6] = clock64(); S.dbg[7] = s; S.dbg[8] = fs; S.dbg[9] = S.child_ptr[g + 1] - S.child_ptr[g]; }
@@ -2095,6 +2139,15 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   // programmatic dependent launch: 0 until a launch of this enqueue has gone out whose wait proves that the assembly
   // kernels (V) / the factor kernels (L) are complete -- see pdl_wait_then_release
   int early_v = 0, early_l = 0;
+  // the last level holds roots only (fronts without update rows): their backward solve is done by the factor kernel
+  // while the front is still in shared memory, and the level's backward launch is dropped (factor2_kernel, flags & 8)
+  bool fuse_roots = false;
+  if (gen2 && !gen3 && D.R == 1 && nlv > 0 && !getenv("SLAM_B200_SEPARATE_FORWARD") && !getenv("SLAM_B200_NO_ROOT_FUSE")) {
+    const LevelLaunch& LL = D.levels[nlv - 1];
+    fuse_roots = LL.n_big == 0 && !(LL.n_tiny && warp_kernels(c, D, LL));
+    for (int q = 0; fuse_roots && q < LL.n_tiny + LL.n_small; q++)
+      if (D.sym.nupd[D.launch_list_host[LL.list_off + q]] != 0) fuse_roots = false;
+  }
   // A level that holds both fronts of <= 64 rows and larger ones would go out as two dependent launches (128- and
   // 512-thread CTAs), the second waiting for the first although they are independent (front timeline of the 10-lap
   // graph: +12 us on each of its two mixed levels).  When the whole level fits one wave of 512-thread CTAs it is ONE
@@ -2105,6 +2158,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   };
   for (int lv = 0; lv < nlv; lv++) {
     const LevelLaunch& LL = D.levels[lv];
+    const int root_flag = (fuse_roots && lv == nlv - 1) ? 8 : 0;
     if (LL.n_tiny && warp_kernels(c, D, LL)) {
       int off = LL.list_off;
       for (int cls = 0; cls < 4; cls++) {
@@ -2124,7 +2178,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       if (gen2) {
         SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(128), LL.smem_tiny + factor_extra_smem(64), c->stream,
             S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p, D.nUvec,
-            D.x.p, D.n, la_idle, early_v | 2 | mma_flag));
+            D.x.p, D.n, la_idle, early_v | 2 | mma_flag | root_flag));
         early_v = 1;
       } else
         factor_kernel<true><<<grid, 128, LL.smem_tiny + factor_extra_smem(64), c->stream>>>(
@@ -2136,7 +2190,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       dim3 grid(LL.n_tiny + LL.n_small, D.R);
       SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(FACTOR_THREADS), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
           S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
-          D.nUvec, D.x.p, D.n, la_idle, early_v | 2 | mma_flag));
+          D.nUvec, D.x.p, D.n, la_idle, early_v | 2 | mma_flag | root_flag));
       early_v = 1;
       c->launches++;
     } else if (LL.n_small) {
@@ -2153,7 +2207,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       } else if (gen2) {
         SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(FACTOR_THREADS), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
             S, LL.list_off + LL.n_tiny, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
-            D.nUvec, D.x.p, D.n, la_idle, early_v | mma_flag));
+            D.nUvec, D.x.p, D.n, la_idle, early_v | mma_flag | root_flag));
         early_v = 1;
       } else
         factor_kernel<true><<<grid, FACTOR_THREADS, LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream>>>(
@@ -2166,7 +2220,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       if (gen2) {
         SLAM_CUDA_TRY(c, launch_front(factor2_kernel<false>, grid, dim3(FACTOR_THREADS), factor_extra_smem(LL.max_fs), c->stream,
             S, LL.list_off + LL.n_tiny + LL.n_small, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig,
-            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n, la_idle, early_v | mma_flag));
+            D.status.p, D.uvec.p, D.nUvec, D.x.p, D.n, la_idle, early_v | mma_flag | root_flag));
         early_v = 1;
       } else
         factor_kernel<false><<<grid, FACTOR_THREADS, factor_extra_smem(LL.max_fs), c->stream>>>(
@@ -2219,6 +2273,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   mark();  // forward done
   for (int lv = nlv - 1; lv >= 0; lv--) {
     const LevelLaunch& LL = D.levels[lv];
+    if (fuse_roots && lv == nlv - 1) continue;  // solved inside the factor kernel
     const int nrest = LL.n_small + LL.n_big;
     const bool merged = nrest && LL.n_big == 0 && merge_classes(LL);  // one launch for a mixed level, as above
     if (nrest) {

@@ -24,7 +24,8 @@ L.slam_b200_debug_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_
 n = L.slam_b200_debug_timeline(ctx.h, None, 0)
 buf = (C.c_longlong * n)()
 L.slam_b200_debug_timeline(ctx.h, buf, n)
-tl = np.array(buf, dtype=np.int64).reshape(-1, 12).astype(np.float64) / 1e3
+raw = np.array(buf, dtype=np.int64).reshape(-1, 12)
+tl = raw.astype(np.float64) / 1e3
 L.slam_b200_graph_export_symbolic.restype = C.c_long
 L.slam_b200_graph_export_symbolic.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_long]
 
@@ -56,6 +57,9 @@ t_factor_end = prev_end
 for l in range(len(level_ptr) - 2, -1, -1):
     a, b = level_ptr[l], level_ptr[l + 1]
     t = tl[a:b]
+    if raw[a:b, 6].min() == 0:
+        print("B L%-2d %5d | solved inside the factor kernel (roots)" % (l, b - a))
+        continue
     dur = t[:, 8] - t[:, 7]
     print("B L%-2d %5d | entry %6.1f released %6.1f..%6.1f (gap %4.1f) end %6.1f | after wait: median %5.1f max %5.1f"
           % (l, b - a, t[:, 6].min(), t[:, 7].min(), t[:, 7].max(), t[:, 7].min() - prev_end, t[:, 8].max(), np.median(dur), dur.max()))
