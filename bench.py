@@ -57,12 +57,14 @@ def peaks():
 
 def measured_traffic(key):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernel, from the
-    committed `ncu --set full` capture summarised in profiles/r01_traffic.json; None if not captured."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        return float(json.load(open(p))[key]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    committed `ncu --set full` captures summarised in profiles/r02_traffic.json (round 2: the single-graph factor
+    kernels re-captured, the other entries as in r01_traffic.json); None if not captured."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))[key]["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:

@@ -38,32 +38,55 @@ struct Nd {
   int next_label = 1;
   // recursion below `defer_depth` is not run but recorded (vertex set, label, parent node): the
   // caller runs those sub-dissections in parallel and splices their trees in, in this order
-  struct Deferred { std::vector<int> verts; int lab; int parent; };
+  struct Deferred { std::vector<int> verts; int lab; int parent; int hint; };
   int defer_depth = -1;
   std::vector<Deferred> deferred;
 
-  // BFS inside region `lab` from r; fills order (visit order) and lvl[]; returns number of levels
-  int bfs(int r, int lab, std::vector<int>& order, std::vector<int>& level_start) {
+  // BFS inside the current region from r; fills order (visit order) and lvl[]; returns the number of levels.
+  // Invariant (kept by order_region): lvl[v] == -1 exactly for the not yet visited vertices of the region being
+  // searched; every other vertex a search can reach -- the separators around the region -- carries lvl >= 0, so the
+  // neighbour test is ONE random read instead of a region label and a level.  With `weights` the search also
+  // accumulates, per level, the weight of the level (w), of its vertices with a neighbour in the next level (wnext)
+  // and in the previous one (wprev): when v is scanned all of level(v) - 1 and the part of level(v) + 1 reached so
+  // far are labelled and the rest of level(v) + 1 is labelled by this very scan, so nothing is missed -- the separate
+  // sweep over the adjacency that used to compute them is gone.
+  template <bool WEIGHTS>
+  int bfs(int r, std::vector<int>& order, std::vector<int>& level_start, std::vector<double>* w = nullptr,
+          std::vector<double>* wnext = nullptr, std::vector<double>* wprev = nullptr) {
     order.clear();
     level_start.clear();
     order.push_back(r);
     lvl[r] = 0;
     level_start.push_back(0);
+    if (WEIGHTS) { w->assign(1, 0.0); wnext->assign(1, 0.0); wprev->assign(1, 0.0); }
     size_t head = 0;
     int cur = 0;
     while (head < order.size()) {
-      int v = order[head];
-      if (lvl[v] != cur) {
-        cur = lvl[v];
+      const int v = order[head];
+      const int lv = lvl[v];
+      if (lv != cur) {
+        cur = lv;
         level_start.push_back((int)head);
+        if (WEIGHTS) { w->push_back(0.0); wnext->push_back(0.0); wprev->push_back(0.0); }
       }
       head++;
+      bool hn = false, hp = false;
       for (int p = xa[v]; p < xa[v + 1]; p++) {
-        int u = ad[p];
-        if (region[u] == lab && lvl[u] < 0) {
-          lvl[u] = lvl[v] + 1;
+        const int u = ad[p];
+        const int lu = lvl[u];
+        if (lu < 0) {
+          lvl[u] = lv + 1;
           order.push_back(u);
+          hn = true;
+        } else if (WEIGHTS) {
+          if (lu == lv + 1) hn = true;
+          else if (lu == lv - 1) hp = true;
         }
+      }
+      if (WEIGHTS) {
+        (*w)[cur] += dim[v];
+        if (hn) (*wnext)[cur] += dim[v];
+        if (hp) (*wprev)[cur] += dim[v];
       }
     }
     level_start.push_back((int)order.size());
@@ -71,23 +94,39 @@ struct Nd {
   }
 
   // orders the vertex set `verts` (all carrying region label `lab`); appends the resulting
-  // subtree roots to `roots`
-  void order_region(std::vector<int>& verts, int lab, std::vector<int>& roots, int depth = 0) {
-    // split into connected components
+  // subtree roots to `roots`.  `hint`: a vertex of `verts` known to lie at an end of its component (the parent
+  // bisection's own root for the near half, the vertex its search reached last for the far half): the search from
+  // it is taken as the level structure at once -- one sweep over the adjacency per bisection instead of two.
+  void order_region(std::vector<int>& verts, int lab, std::vector<int>& roots, int depth = 0, int hint = -1) {
     for (int v : verts) lvl[v] = -1;
     std::vector<int> order, level_start;
+    std::vector<double> w, wnext, wprev;
+    auto leaf = [&](const std::vector<int>& comp) {
+      NdNode nd;
+      nd.verts = comp;
+      nodes.push_back(nd);
+      roots.push_back((int)nodes.size() - 1);
+    };
+    // MEASURED AND OFF BY DEFAULT (SLAM_B200_ND_HINT=1): the hinted search saves a sweep per bisection (nested
+    // dissection of the 10-lap graph 4.4 -> 2.9 ms on one host thread) but its level structures are a little worse --
+    // assembly trees of 13 instead of 10 levels on the 1- and 10-lap graphs, largest corridor front 95 instead of 72
+    // rows -- and every level is a dependent launch in each of the 10 iterations.
+    static const bool use_hint = getenv("SLAM_B200_ND_HINT") != nullptr;
+    if (hint >= 0 && use_hint) {
+      const int nl = bfs<true>(hint, order, level_start, &w, &wnext, &wprev);
+      if ((int)order.size() <= leaf_size) leaf(order);
+      else dissect(order, level_start, w, wnext, wprev, nl, lab, roots, depth);
+    }
+    // the (other) connected components
     std::vector<std::vector<int>> comps;
     for (int v : verts) {
       if (lvl[v] >= 0) continue;
-      bfs(v, lab, order, level_start);
+      bfs<false>(v, order, level_start);
       comps.push_back(order);
     }
     for (auto& comp : comps) {
       if ((int)comp.size() <= leaf_size) {
-        NdNode nd;
-        nd.verts = comp;
-        nodes.push_back(nd);
-        roots.push_back((int)nodes.size() - 1);
+        leaf(comp);
         continue;
       }
       // pseudo-peripheral start: the breadth-first search that found the component (comp is its visit order from
@@ -96,23 +135,18 @@ struct Nd {
       // and corridor graphs to within 1 %, one more pass over the adjacency per bisection.)
       const int r = comp.back();
       for (int v : comp) lvl[v] = -1;
-      int nl = bfs(r, lab, order, level_start);
-      // per-level weights and boundary weights
-      std::vector<double> w(nl, 0), wnext(nl, 0), wprev(nl, 0);
-      for (int l = 0; l < nl; l++)
-        for (int q = level_start[l]; q < level_start[l + 1]; q++) {
-          int v = order[q];
-          w[l] += dim[v];
-          bool hn = false, hp = false;
-          for (int p = xa[v]; p < xa[v + 1]; p++) {
-            int u = ad[p];
-            if (region[u] != lab) continue;
-            if (lvl[u] == l + 1) hn = true;
-            else if (lvl[u] == l - 1) hp = true;
-          }
-          if (hn) wnext[l] += dim[v];
-          if (hp) wprev[l] += dim[v];
-        }
+      const int nl = bfs<true>(r, order, level_start, &w, &wnext, &wprev);
+      dissect(order, level_start, w, wnext, wprev, nl, lab, roots, depth);
+    }
+  }
+
+  // bisects one connected component given its level structure (order = visit order, lvl[] = levels, per-level weights)
+  void dissect(const std::vector<int>& order, const std::vector<int>& level_start, const std::vector<double>& w,
+               const std::vector<double>& wnext, const std::vector<double>& wprev, int nl, int lab, std::vector<int>& roots,
+               int depth) {
+    (void)level_start;
+    {
+      const std::vector<int>& comp = order;
       double W = 0;
       for (double x : w) W += x;
       // candidates: cut between level l and l+1; option 1 separator = boundary of level l
@@ -161,7 +195,7 @@ struct Nd {
         nd.verts = comp;
         nodes.push_back(nd);
         roots.push_back((int)nodes.size() - 1);
-        continue;
+        return;
       }
       int sepLevel = bestOpt == 1 ? bestL : bestL + 1;
       int other = bestOpt == 1 ? bestL + 1 : bestL;
@@ -183,18 +217,19 @@ struct Nd {
       int la = next_label++, lb = next_label++;
       for (int v : A) region[v] = la;
       for (int v : B) region[v] = lb;
-      for (int v : S) region[v] = 0;  // separators leave every region
+      for (int v : S) { region[v] = 0; lvl[v] = 0x3fffffff; }  // separators leave every region: visited, on no level
       NdNode nd;
       nd.verts = S;
       nodes.push_back(nd);
       int me = (int)nodes.size() - 1;
       std::vector<int> kids;
+      const int hintA = A.empty() ? -1 : A.front(), hintB = B.empty() ? -1 : B.back();
       if (depth == defer_depth) {
-        deferred.push_back({std::move(A), la, me});
-        deferred.push_back({std::move(B), lb, me});
+        deferred.push_back({std::move(A), la, me, hintA});
+        deferred.push_back({std::move(B), lb, me, hintB});
       } else {
-        order_region(A, la, kids, depth + 1);
-        order_region(B, lb, kids, depth + 1);
+        order_region(A, la, kids, depth + 1, hintA);
+        order_region(B, lb, kids, depth + 1, hintB);
       }
       nodes[me].kids = kids;
       roots.push_back(me);
@@ -672,7 +707,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     std::vector<std::vector<int>> half_roots(n1);
     HostPool::get().run(n1, [&](int t) {
       init_sub(half[t], 1 + t, 0);
-      half[t].order_region(nd.deferred[t].verts, nd.deferred[t].lab, half_roots[t], 0);
+      half[t].order_region(nd.deferred[t].verts, nd.deferred[t].lab, half_roots[t], 0, nd.deferred[t].hint);
     });
     // quarters of all halves, flattened
     std::vector<std::pair<int, int>> parts;
@@ -684,7 +719,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     HostPool::get().run(n2, [&](int t) {
       Nd::Deferred& d = half[parts[t].first].deferred[parts[t].second];
       init_sub(quarter[t], 1 + n1 + t, -1);
-      quarter[t].order_region(d.verts, d.lab, quarter_roots[t], 0);
+      quarter[t].order_region(d.verts, d.lab, quarter_roots[t], 0, d.hint);
     });
     for (int h = 0, t0q = 0; h < n1; h++) {
       const int cnt = (int)half[h].deferred.size();
