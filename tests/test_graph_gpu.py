@@ -356,6 +356,94 @@ def test_first_generation_front_kernel_still_agrees(ctx, orc, synth, variant):
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
+_VARIANT_CODE = (
+    "import sys, hashlib, json, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+    "from conftest import load_pkg\n"
+    "pkg = load_pkg(); g = pkg.synth.c2_graph(n_laps=4, poses_per_lap=400)\n"
+    "ctx = pkg.Context(0); ctx.graph_load(g); n, chi2 = ctx.graph_optimize(10)\n"
+    "st = ctx.graph_stats(); assert st['max_front'] > 64 and n == 10, (st, n)\n"
+    "pe, le = ctx.graph_get_estimates()\n"
+    "np.save(sys.argv[1], np.concatenate([pe.ravel(), le.ravel(), np.asarray(chi2)]))\n"
+    "print('ok', int(ctx.launch_count()))\n"
+)
+
+
+def _run_variant(tmp_path, name, env_extra):
+    import subprocess
+    import sys
+    out = str(tmp_path / (name + ".npy"))
+    code = _VARIANT_CODE % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)))
+    env = dict(os.environ, **env_extra)
+    r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+    return np.load(out), int(r.stdout.split()[-1])
+
+
+def test_launch_structure_variants_are_bit_identical(tmp_path):
+    """The single-graph front kernels are chained by programmatic dependent launch (prologue of a level under the level
+    before it), mixed levels go out as one launch and the roots solve their backward system inside the factor kernel.
+    Neither the chaining nor the fused roots change a single operation or its order: with them switched off (environment
+    read once per process, hence child processes) the estimates and chi2 of a 4-lap graph (fronts beyond 64 rows, ten
+    levels) after ten iterations are the SAME BITS.  A prologue that read something the previous launch was still writing, or
+    a stale line of it, would show up here."""
+    base, n_base = _run_variant(tmp_path, "default", {})
+    for name, env in (("no_pdl", {"SLAM_B200_NO_PDL": "1"}), ("no_root_fuse", {"SLAM_B200_NO_ROOT_FUSE": "1"}),
+                      ("no_graph", {"SLAM_B200_NO_CUDA_GRAPH": "1"})):
+        other, n_other = _run_variant(tmp_path, name, env)
+        assert base.shape == other.shape and np.array_equal(base, other), (name, float(np.max(np.abs(base - other))))
+        if name == "no_root_fuse":
+            assert n_other > n_base  # the root level's backward launch is back
+    again, _ = _run_variant(tmp_path, "again", {})
+    assert np.array_equal(base, again)
+    # a mixed level as two launches sends its small fronts through the warp-per-front backward kernel, whose sums run
+    # in another order: same answer to rounding, not the same bits
+    split, n_split = _run_variant(tmp_path, "no_merge", {"SLAM_B200_NO_LEVEL_MERGE": "1"})
+    assert n_split > n_base
+    assert np.max(np.abs(base - split)) <= 1e-11 * max(1.0, float(np.max(np.abs(base))))
+
+
+def test_tensor_pipe_and_scalar_trailing_update_agree(tmp_path):
+    """The trailing update of a front runs as 8 x 8 tiles of mma.sync.m8n8k4.f64 straight from shared memory (the next
+    triangle factorised by shuffles in the accumulator layout, seeded reciprocals); SLAM_B200_UPDATE_MMA=0 is the scalar
+    update with the redundant triangle and correctly rounded reciprocals.  Different rounding, same answer: estimates
+    within 1e-9 relative, chi2 within 1e-10 relative."""
+    a, _ = _run_variant(tmp_path, "mma", {})
+    b, _ = _run_variant(tmp_path, "scalar", {"SLAM_B200_UPDATE_MMA": "0"})
+    assert np.max(np.abs(a[:-10] - b[:-10])) <= 1e-9 * max(1.0, float(np.max(np.abs(b[:-10]))))
+    assert np.allclose(a[-10:], b[-10:], rtol=1e-10)
+
+
+def test_front_timeline_is_consistent(tmp_path):
+    """SLAM_B200_TIMELINE: every front of the last iteration carries ordered stamps (entry <= wait passed <= ... <= end),
+    a parent's dependency wait ends after the end of each of its children, and the fused roots have no backward stamps."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, ctypes as C, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import load_pkg\n"
+        "pkg = load_pkg(); ctx = pkg.Context(0); ctx.graph_load(pkg.synth.graph_from_drive(pkg.synth.trackdrive(1)))\n"
+        "ctx.graph_prepare(); ctx.graph_iterate_async(3); ctx.sync(); L = ctx.L\n"
+        "L.slam_b200_debug_timeline.restype = C.c_long; L.slam_b200_debug_timeline.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_long]\n"
+        "n = L.slam_b200_debug_timeline(ctx.h, None, 0); assert n > 0 and n %% 12 == 0, n\n"
+        "buf = (C.c_longlong * n)(); assert L.slam_b200_debug_timeline(ctx.h, buf, n) == n\n"
+        "t = np.array(buf, dtype=np.int64).reshape(-1, 12)\n"
+        "L.slam_b200_graph_export_symbolic.restype = C.c_long\n"
+        "L.slam_b200_graph_export_symbolic.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_long]\n"
+        "m = L.slam_b200_graph_export_symbolic(ctx.h, 7, None, 0); par = np.zeros(m, dtype=np.int32)\n"
+        "L.slam_b200_graph_export_symbolic(ctx.h, 7, par.ctypes.data_as(C.POINTER(C.c_int32)), m)\n"
+        "assert len(par) == len(t)\n"
+        "assert np.all(t[:, 0] > 0) and np.all(np.diff(t[:, :6], axis=1) >= 0)\n"
+        "for f, p in enumerate(par):\n"
+        "    if p >= 0: assert t[p, 1] >= t[f, 5], (f, p)\n"
+        "    else: assert t[f, 6] == 0 and t[f, 8] == 0, f\n"
+        "    if p >= 0: assert 0 < t[f, 6] <= t[f, 7] <= t[f, 8] and t[f, 7] >= max(t[p, 5], t[p, 8]), f\n"
+        "print('ok')\n"
+    ) % (os.path.dirname(__file__), os.path.dirname(os.path.dirname(__file__)))
+    env = dict(os.environ, SLAM_B200_TIMELINE="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
 def test_register_resident_large_front_kernel_agrees(ctx, orc, synth):
     """SLAM_B200_FACTOR_VARIANT=3: the large fronts (more than 64 rows) of a single graph by factor3_kernel -- the tile
     triangle in the registers of 16 warps, DMMA updates (csrc/factor3.cuh; measured no faster than factor2_kernel and
