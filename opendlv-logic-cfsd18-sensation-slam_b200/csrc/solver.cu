@@ -2188,7 +2188,11 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     }
     if (LL.n_small && merge_classes(LL)) {
       dim3 grid(LL.n_tiny + LL.n_small, D.R);
-      SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(FACTOR_THREADS), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
+      // 512 threads x 128 registers are a whole register file: one CTA per SM.  A mixed level with more fronts than SMs
+      // runs 256-thread CTAs (two per SM) instead of two waves of 512-thread ones.
+      static const int wide_threads = getenv("SLAM_B200_MERGE_THREADS") ? atoi(getenv("SLAM_B200_MERGE_THREADS")) : 256;
+      const int threads = (LL.n_tiny + LL.n_small > c->num_sms) ? wide_threads : FACTOR_THREADS;
+      SLAM_CUDA_TRY(c, launch_front(factor2_kernel<true>, grid, dim3(threads), LL.smem_factor + factor_extra_smem(LL.max_fs), c->stream,
           S, LL.list_off, D.V.p, D.nV, D.Lv.p, D.nL, D.Uv.p, D.nU, D.Fbig.p, D.nFbig, D.status.p, D.uvec.p,
           D.nUvec, D.x.p, D.n, la_idle, early_v | 2 | mma_flag | root_flag));
       early_v = 1;
