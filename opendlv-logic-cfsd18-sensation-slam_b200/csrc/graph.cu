@@ -16,7 +16,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <exception>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 
@@ -1312,6 +1315,15 @@ int graph_build_structure(slam_b200_ctx* c) {
   if (const char* s = getenv("SLAM_B200_ND_LEAF")) leaf = std::max(1, atoi(s));
   std::thread sym_thread;
   std::exception_ptr sym_error;
+  // the analysis signals when the tree and the fronts are final; its last stage (the assembly entries) then runs
+  // beside the launch lists built below from them
+  std::mutex sym_m;
+  std::condition_variable sym_cv;
+  bool sym_ready = false, sym_structure_ok = false;
+  const std::function<void(bool)> sym_structure_ready = [&](bool ok) {
+    { std::lock_guard<std::mutex> lk(sym_m); sym_ready = true; sym_structure_ok = ok; }
+    sym_cv.notify_all();
+  };
   struct JoinGuard {  // an early return below must not leave the helper running on locals of this frame
     std::thread& t;
     ~JoinGuard() { if (t.joinable()) t.join(); }
@@ -1329,7 +1341,7 @@ int graph_build_structure(slam_b200_ctx* c) {
       try {
         nvtxRangePushA("slam_b200/symbolic analysis");
         symbolic_analyze(nb, dim.data(), (int)D.off_a.size(), D.off_a.data(), D.off_b.data(), D.hoff_diag.data(),
-                         D.hoff_off.data(), leaf, D.sym);
+                         D.hoff_off.data(), leaf, D.sym, 0, &sym_structure_ready);
         nvtxRangePop();
       } catch (...) {
         sym_error = std::current_exception();
@@ -1408,8 +1420,15 @@ int graph_build_structure(slam_b200_ctx* c) {
   }
   dbg("assembly upload (overlapped)");
   const double t_overlapped = std::chrono::duration<double>(std::chrono::steady_clock::now() - tov0).count();
-  if (sym_thread.joinable()) sym_thread.join();
-  if (sym_error) std::rethrow_exception(sym_error);
+  if (sym_thread.joinable()) {
+    std::unique_lock<std::mutex> lk(sym_m);
+    sym_cv.wait(lk, [&] { return sym_ready; });  // fired on success and on the way out of an exception alike
+  }
+  auto sym_join = [&]() {  // the analysis has finished altogether (assembly entries, timing); rethrows its exception
+    if (sym_thread.joinable()) sym_thread.join();
+    if (sym_error) std::rethrow_exception(sym_error);
+  };
+  if (!sym_structure_ok) sym_join();  // no helper thread (inline / assembly only) or the analysis failed early
   dbg("wait for the symbolic analysis");
   phase.next("slam_b200/launch lists");
   Symbolic& S = D.sym;
@@ -1509,6 +1528,7 @@ int graph_build_structure(slam_b200_ctx* c) {
       for (int k = 0; k < 3; k++) solver2v[so + k] = 6 * L + 3 * p + k;
     }
   }
+  sym_join();  // the assembly entries (tile plan, upload) and the analysis' own clock are needed from here on
   // ---- tiled path for replica batches (tileplan.h) ----
   D.tile_path = false;
   D.tile = TilePlan();

@@ -640,7 +640,13 @@ static std::vector<int> constrained_min_degree(int nb, const int* dim, const std
 }
 
 void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const int* off_b,
-                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S, int amalgamate) {
+                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S, int amalgamate,
+                      const std::function<void(bool)>* structure_ready) {
+  struct ReadyOnce {  // signals the caller exactly once, also on the way out of an exception
+    const std::function<void(bool)>* fn;
+    void fire(bool ok) { if (fn) { const std::function<void(bool)>* f = fn; fn = nullptr; (*f)(ok); } }
+    ~ReadyOnce() { fire(false); }
+  } ready{structure_ready};
   auto t0 = std::chrono::steady_clock::now();
   S = Symbolic();
   S.nb = nb;
@@ -1166,6 +1172,7 @@ void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const i
     S.max_front = std::max<int>(S.max_front, (int)fs);
   }
   dbg("offsets/stats");
+  ready.fire(true);  // tree, fronts, row maps and storage offsets are final: the caller's launch lists may start
   // ---- assembly entries: every H block lands in the front of its earlier-eliminated vertex ----
   // counting sort by front (diagonal blocks first, then the off-diagonal blocks in input order); the
   // row of the later vertex inside the front is looked up in a per-front scratch map

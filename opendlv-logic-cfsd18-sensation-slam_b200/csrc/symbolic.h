@@ -7,6 +7,7 @@
 // the dense fronts the numeric kernels factorise.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 struct AsmEntry {   // one H block landing in a front's pivot columns
@@ -52,5 +53,10 @@ struct Symbolic {
 // Off by default: measured on B200 it shortens the assembly tree (10-lap graph 10 -> 8 levels, 1-lap
 // graph 10 -> 5) but the GN iteration gets slower (507 -> 547 us, 315 -> 332 us): a panel of 8 pivots
 // costs more than the fixed cost of a front, so fewer, larger fronts lose.  SLAM_B200_AMALG enables it.
+// structure_ready (optional): called once, from the analysing thread, with true when everything but asm_ptr /
+// asm_entries / seconds is final -- the caller may build what depends on the tree and the fronts (launch lists,
+// gather lists) on another thread while the assembly entries are still being computed -- or with false on the way
+// out of an exception thrown before that point.
 void symbolic_analyze(int nb, const int* dim, int nnb, const int* off_a, const int* off_b,
-                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S, int amalgamate = 0);
+                      const int* hoff_diag, const int* hoff_off, int leaf_size, Symbolic& S, int amalgamate = 0,
+                      const std::function<void(bool)>* structure_ready = nullptr);
