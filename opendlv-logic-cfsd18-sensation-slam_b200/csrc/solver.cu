@@ -564,7 +564,35 @@ factor2_kernel(SymArgs S, int list_off, const double* __restrict__ V_all, long n
     }
   };
   auto one_batch = [&](int uc) { return staged && uc <= nw * ECB && uc <= 32 * ERC; };
-  {
+  bool all_one = staged;  // every child fits one batch (the rule on SLAM graphs)
+  for (int ci = c_first; all_one && ci < c_end; ci++) all_one = one_batch(S.nupd[S.children[ci]]);
+  if (all_one && !(flags & 16)) {
+    // Two alternating batches: child k is added from one while child k + 1 waits in the other, and the entries of
+    // child k + 2 are requested as soon as the batch of child k is free -- nothing waits for a request inside the
+    // step that issued it (the single-buffer loop below copied the prefetched batch over after the barrier and so
+    // exposed one L2 round trip, ~1 us across the dies, per child: 18 us on the fronts that gather ten children).
+    const int nch = c_end - c_first;
+    auto child_U = [&](int k) { return Uv + S.uptr[S.children[c_first + k]]; };
+    auto child_uc = [&](int k) { return S.nupd[S.children[c_first + k]]; };
+    double va[ECB][ERC], vb[ECB][ERC];
+    if (nch > 0) load_batch(va, child_U(0), child_uc(0), warp, 0);
+    if (nch > 1) load_batch(vb, child_U(1), child_uc(1), warp, 0);
+    int roff = 0;
+    for (int k = 0; k < nch; k += 2) {
+      const int uca = child_uc(k);
+      add_batch(va, srel + roff, uca, warp, 0);
+      __syncthreads();
+      roff += uca;
+      if (k + 2 < nch) load_batch(va, child_U(k + 2), child_uc(k + 2), warp, 0);
+      if (k + 1 < nch) {
+        const int ucb = child_uc(k + 1);
+        add_batch(vb, srel + roff, ucb, warp, 0);
+        __syncthreads();
+        roff += ucb;
+        if (k + 3 < nch) load_batch(vb, child_U(k + 3), child_uc(k + 3), warp, 0);
+      }
+    }
+  } else {
     int roff = 0;
     bool have = false;  // va holds the current child already
     double va[ECB][ERC];
@@ -2135,7 +2163,8 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
   static const bool gen3 = getenv("SLAM_B200_FACTOR_VARIANT") && atoi(getenv("SLAM_B200_FACTOR_VARIANT")) == 3;
   static const int la_idle = getenv("SLAM_B200_LA_IDLE") ? atoi(getenv("SLAM_B200_LA_IDLE")) : 0;
   static const bool merge_ok = getenv("SLAM_B200_NO_LEVEL_MERGE") == nullptr;
-  static const int mma_flag = (getenv("SLAM_B200_UPDATE_MMA") ? atoi(getenv("SLAM_B200_UPDATE_MMA")) : 1) ? 4 : 0;
+  static const int mma_flag = ((getenv("SLAM_B200_UPDATE_MMA") ? atoi(getenv("SLAM_B200_UPDATE_MMA")) : 1) ? 4 : 0) |
+                              (getenv("SLAM_B200_EA_SINGLE") ? 16 : 0);  // 16: single-buffer extend-add (A/B)
   // programmatic dependent launch: 0 until a launch of this enqueue has gone out whose wait proves that the assembly
   // kernels (V) / the factor kernels (L) are complete -- see pdl_wait_then_release
   int early_v = 0, early_l = 0;
