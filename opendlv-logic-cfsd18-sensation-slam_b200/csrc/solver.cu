@@ -1247,14 +1247,23 @@ backward_tiny_kernel(SymArgs S, int list_off, int count, const double* __restric
   double x0 = 0.0, x1 = 0.0;
   if (i0 < fs) x0 = __ldcg(i0 < s ? x + p0 + i0 : x + r0);
   if (i1 < fs) x1 = __ldcg(i1 < s ? x + p0 + i1 : x + r1);
-  for (int kb = ((s - 1) / 4) * 4; kb >= 0; kb -= 4) {
-    double l0[4], l1[4];
+  // The four columns of step kb - 4 are requested before the columns of step kb are used: L comes from L2 (written by
+  // the factor kernels, often on the other die) and a front of 40 pivots would otherwise pay ten round trips in a row.
+  auto load_cols = [&](int kb, double (&l0)[4], double (&l1)[4]) {
 #pragma unroll
     for (int p = 0; p < 4; p++) {
       const int k = kb + p;
-      l0[p] = (k < s && i0 > k && i0 < fs) ? Lg[(size_t)k * fs + i0] : 0.0;
-      l1[p] = (k < s && i1 > k && i1 < fs) ? Lg[(size_t)k * fs + i1] : 0.0;
+      l0[p] = (kb >= 0 && k < s && i0 > k && i0 < fs) ? Lg[(size_t)k * fs + i0] : 0.0;
+      l1[p] = (kb >= 0 && k < s && i1 > k && i1 < fs) ? Lg[(size_t)k * fs + i1] : 0.0;
     }
+  };
+  double n0[4], n1[4];
+  load_cols(((s - 1) / 4) * 4, n0, n1);
+  for (int kb = ((s - 1) / 4) * 4; kb >= 0; kb -= 4) {
+    double l0[4], l1[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) { l0[p] = n0[p]; l1[p] = n1[p]; }
+    load_cols(kb - 4, n0, n1);
 #pragma unroll
     for (int p = 3; p >= 0; p--) {
       const int k = kb + p;
