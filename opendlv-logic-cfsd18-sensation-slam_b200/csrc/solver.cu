@@ -1687,7 +1687,8 @@ constexpr int BACK_SLAB = TILE_MAX_ROWS + 8 + 64;  // x of the front's rows + th
 // tile buffers, 24 instead of 20 resident warps per SM)
 template <int TMAXT>
 __global__ void __launch_bounds__(128, TMAXT <= 8 ? 6 : 5)
-backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__ F_all, long nF, double* x_all, int n) {
+backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__ F_all, long nF, double* x_all, int n,
+                     int early) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int r = blockIdx.x * (blockDim.x >> 5) + wid;
@@ -1702,6 +1703,10 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
   const double* Fg = F_all + (size_t)r * nF + A.fptr[f];
   const int g = lane >> 2, t = lane & 3;
   const int cl = g * 8 + ((2 * t) ^ ((g & 2) << 1));  // this lane's two entries of a tile (accumulator layout, tileplan.h)
+  // Programmatic dependent launch (pdl_wait_then_release): the levels of the backward sweep are one launch each on one
+  // stream; with early set (every launch but the first, whose predecessor is the root's factor launch) the index chain
+  // and the first tiles of L -- written by the factor launches, long complete -- are fetched under the previous level.
+  if (!early) pdl_wait_then_release();
   // the last pivot column's tiles do not depend on x: request them before the gather of x
   double2 lv[TMAXT - 1], dg;
   {
@@ -1711,10 +1716,11 @@ backward_tile_kernel(TileArgs A, int list_off, int R, const double* __restrict__
     for (int d = 0; d < TMAXT - 1; d++)
       if (K + 1 + d < T) lv[d] = *reinterpret_cast<const double2*>(Fg + tile_base(K + 1 + d, K) + cl);
   }
+  if (early) pdl_wait_then_release();  // the parents' x comes from the previous launch
   for (int i = lane; i < (T << 3); i += 32) {
     double v = 0.0;  // padding pivots, the rhs row and the rows behind it contribute nothing
-    if (i < s) v = x[p0 + i];
-    else if (i >= sp && i < sp + u) v = x[rows[i - sp]];
+    if (i < s) v = __ldcg(x + p0 + i);
+    else if (i >= sp && i < sp + u) v = __ldcg(x + rows[i - sp]);
     xs[i] = v;
   }
   __syncwarp();
@@ -2163,6 +2169,7 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
     }
     mark();  // factored
     mark();  // forward (fused)
+    int tile_early_l = 0;  // programmatic dependent launch along the backward sweep (backward_tile_kernel)
     for (int k1 = nTL; k1 > 0;) {  // root -> leaves, one launch per level (no dynamic shared memory: no classes)
       int k = k1 - 1;
       while (k > 0 && D.tile_launches[k - 1].level == D.tile_launches[k1 - 1].level) k--;
@@ -2171,11 +2178,12 @@ int graph_enqueue_solve(slam_b200_ctx* c) {
       for (int o = 0; o < count; o += 65535) {
         dim3 grid((D.R + wpc_b - 1) / wpc_b, std::min(65535, count - o));
         if (D.tile.max_T <= 8)
-          backward_tile_kernel<8><<<grid, 32 * wpc_b, (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream>>>(
-              TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n);
+          SLAM_CUDA_TRY(c, launch_front(backward_tile_kernel<8>, grid, dim3(32 * wpc_b), (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream,
+              TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n, tile_early_l));
         else
-          backward_tile_kernel<TILE_MAX_T><<<grid, 32 * wpc_b, (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream>>>(
-              TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n);
+          SLAM_CUDA_TRY(c, launch_front(backward_tile_kernel<TILE_MAX_T>, grid, dim3(32 * wpc_b), (size_t)wpc_b * BACK_SLAB * sizeof(double), c->stream,
+              TA, D.tile_launches[k].list_off + o, D.R, D.Lv.p, D.nL, D.x.p, D.n, tile_early_l));
+        tile_early_l = 1;
         c->launches++;
       }
       k1 = k;
